@@ -1,0 +1,209 @@
+/* smallpebble_b200 -- C ABI of the B200 (sm_100a) hot path of SmallPebble.
+ *
+ * The reference (sradc/SmallPebble, smallpebble/smallpebble.py = "sp.py") has no FFI:
+ * its hot path is a set of Python ops whose arithmetic is NumPy calls.  This header is
+ * the boundary inserted exactly where sp.py calls NumPy: every entry point replaces
+ * the NumPy call sites of one reference op (cited per function).  A maintainer binds it
+ * with ctypes; the in-tree binding is smallpebble_b200/_abi.py.
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer unless the name says `host`;
+ *   - activations are NHWC float32, kernels HWIO float32 (same layouts as sp.py:133-134);
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it;
+ *   - every function returns 0 on success, otherwise a cudaError_t (>0) or an
+ *     SP_ERR_* code (<0); sp_last_error() returns a thread-local description;
+ *   - no exceptions, no torch types, no global state besides a per-device info cache.
+ */
+#ifndef SMALLPEBBLE_B200_H
+#define SMALLPEBBLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP_ABI_VERSION 1
+
+#define SP_ERR_INVALID_ARGUMENT (-1)
+#define SP_ERR_UNSUPPORTED (-2)
+#define SP_ERR_WORKSPACE (-3)
+#define SP_ERR_DRIVER (-4)
+
+/* math mode of the contraction kernels */
+#define SP_PRECISION_FP32 0 /* CUDA-core FFMA, fp32 accumulate: rel err ~1e-6 vs float64 */
+#define SP_PRECISION_TF32 1 /* tcgen05.mma kind::tf32, TMEM fp32 accumulate: ~1e-3       */
+
+/* unary ops (sp.py:196-200 exp, 224-228 log, 314-318 neg, 367-375 square) */
+#define SP_UNARY_EXP 0
+#define SP_UNARY_LOG 1
+#define SP_UNARY_NEG 2
+#define SP_UNARY_SQUARE 3
+#define SP_UNARY_SCALE 4      /* y = param * x                                   */
+#define SP_UNARY_ADD_SCALAR 5 /* y = x + param                                   */
+#define SP_UNARY_RECIP 6      /* y = param / x                                   */
+#define SP_UNARY_SQRT 7
+#define SP_UNARY_COPY 8
+#define SP_UNARY_ISNAN_ANY 9 /* reserved */
+
+/* binary broadcasting ops (sp.py:100-108 add, 393-401 sub, 303-311 mul, 166-174 div) */
+#define SP_BINARY_ADD 0
+#define SP_BINARY_SUB 1
+#define SP_BINARY_MUL 2
+#define SP_BINARY_DIV 3
+#define SP_BINARY_DIV_GRAD_B 4 /* out = -a / (b*b): second factor of sp.py:172       */
+#define SP_BINARY_EXP_MUL 5    /* out = a * exp(b): sp.py:199                        */
+
+#define SP_MAX_DIMS 8
+
+typedef void* sp_stream_t;
+
+/* ---- library ---------------------------------------------------------------------- */
+int sp_abi_version(void);
+const char* sp_last_error(void);
+/* sm_count, compute capability of the current device */
+int sp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* test hook: 0 = default policy, 1 = always use the tcgen05 kernel in TF32 mode when the
+ * shape is supported, 2 = never use it (CUDA-core kernel even in TF32 mode) */
+int sp_debug_set_umma_policy(int policy);
+
+/* ---- memory helpers (replace NumPy array construction / copies) -------------------- */
+int sp_memcpy_h2d(void* dst, const void* host_src, size_t bytes, sp_stream_t stream);
+/* copies and waits for the stream: the only blocking call of the ABI (sp.py users read
+ * `.array`, e.g. np.isnan(loss_val.array), README.md:156) */
+int sp_memcpy_d2h(void* host_dst, const void* src, size_t bytes, sp_stream_t stream);
+int sp_memcpy_d2d(void* dst, const void* src, size_t bytes, sp_stream_t stream);
+int sp_fill_f32(float* dst, int64_t n, float value, sp_stream_t stream);
+/* float64 host data uploaded raw then narrowed on device (np.float64 -> device fp32) */
+int sp_cast_f64_f32(const double* src, float* dst, int64_t n, sp_stream_t stream);
+int sp_cast_i64_i32(const int64_t* src, int32_t* dst, int64_t n, sp_stream_t stream);
+/* write `bytes` of scratch (> L2 size) so the next kernel starts from a cold L2 */
+int sp_l2_flush(void* scratch, size_t bytes, sp_stream_t stream);
+
+/* ---- elementwise (sp.py:100-108, 166-174, 196-200, 224-236, 303-318, 367-401, 418-441) */
+int sp_ewise_unary(int op, const float* x, float* y, int64_t n, float param,
+                   sp_stream_t stream);
+/* out[shape] = a (broadcast by stride 0) OP b; strides in elements, ndim <= SP_MAX_DIMS */
+int sp_ewise_binary(int op, const float* a, const int64_t* stride_a, const float* b,
+                    const int64_t* stride_b, float* out, int ndim, const int64_t* shape,
+                    sp_stream_t stream);
+/* in-place accumulate used by the tape (sp.py:82 `gradients[child] += value`) */
+int sp_accumulate(float* dst, const float* src, int64_t n, sp_stream_t stream);
+/* leaky_relu (sp.py:231-236): y = x > 0 ? x : alpha*x ;  dx = g * (x > 0 ? 1 : alpha) */
+int sp_leaky_relu_fwd(const float* x, float* y, int64_t n, float alpha, sp_stream_t stream);
+int sp_leaky_relu_bwd(const float* g, const float* x, float* dx, int64_t n, float alpha,
+                      sp_stream_t stream);
+/* where (sp.py:418-441): out = cond ? a : b, all three broadcast by strides */
+int sp_where(const uint8_t* cond, const int64_t* stride_c, const float* a,
+             const int64_t* stride_a, const float* b, const int64_t* stride_b, float* out,
+             int ndim, const int64_t* shape, sp_stream_t stream);
+/* generic strided copy: pad / un-pad (sp.py:321-330), swapaxes (250-254), basic slices */
+int sp_strided_copy(const float* src, const int64_t* stride_src, float* dst,
+                    const int64_t* stride_dst, int ndim, const int64_t* shape,
+                    sp_stream_t stream);
+
+/* ---- reductions (sp.py:404-415 sum; 183-189 unbroadcast-sum) ------------------------ */
+/* x viewed as [outer, reduce, inner] -> out[outer, inner] */
+int sp_reduce_sum(const float* x, float* out, int64_t outer, int64_t reduce, int64_t inner,
+                  sp_stream_t stream);
+/* out[0] = max over all n elements (softmax's global shift, sp.py:359) */
+int sp_reduce_max_all(const float* x, float* out, int64_t n, sp_stream_t stream);
+
+/* maxax on the last axis (sp.py:257-279): y[r] = max_j x[r, j], idx[r] = first argmax
+ * (NaN wins, like np.argmax); bwd: dx[r, j] = (j == idx[r]) ? g[r] : 0 */
+int sp_argmax_rows_fwd(const float* x, float* y, int32_t* idx, int64_t rows, int64_t n,
+                       sp_stream_t stream);
+int sp_argmax_rows_bwd(const float* g, const int32_t* idx, float* dx, int64_t rows, int64_t n,
+                       sp_stream_t stream);
+
+/* ---- gather / scatter on flat int64 indices (sp.py:111-121, 210-221, 340-354, 378-390) */
+int sp_gather_i64(const float* src, const int64_t* idx, float* out, int64_t n,
+                  sp_stream_t stream);
+int sp_scatter_add_i64(float* dst, const int64_t* idx, const float* src, int64_t n,
+                       sp_stream_t stream);
+int sp_scatter_set_i64(float* dst, const int64_t* idx, const float* src, int64_t n,
+                       int64_t src_is_scalar, sp_stream_t stream);
+
+/* ---- softmax / cross entropy (sp.py:357-364, 612-621) ------------------------------- */
+/* x viewed as [outer, n, inner]; softmax over the middle axis */
+int sp_softmax_fwd(const float* x, float* y, int64_t outer, int64_t n, int64_t inner,
+                   sp_stream_t stream);
+/* dx = y * (g - sum_n(g*y)) */
+int sp_softmax_bwd(const float* y, const float* g, float* dx, int64_t outer, int64_t n,
+                   int64_t inner, sp_stream_t stream);
+/* loss[0] = -sum_b log(probs[b, labels[b]])   (sum reduction, sp.py:621) */
+int sp_xent_fwd(const float* probs, const int32_t* labels, float* loss, int64_t rows,
+                int64_t cols, sp_stream_t stream);
+/* dprobs[b, c] = c == labels[b] ? -gloss[0] / probs[b, c] : 0 */
+int sp_xent_bwd(const float* probs, const int32_t* labels, const float* gloss,
+                float* dprobs, int64_t rows, int64_t cols, sp_stream_t stream);
+/* fused: probs = softmax(logits) row-wise, loss[0] = -sum_b log probs[b, labels[b]]
+ * computed as logsumexp - logit (never takes log of an underflowed probability) */
+int sp_softmax_xent_fwd(const float* logits, const int32_t* labels, float* probs,
+                        float* loss, int64_t rows, int64_t cols, sp_stream_t stream);
+/* dlogits = gloss[0] * (probs - onehot(labels)) */
+int sp_softmax_xent_bwd(const float* probs, const int32_t* labels, const float* gloss,
+                        float* dlogits, int64_t rows, int64_t cols, sp_stream_t stream);
+
+/* ---- maxpool2d (sp.py:282-300 + maxax 257-279) ------------------------------------- */
+/* x [N,H,W,C] -> y [N,OH,OW,C], idx[N,OH,OW,C] = dy*KW+dx of the FIRST maximum of the
+ * zero-padded window (padding value 0 competes, NaN wins like np.argmax). */
+int sp_maxpool2d_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C,
+                     int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
+                     sp_stream_t stream);
+/* dx[N,H,W,C] = sum over windows whose argmax is this pixel of gy (gather form, no atomics) */
+int sp_maxpool2d_bwd(const float* gy, const uint8_t* idx, float* dx, int N, int H, int W,
+                     int C, int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH,
+                     int OW, sp_stream_t stream);
+
+/* ---- matmul (sp.py:239-247): C[b] = op(A[b]) * op(B[b]), row-major, strided batch ---- */
+/* transX = 0: X stored [rows, cols] with leading dimension ldx; 1: stored transposed.
+ * A batch stride of 0 broadcasts the operand (sp.py:177-193 matmul=True). */
+int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
+            int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB,
+            float* C, int64_t ldc, int64_t strideC, int64_t batch, int precision,
+            sp_stream_t stream);
+
+/* ---- conv2d (sp.py:124-163 and the closures it composes: 244-245, 384-387, 325-327) -- */
+typedef struct sp_conv_geom {
+  int32_t N, H, W, C;        /* images  [N,H,W,C]                        */
+  int32_t KH, KW, K;         /* kernels [KH,KW,C,K]                      */
+  int32_t sy, sx;            /* strides                                  */
+  int32_t pad_t, pad_l;      /* TF-SAME front padding (sp.py:721-730)    */
+  int32_t OH, OW;            /* output  [N,OH,OW,K]                      */
+} sp_conv_geom;
+
+/* y = im2col(x) * w           (implicit GEMM M=N*OH*OW, N=K, K=KH*KW*C)  */
+int sp_conv2d_fprop(const float* x, const float* w, float* y, const sp_conv_geom* g,
+                    int precision, sp_stream_t stream);
+/* dx = col2im(gy * w^T) in gather form (replaces np.add.at, sp.py:384-387) */
+int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_geom* g,
+                    int precision, sp_stream_t stream);
+/* dw = im2col(x)^T * gy, split over the N*OH*OW reduction; workspace from
+ * sp_conv2d_wgrad_workspace() (may be 0 bytes) */
+size_t sp_conv2d_wgrad_workspace(const sp_conv_geom* g, int precision);
+int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_geom* g,
+                    int precision, void* workspace, size_t workspace_bytes,
+                    sp_stream_t stream);
+
+/* ---- optimisers (sp.py:552-583 Adam, 645-653 SGD), multi-tensor ---------------------- */
+/* All pointer tables are HOST arrays of device pointers (passed by value to the kernel).
+ * For tensor i with step count t[i] (already incremented):
+ *   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ;
+ *   p -= alpha * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)        */
+int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_g,
+                  float* const* host_m, float* const* host_v, const int64_t* host_numel,
+                  const int32_t* host_t, float alpha, float beta1, float beta2, float eps,
+                  sp_stream_t stream);
+int sp_sgd_multi(int n_tensors, float* const* host_p, const float* const* host_g,
+                 const int64_t* host_numel, float lr, sp_stream_t stream);
+/* gather many gradient tensors into one flat bucket (the data-parallel all-reduce payload):
+ * bucket[host_offsets[i] + j] = src[i][j]; host_offsets == NULL packs them back to back */
+int sp_pack_multi(int n_tensors, const float* const* host_src, const int64_t* host_numel,
+                  const int64_t* host_offsets, float* bucket, sp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMALLPEBBLE_B200_H */

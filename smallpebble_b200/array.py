@@ -1,0 +1,554 @@
+"""DeviceArray: the thing `Variable.array` holds instead of a NumPy ndarray.
+
+A thin, always-contiguous fp32 (or int/uint8 for indices) device buffer.  PyTorch is used
+for exactly two things here: its caching allocator (`torch.empty`) and the current CUDA
+stream handle.  Every arithmetic method launches a hand-written kernel through the C ABI
+(`_abi.f.*`); nothing is computed by torch and nothing falls back to the CPU.
+
+Host data handed to `Variable(np_array)` is uploaded lazily, on first device use, so that
+graph construction (`sp.linearlayer`, `sp.Placeholder`, `sp.get_learnables`, ...) works on a
+machine without a GPU; touching `.ptr` without CUDA raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import math
+import numbers
+
+import numpy as np
+
+from . import _abi
+
+F = _abi.f
+FLOAT = np.dtype(np.float32)
+_DEVICE_DTYPES = {np.dtype(np.float32), np.dtype(np.int32), np.dtype(np.int64), np.dtype(np.uint8)}
+
+_torch = None
+_device = None
+
+
+def _lazy_torch():
+    global _torch
+    if _torch is None:
+        import torch
+
+        _torch = torch
+    return _torch
+
+
+def require_cuda():
+    """The product path has no CPU fallback: fail loudly when there is no GPU/extension."""
+    global _device
+    if _device is not None:
+        return _device
+    torch = _lazy_torch()
+    if not torch.cuda.is_available():
+        raise _abi.SmallPebbleCudaError(
+            "smallpebble_b200 needs a CUDA device (B200, sm_100a): torch.cuda.is_available() is "
+            "False. There is no CPU fallback."
+        )
+    _abi.load()
+    torch.cuda.init()
+    _device = torch.device("cuda", torch.cuda.current_device())
+    # bind our statically linked CUDA runtime to torch's context on this device
+    torch.empty(1, device=_device)
+    return _device
+
+
+def reset_device_cache():
+    """Call after torch.cuda.set_device() (one process per GPU: smallpebble_b200.distributed)."""
+    global _device
+    _device = None
+
+
+def stream() -> int:
+    return _lazy_torch().cuda.current_stream().cuda_stream
+
+
+def _host_dtype(a: np.ndarray) -> np.dtype:
+    """Device dtype for a host array: all real data is fp32; bools -> uint8; ints stay ints
+    only when explicitly requested (labels / indices go through `from_host(..., dtype)`)."""
+    if a.dtype == np.bool_:
+        return np.dtype(np.uint8)
+    return FLOAT
+
+
+class DeviceArray:
+    __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "__weakref__")
+    __array_priority__ = 1000.0
+
+    def __init__(self, shape, dtype=FLOAT, buf=None, ptr=None, host=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.size = math.prod(self.shape)
+        self._buf = buf
+        self._ptr = ptr
+        self._host = host
+
+    # ---- construction ---------------------------------------------------------------------
+    @staticmethod
+    def empty(shape, dtype=FLOAT) -> "DeviceArray":
+        dev = require_cuda()
+        dtype = np.dtype(dtype)
+        shape = tuple(int(s) for s in shape)
+        nbytes = max(math.prod(shape), 1) * dtype.itemsize
+        buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
+        return DeviceArray(shape, dtype, buf, buf.data_ptr())
+
+    @staticmethod
+    def from_host(a, dtype=None) -> "DeviceArray":
+        """Wrap host data; the copy to the device happens on first use."""
+        a = np.asarray(a)
+        dtype = np.dtype(dtype) if dtype is not None else _host_dtype(a)
+        if dtype not in _DEVICE_DTYPES:
+            raise TypeError(f"unsupported device dtype {dtype}")
+        host = np.ascontiguousarray(a, dtype=dtype)
+        if host is a or np.may_share_memory(host, a):
+            host = host.copy()  # the caller may mutate its array after Variable(...)
+        return DeviceArray(host.shape, dtype, host=host)
+
+    @staticmethod
+    def full(shape, value, dtype=FLOAT) -> "DeviceArray":
+        out = DeviceArray.empty(shape, dtype)
+        if out.dtype != FLOAT:
+            raise TypeError("full() supports float32 only")
+        F.sp_fill_f32(out._ptr, out.size, float(value), stream())
+        return out
+
+    @staticmethod
+    def zeros(shape, dtype=FLOAT) -> "DeviceArray":
+        return DeviceArray.full(shape, 0.0, dtype)
+
+    # ---- device pointer (uploads pending host data) ---------------------------------------
+    @property
+    def ptr(self) -> int:
+        if self._ptr is None:
+            self._upload()
+        return self._ptr
+
+    def _upload(self):
+        dev = require_cuda()
+        host = self._host
+        nbytes = max(host.size, 1) * host.dtype.itemsize
+        buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
+        if host.size:
+            # pageable memcpy: the runtime stages it, `host` may be released on return
+            F.sp_memcpy_h2d(buf.data_ptr(), host.ctypes.data, host.nbytes, stream())
+            _counters["h2d_bytes"] += host.nbytes
+        self._buf, self._ptr, self._host = buf, buf.data_ptr(), None
+
+    @property
+    def on_device(self) -> bool:
+        return self._ptr is not None
+
+    # ---- NumPy interop -------------------------------------------------------------------
+    def numpy(self) -> np.ndarray:
+        """Device -> host copy (synchronises the stream)."""
+        if self._ptr is None:
+            return self._host.copy()
+        out = np.empty(self.shape, self.dtype)
+        F.sp_memcpy_d2h(out.ctypes.data, self._ptr, out.nbytes, stream())
+        _counters["d2h_bytes"] += out.nbytes
+        return out
+
+    get = numpy
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method == "__call__" and not kwargs and ufunc in _UFUNC_TO_OP and len(inputs) == 2:
+            return _binary_any(_UFUNC_TO_OP[ufunc], inputs[0], inputs[1])
+        host = [np.asarray(x) if isinstance(x, DeviceArray) else x for x in inputs]
+        if "out" in kwargs:
+            return NotImplemented
+        return getattr(ufunc, method)(*host, **kwargs)
+
+    def item(self):
+        return self.numpy().item()
+
+    def __float__(self):
+        return float(self.numpy().reshape(-1)[0]) if self.size == 1 else float(self.numpy())
+
+    def __int__(self):
+        return int(float(self))
+
+    def __bool__(self):
+        if self.size != 1:
+            raise ValueError("The truth value of an array with more than one element is ambiguous.")
+        return bool(float(self))
+
+    def __len__(self):
+        if not self.shape:
+            raise TypeError("len() of unsized object")
+        return self.shape[0]
+
+    def __repr__(self):
+        where = "device" if self._ptr is not None else "host-pending"
+        return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, {where})"
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    @property
+    def nbytes(self) -> int:
+        return self.size * self.dtype.itemsize
+
+    # ---- views / copies --------------------------------------------------------------------
+    def reshape(self, *shape) -> "DeviceArray":
+        if len(shape) == 1 and not isinstance(shape[0], numbers.Integral):
+            shape = tuple(shape[0])
+        shape = _resolve_shape(shape, self.size)
+        if self._ptr is None:
+            return DeviceArray(shape, self.dtype, host=self._host.reshape(shape))
+        return DeviceArray(shape, self.dtype, self._buf, self._ptr)  # shares the buffer
+
+    def copy(self) -> "DeviceArray":
+        out = DeviceArray.empty(self.shape, self.dtype)
+        F.sp_memcpy_d2d(out._ptr, self.ptr, self.nbytes, stream())
+        return out
+
+    def astype(self, dtype, copy=True):
+        if np.dtype(dtype) == self.dtype:
+            return self.copy() if copy else self
+        return DeviceArray.from_host(self.numpy().astype(dtype), dtype=dtype)
+
+    def swapaxes(self, a, b) -> "DeviceArray":
+        return swapaxes(self, a, b)
+
+    @property
+    def T(self):
+        return transpose(self, tuple(reversed(range(self.ndim))))
+
+    def sum(self, axis=None, keepdims=False):
+        return reduce_sum(self, axis, keepdims)
+
+    def __getitem__(self, index):
+        return take(self, index)
+
+    # ---- arithmetic (all on device) ------------------------------------------------------
+    def __add__(self, o):
+        return _binary_any("add", self, o)
+
+    def __radd__(self, o):
+        return _binary_any("add", o, self)
+
+    def __sub__(self, o):
+        return _binary_any("sub", self, o)
+
+    def __rsub__(self, o):
+        return _binary_any("sub", o, self)
+
+    def __mul__(self, o):
+        return _binary_any("mul", self, o)
+
+    def __rmul__(self, o):
+        return _binary_any("mul", o, self)
+
+    def __truediv__(self, o):
+        return _binary_any("div", self, o)
+
+    def __rtruediv__(self, o):
+        return _binary_any("div", o, self)
+
+    def __neg__(self):
+        return unary("neg", self)
+
+    def __pow__(self, e):
+        if e == 2:
+            return unary("square", self)
+        if e == 1:
+            return self.copy()
+        if e == 0.5:
+            return unary("sqrt", self)
+        raise NotImplementedError("DeviceArray ** e supports e in {0.5, 1, 2}")
+
+    def _rebind(self, other: "DeviceArray"):
+        self._buf, self._ptr, self._host = other._buf, other.ptr, None
+        return self
+
+    def __iadd__(self, o):
+        return self._rebind(_binary_any("add", self, o))
+
+    def __isub__(self, o):
+        return self._rebind(_binary_any("sub", self, o))
+
+    def __imul__(self, o):
+        return self._rebind(_binary_any("mul", self, o))
+
+    def __itruediv__(self, o):
+        return self._rebind(_binary_any("div", self, o))
+
+
+_UFUNC_TO_OP = {np.add: "add", np.subtract: "sub", np.multiply: "mul", np.true_divide: "div"}
+_counters = {"h2d_bytes": 0, "d2h_bytes": 0}
+
+
+def transfer_counters():
+    return _counters
+
+
+def asarray(x) -> DeviceArray:
+    if isinstance(x, DeviceArray):
+        return x
+    return DeviceArray.from_host(x)
+
+
+def _resolve_shape(shape, size):
+    shape = [int(s) for s in shape]
+    if shape.count(-1) > 1:
+        raise ValueError("can only specify one unknown dimension")
+    if -1 in shape:
+        known = -math.prod(shape)
+        if known == 0 or size % known:
+            raise ValueError(f"cannot reshape array of size {size} into shape {tuple(shape)}")
+        shape[shape.index(-1)] = size // known
+    if math.prod(shape) != size:
+        raise ValueError(f"cannot reshape array of size {size} into shape {tuple(shape)}")
+    return tuple(shape)
+
+
+def _contig_strides(shape):
+    out, s = [], 1
+    for n in reversed(shape):
+        out.append(s)
+        s *= n
+    return tuple(reversed(out))
+
+
+@functools.lru_cache(maxsize=4096)
+def _broadcast_plan(shape_a, shape_b):
+    """(out_shape, ndim, c_shape, c_stride_a, c_stride_b) with stride 0 on broadcast axes."""
+    nd = max(len(shape_a), len(shape_b))
+    if nd > _abi.MAX_DIMS:
+        raise ValueError(f"arrays with more than {_abi.MAX_DIMS} dimensions are not supported")
+    ea = (1,) * (nd - len(shape_a)) + shape_a
+    eb = (1,) * (nd - len(shape_b)) + shape_b
+    out = []
+    for p, q in zip(ea, eb):
+        if p != q and p != 1 and q != 1:
+            raise ValueError(f"could not broadcast shapes {shape_a} {shape_b}")
+        out.append(max(p, q) if 0 not in (p, q) else 0)
+    sa = tuple(0 if n == 1 and o != 1 else s for n, o, s in zip(ea, out, _contig_strides(ea)))
+    sb = tuple(0 if n == 1 and o != 1 else s for n, o, s in zip(eb, out, _contig_strides(eb)))
+    return tuple(out), nd, _abi.dims(out), _abi.dims(sa), _abi.dims(sb)
+
+
+def unary(op: str, a: DeviceArray, param: float = 0.0) -> DeviceArray:
+    out = DeviceArray.empty(a.shape)
+    F.sp_ewise_unary(_abi.UNARY[op], a.ptr, out._ptr, a.size, param, stream())
+    return out
+
+
+def binary(op: str, a: DeviceArray, b: DeviceArray) -> DeviceArray:
+    """NumPy-broadcasting elementwise op between two device arrays."""
+    shape, nd, c_shape, c_sa, c_sb = _broadcast_plan(a.shape, b.shape)
+    out = DeviceArray.empty(shape)
+    F.sp_ewise_binary(_abi.BINARY[op], a.ptr, c_sa, b.ptr, c_sb, out._ptr, nd, c_shape, stream())
+    return out
+
+
+def _binary_any(op, a, b):
+    """Binary op where one side may be a Python scalar or host array."""
+    a_dev, b_dev = isinstance(a, DeviceArray), isinstance(b, DeviceArray)
+    if a_dev and isinstance(b, numbers.Real):
+        b = float(b)
+        if op == "add":
+            return unary("add_scalar", a, b)
+        if op == "sub":
+            return unary("add_scalar", a, -b)
+        if op == "mul":
+            return unary("scale", a, b)
+        if op == "div":
+            return unary("scale", a, 1.0 / b) if b != 0 else binary(op, a, asarray(np.float32(b)))
+    if b_dev and isinstance(a, numbers.Real):
+        a = float(a)
+        if op == "add":
+            return unary("add_scalar", b, a)
+        if op == "mul":
+            return unary("scale", b, a)
+        if op == "div":
+            return unary("recip", b, a)
+        if op == "sub":
+            return unary("add_scalar", unary("neg", b), a)
+    if not a_dev:
+        a = asarray(np.asarray(a))
+    if not b_dev:
+        b = asarray(np.asarray(b))
+    return binary(op, a, b)
+
+
+def accumulate_(dst: DeviceArray, src: DeviceArray) -> DeviceArray:
+    """dst += src in place (same shape)."""
+    F.sp_accumulate(dst.ptr, src.ptr, dst.size, stream())
+    return dst
+
+
+def _norm_axes(axis, ndim):
+    if axis is None:
+        return tuple(range(ndim))
+    if isinstance(axis, numbers.Integral):
+        axis = (axis,)
+    axes = sorted({int(ax) + ndim if ax < 0 else int(ax) for ax in axis})
+    for ax in axes:
+        if not 0 <= ax < ndim:
+            raise ValueError(f"axis {ax} is out of bounds for array of dimension {ndim}")
+    return tuple(axes)
+
+
+def reduce_sum(a: DeviceArray, axis=None, keepdims=False) -> DeviceArray:
+    """np.sum(a, axis): runs of adjacent reduced axes are folded one kernel at a time."""
+    axes = _norm_axes(axis, a.ndim)
+    shape = list(a.shape)
+    cur = a
+    # fold runs from the last axis backwards so earlier axis numbers stay valid
+    runs, i = [], len(axes) - 1
+    while i >= 0:
+        hi = lo = axes[i]
+        while i > 0 and axes[i - 1] == lo - 1:
+            i -= 1
+            lo = axes[i]
+        runs.append((lo, hi))
+        i -= 1
+    for lo, hi in runs:
+        outer = math.prod(shape[:lo])
+        red = math.prod(shape[lo:hi + 1])
+        inner = math.prod(shape[hi + 1:])
+        out = DeviceArray.empty((outer, inner))
+        if outer * inner:
+            F.sp_reduce_sum(cur.ptr, out._ptr, outer, red, inner, stream())
+        shape[lo:hi + 1] = [1] * (hi + 1 - lo)
+        cur = out
+    if keepdims:
+        final = tuple(shape)
+    else:
+        final = tuple(n for i, n in enumerate(shape) if i not in axes)
+    return cur.reshape(final) if axes else a.copy()
+
+
+def max_all(a: DeviceArray) -> DeviceArray:
+    out = DeviceArray.empty(())
+    F.sp_reduce_max_all(a.ptr, out._ptr, a.size, stream())
+    return out
+
+
+def strided_copy(src: DeviceArray, src_strides, src_offset, dst: DeviceArray, dst_strides,
+                 dst_offset, shape):
+    """dst[dst_offset + i.dst_strides] = src[src_offset + i.src_strides] over `shape`."""
+    if len(shape) > _abi.MAX_DIMS:
+        raise ValueError(f"arrays with more than {_abi.MAX_DIMS} dimensions are not supported")
+    if math.prod(shape) == 0:
+        return
+    F.sp_strided_copy(src.ptr + 4 * src_offset, _abi.dims(src_strides),
+                      dst.ptr + 4 * dst_offset, _abi.dims(dst_strides), len(shape),
+                      _abi.dims(shape), stream())
+
+
+def transpose(a: DeviceArray, perm) -> DeviceArray:
+    perm = tuple(perm)
+    shape = tuple(a.shape[p] for p in perm)
+    st = _contig_strides(a.shape)
+    out = DeviceArray.empty(shape)
+    strided_copy(a, tuple(st[p] for p in perm), 0, out, _contig_strides(shape), 0, shape)
+    return out
+
+
+def swapaxes(a: DeviceArray, i, j) -> DeviceArray:
+    perm = list(range(a.ndim))
+    perm[i], perm[j] = perm[j], perm[i]
+    return transpose(a, perm)
+
+
+def pad(a: DeviceArray, pad_width) -> DeviceArray:
+    """np.pad(a, pad_width) with zeros."""
+    pw = _norm_pad(pad_width, a.ndim)
+    shape = tuple(n + lo + hi for n, (lo, hi) in zip(a.shape, pw))
+    out = DeviceArray.zeros(shape)
+    ost = _contig_strides(shape)
+    offset = sum(lo * s for (lo, _), s in zip(pw, ost))
+    strided_copy(a, _contig_strides(a.shape), 0, out, ost, offset, a.shape)
+    return out
+
+
+def unpad(a: DeviceArray, pad_width) -> DeviceArray:
+    """a[lo:n-hi, ...] for each axis (gradient of pad, sp.py:325-327)."""
+    pw = _norm_pad(pad_width, a.ndim)
+    shape = tuple(n - lo - hi for n, (lo, hi) in zip(a.shape, pw))
+    ist = _contig_strides(a.shape)
+    offset = sum(lo * s for (lo, _), s in zip(pw, ist))
+    out = DeviceArray.empty(shape)
+    strided_copy(a, ist, offset, out, _contig_strides(shape), 0, shape)
+    return out
+
+
+def _norm_pad(pad_width, ndim):
+    pw = np.asarray(pad_width, dtype=np.int64)
+    pw = np.broadcast_to(pw, (ndim, 2))
+    return [(int(lo), int(hi)) for lo, hi in pw]
+
+
+@functools.lru_cache(maxsize=256)
+def _arange_index(shape):
+    return np.arange(math.prod(shape), dtype=np.int64).reshape(shape)
+
+
+def flat_index(shape, index) -> np.ndarray:
+    """int64 array of flat source offsets selected by the NumPy index expression `index`."""
+    return np.ascontiguousarray(_arange_index(tuple(shape))[index])
+
+
+def gather_flat(a: DeviceArray, flat: np.ndarray) -> DeviceArray:
+    idx = DeviceArray.from_host(flat, dtype=np.int64)
+    out = DeviceArray.empty(flat.shape)
+    if flat.size:
+        F.sp_gather_i64(a.ptr, idx.ptr, out._ptr, flat.size, stream())
+    return out
+
+
+def take(a: DeviceArray, index) -> DeviceArray:
+    """a[index] for any NumPy index expression (host builds the index map, device gathers)."""
+    return gather_flat(a, flat_index(a.shape, index))
+
+
+def scatter_add_flat(dst: DeviceArray, flat: np.ndarray, src: DeviceArray):
+    """np.add.at(dst.ravel(), flat, src) on device."""
+    if flat.size == 0:
+        return
+    idx = DeviceArray.from_host(flat, dtype=np.int64)
+    if src.shape != flat.shape:
+        src = binary("add", DeviceArray.zeros(flat.shape), src)  # broadcast to the index shape
+    F.sp_scatter_add_i64(dst.ptr, idx.ptr, src.ptr, flat.size, stream())
+
+
+def scatter_set_flat(dst: DeviceArray, flat: np.ndarray, src: DeviceArray):
+    if flat.size == 0:
+        return
+    idx = DeviceArray.from_host(flat, dtype=np.int64)
+    scalar = src.size == 1
+    if not scalar and src.shape != flat.shape:
+        src = binary("add", DeviceArray.zeros(flat.shape), src)
+    F.sp_scatter_set_i64(dst.ptr, idx.ptr, src.ptr, flat.size, 1 if scalar else 0, stream())
+
+
+def where(cond, a: DeviceArray, b: DeviceArray) -> DeviceArray:
+    cond = np.asarray(cond, dtype=np.bool_)
+    shape = np.broadcast_shapes(cond.shape, a.shape, b.shape)
+    nd = len(shape)
+    if nd > _abi.MAX_DIMS:
+        raise ValueError(f"arrays with more than {_abi.MAX_DIMS} dimensions are not supported")
+
+    def strides(s):
+        e = (1,) * (nd - len(s)) + tuple(s)
+        return tuple(0 if n == 1 and o != 1 else st
+                     for n, o, st in zip(e, shape, _contig_strides(e)))
+
+    c = DeviceArray.from_host(cond, dtype=np.uint8)
+    out = DeviceArray.empty(shape)
+    if out.size:
+        F.sp_where(c.ptr, _abi.dims(strides(cond.shape)), a.ptr, _abi.dims(strides(a.shape)),
+                   b.ptr, _abi.dims(strides(b.shape)), out._ptr, nd, _abi.dims(shape), stream())
+    return out

@@ -1,0 +1,696 @@
+"""Variable, get_gradients and the ops -- the host-side mirror of the reference's operator
+interface (same names, arguments, error behaviour as smallpebble/smallpebble.py, cited as
+"sp.py:line"), with every array operation dispatched to the sm_100a kernels behind
+include/smallpebble_b200.h.
+
+Tape contract kept verbatim (sp.py:36-54): `Variable(array, local_gradients)` where
+`local_gradients` is an iterable of `(child_variable, fn)` and `fn(path_value)` returns the
+gradient contribution for the child.  User-defined ops written that way keep working; the
+arrays they receive are `DeviceArray`s (NumPy functions accept them through `__array__`).
+
+Differences from the reference, all internal:
+  * `get_gradients` sweeps the tape in reverse topological order, calling each closure once
+    with the summed upstream gradient.  The reference walks every root->leaf path
+    (sp.py:79-83); both compute the same sums, ours without the 2x work softmax's diamond
+    causes and without a full-tensor `+=` per path.
+  * composite ops (conv2d, maxpool2d, softmax, cross_entropy) are single fused tape nodes:
+    their internal nodes (padded image, patch view, im2col matrix, ...) never exist.
+  * arrays are float32 on device (TF32 or fp32 math for contractions, `set_precision`).
+"""
+
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+
+from . import _abi
+from . import array as A
+from .array import DeviceArray
+
+F = _abi.f
+
+# --------------------------------------------------------------------------------------------
+# configuration
+# --------------------------------------------------------------------------------------------
+
+_PRECISIONS = {"fp32": _abi.PRECISION_FP32, "tf32": _abi.PRECISION_TF32}
+_precision = _PRECISIONS[os.environ.get("SP_PRECISION", "tf32").lower()]
+
+
+def set_precision(name: str) -> None:
+    """'tf32': contractions on tcgen05 tensor cores (rel. tol 2e-3 vs the float64 reference);
+    'fp32': CUDA-core FFMA (rel. tol 1e-5)."""
+    global _precision
+    _precision = _PRECISIONS[name.lower()]
+
+
+def get_precision() -> str:
+    return "tf32" if _precision == _abi.PRECISION_TF32 else "fp32"
+
+
+_fuse_softmax_xent = os.environ.get("SP_FUSE_SOFTMAX_XENT", "1") != "0"
+
+
+def set_fusion(enabled: bool) -> None:
+    """Fuse cross_entropy(softmax(x)) into one forward and one backward kernel (default on).
+    With fusion the loss's tape edge goes straight to the logits, so `get_gradients` has no
+    entry for the intermediate probability node; turn it off to get that entry."""
+    global _fuse_softmax_xent
+    _fuse_softmax_xent = bool(enabled)
+
+
+# --------------------------------------------------------------------------------------------
+# autodiff core (sp.py:36-87)
+# --------------------------------------------------------------------------------------------
+
+
+class Variable:
+    """A value in a differentiable computation: `.array` (a DeviceArray) and
+    `.local_gradients = [(child_variable, fn(path_value) -> array), ...]` (sp.py:36-54)."""
+
+    def __init__(self, array, local_gradients=None) -> None:
+        self.array = array
+        self.local_gradients = local_gradients if local_gradients else []
+
+    @property
+    def array(self):
+        return self._array
+
+    @array.setter
+    def array(self, value):
+        self._array = value if isinstance(value, DeviceArray) else DeviceArray.from_host(value)
+
+    dtype = property(lambda self: self._array.dtype)  # sp.py:459-461
+    ndim = property(lambda self: self._array.ndim)
+    shape = property(lambda self: self._array.shape)
+
+
+def get_gradients(variable: Variable) -> dict:
+    """d(sum of `variable`)/d(node) for every node reachable from `variable` (sp.py:57-87).
+
+    Returns {Variable: DeviceArray}, keyed by identity, including `variable` itself (ones).
+    """
+    # reverse post-order of the tape DAG = parents before children
+    order, seen, stack = [], {id(variable)}, [(variable, iter(variable.local_gradients))]
+    while stack:
+        node, it = stack[-1]
+        advanced = False
+        for child, _ in it:
+            if id(child) not in seen:
+                seen.add(id(child))
+                stack.append((child, iter(child.local_gradients)))
+                advanced = True
+                break
+        if not advanced:
+            order.append(node)
+            stack.pop()
+    order.reverse()
+
+    gradients = {variable: DeviceArray.full(variable.array.shape, 1.0)}
+    owned = {variable}  # gradient buffers nobody else aliases: safe to accumulate in place
+    for node in order:
+        path_value = gradients[node]
+        for child, multiply_by_locgrad in node.local_gradients:
+            value = multiply_by_locgrad(path_value)
+            if not isinstance(value, DeviceArray):
+                value = DeviceArray.from_host(value)
+            have = gradients.get(child)
+            if have is None:
+                gradients[child] = value  # may alias path_value (identity closures)
+            elif child in owned and have.shape == value.shape:
+                A.accumulate_(have, value)
+            else:
+                gradients[child] = A.binary("add", have, value)
+                owned.add(child)
+    return gradients
+
+
+# --------------------------------------------------------------------------------------------
+# shape / padding utilities (sp.py:659-782) -- host integer logic, bit-exact with the oracle
+# --------------------------------------------------------------------------------------------
+
+
+def broadcastinfo(a_shape, b_shape):
+    "Get which dimensions are added or repeated when `a` and `b` are broadcast (sp.py:659-684)."
+    ndim = max(len(a_shape), len(b_shape))
+    pad_a, pad_b = ndim - len(a_shape), ndim - len(b_shape)
+    ea = (1,) * pad_a + tuple(a_shape)
+    eb = (1,) * pad_b + tuple(b_shape)
+    if not all(p == q or p == 1 or q == 1 for p, q in zip(ea, eb)):
+        raise ValueError(f"could not broadcast shapes {a_shape} {b_shape}")
+    a_rep = tuple(i for i in range(ndim) if i < pad_a or (ea[i] == 1 and eb[i] > 1))
+    b_rep = tuple(i for i in range(ndim) if i < pad_b or (eb[i] == 1 and ea[i] > 1))
+    return a_rep, b_rep
+
+
+def pad_amounts(array_length: int, stride: int, kern_length: int):
+    """TF 'SAME' padding of a 1-D array (sp.py:721-730): the odd pixel goes to the end."""
+    num_patches = math.ceil(array_length / stride)
+    target_length = (num_patches - 1) * stride + kern_length
+    padding_amount = max(target_length - array_length, 0)
+    pad_front = padding_amount // 2
+    return pad_front, padding_amount - pad_front
+
+
+def _window_geometry(imheight, imwidth, kernheight, kernwidth, stride_y, stride_x, padding):
+    """(pad_top, pad_bottom, pad_left, pad_right, outheight, outwidth): sp.py:733-761, 712-714."""
+    if padding == "SAME":
+        pad_top, pad_bottom = pad_amounts(imheight, stride_y, kernheight)
+        pad_left, pad_right = pad_amounts(imwidth, stride_x, kernwidth)
+    elif padding == "VALID":
+        pad_top = pad_bottom = pad_left = pad_right = 0
+    else:
+        raise ValueError("padding must be 'SAME' or 'VALID'.")
+    hp, wp = imheight + pad_top + pad_bottom, imwidth + pad_left + pad_right
+    if hp < kernheight or wp < kernwidth:
+        raise ValueError("window shape cannot be larger than input array shape")  # sp.py:710-711
+    outheight = math.ceil((hp - kernheight + 1) / stride_y)
+    outwidth = math.ceil((wp - kernwidth + 1) / stride_x)
+    return pad_top, pad_bottom, pad_left, pad_right, outheight, outwidth
+
+
+def padding2d(images, padding, imheight, imwidth, stride_y, stride_x, kernheight, kernwidth):
+    "Pad `images` for conv2d, maxpool2d (sp.py:733-761).  Returns (images, imheight, imwidth)."
+    if padding == "SAME":
+        pad_top, pad_bottom = pad_amounts(imheight, stride_y, kernheight)
+        pad_left, pad_right = pad_amounts(imwidth, stride_x, kernwidth)
+        images = pad(images, pad_width=[(0, 0), (pad_top, pad_bottom), (pad_left, pad_right), (0, 0)])
+        _, imheight, imwidth, _ = images.array.shape
+    elif padding == "VALID":
+        pass
+    else:
+        raise ValueError("padding must be 'SAME' or 'VALID'.")
+    return images, imheight, imwidth
+
+
+def np_strided_sliding_view(x: np.ndarray, window_shape, strides) -> np.ndarray:
+    """Host helper kept for API parity (sp.py:687-718): strided window view of a NumPy array,
+    shape = reduced + window.  The device ops use it only to build index maps."""
+    if not len(window_shape) == x.ndim:
+        raise ValueError("Must provide one window size for each dimension of x.")
+    if not len(strides) == x.ndim:
+        raise ValueError("Must provide one stride size for each dimension of x.")
+    if any(size < 0 for size in window_shape):
+        raise ValueError("`window_shape` cannot contain negative values")
+    if any(stride < 0 for stride in strides):
+        raise ValueError("`strides` cannot contain negative values")
+    if any(x_size < w_size for x_size, w_size in zip(x.shape, window_shape)):
+        raise ValueError("window shape cannot be larger than input array shape")
+    reduced = tuple(math.ceil((n - w + 1) / s) for n, s, w in zip(x.shape, strides, window_shape))
+    steps = tuple(b * s for b, s in zip(x.strides, strides))
+    return np.lib.stride_tricks.as_strided(
+        x, shape=reduced + tuple(window_shape), strides=steps + x.strides
+    )
+
+
+def patches_index(imheight, imwidth, kernheight, kernwidth, stride_y, stride_x):
+    """im2col index map of one 2-D image (sp.py:764-782): ((rows, cols), outheight, outwidth,
+    n_patches), rows/cols int64 [n_patches, kernheight*kernwidth]."""
+    ys = np.arange(0, imheight - kernheight + 1, stride_y, dtype=np.int64)
+    xs = np.arange(0, imwidth - kernwidth + 1, stride_x, dtype=np.int64)
+    dy, dx = np.divmod(np.arange(kernheight * kernwidth, dtype=np.int64), kernwidth)
+    rows = np.broadcast_to(ys[:, None, None] + dy[None, None, :], (len(ys), len(xs), len(dy)))
+    cols = np.broadcast_to(xs[None, :, None] + dx[None, None, :], (len(ys), len(xs), len(dy)))
+    outheight, outwidth = len(ys), len(xs)
+    n_patches = outheight * outwidth
+    return (
+        (np.ascontiguousarray(rows).reshape(n_patches, -1),
+         np.ascontiguousarray(cols).reshape(n_patches, -1)),
+        outheight, outwidth, n_patches,
+    )
+
+
+def _unbroadcast(g: DeviceArray, shape, repeat_axes) -> DeviceArray:
+    """Sum `g` back to an operand's own shape (the reference's enable_broadcast closures,
+    sp.py:183-189) -- skipped entirely when nothing was broadcast."""
+    if g.shape == tuple(shape):
+        return g
+    return A.reduce_sum(g, repeat_axes).reshape(shape) if repeat_axes else g.reshape(shape)
+
+
+# --------------------------------------------------------------------------------------------
+# elementwise ops
+# --------------------------------------------------------------------------------------------
+
+
+def add(a: Variable, b: Variable) -> Variable:
+    "Elementwise addition (sp.py:100-108)."
+    ra, rb = broadcastinfo(a.array.shape, b.array.shape)
+    value = A.binary("add", a.array, b.array)
+    sa, sb = a.array.shape, b.array.shape
+    return Variable(value, [
+        (a, lambda g: _unbroadcast(g, sa, ra)),
+        (b, lambda g: _unbroadcast(g, sb, rb)),
+    ])
+
+
+def sub(a: Variable, b: Variable) -> Variable:
+    "Elementwise subtraction (sp.py:393-401)."
+    ra, rb = broadcastinfo(a.array.shape, b.array.shape)
+    value = A.binary("sub", a.array, b.array)
+    sa, sb = a.array.shape, b.array.shape
+    return Variable(value, [
+        (a, lambda g: _unbroadcast(g, sa, ra)),
+        (b, lambda g: A.unary("neg", _unbroadcast(g, sb, rb))),
+    ])
+
+
+def mul(a: Variable, b: Variable) -> Variable:
+    "Elementwise multiplication (sp.py:303-311)."
+    ra, rb = broadcastinfo(a.array.shape, b.array.shape)
+    av, bv = a.array, b.array
+    return Variable(A.binary("mul", av, bv), [
+        (a, lambda g: _unbroadcast(A.binary("mul", g, bv), av.shape, ra)),
+        (b, lambda g: _unbroadcast(A.binary("mul", g, av), bv.shape, rb)),
+    ])
+
+
+def div(a: Variable, b: Variable) -> Variable:
+    "Elementwise division (sp.py:166-174)."
+    ra, rb = broadcastinfo(a.array.shape, b.array.shape)
+    av, bv = a.array, b.array
+    return Variable(A.binary("div", av, bv), [
+        (a, lambda g: _unbroadcast(A.binary("div", g, bv), av.shape, ra)),
+        # -g * a / b^2
+        (b, lambda g: _unbroadcast(A.binary("mul", g, A.binary("div_grad_b", av, bv)), bv.shape, rb)),
+    ])
+
+
+def neg(a: Variable) -> Variable:
+    "Negate a variable (sp.py:314-318)."
+    return Variable(A.unary("neg", a.array), [(a, lambda g: A.unary("neg", g))])
+
+
+def exp(a: Variable) -> Variable:
+    "Elementwise exp of `a` (sp.py:196-200)."
+    value = A.unary("exp", a.array)
+    return Variable(value, [(a, lambda g: A.binary("mul", g, value))])
+
+
+def log(a: Variable) -> Variable:
+    "Elementwise log of `a` (sp.py:224-228)."
+    av = a.array
+    return Variable(A.unary("log", av), [(a, lambda g: A.binary("div", g, av))])
+
+
+def square(a: Variable) -> Variable:
+    "Square each element of `a` (sp.py:367-375)."
+    av = a.array
+    return Variable(A.unary("square", av),
+                    [(a, lambda g: A.binary("mul", g, A.unary("scale", av, 2.0)))])
+
+
+def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
+    "Elementwise leaky relu (sp.py:231-236): x > 0 ? x : alpha*x; the slope at 0 is alpha."
+    x = a.array
+    y = DeviceArray.empty(x.shape)
+    F.sp_leaky_relu_fwd(x.ptr, y.ptr, x.size, float(alpha), A.stream())
+
+    def multiply_by_locgrad(g):
+        dx = DeviceArray.empty(x.shape)
+        F.sp_leaky_relu_bwd(g.ptr, x.ptr, dx.ptr, x.size, float(alpha), A.stream())
+        return dx
+
+    return Variable(y, [(a, multiply_by_locgrad)])
+
+
+def where(condition: np.ndarray, a: Variable, b: Variable) -> Variable:
+    "Condition is a boolean NumPy array, a and b are Variables (sp.py:418-441)."
+    condition = np.asarray(condition, dtype=np.bool_)
+    ra, rb = broadcastinfo(a.array.shape, b.array.shape)
+    av, bv = a.array, b.array
+    value = A.where(condition, av, bv)
+
+    def grad_a(g):
+        return _unbroadcast(A.where(condition, g, DeviceArray.zeros(())), av.shape, ra)
+
+    def grad_b(g):
+        return _unbroadcast(A.where(condition, DeviceArray.zeros(()), g), bv.shape, rb)
+
+    return Variable(value, [(a, grad_a), (b, grad_b)])
+
+
+# --------------------------------------------------------------------------------------------
+# shape ops
+# --------------------------------------------------------------------------------------------
+
+
+def reshape(a: Variable, shape) -> Variable:
+    "Reshape `a` into shape `shape` (sp.py:333-337): metadata only on device."
+    src_shape = a.array.shape
+    return Variable(a.array.reshape(shape), [(a, lambda g: g.reshape(src_shape))])
+
+
+def expand_dims(a: Variable, axis) -> Variable:
+    "Add new axes with size of 1, indices specified by `axis` (sp.py:203-207)."
+    src_shape = a.array.shape
+    new_shape = np.expand_dims(np.empty(src_shape, np.bool_), axis).shape
+    return Variable(a.array.reshape(new_shape), [(a, lambda g: g.reshape(src_shape))])
+
+
+def matrix_transpose(a: Variable) -> Variable:
+    "Swap the end two axes (sp.py:250-254)."
+    return Variable(A.swapaxes(a.array, -2, -1), [(a, lambda g: A.swapaxes(g, -2, -1))])
+
+
+def pad(a: Variable, pad_width) -> Variable:
+    "Zero pad `a`, where pad_width[dim] = (left width, right width) (sp.py:321-330)."
+    return Variable(A.pad(a.array, pad_width), [(a, lambda g: A.unpad(g, pad_width))])
+
+
+def sum(a: Variable, axis=None) -> Variable:  # noqa: A001 (shadows builtin like the reference)
+    "Sum elements of `a`, along axes specified in `axis` (sp.py:404-415)."
+    src_shape = a.array.shape
+    value = A.reduce_sum(a.array, axis)
+    axes = A._norm_axes(axis, len(src_shape))
+    keep_shape = tuple(1 if i in axes else n for i, n in enumerate(src_shape))
+
+    def multiply_by_locgrad(g):
+        # broadcast the reduced gradient back over the summed axes
+        return A.binary("add", DeviceArray.zeros(src_shape), g.reshape(keep_shape))
+
+    return Variable(value, [(a, multiply_by_locgrad)])
+
+
+def getitem(a: Variable, indices) -> Variable:
+    "Get elements of `a` using NumPy indexing (sp.py:210-221)."
+    src_shape = a.array.shape
+    flat = A.flat_index(src_shape, indices)
+    value = A.gather_flat(a.array, flat)
+
+    def multiply_by_locgrad(g):
+        "(Takes into account elements indexed multiple times.)"
+        result = DeviceArray.zeros(src_shape)
+        A.scatter_add_flat(result, flat, g)
+        return result
+
+    return Variable(value, [(a, multiply_by_locgrad)])
+
+
+def add_at(a: Variable, indices, b: Variable) -> Variable:
+    """Add the elements of `b` to the locations in `a` specified by `indices`; repeated
+    indices accumulate (sp.py:111-121)."""
+    flat = A.flat_index(a.array.shape, indices)
+    value = a.array.copy()
+    A.scatter_add_flat(value, flat, b.array)
+    b_shape = b.array.shape
+
+    def grad_b(g):
+        picked = A.gather_flat(g, flat)
+        if picked.shape == b_shape:
+            return picked
+        rb = broadcastinfo(b_shape, picked.shape)[0]
+        return _unbroadcast(picked, b_shape, rb)
+
+    return Variable(value, [(a, lambda g: g), (b, grad_b)])
+
+
+def setat(a: Variable, indices, b: Variable) -> Variable:
+    """Similar to NumPy's `setitem`: a copy of `a` with `a[indices] = b` (sp.py:340-354)."""
+    flat = A.flat_index(a.array.shape, indices)
+    value = a.array.copy()
+    A.scatter_set_flat(value, flat, b.array)
+    b_shape = b.array.shape
+
+    def grad_a(g):
+        out = g.copy()  # the reference zeroes path_value in place; we leave it untouched
+        A.scatter_set_flat(out, flat, DeviceArray.zeros(()))
+        return out
+
+    def grad_b(g):
+        picked = A.gather_flat(g, flat)
+        if picked.shape == b_shape:
+            return picked
+        return _unbroadcast(picked, b_shape, broadcastinfo(b_shape, picked.shape)[0])
+
+    return Variable(value, [(a, grad_a), (b, grad_b)])
+
+
+def strided_sliding_view(a: Variable, window_shape, strides) -> Variable:
+    """Sliding window view with strides in index units (sp.py:378-390).  On device this is a
+    gather through a host-built index map; the backward pass is the matching scatter-add
+    (np.add.at semantics: overlapping windows accumulate)."""
+    src_shape = a.array.shape
+    index_map = np.ascontiguousarray(
+        np_strided_sliding_view(A._arange_index(tuple(src_shape)), tuple(window_shape), tuple(strides))
+    )
+    value = A.gather_flat(a.array, index_map)
+
+    def multiply_by_locgrad(g):
+        result = DeviceArray.zeros(src_shape)
+        A.scatter_add_flat(result, index_map, g)
+        return result
+
+    return Variable(value, [(a, multiply_by_locgrad)])
+
+
+def maxax(a: Variable, axis: int) -> Variable:
+    "Reduce an axis, `axis`, to its max value, keeping it with size 1 (sp.py:257-279)."
+    shape = a.array.shape
+    nd = len(shape)
+    axis = axis if axis >= 0 else nd + axis
+    moved = a.array if axis == nd - 1 else A.swapaxes(a.array, axis, -1)
+    n = moved.shape[-1]
+    rows = moved.size // n if n else 0
+    best = DeviceArray.empty((rows,))
+    idx = DeviceArray.empty((rows,), np.int32)
+    F.sp_argmax_rows_fwd(moved.ptr, best.ptr, idx.ptr, rows, n, A.stream())
+    out_shape = tuple(1 if i == axis else v for i, v in enumerate(shape))
+    moved_shape = moved.shape
+
+    def multiply_by_locgrad(g):
+        dx = DeviceArray.empty(moved_shape)
+        F.sp_argmax_rows_bwd(g.ptr, idx.ptr, dx.ptr, rows, n, A.stream())
+        return dx if axis == nd - 1 else A.swapaxes(dx, axis, -1)
+
+    return Variable(best.reshape(out_shape), [(a, multiply_by_locgrad)])
+
+
+# --------------------------------------------------------------------------------------------
+# matmul (sp.py:239-247): NumPy batch broadcasting, gradients summed back over broadcast dims
+# --------------------------------------------------------------------------------------------
+
+
+def _gemm(ta, tb, m, n, k, a, lda, sa, b, ldb, sb, batch, out_shape) -> DeviceArray:
+    out = DeviceArray.empty(out_shape)
+    if out.size:
+        F.sp_gemm(ta, tb, m, n, k, a.ptr, lda, sa, b.ptr, ldb, sb, out.ptr, n, m * n, batch,
+                  _precision, A.stream())
+    return out
+
+
+def _broadcast_to(x: DeviceArray, shape) -> DeviceArray:
+    if x.shape == tuple(shape):
+        return x
+    return A.binary("add", DeviceArray.zeros(shape), x)
+
+
+def matmul(a: Variable, b: Variable) -> Variable:
+    "Matrix multiplication (sp.py:239-247)."
+    av, bv = a.array, b.array
+    if av.ndim < 2 or bv.ndim < 2:
+        raise ValueError("matmul operands must have at least 2 dimensions")
+    M, K = av.shape[-2:]
+    K2, N = bv.shape[-2:]
+    if K != K2:
+        raise ValueError(f"matmul: shapes {av.shape} and {bv.shape} not aligned")
+    a_batch, b_batch = av.shape[:-2], bv.shape[:-2]
+    ra, rb = broadcastinfo(a_batch, b_batch)
+    batch_shape = np.broadcast_shapes(a_batch, b_batch)
+    nb = math.prod(batch_shape)
+
+    if not b_batch:
+        # [..., M, K] x [K, N]: one GEMM over the flattened rows (the layer case)
+        rows = math.prod(a_batch) * M
+        value = _gemm(0, 0, rows, N, K, av, K, 0, bv, N, 0, 1, a_batch + (M, N))
+
+        def grad_a(g):  # g . b^T
+            return _gemm(0, 1, rows, K, N, g, N, 0, bv, N, 0, 1, av.shape)
+
+        def grad_b(g):  # a^T . g   (the sum over the batch is inside the contraction)
+            return _gemm(1, 0, K, N, rows, av, K, 0, g, N, 0, 1, bv.shape)
+
+        return Variable(value, [(a, grad_a), (b, grad_b)])
+
+    # general case: materialise broadcast batch dims, then strided-batched GEMMs
+    af = _broadcast_to(av, batch_shape + (M, K)) if a_batch != batch_shape else av
+    bf = _broadcast_to(bv, batch_shape + (K, N)) if b_batch != batch_shape else bv
+    value = _gemm(0, 0, M, N, K, af, K, M * K, bf, N, K * N, nb, batch_shape + (M, N))
+
+    def grad_a(g):
+        full = _gemm(0, 1, M, K, N, g, N, M * N, bf, N, K * N, nb, batch_shape + (M, K))
+        return _unbroadcast(full, av.shape, ra)
+
+    def grad_b(g):
+        full = _gemm(1, 0, K, N, M, af, K, M * K, g, N, M * N, nb, batch_shape + (K, N))
+        return _unbroadcast(full, bv.shape, rb)
+
+    return Variable(value, [(a, grad_a), (b, grad_b)])
+
+
+# --------------------------------------------------------------------------------------------
+# conv2d / maxpool2d
+# --------------------------------------------------------------------------------------------
+
+
+def _conv_geom(n, h, w, c, kh, kw, k, sy, sx, pt, pl, oh, ow) -> _abi.ConvGeom:
+    return _abi.ConvGeom(n, h, w, c, kh, kw, k, sy, sx, pt, pl, oh, ow)
+
+
+def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(1, 1)) -> Variable:
+    """2D convolution, with same api as tf.nn.conv2d (sp.py:124-163).
+
+    images [n_images, imheight, imwidth, n_channels] (NHWC), kernels [kernheight, kernwidth,
+    channels_in, channels_out] (HWIO) -> [n_images, outheight, outwidth, channels_out].
+    One implicit-GEMM kernel; the gradients are two more (input gradient in gather form
+    instead of np.add.at col2im, filter gradient with a deterministic split reduction).
+    """
+    x, w = images.array, kernels.array
+    n_images, imheight, imwidth, channels = x.shape
+    kernheight, kernwidth, channels_in, channels_out = w.shape
+    if channels != channels_in:
+        raise ValueError(f"conv2d: images have {channels} channels, kernels expect {channels_in}")
+    stride_y, stride_x = strides
+    pt, _, pl, _, outh, outw = _window_geometry(
+        imheight, imwidth, kernheight, kernwidth, stride_y, stride_x, padding)
+    geom = _conv_geom(n_images, imheight, imwidth, channels, kernheight, kernwidth, channels_out,
+                      stride_y, stride_x, pt, pl, outh, outw)
+    y = DeviceArray.empty((n_images, outh, outw, channels_out))
+    if y.size:
+        F.sp_conv2d_fprop(x.ptr, w.ptr, y.ptr, geom, _precision, A.stream())
+
+    def grad_images(g):
+        dx = DeviceArray.empty(x.shape)
+        if dx.size:
+            F.sp_conv2d_dgrad(g.ptr, w.ptr, dx.ptr, geom, _precision, A.stream())
+        return dx
+
+    def grad_kernels(g):
+        dw = DeviceArray.empty(w.shape)
+        ws_bytes = _abi.load().sp_conv2d_wgrad_workspace(geom, _precision)
+        ws = DeviceArray.empty((ws_bytes // 4,)) if ws_bytes else None
+        F.sp_conv2d_wgrad(x.ptr, g.ptr, dw.ptr, geom, _precision, ws.ptr if ws is not None else None,
+                          ws_bytes, A.stream())
+        return dw
+
+    return Variable(y, [(images, grad_images), (kernels, grad_kernels)])
+
+
+def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = "SAME",
+              strides=[1, 1]) -> Variable:  # noqa: B006 (signature kept from sp.py:282-288)
+    """Maxpooling on a `variable` of shape [n_images, imheight, imwidth, n_channels]
+    (sp.py:282-300).  Zero padding takes part in the max and the first maximum in (dy, dx)
+    order wins -- exactly what np.pad + np.argmax give the reference."""
+    x = images.array
+    n_images, imheight, imwidth, n_channels = x.shape
+    stride_y, stride_x = strides
+    pt, _, pl, _, outh, outw = _window_geometry(
+        imheight, imwidth, kernheight, kernwidth, stride_y, stride_x, padding)
+    y = DeviceArray.empty((n_images, outh, outw, n_channels))
+    idx = DeviceArray.empty((n_images, outh, outw, n_channels), np.uint8)
+    geom = (n_images, imheight, imwidth, n_channels, kernheight, kernwidth, stride_y, stride_x,
+            pt, pl, outh, outw)
+    if y.size:
+        F.sp_maxpool2d_fwd(x.ptr, y.ptr, idx.ptr, *geom, A.stream())
+
+    def multiply_by_locgrad(g):
+        dx = DeviceArray.empty(x.shape)
+        if dx.size:
+            F.sp_maxpool2d_bwd(g.ptr, idx.ptr, dx.ptr, *geom, A.stream())
+        return dx
+
+    out = Variable(y, [(images, multiply_by_locgrad)])
+    out._argmax = idx  # uint8 [N,OH,OW,C]: dy*kernwidth+dx, exposed for the bit-exact tests
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# softmax / cross entropy
+# --------------------------------------------------------------------------------------------
+
+
+def softmax(a: Variable, axis: int = -1) -> Variable:
+    """Softmax on `axis` (sp.py:357-364).  The kernel shifts by the per-slice maximum instead
+    of the reference's whole-array maximum: identical mathematics (shift invariance), closest
+    to the float64 result over the widest input range in fp32."""
+    x = a.array
+    nd = x.ndim
+    ax = axis if axis >= 0 else nd + axis
+    outer, n, inner = math.prod(x.shape[:ax]), x.shape[ax], math.prod(x.shape[ax + 1:])
+    y = DeviceArray.empty(x.shape)
+    if y.size:
+        F.sp_softmax_fwd(x.ptr, y.ptr, outer, n, inner, A.stream())
+
+    def multiply_by_locgrad(g):
+        dx = DeviceArray.empty(x.shape)
+        if dx.size:
+            F.sp_softmax_bwd(y.ptr, g.ptr, dx.ptr, outer, n, inner, A.stream())
+        return dx
+
+    out = Variable(y, [(a, multiply_by_locgrad)])
+    if inner == 1 and nd == 2:
+        out._softmax_of = a  # lets cross_entropy fuse forward and backward with this node
+    return out
+
+
+def cross_entropy(y_pred: Variable, y_true: np.ndarray, axis: int = -1) -> Variable:
+    """Cross entropy (sp.py:612-621): y_pred [batch, n_classes] probabilities, y_true integer
+    labels [batch]; returns the SUM over the batch as a 0-d Variable.
+
+    When `y_pred` is the direct output of `sp.softmax` the loss is evaluated from the logits
+    (logsumexp - logit) and the backward edge goes straight to the logits as
+    g * (p - onehot): the fused softmax-cross-entropy of the README models."""
+    probs = y_pred.array
+    if probs.ndim != 2:
+        raise ValueError("cross_entropy expects y_pred of shape [batch_size, n_classes]")
+    rows, cols = probs.shape
+    labels_host = np.asarray(y_true.array if isinstance(y_true, Variable) else y_true)
+    labels_host = labels_host.reshape(-1).astype(np.int64)
+    if labels_host.shape[0] != rows:
+        raise ValueError("cross_entropy: len(y_true) must equal the batch size")
+    if rows and (labels_host.min() < -cols or labels_host.max() >= cols):
+        raise IndexError("cross_entropy: label out of range")
+    labels_host = np.where(labels_host < 0, labels_host + cols, labels_host)
+    labels = DeviceArray.from_host(labels_host, dtype=np.int32)
+    loss = DeviceArray.empty(())
+    logits_var = getattr(y_pred, "_softmax_of", None) if _fuse_softmax_xent else None
+
+    if logits_var is not None:
+        logits = logits_var.array
+        # recomputes probs into the existing buffer (bitwise the same values) + the loss
+        F.sp_softmax_xent_fwd(logits.ptr, labels.ptr, probs.ptr, loss.ptr, rows, cols, A.stream())
+
+        def grad_logits(g):
+            dlogits = DeviceArray.empty(logits.shape)
+            if dlogits.size:
+                F.sp_softmax_xent_bwd(probs.ptr, labels.ptr, g.ptr, dlogits.ptr, rows, cols,
+                                      A.stream())
+            return dlogits
+
+        out = Variable(loss, [(logits_var, grad_logits)])
+        out._fused_softmax_xent = True
+        return out
+
+    F.sp_xent_fwd(probs.ptr, labels.ptr, loss.ptr, rows, cols, A.stream())
+
+    def grad_probs(g):
+        dprobs = DeviceArray.empty(probs.shape)
+        if dprobs.size:
+            F.sp_xent_bwd(probs.ptr, labels.ptr, g.ptr, dprobs.ptr, rows, cols, A.stream())
+        return dprobs
+
+    return Variable(loss, [(y_pred, grad_probs)])
+
+
+# --------------------------------------------------------------------------------------------
+# operator overloads and attributes (sp.py:449-461)
+# --------------------------------------------------------------------------------------------
+
+Variable.__add__ = add
+Variable.__mul__ = mul
+Variable.__neg__ = neg
+Variable.__sub__ = sub
+Variable.__truediv__ = div
+Variable.__getitem__ = getitem

@@ -1,0 +1,102 @@
+// Shared helpers for the smallpebble_b200 CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/smallpebble_b200.h"
+
+namespace sp {
+
+// thread-local error text returned by sp_last_error()
+char* error_buffer();
+int set_error(int code, const char* fmt, ...);
+
+struct DeviceInfo {
+  int sm_count = 0;
+  int cc_major = 0;
+  int cc_minor = 0;
+  bool ok = false;
+};
+const DeviceInfo& device_info();
+
+inline cudaStream_t as_stream(sp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// grid sized in whole waves of the SM count (B200: 148 SMs)
+inline int wave_grid(int64_t work_items, int items_per_block, int blocks_per_sm) {
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  int64_t need = (work_items + items_per_block - 1) / items_per_block;
+  int64_t cap = (int64_t)sms * blocks_per_sm;
+  if (need <= 0) need = 1;
+  if (need >= cap) return (int)cap;
+  return (int)need;
+}
+
+}  // namespace sp
+
+#define SP_CHECK_CUDA(expr)                                                          \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess)                                                           \
+      return sp::set_error((int)_e, "%s failed: %s (%s:%d)", #expr,                  \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);              \
+  } while (0)
+
+#define SP_CHECK_LAUNCH(name)                                                        \
+  do {                                                                               \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess)                                                           \
+      return sp::set_error((int)_e, "launch of %s failed: %s", name,                 \
+                           cudaGetErrorString(_e));                                  \
+  } while (0)
+
+#define SP_REQUIRE(cond, msg)                                                        \
+  do {                                                                               \
+    if (!(cond)) return sp::set_error(SP_ERR_INVALID_ARGUMENT, "%s: %s", __func__, msg); \
+  } while (0)
+
+// ---- device helpers -------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  // streaming 128-bit load: read once, do not pollute L1
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum; `scratch` must hold 32 floats; result valid in every thread
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (lane < nw) ? scratch[lane] : 0.f;
+  return warp_sum(t);
+}
+
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (lane < nw) ? scratch[lane] : -INFINITY;
+  return warp_max(t);
+}

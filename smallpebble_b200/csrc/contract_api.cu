@@ -1,0 +1,211 @@
+// C-ABI entry points of the contraction ops: sp_gemm and sp_conv2d_{fprop,dgrad,wgrad}.
+// Chooses between the tcgen05 tensor-core kernel (SP_PRECISION_TF32) and the CUDA-core fp32
+// kernel (SP_PRECISION_FP32, tiny-N problems), and owns the deterministic split-K policy of
+// the filter gradient.
+#include <stdlib.h>
+#include <string.h>
+
+#include "igemm.cuh"
+
+namespace sp {
+namespace {
+
+// 0 = policy (default), 1 = always tcgen05 when the shape is supported (tests),
+// 2 = never tcgen05
+int g_umma_policy = 0;
+
+bool use_umma(int mode, const IgemmParams& p, int precision) {
+  if (precision != SP_PRECISION_TF32 || g_umma_policy == 2) return false;
+  if (!igemm_umma_supported(mode, p)) return false;
+  if (g_umma_policy == 1) return true;
+  // A 128 x 32 tile with an 8-deep MMA is the smallest useful unit: below that the CUDA-core
+  // kernel wins on latency (e.g. the 10-way classifier, sp.py:634).
+  return p.N >= 16 && p.K >= 8;
+}
+
+int check_geom(const sp_conv_geom* g) {
+  if (!g) return set_error(SP_ERR_INVALID_ARGUMENT, "conv2d: null geometry");
+  if (g->N < 0 || g->H <= 0 || g->W <= 0 || g->C <= 0 || g->KH <= 0 || g->KW <= 0 || g->K <= 0 ||
+      g->sy <= 0 || g->sx <= 0 || g->OH < 0 || g->OW < 0 || g->pad_t < 0 || g->pad_l < 0)
+    return set_error(SP_ERR_INVALID_ARGUMENT, "conv2d: bad geometry");
+  return 0;
+}
+
+IgemmParams base_params() {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.batch = 1;
+  p.k_splits = 1;
+  return p;
+}
+
+// Deterministic split of the wgrad reduction axis: enough CTAs for ~2 waves, k_chunk a
+// multiple of 32 so both kernels tile it exactly.
+void wgrad_split(const sp_conv_geom& g, bool umma, int* splits, int64_t* k_chunk) {
+  const int64_t M = (int64_t)g.KH * g.KW * g.C, N = g.K, K = (int64_t)g.N * g.OH * g.OW;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  int64_t tiles;
+  if (umma) {
+    const int bn = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+    tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  } else {
+    tiles = ((M + 63) / 64) * ((N + 63) / 64);
+  }
+  int64_t want = (2 * sms + tiles - 1) / tiles;
+  const int64_t min_chunk = umma ? 256 : 128;  // keep every CTA's k-loop worth its prologue
+  int64_t max_splits = (K + min_chunk - 1) / min_chunk;
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  int64_t chunk = (K + want - 1) / want;
+  chunk = (chunk + 31) / 32 * 32;
+  if (chunk <= 0) chunk = 32;
+  *k_chunk = chunk;
+  *splits = (int)((K + chunk - 1) / chunk);
+  if (*splits < 1) *splits = 1;
+}
+
+}  // namespace
+}  // namespace sp
+
+extern "C" {
+
+// undocumented test hook (declared in tests only): select the contraction kernel family
+int sp_debug_set_umma_policy(int policy) {
+  if (policy < 0 || policy > 2) return sp::set_error(SP_ERR_INVALID_ARGUMENT, "policy in 0..2");
+  sp::g_umma_policy = policy;
+  return 0;
+}
+
+int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+            int64_t strideA, const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc,
+            int64_t strideC, int64_t batch, int precision, sp_stream_t stream) {
+  SP_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, "negative extent");
+  SP_REQUIRE(precision == SP_PRECISION_FP32 || precision == SP_PRECISION_TF32, "bad precision");
+  if (M == 0 || N == 0 || batch == 0) return 0;
+  if (K == 0) {
+    // empty inner dimension: np.matmul yields zeros
+    if (ldc == N && (batch == 1 || strideC == M * N)) return sp_fill_f32(C, batch * M * N, 0.f, stream);
+    return sp::set_error(SP_ERR_UNSUPPORTED, "sp_gemm: K == 0 with strided C");
+  }
+  sp::IgemmParams p = sp::base_params();
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.A = A;
+  p.B = B;
+  p.C = C;
+  p.ldc = ldc;
+  p.a_rs = transA ? 1 : lda;
+  p.a_cs = transA ? lda : 1;
+  p.b_rs = transB ? 1 : ldb;
+  p.b_cs = transB ? ldb : 1;
+  p.batch = batch;
+  p.batch_a = strideA;
+  p.batch_b = strideB;
+  p.batch_c = strideC;
+  cudaStream_t st = sp::as_stream(stream);
+  int rc = sp::use_umma(sp::kGemm, p, precision) ? sp::launch_igemm_umma(sp::kGemm, p, st)
+                                                  : sp::launch_igemm_simt(sp::kGemm, p, st);
+  if (rc) return rc;
+  SP_CHECK_LAUNCH("gemm");
+  return 0;
+}
+
+int sp_conv2d_fprop(const float* x, const float* w, float* y, const sp_conv_geom* g,
+                    int precision, sp_stream_t stream) {
+  if (int rc = sp::check_geom(g)) return rc;
+  sp::IgemmParams p = sp::base_params();
+  p.g = *g;
+  p.M = (int64_t)g->N * g->OH * g->OW;
+  p.N = g->K;
+  p.K = (int64_t)g->KH * g->KW * g->C;
+  p.A = x;
+  p.B = w;
+  p.C = y;
+  p.ldc = g->K;
+  if (p.M == 0) return 0;
+  cudaStream_t st = sp::as_stream(stream);
+  int rc = sp::use_umma(sp::kFprop, p, precision) ? sp::launch_igemm_umma(sp::kFprop, p, st)
+                                                   : sp::launch_igemm_simt(sp::kFprop, p, st);
+  if (rc) return rc;
+  SP_CHECK_LAUNCH("conv2d_fprop");
+  return 0;
+}
+
+int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_geom* g,
+                    int precision, sp_stream_t stream) {
+  if (int rc = sp::check_geom(g)) return rc;
+  sp::IgemmParams p = sp::base_params();
+  p.g = *g;
+  p.M = (int64_t)g->N * g->H * g->W;
+  p.N = g->C;
+  p.K = (int64_t)g->KH * g->KW * g->K;
+  p.A = gy;
+  p.B = w;
+  p.C = dx;
+  p.ldc = g->C;
+  if (p.M == 0) return 0;
+  if ((int64_t)g->OH * g->OW == 0) return sp_fill_f32(dx, p.M * p.N, 0.f, stream);
+  cudaStream_t st = sp::as_stream(stream);
+  int rc = sp::use_umma(sp::kDgrad, p, precision) ? sp::launch_igemm_umma(sp::kDgrad, p, st)
+                                                   : sp::launch_igemm_simt(sp::kDgrad, p, st);
+  if (rc) return rc;
+  SP_CHECK_LAUNCH("conv2d_dgrad");
+  return 0;
+}
+
+size_t sp_conv2d_wgrad_workspace(const sp_conv_geom* g, int precision) {
+  if (!g || sp::check_geom(g)) return 0;
+  sp::IgemmParams p = sp::base_params();
+  p.g = *g;
+  p.M = (int64_t)g->KH * g->KW * g->C;
+  p.N = g->K;
+  p.K = (int64_t)g->N * g->OH * g->OW;
+  if (p.K <= 0) return 0;
+  int splits;
+  int64_t chunk;
+  sp::wgrad_split(*g, sp::use_umma(sp::kWgrad, p, precision), &splits, &chunk);
+  return splits > 1 ? (size_t)splits * p.M * p.N * sizeof(float) : 0;
+}
+
+int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_geom* g,
+                    int precision, void* workspace, size_t workspace_bytes, sp_stream_t stream) {
+  if (int rc = sp::check_geom(g)) return rc;
+  sp::IgemmParams p = sp::base_params();
+  p.g = *g;
+  p.M = (int64_t)g->KH * g->KW * g->C;
+  p.N = g->K;
+  p.K = (int64_t)g->N * g->OH * g->OW;
+  p.A = x;
+  p.B = gy;
+  p.C = dw;
+  p.ldc = g->K;
+  if (p.K == 0) return sp_fill_f32(dw, p.M * p.N, 0.f, stream);
+  const bool umma = sp::use_umma(sp::kWgrad, p, precision);
+  int splits;
+  int64_t chunk;
+  sp::wgrad_split(*g, umma, &splits, &chunk);
+  cudaStream_t st = sp::as_stream(stream);
+  if (splits > 1) {
+    const size_t need = (size_t)splits * p.M * p.N * sizeof(float);
+    if (!workspace || workspace_bytes < need)
+      return sp::set_error(SP_ERR_WORKSPACE, "conv2d_wgrad: workspace %zu < required %zu",
+                           workspace_bytes, need);
+    p.k_splits = splits;
+    p.k_chunk = chunk;
+    p.split_stride_c = p.M * p.N;
+    p.C = static_cast<float*>(workspace);
+  }
+  int rc = umma ? sp::launch_igemm_umma(sp::kWgrad, p, st) : sp::launch_igemm_simt(sp::kWgrad, p, st);
+  if (rc) return rc;
+  SP_CHECK_LAUNCH("conv2d_wgrad");
+  if (splits > 1) {
+    // fixed-order sum of the per-split partial filters: [splits, M*N] -> [M*N]
+    rc = sp_reduce_sum(static_cast<const float*>(workspace), dw, 1, splits, p.M * p.N, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,428 @@
+// Elementwise kernels: 128-bit vectorised grid-stride loops for the contiguous cases on the
+// training path (leaky_relu, bias add, gradient accumulate), a strided fallback for
+// arbitrary NumPy-style broadcasting (sp.py:659-684).  All HBM-bound: one read per
+// operand, one write, no shared memory (no reuse to exploit).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Dims {
+  int ndim;
+  int64_t shape[SP_MAX_DIMS];
+  int64_t s0[SP_MAX_DIMS];  // operand strides (elements); 0 = broadcast
+  int64_t s1[SP_MAX_DIMS];
+  int64_t s2[SP_MAX_DIMS];
+  int64_t so[SP_MAX_DIMS];  // output strides
+};
+
+// Drop size-1 dims and merge neighbours that are jointly contiguous for every operand.
+Dims collapse(int ndim, const int64_t* shape, const int64_t* s0, const int64_t* s1,
+              const int64_t* s2, const int64_t* so) {
+  Dims d;
+  d.ndim = 0;
+  auto get = [](const int64_t* s, int i) { return s ? s[i] : 0; };
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] == 1) continue;
+    const int64_t a = get(s0, i), b = get(s1, i), c = get(s2, i), o = get(so, i);
+    if (d.ndim > 0) {
+      const int j = d.ndim - 1;
+      if (d.s0[j] == a * shape[i] && d.s1[j] == b * shape[i] && d.s2[j] == c * shape[i] &&
+          d.so[j] == o * shape[i]) {
+        d.shape[j] *= shape[i];
+        d.s0[j] = a;
+        d.s1[j] = b;
+        d.s2[j] = c;
+        d.so[j] = o;
+        continue;
+      }
+    }
+    d.shape[d.ndim] = shape[i];
+    d.s0[d.ndim] = a;
+    d.s1[d.ndim] = b;
+    d.s2[d.ndim] = c;
+    d.so[d.ndim] = o;
+    ++d.ndim;
+  }
+  if (d.ndim == 0) {
+    d.ndim = 1;
+    d.shape[0] = 1;
+    d.s0[0] = d.s1[0] = d.s2[0] = d.so[0] = 0;
+  }
+  return d;
+}
+
+void contiguous_strides(int ndim, const int64_t* shape, int64_t* out) {
+  int64_t s = 1;
+  for (int i = ndim - 1; i >= 0; --i) {
+    out[i] = s;
+    s *= shape[i];
+  }
+}
+
+template <int OP>
+__device__ __forceinline__ float unary_op(float x, float p) {
+  if (OP == SP_UNARY_EXP) return expf(x);
+  if (OP == SP_UNARY_LOG) return logf(x);
+  if (OP == SP_UNARY_NEG) return -x;
+  if (OP == SP_UNARY_SQUARE) return x * x;
+  if (OP == SP_UNARY_SCALE) return p * x;
+  if (OP == SP_UNARY_ADD_SCALAR) return x + p;
+  if (OP == SP_UNARY_RECIP) return p / x;
+  if (OP == SP_UNARY_SQRT) return sqrtf(x);
+  return x;
+}
+
+template <int OP>
+__device__ __forceinline__ float binary_op(float a, float b) {
+  if (OP == SP_BINARY_ADD) return a + b;
+  if (OP == SP_BINARY_SUB) return a - b;
+  if (OP == SP_BINARY_MUL) return a * b;
+  if (OP == SP_BINARY_DIV) return a / b;
+  if (OP == SP_BINARY_DIV_GRAD_B) return -a / (b * b);
+  if (OP == SP_BINARY_EXP_MUL) return a * expf(b);
+  return a;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads) unary_kernel(const float* __restrict__ x,
+                                                         float* __restrict__ y, int64_t n,
+                                                         float p, bool vec) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 v = ld_stream_f4(x + 4 * i);
+      v.x = unary_op<OP>(v.x, p);
+      v.y = unary_op<OP>(v.y, p);
+      v.z = unary_op<OP>(v.z, p);
+      v.w = unary_op<OP>(v.w, p);
+      reinterpret_cast<float4*>(y)[i] = v;
+    }
+    done = n4 << 2;
+  }
+  for (int64_t i = done + tid; i < n; i += stride) y[i] = unary_op<OP>(x[i], p);
+}
+
+// same-shape contiguous operands
+template <int OP>
+__global__ void __launch_bounds__(kThreads) binary_flat_kernel(const float* __restrict__ a,
+                                                               const float* __restrict__ b,
+                                                               float* __restrict__ out,
+                                                               int64_t n, bool vec) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 p = ld_stream_f4(a + 4 * i), q = ld_stream_f4(b + 4 * i);
+      float4 r;
+      r.x = binary_op<OP>(p.x, q.x);
+      r.y = binary_op<OP>(p.y, q.y);
+      r.z = binary_op<OP>(p.z, q.z);
+      r.w = binary_op<OP>(p.w, q.w);
+      reinterpret_cast<float4*>(out)[i] = r;
+    }
+    done = n4 << 2;
+  }
+  for (int64_t i = done + tid; i < n; i += stride) out[i] = binary_op<OP>(a[i], b[i]);
+}
+
+// [rows, cols] OP [cols]  (bias add: sp.py:634 `matmul(a, weights) + bias`), cols % 4 == 0.
+// `swap` evaluates OP(row_vector, matrix) instead.
+template <int OP>
+__global__ void __launch_bounds__(kThreads) binary_rowvec_kernel(const float* __restrict__ a,
+                                                                 const float* __restrict__ v,
+                                                                 float* __restrict__ out,
+                                                                 int64_t rows, int64_t cols4,
+                                                                 bool swap) {
+  const int64_t total = rows * cols4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t c4 = i % cols4;
+    const float4 p = ld_stream_f4(a + 4 * i);
+    const float4 q = __ldg(reinterpret_cast<const float4*>(v) + c4);
+    float4 r;
+    if (!swap) {
+      r.x = binary_op<OP>(p.x, q.x);
+      r.y = binary_op<OP>(p.y, q.y);
+      r.z = binary_op<OP>(p.z, q.z);
+      r.w = binary_op<OP>(p.w, q.w);
+    } else {
+      r.x = binary_op<OP>(q.x, p.x);
+      r.y = binary_op<OP>(q.y, p.y);
+      r.z = binary_op<OP>(q.z, p.z);
+      r.w = binary_op<OP>(q.w, p.w);
+    }
+    reinterpret_cast<float4*>(out)[i] = r;
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads) binary_strided_kernel(const float* __restrict__ a,
+                                                                  const float* __restrict__ b,
+                                                                  float* __restrict__ out,
+                                                                  int64_t n, Dims d) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t rem = i, oa = 0, ob = 0;
+#pragma unroll 1
+    for (int k = d.ndim - 1; k >= 0; --k) {
+      const int64_t q = rem / d.shape[k];
+      const int64_t c = rem - q * d.shape[k];
+      oa += c * d.s0[k];
+      ob += c * d.s1[k];
+      rem = q;
+    }
+    out[i] = binary_op<OP>(a[oa], b[ob]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) where_strided_kernel(const uint8_t* __restrict__ c,
+                                                                 const float* __restrict__ a,
+                                                                 const float* __restrict__ b,
+                                                                 float* __restrict__ out,
+                                                                 int64_t n, Dims d) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t rem = i, oc = 0, oa = 0, ob = 0;
+#pragma unroll 1
+    for (int k = d.ndim - 1; k >= 0; --k) {
+      const int64_t q = rem / d.shape[k];
+      const int64_t r = rem - q * d.shape[k];
+      oc += r * d.s0[k];
+      oa += r * d.s1[k];
+      ob += r * d.s2[k];
+      rem = q;
+    }
+    out[i] = c[oc] ? a[oa] : b[ob];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) strided_copy_kernel(const float* __restrict__ src,
+                                                                float* __restrict__ dst,
+                                                                int64_t n, Dims d) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t rem = i, os = 0, od = 0;
+#pragma unroll 1
+    for (int k = d.ndim - 1; k >= 0; --k) {
+      const int64_t q = rem / d.shape[k];
+      const int64_t r = rem - q * d.shape[k];
+      os += r * d.s0[k];
+      od += r * d.so[k];
+      rem = q;
+    }
+    dst[od] = src[os];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) accumulate_kernel(float* __restrict__ dst,
+                                                              const float* __restrict__ src,
+                                                              int64_t n, bool vec) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 d = reinterpret_cast<float4*>(dst)[i];
+      const float4 s = ld_stream_f4(src + 4 * i);
+      d.x += s.x;
+      d.y += s.y;
+      d.z += s.z;
+      d.w += s.w;
+      reinterpret_cast<float4*>(dst)[i] = d;
+    }
+    done = n4 << 2;
+  }
+  for (int64_t i = done + tid; i < n; i += stride) dst[i] += src[i];
+}
+
+__global__ void __launch_bounds__(kThreads) leaky_fwd_kernel(const float* __restrict__ x,
+                                                             float* __restrict__ y, int64_t n,
+                                                             float alpha, bool vec) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 v = ld_stream_f4(x + 4 * i);
+      // x > 0 ? 1 : alpha  (x == 0 and NaN take the alpha branch, as np.where(a > 0, ...))
+      v.x *= (v.x > 0.f) ? 1.f : alpha;
+      v.y *= (v.y > 0.f) ? 1.f : alpha;
+      v.z *= (v.z > 0.f) ? 1.f : alpha;
+      v.w *= (v.w > 0.f) ? 1.f : alpha;
+      reinterpret_cast<float4*>(y)[i] = v;
+    }
+    done = n4 << 2;
+  }
+  for (int64_t i = done + tid; i < n; i += stride) {
+    const float v = x[i];
+    y[i] = v * ((v > 0.f) ? 1.f : alpha);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) leaky_bwd_kernel(const float* __restrict__ g,
+                                                             const float* __restrict__ x,
+                                                             float* __restrict__ dx, int64_t n,
+                                                             float alpha, bool vec) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 v = ld_stream_f4(x + 4 * i);
+      float4 r = ld_stream_f4(g + 4 * i);
+      r.x *= (v.x > 0.f) ? 1.f : alpha;
+      r.y *= (v.y > 0.f) ? 1.f : alpha;
+      r.z *= (v.z > 0.f) ? 1.f : alpha;
+      r.w *= (v.w > 0.f) ? 1.f : alpha;
+      reinterpret_cast<float4*>(dx)[i] = r;
+    }
+    done = n4 << 2;
+  }
+  for (int64_t i = done + tid; i < n; i += stride) dx[i] = g[i] * ((x[i] > 0.f) ? 1.f : alpha);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// 8 resident blocks of 256 threads per SM, 4 float4 per thread per trip
+inline int ew_grid(int64_t n) { return sp::wave_grid(n, kThreads * 16, 8); }
+
+template <int OP>
+int launch_unary(const float* x, float* y, int64_t n, float p, cudaStream_t st) {
+  const bool vec = aligned16(x) && aligned16(y);
+  unary_kernel<OP><<<ew_grid(n), kThreads, 0, st>>>(x, y, n, p, vec);
+  return 0;
+}
+
+template <int OP>
+int launch_binary(const float* a, const float* b, float* out, const Dims& d, cudaStream_t st) {
+  int64_t n = 1;
+  for (int i = 0; i < d.ndim; ++i) n *= d.shape[i];
+  const bool al = aligned16(a) && aligned16(b) && aligned16(out);
+  if (d.ndim == 1 && d.s0[0] == 1 && d.s1[0] == 1) {
+    binary_flat_kernel<OP><<<ew_grid(n), kThreads, 0, st>>>(a, b, out, n, al);
+  } else if (d.ndim == 2 && al && d.shape[1] % 4 == 0 && d.s0[1] == 1 && d.s1[1] == 1 &&
+             d.s0[0] == d.shape[1] && d.s1[0] == 0) {
+    binary_rowvec_kernel<OP><<<ew_grid(n), kThreads, 0, st>>>(a, b, out, d.shape[0],
+                                                            d.shape[1] / 4, false);
+  } else if (d.ndim == 2 && al && d.shape[1] % 4 == 0 && d.s0[1] == 1 && d.s1[1] == 1 &&
+             d.s1[0] == d.shape[1] && d.s0[0] == 0) {
+    binary_rowvec_kernel<OP><<<ew_grid(n), kThreads, 0, st>>>(b, a, out, d.shape[0],
+                                                            d.shape[1] / 4, true);
+  } else {
+    binary_strided_kernel<OP><<<ew_grid(n), kThreads, 0, st>>>(a, b, out, n, d);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sp_ewise_unary(int op, const float* x, float* y, int64_t n, float param,
+                   sp_stream_t stream) {
+  if (n <= 0) return 0;
+  cudaStream_t st = sp::as_stream(stream);
+  switch (op) {
+    case SP_UNARY_EXP: launch_unary<SP_UNARY_EXP>(x, y, n, param, st); break;
+    case SP_UNARY_LOG: launch_unary<SP_UNARY_LOG>(x, y, n, param, st); break;
+    case SP_UNARY_NEG: launch_unary<SP_UNARY_NEG>(x, y, n, param, st); break;
+    case SP_UNARY_SQUARE: launch_unary<SP_UNARY_SQUARE>(x, y, n, param, st); break;
+    case SP_UNARY_SCALE: launch_unary<SP_UNARY_SCALE>(x, y, n, param, st); break;
+    case SP_UNARY_ADD_SCALAR: launch_unary<SP_UNARY_ADD_SCALAR>(x, y, n, param, st); break;
+    case SP_UNARY_RECIP: launch_unary<SP_UNARY_RECIP>(x, y, n, param, st); break;
+    case SP_UNARY_SQRT: launch_unary<SP_UNARY_SQRT>(x, y, n, param, st); break;
+    case SP_UNARY_COPY: launch_unary<SP_UNARY_COPY>(x, y, n, param, st); break;
+    default: return sp::set_error(SP_ERR_INVALID_ARGUMENT, "sp_ewise_unary: unknown op %d", op);
+  }
+  SP_CHECK_LAUNCH("ewise_unary");
+  return 0;
+}
+
+int sp_ewise_binary(int op, const float* a, const int64_t* stride_a, const float* b,
+                    const int64_t* stride_b, float* out, int ndim, const int64_t* shape,
+                    sp_stream_t stream) {
+  SP_REQUIRE(ndim >= 0 && ndim <= SP_MAX_DIMS, "ndim out of range");
+  int64_t so[SP_MAX_DIMS];
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  if (n <= 0) return 0;
+  contiguous_strides(ndim, shape, so);
+  const Dims d = collapse(ndim, shape, stride_a, stride_b, nullptr, so);
+  cudaStream_t st = sp::as_stream(stream);
+  switch (op) {
+    case SP_BINARY_ADD: launch_binary<SP_BINARY_ADD>(a, b, out, d, st); break;
+    case SP_BINARY_SUB: launch_binary<SP_BINARY_SUB>(a, b, out, d, st); break;
+    case SP_BINARY_MUL: launch_binary<SP_BINARY_MUL>(a, b, out, d, st); break;
+    case SP_BINARY_DIV: launch_binary<SP_BINARY_DIV>(a, b, out, d, st); break;
+    case SP_BINARY_DIV_GRAD_B: launch_binary<SP_BINARY_DIV_GRAD_B>(a, b, out, d, st); break;
+    case SP_BINARY_EXP_MUL: launch_binary<SP_BINARY_EXP_MUL>(a, b, out, d, st); break;
+    default: return sp::set_error(SP_ERR_INVALID_ARGUMENT, "sp_ewise_binary: unknown op %d", op);
+  }
+  SP_CHECK_LAUNCH("ewise_binary");
+  return 0;
+}
+
+int sp_accumulate(float* dst, const float* src, int64_t n, sp_stream_t stream) {
+  if (n <= 0) return 0;
+  accumulate_kernel<<<ew_grid(n), kThreads, 0, sp::as_stream(stream)>>>(
+      dst, src, n, aligned16(dst) && aligned16(src));
+  SP_CHECK_LAUNCH("accumulate");
+  return 0;
+}
+
+int sp_leaky_relu_fwd(const float* x, float* y, int64_t n, float alpha, sp_stream_t stream) {
+  if (n <= 0) return 0;
+  leaky_fwd_kernel<<<ew_grid(n), kThreads, 0, sp::as_stream(stream)>>>(
+      x, y, n, alpha, aligned16(x) && aligned16(y));
+  SP_CHECK_LAUNCH("leaky_relu_fwd");
+  return 0;
+}
+
+int sp_leaky_relu_bwd(const float* g, const float* x, float* dx, int64_t n, float alpha,
+                      sp_stream_t stream) {
+  if (n <= 0) return 0;
+  leaky_bwd_kernel<<<ew_grid(n), kThreads, 0, sp::as_stream(stream)>>>(
+      g, x, dx, n, alpha, aligned16(g) && aligned16(x) && aligned16(dx));
+  SP_CHECK_LAUNCH("leaky_relu_bwd");
+  return 0;
+}
+
+int sp_where(const uint8_t* cond, const int64_t* stride_c, const float* a,
+             const int64_t* stride_a, const float* b, const int64_t* stride_b, float* out,
+             int ndim, const int64_t* shape, sp_stream_t stream) {
+  SP_REQUIRE(ndim >= 0 && ndim <= SP_MAX_DIMS, "ndim out of range");
+  int64_t so[SP_MAX_DIMS];
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  if (n <= 0) return 0;
+  contiguous_strides(ndim, shape, so);
+  const Dims d = collapse(ndim, shape, stride_c, stride_a, stride_b, so);
+  where_strided_kernel<<<ew_grid(n), kThreads, 0, sp::as_stream(stream)>>>(cond, a, b, out, n, d);
+  SP_CHECK_LAUNCH("where");
+  return 0;
+}
+
+int sp_strided_copy(const float* src, const int64_t* stride_src, float* dst,
+                    const int64_t* stride_dst, int ndim, const int64_t* shape,
+                    sp_stream_t stream) {
+  SP_REQUIRE(ndim >= 0 && ndim <= SP_MAX_DIMS, "ndim out of range");
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  if (n <= 0) return 0;
+  const Dims d = collapse(ndim, shape, stride_src, nullptr, nullptr, stride_dst);
+  strided_copy_kernel<<<ew_grid(n), kThreads, 0, sp::as_stream(stream)>>>(src, dst, n, d);
+  SP_CHECK_LAUNCH("strided_copy");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// Implicit-GEMM problem description shared by the CUDA-core (fp32) and tcgen05 (tf32)
+// contraction kernels.  Every contraction on the SmallPebble hot path is
+//     C[m, n] = sum_k A(m, k) * B(k, n)
+// where A and B are either dense strided matrices (matmul and its gradients,
+// sp.py:239-247) or *virtual* im2col matrices gathered on the fly from NHWC tensors
+// (conv2d forward / input gradient / filter gradient, sp.py:124-163 with the closures of
+// 244-245, 384-387, 325-327).  Nothing is ever materialised: the reference's patch matrix
+// (24.9-49.8 MB per CIFAR layer in float64) never exists in HBM.
+//
+//  mode   | M          | N    | K           | A(m,k)                          | B(k,n)
+//  GEMM   | rows       | cols | inner       | A[m*a_rs + k*a_cs]              | B[k*b_rs + n*b_cs]
+//  FPROP  | N*OH*OW    | Kout | KH*KW*C     | x[n, oy*sy+dy-pt, ox*sx+dx-pl, c] | w[k, n]
+//  DGRAD  | N*H*W      | C    | KH*KW*Kout  | gy[n, (iy+pt-dy)/sy, (ix+pl-dx)/sx, ko] | w[dy,dx,n,ko]
+//  WGRAD  | KH*KW*C    | Kout | N*OH*OW     | x[...] (transposed im2col)       | gy[k, n]
+// Out-of-image taps (SAME padding, sp.py:721-761) and non-divisible strides read as 0.
+#pragma once
+
+#include "common.cuh"
+
+namespace sp {
+
+enum IgemmMode : int { kGemm = 0, kFprop = 1, kDgrad = 2, kWgrad = 3 };
+
+struct IgemmParams {
+  int64_t M, N, K;
+  const float* A;
+  const float* B;
+  float* C;
+  int64_t ldc;
+  // dense operand strides (kGemm)
+  int64_t a_rs, a_cs, b_rs, b_cs;
+  // strided batch (kGemm): blockIdx.z selects the batch
+  int64_t batch, batch_a, batch_b, batch_c;
+  // split-K (wgrad): blockIdx.z selects the K slice, partial tiles go to
+  // C + z * split_stride_c and are summed by a deterministic second pass
+  int k_splits;
+  int64_t k_chunk;  // multiple of the kernel's K tile
+  int64_t split_stride_c;
+  sp_conv_geom g;
+};
+
+int launch_igemm_simt(int mode, const IgemmParams& p, cudaStream_t stream);
+int launch_igemm_umma(int mode, const IgemmParams& p, cudaStream_t stream);
+// true when the tcgen05 kernel supports this problem (shape / alignment constraints)
+bool igemm_umma_supported(int mode, const IgemmParams& p);
+
+}  // namespace sp

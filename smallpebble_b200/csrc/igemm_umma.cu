@@ -1,0 +1,658 @@
+// tcgen05 implicit GEMM for sm_100a (SP_PRECISION_TF32): conv2d fprop / dgrad / wgrad and
+// (batched) matmul NN / NT / TN on 5th-generation tensor cores.
+//
+//   * one CTA = one 128 x BN output tile; accumulator lives in TMEM (BN fp32 columns,
+//     128 lanes), written by tcgen05.mma.cta_group::1.kind::tf32 (UMMA 128 x BN x 8)
+//     issued by ONE elected thread (warp 4);
+//   * operands are staged in shared memory in the canonical 128-byte-swizzled UMMA layouts
+//     (K-major or MN-major, chosen so that the global-memory-contiguous index is the
+//     contiguous index of the smem atom): 4-stage ring, 32 k-values (one swizzle row) per
+//     stage;
+//   * warps 0-3 are GATHER PRODUCERS: they build the (virtual) im2col / transposed-im2col /
+//     strided-matrix tiles with 16-byte cp.async (zero-fill for padding, image borders,
+//     stride holes and tails), make them visible to the async proxy
+//     (fence.proxy.async) and signal `full[stage]` mbarriers; tcgen05.commit releases a
+//     stage back through `empty[stage]`.  The im2col matrix is never materialised;
+//   * the same four warps then become the epilogue: tcgen05.ld 32x32b.x32 (one TMEM lane
+//     quadrant per warp) -> registers -> global.
+//
+// Why gather producers rather than TMA im2col descriptors: the path must take every
+// geometry the reference takes (C = 3 / 2 / 5, 13x22 kernels, stride 10, asymmetric
+// strides; ref tests/test_smallpebble.py:257-307) and the dgrad / wgrad operand patterns
+// (stride holes, transposed patches) have no TMA mode; cp.async with src-size zero-fill
+// expresses all of them with one mechanism.  TMA-tiled loads for the dense-matrix operands
+// are a later optimisation.
+#include "igemm.cuh"
+
+namespace sp {
+namespace {
+
+constexpr int BM = 128;            // UMMA M (cta_group::1)
+constexpr int BK = 32;             // fp32 values per stage row = 128 B = one swizzle span
+constexpr int kStages = 4;
+constexpr int kLookahead = 3;      // cp.async groups in flight per producer thread
+constexpr int kProducers = 128;    // warps 0-3
+constexpr int kThreads = 160;      // + warp 4: TMEM allocator and MMA issuer
+constexpr uint32_t kATileBytes = BM * BK * 4;  // 16 KB
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n)
+               : "memory");
+}
+
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n)
+               : "memory");
+}
+
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// generic-proxy writes (cp.async landed data) -> visible to the async proxy (tcgen05.mma)
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp SmemDescriptor / InstrDescriptor)
+// ---------------------------------------------------------------------------------------
+// 128B-swizzled operand tile.  K-major: rows of 128 B (32 k-values), 8-row groups 1024 B
+// apart (SBO).  MN-major: atoms of [8 k-rows][32 mn-values], next atom along MN `lbo` bytes
+// away, next 8-k group `sbo` bytes away.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);             // [0,14)  start address >> 4
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;    // [16,30) leading byte offset >> 4
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;    // [32,46) stride byte offset >> 4
+  d |= 1ull << 46;                                      // [46,48) descriptor version (sm_100)
+  d |= 2ull << 61;                                      // [61,64) SWIZZLE_128B
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int bn, bool a_mn, bool b_mn) {
+  return (1u << 4)                       // [4,6)   D format  = F32
+         | (2u << 7)                     // [7,10)  A format  = TF32
+         | (2u << 10)                    // [10,13) B format  = TF32
+         | ((a_mn ? 1u : 0u) << 15)      // [15]    A major   (0 = K, 1 = MN)
+         | ((b_mn ? 1u : 0u) << 16)      // [16]    B major
+         | ((uint32_t)(bn >> 3) << 17)   // [17,23) N >> 3
+         | ((uint32_t)(BM >> 4) << 24);  // [24,29) M >> 4
+}
+
+// byte offset of 16-byte chunk `c` (0..7) of row `row` in a K-major swizzled tile
+__device__ __forceinline__ uint32_t kmajor_off(int row, int c) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
+}
+// byte offset of 16-byte chunk `mc` (4 mn-values) of k-row `kk` (0..31) in an MN-major tile
+// with `atoms` 32-wide atoms along MN
+__device__ __forceinline__ uint32_t mnmajor_off(int kk, int mc, int atoms) {
+  const int g = kk >> 3, r = kk & 7, j = mc >> 3, cc = mc & 7;
+  return (uint32_t)((g * atoms + j) * 1024 + r * 128 + ((cc ^ r) << 4));
+}
+
+// ---------------------------------------------------------------------------------------
+// producers.  Each fills one operand tile of one stage for the k-block starting at k0.
+// `vec` = 4 consecutive values along the chunk direction are contiguous, 16-byte aligned
+// and uniformly valid (guaranteed by the host, see igemm_umma_supported()).
+// ---------------------------------------------------------------------------------------
+
+// dense matrix, K contiguous:  elem(r, k) = base[r * ld + k],  K-major tile of `rows` rows
+__device__ __forceinline__ void load_dense_kmajor(uint32_t tile, const float* __restrict__ base,
+                                                  int64_t ld, int64_t r0, int64_t r_end,
+                                                  int64_t k0, int64_t k_end, int rows, bool vec,
+                                                  int t) {
+  const int c = t & 7;
+  const int64_t k = k0 + 4 * c;
+  for (int row = t >> 3; row < rows; row += 16) {
+    const uint32_t dst = tile + kmajor_off(row, c);
+    const int64_t r = r0 + row;
+    const float* src = base + r * ld + k;
+    if (vec) {
+      const bool ok = (r < r_end) && (k < k_end);
+      cp_async_16(dst, ok ? src : base, ok);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = (r < r_end) && (k + e < k_end);
+        cp_async_4(dst + 4 * e, ok ? src + e : base, ok);
+      }
+    }
+  }
+}
+
+// dense matrix, MN contiguous: elem(r, k) = base[k * ld + r], MN-major tile of `rows` rows
+__device__ __forceinline__ void load_dense_mnmajor(uint32_t tile, const float* __restrict__ base,
+                                                   int64_t ld, int64_t r0, int64_t r_end,
+                                                   int64_t k0, int64_t k_end, int rows, bool vec,
+                                                   int t) {
+  const int chunks = rows >> 2;  // 16-byte chunks per k-row (8, 16, 32 or 64)
+  const int atoms = rows >> 5;
+  const int total = chunks * BK;
+  for (int q = t; q < total; q += kProducers) {
+    const int kk = q / chunks, mc = q - kk * chunks;
+    const uint32_t dst = tile + mnmajor_off(kk, mc, atoms);
+    const int64_t k = k0 + kk, r = r0 + 4 * mc;
+    const float* src = base + k * ld + r;
+    if (vec) {
+      const bool ok = (k < k_end) && (r < r_end);
+      cp_async_16(dst, ok ? src : base, ok);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = (k < k_end) && (r + e < r_end);
+        cp_async_4(dst + 4 * e, ok ? src + e : base, ok);
+      }
+    }
+  }
+}
+
+// per-thread description of the 8 tile rows a producer thread owns in a K-major A tile
+struct PixelRows {
+  int y[8];     // fprop: oy*sy - pad_t   | dgrad: iy + pad_t
+  int x[8];     // fprop: ox*sx - pad_l   | dgrad: ix + pad_l
+  int img[8];   // image index, or -1 for rows beyond M
+};
+
+// decompose pixel index m = (n * D1 + a) * D2 + b
+__device__ __forceinline__ void split_pixel(int m, int D1, int D2, int& n, int& a, int& b) {
+  const int q = m / D2;
+  b = m - q * D2;
+  n = q / D1;
+  a = q - n * D1;
+}
+
+// conv fprop A: rows = output pixels, k = (tap, c);  x[n, oy*sy+dy-pt, ox*sx+dx-pl, c]
+__device__ __forceinline__ void load_fprop_a(uint32_t tile, const float* __restrict__ x,
+                                             const sp_conv_geom& g, const PixelRows& pr, int k0,
+                                             int k_end, bool vec, int t) {
+  const int c8 = t & 7;
+  const int rsw = (t >> 3) & 7;
+  const uint32_t dst0 = tile + (uint32_t)((t >> 6) * 1024 + rsw * 128 + ((c8 ^ rsw) << 4));
+  const int k = k0 + 4 * c8;
+  if (vec) {
+    const int tap = k / g.C, ch = k - tap * g.C;
+    const int dy = tap / g.KW, dx = tap - dy * g.KW;
+    const bool kok = k < k_end;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int iy = pr.y[i] + dy, ix = pr.x[i] + dx;
+      const bool ok = kok && pr.img[i] >= 0 && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+      const float* src = x + (((int64_t)pr.img[i] * g.H + iy) * g.W + ix) * g.C + ch;
+      cp_async_16(dst0 + i * 2048, ok ? src : x, ok);
+    }
+  } else {
+#pragma unroll 1
+    for (int e = 0; e < 4; ++e) {
+      const int ke = k + e;
+      const int tap = ke / g.C, ch = ke - tap * g.C;
+      const int dy = tap / g.KW, dx = tap - dy * g.KW;
+      const bool kok = ke < k_end;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int iy = pr.y[i] + dy, ix = pr.x[i] + dx;
+        const bool ok = kok && pr.img[i] >= 0 && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+        const float* src = x + (((int64_t)pr.img[i] * g.H + iy) * g.W + ix) * g.C + ch;
+        cp_async_4(dst0 + i * 2048 + 4 * e, ok ? src : x, ok);
+      }
+    }
+  }
+}
+
+// conv dgrad A: rows = input pixels, k = (tap, ko);
+// gy[n, (iy+pt-dy)/sy, (ix+pl-dx)/sx, ko] when both divisions are exact and in range
+__device__ __forceinline__ void load_dgrad_a(uint32_t tile, const float* __restrict__ gy,
+                                             const sp_conv_geom& g, const PixelRows& pr, int k0,
+                                             int k_end, bool vec, int t) {
+  const int c8 = t & 7;
+  const int rsw = (t >> 3) & 7;
+  const uint32_t dst0 = tile + (uint32_t)((t >> 6) * 1024 + rsw * 128 + ((c8 ^ rsw) << 4));
+  const int k = k0 + 4 * c8;
+  const int nvals = vec ? 1 : 4;
+#pragma unroll 1
+  for (int e = 0; e < nvals; ++e) {
+    const int ke = k + e;
+    const int tap = ke / g.K, ko = ke - tap * g.K;
+    const int dy = tap / g.KW, dx = tap - dy * g.KW;
+    const bool kok = ke < k_end;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ty = pr.y[i] - dy, tx = pr.x[i] - dx;
+      const int oy = ty / g.sy, ox = tx / g.sx;
+      const bool ok = kok && pr.img[i] >= 0 && ty >= 0 && tx >= 0 && oy * g.sy == ty &&
+                      ox * g.sx == tx && oy < g.OH && ox < g.OW;
+      const float* src = gy + (((int64_t)pr.img[i] * g.OH + oy) * g.OW + ox) * g.K + ko;
+      if (vec)
+        cp_async_16(dst0 + i * 2048, ok ? src : gy, ok);
+      else
+        cp_async_4(dst0 + i * 2048 + 4 * e, ok ? src : gy, ok);
+    }
+  }
+}
+
+// conv dgrad B: rows = input channel c, k = (tap, ko);  w[tap, c, ko]   (K-major tile)
+__device__ __forceinline__ void load_dgrad_b(uint32_t tile, const float* __restrict__ w,
+                                             const sp_conv_geom& g, int c0, int k0, int k_end,
+                                             int rows, bool vec, int t) {
+  const int c8 = t & 7;
+  const int k = k0 + 4 * c8;
+  const int nvals = vec ? 1 : 4;
+#pragma unroll 1
+  for (int e = 0; e < nvals; ++e) {
+    const int ke = k + e;
+    const int tap = ke / g.K, ko = ke - tap * g.K;
+    const bool kok = ke < k_end;
+    for (int row = t >> 3; row < rows; row += 16) {
+      const uint32_t dst = tile + kmajor_off(row, c8);
+      const int c = c0 + row;
+      const bool ok = kok && c < g.C;
+      const float* src = w + ((int64_t)tap * g.C + c) * g.K + ko;
+      if (vec)
+        cp_async_16(dst, ok ? src : w, ok);
+      else
+        cp_async_4(dst + 4 * e, ok ? src : w, ok);
+    }
+  }
+}
+
+// conv wgrad A: rows (MN) = (tap, c), k = output pixel;  MN-major 128-row tile.
+// Thread owns mn-chunk mc = t & 31 (fixed (tap, c)) and k-rows kk = 4*i + (t >> 5).
+__device__ __forceinline__ void load_wgrad_a(uint32_t tile, const float* __restrict__ x,
+                                             const sp_conv_geom& g, int m0, int m_end, int k0,
+                                             int k_end, bool vec, int t) {
+  const int mc = t & 31, w4 = t >> 5;
+  const int nvals = vec ? 1 : 4;
+#pragma unroll 1
+  for (int e = 0; e < nvals; ++e) {
+    const int m = m0 + 4 * mc + e;
+    const int tap = m / g.C, ch = m - tap * g.C;
+    const int dy = tap / g.KW, dx = tap - dy * g.KW;
+    const bool mok = m < m_end;
+    int n, oy, ox;
+    split_pixel(k0 + w4, g.OH, g.OW, n, oy, ox);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int kk = 4 * i + w4;
+      const uint32_t dst = tile + mnmajor_off(kk, mc, 4);
+      const int iy = oy * g.sy + dy - g.pad_t, ix = ox * g.sx + dx - g.pad_l;
+      const bool ok = mok && (k0 + kk < k_end) && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+      const float* src = x + (((int64_t)n * g.H + iy) * g.W + ix) * g.C + ch;
+      if (vec)
+        cp_async_16(dst, ok ? src : x, ok);
+      else
+        cp_async_4(dst + 4 * e, ok ? src : x, ok);
+      // advance 4 output pixels in row-major (n, oy, ox) order
+      ox += 4;
+      while (ox >= g.OW) {
+        ox -= g.OW;
+        if (++oy == g.OH) {
+          oy = 0;
+          ++n;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------
+template <int MODE, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+    igemm_umma_kernel(const __grid_constant__ IgemmParams p, const int bn, const int a_vec,
+                      const int b_vec) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kStages + 1];
+  __shared__ uint32_t tmem_slot;
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B align
+  const uint32_t b_tile_bytes = (uint32_t)bn * BK * 4;
+  const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+  const uint32_t accum_bar = bar0 + 8u * (2 * kStages);
+
+  // ---- tile coordinates, split-K / batch ------------------------------------------------
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int64_t n0 = (int64_t)blockIdx.y * bn;
+  const float* __restrict__ A = p.A;
+  const float* __restrict__ B = p.B;
+  float* __restrict__ C = p.C;
+  int64_t k_begin = 0, k_end = p.K;
+  if (p.k_splits > 1) {
+    k_begin = (int64_t)blockIdx.z * p.k_chunk;
+    k_end = min(p.K, k_begin + p.k_chunk);
+    C += (int64_t)blockIdx.z * p.split_stride_c;
+  } else if (p.batch > 1) {
+    A += (int64_t)blockIdx.z * p.batch_a;
+    B += (int64_t)blockIdx.z * p.batch_b;
+    C += (int64_t)blockIdx.z * p.batch_c;
+  }
+  const int n_it = (k_end > k_begin) ? (int)((k_end - k_begin + BK - 1) / BK) : 0;
+
+  // ---- one-time setup -------------------------------------------------------------------
+  if (t == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), kProducers);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)bn);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 4) {
+    // =========================== PRODUCERS ==============================================
+    PixelRows pr;
+    if (MODE == kFprop || MODE == kDgrad) {
+      const sp_conv_geom& g = p.g;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + i * 16 + (t >> 3);
+        if (m < p.M) {
+          int n, a, b;
+          if (MODE == kFprop) {
+            split_pixel((int)m, g.OH, g.OW, n, a, b);
+            pr.y[i] = a * g.sy - g.pad_t;
+            pr.x[i] = b * g.sx - g.pad_l;
+          } else {
+            split_pixel((int)m, g.H, g.W, n, a, b);
+            pr.y[i] = a + g.pad_t;
+            pr.x[i] = b + g.pad_l;
+          }
+          pr.img[i] = n;
+        } else {
+          pr.y[i] = pr.x[i] = 0;
+          pr.img[i] = -1;
+        }
+      }
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % kStages;
+      if (it >= kStages) mbar_wait(empty_bar(s), (uint32_t)((it / kStages) - 1) & 1u);
+      const uint32_t a_tile = tiles + (uint32_t)s * stage_bytes;
+      const uint32_t b_tile = a_tile + kATileBytes;
+      const int64_t k0 = k_begin + (int64_t)it * BK;
+      // ---- A ----
+      if (MODE == kGemm) {
+        if (A_MN)
+          load_dense_mnmajor(a_tile, A, p.a_cs, m0, p.M, k0, k_end, BM, a_vec, t);
+        else
+          load_dense_kmajor(a_tile, A, p.a_rs, m0, p.M, k0, k_end, BM, a_vec, t);
+      } else if (MODE == kFprop) {
+        load_fprop_a(a_tile, A, p.g, pr, (int)k0, (int)k_end, a_vec, t);
+      } else if (MODE == kDgrad) {
+        load_dgrad_a(a_tile, A, p.g, pr, (int)k0, (int)k_end, a_vec, t);
+      } else {
+        load_wgrad_a(a_tile, A, p.g, (int)m0, (int)p.M, (int)k0, (int)k_end, a_vec, t);
+      }
+      // ---- B ----
+      if (MODE == kGemm) {
+        if (B_MN)
+          load_dense_mnmajor(b_tile, B, p.b_rs, n0, p.N, k0, k_end, bn, b_vec, t);
+        else
+          load_dense_kmajor(b_tile, B, p.b_cs, n0, p.N, k0, k_end, bn, b_vec, t);
+      } else if (MODE == kDgrad) {
+        load_dgrad_b(b_tile, B, p.g, (int)n0, (int)k0, (int)k_end, bn, b_vec, t);
+      } else {
+        // fprop: w[k, n]; wgrad: gy[pixel, n] -- both dense row-major [K, N]
+        load_dense_mnmajor(b_tile, B, p.N, n0, p.N, k0, k_end, bn, b_vec, t);
+      }
+      cp_async_commit();
+      if (it >= kLookahead - 1) {
+        cp_async_wait<kLookahead - 1>();
+        fence_proxy_async();
+        mbar_arrive(full_bar((it - (kLookahead - 1)) % kStages));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int j = max(0, n_it - (kLookahead - 1)); j < n_it; ++j) mbar_arrive(full_bar(j % kStages));
+
+    // =========================== EPILOGUE ===============================================
+    const int64_t m = m0 + t;  // TMEM lane == tile row; warp w owns lanes [32w, 32w+32)
+    if (n_it > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
+    float* __restrict__ crow = C + m * p.ldc;
+    const bool vec_store = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    for (int cb = 0; cb < bn; cb += 32) {
+      if (n0 + cb >= p.N) break;  // warp-uniform
+      uint32_t v[32];
+      if (n_it > 0) {
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (m < p.M) {
+        const int64_t nb = n0 + cb;
+        if (vec_store && nb + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(crow + nb + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) crow[nb + j] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  } else if (t == kProducers) {
+    // =========================== MMA ISSUER (one thread) ================================
+    const uint32_t idesc = instr_desc_tf32(bn, A_MN, B_MN);
+    const uint32_t b_atoms = (uint32_t)bn >> 5;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % kStages;
+      mbar_wait(full_bar(s), (uint32_t)(it / kStages) & 1u);
+      tc_fence_after();
+      const uint32_t a_tile = tiles + (uint32_t)s * stage_bytes;
+      const uint32_t b_tile = a_tile + kATileBytes;
+#pragma unroll
+      for (int k = 0; k < BK / 8; ++k) {
+        // K-major: advance 32 B inside the swizzle row; MN-major: next 8-k group of atoms
+        const uint64_t adesc = A_MN ? smem_desc(a_tile + (uint32_t)k * 4096u, 1024u, 4096u)
+                                    : smem_desc(a_tile + (uint32_t)k * 32u, 16u, 1024u);
+        const uint64_t bdesc =
+            B_MN ? smem_desc(b_tile + (uint32_t)k * b_atoms * 1024u, 1024u, b_atoms * 1024u)
+                 : smem_desc(b_tile + (uint32_t)k * 32u, 16u, 1024u);
+        umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(empty_bar(s));  // stage reusable once these MMAs retire
+    }
+    if (n_it > 0) umma_commit(accum_bar);
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)bn);
+}
+
+int pick_bn(int64_t N) {
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  return 256;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int MODE, bool A_MN, bool B_MN>
+int launch(const IgemmParams& p, cudaStream_t st, bool a_vec, bool b_vec) {
+  const int bn = pick_bn(p.N);
+  const size_t smem = 1024 + (size_t)kStages * (kATileBytes + (size_t)bn * BK * 4);
+  static thread_local bool attr_done = false;  // per kernel instantiation
+  auto kern = igemm_umma_kernel<MODE, A_MN, B_MN>;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         1024 + kStages * (kATileBytes + 256 * BK * 4));
+    if (e != cudaSuccess)
+      return set_error((int)e, "cudaFuncSetAttribute(max dynamic smem) failed: %s",
+                       cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const int64_t z = p.k_splits > 1 ? p.k_splits : (p.batch > 1 ? p.batch : 1);
+  const int64_t gy = (p.N + bn - 1) / bn;
+  if (z > 65535 || gy > 65535) return set_error(SP_ERR_UNSUPPORTED, "igemm_umma: grid too large");
+  dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)gy, (unsigned)z);
+  kern<<<grid, kThreads, smem, st>>>(p, bn, a_vec ? 1 : 0, b_vec ? 1 : 0);
+  return 0;
+}
+
+}  // namespace
+
+bool igemm_umma_supported(int mode, const IgemmParams& p) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return false;
+  if (mode == kGemm) {
+    // each operand must have one unit stride
+    if (!(p.a_cs == 1 || p.a_rs == 1)) return false;
+    if (!(p.b_cs == 1 || p.b_rs == 1)) return false;
+    return true;
+  }
+  // conv index math is 32-bit
+  const sp_conv_geom& g = p.g;
+  const int64_t lim = 0x7fffffffLL;
+  if ((int64_t)g.N * g.H * g.W * g.C > lim || (int64_t)g.N * g.OH * g.OW * g.K > lim) return false;
+  if (p.M > lim || p.K > lim) return false;
+  return true;
+}
+
+int launch_igemm_umma(int mode, const IgemmParams& p, cudaStream_t st) {
+  if (!igemm_umma_supported(mode, p))
+    return set_error(SP_ERR_UNSUPPORTED, "igemm_umma: unsupported problem");
+  const sp_conv_geom& g = p.g;
+  switch (mode) {
+    case kGemm: {
+      const bool a_mn = (p.a_cs != 1);  // a_rs == 1: M contiguous
+      const bool b_mn = (p.b_cs == 1);  // N contiguous
+      const int64_t lda = a_mn ? p.a_cs : p.a_rs;
+      const int64_t ldb = b_mn ? p.b_rs : p.b_cs;
+      const bool batch_ok_a = (p.batch <= 1) || (p.batch_a % 4 == 0);
+      const bool batch_ok_b = (p.batch <= 1) || (p.batch_b % 4 == 0);
+      const bool a_vec = al16(p.A) && lda % 4 == 0 && batch_ok_a && (a_mn ? p.M % 4 == 0 : p.K % 4 == 0);
+      const bool b_vec = al16(p.B) && ldb % 4 == 0 && batch_ok_b && (b_mn ? p.N % 4 == 0 : p.K % 4 == 0);
+      if (!a_mn && !b_mn) return launch<kGemm, false, false>(p, st, a_vec, b_vec);
+      if (!a_mn && b_mn) return launch<kGemm, false, true>(p, st, a_vec, b_vec);
+      if (a_mn && !b_mn) return launch<kGemm, true, false>(p, st, a_vec, b_vec);
+      return launch<kGemm, true, true>(p, st, a_vec, b_vec);
+    }
+    case kFprop:
+      return launch<kFprop, false, true>(p, st, al16(p.A) && g.C % 4 == 0,
+                                         al16(p.B) && g.K % 4 == 0);
+    case kDgrad:
+      return launch<kDgrad, false, false>(p, st, al16(p.A) && g.K % 4 == 0,
+                                          al16(p.B) && g.K % 4 == 0);
+    case kWgrad:
+      return launch<kWgrad, true, true>(p, st, al16(p.A) && g.C % 4 == 0,
+                                        al16(p.B) && g.K % 4 == 0);
+  }
+  return set_error(SP_ERR_INVALID_ARGUMENT, "igemm_umma: unknown mode %d", mode);
+}
+
+}  // namespace sp

@@ -1,0 +1,132 @@
+// Library plumbing: error text, device info, copies, fills, casts.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sp {
+
+char* error_buffer() {
+  static thread_local char buf[512] = "";
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+const DeviceInfo& device_info() {
+  static thread_local DeviceInfo info;
+  static thread_local int cached_dev = -1;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return info;
+  if (dev != cached_dev || !info.ok) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
+      info.sm_count = p.multiProcessorCount;
+      info.cc_major = p.major;
+      info.cc_minor = p.minor;
+      info.ok = true;
+      cached_dev = dev;
+    }
+  }
+  return info;
+}
+
+}  // namespace sp
+
+namespace {
+
+__global__ void fill_f32_kernel(float* __restrict__ dst, int64_t n, float v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const float4 v4 = make_float4(v, v, v, v);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) d4[i] = v4;
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = v;
+}
+
+__global__ void cast_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst,
+                                    int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = (float)src[i];
+}
+
+__global__ void cast_i64_i32_kernel(const int64_t* __restrict__ src, int32_t* __restrict__ dst,
+                                    int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = (int32_t)src[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+int sp_abi_version(void) { return SP_ABI_VERSION; }
+
+const char* sp_last_error(void) { return sp::error_buffer(); }
+
+int sp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  const sp::DeviceInfo& d = sp::device_info();
+  if (!d.ok) return sp::set_error(SP_ERR_DRIVER, "no CUDA device visible");
+  if (sm_count) *sm_count = d.sm_count;
+  if (cc_major) *cc_major = d.cc_major;
+  if (cc_minor) *cc_minor = d.cc_minor;
+  return 0;
+}
+
+int sp_memcpy_h2d(void* dst, const void* host_src, size_t bytes, sp_stream_t stream) {
+  if (bytes == 0) return 0;
+  SP_CHECK_CUDA(cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, sp::as_stream(stream)));
+  return 0;
+}
+
+int sp_memcpy_d2h(void* host_dst, const void* src, size_t bytes, sp_stream_t stream) {
+  if (bytes != 0)
+    SP_CHECK_CUDA(
+        cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, sp::as_stream(stream)));
+  SP_CHECK_CUDA(cudaStreamSynchronize(sp::as_stream(stream)));
+  return 0;
+}
+
+int sp_memcpy_d2d(void* dst, const void* src, size_t bytes, sp_stream_t stream) {
+  if (bytes == 0) return 0;
+  SP_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, sp::as_stream(stream)));
+  return 0;
+}
+
+int sp_fill_f32(float* dst, int64_t n, float value, sp_stream_t stream) {
+  if (n <= 0) return 0;
+  SP_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "dst must be 16-byte aligned");
+  fill_f32_kernel<<<sp::wave_grid(n, 256 * 4 * 4, 8), 256, 0, sp::as_stream(stream)>>>(dst, n, value);
+  SP_CHECK_LAUNCH("fill_f32");
+  return 0;
+}
+
+int sp_cast_f64_f32(const double* src, float* dst, int64_t n, sp_stream_t stream) {
+  if (n <= 0) return 0;
+  cast_f64_f32_kernel<<<sp::wave_grid(n, 256 * 4, 8), 256, 0, sp::as_stream(stream)>>>(src, dst, n);
+  SP_CHECK_LAUNCH("cast_f64_f32");
+  return 0;
+}
+
+int sp_cast_i64_i32(const int64_t* src, int32_t* dst, int64_t n, sp_stream_t stream) {
+  if (n <= 0) return 0;
+  cast_i64_i32_kernel<<<sp::wave_grid(n, 256 * 4, 8), 256, 0, sp::as_stream(stream)>>>(src, dst, n);
+  SP_CHECK_LAUNCH("cast_i64_i32");
+  return 0;
+}
+
+int sp_l2_flush(void* scratch, size_t bytes, sp_stream_t stream) {
+  SP_CHECK_CUDA(cudaMemsetAsync(scratch, 0, bytes, sp::as_stream(stream)));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// Fused multi-tensor Adam / SGD and gradient-bucket packing.  One launch updates every
+// learnable: the per-tensor pointers travel by value in the kernel parameter block, each
+// CUDA block owns one 4096-element chunk of one tensor.  HBM-bound: Adam touches
+// 28 B/param (read p,g,m,v; write p,m,v), all with 128-bit accesses.
+// Replaces the Python loop + ~10 NumPy temporaries per variable of sp.py:573-583.
+#include "common.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+constexpr int kChunk = kThreads * 16;  // elements per block
+constexpr int kMaxTensors = 24;
+
+struct AdamArgs {
+  float* p[kMaxTensors];
+  const float* g[kMaxTensors];
+  float* m[kMaxTensors];
+  float* v[kMaxTensors];
+  int64_t n[kMaxTensors];
+  float inv_c1[kMaxTensors];  // 1 / (1 - beta1^t)
+  float inv_c2[kMaxTensors];  // 1 / (1 - beta2^t)
+  int block_start[kMaxTensors + 1];
+  int count;
+};
+
+struct AxpyArgs {
+  float* p[kMaxTensors];
+  const float* g[kMaxTensors];
+  int64_t n[kMaxTensors];
+  int64_t dst_offset[kMaxTensors];
+  int block_start[kMaxTensors + 1];
+  int count;
+};
+
+template <class Args>
+__device__ __forceinline__ int find_tensor(const Args& a, int block) {
+  int t = 0;
+  while (t + 1 < a.count && block >= a.block_start[t + 1]) ++t;
+  return t;
+}
+
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, float b1, float b2,
+                                      float ic1, float ic2, float alpha, float eps) {
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  p = p - alpha * (m * ic1) / (sqrtf(v * ic2) + eps);
+}
+
+__global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_constant__ AdamArgs a,
+                                                              float alpha, float b1, float b2,
+                                                              float eps) {
+  const int t = find_tensor(a, blockIdx.x);
+  const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * kChunk;
+  const int64_t n = a.n[t];
+  float* __restrict__ p = a.p[t];
+  const float* __restrict__ g = a.g[t];
+  float* __restrict__ m = a.m[t];
+  float* __restrict__ v = a.v[t];
+  const float ic1 = a.inv_c1[t], ic2 = a.inv_c2[t];
+  const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  const int64_t end = min(n, base + kChunk);
+  if (vec) {
+    for (int64_t i = base + 4 * threadIdx.x; i + 3 < end; i += 4 * kThreads) {
+      float4 pp = *reinterpret_cast<float4*>(p + i);
+      const float4 gg = ld_stream_f4(g + i);
+      float4 mm = *reinterpret_cast<float4*>(m + i);
+      float4 vv = *reinterpret_cast<float4*>(v + i);
+      adam1(pp.x, gg.x, mm.x, vv.x, b1, b2, ic1, ic2, alpha, eps);
+      adam1(pp.y, gg.y, mm.y, vv.y, b1, b2, ic1, ic2, alpha, eps);
+      adam1(pp.z, gg.z, mm.z, vv.z, b1, b2, ic1, ic2, alpha, eps);
+      adam1(pp.w, gg.w, mm.w, vv.w, b1, b2, ic1, ic2, alpha, eps);
+      *reinterpret_cast<float4*>(p + i) = pp;
+      *reinterpret_cast<float4*>(m + i) = mm;
+      *reinterpret_cast<float4*>(v + i) = vv;
+    }
+    // tail of a tensor whose length is not a multiple of 4 (only the last chunk has one)
+    const int64_t tail = end - ((end - base) & 3);
+    for (int64_t i = tail + threadIdx.x; i < end; i += kThreads)
+      adam1(p[i], g[i], m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
+  } else {
+    for (int64_t i = base + threadIdx.x; i < end; i += kThreads)
+      adam1(p[i], g[i], m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sgd_multi_kernel(const __grid_constant__ AxpyArgs a,
+                                                             float lr) {
+  const int t = find_tensor(a, blockIdx.x);
+  const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * kChunk;
+  const int64_t end = min(a.n[t], base + kChunk);
+  float* __restrict__ p = a.p[t];
+  const float* __restrict__ g = a.g[t];
+  for (int64_t i = base + threadIdx.x; i < end; i += kThreads) p[i] -= lr * g[i];
+}
+
+// bucket[dst_offset[t] + i] = src[t][i]
+__global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_constant__ AxpyArgs a) {
+  const int t = find_tensor(a, blockIdx.x);
+  const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * kChunk;
+  const int64_t end = min(a.n[t], base + kChunk);
+  float* __restrict__ dst = a.p[t] + a.dst_offset[t];
+  const float* __restrict__ src = a.g[t];
+  for (int64_t i = base + threadIdx.x; i < end; i += kThreads) dst[i] = src[i];
+}
+
+inline int blocks_for(int64_t n) { return (int)((n + kChunk - 1) / kChunk); }
+}  // namespace
+
+extern "C" {
+
+int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_g,
+                  float* const* host_m, float* const* host_v, const int64_t* host_numel,
+                  const int32_t* host_t, float alpha, float beta1, float beta2, float eps,
+                  sp_stream_t stream) {
+  SP_REQUIRE(n_tensors >= 0, "negative tensor count");
+  cudaStream_t st = sp::as_stream(stream);
+  for (int first = 0; first < n_tensors; first += kMaxTensors) {
+    AdamArgs a;
+    a.count = 0;
+    int blocks = 0;
+    for (int i = first; i < n_tensors && i < first + kMaxTensors; ++i) {
+      if (host_numel[i] <= 0) continue;
+      SP_REQUIRE(host_t[i] >= 1, "Adam step count must be >= 1");
+      const int k = a.count++;
+      a.p[k] = host_p[i];
+      a.g[k] = host_g[i];
+      a.m[k] = host_m[i];
+      a.v[k] = host_v[i];
+      a.n[k] = host_numel[i];
+      a.inv_c1[k] = (float)(1.0 / (1.0 - pow((double)beta1, (double)host_t[i])));
+      a.inv_c2[k] = (float)(1.0 / (1.0 - pow((double)beta2, (double)host_t[i])));
+      a.block_start[k] = blocks;
+      blocks += blocks_for(host_numel[i]);
+    }
+    if (a.count == 0) continue;
+    a.block_start[a.count] = blocks;
+    adam_multi_kernel<<<blocks, kThreads, 0, st>>>(a, alpha, beta1, beta2, eps);
+    SP_CHECK_LAUNCH("adam_multi");
+  }
+  return 0;
+}
+
+int sp_sgd_multi(int n_tensors, float* const* host_p, const float* const* host_g,
+                 const int64_t* host_numel, float lr, sp_stream_t stream) {
+  SP_REQUIRE(n_tensors >= 0, "negative tensor count");
+  cudaStream_t st = sp::as_stream(stream);
+  for (int first = 0; first < n_tensors; first += kMaxTensors) {
+    AxpyArgs a;
+    a.count = 0;
+    int blocks = 0;
+    for (int i = first; i < n_tensors && i < first + kMaxTensors; ++i) {
+      if (host_numel[i] <= 0) continue;
+      const int k = a.count++;
+      a.p[k] = host_p[i];
+      a.g[k] = host_g[i];
+      a.n[k] = host_numel[i];
+      a.dst_offset[k] = 0;
+      a.block_start[k] = blocks;
+      blocks += blocks_for(host_numel[i]);
+    }
+    if (a.count == 0) continue;
+    a.block_start[a.count] = blocks;
+    sgd_multi_kernel<<<blocks, kThreads, 0, st>>>(a, lr);
+    SP_CHECK_LAUNCH("sgd_multi");
+  }
+  return 0;
+}
+
+int sp_pack_multi(int n_tensors, const float* const* host_src, const int64_t* host_numel,
+                  const int64_t* host_offsets, float* bucket, sp_stream_t stream) {
+  SP_REQUIRE(n_tensors >= 0, "negative tensor count");
+  cudaStream_t st = sp::as_stream(stream);
+  int64_t offset = 0;
+  for (int first = 0; first < n_tensors; first += kMaxTensors) {
+    AxpyArgs a;
+    a.count = 0;
+    int blocks = 0;
+    for (int i = first; i < n_tensors && i < first + kMaxTensors; ++i) {
+      const int64_t n = host_numel[i];
+      if (n > 0) {
+        const int k = a.count++;
+        a.p[k] = bucket;
+        a.g[k] = host_src[i];
+        a.n[k] = n;
+        a.dst_offset[k] = host_offsets ? host_offsets[i] : offset;
+        a.block_start[k] = blocks;
+        blocks += blocks_for(n);
+      }
+      offset += n > 0 ? n : 0;
+    }
+    if (a.count == 0) continue;
+    a.block_start[a.count] = blocks;
+    pack_multi_kernel<<<blocks, kThreads, 0, st>>>(a);
+    SP_CHECK_LAUNCH("pack_multi");
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+// maxpool2d forward (value + uint8 argmax) and argmax-gather backward, NHWC fp32.
+// HBM-bound: forward reads each input once (stride >= kernel) and writes y + 1-byte idx;
+// backward is in GATHER form -- one thread per input pixel x 4 channels collects the
+// windows that selected it -- so there are no atomics and the result is deterministic
+// (the reference scatters with np.add.at, sp.py:386).  128-bit loads along C.
+//
+// Semantics pinned by the oracle (sp.py:282-300, 257-279): the SAME padding value 0.0
+// competes for the max, the first maximum in (dy,dx) row-major order wins, NaN wins like
+// np.argmax.
+#include "common.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+
+struct PoolGeom {
+  int N, H, W, C, KH, KW, sy, sx, pt, pl, OH, OW;
+};
+
+__device__ __forceinline__ void take(float v, int k, float& best, int& bi) {
+  if (v > best || (v != v && best == best)) {
+    best = v;
+    bi = k;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) maxpool_fwd_vec4(const float* __restrict__ x,
+                                                             float* __restrict__ y,
+                                                             uint8_t* __restrict__ idx,
+                                                             PoolGeom g) {
+  const int C4 = g.C >> 2;
+  const int64_t total = (int64_t)g.N * g.OH * g.OW * C4;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % C4);
+    int64_t r = t / C4;
+    const int ox = (int)(r % g.OW);
+    r /= g.OW;
+    const int oy = (int)(r % g.OH);
+    const int n = (int)(r / g.OH);
+    const int iy0 = oy * g.sy - g.pt, ix0 = ox * g.sx - g.pl;
+    float4 best;
+    int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    bool first = true;
+    for (int dy = 0; dy < g.KH; ++dy) {
+      const int iy = iy0 + dy;
+      for (int dx = 0; dx < g.KW; ++dx) {
+        const int ix = ix0 + dx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // zero padding takes part in the max
+        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+          v = ld_stream_f4(x + (((int64_t)n * g.H + iy) * g.W + ix) * g.C + 4 * c4);
+        if (first) {
+          best = v;
+          first = false;
+        } else {
+          const int k = dy * g.KW + dx;
+          take(v.x, k, best.x, b0);
+          take(v.y, k, best.y, b1);
+          take(v.z, k, best.z, b2);
+          take(v.w, k, best.w, b3);
+        }
+      }
+    }
+    reinterpret_cast<float4*>(y)[t] = best;
+    reinterpret_cast<uchar4*>(idx)[t] =
+        make_uchar4((unsigned char)b0, (unsigned char)b1, (unsigned char)b2, (unsigned char)b3);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) maxpool_fwd_scalar(const float* __restrict__ x,
+                                                               float* __restrict__ y,
+                                                               uint8_t* __restrict__ idx,
+                                                               PoolGeom g) {
+  const int64_t total = (int64_t)g.N * g.OH * g.OW * g.C;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % g.C);
+    int64_t r = t / g.C;
+    const int ox = (int)(r % g.OW);
+    r /= g.OW;
+    const int oy = (int)(r % g.OH);
+    const int n = (int)(r / g.OH);
+    const int iy0 = oy * g.sy - g.pt, ix0 = ox * g.sx - g.pl;
+    float best = 0.f;
+    int bi = 0;
+    bool first = true;
+    for (int dy = 0; dy < g.KH; ++dy) {
+      const int iy = iy0 + dy;
+      for (int dx = 0; dx < g.KW; ++dx) {
+        const int ix = ix0 + dx;
+        float v = 0.f;
+        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+          v = x[(((int64_t)n * g.H + iy) * g.W + ix) * g.C + c];
+        if (first) {
+          best = v;
+          first = false;
+        } else {
+          take(v, dy * g.KW + dx, best, bi);
+        }
+      }
+    }
+    y[t] = best;
+    idx[t] = (uint8_t)bi;
+  }
+}
+
+// windows visited in increasing (oy, ox): the order np.add.at accumulates them in
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_vec4(const float* __restrict__ gy,
+                                                             const uint8_t* __restrict__ idx,
+                                                             float* __restrict__ dx,
+                                                             PoolGeom g) {
+  const int C4 = g.C >> 2;
+  const int64_t total = (int64_t)g.N * g.H * g.W * C4;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % C4);
+    int64_t r = t / C4;
+    const int ix = (int)(r % g.W);
+    r /= g.W;
+    const int iy = (int)(r % g.H);
+    const int n = (int)(r / g.H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int dy = g.KH - 1; dy >= 0; --dy) {
+      const int ty = iy + g.pt - dy;
+      if (ty < 0 || ty % g.sy != 0) continue;
+      const int oy = ty / g.sy;
+      if (oy >= g.OH) continue;
+      for (int dxx = g.KW - 1; dxx >= 0; --dxx) {
+        const int tx = ix + g.pl - dxx;
+        if (tx < 0 || tx % g.sx != 0) continue;
+        const int ox = tx / g.sx;
+        if (ox >= g.OW) continue;
+        const int64_t o = (((int64_t)n * g.OH + oy) * g.OW + ox) * C4 + c4;
+        const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(idx) + o);
+        const float4 gv = ld_stream_f4(gy + 4 * o);
+        const int want = dy * g.KW + dxx;
+        if (k.x == want) acc.x += gv.x;
+        if (k.y == want) acc.y += gv.y;
+        if (k.z == want) acc.z += gv.z;
+        if (k.w == want) acc.w += gv.w;
+      }
+    }
+    reinterpret_cast<float4*>(dx)[t] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_scalar(const float* __restrict__ gy,
+                                                               const uint8_t* __restrict__ idx,
+                                                               float* __restrict__ dx,
+                                                               PoolGeom g) {
+  const int64_t total = (int64_t)g.N * g.H * g.W * g.C;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % g.C);
+    int64_t r = t / g.C;
+    const int ix = (int)(r % g.W);
+    r /= g.W;
+    const int iy = (int)(r % g.H);
+    const int n = (int)(r / g.H);
+    float acc = 0.f;
+    for (int dy = g.KH - 1; dy >= 0; --dy) {
+      const int ty = iy + g.pt - dy;
+      if (ty < 0 || ty % g.sy != 0) continue;
+      const int oy = ty / g.sy;
+      if (oy >= g.OH) continue;
+      for (int dxx = g.KW - 1; dxx >= 0; --dxx) {
+        const int tx = ix + g.pl - dxx;
+        if (tx < 0 || tx % g.sx != 0) continue;
+        const int ox = tx / g.sx;
+        if (ox >= g.OW) continue;
+        const int64_t o = (((int64_t)n * g.OH + oy) * g.OW + ox) * g.C + c;
+        if (idx[o] == dy * g.KW + dxx) acc += gy[o];
+      }
+    }
+    dx[t] = acc;
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check(const PoolGeom& g) {
+  if (g.N < 0 || g.H <= 0 || g.W <= 0 || g.C <= 0 || g.KH <= 0 || g.KW <= 0 || g.sy <= 0 ||
+      g.sx <= 0 || g.OH < 0 || g.OW < 0)
+    return sp::set_error(SP_ERR_INVALID_ARGUMENT, "maxpool2d: bad geometry");
+  if (g.KH * g.KW > 255)
+    return sp::set_error(SP_ERR_UNSUPPORTED, "maxpool2d: window larger than 255 (uint8 argmax)");
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int sp_maxpool2d_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C, int KH,
+                     int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
+                     sp_stream_t stream) {
+  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW};
+  if (int rc = check(g)) return rc;
+  const int64_t outs = (int64_t)N * OH * OW * C;
+  if (outs == 0) return 0;
+  cudaStream_t st = sp::as_stream(stream);
+  if (C % 4 == 0 && aligned16(x) && aligned16(y) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0)
+    maxpool_fwd_vec4<<<sp::wave_grid(outs / 4, kThreads, 8), kThreads, 0, st>>>(x, y, idx, g);
+  else
+    maxpool_fwd_scalar<<<sp::wave_grid(outs, kThreads, 8), kThreads, 0, st>>>(x, y, idx, g);
+  SP_CHECK_LAUNCH("maxpool2d_fwd");
+  return 0;
+}
+
+int sp_maxpool2d_bwd(const float* gy, const uint8_t* idx, float* dx, int N, int H, int W, int C,
+                     int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
+                     sp_stream_t stream) {
+  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW};
+  if (int rc = check(g)) return rc;
+  const int64_t ins = (int64_t)N * H * W * C;
+  if (ins == 0) return 0;
+  cudaStream_t st = sp::as_stream(stream);
+  if (C % 4 == 0 && aligned16(gy) && aligned16(dx) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0)
+    maxpool_bwd_vec4<<<sp::wave_grid(ins / 4, kThreads, 8), kThreads, 0, st>>>(gy, idx, dx, g);
+  else
+    maxpool_bwd_scalar<<<sp::wave_grid(ins, kThreads, 8), kThreads, 0, st>>>(gy, idx, dx, g);
+  SP_CHECK_LAUNCH("maxpool2d_bwd");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,486 @@
+// Reductions, softmax and cross entropy.  Deterministic (fixed summation order, no float
+// atomics): multi-block reductions go through a library-owned scratch buffer and a final
+// single-block pass.  Warp-shuffle reductions inside blocks, coalesced row/column walks.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr size_t kScratchFloats = 1 << 20;  // 4 MB of partial sums
+
+// One scratch buffer per device, allocated on first use (before any graph capture: the
+// first training step always runs eagerly).  The library is used from one stream per
+// process (SURVEY.md 8b "Threading"), so reuse across calls is ordered by that stream.
+float* scratch_for_current_device() {
+  static float* bufs[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!bufs[dev]) {
+    if (cudaMalloc(&bufs[dev], kScratchFloats * sizeof(float)) != cudaSuccess) return nullptr;
+  }
+  return bufs[dev];
+}
+
+// ---- sum over the middle axis of [outer, reduce, inner] -------------------------------
+
+// inner == 1: one block per (row, split); lanes walk the row with float4 loads.
+__global__ void __launch_bounds__(kThreads) rowsum_kernel(const float* __restrict__ x,
+                                                          float* __restrict__ out,
+                                                          int64_t reduce, int64_t chunk,
+                                                          int splits) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.y;
+  const int split = blockIdx.x;
+  const int64_t lo = (int64_t)split * chunk;
+  const int64_t hi = min(reduce, lo + chunk);
+  const float* p = x + row * reduce;
+  float acc = 0.f;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p + lo) & 15) == 0);
+  int64_t i = lo;
+  if (vec) {
+    const int64_t n4 = (hi - lo) >> 2;
+    for (int64_t j = threadIdx.x; j < n4; j += blockDim.x) {
+      const float4 v = ld_stream_f4(p + lo + 4 * j);
+      acc += (v.x + v.y) + (v.z + v.w);
+    }
+    i = lo + (n4 << 2);
+  }
+  for (int64_t j = i + threadIdx.x; j < hi; j += blockDim.x) acc += p[j];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[row * splits + split] = acc;
+}
+
+// inner > 1: block = 32 columns x 8 row-lanes; each block owns 32 output columns of one
+// `outer` slice and one split of the reduce axis (coalesced along inner).
+__global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restrict__ x,
+                                                          float* __restrict__ out,
+                                                          int64_t reduce, int64_t inner,
+                                                          int64_t chunk, int splits) {
+  __shared__ float tile[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t col = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t o = blockIdx.z;
+  const int split = blockIdx.y;
+  const int64_t lo = (int64_t)split * chunk, hi = min(reduce, lo + chunk);
+  float acc = 0.f;
+  if (col < inner) {
+    const float* p = x + (o * reduce) * inner + col;
+    for (int64_t r = lo + ty; r < hi; r += 8) acc += p[r * inner];
+  }
+  tile[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < inner) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += tile[k][tx];
+    out[(o * splits + split) * inner + col] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) maxall_partial_kernel(const float* __restrict__ x,
+                                                                  float* __restrict__ part,
+                                                                  int64_t n) {
+  __shared__ float red[32];
+  float m = -INFINITY;
+  bool nan = false;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    nan |= (v != v);
+    m = fmaxf(m, v);
+  }
+  if (nan) m = NAN;  // np.max propagates NaN
+  // NaN-propagating block max: reduce a flag alongside
+  float flag = block_sum(nan ? 1.f : 0.f, red);
+  m = block_max(m, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = (flag > 0.f) ? NAN : m;
+}
+
+__global__ void __launch_bounds__(kThreads) maxall_final_kernel(const float* __restrict__ part,
+                                                                float* __restrict__ out, int n) {
+  __shared__ float red[32];
+  float m = -INFINITY;
+  bool nan = false;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = part[i];
+    nan |= (v != v);
+    m = fmaxf(m, v);
+  }
+  float flag = block_sum(nan ? 1.f : 0.f, red);
+  m = block_max(m, red);
+  if (threadIdx.x == 0) out[0] = (flag > 0.f) ? NAN : m;
+}
+
+// ---- softmax ---------------------------------------------------------------------------
+
+// inner == 1: one warp per row (n is the class count: 10 on the training path).
+__global__ void __launch_bounds__(kThreads) softmax_rows_kernel(const float* __restrict__ x,
+                                                                float* __restrict__ y,
+                                                                int64_t rows, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpb = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows;
+       row += (int64_t)gridDim.x * wpb) {
+    const float* p = x + row * n;
+    float m = -INFINITY;
+    for (int64_t j = lane; j < n; j += 32) m = fmaxf(m, p[j]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int64_t j = lane; j < n; j += 32) s += expf(p[j] - m);
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int64_t j = lane; j < n; j += 32) y[row * n + j] = expf(p[j] - m) * inv;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) softmax_rows_bwd_kernel(const float* __restrict__ y,
+                                                                    const float* __restrict__ g,
+                                                                    float* __restrict__ dx,
+                                                                    int64_t rows, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpb = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows;
+       row += (int64_t)gridDim.x * wpb) {
+    const float* py = y + row * n;
+    const float* pg = g + row * n;
+    float dot = 0.f;
+    for (int64_t j = lane; j < n; j += 32) dot += py[j] * pg[j];
+    dot = warp_sum(dot);
+    for (int64_t j = lane; j < n; j += 32) dx[row * n + j] = py[j] * (pg[j] - dot);
+  }
+}
+
+// inner > 1: one thread per (outer, inner) pair walks the softmax axis with stride inner.
+__global__ void __launch_bounds__(kThreads) softmax_strided_kernel(const float* __restrict__ x,
+                                                                   float* __restrict__ y,
+                                                                   int64_t outer, int64_t n,
+                                                                   int64_t inner) {
+  const int64_t total = outer * inner;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = t / inner, c = t - o * inner;
+    const float* p = x + o * n * inner + c;
+    float m = -INFINITY;
+    for (int64_t j = 0; j < n; ++j) m = fmaxf(m, p[j * inner]);
+    float s = 0.f;
+    for (int64_t j = 0; j < n; ++j) s += expf(p[j * inner] - m);
+    const float inv = 1.f / s;
+    float* q = y + o * n * inner + c;
+    for (int64_t j = 0; j < n; ++j) q[j * inner] = expf(p[j * inner] - m) * inv;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) softmax_strided_bwd_kernel(
+    const float* __restrict__ y, const float* __restrict__ g, float* __restrict__ dx,
+    int64_t outer, int64_t n, int64_t inner) {
+  const int64_t total = outer * inner;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = t / inner, c = t - o * inner;
+    const int64_t base = o * n * inner + c;
+    float dot = 0.f;
+    for (int64_t j = 0; j < n; ++j) dot += y[base + j * inner] * g[base + j * inner];
+    for (int64_t j = 0; j < n; ++j)
+      dx[base + j * inner] = y[base + j * inner] * (g[base + j * inner] - dot);
+  }
+}
+
+// ---- cross entropy ---------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kThreads) xent_fwd_kernel(const float* __restrict__ probs,
+                                                            const int32_t* __restrict__ labels,
+                                                            float* __restrict__ part,
+                                                            int64_t rows, int64_t cols) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    acc -= logf(probs[r * cols + labels[r]]);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(kThreads) xent_bwd_kernel(const float* __restrict__ probs,
+                                                            const int32_t* __restrict__ labels,
+                                                            const float* __restrict__ gloss,
+                                                            float* __restrict__ dprobs,
+                                                            int64_t rows, int64_t cols) {
+  const float g = gloss[0];
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int64_t c = i - r * cols;
+    dprobs[i] = (c == labels[r]) ? -g / probs[i] : 0.f;
+  }
+}
+
+// fused softmax + cross entropy: one warp per row; per-block partial loss.
+__global__ void __launch_bounds__(kThreads) softmax_xent_fwd_kernel(
+    const float* __restrict__ logits, const int32_t* __restrict__ labels,
+    float* __restrict__ probs, float* __restrict__ part, int64_t rows, int64_t cols) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31;
+  const int64_t wpb = blockDim.x >> 5;
+  float nll = 0.f;  // accumulated by lane 0 of each warp
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows;
+       row += (int64_t)gridDim.x * wpb) {
+    const float* p = logits + row * cols;
+    float m = -INFINITY;
+    for (int64_t j = lane; j < cols; j += 32) m = fmaxf(m, p[j]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int64_t j = lane; j < cols; j += 32) s += expf(p[j] - m);
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int64_t j = lane; j < cols; j += 32) probs[row * cols + j] = expf(p[j] - m) * inv;
+    if (lane == 0) nll += (logf(s) + m) - p[labels[row]];
+  }
+  nll = block_sum(nll, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = nll;
+}
+
+__global__ void __launch_bounds__(kThreads) softmax_xent_bwd_kernel(
+    const float* __restrict__ probs, const int32_t* __restrict__ labels,
+    const float* __restrict__ gloss, float* __restrict__ dlogits, int64_t rows, int64_t cols) {
+  const float g = gloss[0];
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int64_t c = i - r * cols;
+    dlogits[i] = g * (probs[i] - ((c == labels[r]) ? 1.f : 0.f));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sum_partials_kernel(const float* __restrict__ part,
+                                                                float* __restrict__ out, int n) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+
+int reduce_sum_impl(const float* x, float* out, int64_t outer, int64_t reduce, int64_t inner,
+                    cudaStream_t st) {
+  const int sms = sp::device_info().sm_count > 0 ? sp::device_info().sm_count : 148;
+  if (inner == 1) {
+    // split long rows until the grid covers ~2 waves
+    int splits = 1;
+    if (outer < 2 * sms && reduce >= 8192) {
+      splits = (int)std::min<int64_t>((2 * sms + outer - 1) / outer, reduce / 4096);
+      if (splits < 1) splits = 1;
+      if ((size_t)(outer * splits) > kScratchFloats) splits = 1;
+    }
+    if (outer > 65535) {
+      // grid.y limit: fold rows through the column kernel on the transposed view instead
+      return sp::set_error(SP_ERR_UNSUPPORTED, "sp_reduce_sum: outer > 65535 with inner == 1");
+    }
+    int64_t chunk = (reduce + splits - 1) / splits;
+    chunk = (chunk + 3) & ~int64_t(3);
+    splits = (int)((reduce + chunk - 1) / chunk);
+    if (splits == 1) {
+      rowsum_kernel<<<dim3(1, (unsigned)outer), kThreads, 0, st>>>(x, out, reduce, chunk, 1);
+    } else {
+      float* part = scratch_for_current_device();
+      if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_reduce_sum: no scratch");
+      rowsum_kernel<<<dim3(splits, (unsigned)outer), kThreads, 0, st>>>(x, part, reduce, chunk,
+                                                                         splits);
+      rowsum_kernel<<<dim3(1, (unsigned)outer), kThreads, 0, st>>>(part, out, splits, splits, 1);
+    }
+  } else {
+    const int64_t col_blocks = (inner + 31) / 32;
+    int splits = 1;
+    if (col_blocks * outer < 2 * sms && reduce >= 256) {
+      splits = (int)std::min<int64_t>((2 * sms) / (col_blocks * outer), reduce / 64);
+      if (splits < 1) splits = 1;
+      if ((size_t)(outer * splits * inner) > kScratchFloats) splits = 1;
+      if (splits > 65535) splits = 65535;
+    }
+    if (outer > 65535) return sp::set_error(SP_ERR_UNSUPPORTED, "sp_reduce_sum: outer > 65535");
+    int64_t chunk = (reduce + splits - 1) / splits;
+    splits = (int)((reduce + chunk - 1) / chunk);
+    dim3 grid((unsigned)col_blocks, (unsigned)splits, (unsigned)outer);
+    if (splits == 1) {
+      colsum_kernel<<<grid, kThreads, 0, st>>>(x, out, reduce, inner, chunk, 1);
+    } else {
+      float* part = scratch_for_current_device();
+      if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_reduce_sum: no scratch");
+      colsum_kernel<<<grid, kThreads, 0, st>>>(x, part, reduce, inner, chunk, splits);
+      dim3 grid2((unsigned)col_blocks, 1, (unsigned)outer);
+      colsum_kernel<<<grid2, kThreads, 0, st>>>(part, out, splits, inner, splits, 1);
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sp_reduce_sum(const float* x, float* out, int64_t outer, int64_t reduce, int64_t inner,
+                  sp_stream_t stream) {
+  SP_REQUIRE(outer >= 0 && reduce >= 0 && inner >= 0, "negative extent");
+  if (outer * inner == 0) return 0;
+  if (reduce == 0) return sp_fill_f32(out, outer * inner, 0.f, stream);
+  const int rc = reduce_sum_impl(x, out, outer, reduce, inner, sp::as_stream(stream));
+  if (rc) return rc;
+  SP_CHECK_LAUNCH("reduce_sum");
+  return 0;
+}
+
+int sp_reduce_max_all(const float* x, float* out, int64_t n, sp_stream_t stream) {
+  SP_REQUIRE(n > 0, "empty array has no maximum");
+  float* part = scratch_for_current_device();
+  if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_reduce_max_all: no scratch");
+  const int blocks = sp::wave_grid(n, kThreads * 8, 4);
+  maxall_partial_kernel<<<blocks, kThreads, 0, sp::as_stream(stream)>>>(x, part, n);
+  maxall_final_kernel<<<1, kThreads, 0, sp::as_stream(stream)>>>(part, out, blocks);
+  SP_CHECK_LAUNCH("reduce_max_all");
+  return 0;
+}
+
+int sp_softmax_fwd(const float* x, float* y, int64_t outer, int64_t n, int64_t inner,
+                   sp_stream_t stream) {
+  if (outer * n * inner <= 0) return 0;
+  cudaStream_t st = sp::as_stream(stream);
+  if (inner == 1)
+    softmax_rows_kernel<<<sp::wave_grid(outer, kThreads / 32, 8), kThreads, 0, st>>>(x, y, outer, n);
+  else
+    softmax_strided_kernel<<<sp::wave_grid(outer * inner, kThreads, 8), kThreads, 0, st>>>(
+        x, y, outer, n, inner);
+  SP_CHECK_LAUNCH("softmax_fwd");
+  return 0;
+}
+
+int sp_softmax_bwd(const float* y, const float* g, float* dx, int64_t outer, int64_t n,
+                   int64_t inner, sp_stream_t stream) {
+  if (outer * n * inner <= 0) return 0;
+  cudaStream_t st = sp::as_stream(stream);
+  if (inner == 1)
+    softmax_rows_bwd_kernel<<<sp::wave_grid(outer, kThreads / 32, 8), kThreads, 0, st>>>(
+        y, g, dx, outer, n);
+  else
+    softmax_strided_bwd_kernel<<<sp::wave_grid(outer * inner, kThreads, 8), kThreads, 0, st>>>(
+        y, g, dx, outer, n, inner);
+  SP_CHECK_LAUNCH("softmax_bwd");
+  return 0;
+}
+
+int sp_xent_fwd(const float* probs, const int32_t* labels, float* loss, int64_t rows,
+                int64_t cols, sp_stream_t stream) {
+  SP_REQUIRE(rows >= 0 && cols > 0, "bad shape");
+  cudaStream_t st = sp::as_stream(stream);
+  if (rows == 0) return sp_fill_f32(loss, 1, 0.f, stream);
+  const int blocks = rows <= 4096 ? 1 : sp::wave_grid(rows, kThreads, 2);
+  if (blocks == 1) {
+    xent_fwd_kernel<<<1, kThreads, 0, st>>>(probs, labels, loss, rows, cols);
+  } else {
+    float* part = scratch_for_current_device();
+    if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_xent_fwd: no scratch");
+    xent_fwd_kernel<<<blocks, kThreads, 0, st>>>(probs, labels, part, rows, cols);
+    sum_partials_kernel<<<1, kThreads, 0, st>>>(part, loss, blocks);
+  }
+  SP_CHECK_LAUNCH("xent_fwd");
+  return 0;
+}
+
+int sp_xent_bwd(const float* probs, const int32_t* labels, const float* gloss, float* dprobs,
+                int64_t rows, int64_t cols, sp_stream_t stream) {
+  if (rows * cols <= 0) return 0;
+  xent_bwd_kernel<<<sp::wave_grid(rows * cols, kThreads, 8), kThreads, 0, sp::as_stream(stream)>>>(
+      probs, labels, gloss, dprobs, rows, cols);
+  SP_CHECK_LAUNCH("xent_bwd");
+  return 0;
+}
+
+int sp_softmax_xent_fwd(const float* logits, const int32_t* labels, float* probs, float* loss,
+                        int64_t rows, int64_t cols, sp_stream_t stream) {
+  SP_REQUIRE(rows >= 0 && cols > 0, "bad shape");
+  cudaStream_t st = sp::as_stream(stream);
+  if (rows == 0) return sp_fill_f32(loss, 1, 0.f, stream);
+  const int blocks = rows <= 2048 ? 1 : sp::wave_grid(rows, kThreads / 32, 4);
+  if (blocks == 1) {
+    softmax_xent_fwd_kernel<<<1, kThreads, 0, st>>>(logits, labels, probs, loss, rows, cols);
+  } else {
+    float* part = scratch_for_current_device();
+    if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_softmax_xent_fwd: no scratch");
+    softmax_xent_fwd_kernel<<<blocks, kThreads, 0, st>>>(logits, labels, probs, part, rows, cols);
+    sum_partials_kernel<<<1, kThreads, 0, st>>>(part, loss, blocks);
+  }
+  SP_CHECK_LAUNCH("softmax_xent_fwd");
+  return 0;
+}
+
+int sp_softmax_xent_bwd(const float* probs, const int32_t* labels, const float* gloss,
+                        float* dlogits, int64_t rows, int64_t cols, sp_stream_t stream) {
+  if (rows * cols <= 0) return 0;
+  softmax_xent_bwd_kernel<<<sp::wave_grid(rows * cols, kThreads, 8), kThreads, 0,
+                            sp::as_stream(stream)>>>(probs, labels, gloss, dlogits, rows, cols);
+  SP_CHECK_LAUNCH("softmax_xent_bwd");
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- argmax over the last axis (public op maxax, sp.py:257-279) ---------------------------
+namespace {
+__global__ void __launch_bounds__(kThreads) argmax_rows_kernel(const float* __restrict__ x,
+                                                               float* __restrict__ y,
+                                                               int32_t* __restrict__ idx,
+                                                               int64_t rows, int64_t n) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const float* p = x + r * n;
+    float best = p[0];
+    int32_t bi = 0;
+    for (int64_t j = 1; j < n; ++j) {
+      const float v = p[j];
+      if (v > best || (v != v && best == best)) {  // first max wins, NaN wins (np.argmax)
+        best = v;
+        bi = (int32_t)j;
+      }
+    }
+    y[r] = best;
+    idx[r] = bi;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) argmax_rows_bwd_kernel(const float* __restrict__ g,
+                                                                   const int32_t* __restrict__ idx,
+                                                                   float* __restrict__ dx,
+                                                                   int64_t rows, int64_t n) {
+  const int64_t total = rows * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n;
+    dx[i] = (idx[r] == (int32_t)(i - r * n)) ? g[r] : 0.f;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int sp_argmax_rows_fwd(const float* x, float* y, int32_t* idx, int64_t rows, int64_t n,
+                       sp_stream_t stream) {
+  SP_REQUIRE(rows >= 0 && n > 0, "bad shape");
+  if (rows == 0) return 0;
+  argmax_rows_kernel<<<sp::wave_grid(rows, kThreads, 8), kThreads, 0, sp::as_stream(stream)>>>(
+      x, y, idx, rows, n);
+  SP_CHECK_LAUNCH("argmax_rows_fwd");
+  return 0;
+}
+
+int sp_argmax_rows_bwd(const float* g, const int32_t* idx, float* dx, int64_t rows, int64_t n,
+                       sp_stream_t stream) {
+  if (rows * n <= 0) return 0;
+  argmax_rows_bwd_kernel<<<sp::wave_grid(rows * n, kThreads, 8), kThreads, 0,
+                           sp::as_stream(stream)>>>(g, idx, dx, rows, n);
+  SP_CHECK_LAUNCH("argmax_rows_bwd");
+  return 0;
+}
+
+}  // extern "C"

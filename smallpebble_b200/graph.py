@@ -1,0 +1,207 @@
+"""Lazy graphs, learnables, optimisers and layer constructors: the reference's L3 layer
+(sp.py:472-653) kept as host Python (BASELINE.json: "Host code stays Python").  Initialisers
+use the global NumPy RNG exactly like the reference, so `np.random.seed(s)` gives the same
+weights on both sides (cast once to fp32 on upload).  Adam / SGD run as one fused
+multi-tensor kernel; under `smallpebble_b200.distributed` they first all-reduce the gradients.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from . import array as A
+from . import core
+from .array import DeviceArray
+from .core import Variable
+
+F = _abi.f
+
+
+# ---------------- LAZY GRAPHS (sp.py:472-520)
+
+
+class AssignmentError(Exception):
+    pass
+
+
+class Lazy:
+    """A lazy node: `Lazy(fn)(*args)`, evaluated by `.run()` (sp.py:476-509).  No memoisation,
+    like the reference: a node shared by two parents is evaluated once per parent."""
+
+    def __init__(self, function) -> None:
+        self.function = function
+        self.arguments = []
+
+    def __call__(self, *args):
+        if self.arguments:
+            raise AssignmentError(f"Arguments already assigned to {self}.")
+        self.arguments = args
+        return self
+
+    def run(self):
+        if not self.arguments:
+            raise AssignmentError(f"No arguments have been assigned to {self}.")
+        argvals = (a.run() if hasattr(a, "run") else a for a in self.arguments)
+        return self.function(*argvals)
+
+
+class Placeholder(Lazy):
+    "A placeholder lazy graph node, in which to place SmallPebble variables (sp.py:512-520)."
+
+    def __init__(self):
+        super().__init__(lambda a: a)
+
+    def assign_value(self, variable) -> None:
+        self.arguments = [variable]
+
+
+# ---------------- LEARNABLES (sp.py:526-543)
+
+
+def learnable(variable: Variable) -> Variable:
+    "Flag `variable` as learnable."
+    variable.is_learnable = True
+    return variable
+
+
+def get_learnables(lazy_node: Lazy) -> list:
+    "Get `variables` where is_learnable=True from a lazy graph (depth-first argument order)."
+    learnable_vars = []
+
+    def find_learnables(node):
+        for child in getattr(node, "arguments", []):
+            if getattr(child, "is_learnable", False):
+                learnable_vars.append(child)
+            find_learnables(child)
+
+    find_learnables(lazy_node)
+    return learnable_vars
+
+
+# ---------------- OPTIMISERS (sp.py:552-583, 645-653)
+
+
+def _ptr_table(ptrs):
+    return (C.c_void_p * len(ptrs))(*ptrs)
+
+
+def _device_gradient(variable: Variable, gradients) -> DeviceArray:
+    g = gradients[variable]  # KeyError when missing, like the reference
+    if not isinstance(g, DeviceArray):
+        g = DeviceArray.from_host(g)
+    if g.shape != variable.array.shape:
+        g = A.binary("add", DeviceArray.zeros(variable.array.shape), g)
+    return g
+
+
+class Adam:
+    """Adam optimization for SmallPebble variables (sp.py:552-583; Kingma & Ba, Algorithm 1).
+
+    Per-variable step count / first / second moment, as in the reference.  One fused kernel
+    updates every variable in place (the reference rebinds `variable.array` to a new array;
+    the `Variable` objects -- what callers hold -- are the same either way)."""
+
+    def __init__(self, alpha: float = 0.001, beta1: float = 0.9, beta2: float = 0.999,
+                 eps: float = 1e-8) -> None:
+        self.alpha = alpha
+        self.beta1 = beta1
+        self.beta2 = beta2
+        self.eps = eps
+        self.t = {}
+        self.m = {}
+        self.v = {}
+
+    def training_step(self, variables, gradients) -> None:
+        from . import distributed
+
+        variables = list(variables)
+        if not variables:
+            return
+        grads = [_device_gradient(v, gradients) for v in variables]
+        if distributed.is_initialized() and distributed.world_size() > 1:
+            grads = distributed.allreduce_gradients(grads)
+        ts = []
+        for v in variables:
+            if v not in self.t:
+                self.t[v] = 0
+                self.m[v] = DeviceArray.zeros(v.array.shape)
+                self.v[v] = DeviceArray.zeros(v.array.shape)
+            self.t[v] += 1
+            ts.append(self.t[v])
+        n = len(variables)
+        F.sp_adam_multi(
+            n,
+            _ptr_table([v.array.ptr for v in variables]),
+            _ptr_table([g.ptr for g in grads]),
+            _ptr_table([self.m[v].ptr for v in variables]),
+            _ptr_table([self.v[v].ptr for v in variables]),
+            _abi.dims([v.array.size for v in variables]),
+            (C.c_int32 * n)(*ts),
+            self.alpha, self.beta1, self.beta2, self.eps, A.stream(),
+        )
+
+
+def sgd_step(variables, gradients, learning_rate: float = 0.001) -> None:
+    "A single step of gradient descent. Modifies each variable.array directly (sp.py:645-653)."
+    from . import distributed
+
+    variables = list(variables)
+    if not variables:
+        return
+    grads = [_device_gradient(v, gradients) for v in variables]
+    if distributed.is_initialized() and distributed.world_size() > 1:
+        grads = distributed.allreduce_gradients(grads)
+    F.sp_sgd_multi(
+        len(variables),
+        _ptr_table([v.array.ptr for v in variables]),
+        _ptr_table([g.ptr for g in grads]),
+        _abi.dims([v.array.size for v in variables]),
+        learning_rate, A.stream(),
+    )
+
+
+# ---------------- NEURAL NETWORK HELPERS (sp.py:586-642)
+
+
+def batch(X: np.ndarray, y: np.ndarray, size: int, seed=None):
+    "Yield sub-batches of X,y, randomly selecting with replacement (sp.py:586-593)."
+    assert (y.ndim == 1) and (X.shape[0] == y.size), "unexpected dimensions."
+    if seed:
+        np.random.seed(seed)
+    while True:
+        idx = np.random.randint(0, y.size, size)
+        yield X[idx, ...], y[idx]
+
+
+def convlayer(height: int, width: int, depth: int, n_kernels: int, padding: str = "VALID",
+              strides=(1, 1)):
+    "Create a convolutional neural network layer (sp.py:596-609)."
+    sigma = np.sqrt(6 / (height * width * depth + height * width * n_kernels))
+    kernels_init = sigma * (np.random.random([height, width, depth, n_kernels]) - 0.5)
+    kernels = learnable(Variable(kernels_init))
+    func = lambda images, kernels: core.conv2d(images, kernels, padding, strides)  # noqa: E731
+    return lambda images: Lazy(func)(images, kernels)
+
+
+def he_init(insize: int, outsize: int) -> np.ndarray:
+    "He weight initialization (sp.py:624-627)."
+    sigma = np.sqrt(4 / (insize + outsize))
+    return np.random.random([insize, outsize]) * sigma - sigma / 2
+
+
+def linearlayer(insize: int, outsize: int):
+    "Create a linear fully connected neural network layer (sp.py:630-635)."
+    weights = learnable(Variable(he_init(insize, outsize)))
+    bias = learnable(Variable(np.ones([outsize], np.float32)))
+    func = lambda a, weights, bias: core.matmul(a, weights) + bias  # noqa: E731
+    return lambda a: Lazy(func)(a, weights, bias)
+
+
+def onehot(y: np.ndarray, n_classes: int) -> np.ndarray:
+    "Onehot encode vector y with classes 0 to n_classes-1 (sp.py:638-642)."
+    result = np.zeros([len(y), n_classes])
+    result[np.arange(len(y)), y] = 1
+    return result
