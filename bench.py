@@ -1,0 +1,423 @@
+"""Headline benchmark: train images/s of the README CIFAR-10 CNN (BASELINE.json configs[1]:
+conv2d 3x3 + leaky_relu + maxpool2d x3 + linear, batch 128 per GPU, Adam, synthetic
+32x32x3 data) through the unchanged SmallPebble API, batch-sharded over N GPUs (weak
+scaling: 128 images per GPU, one NCCL all-reduce of the flat gradient bucket per step).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the NumPy path on host cores
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what every field means.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 128
+WORKLOAD = "cifar_cnn_readme_b128_adam"
+METRIC = "train_images_per_sec"
+UNIT = "images/s"
+L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the NumPy oracle port of the reference's CPU path
+# ------------------------------------------------------------------------------------------
+
+
+def time_cpu_port(steps: int, warmup: int, batch: int = BATCH_PER_GPU):
+    """Reference-style training steps (forward, per-path backward, Adam) in float64 NumPy on
+    the host cores.  Returns (images/s, seconds per step list)."""
+    from oracle import numpy_path as orc
+
+    x, y = orc.synthetic_batch("cnn", batch)
+    model = orc.build_model("cnn", seed=0)
+    opt = orc.AdamState()
+    for _ in range(warmup):
+        model.train_step(opt, x, y)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        model.train_step(opt, x, y)
+        times.append(time.perf_counter() - t0)
+    return batch * len(times) / sum(times), times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    ips, times = time_cpu_port(args.steps, args.warmup)
+    cores = os.cpu_count() or 1
+    sample = (f"{args.steps} timed + {args.warmup} warm-up reference-style steps of the same "
+              f"workload at batch {BATCH_PER_GPU}, float64 NumPy ({np.__version__}); np.matmul "
+              f"uses OpenBLAS threads on all {cores} visible cores, every other op one core")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU,
+                   "note": "CPU arm does not shard: one process, batch 128"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic work of one ABI call, for the roofline of the dominant kernel
+# ------------------------------------------------------------------------------------------
+
+
+def algorithmic_work(name, args):
+    """('tensor', flops) or ('hbm', bytes) for one launching ABI call, or None."""
+    from smallpebble_b200 import _abi
+
+    if name in ("sp_conv2d_fprop", "sp_conv2d_dgrad", "sp_conv2d_wgrad"):
+        g = args[3]
+        g = g.contents if hasattr(g, "contents") else g
+        flops = 2.0 * g.N * g.OH * g.OW * g.K * g.KH * g.KW * g.C
+        desc = (f"{name[3:]} N={g.N} HxW={g.H}x{g.W} C={g.C} K={g.K} k={g.KH}x{g.KW} "
+                f"s={g.sy}x{g.sx}")
+        return "tensor", flops, desc
+    if name == "sp_gemm":
+        m, n, k, batch = args[2], args[3], args[4], args[14]
+        return "tensor", 2.0 * m * n * k * max(batch, 1), f"gemm M={m} N={n} K={k} batch={batch}"
+    if name in ("sp_maxpool2d_fwd", "sp_maxpool2d_bwd"):
+        N, H, W, Cc, KH, KW, sy, sx, pt, pl, OH, OW = args[3:15]
+        ins, outs = N * H * W * Cc, N * OH * OW * Cc
+        b = 4 * ins + 4 * outs + outs  # x (or dx), y (or gy), uint8 argmax
+        return "hbm", float(b), f"{name[3:]} [{N},{H},{W},{Cc}] -> [{N},{OH},{OW},{Cc}]"
+    if name == "sp_leaky_relu_fwd":
+        return "hbm", 8.0 * args[2], f"leaky_relu_fwd n={args[2]}"
+    if name == "sp_leaky_relu_bwd":
+        return "hbm", 12.0 * args[3], f"leaky_relu_bwd n={args[3]}"
+    if name == "sp_adam_multi":
+        n = sum(args[5][i] for i in range(args[0]))
+        return "hbm", 28.0 * n, f"adam_multi params={n}"
+    if name == "sp_ewise_binary":
+        n = 1
+        for i in range(args[6]):
+            n *= args[7][i]
+        return "hbm", 12.0 * n, f"ewise_binary n={n}"
+    if name == "sp_reduce_sum":
+        return "hbm", 4.0 * args[2] * args[3] * args[4], "reduce_sum"
+    del _abi
+    return None
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+
+
+def run_ours(args):
+    import torch
+
+    import smallpebble_b200 as sp
+    from smallpebble_b200 import _abi, workloads
+    from smallpebble_b200.array import DeviceArray, stream, transfer_counters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        sp.distributed.init()
+        import torch.distributed as dist
+    sp.set_precision(args.precision)
+    _abi.load(build_if_missing=False)
+
+    global_batch = BATCH_PER_GPU * world
+    x_global, y_global = workloads.synthetic_batch("cnn", global_batch)
+    lo, hi = rank * BATCH_PER_GPU, (rank + 1) * BATCH_PER_GPU
+    x_host, y_host = x_global[lo:hi], y_global[lo:hi]
+    wl = workloads.cifar_cnn(seed=0)  # identical weights on every rank (same NumPy seed)
+    adam = sp.Adam()
+
+    # device-resident copies for the `value` measurement
+    x_dev = DeviceArray.from_host(x_host)
+    y_dev = DeviceArray.from_host(y_host, dtype=np.int32)
+    x_dev.ptr, y_dev.ptr  # upload now
+    flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        _abi.f.sp_l2_flush(flush_buf.data_ptr(), L2_FLUSH_BYTES, stream())
+
+    def step_resident():
+        wl.x_in.assign_value(sp.Variable(x_dev))
+        wl.y_true.assign_value(y_dev)
+        loss_val = wl.loss.run()
+        gradients = sp.get_gradients(loss_val)
+        adam.training_step(wl.learnables, gradients)
+        return loss_val
+
+    def step_e2e():
+        # the README loop verbatim: host batch in, loss read back (np.isnan(loss_val.array))
+        wl.x_in.assign_value(sp.Variable(x_host))
+        wl.y_true.assign_value(y_host)
+        loss_val = wl.loss.run()
+        if np.isnan(loss_val.array):
+            raise RuntimeError("loss is nan")
+        gradients = sp.get_gradients(loss_val)
+        adam.training_step(wl.learnables, gradients)
+        return loss_val
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        """K steps, each bracketed by CUDA events on the launch stream; L2 flushed (outside the
+        event pairs) between steps.  Returns per-step milliseconds."""
+        pairs = []
+        for _ in range(steps):
+            flush_l2()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            _abi.prof.begin_step()
+            e0.record()
+            step_fn()
+            e1.record()
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in pairs]
+
+    def max_over_ranks(ms_total):
+        if world == 1:
+            return ms_total
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (also: first-use allocations, lazy scratch, NCCL channels) ---------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sync_all()
+
+    # ---- find the dominant kernel: one instrumented (untimed) step -------------------------
+    _abi.prof.records.clear()
+    _abi.prof.select = None
+    _abi.prof.active = True
+    flush_l2()
+    _abi.prof.begin_step()
+    step_resident()
+    torch.cuda.synchronize()
+    _abi.prof.active = False
+    per_call = [(e0.elapsed_time(e1), name, seq, a) for name, seq, a, e0, e1 in _abi.prof.records]
+    per_call.sort(key=lambda r: -r[0])
+    top = next((r for r in per_call if algorithmic_work(r[1], r[3]) is not None), None)
+    calls_per_step = len(per_call)
+    profile_summary = [
+        {"call": n, "seq": s, "ms": round(ms, 4)} for ms, n, s, _ in per_call[:8]]
+
+    # ---- timed region: `value` (inputs resident in HBM) -----------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    sync_all()
+    _abi.prof.records.clear()
+    if top is not None:
+        top_name, top_seq = top[1], top[2]
+        _abi.prof.select = lambda name, seq: name == top_name and seq == top_seq
+        _abi.prof.active = True
+    launches0 = _abi.counter.launches
+    wall0 = time.perf_counter()
+    step_ms = timed(step_resident, args.steps)
+    sync_all()
+    wall = time.perf_counter() - wall0
+    launches = _abi.counter.launches - launches0
+    _abi.prof.active = False
+    top_records = list(_abi.prof.records)
+    _abi.prof.records.clear()
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(sum(step_ms))
+    ms_per_step = total_ms / args.steps
+    value = global_batch * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: host batch -> H2D -> step -> loss D2H, every step ----------------------------
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    tc = transfer_counters()
+    h2d0, d2h0 = tc["h2d_bytes"], tc["d2h_bytes"]
+    e2e_ms = timed(step_e2e, args.steps)
+    sync_all()
+    h2d = (tc["h2d_bytes"] - h2d0) // args.steps
+    d2h = (tc["d2h_bytes"] - d2h0) // args.steps
+    e2e_total = max_over_ranks(sum(e2e_ms))
+    e2e_value = global_batch * args.steps / (e2e_total / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            sp.distributed.shutdown()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------
+    peaks = load_peaks()
+    roofline = None
+    if top is not None and top_records:
+        kind, work, desc = algorithmic_work(top_records[0][0], top_records[0][2])
+        durs = [e0.elapsed_time(e1) for _, _, _, e0, e1 in top_records]
+        avg_ms = sum(durs) / len(durs)
+        if kind == "tensor":
+            if args.precision == "tf32":
+                peak = peaks["bf16_tflops_sustained"] / 2.0
+                peak_note = ("TF32 dense = 1/2 x bf16_tflops_sustained of " + peaks["source"])
+            else:
+                peak = 74.0  # nominal fp32 FFMA: 148 SMs x 128 lanes x 2 x 1.965 GHz
+                peak_note = "fp32 CUDA-core nominal (no measured fp32 peak)"
+            achieved = work / (avg_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peak,
+                        "unit": "TFLOP/s", "frac": achieved / peak}
+        else:
+            peak = peaks["hbm_gbs"]
+            peak_note = "hbm_gbs of " + peaks["source"]
+            achieved = work / (avg_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak}
+        roofline.update({
+            "traffic": None, "kernel": desc, "avg_launch_ms": avg_ms, "launches_timed": len(durs),
+            "algorithmic_work_per_launch": work, "peak_source": peak_note,
+            "share_of_step": avg_ms / ms_per_step,
+            "note": "CUDA events around the ABI call on the launch stream inside the timed "
+                    "region; includes ~2-4 us of event overhead",
+        })
+
+    # ---- CPU baseline beside it (N=1 only) ------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, times = time_cpu_port(steps=4, warmup=1)
+        cpu = {"value": ips, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": (f"4 timed + 1 warm-up reference-style float64 NumPy steps of the same "
+                          f"workload (batch {BATCH_PER_GPU}); {sum(times):.1f} s of CPU work; "
+                          "np.matmul multi-threaded (OpenBLAS), all other ops single-threaded")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD, "global_batch": global_batch, "batch_per_gpu": BATCH_PER_GPU,
+            "parallelism": f"dp{world}", "optimizer": "Adam(1e-3)", "image": "32x32x3",
+            "l2": f"flushed ({L2_FLUSH_BYTES >> 20} MiB memset) between timed steps, outside "
+                  "the event pairs",
+            "timing": "per-step CUDA events on the launch stream, summed; max over ranks",
+            "input_image_gradient": "deferred (computed only if read; the loop never reads it)",
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_total / args.steps,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "abi_calls_per_step": calls_per_step,
+        "wall_s_timed_region": wall,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "top_calls_one_step_ms": profile_summary,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        sp.distributed.shutdown()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("SP_PRECISION", "tf32"),
+                    choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -130,14 +130,46 @@ class _Counter:
 counter = _Counter()  # kernel-launching ABI calls made by this process (bench: gpu_launches)
 
 
-def _checked(name, fn, launching):
-    err = None
+class _Profiler:
+    """Optional per-call CUDA-event timing of kernel-launching ABI calls (bench.py's roofline
+    measurement).  `select(name, seq)` decides which calls get an event pair; `seq` counts
+    launching calls since `begin_step()`.  Inactive by default: one attribute test per call."""
 
+    def __init__(self):
+        self.active = False
+        self.select = None
+        self.seq = 0
+        self.records = []  # (name, seq, args, start_event, stop_event)
+
+    def begin_step(self):
+        self.seq = 0
+
+
+prof = _Profiler()
+
+
+def _checked(name, fn, launching):
     def fail(rc):
         raise SmallPebbleCudaError(f"{name} failed (code {rc}): {last_error()}")
 
     if launching:
         def wrapped(*args):
+            if prof.active:
+                seq = prof.seq
+                prof.seq = seq + 1
+                if prof.select is None or prof.select(name, seq):
+                    import torch
+
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rc = fn(*args)
+                    e1.record()
+                    if rc:
+                        fail(rc)
+                    counter.launches += 1
+                    prof.records.append((name, seq, args, e0, e1))
+                    return
             rc = fn(*args)
             if rc:
                 fail(rc)

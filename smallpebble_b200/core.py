@@ -87,6 +87,85 @@ class Variable:
     shape = property(lambda self: self._array.shape)
 
 
+class Gradients(dict):
+    """{Variable: DeviceArray} returned by get_gradients.  A plain dict, except that the
+    contribution of a tape edge into a LEAF that is not flagged learnable (e.g. the gradient
+    with respect to the input image batch) is evaluated the first time anybody asks for it:
+    indexing, `in`, `get`, iteration, `len`, `items` ... all see the complete dictionary the
+    reference returns (sp.py:87), but a training loop that only reads the learnables'
+    gradients never pays for the image gradient.  SP_EAGER_LEAF_GRADS=1 disables deferral."""
+
+    __slots__ = ("_deferred",)
+
+    def __init__(self):
+        super().__init__()
+        self._deferred = {}
+
+    def _defer(self, child, fn, path_value):
+        self._deferred.setdefault(child, []).append((fn, path_value))
+
+    def _materialise(self, key=None):
+        if not self._deferred:
+            return
+        keys = [key] if key is not None else list(self._deferred)
+        for k in keys:
+            for fn, path_value in self._deferred.pop(k, ()):
+                _accumulate(self, None, k, _as_device(fn(path_value)))
+
+    def __missing__(self, key):
+        if key in self._deferred:
+            self._materialise(key)
+            return dict.__getitem__(self, key)
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._deferred
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def __iter__(self):
+        self._materialise()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        return dict.__len__(self) + len(self._deferred)
+
+    def keys(self):
+        self._materialise()
+        return dict.keys(self)
+
+    def values(self):
+        self._materialise()
+        return dict.values(self)
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+
+def _as_device(value) -> DeviceArray:
+    return value if isinstance(value, DeviceArray) else DeviceArray.from_host(value)
+
+
+def _accumulate(gradients, owned, child, value):
+    have = dict.get(gradients, child)
+    if have is None:
+        dict.__setitem__(gradients, child, value)  # may alias the upstream buffer
+    elif owned is not None and child in owned and have.shape == value.shape:
+        A.accumulate_(have, value)
+    else:
+        dict.__setitem__(gradients, child, A.binary("add", have, value))
+        if owned is not None:
+            owned.add(child)
+
+
+_eager_leaf_grads = os.environ.get("SP_EAGER_LEAF_GRADS", "0") == "1"
+
+
 def get_gradients(variable: Variable) -> dict:
     """d(sum of `variable`)/d(node) for every node reachable from `variable` (sp.py:57-87).
 
@@ -108,22 +187,19 @@ def get_gradients(variable: Variable) -> dict:
             stack.pop()
     order.reverse()
 
-    gradients = {variable: DeviceArray.full(variable.array.shape, 1.0)}
+    gradients = Gradients()
+    dict.__setitem__(gradients, variable, DeviceArray.full(variable.array.shape, 1.0))
     owned = {variable}  # gradient buffers nobody else aliases: safe to accumulate in place
     for node in order:
-        path_value = gradients[node]
+        if not node.local_gradients:
+            continue
+        path_value = dict.__getitem__(gradients, node)
         for child, multiply_by_locgrad in node.local_gradients:
-            value = multiply_by_locgrad(path_value)
-            if not isinstance(value, DeviceArray):
-                value = DeviceArray.from_host(value)
-            have = gradients.get(child)
-            if have is None:
-                gradients[child] = value  # may alias path_value (identity closures)
-            elif child in owned and have.shape == value.shape:
-                A.accumulate_(have, value)
-            else:
-                gradients[child] = A.binary("add", have, value)
-                owned.add(child)
+            if (not child.local_gradients and not getattr(child, "is_learnable", False)
+                    and not _eager_leaf_grads):
+                gradients._defer(child, multiply_by_locgrad, path_value)
+                continue
+            _accumulate(gradients, owned, child, _as_device(multiply_by_locgrad(path_value)))
     return gradients
 
 
@@ -646,14 +722,19 @@ def cross_entropy(y_pred: Variable, y_true: np.ndarray, axis: int = -1) -> Varia
     if probs.ndim != 2:
         raise ValueError("cross_entropy expects y_pred of shape [batch_size, n_classes]")
     rows, cols = probs.shape
-    labels_host = np.asarray(y_true.array if isinstance(y_true, Variable) else y_true)
-    labels_host = labels_host.reshape(-1).astype(np.int64)
-    if labels_host.shape[0] != rows:
-        raise ValueError("cross_entropy: len(y_true) must equal the batch size")
-    if rows and (labels_host.min() < -cols or labels_host.max() >= cols):
-        raise IndexError("cross_entropy: label out of range")
-    labels_host = np.where(labels_host < 0, labels_host + cols, labels_host)
-    labels = DeviceArray.from_host(labels_host, dtype=np.int32)
+    if isinstance(y_true, DeviceArray) and y_true.dtype == np.int32:
+        labels = y_true  # already resident on the device (validated by whoever uploaded it)
+        if labels.size != rows:
+            raise ValueError("cross_entropy: len(y_true) must equal the batch size")
+    else:
+        labels_host = np.asarray(y_true.array if isinstance(y_true, Variable) else y_true)
+        labels_host = labels_host.reshape(-1).astype(np.int64)
+        if labels_host.shape[0] != rows:
+            raise ValueError("cross_entropy: len(y_true) must equal the batch size")
+        if rows and (labels_host.min() < -cols or labels_host.max() >= cols):
+            raise IndexError("cross_entropy: label out of range")
+        labels_host = np.where(labels_host < 0, labels_host + cols, labels_host)
+        labels = DeviceArray.from_host(labels_host, dtype=np.int32)
     loss = DeviceArray.empty(())
     logits_var = getattr(y_pred, "_softmax_of", None) if _fuse_softmax_xent else None
 

@@ -1,0 +1,75 @@
+"""GPU: model-level parity.  The README MNIST MLP and CIFAR CNN, written with the public API
+exactly as the README writes them, trained for k Adam steps from the reference's own initial
+weights (same NumPy seed) on the same synthetic batch: loss curve, first-step gradients,
+final weights and predictions against the golden vectors of the unmodified reference, and
+against the oracle run in the same process."""
+
+import numpy as np
+import pytest
+
+import cases as C
+import smallpebble_b200 as sp
+from conftest import assert_close
+from oracle import numpy_path as orc
+from smallpebble_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+# k-step training compounds per-step error: Adam normalises the update to ~alpha regardless of
+# gradient scale, so a tiny gradient perturbation moves a weight by O(alpha) at most.  Compare
+# weights on the scale of the weights and losses relative to the loss.
+LOSS_RTOL = {"fp32": 2e-5, "tf32": 2e-3}
+GRAD_RTOL = {"fp32": 5e-5, "tf32": 4e-3}
+WEIGHT_RTOL = {"fp32": 1e-4, "tf32": 5e-3}
+
+
+@pytest.mark.parametrize("kind,batch,steps", C.MODEL_CASES)
+def test_training_matches_reference(kind, batch, steps, precision, golden):
+    x, y = C.synthetic_batch(kind, batch)
+    wl = workloads.BUILDERS[kind](seed=0)
+    adam = sp.Adam()
+    losses = []
+    for step in range(steps):
+        loss_val, grads = wl.train_step(adam, x, y)
+        assert not np.isnan(loss_val.array)  # the README loop's own check
+        if step == 0:
+            for i, p in enumerate(wl.learnables):
+                got = np.asarray(grads[p]).ravel()[::7]
+                assert_close(got, golden[f"model/{kind}/grad0/{i}"], GRAD_RTOL[precision],
+                             f"first-step gradient of learnable {i}")
+        losses.append(float(loss_val.array))
+    assert_close(losses, golden[f"model/{kind}/losses"], LOSS_RTOL[precision], "loss curve")
+    for i, p in enumerate(wl.learnables):
+        got = np.asarray(p.array).ravel()[::7]
+        assert_close(got, golden[f"model/{kind}/w_final/{i}"], WEIGHT_RTOL[precision],
+                     f"weights of learnable {i} after {steps} Adam steps")
+    pred = wl.predict(x)
+    assert_close(pred.array, golden[f"model/{kind}/pred_final"], 10 * WEIGHT_RTOL[precision],
+                 "predictions after training")
+    assert np.array_equal(np.argmax(np.asarray(pred.array), 1).shape, (batch,))
+
+
+def test_cnn_batch128_one_step_vs_oracle(precision):
+    """BASELINE config[1] at full size: one training step of the CIFAR CNN at batch 128."""
+    x, y = workloads.synthetic_batch("cnn", 128)
+    wl = workloads.cifar_cnn(seed=0)
+    model = orc.build_model("cnn", seed=0)
+    loss_val, grads = wl.train_step(sp.Adam(), x, y)
+    loss0, grads0 = model.train_step(orc.AdamState(), x, y)
+    assert_close(loss_val.array, loss0, LOSS_RTOL[precision], "loss")
+    for i, (p, p0) in enumerate(zip(wl.learnables, model.params)):
+        assert_close(grads[p], grads0[p0], GRAD_RTOL[precision], f"gradient {i}")
+        assert_close(p.array, p0.value, WEIGHT_RTOL[precision], f"weights {i} after Adam")
+
+
+def test_vgg_small_one_step_vs_oracle(precision):
+    """BASELINE config[3] family (SAME 3x3 convs, 64-256 channels) at a CPU-checkable size."""
+    x, y = workloads.synthetic_batch("vgg", 4, image=16)
+    widths = (16, 16, 32, 32, 64, 64)
+    wl = workloads.vgg6(seed=0, image=16, widths=widths)
+    model = orc.build_model("vgg", seed=0, image=16, widths=widths)
+    loss_val, grads = wl.train_step(sp.Adam(), x, y)
+    loss0, grads0 = model.train_step(orc.AdamState(), x, y)
+    assert_close(loss_val.array, loss0, LOSS_RTOL[precision], "loss")
+    for i, (p, p0) in enumerate(zip(wl.learnables, model.params)):
+        assert_close(grads[p], grads0[p0], GRAD_RTOL[precision], f"gradient {i}")

@@ -1,0 +1,190 @@
+"""GPU parity tests proper: every hot-path op, through the public API (which calls the C
+ABI), against the oracle on the same seeded inputs AND against the golden vectors recorded
+from the unmodified reference.  Integer results (argmax indices) bit-exact; floating point
+within BASELINE.json's relative tolerance of the float64 values (1e-5 fp32, 2e-3 TF32)."""
+
+import numpy as np
+import pytest
+
+import cases as C
+import smallpebble_b200 as sp
+from conftest import RTOL, assert_close
+from oracle import numpy_path as orc
+from smallpebble_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+
+def grads_of(fn, arrays, gy):
+    vs = [sp.Variable(a) for a in arrays]
+    y = fn(*vs)
+    g = sp.get_gradients(sp.mul(y, sp.Variable(gy)))
+    return y, [g[v] for v in vs]
+
+
+@pytest.fixture(params=[0, 1, 2], ids=["policy", "force_umma", "force_simt"])
+def umma_policy(request):
+    _abi.load().sp_debug_set_umma_policy(request.param)
+    yield request.param
+    _abi.load().sp_debug_set_umma_policy(0)
+
+
+@pytest.mark.parametrize("case", C.CONV_CASES, ids=[c[0] for c in C.CONV_CASES])
+def test_conv2d(case, precision, umma_policy, golden):
+    if precision == "fp32" and umma_policy == 1:
+        pytest.skip("tcgen05 kernel is only selected in TF32 mode")
+    name, xs, ws, strides, pad = case
+    x, w, gy = C.conv_inputs(case)
+    tol = RTOL[precision]
+    y, (dx, dw) = grads_of(lambda a, b: sp.conv2d(a, b, pad, strides), [x, w], gy)
+    y0, dx0, dw0 = orc.conv2d_grads(x, w, gy, pad, strides)
+    assert y.shape == y0.shape
+    assert_close(y.array, y0, tol, "y vs oracle")
+    assert_close(dx, dx0, tol, "dX vs oracle")
+    assert_close(dw, dw0, tol, "dW vs oracle")
+    assert_close(y.array, golden[f"conv/{name}/y"], tol, "y vs golden")
+    assert_close(dx, golden[f"conv/{name}/dx"], tol, "dX vs golden")
+    assert_close(dw, golden[f"conv/{name}/dw"], tol, "dW vs golden")
+
+
+@pytest.mark.parametrize("case", C.POOL_CASES, ids=[c[0] for c in C.POOL_CASES])
+def test_maxpool2d_bit_exact_indices(case, golden):
+    name, xs, (kh, kw), strides, pad = case
+    x, gy = C.pool_inputs(case)
+    x32 = x.astype(np.float32)  # the device sees fp32 inputs: argmax is compared on those
+    y, (dx,) = grads_of(lambda a: sp.maxpool2d(a, kh, kw, pad, list(strides)), [x], gy)
+    y0, idx0 = orc.maxpool2d_forward(x32, kh, kw, pad, strides)
+    _, dx0 = orc.maxpool2d_grads(x32, kh, kw, gy.astype(np.float32), pad, strides)
+    idx = np.asarray(y._argmax)
+    assert idx.dtype == np.uint8
+    assert np.array_equal(idx, idx0)  # bit-exact index map
+    assert np.array_equal(np.asarray(y.array), y0.astype(np.float32))  # a max is exact
+    assert_close(dx, dx0, 1e-6, "dX vs oracle")
+    # the float64 golden argmax agrees wherever fp32 rounding created no new ties
+    assert np.mean(idx == golden[f"pool/{name}/idx"]) > 0.999
+    assert_close(y.array, golden[f"pool/{name}/y"], 1e-6, "y vs golden")
+    assert_close(dx, golden[f"pool/{name}/dx"], 1e-5, "dX vs golden")
+
+
+def test_maxpool2d_padding_ties_nan():
+    x = -np.ones((1, 3, 3, 4))
+    v = sp.Variable(x)
+    y = sp.maxpool2d(v, 2, 2, "SAME", [2, 2])
+    out = np.asarray(y.array)
+    assert np.all(out[0, 1, 1] == 0.0) and np.all(out[0, 0, 0] == -1.0)  # zero pad wins
+    assert np.all(np.asarray(y._argmax)[0, 0, 0] == 0)  # all-equal window -> index 0
+    dx = np.asarray(sp.get_gradients(y)[v])
+    assert dx.sum() == 4.0  # windows won by the pad drop their gradient
+    x = np.zeros((1, 2, 2, 3))
+    x[0, 1, 0, :] = np.nan
+    y = sp.maxpool2d(sp.Variable(x), 2, 2, "VALID", [2, 2])
+    assert np.all(np.isnan(np.asarray(y.array))) and np.all(np.asarray(y._argmax) == 2)
+
+
+@pytest.mark.parametrize("case", C.MATMUL_CASES, ids=[c[0] for c in C.MATMUL_CASES])
+def test_matmul(case, precision, umma_policy, golden):
+    if precision == "fp32" and umma_policy == 1:
+        pytest.skip("tcgen05 kernel is only selected in TF32 mode")
+    a, b, gy = C.matmul_inputs(case)
+    tol = RTOL[precision]
+    y, (da, db) = grads_of(sp.matmul, [a, b], gy)
+    y0, da0, db0 = orc.matmul_grads(a, b, gy)
+    assert_close(y.array, y0, tol, "y")
+    assert_close(da, da0, tol, "dA")
+    assert_close(db, db0, tol, "dB")
+    assert_close(y.array, golden[f"matmul/{case[0]}/y"], tol, "y vs golden")
+    assert_close(da, golden[f"matmul/{case[0]}/da"], tol, "dA vs golden")
+    assert_close(db, golden[f"matmul/{case[0]}/db"], tol, "dB vs golden")
+
+
+@pytest.mark.parametrize("case", C.SOFTMAX_CASES, ids=[c[0] for c in C.SOFTMAX_CASES])
+def test_softmax(case, golden):
+    name, shape, axis = case
+    x, gy = C.softmax_inputs(case)
+    y, (dx,) = grads_of(lambda a: sp.softmax(a, axis), [x], gy)
+    assert_close(y.array, golden[f"softmax/{name}/y"], 1e-5, "y")
+    assert_close(dx, golden[f"softmax/{name}/dx"], 1e-5, "dx")
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_softmax_cross_entropy(fused, golden):
+    sp.set_fusion(fused)
+    try:
+        logits, labels = C.xent_inputs()
+        v = sp.Variable(logits)
+        p = sp.softmax(v)
+        loss = sp.cross_entropy(p, labels)
+        assert loss.array.shape == ()
+        g = sp.get_gradients(loss)
+        assert getattr(loss, "_fused_softmax_xent", False) == fused
+        assert_close(p.array, golden["xent/probs"], 1e-5, "probs")
+        assert_close(loss.array, golden["xent/loss"], 1e-5, "loss")
+        assert_close(g[v], golden["xent/dlogits"], 1e-5, "dlogits")
+        if not fused:
+            assert p in g  # the probability node's own gradient is reported
+    finally:
+        sp.set_fusion(True)
+
+
+def test_cross_entropy_known_answer():
+    p = sp.Variable(np.full((2, 3), 1 / 3))
+    loss = sp.cross_entropy(p, np.array([0, 2]))
+    assert abs(float(loss.array) - 2 * np.log(3)) < 1e-5
+    with pytest.raises(IndexError):
+        sp.cross_entropy(p, np.array([0, 3]))
+
+
+def test_leaky_relu(golden):
+    x, gy = C.leaky_inputs()
+    for alpha in (0.02, 0.1):
+        y, (dx,) = grads_of(lambda a: sp.leaky_relu(a, alpha), [x], gy)
+        assert_close(y.array, golden[f"leaky/{alpha}/y"], 1e-6, "y")
+        assert_close(dx, golden[f"leaky/{alpha}/dx"], 1e-6, "dx")
+    v = sp.Variable(np.array([-1.0, 0.0, 2.0]))
+    y = sp.leaky_relu(v)
+    assert np.allclose(np.asarray(y.array), [-0.02, 0.0, 2.0])
+    assert np.allclose(np.asarray(sp.get_gradients(y)[v]), [0.02, 0.02, 1.0])
+
+
+def test_bias_add_and_unbroadcast_sum(golden):
+    a, bias, gy = C.bias_inputs()
+    y, (da, db) = grads_of(sp.add, [a, bias], gy)
+    assert_close(y.array, golden["bias/y"], 1e-6, "y")
+    assert_close(da, golden["bias/da"], 1e-6, "da")
+    assert_close(db, golden["bias/db"], 1e-5, "dbias")
+    assert np.asarray(db).shape == (100,)
+
+
+def test_adam_and_sgd_steps(golden):
+    p0, grads = C.adam_inputs()
+    v = sp.Variable(p0.copy())
+    adam = sp.Adam()
+    for i, g in enumerate(grads):
+        adam.training_step([v], {v: g})
+        assert_close(v.array, golden[f"adam/p{i + 1}"], 1e-5, f"adam step {i + 1}")
+    v = sp.Variable(np.array([1.0, -2.0, 3.0]))
+    adam = sp.Adam()
+    g = np.array([0.1, -0.2, 0.3])
+    adam.training_step([v], {v: g})
+    assert np.allclose(np.asarray(v.array), [0.999, -1.999, 2.999], atol=1e-6)
+    adam.training_step([v], {v: g})
+    assert np.allclose(np.asarray(v.array), [0.998, -1.998, 2.998], atol=1e-6)
+    with pytest.raises(KeyError):
+        adam.training_step([sp.Variable(np.ones(2))], {})
+    v = sp.Variable(p0.copy())
+    sp.sgd_step([v], {v: grads[0]}, learning_rate=0.01)
+    assert_close(v.array, golden["sgd/p1"], 1e-6, "sgd")
+
+
+def test_adam_many_tensors_odd_sizes():
+    rng = np.random.default_rng(5)
+    shapes = [(3,), (17, 5), (4097,), (1,), (64, 33)] * 6  # 30 tensors: two kernel batches
+    vs = [sp.Variable(rng.random(s) - 0.5) for s in shapes]
+    nodes = [orc.Node(np.asarray(v.array, dtype=np.float64)) for v in vs]
+    adam, opt = sp.Adam(alpha=0.01), orc.AdamState(alpha=0.01)
+    for _ in range(3):
+        gs = [rng.random(s) - 0.5 for s in shapes]
+        adam.training_step(vs, dict(zip(vs, gs)))
+        opt.step(nodes, dict(zip(nodes, gs)))
+    for v, n in zip(vs, nodes):
+        assert_close(v.array, n.value, 2e-5, "multi-tensor adam")

@@ -1,0 +1,148 @@
+"""GPU: size-independent properties at BASELINE.json's full sizes (where the float64 oracle
+would take minutes): adjointness of the three conv kernels, linearity, pool round-trips,
+determinism, agreement of the two kernel families."""
+
+import numpy as np
+import pytest
+
+import smallpebble_b200 as sp
+from conftest import RTOL, assert_close, scaled_err
+from smallpebble_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+
+def dot(a, b):
+    return float(np.sum(np.asarray(a, np.float64) * np.asarray(b, np.float64)))
+
+
+CONFIGS = [
+    # name, x shape, w shape, strides, padding
+    ("cnn_conv1_b128", (128, 32, 32, 3), (3, 3, 3, 32), (1, 1), "VALID"),
+    ("cnn_conv2_b128", (128, 15, 15, 32), (3, 3, 32, 128), (1, 1), "VALID"),
+    ("cnn_conv3_b128", (128, 7, 7, 128), (3, 3, 128, 128), (1, 1), "VALID"),
+    ("vgg_conv_64_64", (32, 64, 64, 64), (3, 3, 64, 64), (1, 1), "SAME"),
+    ("sweep_k5_s2", (64, 32, 32, 64), (5, 5, 64, 64), (2, 2), "SAME"),
+    ("sweep_k1", (64, 32, 32, 128), (1, 1, 128, 256), (1, 1), "SAME"),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_conv_adjoint_identities(cfg, precision):
+    """<conv(x,w), gy> == <x, dgrad(gy)> == <w, wgrad(gy)>: the three kernels are consistent
+    linear maps of each other (exact in real arithmetic because conv is bilinear)."""
+    name, xs, ws, strides, pad = cfg
+    rng = np.random.default_rng(7)
+    x, w = rng.random(xs) - 0.5, rng.random(ws) - 0.5
+    xv, wv = sp.Variable(x), sp.Variable(w)
+    y = sp.conv2d(xv, wv, pad, strides)
+    gy = rng.random(y.shape) - 0.5
+    g = sp.get_gradients(sp.mul(y, sp.Variable(gy)))
+    lhs = dot(y.array, gy)
+    # compare on the scale of the accumulated magnitudes, not of the (cancelling) sum
+    scale = float(np.sum(np.abs(np.asarray(y.array, np.float64) * gy)))
+    tol = RTOL[precision]
+    assert abs(lhs - dot(x, g[xv])) <= tol * scale
+    assert abs(lhs - dot(w, g[wv])) <= tol * scale
+
+
+@pytest.mark.parametrize("cfg", CONFIGS[:4], ids=[c[0] for c in CONFIGS[:4]])
+def test_tensor_core_kernel_agrees_with_fp32_kernel(cfg):
+    name, xs, ws, strides, pad = cfg
+    rng = np.random.default_rng(11)
+    x, w = rng.random(xs) - 0.5, rng.random(ws) - 0.5
+
+    def run(prec):
+        sp.set_precision(prec)
+        xv, wv = sp.Variable(x), sp.Variable(w)
+        y = sp.conv2d(xv, wv, pad, strides)
+        g = sp.get_gradients(y)
+        return np.asarray(y.array), np.asarray(g[xv]), np.asarray(g[wv])
+
+    old = sp.get_precision()
+    try:
+        _abi.load().sp_debug_set_umma_policy(1)
+        tf = run("tf32")
+        _abi.load().sp_debug_set_umma_policy(0)
+        fp = run("fp32")
+    finally:
+        _abi.load().sp_debug_set_umma_policy(0)
+        sp.set_precision(old)
+    for a, b, what in zip(tf, fp, ("y", "dX", "dW")):
+        assert_close(a, b, RTOL["tf32"], f"{name} {what}: tcgen05 vs CUDA-core")
+
+
+def test_conv_linearity_and_determinism(precision):
+    rng = np.random.default_rng(3)
+    x1, x2 = rng.random((64, 30, 30, 32)) - 0.5, rng.random((64, 30, 30, 32)) - 0.5
+    w = rng.random((3, 3, 32, 64)) - 0.5
+    wv = sp.Variable(w)
+    f = lambda x: np.asarray(sp.conv2d(sp.Variable(x), wv).array, np.float64)  # noqa: E731
+    y1, y2, y12 = f(x1), f(x2), f(x1 + 2 * x2)
+    assert scaled_err(y12, y1 + 2 * y2) <= 2 * RTOL[precision]
+    assert np.array_equal(f(x1), y1.astype(np.float64))  # bitwise repeatable
+    xv = sp.Variable(x1)
+    gw = [np.asarray(sp.get_gradients(sp.conv2d(xv, wv))[wv]) for _ in range(2)]
+    assert np.array_equal(gw[0], gw[1])  # split-K wgrad has a fixed summation order
+
+
+def test_maxpool_properties_full_size():
+    rng = np.random.default_rng(5)
+    x = (rng.random((128, 30, 30, 32)) - 0.5).astype(np.float32)
+    xv = sp.Variable(x)
+    y = sp.maxpool2d(xv, 2, 2, strides=[2, 2])
+    yy, idx = np.asarray(y.array), np.asarray(y._argmax)
+    # value == the window element the index points at; index in range; max >= every element
+    win = x.reshape(128, 15, 2, 15, 2, 32).transpose(0, 1, 3, 5, 2, 4).reshape(128, 15, 15, 32, 4)
+    assert idx.max() <= 3
+    assert np.array_equal(np.take_along_axis(win, idx[..., None].astype(np.int64), -1)[..., 0], yy)
+    assert np.array_equal(yy, win.max(-1)) and np.array_equal(idx, win.argmax(-1))
+    # backward routes each upstream value to exactly one input: sums are preserved
+    gy = rng.random(yy.shape).astype(np.float32)
+    dx = np.asarray(sp.get_gradients(sp.mul(y, sp.Variable(gy)))[xv])
+    assert abs(dx.sum(dtype=np.float64) - gy.sum(dtype=np.float64)) < 1e-3
+    assert np.count_nonzero(dx) <= gy.size
+    # idempotence: pooling an already pooled (constant-window) image returns it
+    up = np.repeat(np.repeat(yy, 2, 1), 2, 2)
+    again = np.asarray(sp.maxpool2d(sp.Variable(up), 2, 2, strides=[2, 2]).array)
+    assert np.array_equal(again, yy)
+
+
+def test_matmul_full_size_vs_float64(precision):
+    rng = np.random.default_rng(9)
+    a, b = rng.random((1024, 1152)) - 0.5, rng.random((1152, 256)) - 0.5
+    av, bv = sp.Variable(a), sp.Variable(b)
+    y = sp.matmul(av, bv)
+    assert_close(y.array, a @ b, RTOL[precision], "matmul 1024x1152x256")
+    g = sp.get_gradients(y)
+    ones = np.ones((1024, 256))
+    assert_close(g[av], ones @ b.T, RTOL[precision], "dA")
+    assert_close(g[bv], a.T @ ones, RTOL[precision], "dB")
+
+
+def test_elementwise_checksums_full_size():
+    rng = np.random.default_rng(2)
+    x = rng.random((128, 30, 30, 32)) - 0.5
+    xv = sp.Variable(x)
+    y = sp.leaky_relu(xv)
+    x32 = x.astype(np.float32)
+    assert np.array_equal(np.asarray(y.array), np.where(x32 > 0, x32, x32 * np.float32(0.02)))
+    total = sp.sum(y)
+    assert abs(float(total.array) - float(np.sum(np.asarray(y.array), dtype=np.float64))) < 0.5
+    assert_close(sp.sum(y, axis=(0, 1, 2)).array,
+                 np.asarray(y.array, np.float64).sum((0, 1, 2)), 1e-5, "axis sum")
+
+
+def test_empty_and_ragged_inputs():
+    """Edge cases: empty batch, batch of one, window == image, stride > kernel."""
+    w = sp.Variable(np.random.random((3, 3, 4, 8)))
+    y = sp.conv2d(sp.Variable(np.zeros((0, 8, 8, 4))), w)
+    assert y.shape == (0, 8, 8, 8)
+    y = sp.conv2d(sp.Variable(np.random.random((1, 3, 3, 4))), w, "VALID")
+    assert y.shape == (1, 1, 1, 8)
+    p = sp.maxpool2d(sp.Variable(np.random.random((2, 7, 7, 3))), 2, 2, "VALID", [5, 5])
+    assert p.shape == (2, 2, 2, 3)
+    s = sp.sum(sp.Variable(np.zeros((0, 5))), axis=0)
+    assert np.array_equal(np.asarray(s.array), np.zeros(5))
+    m = sp.matmul(sp.Variable(np.zeros((4, 0))), sp.Variable(np.zeros((0, 3))))
+    assert np.array_equal(np.asarray(m.array), np.zeros((4, 3)))
