@@ -65,7 +65,8 @@ const char* sp_last_error(void);
 /* sm_count, compute capability of the current device */
 int sp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* test hook: 0 = default policy, 1 = always use the tcgen05 kernel in TF32 mode when the
- * shape is supported, 2 = never use it (CUDA-core kernel even in TF32 mode) */
+ * shape is supported, 2 = never use it (CUDA-core kernel even in TF32 mode); adding 16
+ * makes the tcgen05 producers wait + proxy-fence after every stage (bring-up aid) */
 int sp_debug_set_umma_policy(int policy);
 
 /* ---- memory helpers (replace NumPy array construction / copies) -------------------- */

@@ -48,7 +48,7 @@ def run(case):
     from smallpebble_b200 import _abi
 
     sp.set_precision("tf32")
-    _abi.load().sp_debug_set_umma_policy(1)
+    _abi.load().sp_debug_set_umma_policy(1 + (16 if os.environ.get('SP_PROBE_SYNC') == '1' else 0))
     rng = np.random.default_rng(0)
     worst = 0.0
     if case.startswith("gemm"):

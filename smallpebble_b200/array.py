@@ -16,6 +16,7 @@ import ctypes as C
 import functools
 import math
 import numbers
+import weakref
 
 import numpy as np
 
@@ -99,14 +100,23 @@ class DeviceArray:
 
     @staticmethod
     def from_host(a, dtype=None) -> "DeviceArray":
-        """Wrap host data; the copy to the device happens on first use."""
+        """Wrap host data; the copy to the device happens on first use.  The host values are
+        snapshotted now (converted to the device dtype, into pinned memory when a GPU is
+        present so the later host->device copy is a true async DMA)."""
         a = np.asarray(a)
         dtype = np.dtype(dtype) if dtype is not None else _host_dtype(a)
         if dtype not in _DEVICE_DTYPES:
             raise TypeError(f"unsupported device dtype {dtype}")
-        host = np.ascontiguousarray(a, dtype=dtype)
-        if host is a or np.may_share_memory(host, a):
-            host = host.copy()  # the caller may mutate its array after Variable(...)
+        nbytes = a.size * dtype.itemsize
+        if nbytes >= _PIN_THRESHOLD and _pinned.available():
+            host = _pinned.take(a.shape, dtype)
+            np.copyto(host, a, casting="unsafe")  # one pass: convert + stage
+            out = DeviceArray(host.shape, dtype, host=host)
+            weakref.finalize(out, _pinned.abandon, host.ctypes.data)  # never uploaded: recycle
+            return out
+        # snapshot: the caller may mutate its array after Variable(...).  (np.array, not
+        # np.ascontiguousarray: the latter promotes 0-d arrays to shape (1,).)
+        host = np.array(a, dtype=dtype, order="C", copy=True)
         return DeviceArray(host.shape, dtype, host=host)
 
     @staticmethod
@@ -134,9 +144,11 @@ class DeviceArray:
         nbytes = max(host.size, 1) * host.dtype.itemsize
         buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
         if host.size:
-            # pageable memcpy: the runtime stages it, `host` may be released on return
+            # pinned staging buffer: async DMA, the buffer returns to the pool once the copy
+            # has completed; pageable memory: the runtime stages it before returning
             F.sp_memcpy_h2d(buf.data_ptr(), host.ctypes.data, host.nbytes, stream())
             _counters["h2d_bytes"] += host.nbytes
+            _pinned.release(host)
         self._buf, self._ptr, self._host = buf, buf.data_ptr(), None
 
     @property
@@ -283,6 +295,60 @@ class DeviceArray:
     def __itruediv__(self, o):
         return self._rebind(_binary_any("div", self, o))
 
+
+class _PinnedPool:
+    """Recycled page-locked staging buffers for host->device uploads (torch.empty(pin_memory)
+    as the allocator).  A buffer handed out by take() is owned by one pending DeviceArray;
+    release() records a CUDA event after the H2D copy and the buffer is reused only once
+    that event has completed."""
+
+    def __init__(self):
+        self.free = {}      # nbytes -> [tensor]
+        self.owned = {}     # id(view base) -> (nbytes, tensor)
+        self.in_flight = []  # (event, nbytes, tensor)
+        self._ok = None
+
+    def available(self) -> bool:
+        if self._ok is None:
+            torch = _lazy_torch()
+            self._ok = bool(torch.cuda.is_available())
+        return self._ok
+
+    def _reclaim(self):
+        keep = []
+        for ev, nbytes, t in self.in_flight:
+            if ev.query():
+                self.free.setdefault(nbytes, []).append(t)
+            else:
+                keep.append((ev, nbytes, t))
+        self.in_flight = keep
+
+    def take(self, shape, dtype) -> np.ndarray:
+        torch = _lazy_torch()
+        nbytes = math.prod(shape) * dtype.itemsize
+        self._reclaim()
+        bucket = self.free.get(nbytes)
+        t = bucket.pop() if bucket else torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        view = t.numpy().view(dtype).reshape(shape)
+        self.owned[view.ctypes.data] = (nbytes, t)
+        return view
+
+    def abandon(self, address: int):
+        entry = self.owned.pop(address, None)
+        if entry is not None:
+            self.free.setdefault(entry[0], []).append(entry[1])
+
+    def release(self, host: np.ndarray):
+        entry = self.owned.pop(host.ctypes.data, None)
+        if entry is None:
+            return
+        ev = _lazy_torch().cuda.Event()
+        ev.record()
+        self.in_flight.append((ev, entry[0], entry[1]))
+
+
+_pinned = _PinnedPool()
+_PIN_THRESHOLD = 64 * 1024
 
 _UFUNC_TO_OP = {np.add: "add", np.subtract: "sub", np.multiply: "mul", np.true_divide: "div"}
 _counters = {"h2d_bytes": 0, "d2h_bytes": 0}
@@ -498,7 +564,7 @@ def _arange_index(shape):
 
 def flat_index(shape, index) -> np.ndarray:
     """int64 array of flat source offsets selected by the NumPy index expression `index`."""
-    return np.ascontiguousarray(_arange_index(tuple(shape))[index])
+    return np.asarray(_arange_index(tuple(shape))[index], order="C")
 
 
 def gather_flat(a: DeviceArray, flat: np.ndarray) -> DeviceArray:

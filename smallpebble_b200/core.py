@@ -509,8 +509,9 @@ def strided_sliding_view(a: Variable, window_shape, strides) -> Variable:
     gather through a host-built index map; the backward pass is the matching scatter-add
     (np.add.at semantics: overlapping windows accumulate)."""
     src_shape = a.array.shape
-    index_map = np.ascontiguousarray(
-        np_strided_sliding_view(A._arange_index(tuple(src_shape)), tuple(window_shape), tuple(strides))
+    index_map = np.array(
+        np_strided_sliding_view(A._arange_index(tuple(src_shape)), tuple(window_shape), tuple(strides)),
+        order="C",
     )
     value = A.gather_flat(a.array, index_map)
 

@@ -21,6 +21,12 @@ struct DeviceInfo {
 };
 const DeviceInfo& device_info();
 
+// Library-owned scratch (one buffer per device, allocated on first use, kScratchFloats fp32):
+// partial sums of deterministic two-pass reductions.  First half: sp_reduce_sum & friends;
+// second half: split-K partial tiles of small-N GEMMs.
+constexpr size_t kScratchFloats = 1 << 20;
+float* scratch_for_current_device();
+
 inline cudaStream_t as_stream(sp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // grid sized in whole waves of the SM count (B200: 148 SMs)

@@ -3,6 +3,8 @@
 // kernel (SP_PRECISION_FP32, tiny-N problems), and owns the deterministic split-K policy of
 // the filter gradient.
 #include <stdlib.h>
+
+#include <algorithm>
 #include <string.h>
 
 #include "igemm.cuh"
@@ -72,8 +74,11 @@ extern "C" {
 
 // undocumented test hook (declared in tests only): select the contraction kernel family
 int sp_debug_set_umma_policy(int policy) {
-  if (policy < 0 || policy > 2) return sp::set_error(SP_ERR_INVALID_ARGUMENT, "policy in 0..2");
-  sp::g_umma_policy = policy;
+  // bits 0-1: kernel family policy; bit 4: conservative producer synchronisation
+  const int family = policy & 3;
+  if (policy < 0 || family > 2) return sp::set_error(SP_ERR_INVALID_ARGUMENT, "policy in 0..2");
+  sp::g_umma_policy = family;
+  sp::igemm_umma_set_sync_mode((policy >> 4) & 1);
   return 0;
 }
 
@@ -105,9 +110,35 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   p.batch_b = strideB;
   p.batch_c = strideC;
   cudaStream_t st = sp::as_stream(stream);
-  int rc = sp::use_umma(sp::kGemm, p, precision) ? sp::launch_igemm_umma(sp::kGemm, p, st)
-                                                  : sp::launch_igemm_simt(sp::kGemm, p, st);
-  if (rc) return rc;
+  if (sp::use_umma(sp::kGemm, p, precision)) {
+    if (int rc = sp::launch_igemm_umma(sp::kGemm, p, st)) return rc;
+    SP_CHECK_LAUNCH("gemm");
+    return 0;
+  }
+  // CUDA-core kernel.  A long inner dimension with only a few output tiles (the 10-way
+  // classifier: 128 x 10 x 1152) would leave the chip idle: split K over CTAs into the
+  // library scratch and sum the partial tiles in a fixed order.
+  const int sms = sp::device_info().sm_count > 0 ? sp::device_info().sm_count : 148;
+  const int64_t tiles = ((M + 63) / 64) * ((N + 63) / 64);
+  if (batch == 1 && ldc == N && tiles * 2 <= sms && K >= 256) {
+    int64_t splits = std::min<int64_t>((sms + tiles - 1) / tiles, K / 64);
+    const int64_t cap = (int64_t)(sp::kScratchFloats / 2) / (M * N);
+    splits = std::min<int64_t>(std::min<int64_t>(splits, cap), 512);
+    float* scratch = sp::scratch_for_current_device();
+    if (splits > 1 && scratch) {
+      int64_t chunk = ((K + splits - 1) / splits + 15) / 16 * 16;
+      splits = (K + chunk - 1) / chunk;
+      float* part = scratch + sp::kScratchFloats / 2;
+      p.k_splits = (int)splits;
+      p.k_chunk = chunk;
+      p.split_stride_c = M * N;
+      p.C = part;
+      if (int rc = sp::launch_igemm_simt(sp::kGemm, p, st)) return rc;
+      SP_CHECK_LAUNCH("gemm(split-K)");
+      return sp_reduce_sum(part, C, 1, splits, M * N, stream);
+    }
+  }
+  if (int rc = sp::launch_igemm_simt(sp::kGemm, p, st)) return rc;
   SP_CHECK_LAUNCH("gemm");
   return 0;
 }

@@ -43,5 +43,7 @@ int launch_igemm_simt(int mode, const IgemmParams& p, cudaStream_t stream);
 int launch_igemm_umma(int mode, const IgemmParams& p, cudaStream_t stream);
 // true when the tcgen05 kernel supports this problem (shape / alignment constraints)
 bool igemm_umma_supported(int mode, const IgemmParams& p);
+// debug: 0 = asynchronous producer arrivals (default), 1 = wait + proxy fence per stage
+void igemm_umma_set_sync_mode(int mode);
 
 }  // namespace sp

@@ -8,13 +8,14 @@
 //     (K-major or MN-major, chosen so that the global-memory-contiguous index is the
 //     contiguous index of the smem atom): 4-stage ring, 32 k-values (one swizzle row) per
 //     stage;
-//   * warps 0-3 are GATHER PRODUCERS: they build the (virtual) im2col / transposed-im2col /
+//   * warps 0-7 are GATHER PRODUCERS: they build the (virtual) im2col / transposed-im2col /
 //     strided-matrix tiles with 16-byte cp.async (zero-fill for padding, image borders,
-//     stride holes and tails), make them visible to the async proxy
-//     (fence.proxy.async) and signal `full[stage]` mbarriers; tcgen05.commit releases a
-//     stage back through `empty[stage]`.  The im2col matrix is never materialised;
-//   * the same four warps then become the epilogue: tcgen05.ld 32x32b.x32 (one TMEM lane
-//     quadrant per warp) -> registers -> global.
+//     stride holes and tails); each thread's arrival on the stage's `full` mbarrier is
+//     triggered asynchronously when its copies land (cp.async.mbarrier.arrive.noinc), so
+//     producers run up to 4 stages ahead; tcgen05.commit releases a stage back through
+//     `empty[stage]`.  The im2col matrix is never materialised;
+//   * the same eight warps then become the epilogue: tcgen05.ld 32x32b.x32 (one TMEM lane
+//     quadrant per warp pair) -> registers -> global.
 //
 // Why gather producers rather than TMA im2col descriptors: the path must take every
 // geometry the reference takes (C = 3 / 2 / 5, 13x22 kernels, stride 10, asymmetric
@@ -30,9 +31,11 @@ namespace {
 constexpr int BM = 128;            // UMMA M (cta_group::1)
 constexpr int BK = 32;             // fp32 values per stage row = 128 B = one swizzle span
 constexpr int kStages = 4;
-constexpr int kLookahead = 3;      // cp.async groups in flight per producer thread
-constexpr int kProducers = 128;    // warps 0-3
-constexpr int kThreads = 160;      // + warp 4: TMEM allocator and MMA issuer
+constexpr int kProducers = 256;    // warps 0-7: gather producers, then epilogue
+constexpr int kProducerWarps = kProducers / 32;
+constexpr int kThreads = kProducers + 32;  // + warp 8: TMEM allocator and MMA issuer
+constexpr int kRowStep = kProducers / 8;   // K-major tiles: rows covered per producer pass (32)
+constexpr int kRowsPerThread = BM / kRowStep;  // 4
 constexpr uint32_t kATileBytes = BM * BK * 4;  // 16 KB
 
 // ---------------------------------------------------------------------------------------
@@ -101,6 +104,12 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// The mbarrier receives one (already counted) arrival from this thread once every cp.async
+// it has issued so far has landed: the producer never blocks on its own loads.
+__device__ __forceinline__ void cp_async_arrive_on(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // generic-proxy writes (cp.async landed data) -> visible to the async proxy (tcgen05.mma)
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -166,17 +175,22 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // ---------------------------------------------------------------------------------------
 // descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp SmemDescriptor / InstrDescriptor)
 // ---------------------------------------------------------------------------------------
-// 128B-swizzled operand tile.  K-major: rows of 128 B (32 k-values), 8-row groups 1024 B
-// apart (SBO).  MN-major: atoms of [8 k-rows][32 mn-values], next atom along MN `lbo` bytes
-// away, next 8-k group `sbo` bytes away.
+// Operand tile descriptors.
+//   K-major  (SWIZZLE_128B, type 2): rows of 128 B (32 k-values); 16-byte chunk index XOR
+//            (row & 7); 8-row groups `sbo` = 1024 B apart; `lbo` unused.
+//   MN-major (SWIZZLE_128B_BASE32B, type 1 -- the only MN-major layout tcgen05 accepts for
+//            32-bit operands): atoms of [4 k-rows][32 mn-values] = 512 B, 32-byte chunk index
+//            XOR (k-row & 3); next atom along MN `lbo` bytes away, next 4-k group `sbo`.
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes,
-                                              uint32_t sbo_bytes) {
+                                              uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);             // [0,14)  start address >> 4
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;    // [16,30) leading byte offset >> 4
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;    // [32,46) stride byte offset >> 4
   d |= 1ull << 46;                                      // [46,48) descriptor version (sm_100)
-  d |= 2ull << 61;                                      // [61,64) SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;                     // [61,64) swizzle mode
   return d;
 }
 
@@ -194,11 +208,12 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int bn, bool a_mn, bool b
 __device__ __forceinline__ uint32_t kmajor_off(int row, int c) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
 }
-// byte offset of 16-byte chunk `mc` (4 mn-values) of k-row `kk` (0..31) in an MN-major tile
-// with `atoms` 32-wide atoms along MN
-__device__ __forceinline__ uint32_t mnmajor_off(int kk, int mc, int atoms) {
-  const int g = kk >> 3, r = kk & 7, j = mc >> 3, cc = mc & 7;
-  return (uint32_t)((g * atoms + j) * 1024 + r * 128 + ((cc ^ r) << 4));
+// byte offset of 16-byte chunk `mc` (4 mn-values) of k-row `kk` (0..31) in an MN-major tile:
+// every 32-wide MN block owns 32 consecutive 128-byte k-rows (4096 B); inside each group of
+// 4 k-rows the 32-byte halves of a row are XOR-swizzled with the row index.
+__device__ __forceinline__ uint32_t mnmajor_off(int kk, int mc) {
+  return (uint32_t)((mc >> 3) * 4096 + kk * 128 + ((((mc & 7) >> 1) ^ (kk & 3)) << 5) +
+                    ((mc & 1) << 4));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -214,7 +229,7 @@ __device__ __forceinline__ void load_dense_kmajor(uint32_t tile, const float* __
                                                   int t) {
   const int c = t & 7;
   const int64_t k = k0 + 4 * c;
-  for (int row = t >> 3; row < rows; row += 16) {
+  for (int row = t >> 3; row < rows; row += kRowStep) {
     const uint32_t dst = tile + kmajor_off(row, c);
     const int64_t r = r0 + row;
     const float* src = base + r * ld + k;
@@ -237,11 +252,10 @@ __device__ __forceinline__ void load_dense_mnmajor(uint32_t tile, const float* _
                                                    int64_t k0, int64_t k_end, int rows, bool vec,
                                                    int t) {
   const int chunks = rows >> 2;  // 16-byte chunks per k-row (8, 16, 32 or 64)
-  const int atoms = rows >> 5;
   const int total = chunks * BK;
   for (int q = t; q < total; q += kProducers) {
     const int kk = q / chunks, mc = q - kk * chunks;
-    const uint32_t dst = tile + mnmajor_off(kk, mc, atoms);
+    const uint32_t dst = tile + mnmajor_off(kk, mc);
     const int64_t k = k0 + kk, r = r0 + 4 * mc;
     const float* src = base + k * ld + r;
     if (vec) {
@@ -259,9 +273,9 @@ __device__ __forceinline__ void load_dense_mnmajor(uint32_t tile, const float* _
 
 // per-thread description of the 8 tile rows a producer thread owns in a K-major A tile
 struct PixelRows {
-  int y[8];     // fprop: oy*sy - pad_t   | dgrad: iy + pad_t
-  int x[8];     // fprop: ox*sx - pad_l   | dgrad: ix + pad_l
-  int img[8];   // image index, or -1 for rows beyond M
+  int y[kRowsPerThread];     // fprop: oy*sy - pad_t   | dgrad: iy + pad_t
+  int x[kRowsPerThread];     // fprop: ox*sx - pad_l   | dgrad: ix + pad_l
+  int img[kRowsPerThread];   // image index, or -1 for rows beyond M
 };
 
 // decompose pixel index m = (n * D1 + a) * D2 + b
@@ -273,23 +287,23 @@ __device__ __forceinline__ void split_pixel(int m, int D1, int D2, int& n, int& 
 }
 
 // conv fprop A: rows = output pixels, k = (tap, c);  x[n, oy*sy+dy-pt, ox*sx+dx-pl, c]
+// K-major tile: thread owns 16-byte chunk c8 = t & 7 of rows (t >> 3) + 32 i.
 __device__ __forceinline__ void load_fprop_a(uint32_t tile, const float* __restrict__ x,
                                              const sp_conv_geom& g, const PixelRows& pr, int k0,
                                              int k_end, bool vec, int t) {
   const int c8 = t & 7;
-  const int rsw = (t >> 3) & 7;
-  const uint32_t dst0 = tile + (uint32_t)((t >> 6) * 1024 + rsw * 128 + ((c8 ^ rsw) << 4));
+  const uint32_t dst0 = tile + kmajor_off(t >> 3, c8);  // + i * 4096: 32 rows further
   const int k = k0 + 4 * c8;
   if (vec) {
     const int tap = k / g.C, ch = k - tap * g.C;
     const int dy = tap / g.KW, dx = tap - dy * g.KW;
     const bool kok = k < k_end;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kRowsPerThread; ++i) {
       const int iy = pr.y[i] + dy, ix = pr.x[i] + dx;
       const bool ok = kok && pr.img[i] >= 0 && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
       const float* src = x + (((int64_t)pr.img[i] * g.H + iy) * g.W + ix) * g.C + ch;
-      cp_async_16(dst0 + i * 2048, ok ? src : x, ok);
+      cp_async_16(dst0 + i * 4096, ok ? src : x, ok);
     }
   } else {
 #pragma unroll 1
@@ -299,11 +313,11 @@ __device__ __forceinline__ void load_fprop_a(uint32_t tile, const float* __restr
       const int dy = tap / g.KW, dx = tap - dy * g.KW;
       const bool kok = ke < k_end;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kRowsPerThread; ++i) {
         const int iy = pr.y[i] + dy, ix = pr.x[i] + dx;
         const bool ok = kok && pr.img[i] >= 0 && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
         const float* src = x + (((int64_t)pr.img[i] * g.H + iy) * g.W + ix) * g.C + ch;
-        cp_async_4(dst0 + i * 2048 + 4 * e, ok ? src : x, ok);
+        cp_async_4(dst0 + i * 4096 + 4 * e, ok ? src : x, ok);
       }
     }
   }
@@ -315,10 +329,10 @@ __device__ __forceinline__ void load_dgrad_a(uint32_t tile, const float* __restr
                                              const sp_conv_geom& g, const PixelRows& pr, int k0,
                                              int k_end, bool vec, int t) {
   const int c8 = t & 7;
-  const int rsw = (t >> 3) & 7;
-  const uint32_t dst0 = tile + (uint32_t)((t >> 6) * 1024 + rsw * 128 + ((c8 ^ rsw) << 4));
+  const uint32_t dst0 = tile + kmajor_off(t >> 3, c8);
   const int k = k0 + 4 * c8;
   const int nvals = vec ? 1 : 4;
+  const bool unit = (g.sy == 1) && (g.sx == 1);  // no stride holes: skip the divisions
 #pragma unroll 1
   for (int e = 0; e < nvals; ++e) {
     const int ke = k + e;
@@ -326,16 +340,21 @@ __device__ __forceinline__ void load_dgrad_a(uint32_t tile, const float* __restr
     const int dy = tap / g.KW, dx = tap - dy * g.KW;
     const bool kok = ke < k_end;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kRowsPerThread; ++i) {
       const int ty = pr.y[i] - dy, tx = pr.x[i] - dx;
-      const int oy = ty / g.sy, ox = tx / g.sx;
-      const bool ok = kok && pr.img[i] >= 0 && ty >= 0 && tx >= 0 && oy * g.sy == ty &&
-                      ox * g.sx == tx && oy < g.OH && ox < g.OW;
+      int oy = ty, ox = tx;
+      bool ok = kok && pr.img[i] >= 0 && ty >= 0 && tx >= 0;
+      if (!unit) {
+        oy = ty / g.sy;
+        ox = tx / g.sx;
+        ok = ok && oy * g.sy == ty && ox * g.sx == tx;
+      }
+      ok = ok && oy < g.OH && ox < g.OW;
       const float* src = gy + (((int64_t)pr.img[i] * g.OH + oy) * g.OW + ox) * g.K + ko;
       if (vec)
-        cp_async_16(dst0 + i * 2048, ok ? src : gy, ok);
+        cp_async_16(dst0 + i * 4096, ok ? src : gy, ok);
       else
-        cp_async_4(dst0 + i * 2048 + 4 * e, ok ? src : gy, ok);
+        cp_async_4(dst0 + i * 4096 + 4 * e, ok ? src : gy, ok);
     }
   }
 }
@@ -352,7 +371,7 @@ __device__ __forceinline__ void load_dgrad_b(uint32_t tile, const float* __restr
     const int ke = k + e;
     const int tap = ke / g.K, ko = ke - tap * g.K;
     const bool kok = ke < k_end;
-    for (int row = t >> 3; row < rows; row += 16) {
+    for (int row = t >> 3; row < rows; row += kRowStep) {
       const uint32_t dst = tile + kmajor_off(row, c8);
       const int c = c0 + row;
       const bool ok = kok && c < g.C;
@@ -366,11 +385,11 @@ __device__ __forceinline__ void load_dgrad_b(uint32_t tile, const float* __restr
 }
 
 // conv wgrad A: rows (MN) = (tap, c), k = output pixel;  MN-major 128-row tile.
-// Thread owns mn-chunk mc = t & 31 (fixed (tap, c)) and k-rows kk = 4*i + (t >> 5).
+// Thread owns mn-chunk mc = t & 31 (a fixed (tap, c)) and k-rows kk = 8 i + (t >> 5).
 __device__ __forceinline__ void load_wgrad_a(uint32_t tile, const float* __restrict__ x,
                                              const sp_conv_geom& g, int m0, int m_end, int k0,
                                              int k_end, bool vec, int t) {
-  const int mc = t & 31, w4 = t >> 5;
+  const int mc = t & 31, wq = t >> 5;
   const int nvals = vec ? 1 : 4;
 #pragma unroll 1
   for (int e = 0; e < nvals; ++e) {
@@ -379,11 +398,11 @@ __device__ __forceinline__ void load_wgrad_a(uint32_t tile, const float* __restr
     const int dy = tap / g.KW, dx = tap - dy * g.KW;
     const bool mok = m < m_end;
     int n, oy, ox;
-    split_pixel(k0 + w4, g.OH, g.OW, n, oy, ox);
+    split_pixel(k0 + wq, g.OH, g.OW, n, oy, ox);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int kk = 4 * i + w4;
-      const uint32_t dst = tile + mnmajor_off(kk, mc, 4);
+    for (int i = 0; i < BK / kProducerWarps; ++i) {
+      const int kk = kProducerWarps * i + wq;
+      const uint32_t dst = tile + mnmajor_off(kk, mc);
       const int iy = oy * g.sy + dy - g.pad_t, ix = ox * g.sx + dx - g.pad_l;
       const bool ok = mok && (k0 + kk < k_end) && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
       const float* src = x + (((int64_t)n * g.H + iy) * g.W + ix) * g.C + ch;
@@ -391,8 +410,8 @@ __device__ __forceinline__ void load_wgrad_a(uint32_t tile, const float* __restr
         cp_async_16(dst, ok ? src : x, ok);
       else
         cp_async_4(dst + 4 * e, ok ? src : x, ok);
-      // advance 4 output pixels in row-major (n, oy, ox) order
-      ox += 4;
+      // advance kProducerWarps output pixels in row-major (n, oy, ox) order
+      ox += kProducerWarps;
       while (ox >= g.OW) {
         ox -= g.OW;
         if (++oy == g.OH) {
@@ -407,17 +426,21 @@ __device__ __forceinline__ void load_wgrad_a(uint32_t tile, const float* __restr
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
+// sync_mode 0 (default): producers never wait for their own loads -- the stage's `full`
+//   mbarrier receives each thread's arrival asynchronously when its cp.asyncs have landed
+//   (cp.async.mbarrier.arrive.noinc), the same protocol as CUTLASS's sm100 cp.async mainloop.
+// sync_mode 1 (debug): wait_group 0 + fence.proxy.async + arrive after every stage.
 template <int MODE, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
     igemm_umma_kernel(const __grid_constant__ IgemmParams p, const int bn, const int a_vec,
-                      const int b_vec) {
+                      const int b_vec, const int sync_mode) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kStages + 1];
   __shared__ uint32_t tmem_slot;
 
   const int t = threadIdx.x;
   const int warp = t >> 5;
-  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B align
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms: 1024-B align
   const uint32_t b_tile_bytes = (uint32_t)bn * BK * 4;
   const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
   const uint32_t bar0 = smem_u32(bars);
@@ -452,20 +475,20 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)bn);
+  if (warp == kProducerWarps) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)bn);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // =========================== PRODUCERS ==============================================
     PixelRows pr;
     if (MODE == kFprop || MODE == kDgrad) {
       const sp_conv_geom& g = p.g;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t m = m0 + i * 16 + (t >> 3);
+      for (int i = 0; i < kRowsPerThread; ++i) {
+        const int64_t m = m0 + i * kRowStep + (t >> 3);
         if (m < p.M) {
           int n, a, b;
           if (MODE == kFprop) {
@@ -515,30 +538,32 @@ __global__ void __launch_bounds__(kThreads, 1)
         // fprop: w[k, n]; wgrad: gy[pixel, n] -- both dense row-major [K, N]
         load_dense_mnmajor(b_tile, B, p.N, n0, p.N, k0, k_end, bn, b_vec, t);
       }
-      cp_async_commit();
-      if (it >= kLookahead - 1) {
-        cp_async_wait<kLookahead - 1>();
+      if (sync_mode == 0) {
+        cp_async_arrive_on(full_bar(s));
+      } else {
+        cp_async_commit();
+        cp_async_wait<0>();
         fence_proxy_async();
-        mbar_arrive(full_bar((it - (kLookahead - 1)) % kStages));
+        mbar_arrive(full_bar(s));
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int j = max(0, n_it - (kLookahead - 1)); j < n_it; ++j) mbar_arrive(full_bar(j % kStages));
 
     // =========================== EPILOGUE ===============================================
-    const int64_t m = m0 + t;  // TMEM lane == tile row; warp w owns lanes [32w, 32w+32)
+    // TMEM lane == tile row.  Warp w reads lane quadrant (w & 3); the two warps sharing a
+    // quadrant interleave the 32-column chunks.
+    const int quad = warp & 3, half = warp >> 2;
+    const int64_t m = m0 + quad * 32 + (t & 31);
     if (n_it > 0) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
     }
     float* __restrict__ crow = C + m * p.ldc;
     const bool vec_store = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    for (int cb = 0; cb < bn; cb += 32) {
+    for (int cb = 32 * half; cb < bn; cb += 64) {
       if (n0 + cb >= p.N) break;  // warp-uniform
       uint32_t v[32];
       if (n_it > 0) {
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb, v);
         tmem_ld_wait();
       } else {
 #pragma unroll
@@ -562,21 +587,23 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (t == kProducers) {
     // =========================== MMA ISSUER (one thread) ================================
     const uint32_t idesc = instr_desc_tf32(bn, A_MN, B_MN);
-    const uint32_t b_atoms = (uint32_t)bn >> 5;
     for (int it = 0; it < n_it; ++it) {
       const int s = it % kStages;
       mbar_wait(full_bar(s), (uint32_t)(it / kStages) & 1u);
+      fence_proxy_async();  // landed cp.async data (generic proxy) -> tcgen05 reads (async proxy)
       tc_fence_after();
       const uint32_t a_tile = tiles + (uint32_t)s * stage_bytes;
       const uint32_t b_tile = a_tile + kATileBytes;
 #pragma unroll
       for (int k = 0; k < BK / 8; ++k) {
-        // K-major: advance 32 B inside the swizzle row; MN-major: next 8-k group of atoms
-        const uint64_t adesc = A_MN ? smem_desc(a_tile + (uint32_t)k * 4096u, 1024u, 4096u)
-                                    : smem_desc(a_tile + (uint32_t)k * 32u, 16u, 1024u);
+        // one MMA consumes 8 k-values.  K-major: +32 B inside the swizzled 128-B rows;
+        // MN-major: two 4-k groups further = +1024 B (MN blocks 4096 B apart, 4-k groups 512 B)
+        const uint64_t adesc =
+            A_MN ? smem_desc(a_tile + (uint32_t)k * 1024u, 4096u, 512u, kLayoutSw128Base32)
+                 : smem_desc(a_tile + (uint32_t)k * 32u, 16u, 1024u, kLayoutSw128);
         const uint64_t bdesc =
-            B_MN ? smem_desc(b_tile + (uint32_t)k * b_atoms * 1024u, 1024u, b_atoms * 1024u)
-                 : smem_desc(b_tile + (uint32_t)k * 32u, 16u, 1024u);
+            B_MN ? smem_desc(b_tile + (uint32_t)k * 1024u, 4096u, 512u, kLayoutSw128Base32)
+                 : smem_desc(b_tile + (uint32_t)k * 32u, 16u, 1024u, kLayoutSw128);
         umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
       }
       umma_commit(empty_bar(s));  // stage reusable once these MMAs retire
@@ -587,8 +614,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   // ---- teardown ---------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)bn);
+  if (warp == kProducerWarps) tmem_dealloc(tmem_base, (uint32_t)bn);
 }
+
+int g_sync_mode = 0;
 
 int pick_bn(int64_t N) {
   if (N <= 32) return 32;
@@ -617,11 +646,13 @@ int launch(const IgemmParams& p, cudaStream_t st, bool a_vec, bool b_vec) {
   const int64_t gy = (p.N + bn - 1) / bn;
   if (z > 65535 || gy > 65535) return set_error(SP_ERR_UNSUPPORTED, "igemm_umma: grid too large");
   dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)gy, (unsigned)z);
-  kern<<<grid, kThreads, smem, st>>>(p, bn, a_vec ? 1 : 0, b_vec ? 1 : 0);
+  kern<<<grid, kThreads, smem, st>>>(p, bn, a_vec ? 1 : 0, b_vec ? 1 : 0, g_sync_mode);
   return 0;
 }
 
 }  // namespace
+
+void igemm_umma_set_sync_mode(int mode) { g_sync_mode = mode; }
 
 bool igemm_umma_supported(int mode, const IgemmParams& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return false;

@@ -5,11 +5,7 @@
 
 #include "common.cuh"
 
-namespace {
-
-constexpr int kThreads = 256;
-constexpr size_t kScratchFloats = 1 << 20;  // 4 MB of partial sums
-
+namespace sp {
 // One scratch buffer per device, allocated on first use (before any graph capture: the
 // first training step always runs eagerly).  The library is used from one stream per
 // process (SURVEY.md 8b "Threading"), so reuse across calls is ordered by that stream.
@@ -22,6 +18,14 @@ float* scratch_for_current_device() {
   }
   return bufs[dev];
 }
+}  // namespace sp
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr size_t kScratchFloats = sp::kScratchFloats / 2;  // this file's half of the scratch
+
+float* scratch_for_current_device() { return sp::scratch_for_current_device(); }
 
 // ---- sum over the middle axis of [outer, reduce, inner] -------------------------------
 

@@ -49,6 +49,20 @@ def test_training_matches_reference(kind, batch, steps, precision, golden):
     assert np.array_equal(np.argmax(np.asarray(pred.array), 1).shape, (batch,))
 
 
+def assert_first_adam_step_close(p_new, p0_new, g0, rtol, grad_rtol, alpha=1e-3):
+    """First Adam step: w -= alpha * g / (|g| + eps') = alpha * sign(g) for all but tiny g.
+    Elements whose reference gradient is ~0 are ill-conditioned (their sign is rounding
+    noise): they are only required to stay inside the 2*alpha envelope; every
+    well-conditioned element must match to the weight tolerance."""
+    p_new, p0_new, g0 = (np.asarray(t, np.float64) for t in (p_new, p0_new, g0))
+    diff = np.abs(p_new - p0_new)
+    assert diff.max() <= 2.05 * alpha
+    solid = np.abs(g0) > 5 * grad_rtol * np.abs(g0).max()
+    assert solid.mean() > 0.8
+    scale = max(np.abs(p0_new).max(), 1e-30)
+    assert (diff[solid] / scale).max() <= rtol, (diff[solid] / scale).max()
+
+
 def test_cnn_batch128_one_step_vs_oracle(precision):
     """BASELINE config[1] at full size: one training step of the CIFAR CNN at batch 128."""
     x, y = workloads.synthetic_batch("cnn", 128)
@@ -59,7 +73,8 @@ def test_cnn_batch128_one_step_vs_oracle(precision):
     assert_close(loss_val.array, loss0, LOSS_RTOL[precision], "loss")
     for i, (p, p0) in enumerate(zip(wl.learnables, model.params)):
         assert_close(grads[p], grads0[p0], GRAD_RTOL[precision], f"gradient {i}")
-        assert_close(p.array, p0.value, WEIGHT_RTOL[precision], f"weights {i} after Adam")
+        assert_first_adam_step_close(p.array, p0.value, grads0[p0], WEIGHT_RTOL[precision],
+                                     GRAD_RTOL[precision])
 
 
 def test_vgg_small_one_step_vs_oracle(precision):
