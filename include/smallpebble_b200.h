@@ -190,12 +190,14 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
 
 /* ---- optimisers (sp.py:552-583 Adam, 645-653 SGD), multi-tensor ---------------------- */
 /* All pointer tables are HOST arrays of device pointers (passed by value to the kernel).
- * For tensor i with step count t[i] (already incremented):
+ * host_step[i] points to a DEVICE int32 holding the number of completed steps of tensor i;
+ * the launch uses t = *step + 1 and then increments it, so no launch parameter depends on
+ * the step (a captured CUDA graph of the training step stays valid):
  *   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ;
  *   p -= alpha * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)        */
 int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_g,
                   float* const* host_m, float* const* host_v, const int64_t* host_numel,
-                  const int32_t* host_t, float alpha, float beta1, float beta2, float eps,
+                  int32_t* const* host_step, float alpha, float beta1, float beta2, float eps,
                   sp_stream_t stream);
 int sp_sgd_multi(int n_tensors, float* const* host_p, const float* const* host_g,
                  const int64_t* host_numel, float lr, sp_stream_t stream);

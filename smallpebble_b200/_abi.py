@@ -74,7 +74,7 @@ SIGNATURES = {
     "sp_conv2d_wgrad_workspace": (sz, [C.POINTER(ConvGeom), C.c_int]),
     "sp_conv2d_wgrad": (C.c_int, [vp, vp, vp, C.POINTER(ConvGeom), C.c_int, vp, sz, vp]),
     "sp_adam_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
-                                C.POINTER(vp), p_i64, C.POINTER(i32), f32, f32, f32, f32, vp]),
+                                C.POINTER(vp), p_i64, C.POINTER(vp), f32, f32, f32, f32, vp]),
     "sp_sgd_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), p_i64, f32, vp]),
     "sp_pack_multi": (C.c_int, [C.c_int, C.POINTER(vp), p_i64, p_i64, vp, vp]),
 }

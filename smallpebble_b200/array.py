@@ -55,17 +55,30 @@ def require_cuda():
     _device = torch.device("cuda", torch.cuda.current_device())
     # bind our statically linked CUDA runtime to torch's context on this device
     torch.empty(1, device=_device)
+    global _raw_stream, _device_index
+    _device_index = _device.index
+    _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if _raw_stream is None:  # older torch: slower, same handle
+        _raw_stream = lambda idx: torch.cuda.current_stream(idx).cuda_stream  # noqa: E731
     return _device
 
 
 def reset_device_cache():
     """Call after torch.cuda.set_device() (one process per GPU: smallpebble_b200.distributed)."""
-    global _device
+    global _device, _raw_stream
     _device = None
+    _raw_stream = None
+
+
+_raw_stream = None
+_device_index = 0
 
 
 def stream() -> int:
-    return _lazy_torch().cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream on our device (all kernels launch here)."""
+    if _raw_stream is None:
+        require_cuda()
+    return _raw_stream(_device_index)
 
 
 def _host_dtype(a: np.ndarray) -> np.dtype:
@@ -91,12 +104,15 @@ class DeviceArray:
     # ---- construction ---------------------------------------------------------------------
     @staticmethod
     def empty(shape, dtype=FLOAT) -> "DeviceArray":
-        dev = require_cuda()
-        dtype = np.dtype(dtype)
-        shape = tuple(int(s) for s in shape)
-        nbytes = max(math.prod(shape), 1) * dtype.itemsize
-        buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
-        return DeviceArray(shape, dtype, buf, buf.data_ptr())
+        dev = _device if _device is not None else require_cuda()
+        self = object.__new__(DeviceArray)
+        self.shape = shape = tuple(shape)
+        self.dtype = dtype = dtype if dtype is FLOAT else np.dtype(dtype)
+        self.size = size = math.prod(shape)
+        self._buf = buf = _torch.empty((size or 1) * dtype.itemsize, dtype=_torch.uint8, device=dev)
+        self._ptr = buf.data_ptr()
+        self._host = None
+        return self
 
     @staticmethod
     def from_host(a, dtype=None) -> "DeviceArray":

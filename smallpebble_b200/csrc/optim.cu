@@ -3,6 +3,8 @@
 // CUDA block owns one 4096-element chunk of one tensor.  HBM-bound: Adam touches
 // 28 B/param (read p,g,m,v; write p,m,v), all with 128-bit accesses.
 // Replaces the Python loop + ~10 NumPy temporaries per variable of sp.py:573-583.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -16,8 +18,7 @@ struct AdamArgs {
   float* m[kMaxTensors];
   float* v[kMaxTensors];
   int64_t n[kMaxTensors];
-  float inv_c1[kMaxTensors];  // 1 / (1 - beta1^t)
-  float inv_c2[kMaxTensors];  // 1 / (1 - beta2^t)
+  int32_t* step[kMaxTensors];  // device-resident count of COMPLETED steps of this tensor
   int block_start[kMaxTensors + 1];
   int count;
 };
@@ -45,17 +46,28 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
   p = p - alpha * (m * ic1) / (sqrtf(v * ic2) + eps);
 }
 
+// The bias corrections 1/(1 - beta^t) are evaluated on the device from a device-resident
+// step count (in double: 1 - 0.999 loses 1e-5 relative in fp32), so the launch carries no
+// step-dependent parameter and a captured CUDA graph of the training step stays valid.
 __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_constant__ AdamArgs a,
-                                                              float alpha, float b1, float b2,
+                                                              float alpha, double b1d, double b2d,
                                                               float eps) {
+  __shared__ float corr[2];
   const int t = find_tensor(a, blockIdx.x);
+  if (threadIdx.x == 0) {
+    const double step = (double)(*a.step[t] + 1);
+    corr[0] = (float)(1.0 / (1.0 - pow(b1d, step)));
+    corr[1] = (float)(1.0 / (1.0 - pow(b2d, step)));
+  }
+  __syncthreads();
+  const float b1 = (float)b1d, b2 = (float)b2d;
   const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * kChunk;
   const int64_t n = a.n[t];
   float* __restrict__ p = a.p[t];
   const float* __restrict__ g = a.g[t];
   float* __restrict__ m = a.m[t];
   float* __restrict__ v = a.v[t];
-  const float ic1 = a.inv_c1[t], ic2 = a.inv_c2[t];
+  const float ic1 = corr[0], ic2 = corr[1];
   const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
   const int64_t end = min(n, base + kChunk);
   if (vec) {
@@ -82,6 +94,11 @@ __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_const
   }
 }
 
+// runs after adam_multi_kernel on the same stream: step[t] += 1
+__global__ void adam_advance_kernel(const __grid_constant__ AdamArgs a) {
+  for (int t = threadIdx.x; t < a.count; t += blockDim.x) *a.step[t] += 1;
+}
+
 __global__ void __launch_bounds__(kThreads) sgd_multi_kernel(const __grid_constant__ AxpyArgs a,
                                                              float lr) {
   const int t = find_tensor(a, blockIdx.x);
@@ -103,13 +120,25 @@ __global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_const
 }
 
 inline int blocks_for(int64_t n) { return (int)((n + kChunk - 1) / kChunk); }
+
+// The ABI carries beta1/beta2 as float; the reference computes with the Python float the
+// user wrote (0.9, 0.999).  Recover it: the shortest decimal that round-trips the float.
+inline double strtod_round(float f) {
+  char buf[32];
+  snprintf(buf, sizeof(buf), "%.9g", (double)f);
+  for (int digits = 1; digits <= 9; ++digits) {
+    snprintf(buf, sizeof(buf), "%.*g", digits, (double)f);
+    if ((float)strtod(buf, nullptr) == f) return strtod(buf, nullptr);
+  }
+  return (double)f;
+}
 }  // namespace
 
 extern "C" {
 
 int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_g,
                   float* const* host_m, float* const* host_v, const int64_t* host_numel,
-                  const int32_t* host_t, float alpha, float beta1, float beta2, float eps,
+                  int32_t* const* host_step, float alpha, float beta1, float beta2, float eps,
                   sp_stream_t stream) {
   SP_REQUIRE(n_tensors >= 0, "negative tensor count");
   cudaStream_t st = sp::as_stream(stream);
@@ -118,23 +147,28 @@ int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_
     a.count = 0;
     int blocks = 0;
     for (int i = first; i < n_tensors && i < first + kMaxTensors; ++i) {
-      if (host_numel[i] <= 0) continue;
-      SP_REQUIRE(host_t[i] >= 1, "Adam step count must be >= 1");
+      SP_REQUIRE(host_step[i] != nullptr, "missing device step counter");
       const int k = a.count++;
       a.p[k] = host_p[i];
       a.g[k] = host_g[i];
       a.m[k] = host_m[i];
       a.v[k] = host_v[i];
-      a.n[k] = host_numel[i];
-      a.inv_c1[k] = (float)(1.0 / (1.0 - pow((double)beta1, (double)host_t[i])));
-      a.inv_c2[k] = (float)(1.0 / (1.0 - pow((double)beta2, (double)host_t[i])));
+      a.n[k] = host_numel[i] > 0 ? host_numel[i] : 0;
+      a.step[k] = host_step[i];
       a.block_start[k] = blocks;
-      blocks += blocks_for(host_numel[i]);
+      blocks += blocks_for(a.n[k]);
     }
     if (a.count == 0) continue;
     a.block_start[a.count] = blocks;
-    adam_multi_kernel<<<blocks, kThreads, 0, st>>>(a, alpha, beta1, beta2, eps);
-    SP_CHECK_LAUNCH("adam_multi");
+    if (blocks > 0) {
+      // beta as the double nearest to what the caller wrote (0.9f -> 0.9), like the reference
+      const double b1 = strtod_round(beta1);
+      const double b2 = strtod_round(beta2);
+      adam_multi_kernel<<<blocks, kThreads, 0, st>>>(a, alpha, b1, b2, eps);
+      SP_CHECK_LAUNCH("adam_multi");
+    }
+    adam_advance_kernel<<<1, 32, 0, st>>>(a);
+    SP_CHECK_LAUNCH("adam_advance");
   }
   return 0;
 }

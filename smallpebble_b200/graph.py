@@ -113,6 +113,7 @@ class Adam:
         self.t = {}
         self.m = {}
         self.v = {}
+        self._step = {}  # Variable -> device int32[1]: completed steps (read by the kernel)
 
     def training_step(self, variables, gradients) -> None:
         from . import distributed
@@ -123,14 +124,13 @@ class Adam:
         grads = [_device_gradient(v, gradients) for v in variables]
         if distributed.is_initialized() and distributed.world_size() > 1:
             grads = distributed.allreduce_gradients(grads)
-        ts = []
         for v in variables:
             if v not in self.t:
                 self.t[v] = 0
                 self.m[v] = DeviceArray.zeros(v.array.shape)
                 self.v[v] = DeviceArray.zeros(v.array.shape)
-            self.t[v] += 1
-            ts.append(self.t[v])
+                self._step[v] = DeviceArray.from_host(np.zeros(1, np.int32), dtype=np.int32)
+            self.t[v] += 1  # host mirror of the device-resident step count
         n = len(variables)
         F.sp_adam_multi(
             n,
@@ -139,7 +139,7 @@ class Adam:
             _ptr_table([self.m[v].ptr for v in variables]),
             _ptr_table([self.v[v].ptr for v in variables]),
             _abi.dims([v.array.size for v in variables]),
-            (C.c_int32 * n)(*ts),
+            _ptr_table([self._step[v].ptr for v in variables]),
             self.alpha, self.beta1, self.beta2, self.eps, A.stream(),
         )
 

@@ -46,6 +46,14 @@ def scaled_err(actual, expected) -> float:
     return float(np.max(np.abs(a - e))) / scale
 
 
+def rel_l2(actual, expected) -> float:
+    """||actual - expected||_2 / ||expected||_2."""
+    a = np.asarray(actual, dtype=np.float64).ravel()
+    e = np.asarray(expected, dtype=np.float64).ravel()
+    assert a.shape == e.shape
+    return float(np.linalg.norm(a - e) / max(np.linalg.norm(e), 1e-30))
+
+
 def assert_close(actual, expected, rtol, what=""):
     err = scaled_err(actual, expected)
     assert err <= rtol, f"{what}: scaled max error {err:.3e} > {rtol:.1e}"
