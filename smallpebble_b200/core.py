@@ -20,6 +20,7 @@ Differences from the reference, all internal:
 
 from __future__ import annotations
 
+import functools
 import math
 import os
 
@@ -616,6 +617,21 @@ def _conv_geom(n, h, w, c, kh, kw, k, sy, sx, pt, pl, oh, ow) -> _abi.ConvGeom:
     return _abi.ConvGeom(n, h, w, c, kh, kw, k, sy, sx, pt, pl, oh, ow)
 
 
+@functools.lru_cache(maxsize=1024)
+def _conv_plan(x_shape, w_shape, padding, strides):
+    """(ConvGeom, output shape, {precision: wgrad workspace bytes}) for one conv geometry."""
+    n_images, imheight, imwidth, channels = x_shape
+    kernheight, kernwidth, channels_in, channels_out = w_shape
+    if channels != channels_in:
+        raise ValueError(f"conv2d: images have {channels} channels, kernels expect {channels_in}")
+    stride_y, stride_x = strides
+    pt, _, pl, _, outh, outw = _window_geometry(
+        imheight, imwidth, kernheight, kernwidth, stride_y, stride_x, padding)
+    geom = _conv_geom(n_images, imheight, imwidth, channels, kernheight, kernwidth, channels_out,
+                      stride_y, stride_x, pt, pl, outh, outw)
+    return geom, (n_images, outh, outw, channels_out), {}
+
+
 def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(1, 1)) -> Variable:
     """2D convolution, with same api as tf.nn.conv2d (sp.py:124-163).
 
@@ -625,16 +641,9 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
     instead of np.add.at col2im, filter gradient with a deterministic split reduction).
     """
     x, w = images.array, kernels.array
-    n_images, imheight, imwidth, channels = x.shape
-    kernheight, kernwidth, channels_in, channels_out = w.shape
-    if channels != channels_in:
-        raise ValueError(f"conv2d: images have {channels} channels, kernels expect {channels_in}")
-    stride_y, stride_x = strides
-    pt, _, pl, _, outh, outw = _window_geometry(
-        imheight, imwidth, kernheight, kernwidth, stride_y, stride_x, padding)
-    geom = _conv_geom(n_images, imheight, imwidth, channels, kernheight, kernwidth, channels_out,
-                      stride_y, stride_x, pt, pl, outh, outw)
-    y = DeviceArray.empty((n_images, outh, outw, channels_out))
+    plan = _conv_plan(x.shape, w.shape, padding, tuple(strides))
+    geom, out_shape = plan[0], plan[1]
+    y = DeviceArray.empty(out_shape)
     if y.size:
         F.sp_conv2d_fprop(x.ptr, w.ptr, y.ptr, geom, _precision, A.stream())
 
@@ -646,10 +655,12 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
 
     def grad_kernels(g):
         dw = DeviceArray.empty(w.shape)
-        ws_bytes = _abi.load().sp_conv2d_wgrad_workspace(geom, _precision)
+        ws_bytes = plan[2].get(_precision)
+        if ws_bytes is None:
+            ws_bytes = plan[2][_precision] = _abi.load().sp_conv2d_wgrad_workspace(geom, _precision)
         ws = DeviceArray.empty((ws_bytes // 4,)) if ws_bytes else None
-        F.sp_conv2d_wgrad(x.ptr, g.ptr, dw.ptr, geom, _precision, ws.ptr if ws is not None else None,
-                          ws_bytes, A.stream())
+        F.sp_conv2d_wgrad(x.ptr, g.ptr, dw.ptr, geom, _precision,
+                          ws.ptr if ws is not None else None, ws_bytes, A.stream())
         return dw
 
     return Variable(y, [(images, grad_images), (kernels, grad_kernels)])

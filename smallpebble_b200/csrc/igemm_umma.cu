@@ -424,6 +424,261 @@ __device__ __forceinline__ void load_wgrad_a(uint32_t tile, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------
+// Fast producers (vector path).  ncu on the first version showed the kernel ISSUE-bound:
+// ~300 instructions per thread per k-block of address arithmetic (64-bit multiplies,
+// divisions by runtime shapes) against 24-48 KB of copies.  Everything that does not change
+// from one k-block to the next -- which smem chunk a thread fills, which tile rows /
+// pixels it reads, their base offsets -- is therefore computed once before the k-loop; per
+// k-block a thread only advances a (tap, channel) counter with carries and adds offsets.
+// All element offsets are 32-bit (igemm_umma_supported() guarantees tensors < 2^31 elems).
+// ---------------------------------------------------------------------------------------
+
+// this thread's k (a multiple of 4) as (dy, dx, ch) over an inner extent `inner` (C for
+// fprop, Kout for dgrad); advances by one k-block (32) with carries, no division.
+struct TapCounter {
+  int dy, dx, ch;
+  __device__ __forceinline__ void init(int k, int inner, int KW) {
+    const int tap = k / inner;
+    ch = k - tap * inner;
+    dy = tap / KW;
+    dx = tap - dy * KW;
+  }
+  __device__ __forceinline__ void advance(int inner, int KW) {
+    ch += BK;
+    while (ch >= inner) {
+      ch -= inner;
+      if (++dx == KW) {
+        dx = 0;
+        ++dy;
+      }
+    }
+  }
+};
+
+// conv fprop A, C % 4 == 0
+struct FpropAFast {
+  int base[kRowsPerThread];  // element offset of pixel (n, oy*sy-pt, ox*sx-pl), channel 0
+  int y0[kRowsPerThread], x0[kRowsPerThread];
+  TapCounter tc;
+  uint32_t dst0;
+  __device__ __forceinline__ void init(const IgemmParams& p, int64_t m0, int k_begin, int t) {
+    const sp_conv_geom& g = p.g;
+    dst0 = kmajor_off(t >> 3, t & 7);
+    tc.init(k_begin + 4 * (t & 7), g.C, g.KW);
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      const int64_t m = m0 + i * kRowStep + (t >> 3);
+      if (m < p.M) {
+        int n, oy, ox;
+        split_pixel((int)m, g.OH, g.OW, n, oy, ox);
+        y0[i] = oy * g.sy - g.pad_t;
+        x0[i] = ox * g.sx - g.pad_l;
+        base[i] = ((n * g.H + y0[i]) * g.W + x0[i]) * g.C;
+      } else {
+        y0[i] = -(1 << 24);  // never in bounds
+        x0[i] = 0;
+        base[i] = 0;
+      }
+    }
+  }
+  __device__ __forceinline__ void load(uint32_t tile, const float* __restrict__ x,
+                                       const sp_conv_geom& g) {
+    const int tapoff = (tc.dy * g.W + tc.dx) * g.C + tc.ch;
+    const bool kok = tc.dy < g.KH;
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      const bool ok = kok && (unsigned)(y0[i] + tc.dy) < (unsigned)g.H &&
+                      (unsigned)(x0[i] + tc.dx) < (unsigned)g.W;
+      cp_async_16(tile + dst0 + i * 4096, x + (ok ? base[i] + tapoff : 0), ok);
+    }
+    tc.advance(g.C, g.KW);
+  }
+};
+
+// conv dgrad A, unit strides, Kout % 4 == 0
+struct DgradAFast {
+  int base[kRowsPerThread];  // element offset of gy pixel (n, iy+pt, ix+pl), channel 0
+  int yb[kRowsPerThread], xb[kRowsPerThread];
+  TapCounter tc;
+  uint32_t dst0;
+  __device__ __forceinline__ void init(const IgemmParams& p, int64_t m0, int k_begin, int t) {
+    const sp_conv_geom& g = p.g;
+    dst0 = kmajor_off(t >> 3, t & 7);
+    tc.init(k_begin + 4 * (t & 7), g.K, g.KW);
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      const int64_t m = m0 + i * kRowStep + (t >> 3);
+      if (m < p.M) {
+        int n, iy, ix;
+        split_pixel((int)m, g.H, g.W, n, iy, ix);
+        yb[i] = iy + g.pad_t;
+        xb[i] = ix + g.pad_l;
+        base[i] = ((n * g.OH + yb[i]) * g.OW + xb[i]) * g.K;
+      } else {
+        yb[i] = -(1 << 24);
+        xb[i] = 0;
+        base[i] = 0;
+      }
+    }
+  }
+  __device__ __forceinline__ void load(uint32_t tile, const float* __restrict__ gy,
+                                       const sp_conv_geom& g) {
+    const int tapoff = tc.ch - (tc.dy * g.OW + tc.dx) * g.K;
+    const bool kok = tc.dy < g.KH;
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      const bool ok = kok && (unsigned)(yb[i] - tc.dy) < (unsigned)g.OH &&
+                      (unsigned)(xb[i] - tc.dx) < (unsigned)g.OW;
+      cp_async_16(tile + dst0 + i * 4096, gy + (ok ? base[i] + tapoff : 0), ok);
+    }
+    tc.advance(g.K, g.KW);
+  }
+};
+
+// conv dgrad B (w[tap, c, ko] as rows c, k = (tap, ko)), Kout % 4 == 0
+struct DgradBFast {
+  TapCounter tc;
+  int row0_off;  // (c0 + (t >> 3)) * Kout
+  int c_first;
+  uint32_t dst0;
+  __device__ __forceinline__ void init(const IgemmParams& p, int c0, int k_begin, int t) {
+    const sp_conv_geom& g = p.g;
+    dst0 = kmajor_off(t >> 3, t & 7);
+    tc.init(k_begin + 4 * (t & 7), g.K, g.KW);
+    c_first = c0 + (t >> 3);
+    row0_off = c_first * g.K;
+  }
+  __device__ __forceinline__ void load(uint32_t tile, const float* __restrict__ w,
+                                       const sp_conv_geom& g, int rows) {
+    const int tapoff = (tc.dy * g.KW + tc.dx) * g.C * g.K + tc.ch + row0_off;
+    const bool kok = tc.dy < g.KH;
+    for (int i = 0; i * kRowStep < rows; ++i) {
+      const bool ok = kok && (c_first + i * kRowStep) < g.C;
+      cp_async_16(tile + dst0 + i * 4096, w + (ok ? tapoff + i * kRowStep * g.K : 0), ok);
+    }
+    tc.advance(g.K, g.KW);
+  }
+};
+
+// conv wgrad A (transposed im2col), C % 4 == 0: a thread owns one (tap, channel-quad) and
+// BK / 8 pixel rows whose (n, oy, ox) advance by 32 pixels per k-block with carries.
+struct WgradAFast {
+  int n[BK / kProducerWarps], oy[BK / kProducerWarps], ox[BK / kProducerWarps];
+  int dy, dx, ch, step_n, step_y, step_x;
+  int pix;  // linear output-pixel index of row 0 (for the k_end test)
+  bool mok;
+  uint32_t dst0;
+  __device__ __forceinline__ void init(const IgemmParams& p, int m0, int k_begin, int t) {
+    const sp_conv_geom& g = p.g;
+    const int mc = t & 31, wq = t >> 5;
+    const int m = m0 + 4 * mc;
+    const int tap = m / g.C;
+    ch = m - tap * g.C;
+    dy = tap / g.KW - g.pad_t;
+    dx = tap - (tap / g.KW) * g.KW - g.pad_l;
+    mok = m < (int)p.M;
+    dst0 = mnmajor_off(wq, mc);  // + i * 8 rows * 128 B (8 % 4 == 0 keeps the swizzle phase)
+    pix = k_begin + wq;
+#pragma unroll
+    for (int i = 0; i < BK / kProducerWarps; ++i)
+      split_pixel(pix + kProducerWarps * i, g.OH, g.OW, n[i], oy[i], ox[i]);
+    // one k-block = 32 pixels = (step_n, step_y, step_x) in the mixed radix (OH, OW)
+    step_x = BK % g.OW;
+    const int q = BK / g.OW;
+    step_y = q % g.OH;
+    step_n = q / g.OH;
+  }
+  __device__ __forceinline__ void load(uint32_t tile, const float* __restrict__ x,
+                                       const sp_conv_geom& g, int k_end) {
+#pragma unroll
+    for (int i = 0; i < BK / kProducerWarps; ++i) {
+      const int iy = oy[i] * g.sy + dy, ix = ox[i] * g.sx + dx;
+      const bool ok = mok && (pix + kProducerWarps * i) < k_end && (unsigned)iy < (unsigned)g.H &&
+                      (unsigned)ix < (unsigned)g.W;
+      const int off = ((n[i] * g.H + iy) * g.W + ix) * g.C + ch;
+      cp_async_16(tile + dst0 + i * (kProducerWarps * 128), x + (ok ? off : 0), ok);
+      ox[i] += step_x;
+      if (ox[i] >= g.OW) {
+        ox[i] -= g.OW;
+        ++oy[i];
+      }
+      oy[i] += step_y;
+      if (oy[i] >= g.OH) {
+        oy[i] -= g.OH;
+        ++n[i];
+      }
+      n[i] += step_n;
+    }
+    pix += BK;
+  }
+};
+
+// dense [K, R] row-major operand (R contiguous) -> MN-major tile; R in {32, 64, 128, 256},
+// ld % 4 == 0.  A thread owns column chunk mc and every kstep-th k-row from kk0.
+struct DenseMnFast {
+  const float* ptr;   // &base[(k_begin + kk0) * ld + r0 + 4 mc]
+  int64_t jstride;    // kstep * ld
+  int64_t kstride;    // BK * ld
+  int kk0, kstep, njobs, kpos;
+  bool colok;
+  uint32_t dst0;
+  __device__ __forceinline__ void init(const float* base, int64_t ld, int64_t r0, int64_t r_end,
+                                       int64_t k_begin, int rows, int t) {
+    const int chunks = rows >> 2;          // power of two, 8..64
+    const int lg = __ffs(chunks) - 1;
+    const int mc = t & (chunks - 1);
+    kk0 = t >> lg;
+    kstep = kProducers >> lg;               // multiple of 4: the swizzle phase is constant
+    njobs = BK / kstep;
+    dst0 = mnmajor_off(kk0, mc);
+    colok = (r0 + 4 * mc) < r_end;
+    ptr = base + (k_begin + kk0) * ld + r0 + 4 * mc;
+    jstride = (int64_t)kstep * ld;
+    kstride = (int64_t)BK * ld;
+    kpos = (int)k_begin + kk0;
+  }
+  __device__ __forceinline__ void load(uint32_t tile, const float* __restrict__ base, int k_end) {
+    const float* q = ptr;
+    for (int j = 0; j < njobs; ++j) {
+      const bool ok = colok && (kpos + j * kstep) < k_end;
+      cp_async_16(tile + dst0 + j * kstep * 128, ok ? q : base, ok);
+      q += jstride;
+    }
+    ptr += kstride;
+    kpos += BK;
+  }
+};
+
+// dense [R, K] row-major operand (K contiguous) -> K-major tile; ld % 4 == 0, K % 4 == 0
+struct DenseKFast {
+  const float* ptr;  // &base[(r0 + (t >> 3)) * ld + k_begin + 4 c]
+  int64_t rstride;   // kRowStep * ld
+  int64_t row_first;
+  int kpos;
+  uint32_t dst0;
+  __device__ __forceinline__ void init(const float* base, int64_t ld, int64_t r0, int64_t k_begin,
+                                       int t) {
+    dst0 = kmajor_off(t >> 3, t & 7);
+    row_first = r0 + (t >> 3);
+    kpos = (int)k_begin + 4 * (t & 7);
+    ptr = base + row_first * ld + kpos;
+    rstride = (int64_t)kRowStep * ld;
+  }
+  __device__ __forceinline__ void load(uint32_t tile, const float* __restrict__ base,
+                                       int64_t r_end, int k_end, int rows) {
+    const bool kok = kpos < k_end;
+    const float* q = ptr;
+    for (int i = 0; i * kRowStep < rows; ++i) {
+      const bool ok = kok && (row_first + i * kRowStep) < r_end;
+      cp_async_16(tile + dst0 + i * 4096, ok ? q : base, ok);
+      q += rstride;
+    }
+    ptr += BK;
+    kpos += BK;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
 // sync_mode 0 (default): producers never wait for their own loads -- the stage's `full`
@@ -483,9 +738,32 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp < kProducerWarps) {
     // =========================== PRODUCERS ==============================================
+    // Fast (vector) producers where the operand is 16-byte chunkable, the generic
+    // element-wise loaders otherwise (C = 3, odd leading dimensions, strided dgrad, ...).
+    const sp_conv_geom& g = p.g;
+    const bool a_fast = a_vec && !(MODE == kDgrad && (g.sy != 1 || g.sx != 1));
+    const bool b_fast = b_vec != 0;
     PixelRows pr;
-    if (MODE == kFprop || MODE == kDgrad) {
-      const sp_conv_geom& g = p.g;
+    FpropAFast fa;
+    DgradAFast da;
+    WgradAFast wa;
+    DgradBFast db;
+    DenseMnFast a_mn, b_mn;
+    DenseKFast a_k, b_k;
+    if (a_fast) {
+      if (MODE == kGemm) {
+        if (A_MN)
+          a_mn.init(A, p.a_cs, m0, p.M, k_begin, BM, t);
+        else
+          a_k.init(A, p.a_rs, m0, k_begin, t);
+      } else if (MODE == kFprop) {
+        fa.init(p, m0, (int)k_begin, t);
+      } else if (MODE == kDgrad) {
+        da.init(p, m0, (int)k_begin, t);
+      } else {
+        wa.init(p, (int)m0, (int)k_begin, t);
+      }
+    } else if (MODE == kFprop || MODE == kDgrad) {
 #pragma unroll
       for (int i = 0; i < kRowsPerThread; ++i) {
         const int64_t m = m0 + i * kRowStep + (t >> 3);
@@ -507,6 +785,18 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     }
+    if (b_fast) {
+      if (MODE == kGemm) {
+        if (B_MN)
+          b_mn.init(B, p.b_rs, n0, p.N, k_begin, bn, t);
+        else
+          b_k.init(B, p.b_cs, n0, k_begin, t);
+      } else if (MODE == kDgrad) {
+        db.init(p, (int)n0, (int)k_begin, t);
+      } else {
+        b_mn.init(B, p.N, n0, p.N, k_begin, bn, t);
+      }
+    }
     for (int it = 0; it < n_it; ++it) {
       const int s = it % kStages;
       if (it >= kStages) mbar_wait(empty_bar(s), (uint32_t)((it / kStages) - 1) & 1u);
@@ -514,7 +804,20 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t b_tile = a_tile + kATileBytes;
       const int64_t k0 = k_begin + (int64_t)it * BK;
       // ---- A ----
-      if (MODE == kGemm) {
+      if (a_fast) {
+        if (MODE == kGemm) {
+          if (A_MN)
+            a_mn.load(a_tile, A, (int)k_end);
+          else
+            a_k.load(a_tile, A, p.M, (int)k_end, BM);
+        } else if (MODE == kFprop) {
+          fa.load(a_tile, A, g);
+        } else if (MODE == kDgrad) {
+          da.load(a_tile, A, g);
+        } else {
+          wa.load(a_tile, A, g, (int)k_end);
+        }
+      } else if (MODE == kGemm) {
         if (A_MN)
           load_dense_mnmajor(a_tile, A, p.a_cs, m0, p.M, k0, k_end, BM, a_vec, t);
         else
@@ -527,7 +830,18 @@ __global__ void __launch_bounds__(kThreads, 1)
         load_wgrad_a(a_tile, A, p.g, (int)m0, (int)p.M, (int)k0, (int)k_end, a_vec, t);
       }
       // ---- B ----
-      if (MODE == kGemm) {
+      if (b_fast) {
+        if (MODE == kGemm) {
+          if (B_MN)
+            b_mn.load(b_tile, B, (int)k_end);
+          else
+            b_k.load(b_tile, B, p.N, (int)k_end, bn);
+        } else if (MODE == kDgrad) {
+          db.load(b_tile, B, g, bn);
+        } else {
+          b_mn.load(b_tile, B, (int)k_end);  // fprop: w[k, n]; wgrad: gy[pixel, n]
+        }
+      } else if (MODE == kGemm) {
         if (B_MN)
           load_dense_mnmajor(b_tile, B, p.b_rs, n0, p.N, k0, k_end, bn, b_vec, t);
         else

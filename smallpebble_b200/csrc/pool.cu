@@ -23,46 +23,47 @@ __device__ __forceinline__ void take(float v, int k, float& best, int& bi) {
   }
 }
 
+// One CUDA block row per output row (n, oy): blockIdx.x walks rows, threads walk (ox, c4)
+// -- no 64-bit divisions, consecutive threads touch consecutive 16-byte chunks.
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_vec4(const float* __restrict__ x,
                                                              float* __restrict__ y,
                                                              uint8_t* __restrict__ idx,
                                                              PoolGeom g) {
   const int C4 = g.C >> 2;
-  const int64_t total = (int64_t)g.N * g.OH * g.OW * C4;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(t % C4);
-    int64_t r = t / C4;
-    const int ox = (int)(r % g.OW);
-    r /= g.OW;
-    const int oy = (int)(r % g.OH);
-    const int n = (int)(r / g.OH);
-    const int iy0 = oy * g.sy - g.pt, ix0 = ox * g.sx - g.pl;
-    float4 best;
-    int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    bool first = true;
-    for (int dy = 0; dy < g.KH; ++dy) {
-      const int iy = iy0 + dy;
-      for (int dx = 0; dx < g.KW; ++dx) {
-        const int ix = ix0 + dx;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // zero padding takes part in the max
-        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
-          v = ld_stream_f4(x + (((int64_t)n * g.H + iy) * g.W + ix) * g.C + 4 * c4);
-        if (first) {
-          best = v;
-          first = false;
-        } else {
+  const int row_len = g.OW * C4;
+  const int n_rows = g.N * g.OH;
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int n = row / g.OH, oy = row - n * g.OH;
+    const int iy0 = oy * g.sy - g.pt;
+    const float* __restrict__ xin = x + (int64_t)n * g.H * g.W * g.C;
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < row_len; e += gridDim.y * blockDim.x) {
+      const int ox = e / C4, c4 = e - ox * C4;
+      const int ix0 = ox * g.sx - g.pl;
+      float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+      int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+      for (int dy = 0; dy < g.KH; ++dy) {
+        const int iy = iy0 + dy;
+        for (int dx = 0; dx < g.KW; ++dx) {
+          const int ix = ix0 + dx;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // zero padding takes part in the max
+          if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W)
+            v = ld_stream_f4(xin + ((int64_t)iy * g.W + ix) * g.C + 4 * c4);
           const int k = dy * g.KW + dx;
-          take(v.x, k, best.x, b0);
-          take(v.y, k, best.y, b1);
-          take(v.z, k, best.z, b2);
-          take(v.w, k, best.w, b3);
+          if (k == 0) {
+            best = v;
+          } else {
+            take(v.x, k, best.x, b0);
+            take(v.y, k, best.y, b1);
+            take(v.z, k, best.z, b2);
+            take(v.w, k, best.w, b3);
+          }
         }
       }
+      const int64_t o = (int64_t)row * row_len + e;
+      reinterpret_cast<float4*>(y)[o] = best;
+      reinterpret_cast<uchar4*>(idx)[o] =
+          make_uchar4((unsigned char)b0, (unsigned char)b1, (unsigned char)b2, (unsigned char)b3);
     }
-    reinterpret_cast<float4*>(y)[t] = best;
-    reinterpret_cast<uchar4*>(idx)[t] =
-        make_uchar4((unsigned char)b0, (unsigned char)b1, (unsigned char)b2, (unsigned char)b3);
   }
 }
 
@@ -103,43 +104,60 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_scalar(const float* __re
   }
 }
 
-// windows visited in increasing (oy, ox): the order np.add.at accumulates them in
+// windows visited in increasing (oy, ox): the order np.add.at accumulates them in.
+// One block row per input row (n, iy); NONOVERLAP (stride == window, the pooling layers of
+// every BASELINE model): exactly one candidate window per pixel, no loops, no modulo.
+template <bool NONOVERLAP>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_vec4(const float* __restrict__ gy,
                                                              const uint8_t* __restrict__ idx,
                                                              float* __restrict__ dx,
                                                              PoolGeom g) {
   const int C4 = g.C >> 2;
-  const int64_t total = (int64_t)g.N * g.H * g.W * C4;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(t % C4);
-    int64_t r = t / C4;
-    const int ix = (int)(r % g.W);
-    r /= g.W;
-    const int iy = (int)(r % g.H);
-    const int n = (int)(r / g.H);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int dy = g.KH - 1; dy >= 0; --dy) {
-      const int ty = iy + g.pt - dy;
-      if (ty < 0 || ty % g.sy != 0) continue;
-      const int oy = ty / g.sy;
-      if (oy >= g.OH) continue;
-      for (int dxx = g.KW - 1; dxx >= 0; --dxx) {
-        const int tx = ix + g.pl - dxx;
-        if (tx < 0 || tx % g.sx != 0) continue;
-        const int ox = tx / g.sx;
-        if (ox >= g.OW) continue;
-        const int64_t o = (((int64_t)n * g.OH + oy) * g.OW + ox) * C4 + c4;
-        const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(idx) + o);
-        const float4 gv = ld_stream_f4(gy + 4 * o);
-        const int want = dy * g.KW + dxx;
-        if (k.x == want) acc.x += gv.x;
-        if (k.y == want) acc.y += gv.y;
-        if (k.z == want) acc.z += gv.z;
-        if (k.w == want) acc.w += gv.w;
+  const int row_len = g.W * C4;
+  const int n_rows = g.N * g.H;
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int n = row / g.H, iy = row - n * g.H;
+    const int64_t obase = (int64_t)n * g.OH * g.OW * C4;
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < row_len; e += gridDim.y * blockDim.x) {
+      const int ix = e / C4, c4 = e - ix * C4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (NONOVERLAP) {
+        const int ty = iy + g.pt, tx = ix + g.pl;
+        const int oy = ty / g.sy, ox = tx / g.sx;
+        if (oy < g.OH && ox < g.OW) {
+          const int want = (ty - oy * g.sy) * g.KW + (tx - ox * g.sx);
+          const int64_t o = obase + ((int64_t)oy * g.OW + ox) * C4 + c4;
+          const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(idx) + o);
+          const float4 gv = ld_stream_f4(gy + 4 * o);
+          acc.x = (k.x == want) ? gv.x : 0.f;
+          acc.y = (k.y == want) ? gv.y : 0.f;
+          acc.z = (k.z == want) ? gv.z : 0.f;
+          acc.w = (k.w == want) ? gv.w : 0.f;
+        }
+      } else {
+        for (int dy = g.KH - 1; dy >= 0; --dy) {
+          const int ty = iy + g.pt - dy;
+          if (ty < 0 || ty % g.sy != 0) continue;
+          const int oy = ty / g.sy;
+          if (oy >= g.OH) continue;
+          for (int dxx = g.KW - 1; dxx >= 0; --dxx) {
+            const int tx = ix + g.pl - dxx;
+            if (tx < 0 || tx % g.sx != 0) continue;
+            const int ox = tx / g.sx;
+            if (ox >= g.OW) continue;
+            const int64_t o = obase + ((int64_t)oy * g.OW + ox) * C4 + c4;
+            const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(idx) + o);
+            const float4 gv = ld_stream_f4(gy + 4 * o);
+            const int want = dy * g.KW + dxx;
+            if (k.x == want) acc.x += gv.x;
+            if (k.y == want) acc.y += gv.y;
+            if (k.z == want) acc.z += gv.z;
+            if (k.w == want) acc.w += gv.w;
+          }
+        }
       }
+      reinterpret_cast<float4*>(dx)[(int64_t)row * row_len + e] = acc;
     }
-    reinterpret_cast<float4*>(dx)[t] = acc;
   }
 }
 
@@ -177,6 +195,19 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_scalar(const float* __re
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// grid.x walks image rows, grid.y splits a row into 256-thread pieces; sized to >= 8 CTAs/SM
+inline dim3 row_grid(int n_rows, int row_len) {
+  const int sms = sp::device_info().sm_count > 0 ? sp::device_info().sm_count : 148;
+  int gy = (row_len + kThreads - 1) / kThreads;
+  if (gy < 1) gy = 1;
+  if (gy > 64) gy = 64;
+  int gx = n_rows;
+  const int cap = (sms * 8 + gy - 1) / gy;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
 int check(const PoolGeom& g) {
   if (g.N < 0 || g.H <= 0 || g.W <= 0 || g.C <= 0 || g.KH <= 0 || g.KW <= 0 || g.sy <= 0 ||
       g.sx <= 0 || g.OH < 0 || g.OW < 0)
@@ -198,7 +229,7 @@ int sp_maxpool2d_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W
   if (outs == 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
   if (C % 4 == 0 && aligned16(x) && aligned16(y) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0)
-    maxpool_fwd_vec4<<<sp::wave_grid(outs / 4, kThreads, 8), kThreads, 0, st>>>(x, y, idx, g);
+    maxpool_fwd_vec4<<<row_grid(N * OH, OW * (C / 4)), kThreads, 0, st>>>(x, y, idx, g);
   else
     maxpool_fwd_scalar<<<sp::wave_grid(outs, kThreads, 8), kThreads, 0, st>>>(x, y, idx, g);
   SP_CHECK_LAUNCH("maxpool2d_fwd");
@@ -214,7 +245,12 @@ int sp_maxpool2d_bwd(const float* gy, const uint8_t* idx, float* dx, int N, int 
   if (ins == 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
   if (C % 4 == 0 && aligned16(gy) && aligned16(dx) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0)
-    maxpool_bwd_vec4<<<sp::wave_grid(ins / 4, kThreads, 8), kThreads, 0, st>>>(gy, idx, dx, g);
+  {
+    if (sy == KH && sx == KW)
+      maxpool_bwd_vec4<true><<<row_grid(N * H, W * (C / 4)), kThreads, 0, st>>>(gy, idx, dx, g);
+    else
+      maxpool_bwd_vec4<false><<<row_grid(N * H, W * (C / 4)), kThreads, 0, st>>>(gy, idx, dx, g);
+  }
   else
     maxpool_bwd_scalar<<<sp::wave_grid(ins, kThreads, 8), kThreads, 0, st>>>(gy, idx, dx, g);
   SP_CHECK_LAUNCH("maxpool2d_bwd");

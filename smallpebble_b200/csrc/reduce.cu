@@ -83,6 +83,51 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restric
   }
 }
 
+// inner % 4 == 0, 16-byte aligned: each thread sums 4 adjacent columns with 128-bit loads,
+// 4 independent row streams in flight.  Block = 32 column-quads x 8 row-lanes.
+__global__ void __launch_bounds__(kThreads) colsum_vec4_kernel(const float* __restrict__ x,
+                                                               float* __restrict__ out,
+                                                               int64_t reduce, int64_t inner,
+                                                               int64_t chunk, int splits) {
+  __shared__ float4 tile[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t inner4 = inner >> 2;
+  const int64_t col4 = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t o = blockIdx.z;
+  const int split = blockIdx.y;
+  const int64_t lo = (int64_t)split * chunk, hi = min(reduce, lo + chunk);
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  if (col4 < inner4) {
+    const float* p = x + (o * reduce) * inner + 4 * col4;
+    int64_t r = lo + ty;
+    for (; r + 24 < hi; r += 32) {
+      const float4 v0 = ld_stream_f4(p + r * inner);
+      const float4 v1 = ld_stream_f4(p + (r + 8) * inner);
+      const float4 v2 = ld_stream_f4(p + (r + 16) * inner);
+      const float4 v3 = ld_stream_f4(p + (r + 24) * inner);
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+      a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+      a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+    }
+    for (; r < hi; r += 8) {
+      const float4 v0 = ld_stream_f4(p + r * inner);
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+  }
+  tile[ty][tx] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                             (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+  __syncthreads();
+  if (ty == 0 && col4 < inner4) {
+    float4 s = tile[0][tx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      s.x += tile[k][tx].x; s.y += tile[k][tx].y; s.z += tile[k][tx].z; s.w += tile[k][tx].w;
+    }
+    reinterpret_cast<float4*>(out + (o * splits + split) * inner)[col4] = s;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) maxall_partial_kernel(const float* __restrict__ x,
                                                                   float* __restrict__ part,
                                                                   int64_t n) {
@@ -222,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) xent_bwd_kernel(const float* __restr
 }
 
 // fused softmax + cross entropy: one warp per row; per-block partial loss.
-__global__ void __launch_bounds__(kThreads) softmax_xent_fwd_kernel(
+__global__ void __launch_bounds__(1024) softmax_xent_fwd_kernel(
     const float* __restrict__ logits, const int32_t* __restrict__ labels,
     float* __restrict__ probs, float* __restrict__ part, int64_t rows, int64_t cols) {
   __shared__ float red[32];
@@ -296,10 +341,12 @@ int reduce_sum_impl(const float* x, float* out, int64_t outer, int64_t reduce, i
       rowsum_kernel<<<dim3(1, (unsigned)outer), kThreads, 0, st>>>(part, out, splits, splits, 1);
     }
   } else {
-    const int64_t col_blocks = (inner + 31) / 32;
+    const bool vec = (inner % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int64_t col_blocks = vec ? (inner / 4 + 31) / 32 : (inner + 31) / 32;
     int splits = 1;
-    if (col_blocks * outer < 2 * sms && reduce >= 256) {
-      splits = (int)std::min<int64_t>((2 * sms) / (col_blocks * outer), reduce / 64);
+    if (col_blocks * outer < 4 * sms && reduce >= 128) {
+      splits = (int)std::min<int64_t>((4 * sms) / (col_blocks * outer), reduce / 32);
       if (splits < 1) splits = 1;
       if ((size_t)(outer * splits * inner) > kScratchFloats) splits = 1;
       if (splits > 65535) splits = 65535;
@@ -308,14 +355,20 @@ int reduce_sum_impl(const float* x, float* out, int64_t outer, int64_t reduce, i
     int64_t chunk = (reduce + splits - 1) / splits;
     splits = (int)((reduce + chunk - 1) / chunk);
     dim3 grid((unsigned)col_blocks, (unsigned)splits, (unsigned)outer);
+    auto launch = [&](const float* src, float* dst, int64_t red, int64_t ch, int sp_, dim3 gr) {
+      if (vec)
+        colsum_vec4_kernel<<<gr, kThreads, 0, st>>>(src, dst, red, inner, ch, sp_);
+      else
+        colsum_kernel<<<gr, kThreads, 0, st>>>(src, dst, red, inner, ch, sp_);
+    };
     if (splits == 1) {
-      colsum_kernel<<<grid, kThreads, 0, st>>>(x, out, reduce, inner, chunk, 1);
+      launch(x, out, reduce, chunk, 1, grid);
     } else {
       float* part = scratch_for_current_device();
       if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_reduce_sum: no scratch");
-      colsum_kernel<<<grid, kThreads, 0, st>>>(x, part, reduce, inner, chunk, splits);
+      launch(x, part, reduce, chunk, splits, grid);
       dim3 grid2((unsigned)col_blocks, 1, (unsigned)outer);
-      colsum_kernel<<<grid2, kThreads, 0, st>>>(part, out, splits, inner, splits, 1);
+      launch(part, out, splits, splits, 1, grid2);
     }
   }
   return 0;
@@ -408,7 +461,9 @@ int sp_softmax_xent_fwd(const float* logits, const int32_t* labels, float* probs
   if (rows == 0) return sp_fill_f32(loss, 1, 0.f, stream);
   const int blocks = rows <= 2048 ? 1 : sp::wave_grid(rows, kThreads / 32, 4);
   if (blocks == 1) {
-    softmax_xent_fwd_kernel<<<1, kThreads, 0, st>>>(logits, labels, probs, loss, rows, cols);
+    // one block so the loss needs no second pass; 32 warps = 32 rows in flight
+    softmax_xent_fwd_kernel<<<1, rows > 64 ? 1024 : kThreads, 0, st>>>(logits, labels, probs, loss,
+                                                                      rows, cols);
   } else {
     float* part = scratch_for_current_device();
     if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_softmax_xent_fwd: no scratch");

@@ -114,6 +114,7 @@ class Adam:
         self.m = {}
         self.v = {}
         self._step = {}  # Variable -> device int32[1]: completed steps (read by the kernel)
+        self._tables = {}  # ids of the parameter arrays -> cached ctypes pointer tables
 
     def training_step(self, variables, gradients) -> None:
         from . import distributed
@@ -132,16 +133,19 @@ class Adam:
                 self._step[v] = DeviceArray.from_host(np.zeros(1, np.int32), dtype=np.int32)
             self.t[v] += 1  # host mirror of the device-resident step count
         n = len(variables)
-        F.sp_adam_multi(
-            n,
-            _ptr_table([v.array.ptr for v in variables]),
-            _ptr_table([g.ptr for g in grads]),
-            _ptr_table([self.m[v].ptr for v in variables]),
-            _ptr_table([self.v[v].ptr for v in variables]),
-            _abi.dims([v.array.size for v in variables]),
-            _ptr_table([self._step[v].ptr for v in variables]),
-            self.alpha, self.beta1, self.beta2, self.eps, A.stream(),
-        )
+        key = tuple((id(v), v.array.ptr) for v in variables)
+        static = self._tables.get(key)
+        if static is None:  # pointer tables of everything that does not change step to step
+            static = self._tables[key] = (
+                _ptr_table([v.array.ptr for v in variables]),
+                _ptr_table([self.m[v].ptr for v in variables]),
+                _ptr_table([self.v[v].ptr for v in variables]),
+                _abi.dims([v.array.size for v in variables]),
+                _ptr_table([self._step[v].ptr for v in variables]),
+            )
+        p_tab, m_tab, v_tab, numel, step_tab = static
+        F.sp_adam_multi(n, p_tab, _ptr_table([g.ptr for g in grads]), m_tab, v_tab, numel,
+                        step_tab, self.alpha, self.beta1, self.beta2, self.eps, A.stream())
 
 
 def sgd_step(variables, gradients, learning_rate: float = 0.001) -> None:
