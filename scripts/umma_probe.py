@@ -45,10 +45,10 @@ def report(name, got, ref):
 def run(case):
     import smallpebble_b200 as sp
     from oracle import numpy_path as orc
-    from smallpebble_b200 import _abi
+    from smallpebble_b200 import _abi, core
 
     sp.set_precision("tf32")
-    _abi.load().sp_debug_set_umma_policy(1 + (16 if os.environ.get('SP_PROBE_SYNC') == '1' else 0))
+    core.debug_set_kernel_policy(1 + (16 if os.environ.get('SP_PROBE_SYNC') == '1' else 0))
     rng = np.random.default_rng(0)
     worst = 0.0
     if case.startswith("gemm"):

@@ -51,6 +51,14 @@ def get_precision() -> str:
     return "tf32" if _precision == _abi.PRECISION_TF32 else "fp32"
 
 
+def debug_set_kernel_policy(policy: int) -> None:
+    """Test hook (sp_debug_set_umma_policy): 0 default, 1 force the tcgen05 kernel, 2 force the
+    CUDA-core kernel (+16: conservative producer synchronisation).  Cached conv plans hold
+    policy-dependent workspace sizes, so they are dropped."""
+    _abi.f.sp_debug_set_umma_policy(policy)
+    _conv_plan.cache_clear()
+
+
 _fuse_softmax_xent = os.environ.get("SP_FUSE_SOFTMAX_XENT", "1") != "0"
 
 

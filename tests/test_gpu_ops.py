@@ -10,7 +10,7 @@ import cases as C
 import smallpebble_b200 as sp
 from conftest import RTOL, assert_close
 from oracle import numpy_path as orc
-from smallpebble_b200 import _abi
+from smallpebble_b200 import _abi, core
 
 pytestmark = pytest.mark.gpu
 
@@ -24,9 +24,9 @@ def grads_of(fn, arrays, gy):
 
 @pytest.fixture(params=[0, 1, 2], ids=["policy", "force_umma", "force_simt"])
 def umma_policy(request):
-    _abi.load().sp_debug_set_umma_policy(request.param)
+    core.debug_set_kernel_policy(request.param)
     yield request.param
-    _abi.load().sp_debug_set_umma_policy(0)
+    core.debug_set_kernel_policy(0)
 
 
 @pytest.mark.parametrize("case", C.CONV_CASES, ids=[c[0] for c in C.CONV_CASES])

@@ -7,7 +7,7 @@ import pytest
 
 import smallpebble_b200 as sp
 from conftest import RTOL, assert_close, scaled_err
-from smallpebble_b200 import _abi
+from smallpebble_b200 import _abi, core
 
 pytestmark = pytest.mark.gpu
 
@@ -61,12 +61,12 @@ def test_tensor_core_kernel_agrees_with_fp32_kernel(cfg):
 
     old = sp.get_precision()
     try:
-        _abi.load().sp_debug_set_umma_policy(1)
+        core.debug_set_kernel_policy(1)
         tf = run("tf32")
-        _abi.load().sp_debug_set_umma_policy(0)
+        core.debug_set_kernel_policy(0)
         fp = run("fp32")
     finally:
-        _abi.load().sp_debug_set_umma_policy(0)
+        core.debug_set_kernel_policy(0)
         sp.set_precision(old)
     for a, b, what in zip(tf, fp, ("y", "dX", "dW")):
         assert_close(a, b, RTOL["tf32"], f"{name} {what}: tcgen05 vs CUDA-core")
