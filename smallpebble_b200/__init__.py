@@ -12,6 +12,7 @@ import numpy as np  # noqa: F401
 
 from . import distributed  # noqa: F401
 from .array import DeviceArray, transfer_counters  # noqa: F401
+from .capture import CapturedStep, capture  # noqa: F401
 from .core import (  # noqa: F401
     Variable, add, add_at, broadcastinfo, conv2d, cross_entropy, div, exp, expand_dims,
     get_gradients, get_precision, getitem, leaky_relu, log, matmul, matrix_transpose, maxax,

@@ -48,6 +48,8 @@ void wgrad_split(const sp_conv_geom& g, bool umma, int* splits, int64_t* k_chunk
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   int64_t tiles;
   if (umma) {
+    // the kernel may pick a narrower N tile for small grids; the split only needs a rough
+    // count of output tiles, taken at the widest tile
     const int bn = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
     tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   } else {
@@ -157,6 +159,11 @@ int sp_conv2d_fprop(const float* x, const float* w, float* y, const sp_conv_geom
   p.ldc = g->K;
   if (p.M == 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
+  if (sp::g_umma_policy == 0 && sp::small_c_supported(*g)) {
+    if (int rc = sp::launch_conv_fprop_smallc(x, w, y, *g, st)) return rc;
+    SP_CHECK_LAUNCH("conv2d_fprop(small C)");
+    return 0;
+  }
   int rc = sp::use_umma(sp::kFprop, p, precision) ? sp::launch_igemm_umma(sp::kFprop, p, st)
                                                    : sp::launch_igemm_simt(sp::kFprop, p, st);
   if (rc) return rc;
@@ -194,6 +201,8 @@ size_t sp_conv2d_wgrad_workspace(const sp_conv_geom* g, int precision) {
   p.N = g->K;
   p.K = (int64_t)g->N * g->OH * g->OW;
   if (p.K <= 0) return 0;
+  if (sp::g_umma_policy == 0 && sp::small_c_supported(*g))
+    return (size_t)sp::small_c_wgrad_blocks(*g) * p.M * p.N * sizeof(float);
   int splits;
   int64_t chunk;
   sp::wgrad_split(*g, sp::use_umma(sp::kWgrad, p, precision), &splits, &chunk);
@@ -213,6 +222,18 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
   p.C = dw;
   p.ldc = g->K;
   if (p.K == 0) return sp_fill_f32(dw, p.M * p.N, 0.f, stream);
+  if (sp::g_umma_policy == 0 && sp::small_c_supported(*g)) {
+    const int blocks = sp::small_c_wgrad_blocks(*g);
+    const size_t need = (size_t)blocks * p.M * p.N * sizeof(float);
+    if (!workspace || workspace_bytes < need)
+      return sp::set_error(SP_ERR_WORKSPACE, "conv2d_wgrad: workspace %zu < required %zu",
+                           workspace_bytes, need);
+    if (int rc = sp::launch_conv_wgrad_smallc(x, gy, static_cast<float*>(workspace), *g, blocks,
+                                              sp::as_stream(stream)))
+      return rc;
+    SP_CHECK_LAUNCH("conv2d_wgrad(small C)");
+    return sp_reduce_sum(static_cast<const float*>(workspace), dw, 1, blocks, p.M * p.N, stream);
+  }
   const bool umma = sp::use_umma(sp::kWgrad, p, precision);
   int splits;
   int64_t chunk;

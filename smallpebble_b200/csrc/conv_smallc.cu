@@ -1,0 +1,208 @@
+// First-layer convolutions: tiny channel count (RGB, C = 3) and a short reduction
+// (KH*KW*C = 27).  As implicit GEMMs these are the worst case for the tensor-core kernel --
+// 12-byte pixels rule out 16-byte copies, M or K pads 27 -> 128/32 -- while the arithmetic is
+// negligible (0.2 GFLOP for the CIFAR layer): they are HBM-bound (read x, write y: 16 MB).
+// So they run on CUDA cores in exact fp32, organised around coalesced memory traffic:
+//
+//   fprop: weights (KH*KW*C x K, a few KB) live in shared memory; a thread produces 8 output
+//          channels of one pixel, so a pixel's K outputs are written as one contiguous run.
+//   wgrad: a block owns a slice of the N*OH*OW reduction; pixel tiles (patches and dY rows)
+//          are staged in shared memory with coalesced loads; each thread accumulates 4
+//          filter taps in registers; per-block partial filters are summed by a second,
+//          fixed-order pass (deterministic, like the tensor-core split-K path).
+//
+// Used for both precision modes when small_c_supported() holds (results are fp32-exact).
+#include <algorithm>
+
+#include "igemm.cuh"
+
+namespace sp {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxKc = 64;    // KH*KW*C
+constexpr int kMaxK = 64;     // output channels handled by the wgrad kernel
+constexpr int kPixTile = 64;  // wgrad: pixels staged per iteration
+
+__global__ void __launch_bounds__(kThreads) conv_fprop_smallc_kernel(
+    const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+    const __grid_constant__ sp_conv_geom g, int kc, int k8) {
+  extern __shared__ float w_s[];  // [kc][k8 * 8] zero padded
+  const int kpad = k8 * 8;
+  for (int i = threadIdx.x; i < kc * kpad; i += blockDim.x) {
+    const int r = i / kpad, c = i - r * kpad;
+    w_s[i] = (c < g.K) ? w[r * g.K + c] : 0.f;
+  }
+  __syncthreads();
+  const int pix_per_block = kThreads / k8;
+  const int64_t n_pix = (int64_t)g.N * g.OH * g.OW;
+  const int lane_pix = threadIdx.x / k8, cg = threadIdx.x - lane_pix * k8;
+  if (lane_pix >= pix_per_block) return;
+  for (int64_t p = (int64_t)blockIdx.x * pix_per_block + lane_pix; p < n_pix;
+       p += (int64_t)gridDim.x * pix_per_block) {
+    const int ox = (int)(p % g.OW);
+    const int64_t r = p / g.OW;
+    const int oy = (int)(r % g.OH);
+    const int n = (int)(r / g.OH);
+    const int iy0 = oy * g.sy - g.pad_t, ix0 = ox * g.sx - g.pad_l;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    int k = 0;
+    for (int dy = 0; dy < g.KH; ++dy) {
+      const int iy = iy0 + dy;
+      for (int dx = 0; dx < g.KW; ++dx) {
+        const int ix = ix0 + dx;
+        const bool in = (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
+        const float* px = x + (((int64_t)n * g.H + iy) * g.W + ix) * g.C;
+        for (int c = 0; c < g.C; ++c, ++k) {
+          const float v = in ? __ldg(px + c) : 0.f;
+          const float4 w0 = *reinterpret_cast<const float4*>(&w_s[k * kpad + cg * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&w_s[k * kpad + cg * 8 + 4]);
+          acc[0] = fmaf(v, w0.x, acc[0]);
+          acc[1] = fmaf(v, w0.y, acc[1]);
+          acc[2] = fmaf(v, w0.z, acc[2]);
+          acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]);
+          acc[5] = fmaf(v, w1.y, acc[5]);
+          acc[6] = fmaf(v, w1.z, acc[6]);
+          acc[7] = fmaf(v, w1.w, acc[7]);
+        }
+      }
+    }
+    float* out = y + p * g.K + cg * 8;
+    if ((g.K & 3) == 0 && cg * 8 + 8 <= g.K) {
+      reinterpret_cast<float4*>(out)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(out)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (cg * 8 + j < g.K) out[j] = acc[j];
+    }
+  }
+}
+
+// partial[block][kc][K] = sum over the block's pixel slice of patch[p][kc] * gy[p][K]
+__global__ void __launch_bounds__(kThreads) conv_wgrad_smallc_kernel(
+    const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partial,
+    const __grid_constant__ sp_conv_geom g, int kc, int64_t pix_per_block) {
+  __shared__ float patch_s[kPixTile][kMaxKc + 1];
+  __shared__ __align__(16) float gy_s[kPixTile][kMaxK];
+  __shared__ int pix_y[kPixTile], pix_x[kPixTile];
+  __shared__ int64_t pix_base[kPixTile];
+
+  const int K = g.K;
+  const int k4 = (K + 3) >> 2;              // output-channel quads
+  const int n_jobs = kc * k4;               // (tap-channel, quad) accumulators in this block
+  const int64_t n_pix = (int64_t)g.N * g.OH * g.OW;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p_end = min(n_pix, p_begin + pix_per_block);
+
+  // a thread owns up to two jobs (n_jobs <= 2 * kThreads is guaranteed by the host)
+  const int job0 = threadIdx.x, job1 = threadIdx.x + kThreads;
+  const int r0 = job0 / k4, q0 = job0 - r0 * k4;
+  const int r1 = job1 / k4, q1 = job1 - r1 * k4;
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+
+  for (int64_t pt = p_begin; pt < p_end; pt += kPixTile) {
+    const int tile = (int)min((int64_t)kPixTile, p_end - pt);
+    __syncthreads();  // previous tile consumed
+    if (threadIdx.x < tile) {
+      const int64_t p = pt + threadIdx.x;
+      const int ox = (int)(p % g.OW);
+      const int64_t r = p / g.OW;
+      const int oy = (int)(r % g.OH);
+      const int n = (int)(r / g.OH);
+      pix_y[threadIdx.x] = oy * g.sy - g.pad_t;
+      pix_x[threadIdx.x] = ox * g.sx - g.pad_l;
+      pix_base[threadIdx.x] = (int64_t)n * g.H * g.W * g.C;
+    }
+    // dY rows: contiguous, coalesced
+    for (int i = threadIdx.x; i < tile * K; i += kThreads) {
+      const int pp = i / K, c = i - pp * K;
+      gy_s[pp][c] = gy[(pt + pp) * K + c];
+    }
+    __syncthreads();
+    // patches: gather with zero padding
+    for (int i = threadIdx.x; i < tile * kc; i += kThreads) {
+      const int pp = i / kc, k = i - pp * kc;
+      const int c = k % g.C, tap = k / g.C;
+      const int dy = tap / g.KW, dx = tap - dy * g.KW;
+      const int iy = pix_y[pp] + dy, ix = pix_x[pp] + dx;
+      float v = 0.f;
+      if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W)
+        v = __ldg(x + pix_base[pp] + ((int64_t)iy * g.W + ix) * g.C + c);
+      patch_s[pp][k] = v;
+    }
+    __syncthreads();
+    if (job0 < n_jobs) {
+      for (int pp = 0; pp < tile; ++pp) {
+        const float v = patch_s[pp][r0];
+        const float4 d = *reinterpret_cast<const float4*>(&gy_s[pp][q0 * 4]);
+        acc0.x = fmaf(v, d.x, acc0.x);
+        acc0.y = fmaf(v, d.y, acc0.y);
+        acc0.z = fmaf(v, d.z, acc0.z);
+        acc0.w = fmaf(v, d.w, acc0.w);
+      }
+    }
+    if (job1 < n_jobs) {
+      for (int pp = 0; pp < tile; ++pp) {
+        const float v = patch_s[pp][r1];
+        const float4 d = *reinterpret_cast<const float4*>(&gy_s[pp][q1 * 4]);
+        acc1.x = fmaf(v, d.x, acc1.x);
+        acc1.y = fmaf(v, d.y, acc1.y);
+        acc1.z = fmaf(v, d.z, acc1.z);
+        acc1.w = fmaf(v, d.w, acc1.w);
+      }
+    }
+  }
+  float* out = partial + (int64_t)blockIdx.x * kc * K;
+  auto store = [&](int r, int q, const float4& a) {
+    const float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < K) out[r * K + q * 4 + j] = v[j];
+  };
+  if (job0 < n_jobs) store(r0, q0, acc0);
+  if (job1 < n_jobs) store(r1, q1, acc1);
+}
+
+}  // namespace
+
+bool small_c_supported(const sp_conv_geom& g) {
+  const int kc = g.KH * g.KW * g.C;
+  return g.C <= 4 && kc <= kMaxKc && g.K <= kMaxK && g.K >= 1 &&
+         kc * ((g.K + 3) / 4) <= 2 * kThreads;
+}
+
+int small_c_wgrad_blocks(const sp_conv_geom& g) {
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int64_t n_pix = (int64_t)g.N * g.OH * g.OW;
+  int64_t blocks = std::min<int64_t>(2 * sms, (n_pix + kPixTile - 1) / kPixTile);
+  return (int)std::max<int64_t>(blocks, 1);
+}
+
+int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_conv_geom& g,
+                             cudaStream_t st) {
+  const int kc = g.KH * g.KW * g.C;
+  const int k8 = (g.K + 7) / 8;
+  const int pix_per_block = kThreads / k8;
+  const int64_t n_pix = (int64_t)g.N * g.OH * g.OW;
+  const int grid = wave_grid(n_pix, pix_per_block, 8);
+  const size_t smem = (size_t)kc * k8 * 8 * sizeof(float);
+  conv_fprop_smallc_kernel<<<grid, kThreads, smem, st>>>(x, w, y, g, kc, k8);
+  return 0;
+}
+
+// partial must hold small_c_wgrad_blocks(g) * KH*KW*C * K floats
+int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial,
+                             const sp_conv_geom& g, int blocks, cudaStream_t st) {
+  const int kc = g.KH * g.KW * g.C;
+  const int64_t n_pix = (int64_t)g.N * g.OH * g.OW;
+  int64_t per = (n_pix + blocks - 1) / blocks;
+  per = (per + kPixTile - 1) / kPixTile * kPixTile;
+  conv_wgrad_smallc_kernel<<<blocks, kThreads, 0, st>>>(x, gy, partial, g, kc, per);
+  return 0;
+}
+
+}  // namespace sp

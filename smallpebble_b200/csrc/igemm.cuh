@@ -46,4 +46,13 @@ bool igemm_umma_supported(int mode, const IgemmParams& p);
 // debug: 0 = asynchronous producer arrivals (default), 1 = wait + proxy fence per stage
 void igemm_umma_set_sync_mode(int mode);
 
+
+// First-layer (C <= 4) CUDA-core kernels, conv_smallc.cu
+bool small_c_supported(const sp_conv_geom& g);
+int small_c_wgrad_blocks(const sp_conv_geom& g);
+int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_conv_geom& g,
+                             cudaStream_t st);
+int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial,
+                             const sp_conv_geom& g, int blocks, cudaStream_t st);
+
 }  // namespace sp

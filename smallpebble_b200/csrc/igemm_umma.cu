@@ -937,18 +937,23 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 int g_sync_mode = 0;
 
-int pick_bn(int64_t N) {
-  if (N <= 32) return 32;
-  if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  return 256;
+// N tile.  Largest UMMA N that covers the problem (fewest passes over A) -- unless that
+// leaves the chip under-filled: then halve it (down to 32) so that the whole grid is resident
+// in one wave with 2-3 CTAs per SM hiding each other's load latency.
+int pick_bn(int64_t M, int64_t N, int64_t z) {
+  int bn = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int64_t m_tiles = (M + BM - 1) / BM;
+  while (bn > 32 && m_tiles * ((N + bn - 1) / bn) * z < 2 * sms) bn >>= 1;
+  return bn;
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int MODE, bool A_MN, bool B_MN>
 int launch(const IgemmParams& p, cudaStream_t st, bool a_vec, bool b_vec) {
-  const int bn = pick_bn(p.N);
+  const int64_t zdim = p.k_splits > 1 ? p.k_splits : (p.batch > 1 ? p.batch : 1);
+  const int bn = pick_bn(p.M, p.N, zdim);
   const size_t smem = 1024 + (size_t)kStages * (kATileBytes + (size_t)bn * BK * 4);
   static thread_local bool attr_done = false;  // per kernel instantiation
   auto kern = igemm_umma_kernel<MODE, A_MN, B_MN>;

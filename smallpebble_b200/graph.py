@@ -97,6 +97,26 @@ def _device_gradient(variable: Variable, gradients) -> DeviceArray:
     return g
 
 
+class _StepCounts:
+    """`adam.t[variable]` (sp.py:569): completed steps of each variable, read from the
+    device-resident counters the fused kernel maintains (so it stays right under CUDA-graph
+    replay, where no Python runs per step)."""
+
+    def __init__(self, counters):
+        self._counters = counters
+
+    def __getitem__(self, variable):
+        if variable not in self._counters:
+            return 0  # defaultdict(lambda: 0) behaviour of the reference
+        return int(np.asarray(self._counters[variable])[0])
+
+    def __contains__(self, variable):
+        return variable in self._counters
+
+    def __len__(self):
+        return len(self._counters)
+
+
 class Adam:
     """Adam optimization for SmallPebble variables (sp.py:552-583; Kingma & Ba, Algorithm 1).
 
@@ -110,10 +130,10 @@ class Adam:
         self.beta1 = beta1
         self.beta2 = beta2
         self.eps = eps
-        self.t = {}
         self.m = {}
         self.v = {}
         self._step = {}  # Variable -> device int32[1]: completed steps (read by the kernel)
+        self.t = _StepCounts(self._step)
         self._tables = {}  # ids of the parameter arrays -> cached ctypes pointer tables
 
     def training_step(self, variables, gradients) -> None:
@@ -126,12 +146,10 @@ class Adam:
         if distributed.is_initialized() and distributed.world_size() > 1:
             grads = distributed.allreduce_gradients(grads)
         for v in variables:
-            if v not in self.t:
-                self.t[v] = 0
+            if v not in self._step:
                 self.m[v] = DeviceArray.zeros(v.array.shape)
                 self.v[v] = DeviceArray.zeros(v.array.shape)
                 self._step[v] = DeviceArray.from_host(np.zeros(1, np.int32), dtype=np.int32)
-            self.t[v] += 1  # host mirror of the device-resident step count
         n = len(variables)
         key = tuple((id(v), v.array.ptr) for v in variables)
         static = self._tables.get(key)

@@ -26,6 +26,18 @@ class Workload:
         optimiser.training_step(self.learnables, gradients)
         return loss_val, gradients
 
+    def captured_train_step(self, optimiser):
+        """The same step as `train_step`, recorded once into a CUDA graph (sp.capture):
+        `step(xbatch, ybatch) -> loss Variable`."""
+        def step(x, y):
+            self.x_in.assign_value(sp.Variable(x))
+            self.y_true.assign_value(y)
+            loss_val = self.loss.run()
+            optimiser.training_step(self.learnables, sp.get_gradients(loss_val))
+            return loss_val
+
+        return sp.capture(step)
+
     def predict(self, xbatch):
         self.x_in.assign_value(sp.Variable(xbatch))
         return self.y_pred.run()

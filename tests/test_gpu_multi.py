@@ -1,0 +1,42 @@
+"""GPU (needs >= 2 devices, skipped otherwise): the data-parallel run over N GPUs equals the
+single-GPU run at the same global batch -- sum-reduced loss => all-reduce(SUM) of shard
+gradients is exactly the global-batch gradient."""
+
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
+                    reason="needs at least 2 GPUs")
+def test_data_parallel_equals_single_gpu(tmp_path):
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(HERE, "_dp_gpu_worker.py"),
+           str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    single = np.load(tmp_path / "single.npz")
+    ranks = [np.load(tmp_path / f"rank{i}.npz") for i in range(world)]
+    for key in single.files:
+        # every rank ends with identical weights ...
+        assert np.array_equal(ranks[0][key], ranks[1][key]), key
+        # ... equal to the single-GPU global-batch run up to fp32 summation order
+        ref = single[key].astype(np.float64)
+        err = np.max(np.abs(ranks[0][key] - ref)) / max(np.max(np.abs(ref)), 1e-30)
+        assert err < 2e-3 if key.startswith("w") else err < 1e-5, (key, err)
