@@ -1,0 +1,168 @@
+"""Bring-up probe for the 2-SM TMA conv kernels (csrc/conv_tma2.cu): one geometry per
+process (a trap must not poison the others), all three contractions compared with the
+float64 oracle, then timed against the 1-SM cp.async kernel on the same inputs.
+
+    python scripts/tma2_probe.py all            # every case, one subprocess each
+    python scripts/tma2_probe.py <case>         # one case in-process
+    python scripts/tma2_probe.py time           # timing table at the VGG shapes
+"""
+
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+FORCE_TMA2 = 1 << 5      # sp_debug_set_umma_policy: 2-SM kernel whenever supported
+NO_TMA2 = 2 << 5
+
+#        name            x shape            w shape           strides  padding
+CASES = {
+    "same3_n64":   ((4, 12, 12, 32),  (3, 3, 32, 64),   (1, 1), "SAME"),
+    "valid3_n128": ((4, 13, 11, 64),  (3, 3, 64, 128),  (1, 1), "VALID"),
+    "s2_k5":       ((2, 17, 19, 32),  (5, 5, 32, 64),   (2, 2), "SAME"),
+    "k1_n192":     ((2, 8, 8, 64),    (1, 1, 64, 192),  (1, 1), "SAME"),
+    "n512":        ((2, 8, 8, 32),    (3, 3, 32, 512),  (1, 1), "SAME"),
+    "c512":        ((2, 6, 6, 512),   (3, 3, 512, 64),  (1, 1), "SAME"),
+    "k2x3":        ((3, 9, 10, 32),   (2, 3, 32, 64),   (1, 1), "SAME"),
+    "s1x2_valid":  ((2, 11, 16, 32),  (3, 3, 32, 64),   (1, 2), "VALID"),
+    "mid":         ((32, 32, 32, 128), (3, 3, 128, 256), (1, 1), "SAME"),
+    "tiny_img":    ((1, 3, 3, 32),    (3, 3, 32, 64),   (1, 1), "SAME"),
+}
+
+
+def scaled_err(got, ref):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    scale = max(np.max(np.abs(ref)), 1e-30)
+    return np.abs(got - ref) / scale
+
+
+def describe(name, got, ref, cols):
+    err = scaled_err(got, ref)
+    worst = float(err.max()) if err.size else 0.0
+    nan = int(np.isnan(np.asarray(got, np.float64)).sum())
+    print(f"  {name}: shape {np.shape(got)} worst {worst:.3e} mean {err.mean():.3e} nan {nan}")
+    if not worst < 5e-3:
+        m = err.reshape(-1, cols)
+        bad_rows = np.where((m > 5e-3).any(axis=1))[0]
+        bad_cols = np.where((m > 5e-3).any(axis=0))[0]
+        print(f"    bad rows {len(bad_rows)}/{m.shape[0]} first {bad_rows[:12]} last {bad_rows[-4:]}")
+        print(f"    bad cols {len(bad_cols)}/{m.shape[1]} first {bad_cols[:12]} last {bad_cols[-4:]}")
+        g2 = np.asarray(got, np.float64).reshape(-1, cols)
+        r2 = np.asarray(ref, np.float64).reshape(-1, cols)
+        r = int(bad_rows[0])
+        print("    got", np.round(g2[r, :6], 4), "ref", np.round(r2[r, :6], 4))
+        print("    row sorted match:", np.allclose(np.sort(g2[r]), np.sort(r2[r]), atol=5e-3))
+    return worst if nan == 0 else float("inf")
+
+
+def run(case):
+    import smallpebble_b200 as sp
+    from oracle import numpy_path as orc
+    from smallpebble_b200 import core
+
+    sp.set_precision("tf32")
+    core.debug_set_kernel_policy(FORCE_TMA2)
+    xs, ws, strides, pad = CASES[case]
+    rng = np.random.default_rng(1)
+    x, w = rng.random(xs) - 0.5, rng.random(ws) - 0.5
+    xv, wv = sp.Variable(x), sp.Variable(w)
+    y = sp.conv2d(xv, wv, pad, strides)
+    gy = rng.random(y.shape) - 0.5
+    y0, dx0, dw0 = orc.conv2d_grads(x, w, gy, pad, strides)
+    worst = describe("fprop y", y.array, y0, ws[3])
+    g = sp.get_gradients(sp.mul(y, sp.Variable(gy)))
+    worst = max(worst, describe("dgrad dX", g[xv], dx0, xs[3]))
+    worst = max(worst, describe("wgrad dW", g[wv], dw0, ws[3]))
+    print(f"CASE {case}: {'PASS' if worst < 5e-3 else 'FAIL'} worst={worst:.3e}")
+
+
+def timing():
+    import torch
+
+    import smallpebble_b200 as sp
+    from bench import load_peaks
+    from smallpebble_b200 import _abi, core
+    from smallpebble_b200.array import DeviceArray, stream
+
+    sp.set_precision("tf32")
+    peak = load_peaks()["bf16_tflops"] / 2
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    rng = np.random.default_rng(0)
+
+    def timeit(fn, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(reps):
+            _abi.f.sp_l2_flush(flush.data_ptr(), 256 << 20, stream())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        return float(np.median(times))
+
+    cfgs = [
+        ("cnn_conv2", (128, 15, 15, 32), (3, 3, 32, 128), "VALID"),
+        ("cnn_conv3", (128, 7, 7, 128), (3, 3, 128, 128), "VALID"),
+        ("vgg_conv1b_64_64", (256, 64, 64, 64), (3, 3, 64, 64), "SAME"),
+        ("vgg_conv2a_64_128", (256, 32, 32, 64), (3, 3, 64, 128), "SAME"),
+        ("vgg_conv2b_128_128", (256, 32, 32, 128), (3, 3, 128, 128), "SAME"),
+        ("vgg_conv3a_128_256", (256, 16, 16, 128), (3, 3, 128, 256), "SAME"),
+        ("vgg_conv3b_256_256", (256, 16, 16, 256), (3, 3, 256, 256), "SAME"),
+        ("sweep_n64_c512_k1", (64, 32, 32, 512), (1, 1, 512, 512), "SAME"),
+        ("big_512_512", (128, 16, 16, 512), (3, 3, 512, 512), "SAME"),
+    ]
+    only = os.environ.get("SP_PROBE_ONLY")
+    if only:
+        cfgs = [c for c in cfgs if c[0] in only.split(",")]
+    rows = []
+    for name, xs, ws, pad in cfgs:
+        x = sp.Variable(rng.random(xs, dtype=np.float32) - 0.5)
+        w = sp.Variable(rng.random(ws, dtype=np.float32) - 0.5)
+        res = {}
+        for label, pol in (("umma1", NO_TMA2 | 1), ("tma2", FORCE_TMA2)):
+            core.debug_set_kernel_policy(pol)
+            y = sp.conv2d(x, w, pad, (1, 1))
+            gy = DeviceArray.from_host(rng.random(y.shape, dtype=np.float32) - 0.5)
+            gy.ptr
+            (_, fdx), (_, fdw) = y.local_gradients
+            flops = 2.0 * np.prod(y.shape) * ws[0] * ws[1] * ws[2]
+            for op, fn in (("fprop", lambda: sp.conv2d(x, w, pad, (1, 1))),
+                           ("dgrad", lambda: fdx(gy)), ("wgrad", lambda: fdw(gy))):
+                ms = timeit(fn)
+                res[(label, op)] = (ms, flops / (ms * 1e-3) / 1e12)
+        for op in ("fprop", "dgrad", "wgrad"):
+            a, b = res[("umma1", op)], res[("tma2", op)]
+            row = {"op": f"{name}/{op}", "umma1_ms": a[0], "umma1_tflops": a[1], "tma2_ms": b[0],
+                   "tma2_tflops": b[1], "tma2_frac_of_tf32_peak": b[1] / peak, "speedup": a[0] / b[0]}
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "tma2_timing.json"), "w") as fh:
+        json.dump({"tf32_peak_tflops": peak, "rows": rows}, fh, indent=1)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "all":
+        for c in CASES:
+            try:
+                r = subprocess.run([sys.executable, __file__, c], capture_output=True, text=True,
+                                   timeout=180)
+                print(r.stdout.strip())
+                if r.returncode != 0:
+                    print(f"CASE {c}: CRASH rc={r.returncode}\n{r.stderr.strip()[-1200:]}")
+            except subprocess.TimeoutExpired:
+                print(f"CASE {c}: TIMEOUT")
+    elif which == "time":
+        timing()
+    else:
+        run(which)

@@ -15,6 +15,18 @@ namespace {
 // 0 = policy (default), 1 = always tcgen05 when the shape is supported (tests),
 // 2 = never tcgen05
 int g_umma_policy = 0;
+// 0 = policy (large problems), 1 = whenever supported (tests), 2 = never
+int g_tma2_policy = 0;
+
+// The 2-SM TMA kernel runs 74 persistent CTA pairs over 256-row tiles: it pays off once the
+// problem fills them (>= 1 tile per pair and enough MMA work to amortise the pipeline fill).
+bool use_tma2(int mode, const IgemmParams& p, int precision) {
+  if (precision != SP_PRECISION_TF32 || g_umma_policy == 2 || g_tma2_policy == 2) return false;
+  if (!conv_tma2_supported(mode, p)) return false;
+  if (g_tma2_policy == 1) return true;
+  const double flop = 2.0 * (double)p.M * (double)p.N * (double)p.K;
+  return flop >= 4e9;
+}
 
 bool use_umma(int mode, const IgemmParams& p, int precision) {
   if (precision != SP_PRECISION_TF32 || g_umma_policy == 2) return false;
@@ -69,6 +81,22 @@ void wgrad_split(const sp_conv_geom& g, bool umma, int* splits, int64_t* k_chunk
   if (*splits < 1) *splits = 1;
 }
 
+// Split of the wgrad reduction axis for the 2-SM kernel: 74 persistent CTA pairs, so aim for a
+// whole number of rounds over the (256-row x 256-column) output tiles; k_chunk % 64 == 0.
+void wgrad_split_tma2(const sp_conv_geom& g, int* splits, int64_t* k_chunk) {
+  const int64_t M = (int64_t)g.KH * g.KW * g.C, N = g.K, K = (int64_t)g.N * g.OH * g.OW;
+  const int pairs = (device_info().sm_count > 0 ? device_info().sm_count : 148) / 2;
+  const int64_t tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  int64_t want = tiles >= pairs ? 1 : pairs / tiles;
+  const int64_t max_splits = (K + 1023) / 1024;  // >= 32 k-blocks per tile
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  int64_t chunk = ((K + want - 1) / want + 63) / 64 * 64;
+  *k_chunk = chunk;
+  *splits = (int)((K + chunk - 1) / chunk);
+  if (*splits < 1) *splits = 1;
+}
+
 }  // namespace
 }  // namespace sp
 
@@ -76,10 +104,14 @@ extern "C" {
 
 // undocumented test hook (declared in tests only): select the contraction kernel family
 int sp_debug_set_umma_policy(int policy) {
-  // bits 0-1: kernel family policy; bit 4: conservative producer synchronisation
+  // bits 0-1: kernel family policy; bit 4: conservative producer synchronisation;
+  // bits 5-6: 2-SM TMA conv kernel (0 = size policy, 1 = whenever supported, 2 = never)
   const int family = policy & 3;
-  if (policy < 0 || family > 2) return sp::set_error(SP_ERR_INVALID_ARGUMENT, "policy in 0..2");
+  const int tma2 = (policy >> 5) & 3;
+  if (policy < 0 || family > 2 || tma2 > 2)
+    return sp::set_error(SP_ERR_INVALID_ARGUMENT, "policy in 0..2");
   sp::g_umma_policy = family;
+  sp::g_tma2_policy = tma2;
   sp::igemm_umma_set_sync_mode((policy >> 4) & 1);
   return 0;
 }
@@ -164,8 +196,9 @@ int sp_conv2d_fprop(const float* x, const float* w, float* y, const sp_conv_geom
     SP_CHECK_LAUNCH("conv2d_fprop(small C)");
     return 0;
   }
-  int rc = sp::use_umma(sp::kFprop, p, precision) ? sp::launch_igemm_umma(sp::kFprop, p, st)
-                                                   : sp::launch_igemm_simt(sp::kFprop, p, st);
+  int rc = sp::use_tma2(sp::kFprop, p, precision)   ? sp::launch_conv_tma2(sp::kFprop, p, st)
+           : sp::use_umma(sp::kFprop, p, precision) ? sp::launch_igemm_umma(sp::kFprop, p, st)
+                                                    : sp::launch_igemm_simt(sp::kFprop, p, st);
   if (rc) return rc;
   SP_CHECK_LAUNCH("conv2d_fprop");
   return 0;
@@ -186,8 +219,9 @@ int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_ge
   if (p.M == 0) return 0;
   if ((int64_t)g->OH * g->OW == 0) return sp_fill_f32(dx, p.M * p.N, 0.f, stream);
   cudaStream_t st = sp::as_stream(stream);
-  int rc = sp::use_umma(sp::kDgrad, p, precision) ? sp::launch_igemm_umma(sp::kDgrad, p, st)
-                                                   : sp::launch_igemm_simt(sp::kDgrad, p, st);
+  int rc = sp::use_tma2(sp::kDgrad, p, precision)   ? sp::launch_conv_tma2(sp::kDgrad, p, st)
+           : sp::use_umma(sp::kDgrad, p, precision) ? sp::launch_igemm_umma(sp::kDgrad, p, st)
+                                                    : sp::launch_igemm_simt(sp::kDgrad, p, st);
   if (rc) return rc;
   SP_CHECK_LAUNCH("conv2d_dgrad");
   return 0;
@@ -206,7 +240,14 @@ size_t sp_conv2d_wgrad_workspace(const sp_conv_geom* g, int precision) {
   int splits;
   int64_t chunk;
   sp::wgrad_split(*g, sp::use_umma(sp::kWgrad, p, precision), &splits, &chunk);
-  return splits > 1 ? (size_t)splits * p.M * p.N * sizeof(float) : 0;
+  size_t need = splits > 1 ? (size_t)splits * p.M * p.N * sizeof(float) : 0;
+  if (sp::use_tma2(sp::kWgrad, p, precision)) {
+    // pointers are unknown here: reserve for whichever kernel the call ends up on
+    sp::wgrad_split_tma2(*g, &splits, &chunk);
+    const size_t need2 = splits > 1 ? (size_t)splits * p.M * p.N * sizeof(float) : 0;
+    if (need2 > need) need = need2;
+  }
+  return need;
 }
 
 int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_geom* g,
@@ -234,10 +275,14 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
     SP_CHECK_LAUNCH("conv2d_wgrad(small C)");
     return sp_reduce_sum(static_cast<const float*>(workspace), dw, 1, blocks, p.M * p.N, stream);
   }
+  const bool tma2 = sp::use_tma2(sp::kWgrad, p, precision);
   const bool umma = sp::use_umma(sp::kWgrad, p, precision);
   int splits;
   int64_t chunk;
-  sp::wgrad_split(*g, umma, &splits, &chunk);
+  if (tma2)
+    sp::wgrad_split_tma2(*g, &splits, &chunk);
+  else
+    sp::wgrad_split(*g, umma, &splits, &chunk);
   cudaStream_t st = sp::as_stream(stream);
   if (splits > 1) {
     const size_t need = (size_t)splits * p.M * p.N * sizeof(float);
@@ -249,7 +294,9 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
     p.split_stride_c = p.M * p.N;
     p.C = static_cast<float*>(workspace);
   }
-  int rc = umma ? sp::launch_igemm_umma(sp::kWgrad, p, st) : sp::launch_igemm_simt(sp::kWgrad, p, st);
+  int rc = tma2   ? sp::launch_conv_tma2(sp::kWgrad, p, st)
+           : umma ? sp::launch_igemm_umma(sp::kWgrad, p, st)
+                  : sp::launch_igemm_simt(sp::kWgrad, p, st);
   if (rc) return rc;
   SP_CHECK_LAUNCH("conv2d_wgrad");
   if (splits > 1) {

@@ -67,6 +67,97 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_vec4(const float* __rest
   }
 }
 
+// Window known at compile time (2x2 and 3x3 cover every BASELINE model): all KH*KW 128-bit
+// loads of a thread are issued before the first compare, so each thread keeps KH*KW*16 bytes
+// in flight instead of 16 (the runtime-window loop above serialises load -> compare).
+template <int KH, int KW>
+__global__ void __launch_bounds__(kThreads) maxpool_fwd_vec4_fixed(const float* __restrict__ x,
+                                                                   float* __restrict__ y,
+                                                                   uint8_t* __restrict__ idx,
+                                                                   PoolGeom g) {
+  const int C4 = g.C >> 2;
+  const int row_len = g.OW * C4;
+  const int n_rows = g.N * g.OH;
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int n = row / g.OH, oy = row - n * g.OH;
+    const int iy0 = oy * g.sy - g.pt;
+    const float* __restrict__ xin = x + (int64_t)n * g.H * g.W * g.C;
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < row_len; e += gridDim.y * blockDim.x) {
+      const int ox = e / C4, c4 = e - ox * C4;
+      const int ix0 = ox * g.sx - g.pl;
+      float4 v[KH * KW];
+#pragma unroll
+      for (int dy = 0; dy < KH; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < KW; ++dx) {
+          const int iy = iy0 + dy, ix = ix0 + dx;
+          v[dy * KW + dx] = make_float4(0.f, 0.f, 0.f, 0.f);  // zero padding competes
+          if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W)
+            v[dy * KW + dx] = ld_stream_f4(xin + ((int64_t)iy * g.W + ix) * g.C + 4 * c4);
+        }
+      }
+      float4 best = v[0];
+      int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+#pragma unroll
+      for (int k = 1; k < KH * KW; ++k) {
+        take(v[k].x, k, best.x, b0);
+        take(v[k].y, k, best.y, b1);
+        take(v[k].z, k, best.z, b2);
+        take(v[k].w, k, best.w, b3);
+      }
+      const int64_t o = (int64_t)row * row_len + e;
+      reinterpret_cast<float4*>(y)[o] = best;
+      reinterpret_cast<uchar4*>(idx)[o] =
+          make_uchar4((unsigned char)b0, (unsigned char)b1, (unsigned char)b2, (unsigned char)b3);
+    }
+  }
+}
+
+// Backward for stride == window (every pooling layer of the BASELINE models), window known at
+// compile time: one thread per (virtual) WINDOW x 4 channels reads gy and the argmax once and
+// writes all KH*KW input pixels of its window -- the selected one gets g, the others 0.
+// Non-overlapping windows tile the padded image, so every in-range input pixel is written by
+// exactly one thread (no atomics, deterministic); windows beyond OH/OW (rows/columns that no
+// pooling window covers, VALID padding) are visited too and write zeros.
+template <int KH, int KW>
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_tile_vec4(const float* __restrict__ gy,
+                                                                  const uint8_t* __restrict__ idx,
+                                                                  float* __restrict__ dx,
+                                                                  PoolGeom g, int VOH, int VOW) {
+  const int C4 = g.C >> 2;
+  const int row_len = VOW * C4;
+  const int n_rows = g.N * VOH;
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int n = row / VOH, oy = row - n * VOH;
+    const int iy0 = oy * KH - g.pt;
+    float* __restrict__ dimg = dx + (int64_t)n * g.H * g.W * g.C;
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < row_len; e += gridDim.y * blockDim.x) {
+      const int ox = e / C4, c4 = e - ox * C4;
+      const int ix0 = ox * KW - g.pl;
+      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+      uchar4 k = make_uchar4(255, 255, 255, 255);
+      if (oy < g.OH && ox < g.OW) {
+        const int64_t o = (((int64_t)n * g.OH + oy) * g.OW + ox) * C4 + c4;
+        k = __ldg(reinterpret_cast<const uchar4*>(idx) + o);
+        gv = ld_stream_f4(gy + 4 * o);
+      }
+#pragma unroll
+      for (int dy = 0; dy < KH; ++dy) {
+#pragma unroll
+        for (int dxx = 0; dxx < KW; ++dxx) {
+          const int iy = iy0 + dy, ix = ix0 + dxx;
+          if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) {
+            const int want = dy * KW + dxx;
+            const float4 out = make_float4(k.x == want ? gv.x : 0.f, k.y == want ? gv.y : 0.f,
+                                           k.z == want ? gv.z : 0.f, k.w == want ? gv.w : 0.f);
+            *reinterpret_cast<float4*>(dimg + ((int64_t)iy * g.W + ix) * g.C + 4 * c4) = out;
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_scalar(const float* __restrict__ x,
                                                                float* __restrict__ y,
                                                                uint8_t* __restrict__ idx,
@@ -228,9 +319,15 @@ int sp_maxpool2d_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W
   const int64_t outs = (int64_t)N * OH * OW * C;
   if (outs == 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
-  if (C % 4 == 0 && aligned16(x) && aligned16(y) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0)
-    maxpool_fwd_vec4<<<row_grid(N * OH, OW * (C / 4)), kThreads, 0, st>>>(x, y, idx, g);
-  else
+  if (C % 4 == 0 && aligned16(x) && aligned16(y) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0) {
+    const dim3 grid = row_grid(N * OH, OW * (C / 4));
+    if (KH == 2 && KW == 2)
+      maxpool_fwd_vec4_fixed<2, 2><<<grid, kThreads, 0, st>>>(x, y, idx, g);
+    else if (KH == 3 && KW == 3)
+      maxpool_fwd_vec4_fixed<3, 3><<<grid, kThreads, 0, st>>>(x, y, idx, g);
+    else
+      maxpool_fwd_vec4<<<grid, kThreads, 0, st>>>(x, y, idx, g);
+  } else
     maxpool_fwd_scalar<<<sp::wave_grid(outs, kThreads, 8), kThreads, 0, st>>>(x, y, idx, g);
   SP_CHECK_LAUNCH("maxpool2d_fwd");
   return 0;
@@ -246,7 +343,15 @@ int sp_maxpool2d_bwd(const float* gy, const uint8_t* idx, float* dx, int N, int 
   cudaStream_t st = sp::as_stream(stream);
   if (C % 4 == 0 && aligned16(gy) && aligned16(dx) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0)
   {
-    if (sy == KH && sx == KW)
+    // virtual window grid that tiles the whole (top/left padded) image
+    const int VOH = (H + pad_t + KH - 1) / KH, VOW = (W + pad_l + KW - 1) / KW;
+    if (sy == KH && sx == KW && KH == 2 && KW == 2)
+      maxpool_bwd_tile_vec4<2, 2><<<row_grid(N * VOH, VOW * (C / 4)), kThreads, 0, st>>>(
+          gy, idx, dx, g, VOH, VOW);
+    else if (sy == KH && sx == KW && KH == 3 && KW == 3)
+      maxpool_bwd_tile_vec4<3, 3><<<row_grid(N * VOH, VOW * (C / 4)), kThreads, 0, st>>>(
+          gy, idx, dx, g, VOH, VOW);
+    else if (sy == KH && sx == KW)
       maxpool_bwd_vec4<true><<<row_grid(N * H, W * (C / 4)), kThreads, 0, st>>>(gy, idx, dx, g);
     else
       maxpool_bwd_vec4<false><<<row_grid(N * H, W * (C / 4)), kThreads, 0, st>>>(gy, idx, dx, g);
