@@ -98,6 +98,19 @@ def timing():
     def timeit(fn, reps=10):
         fn()
         torch.cuda.synchronize()
+        if os.environ.get("SP_PROBE_B2B"):
+            # 30 back-to-back launches in one event pair: warm L2, host launch cost hidden
+            # behind the queue -- the steady-state device time of a small kernel
+            best = 1e9
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(30):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) / 30)
+            return best
         times = []
         for _ in range(reps):
             _abi.f.sp_l2_flush(flush.data_ptr(), 256 << 20, stream())
@@ -135,8 +148,19 @@ def timing():
             gy.ptr
             (_, fdx), (_, fdw) = y.local_gradients
             flops = 2.0 * np.prod(y.shape) * ws[0] * ws[1] * ws[2]
-            for op, fn in (("fprop", lambda: sp.conv2d(x, w, pad, (1, 1))),
-                           ("dgrad", lambda: fdx(gy)), ("wgrad", lambda: fdw(gy))):
+            # raw C-ABI calls into preallocated buffers: no Python allocation in the loop
+            from smallpebble_b200.core import _conv_plan, _precision
+            geom = _conv_plan(x.array.shape, w.array.shape, pad, (1, 1))[0]
+            F = _abi.f
+            dxb, dwb = DeviceArray.empty(xs), DeviceArray.empty(ws)
+            wsb = _abi.load().sp_conv2d_wgrad_workspace(geom, 1)
+            wsa = DeviceArray.empty((max(wsb, 4) // 4,))
+            st = stream()
+            xp, wp, yp, gp, dxp, dwp, wsp = (x.array.ptr, w.array.ptr, y.array.ptr, gy.ptr, dxb.ptr,
+                                            dwb.ptr, wsa.ptr)
+            for op, fn in (("fprop", lambda: F.sp_conv2d_fprop(xp, wp, yp, geom, 1, st)),
+                           ("dgrad", lambda: F.sp_conv2d_dgrad(gp, wp, dxp, geom, 1, st)),
+                           ("wgrad", lambda: F.sp_conv2d_wgrad(xp, gp, dwp, geom, 1, wsp, wsb, st))):
                 ms = timeit(fn)
                 res[(label, op)] = (ms, flops / (ms * 1e-3) / 1e12)
         for op in ("fprop", "dgrad", "wgrad"):

@@ -24,6 +24,12 @@ CONV_CASES = [
     ("asym_stride", (1, 9, 10, 2), (3, 2, 2, 5), (2, 1), "SAME"),
     ("asym_stride_valid", (1, 9, 10, 2), (3, 2, 2, 5), (2, 3), "VALID"),
     ("c32_k128", (2, 15, 15, 32), (3, 3, 32, 128), (1, 1), "VALID"),  # CNN conv2 shape family
+    # channel counts % 32 == 0: eligible for the 2-SM TMA kernels (csrc/conv_tma2.cu)
+    ("c64_k128_same", (3, 12, 11, 64), (3, 3, 64, 128), (1, 1), "SAME"),
+    ("c32_k64_k5_s2", (2, 17, 19, 32), (5, 5, 32, 64), (2, 2), "SAME"),
+    ("c128_k256_valid", (2, 9, 9, 128), (3, 3, 128, 256), (1, 1), "VALID"),
+    ("c32_k192_k2x3", (3, 9, 10, 32), (2, 3, 32, 192), (1, 1), "SAME"),
+    ("c512_k64_k1", (1, 10, 13, 512), (1, 1, 512, 64), (1, 1), "SAME"),
 ]
 
 # name, x shape, (kh, kw), (sy, sx), padding
@@ -38,6 +44,8 @@ POOL_CASES = [
     ("k3_s2", (2, 9, 7, 4), (3, 3), (2, 2), "SAME"),
     ("k3_s1_overlap", (2, 9, 7, 4), (3, 3), (1, 1), "SAME"),
     ("k32_s1_valid", (2, 6, 6, 5), (3, 2), (1, 1), "VALID"),
+    ("k3_s3_same", (2, 10, 8, 8), (3, 3), (3, 3), "SAME"),  # tiled backward, pad_t = 1
+    ("k2_s2_valid_odd", (2, 7, 9, 4), (2, 2), (2, 2), "VALID"),  # last row/col in no window
 ]
 
 # a shape, b shape

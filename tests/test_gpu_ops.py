@@ -22,7 +22,10 @@ def grads_of(fn, arrays, gy):
     return y, [g[v] for v in vs]
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["policy", "force_umma", "force_simt"])
+# sp_debug_set_umma_policy: bits 0-1 kernel family, bits 5-6 the 2-SM TMA conv kernels
+# (32 = whenever the geometry is eligible, 64 = never)
+@pytest.fixture(params=[0, 1, 2, 32, 1 + 64], ids=["policy", "force_umma", "force_simt",
+                                                   "force_tma2", "umma_no_tma2"])
 def umma_policy(request):
     core.debug_set_kernel_policy(request.param)
     yield request.param
@@ -31,8 +34,8 @@ def umma_policy(request):
 
 @pytest.mark.parametrize("case", C.CONV_CASES, ids=[c[0] for c in C.CONV_CASES])
 def test_conv2d(case, precision, umma_policy, golden):
-    if precision == "fp32" and umma_policy == 1:
-        pytest.skip("tcgen05 kernel is only selected in TF32 mode")
+    if precision == "fp32" and umma_policy not in (0, 2):
+        pytest.skip("tcgen05 kernels are only selected in TF32 mode")
     name, xs, ws, strides, pad = case
     x, w, gy = C.conv_inputs(case)
     tol = RTOL[precision]
@@ -83,8 +86,10 @@ def test_maxpool2d_padding_ties_nan():
 
 @pytest.mark.parametrize("case", C.MATMUL_CASES, ids=[c[0] for c in C.MATMUL_CASES])
 def test_matmul(case, precision, umma_policy, golden):
-    if precision == "fp32" and umma_policy == 1:
-        pytest.skip("tcgen05 kernel is only selected in TF32 mode")
+    if precision == "fp32" and umma_policy != 0 and umma_policy != 2:
+        pytest.skip("tcgen05 kernels are only selected in TF32 mode")
+    if umma_policy >= 32:
+        pytest.skip("the 2-SM TMA kernels are conv-only")
     a, b, gy = C.matmul_inputs(case)
     tol = RTOL[precision]
     y, (da, db) = grads_of(sp.matmul, [a, b], gy)

@@ -24,6 +24,9 @@ CONFIGS = [
     ("vgg_conv_64_64", (32, 64, 64, 64), (3, 3, 64, 64), (1, 1), "SAME"),
     ("sweep_k5_s2", (64, 32, 32, 64), (5, 5, 64, 64), (2, 2), "SAME"),
     ("sweep_k1", (64, 32, 32, 128), (1, 1, 128, 256), (1, 1), "SAME"),
+    # BASELINE configs[3] (VGG-style, batch 256): large enough for the 2-SM TMA kernels
+    ("vgg_conv_128_256_b256", (256, 16, 16, 128), (3, 3, 128, 256), (1, 1), "SAME"),
+    ("vgg_conv_256_256_b256", (256, 16, 16, 256), (3, 3, 256, 256), (1, 1), "SAME"),
 ]
 
 
@@ -70,6 +73,41 @@ def test_tensor_core_kernel_agrees_with_fp32_kernel(cfg):
         sp.set_precision(old)
     for a, b, what in zip(tf, fp, ("y", "dX", "dW")):
         assert_close(a, b, RTOL["tf32"], f"{name} {what}: tcgen05 vs CUDA-core")
+
+
+TMA2_CONFIGS = [CONFIGS[1], CONFIGS[2], CONFIGS[3], CONFIGS[4], CONFIGS[6]]
+
+
+@pytest.mark.parametrize("cfg", TMA2_CONFIGS, ids=[c[0] for c in TMA2_CONFIGS])
+def test_tma2_kernel_agrees_with_fp32_kernel(cfg):
+    """The 2-SM TMA kernels (forced, policy bit 5) against the CUDA-core fp32 kernels at full
+    BASELINE sizes -- including the strided k5 case whose dgrad stays on the 1-SM kernel."""
+    name, xs, ws, strides, pad = cfg
+    rng = np.random.default_rng(13)
+    x, w = rng.random(xs) - 0.5, rng.random(ws) - 0.5
+
+    def run(prec, gy=None):
+        sp.set_precision(prec)
+        xv, wv = sp.Variable(x), sp.Variable(w)
+        y = sp.conv2d(xv, wv, pad, strides)
+        if gy is None:
+            gy = rng.random(y.shape) - 0.5
+        g = sp.get_gradients(sp.mul(y, sp.Variable(gy)))
+        return (np.asarray(y.array), np.asarray(g[xv]), np.asarray(g[wv])), gy
+
+    old = sp.get_precision()
+    try:
+        core.debug_set_kernel_policy(32)
+        tf, gy = run("tf32")
+        tf_again, _ = run("tf32", gy)
+        core.debug_set_kernel_policy(0)
+        fp, _ = run("fp32", gy)
+    finally:
+        core.debug_set_kernel_policy(0)
+        sp.set_precision(old)
+    for a, b, c, what in zip(tf, fp, tf_again, ("y", "dX", "dW")):
+        assert_close(a, b, RTOL["tf32"], f"{name} {what}: 2-SM TMA vs CUDA-core")
+        assert np.array_equal(a, c), f"{name} {what}: not bitwise repeatable"
 
 
 def test_conv_linearity_and_determinism(precision):
