@@ -68,6 +68,11 @@ int sp_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * shape is supported, 2 = never use it (CUDA-core kernel even in TF32 mode); adding 16
  * makes the tcgen05 producers wait + proxy-fence after every stage (bring-up aid) */
 int sp_debug_set_umma_policy(int policy);
+/* bits 5-6 of `policy` steer the 2-SM TMA conv kernels (csrc/conv_tma2.cu): 0 = by problem
+ * size, 1 (+32) = whenever the geometry is eligible, 2 (+64) = never.
+ * bring-up hook: cluster 0 of those kernels writes clock64 stamps into `device_buffer`
+ * (>= 512 int64, layout in scripts/tma2_trace.py); NULL switches tracing off */
+int sp_debug_tma2_trace(void* device_buffer);
 
 /* ---- memory helpers (replace NumPy array construction / copies) -------------------- */
 int sp_memcpy_h2d(void* dst, const void* host_src, size_t bytes, sp_stream_t stream);

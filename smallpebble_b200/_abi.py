@@ -38,6 +38,7 @@ SIGNATURES = {
     "sp_last_error": (C.c_char_p, []),
     "sp_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "sp_debug_set_umma_policy": (C.c_int, [C.c_int]),
+    "sp_debug_tma2_trace": (C.c_int, [vp]),
     "sp_memcpy_h2d": (C.c_int, [vp, vp, sz, vp]),
     "sp_memcpy_d2h": (C.c_int, [vp, vp, sz, vp]),
     "sp_memcpy_d2d": (C.c_int, [vp, vp, sz, vp]),
@@ -85,7 +86,7 @@ _lib = None
 _LAUNCHING = {
     n for n in SIGNATURES
     if n not in ("sp_abi_version", "sp_last_error", "sp_device_info", "sp_debug_set_umma_policy",
-                 "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
+                 "sp_debug_tma2_trace", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
                  "sp_conv2d_wgrad_workspace")
 }
 

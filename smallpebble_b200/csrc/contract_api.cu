@@ -18,14 +18,18 @@ int g_umma_policy = 0;
 // 0 = policy (large problems), 1 = whenever supported (tests), 2 = never
 int g_tma2_policy = 0;
 
-// The 2-SM TMA kernel runs 74 persistent CTA pairs over 256-row tiles: it pays off once the
-// problem fills them (>= 1 tile per pair and enough MMA work to amortise the pipeline fill).
+// The 2-SM TMA kernel (74 persistent CTA pairs over 256-row tiles) beats the 1-SM cp.async
+// kernel on every eligible shape measured back to back (profiles/r01_tma2_vs_umma1_b2b.txt:
+// CIFAR conv2 / conv3 at batch 128 up to the 512-channel sweep) except narrow-N dgrad, where a
+// 256 x 32 tile leaves the pair's tensor cores idle behind the A stream.
 bool use_tma2(int mode, const IgemmParams& p, int precision) {
   if (precision != SP_PRECISION_TF32 || g_umma_policy == 2 || g_tma2_policy == 2) return false;
   if (!conv_tma2_supported(mode, p)) return false;
   if (g_tma2_policy == 1) return true;
+  if (g_umma_policy == 1) return false;  // tests: force the 1-SM tcgen05 kernel
   const double flop = 2.0 * (double)p.M * (double)p.N * (double)p.K;
-  return flop >= 4e9;
+  if (mode == kDgrad && p.N < 64) return false;
+  return flop >= 2.5e8;
 }
 
 bool use_umma(int mode, const IgemmParams& p, int precision) {
@@ -113,6 +117,12 @@ int sp_debug_set_umma_policy(int policy) {
   sp::g_umma_policy = family;
   sp::g_tma2_policy = tma2;
   sp::igemm_umma_set_sync_mode((policy >> 4) & 1);
+  return 0;
+}
+
+// undocumented bring-up hook (scripts/tma2_trace.py): in-kernel timestamps of the 2-SM kernel
+int sp_debug_tma2_trace(void* device_buffer) {
+  sp::conv_tma2_set_trace(static_cast<long long*>(device_buffer));
   return 0;
 }
 

@@ -325,6 +325,192 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_smallc_fixed_kernel(
   if (job2 < n_jobs) *reinterpret_cast<float4*>(out + jr2 * K + jq2 * 4) = acc2;
 }
 
+// ---- register-tiled versions (round 1, after ncu showed the kernels above LDS-bound) ------
+// fprop: a thread produces 4 consecutive output pixels x 8 output channels, so every weight
+// quad read from shared memory feeds 16 FMAs (was 4) and neighbouring pixels share their
+// input taps in registers (54 loads for 4 pixels instead of 108).
+template <bool CHECK>
+__global__ void __launch_bounds__(kThreads) conv_fprop_rgb3x3_tile4_kernel(
+    const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+    const __grid_constant__ sp_conv_geom g, int k8) {
+  constexpr int KC = 27, PX = 4, IN_W = (PX + 2) * 3;  // stride-1 only: 6 input pixels per row
+  extern __shared__ float w_s[];                       // [KC][k8 * 8] zero padded
+  const int kpad = k8 * 8;
+  for (int i = threadIdx.x; i < KC * kpad; i += blockDim.x) {
+    const int r = i / kpad, c = i - r * kpad;
+    w_s[i] = (c < g.K) ? w[r * g.K + c] : 0.f;
+  }
+  __syncthreads();
+  const int groups_per_row = (g.OW + PX - 1) / PX;
+  const int n_groups = g.N * g.OH * groups_per_row;
+  const int groups_per_block = kThreads / k8;
+  const int lg = threadIdx.x / k8, cg = threadIdx.x - lg * k8;
+  if (lg >= groups_per_block) return;
+  for (int grp = blockIdx.x * groups_per_block + lg; grp < n_groups;
+       grp += gridDim.x * groups_per_block) {
+    const int gx = grp % groups_per_row;
+    const int r = grp / groups_per_row;
+    const int oy = r % g.OH, n = r / g.OH;
+    const int ox0 = gx * PX;
+    const int iy0 = oy - g.pad_t, ix0 = ox0 - g.pad_l;
+    const float* px = x + ((int64_t)(n * g.H + iy0) * g.W + ix0) * 3;
+    float v[3][IN_W];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const bool row_in = !CHECK || (unsigned)(iy0 + dy) < (unsigned)g.H;
+#pragma unroll
+      for (int j = 0; j < PX + 2; ++j) {
+        // columns beyond the image (right edge of the last group / SAME padding) read as 0
+        const bool in = row_in && (unsigned)(ix0 + j) < (unsigned)g.W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          v[dy][j * 3 + c] = in ? __ldg(px + (dy * g.W + j) * 3 + c) : 0.f;
+      }
+    }
+    float acc[PX][8];
+#pragma unroll
+    for (int q = 0; q < PX; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {  // t = dx * 3 + c
+        const int k = dy * 9 + t;
+        const float4 w0 = *reinterpret_cast<const float4*>(&w_s[k * kpad + cg * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&w_s[k * kpad + cg * 8 + 4]);
+#pragma unroll
+        for (int q = 0; q < PX; ++q) {
+          const float a = v[dy][q * 3 + t];
+          acc[q][0] = fmaf(a, w0.x, acc[q][0]);
+          acc[q][1] = fmaf(a, w0.y, acc[q][1]);
+          acc[q][2] = fmaf(a, w0.z, acc[q][2]);
+          acc[q][3] = fmaf(a, w0.w, acc[q][3]);
+          acc[q][4] = fmaf(a, w1.x, acc[q][4]);
+          acc[q][5] = fmaf(a, w1.y, acc[q][5]);
+          acc[q][6] = fmaf(a, w1.z, acc[q][6]);
+          acc[q][7] = fmaf(a, w1.w, acc[q][7]);
+        }
+      }
+    float* out = y + ((int64_t)(n * g.OH + oy) * g.OW + ox0) * g.K + cg * 8;
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+      if (ox0 + q < g.OW) {
+        reinterpret_cast<float4*>(out + (int64_t)q * g.K)[0] =
+            make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+        reinterpret_cast<float4*>(out + (int64_t)q * g.K)[1] =
+            make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+      }
+    }
+  }
+}
+
+// wgrad: a thread owns a 4 (tap-channel) x 8 (output channel) register tile and a 1/S share of
+// the staged pixels: 3 shared-memory quads feed 32 FMAs (the kernel above: 2 loads per 4).
+// The S pixel shares are summed through shared memory in a fixed order at the end, then the
+// per-block partial filter goes to the usual deterministic second pass.
+template <bool CHECK>
+__global__ void __launch_bounds__(kThreads) conv_wgrad_rgb3x3_tile_kernel(
+    const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partial,
+    const __grid_constant__ sp_conv_geom g, int pix_per_block) {
+  constexpr int KC = 27, KCP = 28, RG = 7;       // 7 row groups of 4 (row 27 is a zero pad)
+  extern __shared__ __align__(16) float sm[];
+  const int K = g.K, k8 = K >> 3;
+  float* patch_s = sm;                             // [kWgTile][KCP]
+  float* gy_s = sm + kWgTile * KCP;                // [kWgTile][K]
+  const int per_share = RG * k8;                   // threads working on one pixel share
+  const int S = kThreads / per_share;              // pixel shares
+  const int share = threadIdx.x / per_share;
+  const int rem = threadIdx.x - share * per_share;
+  const int rg = rem / k8, kg = rem - rg * k8;
+  const bool worker = share < S;
+  const int n_pix = g.N * g.OH * g.OW;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(n_pix, p_begin + pix_per_block);
+  const int row_stride = g.W * 3;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int pt = p_begin; pt < p_end; pt += kWgTile) {
+    const int tile = min(kWgTile, p_end - pt);
+    __syncthreads();  // previous tile consumed
+    const int k4 = K >> 2;
+    for (int i = threadIdx.x; i < tile * k4; i += kThreads) {
+      const int pp = i / k4, q = i - pp * k4;
+      *reinterpret_cast<float4*>(&gy_s[pp * K + q * 4]) =
+          __ldg(reinterpret_cast<const float4*>(gy + (int64_t)(pt + pp) * K) + q);
+    }
+    {
+      // thread (pixel, half): rows dy = 0,1 (18 values) or dy = 2 plus the pad (10 values)
+      const int pp = threadIdx.x >> 1, h = threadIdx.x & 1;
+      if (pp < tile) {
+        const int p = pt + pp;
+        const int ox = p % g.OW;
+        const int r = p / g.OW;
+        const int oy = r % g.OH, n = r / g.OH;
+        const int iy0 = oy * g.sy - g.pad_t, ix0 = ox * g.sx - g.pad_l;
+        const float* px = x + ((int64_t)(n * g.H + iy0) * g.W + ix0) * 3;
+        float* dst = patch_s + pp * KCP;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          if ((dy < 2) == (h == 0)) {
+            const bool row_in = !CHECK || (unsigned)(iy0 + dy) < (unsigned)g.H;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const bool in = row_in && (!CHECK || (unsigned)(ix0 + dx) < (unsigned)g.W);
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                dst[(dy * 3 + dx) * 3 + c] = in ? __ldg(px + dy * row_stride + dx * 3 + c) : 0.f;
+            }
+          }
+        }
+        if (h == 1) dst[KC] = 0.f;
+      }
+    }
+    __syncthreads();
+    if (worker) {
+      for (int pp = share; pp < tile; pp += S) {
+        const float4 a = *reinterpret_cast<const float4*>(&patch_s[pp * KCP + rg * 4]);
+        const float4 d0 = *reinterpret_cast<const float4*>(&gy_s[pp * K + kg * 8]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&gy_s[pp * K + kg * 8 + 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i][0] = fmaf(av[i], d0.x, acc[i][0]);
+          acc[i][1] = fmaf(av[i], d0.y, acc[i][1]);
+          acc[i][2] = fmaf(av[i], d0.z, acc[i][2]);
+          acc[i][3] = fmaf(av[i], d0.w, acc[i][3]);
+          acc[i][4] = fmaf(av[i], d1.x, acc[i][4]);
+          acc[i][5] = fmaf(av[i], d1.y, acc[i][5]);
+          acc[i][6] = fmaf(av[i], d1.z, acc[i][6]);
+          acc[i][7] = fmaf(av[i], d1.w, acc[i][7]);
+        }
+      }
+    }
+  }
+  // fixed-order sum of the S pixel shares: red[share][row][K] aliases the staging buffers
+  __syncthreads();
+  float* red = sm;
+  if (worker) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* dst = red + ((share * KCP) + rg * 4 + i) * K + kg * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+  }
+  __syncthreads();
+  float* out = partial + (int64_t)blockIdx.x * KC * K;
+  for (int i = threadIdx.x; i < KC * K; i += kThreads) {
+    float s = 0.f;
+    for (int sh = 0; sh < S; ++sh) s += red[sh * KCP * K + i];
+    out[i] = s;
+  }
+}
+
 }  // namespace
 
 bool small_c_supported(const sp_conv_geom& g) {
@@ -344,12 +530,26 @@ static bool needs_bounds_check(const sp_conv_geom& g) {
          (g.OW - 1) * g.sx + g.KW > g.W;
 }
 
+// register-tiled RGB 3x3 kernels: K a multiple of 8 (float4 pairs), stride 1 for fprop
+static bool rgb_tile_fprop(const sp_conv_geom& g) {
+  return fixed_window(g) && g.K % 8 == 0 && g.sy == 1 && g.sx == 1;
+}
+static bool rgb_tile_wgrad(const sp_conv_geom& g) { return fixed_window(g) && g.K % 8 == 0; }
+static size_t rgb_tile_wgrad_smem(const sp_conv_geom& g) {
+  const size_t stage = (size_t)kWgTile * (28 + g.K);
+  const size_t shares = kThreads / (7 * (g.K / 8));
+  const size_t red = shares * 28 * g.K;
+  return std::max(stage, red) * sizeof(float);
+}
+
 int small_c_wgrad_blocks(const sp_conv_geom& g) {
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int64_t n_pix = (int64_t)g.N * g.OH * g.OW;
   const bool fixed = fixed_window(g) && (g.K % 4 == 0);
   const int tile = fixed ? kWgTile : kPixTile;
   int64_t blocks = std::min<int64_t>((fixed ? 4 : 2) * sms, (n_pix + tile - 1) / tile);
+  // fewer, longer blocks for the register-tiled kernel: less partial-filter traffic
+  if (rgb_tile_wgrad(g)) blocks = std::min<int64_t>(2 * sms, (n_pix + tile - 1) / tile);
   return (int)std::max<int64_t>(blocks, 1);
 }
 
@@ -361,7 +561,14 @@ int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_
   const int64_t n_pix = (int64_t)g.N * g.OH * g.OW;
   const int grid = wave_grid(n_pix, pix_per_block, 8);
   const size_t smem = (size_t)kc * k8 * 8 * sizeof(float);
-  if (fixed_window(g)) {
+  if (rgb_tile_fprop(g) && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    const int64_t n_groups = (int64_t)g.N * g.OH * ((g.OW + 3) / 4);
+    const int grid4 = wave_grid(n_groups, kThreads / k8, 4);
+    if (needs_bounds_check(g))
+      conv_fprop_rgb3x3_tile4_kernel<true><<<grid4, kThreads, smem, st>>>(x, w, y, g, k8);
+    else
+      conv_fprop_rgb3x3_tile4_kernel<false><<<grid4, kThreads, smem, st>>>(x, w, y, g, k8);
+  } else if (fixed_window(g)) {
     if (needs_bounds_check(g))
       conv_fprop_smallc_fixed_kernel<3, 3, 3, true><<<grid, kThreads, smem, st>>>(x, w, y, g, k8);
     else
@@ -383,7 +590,21 @@ int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial,
   const int tile = (fixed_window(g) && (g.K % 4 == 0)) ? kWgTile : kPixTile;
   int64_t per = (n_pix + blocks - 1) / blocks;
   per = (per + tile - 1) / tile * tile;
-  if (fixed) {
+  if (fixed && rgb_tile_wgrad(g)) {
+    const size_t smem = rgb_tile_wgrad_smem(g);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(conv_wgrad_rgb3x3_tile_kernel<true>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(conv_wgrad_rgb3x3_tile_kernel<false>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr_done = true;
+    }
+    if (needs_bounds_check(g))
+      conv_wgrad_rgb3x3_tile_kernel<true><<<blocks, kThreads, smem, st>>>(x, gy, partial, g, (int)per);
+    else
+      conv_wgrad_rgb3x3_tile_kernel<false><<<blocks, kThreads, smem, st>>>(x, gy, partial, g, (int)per);
+  } else if (fixed) {
     if (needs_bounds_check(g))
       conv_wgrad_smallc_fixed_kernel<3, 3, 3, true><<<blocks, kThreads, 0, st>>>(x, gy, partial, g,
                                                                                 (int)per);

@@ -63,6 +63,7 @@ struct Tma2Params {
   int k_chunk;         // wgrad: pixels per split (multiple of 32)
   int k_total;         // wgrad: N*OH*OW
   int debug;           // experiments (SP_TMA2_DEBUG), unused by default
+  long long* trace;    // sp_debug_tma2_trace: clock64 stamps of cluster 0's leader CTA, or null
   float* C;
   int64_t ldc;
   int64_t split_stride;
@@ -98,15 +99,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 }
 // arrive on a barrier addressed in the cluster window (own or peer CTA)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
+// Default (CTA-scope acquire) wait, as CUTLASS's ClusterBarrier: a `.acquire.cluster` wait
+// makes ptxas append CCTL.IVALL (invalidate all of L1) to every successful wait -- measured
+// ~400 cycles per pipeline step on the producer and MMA threads (profiles/r01_tma2_trace_*).
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
@@ -236,6 +240,12 @@ __device__ __forceinline__ uint32_t instr_desc_tf32_m256(int bn, bool a_mn, bool
          ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
+// bring-up instrumentation: slot layout documented in scripts/tma2_trace.py
+constexpr int kTraceKb = 96;
+__device__ __forceinline__ void trace_at(const Tma2Params& p, bool on, int slot) {
+  if (on) p.trace[slot] = clock64();
+}
+
 struct TileCoord {
   int m_pair, n_tile, split, n0, bn, kblocks;
 };
@@ -306,6 +316,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
   auto tmem_full_bar = [&](int a) { return bar0 + 8u * (2 * kStages + a); };
   auto tmem_empty_bar = [&](int a) { return bar0 + 8u * (2 * kStages + 2 + a); };
+  const bool tr = p.trace != nullptr && cluster_id == 0 && leader && lane == 0;
+  trace_at(p, tr && warp == 0, 0);
 
   if (t == 0) {
     for (int s = 0; s < kS; ++s) {
@@ -326,6 +338,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  trace_at(p, tr && warp == 0, 1);
 
   if (warp <= kWarpB) {
     // =========================== TMA PRODUCERS (both CTAs) ================================
@@ -337,6 +350,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       int s = 0;
       uint32_t ph = 0;
       int rr = 0;  // fprop / dgrad: k-block counter modulo kAWarps
+      int gkb = 0;
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
         const TileCoord tc = tile_coord(p, tile);
         const int bnh = tc.bn >> 1;  // this CTA's share of the N columns
@@ -366,6 +380,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const bool mine = is_b || MODE == kWgrad || rr == warp;
           if (mine) {
             mbar_wait(empty_bar(s), ph ^ 1u);
+            trace_at(p, tr && gkb < kTraceKb && (is_b || warp == 0 || MODE != kWgrad),
+                     16 + (is_b ? kTraceKb : 0) + gkb);
             const uint32_t fb = full0 + 8u * s;
             const uint32_t a_tile = tiles + (uint32_t)s * Cfg::kStage;
             const uint32_t b_tile = a_tile + Cfg::kABytes;
@@ -407,6 +423,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             }
           }
           pix += Cfg::kKStage;
+          ++gkb;
           if (++cb == p.cblocks) {
             cb = 0;
             ++tap;
@@ -425,6 +442,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
+      int gkb = 0;
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
         const TileCoord tc = tile_coord(p, tile);
         const uint32_t idesc = instr_desc_tf32_m256(tc.bn, A_MN, B_MN);
@@ -434,6 +452,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccumCols);
         for (int kb = 0; kb < tc.kblocks; ++kb) {
           mbar_wait(full_bar(s), ph);
+          trace_at(p, tr && gkb < kTraceKb, 16 + 2 * kTraceKb + gkb);
+          ++gkb;
           tc_fence_after();
           const uint32_t a_tile = tiles + (uint32_t)s * Cfg::kStage;
           const uint32_t b_tile = a_tile + Cfg::kABytes;
@@ -456,6 +476,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
         umma_commit_2sm(tmem_full_bar(acc));  // both CTAs' epilogues may drain stage acc
+        trace_at(p, tr && it < 4, 2 + it);
       }
     }
   } else if (warp >= kWarpEpi0) {
@@ -469,6 +490,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const TileCoord tc = tile_coord(p, tile);
       const int acc = it & 1;
       mbar_wait(tmem_full_bar(acc), ((uint32_t)it >> 1) & 1u);
+      trace_at(p, tr && warp == kWarpEpi0 && it < 4, 6 + it);
       tc_fence_after();
       const int m = (tc.m_pair * 2 + (int)rank) * 128 + quad * 32 + lane;
       float* __restrict__ crow =
@@ -494,6 +516,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(empty_leader0 + 8u * acc);
+      trace_at(p, tr && warp == kWarpEpi0 && it < 4, 10 + it);
     }
   }
 
@@ -502,6 +525,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   __syncthreads();
   cluster_sync_all();
   if (warp == kWarpTmem) tmem_dealloc_2sm(tmem_base, 512);
+  trace_at(p, tr && warp == 0, 14);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -642,10 +666,14 @@ bool cached_map(const void* ptr, int kind, const sp_conv_geom& g, int extra, CUt
   return true;
 }
 
+long long* g_trace = nullptr;
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline bool corner_ok(int v) { return v >= -128 && v <= 127; }
 
 }  // namespace
+
+void conv_tma2_set_trace(long long* device_buffer) { g_trace = device_buffer; }
 
 bool conv_tma2_supported(int mode, const IgemmParams& p) {
   const sp_conv_geom& g = p.g;
@@ -703,6 +731,7 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
     const char* dbg = getenv("SP_TMA2_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+  p.trace = g_trace;
   const int up_h = (g.OH - 1) * g.sy + 1 - g.H - g.pad_t, up_w = (g.OW - 1) * g.sx + 1 - g.W - g.pad_l;
   if (mode == kFprop) {
     p.cblocks = g.C / 32;

@@ -50,6 +50,8 @@ void igemm_umma_set_sync_mode(int mode);
 // 2-SM (cta_group::2) TMA-fed tcgen05 conv kernels, conv_tma2.cu: channel counts % 32 == 0
 bool conv_tma2_supported(int mode, const IgemmParams& p);
 int launch_conv_tma2(int mode, const IgemmParams& p, cudaStream_t stream);
+// bring-up: cluster 0 writes clock64 stamps into `device_buffer` (>= 512 int64), null = off
+void conv_tma2_set_trace(long long* device_buffer);
 
 // First-layer (C <= 4) CUDA-core kernels, conv_smallc.cu
 bool small_c_supported(const sp_conv_geom& g);

@@ -30,6 +30,10 @@ CONV_CASES = [
     ("c128_k256_valid", (2, 9, 9, 128), (3, 3, 128, 256), (1, 1), "VALID"),
     ("c32_k192_k2x3", (3, 9, 10, 32), (2, 3, 32, 192), (1, 1), "SAME"),
     ("c512_k64_k1", (1, 10, 13, 512), (1, 1, 512, 64), (1, 1), "SAME"),
+    # RGB 3x3 first layers: register-tiled CUDA-core kernels (csrc/conv_smallc.cu)
+    ("k3_c3_same_k64", (2, 9, 7, 3), (3, 3, 3, 64), (1, 1), "SAME"),
+    ("k3_c3_s2_k16", (2, 11, 10, 3), (3, 3, 3, 16), (2, 2), "SAME"),
+    ("k3_c3_valid_k8", (3, 6, 13, 3), (3, 3, 3, 8), (1, 1), "VALID"),
 ]
 
 # name, x shape, (kh, kw), (sy, sx), padding
