@@ -76,6 +76,10 @@ int sp_debug_tma2_trace(void* device_buffer);
 
 /* ---- memory helpers (replace NumPy array construction / copies) -------------------- */
 int sp_memcpy_h2d(void* dst, const void* host_src, size_t bytes, sp_stream_t stream);
+/* *pinned = 1 when host_ptr is page-locked memory: the input pipeline then DMAs straight out
+ * of the caller's batch (sp.batch / X[indices], sp.py:586-593) and narrows float64 -> fp32 on
+ * the device instead of converting on a host core */
+int sp_host_is_pinned(const void* host_ptr, int* pinned);
 /* copies and waits for the stream: the only blocking call of the ABI (sp.py users read
  * `.array`, e.g. np.isnan(loss_val.array), README.md:156) */
 int sp_memcpy_d2h(void* host_dst, const void* src, size_t bytes, sp_stream_t stream);

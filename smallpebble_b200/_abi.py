@@ -40,6 +40,7 @@ SIGNATURES = {
     "sp_debug_set_umma_policy": (C.c_int, [C.c_int]),
     "sp_debug_tma2_trace": (C.c_int, [vp]),
     "sp_memcpy_h2d": (C.c_int, [vp, vp, sz, vp]),
+    "sp_host_is_pinned": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "sp_memcpy_d2h": (C.c_int, [vp, vp, sz, vp]),
     "sp_memcpy_d2d": (C.c_int, [vp, vp, sz, vp]),
     "sp_fill_f32": (C.c_int, [vp, i64, f32, vp]),
@@ -86,7 +87,7 @@ _lib = None
 _LAUNCHING = {
     n for n in SIGNATURES
     if n not in ("sp_abi_version", "sp_last_error", "sp_device_info", "sp_debug_set_umma_policy",
-                 "sp_debug_tma2_trace", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
+                 "sp_debug_tma2_trace", "sp_host_is_pinned", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
                  "sp_conv2d_wgrad_workspace")
 }
 
@@ -122,28 +123,123 @@ def last_error() -> str:
 
 
 class _Counter:
-    __slots__ = ("launches",)
+    """Kernel-launching ABI calls made by this process (bench: gpu_launches): the ones that
+    went through ctypes plus the ones counted inside the fast-call binding."""
+
+    __slots__ = ("_py",)
 
     def __init__(self):
-        self.launches = 0
+        self._py = 0
+
+    @property
+    def launches(self):
+        return self._py + (_fast.launches() if _fast is not None else 0)
+
+    @launches.setter
+    def launches(self, value):
+        self._py = value - (_fast.launches() if _fast is not None else 0)
 
 
-counter = _Counter()  # kernel-launching ABI calls made by this process (bench: gpu_launches)
+counter = _Counter()
+_fast = None          # the _sp_fastcall module once loaded (None: ctypes only)
+_fast_tried = False
+
+
+def _load_fast():
+    """Import smallpebble_b200/_lib/_sp_fastcall.so (csrc/fastcall.c); ctypes stays the
+    fallback binding when it is missing or SP_NO_FASTCALL=1."""
+    global _fast, _fast_tried
+    if _fast_tried:
+        return _fast
+    _fast_tried = True
+    if os.environ.get("SP_NO_FASTCALL") == "1":
+        return None
+    path = os.path.join(_HERE, "_lib", "_sp_fastcall.so")
+    if not os.path.exists(path):
+        return None
+    try:
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("_sp_fastcall", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _fast = mod
+    except Exception:  # noqa: BLE001 - any failure means "use ctypes"
+        _fast = None
+    return _fast
+
+
+def _fail(name, rc):
+    raise SmallPebbleCudaError(f"{name} failed (code {rc}): {last_error()}")
 
 
 class _Profiler:
-    """Optional per-call CUDA-event timing of kernel-launching ABI calls (bench.py's roofline
-    measurement).  `select(name, seq)` decides which calls get an event pair; `seq` counts
-    launching calls since `begin_step()`.  Inactive by default: one attribute test per call."""
+    """Optional CUDA-event timing of kernel-launching ABI calls (bench.py's roofline).
+
+    Two modes, both off by default (then an ABI call costs one attribute test):
+      * `active = True`: every launching call gets an event pair (one instrumented step, to
+        find the dominant call);  `seq` counts launching calls since `begin_step()`.
+      * `arm(name, seq, every)`: ONLY calls of ABI function `name` pay anything: the one whose
+        per-step sequence number is `seq` is bracketed by events on every `every`-th step.
+        This is what runs inside the timed region."""
 
     def __init__(self):
-        self.active = False
-        self.select = None
+        self._active = False
+        self.select = None   # callable(name, seq) -> bool, or None (all)
         self.seq = 0
-        self.records = []  # (name, seq, args, start_event, stop_event)
+        self.step = 0
+        self.records = []    # (name, seq, args, start_event, stop_event)
+        self._armed = None   # (name, original wrapper)
+
+    @property
+    def active(self):
+        return self._active
+
+    @active.setter
+    def active(self, value):
+        # the per-call bookkeeping lives in the ctypes wrappers: swap bindings while it is on
+        self._active = bool(value)
+        f._rebind(slow=self._active)
 
     def begin_step(self):
         self.seq = 0
+        self.step += 1
+
+    def arm(self, name, seq, every=1):
+        """Time call number `seq` (as counted in `active` mode) of function `name`."""
+        self.disarm()
+        inner = getattr(f, name)
+        # position of the target among the calls of `name` within one step
+        nth = sum(1 for r in self.records if r[0] == name and r[1] < seq)
+        state = {"count": 0, "step": -1}
+        prof_self = self
+
+        def timed(*args):
+            if state["step"] != prof_self.step:
+                state["step"] = prof_self.step
+                state["count"] = 0
+            k = state["count"]
+            state["count"] = k + 1
+            if k == nth and prof_self.step % every == 0:
+                import torch
+
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                inner(*args)
+                e1.record()
+                prof_self.timed_records.append((name, seq, args, e0, e1))
+            else:
+                inner(*args)
+
+        self.timed_records = []
+        self._armed = (name, inner)
+        setattr(f, name, timed)
+
+    def disarm(self):
+        if self._armed is not None:
+            setattr(f, self._armed[0], self._armed[1])
+            self._armed = None
 
 
 prof = _Profiler()
@@ -189,17 +285,35 @@ class _Functions:
     that importing the package works on a machine without the library (host-only tests);
     the first real call loads it or raises."""
 
+    _slow_mode = False
+
     def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
         lib = load()
         if name not in SIGNATURES:
             raise AttributeError(name)
         raw = getattr(lib, name)
-        if SIGNATURES[name][0] is C.c_int and name != "sp_abi_version":
-            fn = _checked(name, raw, name in _LAUNCHING)
+        restype, argtypes = SIGNATURES[name]
+        if restype is C.c_int and name != "sp_abi_version":
+            fast = _load_fast()
+            if fast is not None and not self._slow_mode:
+                sig = "".join("f" if t is f32 else "p" for t in argtypes)
+                fn = fast.bind(C.cast(raw, C.c_void_p).value, sig, name, _fail, name in _LAUNCHING)
+            else:
+                fn = _checked(name, raw, name in _LAUNCHING)
         else:
             fn = raw
         setattr(self, name, fn)
         return fn
+
+    def _rebind(self, slow: bool):
+        """Drop the cached bindings so that the next use re-creates them in the other mode."""
+        if slow == self._slow_mode:
+            return
+        self._slow_mode = slow
+        for name in [n for n in self.__dict__ if n in SIGNATURES]:
+            delattr(self, name)
 
 
 f = _Functions()

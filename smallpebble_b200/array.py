@@ -16,6 +16,7 @@ import ctypes as C
 import functools
 import math
 import numbers
+import sys
 import weakref
 
 import numpy as np
@@ -68,6 +69,7 @@ def reset_device_cache():
     global _device, _raw_stream
     _device = None
     _raw_stream = None
+    trim_pool()  # recycled buffers belong to the previous device
 
 
 _raw_stream = None
@@ -89,8 +91,58 @@ def _host_dtype(a: np.ndarray) -> np.dtype:
     return FLOAT
 
 
+# Free list in front of torch's caching allocator.  A training step allocates the same ~35
+# buffer sizes over and over; recycling the torch buffers by exact byte size turns each
+# `DeviceArray.empty` from a ~2 us torch.empty call into a dict lookup (the README loop is
+# host-bound on a B200).  Safety: a buffer goes back only when the dying DeviceArray holds the
+# LAST reference to it (views and in-place rebinding share buffers), everything runs on one
+# stream so reuse is stream-ordered, and the list is bypassed while a CUDA graph is being
+# recorded (graph-private memory must come from torch's capture pool).
+_free_blocks = {}            # nbytes -> [torch uint8 tensor]
+_free_bytes = 0
+_POOL_MAX_BLOCK = 64 << 20
+_POOL_MAX_TOTAL = 2 << 30
+_pool_bypass = 0
+_getrefcount = sys.getrefcount
+
+
+class pool_bypass:
+    """Context manager: allocate straight from torch (used around CUDA-graph capture)."""
+
+    def __enter__(self):
+        global _pool_bypass
+        _pool_bypass += 1
+
+    def __exit__(self, *exc):
+        global _pool_bypass
+        _pool_bypass -= 1
+
+
+def trim_pool() -> None:
+    """Hand every recycled buffer back to torch's allocator."""
+    global _free_bytes
+    _free_blocks.clear()
+    _free_bytes = 0
+    _scalar_ones.clear()
+
+
+_scalar_ones = {}  # shape -> read-only device constant 1.0 (the gradient seed of a scalar loss)
+
+
+def scalar_one(shape):
+    """(array of ones, fresh?) for a one-element `shape`.  Outside CUDA-graph recording the
+    constant is created once and shared (saves a fill launch per get_gradients); callers must
+    treat a shared one as read-only."""
+    if _pool_bypass:
+        return DeviceArray.full(shape, 1.0), True
+    arr = _scalar_ones.get(shape)
+    if arr is None:
+        arr = _scalar_ones[shape] = DeviceArray.full(shape, 1.0)
+    return arr, False
+
+
 class DeviceArray:
-    __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "__weakref__")
+    __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "_pk", "__weakref__")
     __array_priority__ = 1000.0
 
     def __init__(self, shape, dtype=FLOAT, buf=None, ptr=None, host=None):
@@ -100,6 +152,24 @@ class DeviceArray:
         self._buf = buf
         self._ptr = ptr
         self._host = host
+        self._pk = 0
+
+    def __del__(self):
+        # recycle the buffer if this was its last user (refs: slot, local, getrefcount arg)
+        global _free_bytes
+        try:
+            pk = self._pk
+            if pk and not _pool_bypass:
+                buf = self._buf
+                if buf is not None and _getrefcount(buf) == 3 and _free_bytes + pk <= _POOL_MAX_TOTAL:
+                    bucket = _free_blocks.get(pk)
+                    if bucket is None:
+                        _free_blocks[pk] = [buf]
+                    else:
+                        bucket.append(buf)
+                    _free_bytes += pk
+        except Exception:  # interpreter shutdown: module globals may be gone
+            pass
 
     # ---- construction ---------------------------------------------------------------------
     @staticmethod
@@ -109,9 +179,21 @@ class DeviceArray:
         self.shape = shape = tuple(shape)
         self.dtype = dtype = dtype if dtype is FLOAT else np.dtype(dtype)
         self.size = size = math.prod(shape)
-        self._buf = buf = _torch.empty((size or 1) * dtype.itemsize, dtype=_torch.uint8, device=dev)
-        self._ptr = buf.data_ptr()
         self._host = None
+        nbytes = (size or 1) * dtype.itemsize
+        if _pool_bypass or nbytes > _POOL_MAX_BLOCK:
+            self._pk = 0
+            self._buf = buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
+        else:
+            self._pk = nbytes
+            bucket = _free_blocks.get(nbytes)
+            if bucket:
+                global _free_bytes
+                _free_bytes -= nbytes
+                self._buf = buf = bucket.pop()
+            else:
+                self._buf = buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
+        self._ptr = buf.data_ptr()
         return self
 
     @staticmethod
@@ -125,6 +207,13 @@ class DeviceArray:
             raise TypeError(f"unsupported device dtype {dtype}")
         nbytes = a.size * dtype.itemsize
         if nbytes >= _PIN_THRESHOLD and _pinned.available():
+            if (dtype == FLOAT and a.dtype in _DIRECT_DTYPES and a.flags.c_contiguous
+                    and _is_pinned(a)):
+                # The caller's batch already sits in page-locked memory: no host pass at all.
+                # The upload DMAs the raw bytes from it and float64 is narrowed on the device.
+                # Like the reference's Variable(array), this aliases the caller's array until
+                # the copy has run (the array is kept alive; do not overwrite it in between).
+                return DeviceArray(a.shape, dtype, host=a)
             host = _pinned.take(a.shape, dtype)
             np.copyto(host, a, casting="unsafe")  # one pass: convert + stage
             out = DeviceArray(host.shape, dtype, host=host)
@@ -157,6 +246,17 @@ class DeviceArray:
     def _upload(self):
         dev = require_cuda()
         host = self._host
+        if host.dtype != self.dtype:
+            # pinned float64 source: raw DMA, then narrow on the device
+            raw = _torch.empty(host.nbytes, dtype=_torch.uint8, device=dev)
+            buf = _torch.empty(host.size * 4, dtype=_torch.uint8, device=dev)
+            st = stream()
+            F.sp_memcpy_h2d(raw.data_ptr(), host.ctypes.data, host.nbytes, st)
+            F.sp_cast_f64_f32(raw.data_ptr(), buf.data_ptr(), host.size, st)
+            _counters["h2d_bytes"] += host.nbytes
+            _keep_alive_until_copied(host)
+            self._buf, self._ptr, self._host = buf, buf.data_ptr(), None
+            return
         nbytes = max(host.size, 1) * host.dtype.itemsize
         buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
         if host.size:
@@ -164,7 +264,10 @@ class DeviceArray:
             # has completed; pageable memory: the runtime stages it before returning
             F.sp_memcpy_h2d(buf.data_ptr(), host.ctypes.data, host.nbytes, stream())
             _counters["h2d_bytes"] += host.nbytes
-            _pinned.release(host)
+            if host.ctypes.data in _pinned.owned:
+                _pinned.release(host)
+            elif host.nbytes >= _PIN_THRESHOLD:
+                _keep_alive_until_copied(host)  # direct DMA from the caller's pinned array
         self._buf, self._ptr, self._host = buf, buf.data_ptr(), None
 
     @property
@@ -175,7 +278,7 @@ class DeviceArray:
     def numpy(self) -> np.ndarray:
         """Device -> host copy (synchronises the stream)."""
         if self._ptr is None:
-            return self._host.copy()
+            return np.array(self._host, dtype=self.dtype, copy=True)
         out = np.empty(self.shape, self.dtype)
         F.sp_memcpy_d2h(out.ctypes.data, self._ptr, out.nbytes, stream())
         _counters["d2h_bytes"] += out.nbytes
@@ -233,7 +336,9 @@ class DeviceArray:
         shape = _resolve_shape(shape, self.size)
         if self._ptr is None:
             return DeviceArray(shape, self.dtype, host=self._host.reshape(shape))
-        return DeviceArray(shape, self.dtype, self._buf, self._ptr)  # shares the buffer
+        out = DeviceArray(shape, self.dtype, self._buf, self._ptr)  # shares the buffer
+        out._pk = self._pk  # whichever of the two dies last recycles it
+        return out
 
     def copy(self) -> "DeviceArray":
         out = DeviceArray.empty(self.shape, self.dtype)
@@ -297,6 +402,7 @@ class DeviceArray:
 
     def _rebind(self, other: "DeviceArray"):
         self._buf, self._ptr, self._host = other._buf, other.ptr, None
+        self._pk = other._pk
         return self
 
     def __iadd__(self, o):
@@ -365,6 +471,22 @@ class _PinnedPool:
 
 _pinned = _PinnedPool()
 _PIN_THRESHOLD = 64 * 1024
+_DIRECT_DTYPES = {np.dtype(np.float32), np.dtype(np.float64)}
+_in_flight_sources = []  # (event, ndarray): caller arrays an async H2D is still reading
+
+
+def _is_pinned(a: np.ndarray) -> bool:
+    flag = C.c_int(0)
+    F.sp_host_is_pinned(a.ctypes.data, flag)
+    return bool(flag.value)
+
+
+def _keep_alive_until_copied(host: np.ndarray) -> None:
+    ev = _torch.cuda.Event()
+    ev.record()
+    if len(_in_flight_sources) >= 8:
+        _in_flight_sources[:] = [(e, h) for e, h in _in_flight_sources if not e.query()]
+    _in_flight_sources.append((ev, host))
 
 _UFUNC_TO_OP = {np.add: "add", np.subtract: "sub", np.multiply: "mul", np.true_divide: "div"}
 _counters = {"h2d_bytes": 0, "d2h_bytes": 0}

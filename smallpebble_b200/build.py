@@ -19,6 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(OUT_DIR, "libsmallpebble_b200.so")
+FASTCALL_PATH = os.path.join(OUT_DIR, "_sp_fastcall.so")  # CPython binding (csrc/fastcall.c)
 STAMP = os.path.join(OUT_DIR, "build.stamp")
 
 NVCC_FLAGS = [
@@ -39,6 +40,7 @@ def _digest():
         os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")
     )
     files.append(os.path.join(os.path.dirname(HERE), "include", "smallpebble_b200.h"))
+    files.append(os.path.join(CSRC, "fastcall.c"))
     for f in files:
         h.update(f.encode())
         with open(f, "rb") as fh:
@@ -57,7 +59,8 @@ def find_nvcc():
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     digest = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
+    if (not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP)
+            and os.path.exists(FASTCALL_PATH)):
         with open(STAMP) as fh:
             if fh.read().strip() == digest:
                 return LIB_PATH
@@ -87,9 +90,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    build_fastcall()
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB_PATH
+
+
+def build_fastcall() -> str:
+    """The CPython fast-call binding: plain C, no CUDA (gcc + the interpreter's headers)."""
+    import sysconfig
+
+    cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        raise RuntimeError("no C compiler for smallpebble_b200/csrc/fastcall.c")
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-I", sysconfig.get_paths()["include"],
+           os.path.join(CSRC, "fastcall.c"), "-o", FASTCALL_PATH]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"fastcall build failed:\n{r.stdout}\n{r.stderr}")
+    return FASTCALL_PATH
 
 
 if __name__ == "__main__":

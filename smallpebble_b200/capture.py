@@ -53,10 +53,21 @@ def _copy_into(dst: DeviceArray, value) -> None:
     if staged.shape != dst.shape:
         raise ValueError(f"captured step: input shape {staged.shape} != captured {dst.shape}")
     host = staged._host
-    if host.size:
-        F.sp_memcpy_h2d(dst.ptr, host.ctypes.data, host.nbytes, A.stream())
-        A._counters["h2d_bytes"] += host.nbytes
+    if not host.size:
+        return
+    st = A.stream()
+    if host.dtype != dst.dtype:
+        # caller's pinned float64 batch: raw DMA into scratch, narrowed into the static buffer
+        raw = DeviceArray.empty((host.nbytes,), np.uint8)
+        F.sp_memcpy_h2d(raw.ptr, host.ctypes.data, host.nbytes, st)
+        F.sp_cast_f64_f32(raw.ptr, dst.ptr, host.size, st)
+    else:
+        F.sp_memcpy_h2d(dst.ptr, host.ctypes.data, host.nbytes, st)
+    A._counters["h2d_bytes"] += host.nbytes
+    if host.ctypes.data in A._pinned.owned:
         A._pinned.release(host)
+    else:
+        A._keep_alive_until_copied(host)
 
 
 class CapturedStep:
@@ -82,6 +93,10 @@ class CapturedStep:
         import torch
 
         A.require_cuda()
+        with A.pool_bypass():  # static buffers, warm-up and capture allocate from torch itself
+            return self._record_unpooled(args, torch)
+
+    def _record_unpooled(self, args, torch):
         static = [_static_like(a) for a in args]
         for dst, a in zip(static, args):
             _copy_into(dst, a)

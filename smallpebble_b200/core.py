@@ -197,8 +197,14 @@ def get_gradients(variable: Variable) -> dict:
     order.reverse()
 
     gradients = Gradients()
-    dict.__setitem__(gradients, variable, DeviceArray.full(variable.array.shape, 1.0))
-    owned = {variable}  # gradient buffers nobody else aliases: safe to accumulate in place
+    seed_shape = variable.array.shape
+    if math.prod(seed_shape) == 1:
+        seed, fresh = A.scalar_one(seed_shape)  # shared read-only constant: no fill launch
+    else:
+        seed, fresh = DeviceArray.full(seed_shape, 1.0), True
+    dict.__setitem__(gradients, variable, seed)
+    # gradient buffers nobody else aliases: safe to accumulate in place
+    owned = {variable} if fresh else set()
     for node in order:
         if not node.local_gradients:
             continue

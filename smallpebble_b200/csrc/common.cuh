@@ -27,6 +27,12 @@ const DeviceInfo& device_info();
 constexpr size_t kScratchFloats = 1 << 20;
 float* scratch_for_current_device();
 
+// Library-owned, zero-initialised synchronisation words (one set per device): self-resetting
+// arrival counters of single-launch "last block finishes the job" kernels.
+//   [0, 24)  fused Adam: per-tensor arrivals          [32], [33] grid barrier (count, generation)
+constexpr int kSyncWords = 64;
+unsigned int* sync_words_for_current_device();
+
 inline cudaStream_t as_stream(sp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // grid sized in whole waves of the SM count (B200: 148 SMs)
@@ -63,6 +69,26 @@ inline int wave_grid(int64_t work_items, int items_per_block, int blocks_per_sm)
   } while (0)
 
 // ---- device helpers -------------------------------------------------------------------
+// Barrier across all blocks of a COOPERATIVE launch (co-residency guaranteed by
+// cudaLaunchCooperativeKernel).  words[0] counts arrivals and wraps to 0 with the last one,
+// words[1] is the generation the waiters spin on: nothing to reset between launches and the
+// block count may differ from launch to launch.
+__device__ __forceinline__ void grid_barrier(unsigned int* words, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int* gen = words + 1;
+    const unsigned int my_gen = *gen;
+    __threadfence();  // this block's global writes are visible before it arrives
+    if (atomicInc(words, nblocks - 1) == nblocks - 1) {
+      atomicAdd(words + 1, 1u);
+    } else {
+      while (*gen == my_gen) __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
   // streaming 128-bit load: read once, do not pollute L1
   float4 r;

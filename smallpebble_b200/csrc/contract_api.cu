@@ -279,10 +279,12 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
     if (!workspace || workspace_bytes < need)
       return sp::set_error(SP_ERR_WORKSPACE, "conv2d_wgrad: workspace %zu < required %zu",
                            workspace_bytes, need);
-    if (int rc = sp::launch_conv_wgrad_smallc(x, gy, static_cast<float*>(workspace), *g, blocks,
-                                              sp::as_stream(stream)))
+    bool reduced = false;
+    if (int rc = sp::launch_conv_wgrad_smallc(x, gy, static_cast<float*>(workspace), dw, *g, blocks,
+                                              sp::as_stream(stream), &reduced))
       return rc;
     SP_CHECK_LAUNCH("conv2d_wgrad(small C)");
+    if (reduced) return 0;
     return sp_reduce_sum(static_cast<const float*>(workspace), dw, 1, blocks, p.M * p.N, stream);
   }
   const bool tma2 = sp::use_tma2(sp::kWgrad, p, precision);

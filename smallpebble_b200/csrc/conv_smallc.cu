@@ -511,6 +511,154 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_rgb3x3_tile_kernel(
   }
 }
 
+// Single-launch RGB 3x3 filter gradient (cooperative grid, one block per SM):
+//   * the block walks its pixel tiles with a two-stage cp.async pipeline (dY rows as 16-byte
+//     copies, patches as zero-filling 4-byte copies): the next tile streams in while the
+//     current one is multiplied, so no thread ever waits on a global round trip;
+//   * register tiling as in conv_wgrad_rgb3x3_tile_kernel (4 x 8 accumulators per thread);
+//   * per-block partial filters meet at a grid barrier and are summed in a fixed order by
+//     one warp per filter element -- deterministic, and no second kernel launch.
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const float* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+
+template <bool CHECK>
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rgb3x3_coop_kernel(
+    const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partial,
+    float* __restrict__ dw, const __grid_constant__ sp_conv_geom g, int n_tiles,
+    unsigned int* __restrict__ sync_words) {
+  constexpr int KC = 27, KCP = 28, RG = 7;
+  extern __shared__ __align__(16) float sm[];
+  const int K = g.K, k8 = K >> 3, k4 = K >> 2;
+  const int stage_floats = kWgTile * (KCP + K);
+  const int per_share = RG * k8;
+  const int S = kThreads / per_share;
+  const int share = threadIdx.x / per_share;
+  const int rem = threadIdx.x - share * per_share;
+  const int rg = rem / k8, kg = rem - rg * k8;
+  const bool worker = share < S;
+  const int n_pix = g.N * g.OH * g.OW;
+  const int row_stride = g.W * 3;
+
+  // the pad column of both stages is never written by the pipeline
+  for (int i = threadIdx.x; i < 2 * kWgTile; i += kThreads)
+    sm[(i / kWgTile) * stage_floats + (i % kWgTile) * KCP + KC] = 0.f;
+
+  auto prefetch = [&](int tile_idx, int stage) {
+    float* patch_s = sm + stage * stage_floats;
+    float* gy_s = patch_s + kWgTile * KCP;
+    const int pt = tile_idx * kWgTile;
+    const int tile = min(kWgTile, n_pix - pt);
+    for (int i = threadIdx.x; i < tile * k4; i += kThreads) {
+      const int pp = i / k4, q = i - pp * k4;
+      cp_async16(&gy_s[pp * K + q * 4], gy + (int64_t)(pt + pp) * K + q * 4);
+    }
+    const int pp = threadIdx.x >> 1, h = threadIdx.x & 1;
+    if (pp < tile) {
+      const int p = pt + pp;
+      const int ox = p % g.OW;
+      const int r = p / g.OW;
+      const int oy = r % g.OH, n = r / g.OH;
+      const int iy0 = oy * g.sy - g.pad_t, ix0 = ox * g.sx - g.pad_l;
+      const float* px = x + ((int64_t)(n * g.H + iy0) * g.W + ix0) * 3;
+      float* dst = patch_s + pp * KCP;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        if ((dy < 2) == (h == 0)) {
+          const bool row_in = !CHECK || (unsigned)(iy0 + dy) < (unsigned)g.H;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const bool in = row_in && (!CHECK || (unsigned)(ix0 + dx) < (unsigned)g.W);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              cp_async4_zfill(&dst[(dy * 3 + dx) * 3 + c],
+                              in ? px + dy * row_stride + dx * 3 + c : x, in);
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  int stage = 0;
+  if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int next = t + gridDim.x;
+    if (next < n_tiles) {
+      prefetch(next, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // this stage has landed for every thread
+    const float* patch_s = sm + stage * stage_floats;
+    const float* gy_s = patch_s + kWgTile * KCP;
+    const int tile = min(kWgTile, n_pix - t * kWgTile);
+    if (worker) {
+      for (int pp = share; pp < tile; pp += S) {
+        const float4 a = *reinterpret_cast<const float4*>(&patch_s[pp * KCP + rg * 4]);
+        const float4 d0 = *reinterpret_cast<const float4*>(&gy_s[pp * K + kg * 8]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&gy_s[pp * K + kg * 8 + 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i][0] = fmaf(av[i], d0.x, acc[i][0]);
+          acc[i][1] = fmaf(av[i], d0.y, acc[i][1]);
+          acc[i][2] = fmaf(av[i], d0.z, acc[i][2]);
+          acc[i][3] = fmaf(av[i], d0.w, acc[i][3]);
+          acc[i][4] = fmaf(av[i], d1.x, acc[i][4]);
+          acc[i][5] = fmaf(av[i], d1.y, acc[i][5]);
+          acc[i][6] = fmaf(av[i], d1.z, acc[i][6]);
+          acc[i][7] = fmaf(av[i], d1.w, acc[i][7]);
+        }
+      }
+    }
+    __syncthreads();  // stage consumed: the prefetch of the iteration after next may reuse it
+    stage ^= 1;
+  }
+
+  // fixed-order sum of the S pixel shares through shared memory (aliases the stages)
+  float* red = sm;
+  if (worker) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* dst = red + ((share * KCP) + rg * 4 + i) * K + kg * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+  }
+  __syncthreads();
+  float* out = partial + (int64_t)blockIdx.x * KC * K;
+  for (int i = threadIdx.x; i < KC * K; i += kThreads) {
+    float s = 0.f;
+    for (int sh = 0; sh < S; ++sh) s += red[sh * KCP * K + i];
+    out[i] = s;
+  }
+
+  // every block's partial filter is in global memory: sum them, one warp per element
+  grid_barrier(sync_words + 32, gridDim.x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps = kThreads / 32;
+  for (int o = blockIdx.x * warps + warp; o < KC * K; o += gridDim.x * warps) {
+    float s = 0.f;
+    for (int j = lane; j < (int)gridDim.x; j += 32) s += __ldcg(partial + (int64_t)j * KC * K + o);
+    s = warp_sum(s);
+    if (lane == 0) dw[o] = s;
+  }
+}
+
 }  // namespace
 
 bool small_c_supported(const sp_conv_geom& g) {
@@ -536,10 +684,10 @@ static bool rgb_tile_fprop(const sp_conv_geom& g) {
 }
 static bool rgb_tile_wgrad(const sp_conv_geom& g) { return fixed_window(g) && g.K % 8 == 0; }
 static size_t rgb_tile_wgrad_smem(const sp_conv_geom& g) {
-  const size_t stage = (size_t)kWgTile * (28 + g.K);
+  const size_t stages = 2 * (size_t)kWgTile * (28 + g.K);
   const size_t shares = kThreads / (7 * (g.K / 8));
   const size_t red = shares * 28 * g.K;
-  return std::max(stage, red) * sizeof(float);
+  return std::max(stages, red) * sizeof(float);
 }
 
 int small_c_wgrad_blocks(const sp_conv_geom& g) {
@@ -548,8 +696,8 @@ int small_c_wgrad_blocks(const sp_conv_geom& g) {
   const bool fixed = fixed_window(g) && (g.K % 4 == 0);
   const int tile = fixed ? kWgTile : kPixTile;
   int64_t blocks = std::min<int64_t>((fixed ? 4 : 2) * sms, (n_pix + tile - 1) / tile);
-  // fewer, longer blocks for the register-tiled kernel: less partial-filter traffic
-  if (rgb_tile_wgrad(g)) blocks = std::min<int64_t>(2 * sms, (n_pix + tile - 1) / tile);
+  // single-launch cooperative kernel: one block per SM
+  if (rgb_tile_wgrad(g)) blocks = std::min<int64_t>(sms, (n_pix + tile - 1) / tile);
   return (int)std::max<int64_t>(blocks, 1);
 }
 
@@ -580,8 +728,9 @@ int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_
 }
 
 // partial must hold small_c_wgrad_blocks(g) * KH*KW*C * K floats
-int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial,
-                             const sp_conv_geom& g, int blocks, cudaStream_t st) {
+int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial, float* dw,
+                             const sp_conv_geom& g, int blocks, cudaStream_t st, bool* reduced) {
+  *reduced = false;
   const int kc = g.KH * g.KW * g.C;
   const int64_t n_pix = (int64_t)g.N * g.OH * g.OW;
   const bool fixed = fixed_window(g) && (g.K % 4 == 0) &&
@@ -590,20 +739,30 @@ int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial,
   const int tile = (fixed_window(g) && (g.K % 4 == 0)) ? kWgTile : kPixTile;
   int64_t per = (n_pix + blocks - 1) / blocks;
   per = (per + tile - 1) / tile * tile;
-  if (fixed && rgb_tile_wgrad(g)) {
+  if (fixed && rgb_tile_wgrad(g) && (reinterpret_cast<uintptr_t>(dw) & 15) == 0) {
     const size_t smem = rgb_tile_wgrad_smem(g);
     static bool attr_done = false;
     if (!attr_done) {
-      cudaFuncSetAttribute(conv_wgrad_rgb3x3_tile_kernel<true>,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      cudaFuncSetAttribute(conv_wgrad_rgb3x3_tile_kernel<false>,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(conv_wgrad_rgb3x3_coop_kernel<true>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+      cudaFuncSetAttribute(conv_wgrad_rgb3x3_coop_kernel<false>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
       attr_done = true;
     }
-    if (needs_bounds_check(g))
-      conv_wgrad_rgb3x3_tile_kernel<true><<<blocks, kThreads, smem, st>>>(x, gy, partial, g, (int)per);
-    else
-      conv_wgrad_rgb3x3_tile_kernel<false><<<blocks, kThreads, smem, st>>>(x, gy, partial, g, (int)per);
+    unsigned int* words = sync_words_for_current_device();
+    if (!words) return set_error(SP_ERR_WORKSPACE, "conv2d_wgrad: no sync words");
+    int n_tiles = (int)((n_pix + kWgTile - 1) / kWgTile);
+    sp_conv_geom gg = g;
+    void* args[] = {(void*)&x, (void*)&gy, (void*)&partial, (void*)&dw, (void*)&gg,
+                    (void*)&n_tiles, (void*)&words};
+    const void* fn = needs_bounds_check(g) ? (const void*)conv_wgrad_rgb3x3_coop_kernel<true>
+                                           : (const void*)conv_wgrad_rgb3x3_coop_kernel<false>;
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(kThreads), args,
+                                                smem, st);
+    if (e != cudaSuccess)
+      return set_error((int)e, "cooperative launch of conv_wgrad_rgb3x3 failed: %s",
+                       cudaGetErrorString(e));
+    *reduced = true;
   } else if (fixed) {
     if (needs_bounds_check(g))
       conv_wgrad_smallc_fixed_kernel<3, 3, 3, true><<<blocks, kThreads, 0, st>>>(x, gy, partial, g,

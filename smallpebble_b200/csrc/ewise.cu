@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(kThreads) leaky_bwd_kernel(const float* __rest
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // 8 resident blocks of 256 threads per SM, 4 float4 per thread per trip
-inline int ew_grid(int64_t n) { return sp::wave_grid(n, kThreads * 16, 8); }
+// >= 4 elements per thread; tiny arrays spread over several blocks (latency, not bandwidth)
+inline int ew_grid(int64_t n) { return sp::wave_grid(n, kThreads * 4, 8); }
 
 template <int OP>
 int launch_unary(const float* x, float* y, int64_t n, float p, cudaStream_t st) {

@@ -58,7 +58,8 @@ bool small_c_supported(const sp_conv_geom& g);
 int small_c_wgrad_blocks(const sp_conv_geom& g);
 int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_conv_geom& g,
                              cudaStream_t st);
-int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial,
-                             const sp_conv_geom& g, int blocks, cudaStream_t st);
+// `*reduced` = true when the kernel already summed its partial filters into dw
+int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial, float* dw,
+                             const sp_conv_geom& g, int blocks, cudaStream_t st, bool* reduced);
 
 }  // namespace sp

@@ -88,6 +88,21 @@ int sp_memcpy_h2d(void* dst, const void* host_src, size_t bytes, sp_stream_t str
   return 0;
 }
 
+// 1 when `host_ptr` lies in page-locked (cudaHostAlloc / cudaHostRegister) memory, so that an
+// async copy from it is a true DMA that needs no staging.
+int sp_host_is_pinned(const void* host_ptr, int* pinned) {
+  if (!pinned) return sp::set_error(SP_ERR_INVALID_ARGUMENT, "sp_host_is_pinned: null output");
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, host_ptr);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();  // unregistered pageable memory on old drivers: not an error here
+    *pinned = 0;
+    return 0;
+  }
+  *pinned = attr.type == cudaMemoryTypeHost ? 1 : 0;
+  return 0;
+}
+
 int sp_memcpy_d2h(void* host_dst, const void* src, size_t bytes, sp_stream_t stream) {
   if (bytes != 0)
     SP_CHECK_CUDA(

@@ -3,13 +3,15 @@
 // CUDA block owns one 4096-element chunk of one tensor.  HBM-bound: Adam touches
 // 28 B/param (read p,g,m,v; write p,m,v), all with 128-bit accesses.
 // Replaces the Python loop + ~10 NumPy temporaries per variable of sp.py:573-583.
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace {
 constexpr int kThreads = 256;
-constexpr int kChunk = kThreads * 16;  // elements per block
+constexpr int kChunk = kThreads * 16;      // elements per block (large models)
+constexpr int kChunkSmall = kThreads * 4;  // small models: one 128-bit access per thread
 constexpr int kMaxTensors = 24;
 
 struct AdamArgs {
@@ -21,6 +23,8 @@ struct AdamArgs {
   int32_t* step[kMaxTensors];  // device-resident count of COMPLETED steps of this tensor
   int block_start[kMaxTensors + 1];
   int count;
+  int chunk;                   // elements per block
+  unsigned int* done;          // [kMaxTensors] self-resetting arrival counters (library-owned)
 };
 
 struct AxpyArgs {
@@ -47,29 +51,27 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
 }
 
 // The bias corrections 1/(1 - beta^t) are evaluated on the device from a device-resident
-// step count (in double: 1 - 0.999 loses 1e-5 relative in fp32), so the launch carries no
-// step-dependent parameter and a captured CUDA graph of the training step stays valid.
+// step count, so the launch carries no step-dependent parameter and a captured CUDA graph of
+// the training step stays valid.  1 - beta^t = -expm1(t * ln(beta)) with ln(beta) rounded from
+// double: relative error ~1e-7 for every t (a naive 1 - powf(beta, t) loses 1e-5 at t = 1
+// for beta = 0.999; a double pow costs microseconds on this chip's few FP64 units).
+// The block that arrives last for a tensor bumps its step counter: every block of the tensor
+// has read the counter before it signals, so no second kernel is needed.
 __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_constant__ AdamArgs a,
-                                                              float alpha, double b1d, double b2d,
-                                                              float eps) {
-  __shared__ float corr[2];
+                                                              float alpha, float b1, float b2,
+                                                              float lnb1, float lnb2, float eps) {
   const int t = find_tensor(a, blockIdx.x);
-  if (threadIdx.x == 0) {
-    const double step = (double)(*a.step[t] + 1);
-    corr[0] = (float)(1.0 / (1.0 - pow(b1d, step)));
-    corr[1] = (float)(1.0 / (1.0 - pow(b2d, step)));
-  }
-  __syncthreads();
-  const float b1 = (float)b1d, b2 = (float)b2d;
-  const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * kChunk;
+  const float step = (float)(*a.step[t] + 1);
+  const float ic1 = 1.f / -expm1f(step * lnb1);
+  const float ic2 = 1.f / -expm1f(step * lnb2);
+  const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * a.chunk;
   const int64_t n = a.n[t];
   float* __restrict__ p = a.p[t];
   const float* __restrict__ g = a.g[t];
   float* __restrict__ m = a.m[t];
   float* __restrict__ v = a.v[t];
-  const float ic1 = corr[0], ic2 = corr[1];
   const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
-  const int64_t end = min(n, base + kChunk);
+  const int64_t end = min(n, base + a.chunk);
   if (vec) {
     for (int64_t i = base + 4 * threadIdx.x; i + 3 < end; i += 4 * kThreads) {
       float4 pp = *reinterpret_cast<float4*>(p + i);
@@ -92,11 +94,18 @@ __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_const
     for (int64_t i = base + threadIdx.x; i < end; i += kThreads)
       adam1(p[i], g[i], m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
   }
+  // all threads of this block have read the step count (it feeds ic1/ic2 used above)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int blocks_t = (unsigned int)(a.block_start[t + 1] - a.block_start[t]);
+    if (atomicInc(&a.done[t], blocks_t - 1) == blocks_t - 1) *a.step[t] += 1;
+  }
 }
 
-// runs after adam_multi_kernel on the same stream: step[t] += 1
+// tensors without elements still count their steps
 __global__ void adam_advance_kernel(const __grid_constant__ AdamArgs a) {
-  for (int t = threadIdx.x; t < a.count; t += blockDim.x) *a.step[t] += 1;
+  for (int t = threadIdx.x; t < a.count; t += blockDim.x)
+    if (a.n[t] == 0) *a.step[t] += 1;
 }
 
 __global__ void __launch_bounds__(kThreads) sgd_multi_kernel(const __grid_constant__ AxpyArgs a,
@@ -121,11 +130,13 @@ __global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_const
 
 inline int blocks_for(int64_t n) { return (int)((n + kChunk - 1) / kChunk); }
 
+// arrival counters: words [0, kMaxTensors) of the library's zero-initialised sync words
+unsigned int* adam_counters() { return sp::sync_words_for_current_device(); }
+
 // The ABI carries beta1/beta2 as float; the reference computes with the Python float the
 // user wrote (0.9, 0.999).  Recover it: the shortest decimal that round-trips the float.
 inline double strtod_round(float f) {
   char buf[32];
-  snprintf(buf, sizeof(buf), "%.9g", (double)f);
   for (int digits = 1; digits <= 9; ++digits) {
     snprintf(buf, sizeof(buf), "%.*g", digits, (double)f);
     if ((float)strtod(buf, nullptr) == f) return strtod(buf, nullptr);
@@ -142,10 +153,19 @@ int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_
                   sp_stream_t stream) {
   SP_REQUIRE(n_tensors >= 0, "negative tensor count");
   cudaStream_t st = sp::as_stream(stream);
+  unsigned int* counters = adam_counters();
+  if (!counters) return sp::set_error(SP_ERR_WORKSPACE, "sp_adam_multi: no counter scratch");
   for (int first = 0; first < n_tensors; first += kMaxTensors) {
     AdamArgs a;
     a.count = 0;
+    a.done = counters;
     int blocks = 0;
+    bool any_empty = false;
+    // a model that would not fill the chip with 4096-element chunks gets 1024-element ones
+    int64_t total = 0;
+    for (int i = first; i < n_tensors && i < first + kMaxTensors; ++i)
+      total += host_numel[i] > 0 ? host_numel[i] : 0;
+    a.chunk = (total / kChunk < 4 * 148) ? kChunkSmall : kChunk;
     for (int i = first; i < n_tensors && i < first + kMaxTensors; ++i) {
       SP_REQUIRE(host_step[i] != nullptr, "missing device step counter");
       const int k = a.count++;
@@ -154,9 +174,10 @@ int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_
       a.m[k] = host_m[i];
       a.v[k] = host_v[i];
       a.n[k] = host_numel[i] > 0 ? host_numel[i] : 0;
+      any_empty = any_empty || a.n[k] == 0;
       a.step[k] = host_step[i];
       a.block_start[k] = blocks;
-      blocks += blocks_for(a.n[k]);
+      blocks += (int)((a.n[k] + a.chunk - 1) / a.chunk);
     }
     if (a.count == 0) continue;
     a.block_start[a.count] = blocks;
@@ -164,11 +185,14 @@ int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_
       // beta as the double nearest to what the caller wrote (0.9f -> 0.9), like the reference
       const double b1 = strtod_round(beta1);
       const double b2 = strtod_round(beta2);
-      adam_multi_kernel<<<blocks, kThreads, 0, st>>>(a, alpha, b1, b2, eps);
+      adam_multi_kernel<<<blocks, kThreads, 0, st>>>(a, alpha, (float)b1, (float)b2,
+                                                     (float)log(b1), (float)log(b2), eps);
       SP_CHECK_LAUNCH("adam_multi");
     }
-    adam_advance_kernel<<<1, 32, 0, st>>>(a);
-    SP_CHECK_LAUNCH("adam_advance");
+    if (any_empty || blocks == 0) {
+      adam_advance_kernel<<<1, 32, 0, st>>>(a);
+      SP_CHECK_LAUNCH("adam_advance");
+    }
   }
   return 0;
 }

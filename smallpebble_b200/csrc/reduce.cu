@@ -18,6 +18,16 @@ float* scratch_for_current_device() {
   }
   return bufs[dev];
 }
+unsigned int* sync_words_for_current_device() {
+  static unsigned int* bufs[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!bufs[dev]) {
+    if (cudaMalloc(&bufs[dev], kSyncWords * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(bufs[dev], 0, kSyncWords * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+  }
+  return bufs[dev];
+}
 }  // namespace sp
 
 namespace {
@@ -267,25 +277,56 @@ __global__ void __launch_bounds__(kThreads) xent_bwd_kernel(const float* __restr
 }
 
 // fused softmax + cross entropy: one warp per row; per-block partial loss.
+// Rows are processed four at a time per warp with all their loads issued up front: at the
+// classifier sizes of the BASELINE models ([128,10], [200,10]) the kernel is one block whose
+// run time is the number of DEPENDENT global round trips, not bandwidth.
 __global__ void __launch_bounds__(1024) softmax_xent_fwd_kernel(
     const float* __restrict__ logits, const int32_t* __restrict__ labels,
     float* __restrict__ probs, float* __restrict__ part, int64_t rows, int64_t cols) {
   __shared__ float red[32];
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
+  const int64_t stride = (int64_t)gridDim.x * wpb;
   float nll = 0.f;  // accumulated by lane 0 of each warp
-  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows;
-       row += (int64_t)gridDim.x * wpb) {
-    const float* p = logits + row * cols;
-    float m = -INFINITY;
-    for (int64_t j = lane; j < cols; j += 32) m = fmaxf(m, p[j]);
-    m = warp_max(m);
-    float s = 0.f;
-    for (int64_t j = lane; j < cols; j += 32) s += expf(p[j] - m);
-    s = warp_sum(s);
-    const float inv = 1.f / s;
-    for (int64_t j = lane; j < cols; j += 32) probs[row * cols + j] = expf(p[j] - m) * inv;
-    if (lane == 0) nll += (logf(s) + m) - p[labels[row]];
+  int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5);
+  if (cols <= 32) {
+    constexpr int R = 4;
+    for (; row < rows; row += R * stride) {
+      float v[R];
+      int lab[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int64_t r = row + q * stride;
+        const bool ok = r < rows;
+        v[q] = (ok && lane < cols) ? logits[r * cols + lane] : -INFINITY;
+        lab[q] = (ok && lane == 0) ? labels[r] : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int64_t r = row + q * stride;
+        if (r >= rows) break;  // warp-uniform
+        const float m = warp_max(v[q]);
+        const float e = (lane < cols) ? expf(v[q] - m) : 0.f;
+        const float ssum = warp_sum(e);
+        if (lane < cols) probs[r * cols + lane] = e * (1.f / ssum);
+        const int l = __shfl_sync(0xffffffffu, lab[q], 0);
+        const float at = __shfl_sync(0xffffffffu, v[q], l & 31);
+        if (lane == 0) nll += (logf(ssum) + m) - at;
+      }
+    }
+  } else {
+    for (; row < rows; row += stride) {
+      const float* p = logits + row * cols;
+      float m = -INFINITY;
+      for (int64_t j = lane; j < cols; j += 32) m = fmaxf(m, p[j]);
+      m = warp_max(m);
+      float ssum = 0.f;
+      for (int64_t j = lane; j < cols; j += 32) ssum += expf(p[j] - m);
+      ssum = warp_sum(ssum);
+      const float inv = 1.f / ssum;
+      for (int64_t j = lane; j < cols; j += 32) probs[row * cols + j] = expf(p[j] - m) * inv;
+      if (lane == 0) nll += (logf(ssum) + m) - p[labels[row]];
+    }
   }
   nll = block_sum(nll, red);
   if (threadIdx.x == 0) part[blockIdx.x] = nll;
@@ -311,6 +352,28 @@ __global__ void __launch_bounds__(kThreads) sum_partials_kernel(const float* __r
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) out[0] = acc;
+}
+
+// Second pass of a split column sum when there are few columns: one WARP per output quad,
+// lanes stride over the partial rows (all loads independent), fixed-order shuffle tree.
+// The column kernel above would walk the partials with 8 row-lanes per block in a handful of
+// blocks -- a chain of dependent round trips (11.5 us for 296 x 256, ncu r01 v2).
+__global__ void __launch_bounds__(kThreads) colsum_final_vec4_kernel(const float* __restrict__ part,
+                                                                     float* __restrict__ out,
+                                                                     int64_t splits, int64_t inner) {
+  const int lane = threadIdx.x & 31;
+  const int64_t inner4 = inner >> 2;
+  const int64_t col4 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t o = blockIdx.z;
+  if (col4 >= inner4) return;
+  const float* p = part + (o * splits) * inner + 4 * col4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = lane; r < splits; r += 32) {
+    const float4 v = ld_stream_f4(p + r * inner);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  a.x = warp_sum(a.x); a.y = warp_sum(a.y); a.z = warp_sum(a.z); a.w = warp_sum(a.w);
+  if (lane == 0) reinterpret_cast<float4*>(out + o * inner)[col4] = a;
 }
 
 int reduce_sum_impl(const float* x, float* out, int64_t outer, int64_t reduce, int64_t inner,
@@ -367,8 +430,13 @@ int reduce_sum_impl(const float* x, float* out, int64_t outer, int64_t reduce, i
       float* part = scratch_for_current_device();
       if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_reduce_sum: no scratch");
       launch(x, part, reduce, chunk, splits, grid);
-      dim3 grid2((unsigned)col_blocks, 1, (unsigned)outer);
-      launch(part, out, splits, splits, 1, grid2);
+      if (vec && col_blocks * outer < sms && splits > 8) {
+        dim3 gridw((unsigned)((inner / 4 + kThreads / 32 - 1) / (kThreads / 32)), 1, (unsigned)outer);
+        colsum_final_vec4_kernel<<<gridw, kThreads, 0, st>>>(part, out, splits, inner);
+      } else {
+        dim3 grid2((unsigned)col_blocks, 1, (unsigned)outer);
+        launch(part, out, splits, splits, 1, grid2);
+      }
     }
   }
   return 0;

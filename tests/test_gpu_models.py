@@ -107,3 +107,24 @@ def test_vgg_small_one_step_vs_oracle(precision):
     assert_close(loss_val.array, loss0, LOSS_RTOL[precision], "loss")
     for i, (p, p0) in enumerate(zip(wl.learnables, model.params)):
         assert_grad_close(grads[p], grads0[p0], precision, f"gradient {i}")
+
+
+def test_pinned_host_batches_upload_without_a_host_pass():
+    """float64 / float32 batches that already live in page-locked memory are DMA'd as they are
+    and narrowed on the device (array.py from_host); values match the snapshot path."""
+    import torch
+
+    from smallpebble_b200.array import transfer_counters
+
+    rng = np.random.default_rng(4)
+    for dtype, tdtype in ((np.float64, torch.float64), (np.float32, torch.float32)):
+        pinned = torch.empty((64, 32, 32, 3), dtype=tdtype).pin_memory().numpy()
+        pinned[...] = rng.random(pinned.shape)
+        before = transfer_counters()["h2d_bytes"]
+        v = sp.Variable(pinned)
+        assert v.array._host is pinned  # no staging copy was made
+        got = np.asarray(sp.leaky_relu(v).array)
+        assert transfer_counters()["h2d_bytes"] - before == pinned.nbytes
+        assert np.array_equal(got, pinned.astype(np.float32))
+        pageable = np.array(pinned)
+        assert np.array_equal(np.asarray(sp.Variable(pageable).array), pinned.astype(np.float32))
