@@ -19,6 +19,9 @@ sys.path.insert(0, ROOT)
 
 FORCE_TMA2 = 1 << 5      # sp_debug_set_umma_policy: 2-SM kernel whenever supported
 NO_TMA2 = 2 << 5
+FORCE_HALO = 1 << 7      # halo-reuse variant whenever supported (stride-1 fprop / dgrad)
+NO_HALO = 2 << 7
+PROBE_POLICY = (FORCE_TMA2 | FORCE_HALO) if os.environ.get("SP_PROBE_HALO") == "1" else (FORCE_TMA2 | NO_HALO)
 
 #        name            x shape            w shape           strides  padding
 CASES = {
@@ -67,7 +70,7 @@ def run(case):
     from smallpebble_b200 import core
 
     sp.set_precision("tf32")
-    core.debug_set_kernel_policy(FORCE_TMA2)
+    core.debug_set_kernel_policy(PROBE_POLICY)
     xs, ws, strides, pad = CASES[case]
     rng = np.random.default_rng(1)
     x, w = rng.random(xs) - 0.5, rng.random(ws) - 0.5
@@ -141,7 +144,8 @@ def timing():
         x = sp.Variable(rng.random(xs, dtype=np.float32) - 0.5)
         w = sp.Variable(rng.random(ws, dtype=np.float32) - 0.5)
         res = {}
-        for label, pol in (("umma1", NO_TMA2 | 1), ("tma2", FORCE_TMA2)):
+        for label, pol in (("umma1", (FORCE_TMA2 | NO_HALO) if os.environ.get("SP_PROBE_HALO") == "1"
+                            else (NO_TMA2 | NO_HALO | 1)), ("tma2", PROBE_POLICY)):
             core.debug_set_kernel_policy(pol)
             y = sp.conv2d(x, w, pad, (1, 1))
             gy = DeviceArray.from_host(rng.random(y.shape, dtype=np.float32) - 0.5)

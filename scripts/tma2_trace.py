@@ -16,7 +16,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+POLICY = 32 + (128 if os.environ.get("SP_PROBE_HALO") == "1" else 256)
 CASES = {
+    "vgg_conv1b": ((256, 64, 64, 64), (3, 3, 64, 64), "SAME"),
+    "vgg_conv2b": ((256, 32, 32, 128), (3, 3, 128, 128), "SAME"),
     "cnn_conv2": ((128, 15, 15, 32), (3, 3, 32, 128), "VALID"),
     "cnn_conv3": ((128, 7, 7, 128), (3, 3, 128, 128), "VALID"),
     "vgg_conv3b": ((256, 16, 16, 256), (3, 3, 256, 256), "SAME"),
@@ -32,7 +35,7 @@ def main():
     from smallpebble_b200.array import DeviceArray
 
     sp.set_precision("tf32")
-    core.debug_set_kernel_policy(32)
+    core.debug_set_kernel_policy(POLICY)
     rng = np.random.default_rng(0)
     buf = torch.zeros(512, dtype=torch.int64, device="cuda")
     names = sys.argv[1:] or list(CASES)
@@ -70,6 +73,14 @@ def main():
             print("   A issue :", a[:40])
             print("   B issue :", b[:40])
             print("   landed  :", m[:40])
+            fine = t[352:352 + 90].reshape(30, 3)
+            if fine[:, 1].any():
+                print("   MMA thread per k-block (cycles): wait-done -> 4 MMAs issued -> commit issued:")
+                print("     ", [(int(m_ - l_), int(c_ - m_)) for l_, m_, c_ in
+                                 zip(t[16 + 2 * KB:16 + 2 * KB + 30], fine[:, 1], fine[:, 2]) if m_][:20])
+            strips = [rel(v) for v in t[320:352] if v]
+            if strips:
+                print("   strip landed (halo):", strips[:16])
             if len(m) > 8:
                 d = np.diff(m)
                 print(f"   landed cadence: median {int(np.median(d))} cyc, first {m[0]}, "

@@ -17,6 +17,8 @@ namespace {
 int g_umma_policy = 0;
 // 0 = policy (large problems), 1 = whenever supported (tests), 2 = never
 int g_tma2_policy = 0;
+// halo-reuse variant of the 2-SM kernel: 0 = policy, 1 = whenever supported, 2 = never
+int g_halo_policy = 0;
 
 // The 2-SM TMA kernel (74 persistent CTA pairs over 256-row tiles) beats the 1-SM cp.async
 // kernel on every eligible shape measured back to back (profiles/r01_tma2_vs_umma1_b2b.txt:
@@ -55,6 +57,17 @@ IgemmParams base_params() {
   p.batch = 1;
   p.k_splits = 1;
   return p;
+}
+
+// The halo-reuse variant moves 4-5x fewer activation bytes from L2 but, with one k-block per
+// pipeline step, is bound by the fixed per-step cost of its MMA-issuing thread (~490 cycles,
+// profiles/r01_halo_trace_v1_issue_bound.log) and measures slower than the im2col kernel with
+// 64-wide stages on every shape tried (profiles/r01_tma2_halo_b2b.txt).  It is correct and
+// tested, and stays opt-in (policy bit 7) until its stages carry two taps per step.
+bool use_halo(int mode, const IgemmParams& p, int precision) {
+  if (precision != SP_PRECISION_TF32 || g_umma_policy == 2 || g_halo_policy != 1) return false;
+  if (mode != kFprop && mode != kDgrad) return false;
+  return conv_halo2_supported(mode, p);
 }
 
 // Deterministic split of the wgrad reduction axis: enough CTAs for ~2 waves, k_chunk a
@@ -109,13 +122,16 @@ extern "C" {
 // undocumented test hook (declared in tests only): select the contraction kernel family
 int sp_debug_set_umma_policy(int policy) {
   // bits 0-1: kernel family policy; bit 4: conservative producer synchronisation;
-  // bits 5-6: 2-SM TMA conv kernel (0 = size policy, 1 = whenever supported, 2 = never)
+  // bits 5-6: 2-SM TMA conv kernel (0 = size policy, 1 = whenever supported, 2 = never);
+  // bits 7-8: its halo-reuse variant (same encoding)
   const int family = policy & 3;
   const int tma2 = (policy >> 5) & 3;
-  if (policy < 0 || family > 2 || tma2 > 2)
+  const int halo = (policy >> 7) & 3;
+  if (policy < 0 || family > 2 || tma2 > 2 || halo > 2)
     return sp::set_error(SP_ERR_INVALID_ARGUMENT, "policy in 0..2");
   sp::g_umma_policy = family;
   sp::g_tma2_policy = tma2;
+  sp::g_halo_policy = halo;
   sp::igemm_umma_set_sync_mode((policy >> 4) & 1);
   return 0;
 }
@@ -206,7 +222,8 @@ int sp_conv2d_fprop(const float* x, const float* w, float* y, const sp_conv_geom
     SP_CHECK_LAUNCH("conv2d_fprop(small C)");
     return 0;
   }
-  int rc = sp::use_tma2(sp::kFprop, p, precision)   ? sp::launch_conv_tma2(sp::kFprop, p, st)
+  int rc = sp::use_halo(sp::kFprop, p, precision)   ? sp::launch_conv_halo2(sp::kFprop, p, st)
+           : sp::use_tma2(sp::kFprop, p, precision) ? sp::launch_conv_tma2(sp::kFprop, p, st)
            : sp::use_umma(sp::kFprop, p, precision) ? sp::launch_igemm_umma(sp::kFprop, p, st)
                                                     : sp::launch_igemm_simt(sp::kFprop, p, st);
   if (rc) return rc;
@@ -229,7 +246,8 @@ int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_ge
   if (p.M == 0) return 0;
   if ((int64_t)g->OH * g->OW == 0) return sp_fill_f32(dx, p.M * p.N, 0.f, stream);
   cudaStream_t st = sp::as_stream(stream);
-  int rc = sp::use_tma2(sp::kDgrad, p, precision)   ? sp::launch_conv_tma2(sp::kDgrad, p, st)
+  int rc = sp::use_halo(sp::kDgrad, p, precision)   ? sp::launch_conv_halo2(sp::kDgrad, p, st)
+           : sp::use_tma2(sp::kDgrad, p, precision) ? sp::launch_conv_tma2(sp::kDgrad, p, st)
            : sp::use_umma(sp::kDgrad, p, precision) ? sp::launch_igemm_umma(sp::kDgrad, p, st)
                                                     : sp::launch_igemm_simt(sp::kDgrad, p, st);
   if (rc) return rc;

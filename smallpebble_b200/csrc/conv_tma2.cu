@@ -31,6 +31,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -86,6 +87,21 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Value of lane 0, which the compiler KNOWS to be warp-uniform.  The single-issuer roles below
+// run as warp-converged loops over uniform values and elect one lane only for the issue
+// itself: under a plain `if (lane == 0)` every UTMALDG / UTCHMMA was wrapped in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall (operands not provably uniform) and the MMA
+// thread needed ~84 cycles per tcgen05.mma and ~600 per k-block -- the real bound of the
+// first versions of these kernels (profiles/r01_halo_trace_v1_issue_bound.log).
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -173,6 +189,16 @@ __device__ __forceinline__ void tma_tile_3d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+__device__ __forceinline__ void tma_tile_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t slot_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
                "r"(ncols)
@@ -235,6 +261,20 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)layout_type << 61;
   return d;
 }
+// The same descriptor as two 32-bit halves: only the start-address field (low 14 bits, in
+// 16-byte units) changes between the MMAs of a k-block, so the issuing thread adds a constant
+// to the low word instead of rebuilding 64 bits (shared-memory addresses are < 256 KB: the
+// field cannot overflow into the LBO bits).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) {
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
 __device__ __forceinline__ uint32_t instr_desc_tf32_m256(int bn, bool a_mn, bool b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -281,13 +321,24 @@ __device__ __forceinline__ TileCoord tile_coord(const Tma2Params& p, int t) {
 // the first version of this kernel.
 constexpr int kAWarps = 4;
 constexpr int kWarpB = 4, kWarpMma = 5, kWarpTmem = 6, kWarpEpi0 = 8;
+// B producers: warps 4, 6 and 7 take the k-blocks round-robin (warp 6 allocates TMEM first).
+// A single producer warp needs ~360-390 cycles per loop iteration (TRYWAIT ~90 + a dependent
+// R2UR / issue chain) and paced the whole pipeline at one k-block per ~400 cycles.
+constexpr int kBWarps = 3;
+__device__ __forceinline__ int b_warp_slot(int warp) {  // 0..2 for the B warps, -1 otherwise
+  return warp == 4 ? 0 : warp == 6 ? 1 : warp == 7 ? 2 : -1;
+}
 
 template <int MODE>
 struct ModeCfg {
-  static constexpr int kKStage = (MODE == kWgrad) ? 64 : 32;        // k-values per stage
-  static constexpr uint32_t kABytes = 128u * kKStage * 4u;            // 16 / 32 KB
+  // 64 k-values per stage in every mode: the MMA-issuing thread pays ~350 cycles of fixed work
+  // per stage (TRYWAIT, register -> uniform-register moves, commits), so a stage carries 8 MMAs.
+  // fprop / dgrad: two 32-wide k-blocks ("halves") = two (tap, channel-block) im2col boxes.
+  static constexpr int kKStage = 64;
+  static constexpr uint32_t kABytes = 128u * kKStage * 4u;            // 32 KB
+  static constexpr uint32_t kHalfA = kABytes / 2;                     // one K-major 128 x 32 box
   static constexpr uint32_t kStage = 2u * kABytes;                    // A + B (<= A bytes)
-  static constexpr int kStages = (MODE == kWgrad) ? 3 : 6;
+  static constexpr int kStages = 3;
   static constexpr uint32_t kMnBlock = 128u * kKStage;                // bytes of one MN block
 };
 
@@ -304,8 +355,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   __shared__ uint32_t tmem_slot;
 
   const int t = threadIdx.x;
-  const int warp = t >> 5, lane = t & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int warp = (int)uniform((uint32_t)(t >> 5)), lane = t & 31;
+  const uint32_t rank = uniform(cluster_ctarank());
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
@@ -337,19 +388,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = uniform(tmem_slot);
   trace_at(p, tr && warp == 0, 1);
 
-  if (warp <= kWarpB) {
+  if (warp < kAWarps || b_warp_slot(warp) >= 0) {
     // =========================== TMA PRODUCERS (both CTAs) ================================
     // Every producer warp walks the same (tile, k-block, stage) sequence and issues only its
     // share; all of them wait on the stage's `empty` barrier before touching it.
-    if (lane == 0) {
-      const bool is_b = warp == kWarpB;
-      const uint32_t full0 = mapa(full_bar(0), 0);  // the leader's `full` barriers
+    {
+      const int bslot = b_warp_slot(warp);
+      const bool is_b = bslot >= 0;
+      const uint32_t full0 = uniform(mapa(full_bar(0), 0));  // the leader's `full` barriers
       int s = 0;
       uint32_t ph = 0;
-      int rr = 0;  // fprop / dgrad: k-block counter modulo kAWarps
+      int rrb = 0;  // stage counter modulo kBWarps
       int gkb = 0;
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
         const TileCoord tc = tile_coord(p, tile);
@@ -375,60 +427,90 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           cn = q / p.D1;
           ch = p.base_h + (q - cn * p.D1) * p.sy;
         }
-        int tap = 0, cb = 0;  // k-block -> (filter tap, 32-channel block)
-        for (int kb = 0; kb < tc.kblocks; ++kb) {
-          const bool mine = is_b || MODE == kWgrad || rr == warp;
-          if (mine) {
+        int tap = 0, cb = 0;  // (filter tap, 32-channel block) of half 0 of the stage
+        const int nst = (MODE == kWgrad) ? tc.kblocks : (tc.kblocks + 1) >> 1;
+        for (int st = 0; st < nst; ++st) {
+          // fprop / dgrad: the two halves of this stage
+          int tap1 = tap, cb1 = cb + 1;
+          if (cb1 == p.cblocks) {
+            cb1 = 0;
+            ++tap1;
+          }
+          const bool valid1 = MODE != kWgrad && (2 * st + 1) < tc.kblocks;
+          const uint32_t fb = full0 + 8u * s;
+          const uint32_t a_tile = tiles + (uint32_t)s * Cfg::kStage;
+          const uint32_t b_tile = a_tile + Cfg::kABytes;
+          if (is_b) {
+            if (rrb == bslot) {
+              mbar_wait(empty_bar(s), ph ^ 1u);
+              trace_at(p, tr && gkb < kTraceKb, 16 + kTraceKb + gkb);
+              if (elect_one()) {
+                if (MODE == kFprop) {
+                  // w as [32][KH*KW*C][Kout/32]: rows st*64 .. +64 (rows past the end read 0)
+                  tma_tile_3d(b_tile, &tmB, fb, 0, st * 64, nb0 >> 5);
+                } else if (MODE == kDgrad) {
+                  // w as [tap][c][ko]: rows = this CTA's input channels, 32 ko per half
+                  tma_tile_3d(b_tile, &tmB, fb, cb * 32, nb0, tap);
+                  if (valid1) tma_tile_3d(b_tile + (uint32_t)bnh * 128u, &tmB, fb, cb1 * 32, nb0, tap1);
+                } else {
+                  // gy as [32][N*OH*OW][Kout/32]
+                  tma_tile_3d(b_tile, &tmB, fb, 0, pix, nb0 >> 5);
+                }
+              }
+              __syncwarp();
+            }
+          } else if (MODE == kWgrad) {
             mbar_wait(empty_bar(s), ph ^ 1u);
-            trace_at(p, tr && gkb < kTraceKb && (is_b || warp == 0 || MODE != kWgrad),
-                     16 + (is_b ? kTraceKb : 0) + gkb);
-            const uint32_t fb = full0 + 8u * s;
-            const uint32_t a_tile = tiles + (uint32_t)s * Cfg::kStage;
-            const uint32_t b_tile = a_tile + Cfg::kABytes;
-            if (MODE == kFprop) {
-              if (is_b) {
-                // w as [32][KH*KW*C][Kout/32]: rows kb*32.. of this CTA's 32-wide MN blocks
-                tma_tile_3d(b_tile, &tmB, fb, 0, kb * 32, nb0 >> 5);
-              } else {
-                if (leader) mbar_arrive_expect_tx(full_bar(s), tx_bytes);
-                const int dy = tap / p.KW, dx = tap - dy * p.KW;
-                tma_im2col_4d(a_tile, &tmA, fb, cb * 32, cw, ch, cn, (uint16_t)dx, (uint16_t)dy);
-              }
-            } else if (MODE == kDgrad) {
-              if (is_b) {
-                // w as [tap][c][ko]: rows = this CTA's input channels, 32 ko
-                tma_tile_3d(b_tile, &tmB, fb, cb * 32, nb0, tap);
-              } else {
-                if (leader) mbar_arrive_expect_tx(full_bar(s), tx_bytes);
-                const int dy = tap / p.KW, dx = tap - dy * p.KW;
-                // gy pixel (iy + pad_t - dy, ix + pad_l - dx): base = lower corner, offset = K-1-d
-                tma_im2col_4d(a_tile, &tmA, fb, cb * 32, cw, ch, cn, (uint16_t)(p.KW - 1 - dx),
-                              (uint16_t)(p.KH - 1 - dy));
-              }
-            } else {
-              if (is_b) {
-                // gy as [32][N*OH*OW][Kout/32]
-                tma_tile_3d(b_tile, &tmB, fb, 0, pix, nb0 >> 5);
-              } else {
-                if (leader && warp == 0) mbar_arrive_expect_tx(full_bar(s), tx_bytes);
-                // this warp's 32 channels x 64 pixels -> MN block `warp` of the A tile
-                const int q = pix / p.D2;
-                const int ox = pix - q * p.D2;
-                const int n = q / p.D1;
-                const int oy = q - n * p.D1;
-                tma_im2col_4d(a_tile + (uint32_t)warp * Cfg::kMnBlock, &tmA, fb, wc,
-                              p.base_w + ox * p.sx, p.base_h + oy * p.sy, n, (uint16_t)wdx,
-                              (uint16_t)wdy);
+            trace_at(p, tr && warp == 0 && gkb < kTraceKb, 16 + gkb);
+            if (elect_one()) {
+              if (leader && warp == 0) mbar_arrive_expect_tx(full_bar(s), tx_bytes);
+              // this warp's 32 channels x 64 pixels -> MN block `warp` of the A tile
+              const int q = pix / p.D2;
+              const int ox = pix - q * p.D2;
+              const int n = q / p.D1;
+              const int oy = q - n * p.D1;
+              tma_im2col_4d(a_tile + (uint32_t)warp * Cfg::kMnBlock, &tmA, fb, wc,
+                            p.base_w + ox * p.sx, p.base_h + oy * p.sy, n, (uint16_t)wdx,
+                            (uint16_t)wdy);
+            }
+            __syncwarp();
+          } else {
+            // half h of stage st is k-block 2*st + h: A warps take the k-blocks round-robin
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if ((h == 0 || valid1) && ((2 * st + h) & (kAWarps - 1)) == warp) {
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                trace_at(p, tr && gkb < kTraceKb, 16 + gkb);
+                if (elect_one()) {
+                  if (leader && h == 0) {
+                    const uint32_t halves = valid1 ? 2u : 1u;
+                    const uint32_t b_bytes = MODE == kFprop ? (uint32_t)bnh * 256u
+                                                            : halves * (uint32_t)bnh * 128u;
+                    mbar_arrive_expect_tx(full_bar(s), 2u * (halves * Cfg::kHalfA + b_bytes));
+                  }
+                  const int tp = h ? tap1 : tap, c32 = h ? cb1 : cb;
+                  const int dy = tp / p.KW, dx = tp - dy * p.KW;
+                  if (MODE == kFprop)
+                    tma_im2col_4d(a_tile + (uint32_t)h * Cfg::kHalfA, &tmA, fb, c32 * 32, cw, ch, cn,
+                                  (uint16_t)dx, (uint16_t)dy);
+                  else  // gy pixel (iy + pad_t - dy, ix + pad_l - dx): lower corner + (K-1-d)
+                    tma_im2col_4d(a_tile + (uint32_t)h * Cfg::kHalfA, &tmA, fb, c32 * 32, cw, ch, cn,
+                                  (uint16_t)(p.KW - 1 - dx), (uint16_t)(p.KH - 1 - dy));
+                }
+                __syncwarp();
               }
             }
           }
           pix += Cfg::kKStage;
           ++gkb;
-          if (++cb == p.cblocks) {
+          // advance (tap, cb) by the two halves
+          tap = tap1;
+          cb = cb1 + 1;
+          if (cb == p.cblocks) {
             cb = 0;
             ++tap;
           }
-          if (++rr == kAWarps) rr = 0;
+          if (++rrb == kBWarps) rrb = 0;
           if (++s == kS) {
             s = 0;
             ph ^= 1u;
@@ -437,12 +519,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == kWarpMma) {
-    if (leader && lane == 0) {
-      // =========================== MMA ISSUER (leader CTA, one thread) ====================
+    if (leader) {
+      // =========================== MMA ISSUER (leader CTA, one elected lane) ==============
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
       int gkb = 0;
+      const uint32_t a_hi = A_MN ? desc_hi(512u, kLayoutSw128Base32) : desc_hi(1024u, kLayoutSw128);
+      const uint32_t b_hi = B_MN ? desc_hi(512u, kLayoutSw128Base32) : desc_hi(1024u, kLayoutSw128);
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
         const TileCoord tc = tile_coord(p, tile);
         const uint32_t idesc = instr_desc_tf32_m256(tc.bn, A_MN, B_MN);
@@ -450,32 +534,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         mbar_wait(tmem_empty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccumCols);
-        for (int kb = 0; kb < tc.kblocks; ++kb) {
+        const int nst = (MODE == kWgrad) ? tc.kblocks : (tc.kblocks + 1) >> 1;
+        const uint32_t bnh_bytes = (uint32_t)(tc.bn >> 1) * 128u;
+        for (int st = 0; st < nst; ++st) {
           mbar_wait(full_bar(s), ph);
           trace_at(p, tr && gkb < kTraceKb, 16 + 2 * kTraceKb + gkb);
           ++gkb;
           tc_fence_after();
           const uint32_t a_tile = tiles + (uint32_t)s * Cfg::kStage;
           const uint32_t b_tile = a_tile + Cfg::kABytes;
+          const bool valid1 = MODE == kWgrad || (2 * st + 1) < tc.kblocks;
+          if (elect_one()) {
+            // one MMA consumes 8 k-values.  K-major: +32 B inside the 128-B swizzled rows of a
+            // half; MN-major: 8 k-rows of 128 B = +1024 B, MN blocks kMnBlock bytes apart
+            const uint32_t a_lo = A_MN ? desc_lo(a_tile, Cfg::kMnBlock) : desc_lo(a_tile, 16u);
+            const uint32_t b_lo = B_MN ? desc_lo(b_tile, Cfg::kMnBlock) : desc_lo(b_tile, 16u);
+            // second half: A K-major -> next 16 KB box; B K-major -> next bnh rows
+            const uint32_t a_half = A_MN ? 4u * (1024u >> 4) : (Cfg::kHalfA >> 4);
+            const uint32_t b_half = B_MN ? 4u * (1024u >> 4) : (bnh_bytes >> 4);
+            constexpr uint32_t a_step = A_MN ? (1024u >> 4) : (32u >> 4);
+            constexpr uint32_t b_step = B_MN ? (1024u >> 4) : (32u >> 4);
 #pragma unroll
-          for (int k = 0; k < Cfg::kKStage / 8; ++k) {
-            // one MMA consumes 8 k-values.  K-major: +32 B inside the 128-B swizzled rows;
-            // MN-major: 8 k-rows of 128 B = +1024 B, MN blocks kMnBlock bytes apart
-            const uint64_t adesc =
-                A_MN ? smem_desc(a_tile + (uint32_t)k * 1024u, Cfg::kMnBlock, 512u, kLayoutSw128Base32)
-                     : smem_desc(a_tile + (uint32_t)k * 32u, 16u, 1024u, kLayoutSw128);
-            const uint64_t bdesc =
-                B_MN ? smem_desc(b_tile + (uint32_t)k * 1024u, Cfg::kMnBlock, 512u, kLayoutSw128Base32)
-                     : smem_desc(b_tile + (uint32_t)k * 32u, 16u, 1024u, kLayoutSw128);
-            umma_tf32_2sm(tmem_d, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_2sm(tmem_d, desc_join(a_lo + (uint32_t)k * a_step, a_hi),
+                            desc_join(b_lo + (uint32_t)k * b_step, b_hi), idesc,
+                            (st > 0 || k > 0) ? 1u : 0u);
+            if (valid1) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_tf32_2sm(tmem_d, desc_join(a_lo + a_half + (uint32_t)k * a_step, a_hi),
+                              desc_join(b_lo + b_half + (uint32_t)k * b_step, b_hi), idesc, 1u);
+            }
+            umma_commit_2sm(empty_bar(s));  // both CTAs' producers may refill stage s
+            if (st == nst - 1)
+              umma_commit_2sm(tmem_full_bar(acc));  // both CTAs' epilogues may drain stage acc
           }
-          umma_commit_2sm(empty_bar(s));  // both CTAs' producers may refill stage s
+          __syncwarp();
           if (++s == kS) {
             s = 0;
             ph ^= 1u;
           }
         }
-        umma_commit_2sm(tmem_full_bar(acc));  // both CTAs' epilogues may drain stage acc
         trace_at(p, tr && it < 4, 2 + it);
       }
     }
@@ -526,6 +625,326 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();
   if (warp == kWarpTmem) tmem_dealloc_2sm(tmem_base, 512);
   trace_at(p, tr && warp == 0, 14);
+}
+
+
+// =======================================================================================
+// Halo-reuse variant (stride-1 fprop / dgrad): the im2col matrix repeats every input pixel
+// KH*KW times, and the TMA unit -- not the tensor pipe -- paces the kernel above (one
+// 128-byte row per ~4 cycles per SM).  Here each CTA stages ONE strip of input pixels per
+// 32-channel block and reads all KH*KW taps out of it:
+//
+//   * pixels are numbered in PADDED-LINEAR order q = (n * Hv + yv) * Wv + xv over a virtual
+//     grid of Hv = OH + KH - 1 rows and Wv = OW + KW - 1 columns per image (the zero halo is part
+//     of the grid).  Output pixel q reads input pixels q + dy * Wv + dx: a CONSTANT row shift
+//     per tap, for every pixel of a tile of 128 consecutive q (columns >= OW and rows >= OH of
+//     the virtual grid are computed and thrown away: (OH*OW)/(Hv*Wv) of the MMAs are useful);
+//   * the strip [q0, q0 + 128 + (KH-1)*Wv + KW-1) is fetched as whole virtual rows: one tiled
+//     TMA box {32 channels, Wv pixels} per row at coordinates (c0, -pad_l, yv - pad_t, n) --
+//     out-of-range coordinates zero-fill, which IS the padding; each box lands at a
+//     128-byte-aligned row of the strip (SWIZZLE_128B keys on absolute smem address bits:
+//     scripts/probe_rowshift.cu, profiles/r01_probe_umma_rowshift.log);
+//   * the A descriptor of tap (dy, dx) is the strip's address + (L + dy*Wv + dx) rows with
+//     base_offset 0 (same probe): no data is moved or duplicated per tap.
+//   3x3 on 32x32 images: 238 strip rows instead of 9 x 128 im2col rows per channel block.
+// Pipeline: a 2-stage strip ring + a ring of per-tap B tiles; everything else (2-SM pairs,
+// persistent tiles, two TMEM accumulator stages, warp roles) as in conv_tma2_kernel.
+// =======================================================================================
+struct HaloParams {
+  int mode;            // kFprop / kDgrad
+  int N_img;           // images
+  int OHo, OWo;        // output grid: (OH, OW) fprop, (H, W) dgrad
+  int Hv, Wv;          // virtual (padded) grid per image
+  int pad_t, pad_l;    // of the virtual grid w.r.t. the A tensor: (pad) fprop, (K-1-pad) dgrad
+  int KH, KW;
+  int N;               // GEMM columns: Kout (fprop), C (dgrad)
+  int n_tiles, m_pairs, total_tiles;
+  int cblocks;         // 32-channel blocks of the A tensor
+  int L;               // lead-in rows of a strip stage (= Wv)
+  uint32_t strip_bytes;  // one strip stage
+  uint32_t b_bytes;      // one B stage (BN/2 rows or columns x 128 B)
+  int b_stages;
+  long long* trace;    // sp_debug_tma2_trace (cluster 0, leader CTA), or null
+  float* C;
+  int64_t ldc;
+};
+
+constexpr int kMaxBStages = 8;
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ HaloParams p) {
+  constexpr bool B_MN = (MODE == kFprop);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[4 + 2 * kMaxBStages + 4];
+  __shared__ uint32_t tmem_slot;
+
+  const int t = threadIdx.x;
+  const int warp = (int)uniform((uint32_t)(t >> 5)), lane = t & 31;
+  const uint32_t rank = uniform(cluster_ctarank());
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int T = p.KH * p.KW;
+  const int SB = p.b_stages;
+  const bool tr = p.trace != nullptr && cluster_id == 0 && leader && lane == 0;
+  auto stamp = [&](bool on, int slot) {
+    if (on) p.trace[slot] = clock64();
+  };
+  stamp(tr && warp == 0, 0);
+
+  const uint32_t strips = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_ring = strips + 2u * p.strip_bytes;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (4 + kMaxBStages + s); };
+  auto tmem_full_bar = [&](int a) { return bar0 + 8u * (4 + 2 * kMaxBStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bar0 + 8u * (6 + 2 * kMaxBStages + a); };
+
+  if (t == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) prefetch_tmap(&tmA);
+  if (warp == kWarpB && lane == 0) prefetch_tmap(&tmB);
+  if (warp == kWarpTmem) tmem_alloc_2sm(smem_u32(&tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform(tmem_slot);
+
+  stamp(tr && warp == 0, 1);
+  // rows this CTA's strip needs for the pair tile that starts at pixel q0
+  auto strip_rows = [&](int q0, uint32_t r, int& first_row, int& lead) {
+    const int pc = q0 + 128 * (int)r;
+    first_row = pc / p.Wv;
+    lead = pc - first_row * p.Wv;
+    const int last = (pc + 127 + (p.KH - 1) * p.Wv + (p.KW - 1)) / p.Wv;
+    return last - first_row + 1;
+  };
+
+  if (warp < kAWarps) {
+    // =========================== A PRODUCERS: strip rows ==================================
+    {
+      const uint32_t afull0 = uniform(mapa(a_full(0), 0));
+      int as = 0;
+      uint32_t aph = 0;
+      int gi = 0;
+      for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+        const int m_pair = tile % p.m_pairs;
+        const int q0 = m_pair * 256;
+        int row0, lead;
+        const int nbox = strip_rows(q0, rank, row0, lead);
+        uint32_t tx = 0;
+        if (leader && warp == 0) {
+          int r1, l1;
+          tx = (uint32_t)(nbox + strip_rows(q0, 1, r1, l1)) * (uint32_t)p.Wv * 128u;
+        }
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          mbar_wait(a_empty(as), aph ^ 1u);
+          const uint32_t fb = afull0 + 8u * as;
+          const uint32_t dst0 = strips + (uint32_t)as * p.strip_bytes + (uint32_t)(p.L - lead) * 128u;
+          stamp(tr && warp == 0 && gi < kTraceKb, 16 + gi);
+          ++gi;
+          if (elect_one()) {
+            if (leader && warp == 0) mbar_arrive_expect_tx(a_full(as), tx);
+            for (int i = warp; i < nbox; i += kAWarps) {
+              const int r = row0 + i;
+              const int n = r / p.Hv;
+              const int yv = r - n * p.Hv;
+              tma_tile_4d(dst0 + (uint32_t)(i * p.Wv) * 128u, &tmA, fb, cb * 32, -p.pad_l,
+                          yv - p.pad_t, n);
+            }
+          }
+          __syncwarp();
+          as ^= 1;
+          if (as == 0) aph ^= 1u;
+        }
+      }
+    }
+  } else if (b_warp_slot(warp) >= 0) {
+    // =========================== B PRODUCERS: one tile per (channel block, tap) ===========
+    {
+      const int bslot = b_warp_slot(warp);
+      const uint32_t bfull0 = uniform(mapa(b_full(0), 0));
+      int bs = 0;
+      uint32_t bph = 0;
+      int gkb = 0;
+      int rrb = 0;
+      for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+        const int n_tile = tile / p.m_pairs;
+        const int n0 = n_tile * 256;
+        const int bn = min(256, p.N - n0);
+        const int bnh = bn >> 1;
+        const int nb0 = n0 + (int)rank * bnh;
+        const uint32_t tx = 2u * (uint32_t)bnh * 128u;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          for (int tap = 0; tap < T; ++tap) {
+            const bool mine = rrb == bslot;
+            if (++rrb == kBWarps) rrb = 0;
+            if (mine) {
+            mbar_wait(b_empty(bs), bph ^ 1u);
+            stamp(tr && gkb < kTraceKb, 16 + kTraceKb + gkb);
+            const uint32_t fb = bfull0 + 8u * bs;
+            const uint32_t dst = b_ring + (uint32_t)bs * p.b_bytes;
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(b_full(bs), tx);
+              if (MODE == kFprop) {
+                // w as [32][KH*KW*C][Kout/32]: rows (tap*C + cb*32) .. +32
+                tma_tile_3d(dst, &tmB, fb, 0, (tap * p.cblocks + cb) * 32, nb0 >> 5);
+              } else {
+                // virtual tap (dy', dx') of the flipped filter = weight tap (KH-1-dy', KW-1-dx')
+                tma_tile_3d(dst, &tmB, fb, cb * 32, nb0, T - 1 - tap);
+              }
+            }
+            __syncwarp();
+            }  // mine
+            ++gkb;
+            if (++bs == SB) {
+              bs = 0;
+              bph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    if (leader) {
+      // =========================== MMA ISSUER (one elected lane issues) =====================
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      int gkb = 0, gcb = 0;
+      const uint32_t a_hi = desc_hi(1024u, kLayoutSw128);
+      const uint32_t b_hi = B_MN ? desc_hi(512u, kLayoutSw128Base32) : desc_hi(1024u, kLayoutSw128);
+      for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
+        const int n_tile = tile / p.m_pairs;
+        const int bn = min(256, p.N - n_tile * 256);
+        const uint32_t idesc = instr_desc_tf32_m256(bn, false, B_MN);
+        const int acc = it & 1;
+        mbar_wait(tmem_empty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccumCols);
+        uint32_t first = 0;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          mbar_wait(a_full(as), aph);
+          stamp(tr && gcb < 32, 320 + gcb);
+          ++gcb;
+          tc_fence_after();
+          const uint32_t strip = strips + (uint32_t)as * p.strip_bytes + (uint32_t)p.L * 128u;
+          int dy = 0, dx = 0;
+          for (int tap = 0; tap < T; ++tap) {
+            mbar_wait(b_full(bs), bph);
+            stamp(tr && gkb < kTraceKb, 16 + 2 * kTraceKb + gkb);
+            ++gkb;
+            tc_fence_after();
+            const uint32_t a_view = strip + (uint32_t)(dy * p.Wv + dx) * 128u;
+            const uint32_t b_tile = b_ring + (uint32_t)bs * p.b_bytes;
+            const bool last_tap = tap == T - 1;
+            const bool last_kb = last_tap && cb == p.cblocks - 1;
+            if (elect_one()) {
+            const uint32_t a_lo = desc_lo(a_view, 16u);
+            const uint32_t b_lo = B_MN ? desc_lo(b_tile, 4096u) : desc_lo(b_tile, 16u);
+            constexpr uint32_t b_step = B_MN ? (1024u >> 4) : (32u >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_tf32_2sm(tmem_d, desc_join(a_lo + (uint32_t)k * 2u, a_hi),
+                            desc_join(b_lo + (uint32_t)k * b_step, b_hi), idesc,
+                            (first | (uint32_t)k) ? 1u : 0u);
+            }
+            if (p.trace != nullptr && cluster_id == 0 && gkb <= 30)
+              p.trace[352 + 3 * (gkb - 1) + 1] = clock64();
+            umma_commit_2sm(b_empty(bs));
+            if (last_tap) umma_commit_2sm(a_empty(as));  // every tap of this strip was issued
+            if (last_kb) umma_commit_2sm(tmem_full_bar(acc));
+            }  // elect_one
+            __syncwarp();
+            first = 1u;
+            stamp(tr && gkb <= 30, 352 + 3 * (gkb - 1) + 2);
+            if (++bs == SB) {
+              bs = 0;
+              bph ^= 1u;
+            }
+            if (++dx == p.KW) {
+              dx = 0;
+              ++dy;
+            }
+          }
+          as ^= 1;
+          if (as == 0) aph ^= 1u;
+        }
+        stamp(tr && it < 4, 2 + it);
+      }
+    }
+  } else if (warp >= kWarpEpi0) {
+    // =========================== EPILOGUE ===================================================
+    const int quad = warp & 3;
+    const uint32_t empty_leader0 = mapa(tmem_empty_bar(0), 0);
+    const bool vec_store = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    int it = 0;
+    for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
+      const int m_pair = tile % p.m_pairs;
+      const int n_tile = tile / p.m_pairs;
+      const int n0 = n_tile * 256;
+      const int bn = min(256, p.N - n0);
+      const int acc = it & 1;
+      mbar_wait(tmem_full_bar(acc), ((uint32_t)it >> 1) & 1u);
+      stamp(tr && warp == kWarpEpi0 && it < 4, 6 + it);
+      tc_fence_after();
+      // this thread's row: virtual pixel q -> (image, yv, xv); rows of the halo are dropped
+      const int q = m_pair * 256 + (int)rank * 128 + quad * 32 + lane;
+      const int r = q / p.Wv;
+      const int xv = q - r * p.Wv;
+      const int n = r / p.Hv;
+      const int yv = r - n * p.Hv;
+      const bool valid = n < p.N_img && yv < p.OHo && xv < p.OWo;
+      float* __restrict__ crow =
+          p.C + ((int64_t)(n * p.OHo + yv) * p.OWo + xv) * p.ldc + n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccumCols);
+      for (int cb = 0; cb < bn; cb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
+        tmem_ld_wait();
+        if (valid) {
+          if (vec_store) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(crow + cb + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) crow[cb + j] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(empty_leader0 + 8u * acc);
+      stamp(tr && warp == kWarpEpi0 && it < 4, 10 + it);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kWarpTmem) tmem_dealloc_2sm(tmem_base, 512);
+  stamp(tr && warp == 0, 14);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -746,8 +1165,8 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
       return encode_im2col(m, ip.A, g.N, g.H, g.W, g.C, -g.pad_l, -g.pad_t, up_w, up_h, g.sx, g.sy,
                            128, CU_TENSOR_MAP_SWIZZLE_128B);
     });
-    ok = ok && cached_map(ip.B, 1, g, bnh_max, &tmB, [&](CUtensorMap* m) {
-      return encode_mn_blocks(m, ip.B, (int64_t)g.KH * g.KW * g.C, g.K, 32, bnh_max / 32);
+    ok = ok && cached_map(ip.B, 8, g, bnh_max, &tmB, [&](CUtensorMap* m) {
+      return encode_mn_blocks(m, ip.B, (int64_t)g.KH * g.KW * g.C, g.K, 64, bnh_max / 32);
     });
   } else if (mode == kDgrad) {
     p.cblocks = g.K / 32;
@@ -814,6 +1233,149 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
   else
     SP_TMA2_LAUNCH(kWgrad);
 #undef SP_TMA2_LAUNCH
+  return 0;
+}
+
+// ---- halo-reuse variant: eligibility, shared-memory plan, launch ---------------------------
+namespace {
+struct HaloPlan {
+  int Hv, Wv, OHo, OWo, pad_t, pad_l, L, b_stages;
+  uint32_t strip_bytes, b_bytes;
+  size_t smem;
+  bool ok;
+};
+
+HaloPlan halo_plan(int mode, const sp_conv_geom& g, int N) {
+  HaloPlan h;
+  memset(&h, 0, sizeof(h));
+  if (mode == kFprop) {
+    h.OHo = g.OH;
+    h.OWo = g.OW;
+    h.pad_t = g.pad_t;
+    h.pad_l = g.pad_l;
+  } else {
+    h.OHo = g.H;
+    h.OWo = g.W;
+    h.pad_t = g.KH - 1 - g.pad_t;
+    h.pad_l = g.KW - 1 - g.pad_l;
+  }
+  h.Hv = h.OHo + g.KH - 1;
+  h.Wv = h.OWo + g.KW - 1;
+  h.L = h.Wv;
+  const int rows = h.L + 128 + g.KH * h.Wv + g.KW;
+  h.strip_bytes = ((uint32_t)rows * 128u + 1023u) & ~1023u;  // B ring stays 1024-B aligned
+  const int bn = N >= 256 ? 256 : N;
+  h.b_bytes = (uint32_t)(bn / 2) * 128u;
+  const size_t budget = 200 * 1024;
+  if (2 * (size_t)h.strip_bytes + 3 * (size_t)h.b_bytes > budget || h.Wv > 256 || h.pad_t < 0 ||
+      h.pad_l < 0) {
+    h.ok = false;
+    return h;
+  }
+  size_t nb = (budget - 2 * (size_t)h.strip_bytes) / h.b_bytes;
+  h.b_stages = (int)std::min<size_t>(nb, kMaxBStages);
+  h.smem = 1024 + 2 * (size_t)h.strip_bytes + (size_t)h.b_stages * h.b_bytes;
+  h.ok = true;
+  return h;
+}
+}  // namespace
+
+bool conv_halo2_supported(int mode, const IgemmParams& p) {
+  const sp_conv_geom& g = p.g;
+  if (mode != kFprop && mode != kDgrad) return false;
+  if (!conv_tma2_supported(mode, p)) return false;
+  if (g.sy != 1 || g.sx != 1) return false;
+  const int N = mode == kFprop ? g.K : g.C;
+  const HaloPlan h = halo_plan(mode, g, N);
+  if (!h.ok) return false;
+  // padded-linear pixel indices are 32-bit
+  return (int64_t)g.N * h.Hv * h.Wv < 0x7fffff00LL;
+}
+
+// fraction of the MMA rows that are real output pixels
+double conv_halo2_efficiency(int mode, const IgemmParams& p) {
+  const sp_conv_geom& g = p.g;
+  const HaloPlan h = halo_plan(mode, g, mode == kFprop ? g.K : g.C);
+  return h.ok ? ((double)h.OHo * h.OWo) / ((double)h.Hv * h.Wv) : 0.0;
+}
+
+int launch_conv_halo2(int mode, const IgemmParams& ip, cudaStream_t st) {
+  if (!conv_halo2_supported(mode, ip))
+    return set_error(SP_ERR_UNSUPPORTED, "conv_halo2: unsupported problem");
+  const sp_conv_geom& g = ip.g;
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = mode;
+  p.N = (int)ip.N;
+  const HaloPlan h = halo_plan(mode, g, p.N);
+  p.N_img = g.N;
+  p.OHo = h.OHo;
+  p.OWo = h.OWo;
+  p.Hv = h.Hv;
+  p.Wv = h.Wv;
+  p.pad_t = h.pad_t;
+  p.pad_l = h.pad_l;
+  p.KH = g.KH;
+  p.KW = g.KW;
+  p.L = h.L;
+  p.strip_bytes = h.strip_bytes;
+  p.b_bytes = h.b_bytes;
+  p.b_stages = h.b_stages;
+  p.n_tiles = (p.N + 255) / 256;
+  const int64_t Q = (int64_t)g.N * h.Hv * h.Wv;
+  p.m_pairs = (int)((Q + 255) / 256);
+  p.total_tiles = p.m_pairs * p.n_tiles;
+  p.C = ip.C;
+  p.ldc = ip.ldc;
+  p.trace = g_trace;
+  const int bnh_max = (p.N >= 256 ? 256 : p.N) / 2;
+  alignas(64) CUtensorMap tmA, tmB;
+  bool ok = true;
+  if (mode == kFprop) {
+    p.cblocks = g.C / 32;
+    // activation as a plain tiled 4-D tensor (C, W, H, N): one box = one virtual row
+    ok = cached_map(ip.A, 6, g, h.Wv, &tmA, [&](CUtensorMap* m) {
+      const cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+      const cuuint32_t box[4] = {32, (cuuint32_t)h.Wv, 1, 1};
+      return encode_tiled(m, ip.A, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    });
+    ok = ok && cached_map(ip.B, 1, g, bnh_max, &tmB, [&](CUtensorMap* m) {
+      return encode_mn_blocks(m, ip.B, (int64_t)g.KH * g.KW * g.C, g.K, 32, bnh_max / 32);
+    });
+  } else {
+    p.cblocks = g.K / 32;
+    ok = cached_map(ip.A, 7, g, h.Wv, &tmA, [&](CUtensorMap* m) {
+      const cuuint64_t dims[4] = {(cuuint64_t)g.K, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
+      const cuuint32_t box[4] = {32, (cuuint32_t)h.Wv, 1, 1};
+      return encode_tiled(m, ip.A, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    });
+    ok = ok && cached_map(ip.B, 3, g, bnh_max, &tmB, [&](CUtensorMap* m) {
+      const cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.C, (cuuint64_t)g.KH * g.KW};
+      const cuuint32_t box[3] = {32, (cuuint32_t)bnh_max, 1};
+      return encode_tiled(m, ip.B, 3, dims, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    });
+  }
+  if (!ok) return set_error(SP_ERR_UNSUPPORTED, "conv_halo2: cuTensorMapEncode failed");
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int clusters = std::min(p.total_tiles, sms / 2);
+  dim3 grid((unsigned)(2 * clusters));
+  static bool attr_done[2] = {false, false};
+  const int which = mode == kFprop ? 0 : 1;
+  if (!attr_done[which]) {
+    cudaError_t e =
+        mode == kFprop
+            ? cudaFuncSetAttribute(conv_halo2_kernel<kFprop>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024)
+            : cudaFuncSetAttribute(conv_halo2_kernel<kDgrad>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
+    if (e != cudaSuccess)
+      return set_error((int)e, "cudaFuncSetAttribute(conv_halo2) failed: %s", cudaGetErrorString(e));
+    attr_done[which] = true;
+  }
+  if (mode == kFprop)
+    conv_halo2_kernel<kFprop><<<grid, kThreads, h.smem, st>>>(tmA, tmB, p);
+  else
+    conv_halo2_kernel<kDgrad><<<grid, kThreads, h.smem, st>>>(tmA, tmB, p);
   return 0;
 }
 

@@ -50,6 +50,11 @@ void igemm_umma_set_sync_mode(int mode);
 // 2-SM (cta_group::2) TMA-fed tcgen05 conv kernels, conv_tma2.cu: channel counts % 32 == 0
 bool conv_tma2_supported(int mode, const IgemmParams& p);
 int launch_conv_tma2(int mode, const IgemmParams& p, cudaStream_t stream);
+// halo-reuse variant of the 2-SM kernel (stride-1 fprop / dgrad): every input pixel is staged
+// once per tile and the filter taps are row-shifted descriptor views of that strip
+bool conv_halo2_supported(int mode, const IgemmParams& p);
+double conv_halo2_efficiency(int mode, const IgemmParams& p);
+int launch_conv_halo2(int mode, const IgemmParams& p, cudaStream_t stream);
 // bring-up: cluster 0 writes clock64 stamps into `device_buffer` (>= 512 int64), null = off
 void conv_tma2_set_trace(long long* device_buffer);
 

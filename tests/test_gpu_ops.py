@@ -24,8 +24,10 @@ def grads_of(fn, arrays, gy):
 
 # sp_debug_set_umma_policy: bits 0-1 kernel family, bits 5-6 the 2-SM TMA conv kernels
 # (32 = whenever the geometry is eligible, 64 = never)
-@pytest.fixture(params=[0, 1, 2, 32, 1 + 64], ids=["policy", "force_umma", "force_simt",
-                                                   "force_tma2", "umma_no_tma2"])
+# bits 7-8: the halo-reuse variant of the 2-SM kernels (128 = whenever eligible)
+@pytest.fixture(params=[0, 1, 2, 32, 1 + 64, 32 + 128],
+                ids=["policy", "force_umma", "force_simt", "force_tma2", "umma_no_tma2",
+                     "force_halo"])
 def umma_policy(request):
     core.debug_set_kernel_policy(request.param)
     yield request.param

@@ -78,10 +78,12 @@ def test_tensor_core_kernel_agrees_with_fp32_kernel(cfg):
 TMA2_CONFIGS = [CONFIGS[1], CONFIGS[2], CONFIGS[3], CONFIGS[4], CONFIGS[6]]
 
 
+@pytest.mark.parametrize("policy", [32, 32 + 128], ids=["im2col", "halo"])
 @pytest.mark.parametrize("cfg", TMA2_CONFIGS, ids=[c[0] for c in TMA2_CONFIGS])
-def test_tma2_kernel_agrees_with_fp32_kernel(cfg):
-    """The 2-SM TMA kernels (forced, policy bit 5) against the CUDA-core fp32 kernels at full
-    BASELINE sizes -- including the strided k5 case whose dgrad stays on the 1-SM kernel."""
+def test_tma2_kernel_agrees_with_fp32_kernel(cfg, policy):
+    """The 2-SM TMA kernels (forced: policy bit 5, halo-reuse variant: + bit 7) against the
+    CUDA-core fp32 kernels at full BASELINE sizes -- including the strided k5 case whose dgrad
+    stays on the 1-SM kernel."""
     name, xs, ws, strides, pad = cfg
     rng = np.random.default_rng(13)
     x, w = rng.random(xs) - 0.5, rng.random(ws) - 0.5
@@ -97,7 +99,7 @@ def test_tma2_kernel_agrees_with_fp32_kernel(cfg):
 
     old = sp.get_precision()
     try:
-        core.debug_set_kernel_policy(32)
+        core.debug_set_kernel_policy(policy)
         tf, gy = run("tf32")
         tf_again, _ = run("tf32", gy)
         core.debug_set_kernel_policy(0)
