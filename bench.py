@@ -378,9 +378,30 @@ def run_ours(args):
                     "copied into static buffers inside the timed region",
         }
 
+    def finish():
+        """Multi-rank exit.  The captured CUDA graph holds the NCCL all-reduce: release it before
+        the communicator goes away (destroying the process group under a live graph hung both
+        ranks for minutes on this stack), then leave through a barrier and a hard exit so that
+        no interpreter-teardown ordering between torch, NCCL and our library can stall torchrun."""
+        if world == 1:
+            return
+        import gc
+
+        nonlocal_refs.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+    nonlocal_refs = [graph_stats]
+    if not args.no_graph:
+        gstep._graphs.clear()
+        del gstep
+
     if rank != 0:
-        if world > 1:
-            sp.distributed.shutdown()
+        finish()
         return
 
     # ---- roofline of the dominant kernel ----------------------------------------------------
@@ -453,8 +474,7 @@ def run_ours(args):
         "cuda_graph": graph_stats,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        sp.distributed.shutdown()
+    finish()
 
 
 def main():
