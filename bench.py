@@ -160,6 +160,11 @@ def algorithmic_work(name, args):
         flops = 2.0 * g.N * g.OH * g.OW * g.K * g.KH * g.KW * g.C
         desc = (f"{name[3:]} N={g.N} HxW={g.H}x{g.W} C={g.C} K={g.K} k={g.KH}x{g.KW} "
                 f"s={g.sy}x{g.sx}")
+        if g.C <= 4:
+            # RGB first layer: 0.2 GFLOP against 16 MB -- exact-fp32 CUDA-core kernels whose
+            # roofline is memory, not the tensor pipe
+            nbytes = 4.0 * (g.N * g.H * g.W * g.C + g.N * g.OH * g.OW * g.K + g.KH * g.KW * g.C * g.K)
+            return "hbm", nbytes, desc + " (first layer, CUDA cores)"
         return "tensor", flops, desc
     if name == "sp_gemm":
         m, n, k, batch = args[2], args[3], args[4], args[14]
@@ -210,6 +215,7 @@ def run_ours(args):
         import torch.distributed as dist
     sp.set_precision(args.precision)
     _abi.load(build_if_missing=False)
+    peaks_early = load_peaks()
 
     global_batch = BATCH_PER_GPU * world
     x_global, y_global = workloads.synthetic_batch("cnn", global_batch)
@@ -405,7 +411,7 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel ----------------------------------------------------
-    peaks = load_peaks()
+    peaks = peaks_early
     roofline = None
     if top is not None and top_records:
         kind, work, desc = algorithmic_work(top_records[0][0], top_records[0][2])
@@ -427,13 +433,67 @@ def run_ours(args):
             achieved = work / (avg_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak}
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+                for prefix, row in json.load(fh).items():
+                    if desc.startswith(prefix):
+                        traffic = row["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            traffic = None
         roofline.update({
-            "traffic": None, "kernel": desc, "avg_launch_ms": avg_ms, "launches_timed": len(durs),
+            "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
+            "ncu --set full capture of this kernel at this shape (profiles/r01_ncu_traffic.json); "
+            "null when the dominant kernel has no capture", "kernel": desc, "avg_launch_ms": avg_ms, "launches_timed": len(durs),
             "algorithmic_work_per_launch": work, "peak_source": peak_note,
             "share_of_step": avg_ms / ms_per_step,
             "note": "CUDA events around the ABI call on the launch stream inside the timed "
                     "region; includes ~2-4 us of event overhead",
         })
+
+    # ---- the other BASELINE configs, briefly (N=1 only): MNIST MLP and the VGG-style net ------
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = {}
+        for key, kind, batch, steps in (("mnist_mlp_784-100-100-10_b200", "mlp", 200, 50),
+                                        ("vgg6_64-64-128-128-256-256_64x64_b256", "vgg", 256, 8)):
+            try:
+                xb, yb = workloads.synthetic_batch(kind, batch)
+                w2 = workloads.BUILDERS[kind](seed=0)
+                opt = sp.Adam()
+                xd = DeviceArray.from_host(xb)
+                yd = DeviceArray.from_host(yb, dtype=np.int32)
+                xd.ptr, yd.ptr
+
+                def one(_i=0, w2=w2, opt=opt, xd=xd, yd=yd):
+                    w2.x_in.assign_value(sp.Variable(xd))
+                    w2.y_true.assign_value(yd)
+                    lv = w2.loss.run()
+                    opt.training_step(w2.learnables, sp.get_gradients(lv))
+
+                for _ in range(3):
+                    one()
+                torch.cuda.synchronize()
+                ms = timed(one, steps)[0]
+                entry = {"value": batch * steps / (ms / 1e3), "unit": UNIT,
+                         "ms_per_step": ms / steps, "batch": batch, "steps": steps}
+                if kind == "vgg":
+                    # conv flops: fprop + dgrad + wgrad per layer, no dgrad for the first layer
+                    chans, hw, fl = [3, 64, 64, 128, 128, 256, 256], 64, 0.0
+                    for i in range(6):
+                        per = 2.0 * batch * hw * hw * 9 * chans[i] * chans[i + 1]
+                        fl += per * (2 if i == 0 else 3)
+                        if i % 2 == 1:
+                            hw //= 2
+                    tfs = fl * steps / (ms / 1e3) / 1e12
+                    entry.update({"conv_tflops": tfs,
+                                  "frac_of_tf32_peak": tfs / (peaks_early["bf16_tflops_sustained"] / 2),
+                                  "note": "conv2d fprop+dgrad+wgrad flops only, over the whole step "
+                                          "(elementwise / pool / Adam time included in the divisor)"})
+                extras[key] = entry
+                del w2, opt, xd, yd
+            except Exception as exc:  # noqa: BLE001 - an extra must never sink the headline
+                extras[key] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     # ---- CPU baseline beside it (N=1 only) ------------------------------------------------
     cpu = None
@@ -472,6 +532,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "top_calls_one_step_ms": profile_summary,
         "cuda_graph": graph_stats,
+        "other_configs": extras,
     }
     print(json.dumps(line), flush=True)
     finish()
@@ -487,6 +548,8 @@ def main():
                     choices=["tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay extra")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the brief MNIST-MLP / VGG-6 measurements (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

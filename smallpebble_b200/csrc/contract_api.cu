@@ -22,15 +22,14 @@ int g_halo_policy = 0;
 
 // The 2-SM TMA kernel (74 persistent CTA pairs over 256-row tiles) beats the 1-SM cp.async
 // kernel on every eligible shape measured back to back (profiles/r01_tma2_vs_umma1_b2b.txt:
-// CIFAR conv2 / conv3 at batch 128 up to the 512-channel sweep) except narrow-N dgrad, where a
-// 256 x 32 tile leaves the pair's tensor cores idle behind the A stream.
+// CIFAR conv2 / conv3 at batch 128 -- including the N = 32 input gradient -- up to the
+// 512-channel sweep).
 bool use_tma2(int mode, const IgemmParams& p, int precision) {
   if (precision != SP_PRECISION_TF32 || g_umma_policy == 2 || g_tma2_policy == 2) return false;
   if (!conv_tma2_supported(mode, p)) return false;
   if (g_tma2_policy == 1) return true;
   if (g_umma_policy == 1) return false;  // tests: force the 1-SM tcgen05 kernel
   const double flop = 2.0 * (double)p.M * (double)p.N * (double)p.K;
-  if (mode == kDgrad && p.N < 64) return false;
   return flop >= 2.5e8;
 }
 
