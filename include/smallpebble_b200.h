@@ -168,6 +168,16 @@ int sp_maxpool2d_bwd(const float* gy, const uint8_t* idx, float* dx, int N, int 
                      int C, int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH,
                      int OW, sp_stream_t stream);
 
+/* Fused across the API seam: maxpool2d(leaky_relu(x)) without storing leaky(x),
+ * bit-identical to the two separate calls; and its gradient dx = maxpool_bwd(gy) * slope(x)
+ * (slope = x > 0 ? 1 : alpha, sp.py:233) without storing the intermediate gradient. */
+int sp_maxpool2d_leaky_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C,
+                           int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
+                           float alpha, sp_stream_t stream);
+int sp_maxpool2d_leaky_bwd(const float* gy, const uint8_t* idx, const float* x, float* dx, int N,
+                           int H, int W, int C, int KH, int KW, int sy, int sx, int pad_t,
+                           int pad_l, int OH, int OW, float alpha, sp_stream_t stream);
+
 /* ---- matmul (sp.py:239-247): C[b] = op(A[b]) * op(B[b]), row-major, strided batch ---- */
 /* transX = 0: X stored [rows, cols] with leading dimension ldx; 1: stored transposed.
  * A batch stride of 0 broadcasts the operand (sp.py:177-193 matmul=True). */

@@ -142,7 +142,8 @@ def scalar_one(shape):
 
 
 class DeviceArray:
-    __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "_pk", "__weakref__")
+    __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "_pk", "_thunk", "_tag",
+                 "__weakref__")
     __array_priority__ = 1000.0
 
     def __init__(self, shape, dtype=FLOAT, buf=None, ptr=None, host=None):
@@ -153,6 +154,8 @@ class DeviceArray:
         self._ptr = ptr
         self._host = host
         self._pk = 0
+        self._thunk = None
+        self._tag = None
 
     def __del__(self):
         # recycle the buffer if this was its last user (refs: slot, local, getrefcount arg)
@@ -180,6 +183,8 @@ class DeviceArray:
         self.dtype = dtype = dtype if dtype is FLOAT else np.dtype(dtype)
         self.size = size = math.prod(shape)
         self._host = None
+        self._thunk = None
+        self._tag = None
         nbytes = (size or 1) * dtype.itemsize
         if _pool_bypass or nbytes > _POOL_MAX_BLOCK:
             self._pk = 0
@@ -195,6 +200,40 @@ class DeviceArray:
                 self._buf = buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
         self._ptr = buf.data_ptr()
         return self
+
+    @staticmethod
+    def deferred(shape, thunk, tag) -> "DeviceArray":
+        """A float32 array whose producing kernel has not been launched yet.  `thunk(out)` fills
+        a freshly allocated `out`; it runs the first time anything needs the data (`.ptr`,
+        `.numpy()`, ...).  `tag` describes the pending op so that a consumer able to fuse it
+        (core.maxpool2d after core.leaky_relu, and their gradients) can skip it altogether --
+        the fusion across the API seam of SURVEY.md 8(f)."""
+        self = object.__new__(DeviceArray)
+        self.shape = tuple(shape)
+        self.dtype = FLOAT
+        self.size = math.prod(self.shape)
+        self._buf = None
+        self._ptr = None
+        self._host = None
+        self._pk = 0
+        self._thunk = thunk
+        self._tag = tag
+        return self
+
+    @property
+    def pending_tag(self):
+        """The tag of a not-yet-launched deferred array, else None."""
+        return self._tag if self._ptr is None else None
+
+    def _materialize(self):
+        thunk = self._thunk
+        out = DeviceArray.empty(self.shape)
+        thunk(out)
+        # adopt the buffer (the temporary `out` must not hand it to the free list when it dies)
+        self._buf, self._ptr, self._pk = out._buf, out._ptr, out._pk
+        out._pk = 0
+        self._thunk = None
+        self._tag = None
 
     @staticmethod
     def from_host(a, dtype=None) -> "DeviceArray":
@@ -244,6 +283,9 @@ class DeviceArray:
         return self._ptr
 
     def _upload(self):
+        if self._thunk is not None:
+            self._materialize()
+            return
         dev = require_cuda()
         host = self._host
         if host.dtype != self.dtype:
@@ -277,6 +319,8 @@ class DeviceArray:
     # ---- NumPy interop -------------------------------------------------------------------
     def numpy(self) -> np.ndarray:
         """Device -> host copy (synchronises the stream)."""
+        if self._ptr is None and self._thunk is not None:
+            self._materialize()
         if self._ptr is None:
             return np.array(self._host, dtype=self.dtype, copy=True)
         out = np.empty(self.shape, self.dtype)
@@ -334,6 +378,8 @@ class DeviceArray:
         if len(shape) == 1 and not isinstance(shape[0], numbers.Integral):
             shape = tuple(shape[0])
         shape = _resolve_shape(shape, self.size)
+        if self._ptr is None and self._thunk is not None:
+            self._materialize()
         if self._ptr is None:
             return DeviceArray(shape, self.dtype, host=self._host.reshape(shape))
         out = DeviceArray(shape, self.dtype, self._buf, self._ptr)  # shares the buffer

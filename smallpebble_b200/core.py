@@ -62,12 +62,16 @@ def debug_set_kernel_policy(policy: int) -> None:
 _fuse_softmax_xent = os.environ.get("SP_FUSE_SOFTMAX_XENT", "1") != "0"
 
 
+_fuse_leaky_pool = os.environ.get("SP_FUSE_LEAKY_POOL", "1") != "0"
+
+
 def set_fusion(enabled: bool) -> None:
     """Fuse cross_entropy(softmax(x)) into one forward and one backward kernel (default on).
     With fusion the loss's tape edge goes straight to the logits, so `get_gradients` has no
     entry for the intermediate probability node; turn it off to get that entry."""
-    global _fuse_softmax_xent
+    global _fuse_softmax_xent, _fuse_leaky_pool
     _fuse_softmax_xent = bool(enabled)
+    _fuse_leaky_pool = bool(enabled)
 
 
 # --------------------------------------------------------------------------------------------
@@ -394,14 +398,36 @@ def square(a: Variable) -> Variable:
 
 
 def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
-    "Elementwise leaky relu (sp.py:231-236): x > 0 ? x : alpha*x; the slope at 0 is alpha."
+    """Elementwise leaky relu (sp.py:231-236): x > 0 ? x : alpha*x; the slope at 0 is alpha.
+
+    When the input is itself an op result (an activation, not a leaf that an optimiser may
+    update in place) the launch is DEFERRED: the output is a pending array that a following
+    `maxpool2d` consumes without it ever being stored (one fused kernel), and the gradient of
+    that pool is folded into this op's gradient the same way.  Anything else that touches the
+    output launches the ordinary kernel first, so results are bit-identical either way."""
     x = a.array
-    y = DeviceArray.empty(x.shape)
-    F.sp_leaky_relu_fwd(x.ptr, y.ptr, x.size, float(alpha), A.stream())
+    alpha = float(alpha)
+
+    def launch(out):
+        F.sp_leaky_relu_fwd(x.ptr, out.ptr, x.size, alpha, A.stream())
+
+    if _fuse_leaky_pool and a.local_gradients and x.ndim == 4 and x.size:
+        y = DeviceArray.deferred(x.shape, launch, ("leaky_relu", x, alpha))
+    else:
+        y = DeviceArray.empty(x.shape)
+        launch(y)
 
     def multiply_by_locgrad(g):
         dx = DeviceArray.empty(x.shape)
-        F.sp_leaky_relu_bwd(g.ptr, x.ptr, dx.ptr, x.size, float(alpha), A.stream())
+        tag = g.pending_tag if isinstance(g, DeviceArray) else None
+        if tag is not None and tag[0] == "maxpool2d_bwd" and tag[1] is y:
+            # the upstream gradient is a pool gradient that has not been launched: one kernel
+            # scatters it and applies this op's slope
+            _, _, g0, idx, geom = tag
+            F.sp_maxpool2d_leaky_bwd(g0.ptr, idx.ptr, x.ptr, dx.ptr, *geom, alpha, A.stream())
+            return dx
+        g = _as_device(g)
+        F.sp_leaky_relu_bwd(g.ptr, x.ptr, dx.ptr, x.size, alpha, A.stream())
         return dx
 
     return Variable(y, [(a, multiply_by_locgrad)])
@@ -694,13 +720,26 @@ def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = 
     idx = DeviceArray.empty((n_images, outh, outw, n_channels), np.uint8)
     geom = (n_images, imheight, imwidth, n_channels, kernheight, kernwidth, stride_y, stride_x,
             pt, pl, outh, outw)
-    if y.size:
+    tag = x.pending_tag
+    fused = tag is not None and tag[0] == "leaky_relu" and y.size > 0
+    if fused:
+        # the input is a leaky_relu that has not been launched: pool leaky(src) directly
+        F.sp_maxpool2d_leaky_fwd(tag[1].ptr, y.ptr, idx.ptr, *geom, tag[2], A.stream())
+    elif y.size:
         F.sp_maxpool2d_fwd(x.ptr, y.ptr, idx.ptr, *geom, A.stream())
 
     def multiply_by_locgrad(g):
+        g = _as_device(g)
+
+        def launch(out):
+            if out.size:
+                F.sp_maxpool2d_bwd(g.ptr, idx.ptr, out.ptr, *geom, A.stream())
+
+        if fused and x.size:
+            # deferred: leaky_relu's gradient closure folds this scatter into its own kernel
+            return DeviceArray.deferred(x.shape, launch, ("maxpool2d_bwd", x, g, idx, geom))
         dx = DeviceArray.empty(x.shape)
-        if dx.size:
-            F.sp_maxpool2d_bwd(g.ptr, idx.ptr, dx.ptr, *geom, A.stream())
+        launch(dx)
         return dx
 
     out = Variable(y, [(images, multiply_by_locgrad)])

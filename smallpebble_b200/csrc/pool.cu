@@ -14,7 +14,17 @@ constexpr int kThreads = 256;
 
 struct PoolGeom {
   int N, H, W, C, KH, KW, sy, sx, pt, pl, OH, OW;
+  // fused leaky_relu (sp.py:231-236) on the pooled tensor: forward pools leaky(x) without
+  // ever storing it, backward multiplies by leaky's slope at x.  leaky == 0: plain max-pool.
+  int leaky;
+  float alpha;
 };
+
+__device__ __forceinline__ float lrelu(float v, float alpha) { return v > 0.f ? v : alpha * v; }
+__device__ __forceinline__ float4 lrelu4(float4 v, float alpha) {
+  return make_float4(lrelu(v.x, alpha), lrelu(v.y, alpha), lrelu(v.z, alpha), lrelu(v.w, alpha));
+}
+__device__ __forceinline__ float slope(float x, float alpha) { return x > 0.f ? 1.f : alpha; }
 
 __device__ __forceinline__ void take(float v, int k, float& best, int& bi) {
   if (v > best || (v != v && best == best)) {
@@ -46,8 +56,10 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_vec4(const float* __rest
         for (int dx = 0; dx < g.KW; ++dx) {
           const int ix = ix0 + dx;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // zero padding takes part in the max
-          if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W)
+          if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) {
             v = ld_stream_f4(xin + ((int64_t)iy * g.W + ix) * g.C + 4 * c4);
+            if (g.leaky) v = lrelu4(v, g.alpha);
+          }
           const int k = dy * g.KW + dx;
           if (k == 0) {
             best = v;
@@ -96,6 +108,10 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_vec4_fixed(const float* 
             v[dy * KW + dx] = ld_stream_f4(xin + ((int64_t)iy * g.W + ix) * g.C + 4 * c4);
         }
       }
+      if (g.leaky) {
+#pragma unroll
+        for (int k = 0; k < KH * KW; ++k) v[k] = lrelu4(v[k], g.alpha);  // lrelu(0) == 0: pads stay 0
+      }
       float4 best = v[0];
       int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
 #pragma unroll
@@ -123,6 +139,7 @@ template <int KH, int KW>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_tile_vec4(const float* __restrict__ gy,
                                                                   const uint8_t* __restrict__ idx,
                                                                   float* __restrict__ dx,
+                                                                  const float* __restrict__ xl,
                                                                   PoolGeom g, int VOH, int VOW) {
   const int C4 = g.C >> 2;
   const int row_len = VOW * C4;
@@ -148,9 +165,17 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_tile_vec4(const float* _
           const int iy = iy0 + dy, ix = ix0 + dxx;
           if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) {
             const int want = dy * KW + dxx;
-            const float4 out = make_float4(k.x == want ? gv.x : 0.f, k.y == want ? gv.y : 0.f,
-                                           k.z == want ? gv.z : 0.f, k.w == want ? gv.w : 0.f);
-            *reinterpret_cast<float4*>(dimg + ((int64_t)iy * g.W + ix) * g.C + 4 * c4) = out;
+            float4 out = make_float4(k.x == want ? gv.x : 0.f, k.y == want ? gv.y : 0.f,
+                                     k.z == want ? gv.z : 0.f, k.w == want ? gv.w : 0.f);
+            const int64_t off = ((int64_t)iy * g.W + ix) * g.C + 4 * c4;
+            if (g.leaky) {
+              const float4 xv = ld_stream_f4(xl + (int64_t)n * g.H * g.W * g.C + off);
+              out.x *= slope(xv.x, g.alpha);
+              out.y *= slope(xv.y, g.alpha);
+              out.z *= slope(xv.z, g.alpha);
+              out.w *= slope(xv.w, g.alpha);
+            }
+            *reinterpret_cast<float4*>(dimg + off) = out;
           }
         }
       }
@@ -180,8 +205,10 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_scalar(const float* __re
       for (int dx = 0; dx < g.KW; ++dx) {
         const int ix = ix0 + dx;
         float v = 0.f;
-        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) {
           v = x[(((int64_t)n * g.H + iy) * g.W + ix) * g.C + c];
+          if (g.leaky) v = lrelu(v, g.alpha);
+        }
         if (first) {
           best = v;
           first = false;
@@ -202,6 +229,7 @@ template <bool NONOVERLAP>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_vec4(const float* __restrict__ gy,
                                                              const uint8_t* __restrict__ idx,
                                                              float* __restrict__ dx,
+                                                             const float* __restrict__ xl,
                                                              PoolGeom g) {
   const int C4 = g.C >> 2;
   const int row_len = g.W * C4;
@@ -247,6 +275,13 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_vec4(const float* __rest
           }
         }
       }
+      if (g.leaky) {
+        const float4 xv = ld_stream_f4(xl + 4 * ((int64_t)row * row_len + e));
+        acc.x *= slope(xv.x, g.alpha);
+        acc.y *= slope(xv.y, g.alpha);
+        acc.z *= slope(xv.z, g.alpha);
+        acc.w *= slope(xv.w, g.alpha);
+      }
       reinterpret_cast<float4*>(dx)[(int64_t)row * row_len + e] = acc;
     }
   }
@@ -255,6 +290,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_vec4(const float* __rest
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_scalar(const float* __restrict__ gy,
                                                                const uint8_t* __restrict__ idx,
                                                                float* __restrict__ dx,
+                                                               const float* __restrict__ xl,
                                                                PoolGeom g) {
   const int64_t total = (int64_t)g.N * g.H * g.W * g.C;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -280,6 +316,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_scalar(const float* __re
         if (idx[o] == dy * g.KW + dxx) acc += gy[o];
       }
     }
+    if (g.leaky) acc *= slope(xl[t], g.alpha);
     dx[t] = acc;
   }
 }
@@ -311,10 +348,10 @@ int check(const PoolGeom& g) {
 
 extern "C" {
 
-int sp_maxpool2d_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C, int KH,
-                     int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
-                     sp_stream_t stream) {
-  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW};
+static int maxpool2d_fwd_impl(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C,
+                              int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
+                              int leaky, float alpha, sp_stream_t stream) {
+  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, leaky, alpha};
   if (int rc = check(g)) return rc;
   const int64_t outs = (int64_t)N * OH * OW * C;
   if (outs == 0) return 0;
@@ -333,33 +370,64 @@ int sp_maxpool2d_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W
   return 0;
 }
 
-int sp_maxpool2d_bwd(const float* gy, const uint8_t* idx, float* dx, int N, int H, int W, int C,
-                     int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
+int sp_maxpool2d_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C, int KH,
+                     int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
                      sp_stream_t stream) {
-  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW};
+  return maxpool2d_fwd_impl(x, y, idx, N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, 0, 0.f,
+                            stream);
+}
+
+int sp_maxpool2d_leaky_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C,
+                           int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
+                           float alpha, sp_stream_t stream) {
+  return maxpool2d_fwd_impl(x, y, idx, N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, 1, alpha,
+                            stream);
+}
+
+static int maxpool2d_bwd_impl(const float* gy, const uint8_t* idx, float* dx, const float* xl,
+                              int N, int H, int W, int C, int KH, int KW, int sy, int sx,
+                              int pad_t, int pad_l, int OH, int OW, int leaky, float alpha,
+                              sp_stream_t stream) {
+  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, leaky, alpha};
   if (int rc = check(g)) return rc;
   const int64_t ins = (int64_t)N * H * W * C;
   if (ins == 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
-  if (C % 4 == 0 && aligned16(gy) && aligned16(dx) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0)
+  if (C % 4 == 0 && aligned16(gy) && aligned16(dx) && (!leaky || aligned16(xl)) &&
+      (reinterpret_cast<uintptr_t>(idx) & 3) == 0)
   {
     // virtual window grid that tiles the whole (top/left padded) image
     const int VOH = (H + pad_t + KH - 1) / KH, VOW = (W + pad_l + KW - 1) / KW;
     if (sy == KH && sx == KW && KH == 2 && KW == 2)
       maxpool_bwd_tile_vec4<2, 2><<<row_grid(N * VOH, VOW * (C / 4)), kThreads, 0, st>>>(
-          gy, idx, dx, g, VOH, VOW);
+          gy, idx, dx, xl, g, VOH, VOW);
     else if (sy == KH && sx == KW && KH == 3 && KW == 3)
       maxpool_bwd_tile_vec4<3, 3><<<row_grid(N * VOH, VOW * (C / 4)), kThreads, 0, st>>>(
-          gy, idx, dx, g, VOH, VOW);
+          gy, idx, dx, xl, g, VOH, VOW);
     else if (sy == KH && sx == KW)
-      maxpool_bwd_vec4<true><<<row_grid(N * H, W * (C / 4)), kThreads, 0, st>>>(gy, idx, dx, g);
+      maxpool_bwd_vec4<true><<<row_grid(N * H, W * (C / 4)), kThreads, 0, st>>>(gy, idx, dx, xl, g);
     else
-      maxpool_bwd_vec4<false><<<row_grid(N * H, W * (C / 4)), kThreads, 0, st>>>(gy, idx, dx, g);
+      maxpool_bwd_vec4<false><<<row_grid(N * H, W * (C / 4)), kThreads, 0, st>>>(gy, idx, dx, xl, g);
   }
   else
-    maxpool_bwd_scalar<<<sp::wave_grid(ins, kThreads, 8), kThreads, 0, st>>>(gy, idx, dx, g);
+    maxpool_bwd_scalar<<<sp::wave_grid(ins, kThreads, 8), kThreads, 0, st>>>(gy, idx, dx, xl, g);
   SP_CHECK_LAUNCH("maxpool2d_bwd");
   return 0;
+}
+
+int sp_maxpool2d_bwd(const float* gy, const uint8_t* idx, float* dx, int N, int H, int W, int C,
+                     int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
+                     sp_stream_t stream) {
+  return maxpool2d_bwd_impl(gy, idx, dx, nullptr, N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW,
+                            0, 0.f, stream);
+}
+
+int sp_maxpool2d_leaky_bwd(const float* gy, const uint8_t* idx, const float* x, float* dx, int N,
+                           int H, int W, int C, int KH, int KW, int sy, int sx, int pad_t, int pad_l,
+                           int OH, int OW, float alpha, sp_stream_t stream) {
+  if (!x) return sp::set_error(SP_ERR_INVALID_ARGUMENT, "sp_maxpool2d_leaky_bwd: null x");
+  return maxpool2d_bwd_impl(gy, idx, dx, x, N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, 1,
+                            alpha, stream);
 }
 
 }  // extern "C"

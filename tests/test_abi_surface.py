@@ -56,3 +56,48 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "numpy_path" not in text, f
                 assert "/root/reference" not in text, f
+
+
+def test_fastcall_binding_matches_ctypes_without_device():
+    """csrc/fastcall.c: the CPython binding calls the same exports as ctypes -- argument
+    conversion (ints, None, floats, NumPy integer scalars, ctypes buffers), the status check and
+    the error text are exercised on calls that fail or finish before touching a device."""
+    import numpy as np
+
+    _abi.load()
+    fast = _abi._load_fast()
+    assert fast is not None, "smallpebble_b200/_lib/_sp_fastcall.so was not built"
+    fn = _abi.f.sp_gemm
+    assert type(fn).__name__ == "FastFn" and fn.__name__ == "sp_gemm"
+    with __import__("pytest").raises(_abi.SmallPebbleCudaError, match="negative extent"):
+        fn(0, 0, -1, 1, 1, None, 1, 0, None, 1, 0, None, 1, 0, 1, 0, None)
+    # a NumPy integer scalar passes its VALUE (not the address of its buffer)
+    with __import__("pytest").raises(_abi.SmallPebbleCudaError, match="negative extent"):
+        fn(0, 0, np.int64(-1), 1, 1, None, 1, 0, None, 1, 0, None, 1, 0, 1, 0, None)
+    # wrong arity is a TypeError, not a crash
+    with __import__("pytest").raises(TypeError):
+        fn(0, 0)
+    # M == 0: returns before any launch; counts as a launching call of the binding
+    before = _abi.counter.launches
+    fn(0, 0, 0, 4, 4, None, 4, 0, None, 4, 0, None, 4, 0, 1, 0, None)
+    assert _abi.counter.launches == before + 1
+    # a ctypes object is passed by address: the flag is written through it
+    flag = ctypes.c_int(7)
+    _abi.f.sp_host_is_pinned(np.zeros(4).ctypes.data, flag)
+    assert flag.value == 0
+
+
+def test_ctypes_fallback_binding(monkeypatch):
+    """SP_NO_FASTCALL=1 (or a missing _sp_fastcall.so) leaves the ctypes binding in charge."""
+    import subprocess
+    import sys
+
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['SP_NO_FASTCALL'] = '1';"
+            "from smallpebble_b200 import _abi; _abi.load();"
+            "fn = _abi.f.sp_gemm; assert type(fn).__name__ == 'function', type(fn);\n"
+            "try:\n"
+            "    fn(0, 0, -1, 1, 1, None, 1, 0, None, 1, 0, None, 1, 0, 1, 0, None)\n"
+            "except _abi.SmallPebbleCudaError as e:\n"
+            "    assert 'negative extent' in str(e); print('ok')\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-500:]

@@ -128,3 +128,29 @@ def test_pinned_host_batches_upload_without_a_host_pass():
         assert np.array_equal(got, pinned.astype(np.float32))
         pageable = np.array(pinned)
         assert np.array_equal(np.asarray(sp.Variable(pageable).array), pinned.astype(np.float32))
+
+
+def test_device_array_free_list_never_aliases_live_buffers():
+    """array.py recycles buffers by byte size; a buffer must not come back while a view or an
+    in-place-rebound alias of it is alive, and it must come back once the last holder dies."""
+    from smallpebble_b200.array import DeviceArray, trim_pool
+
+    trim_pool()
+    a = DeviceArray.full((1024,), 1.0)
+    pa = a.ptr
+    view = a.reshape(32, 32)          # shares a's buffer
+    del a
+    b = DeviceArray.full((1024,), 2.0)  # same size: must NOT reuse the viewed buffer
+    assert b.ptr != pa
+    assert np.all(np.asarray(view) == 1.0)
+    del view                           # last holder: the buffer goes back to the free list
+    c = DeviceArray.empty((1024,))
+    assert c.ptr == pa
+    # in-place arithmetic rebinding keeps exactly one owner
+    x = sp.Variable(np.ones((64, 64))).array
+    x.ptr
+    y = x
+    y += 1.0
+    assert np.all(np.asarray(y) == 2.0)
+    del b, c, x, y
+    trim_pool()

@@ -195,3 +195,46 @@ def test_adam_many_tensors_odd_sizes():
         opt.step(nodes, dict(zip(nodes, gs)))
     for v, n in zip(vs, nodes):
         assert_close(v.array, n.value, 2e-5, "multi-tensor adam")
+
+
+@pytest.mark.parametrize("pool", [((2, 2), (2, 2), "SAME"), ((3, 3), (3, 3), "SAME"),
+                                  ((2, 2), (1, 1), "VALID"), ((3, 2), (2, 3), "SAME")],
+                         ids=["k2s2", "k3s3", "k2s1_overlap", "k3x2_s2x3"])
+@pytest.mark.parametrize("alpha", [0.02, 0.0, -0.5])
+def test_leaky_relu_maxpool_fusion_is_bit_identical(pool, alpha):
+    """maxpool2d(leaky_relu(op_result)) runs as ONE deferred-launch kernel forward and ONE
+    backward (core.leaky_relu docstring).  Values, argmax indices and gradients must equal the
+    unfused path bit for bit -- including alpha = 0 (ties between clamped values) and a
+    negative slope (non-monotonic activation), and the skipped leaky output must still
+    materialise correctly when somebody reads it."""
+    (kh, kw), strides, pad = pool
+    rng = np.random.default_rng(21)
+    x = rng.random((3, 9, 11, 8)) - 0.5
+    gy_seed = rng.random((3, 9, 11, 8)) + 0.5
+
+    def run(fuse):
+        sp.set_fusion(fuse)
+        try:
+            xv = sp.Variable(x)
+            pre = sp.mul(xv, sp.Variable(np.full(x.shape, 1.5)))   # an op result feeds leaky
+            act = sp.leaky_relu(pre, alpha)
+            pooled = sp.maxpool2d(act, kh, kw, pad, list(strides))
+            assert (act.array.pending_tag is not None) == fuse
+            gy = rng.random(pooled.shape)
+            g = sp.get_gradients(sp.mul(pooled, sp.Variable(np.ones(pooled.shape) * 0.75)))
+            out = (np.asarray(pooled.array), np.asarray(pooled._argmax), np.asarray(g[xv]),
+                   np.asarray(g[pre]), np.asarray(g[act]), np.asarray(act.array))
+            del gy
+            return out
+        finally:
+            sp.set_fusion(True)
+
+    fused, plain = run(True), run(False)
+    for a, b, what in zip(fused, plain, ("pooled", "argmax", "dX", "d(pre)", "d(act)", "act")):
+        assert np.array_equal(a, b, equal_nan=True), f"{what} differs between fused and unfused"
+    # and against the oracle
+    x32 = (x.astype(np.float32) * np.float32(1.5))
+    act0 = np.where(x32 > 0, x32, x32 * np.float32(alpha))
+    y0, idx0 = orc.maxpool2d_forward(act0, kh, kw, pad, strides)
+    assert np.array_equal(fused[0], y0.astype(np.float32)) and np.array_equal(fused[1], idx0)
+    del gy_seed
