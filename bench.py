@@ -98,51 +98,84 @@ def run_reference_arm(args):
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region by a background thread
+    through NVML (pynvml, in-process: a forked `nvidia-smi -lms` poller measurably slowed the
+    launch path it was watching).  One sample every 25 ms; `mark_begin/mark_end` bracket the
+    timed region, only samples taken inside it are reported."""
+
+    # nvmlClocksEventReason* bit -> name (the ones that invalidate a measurement, + power cap)
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.rows = []   # (sm_mhz, reasons bitmask)
+        self.lo = 0
+        self.hi = None
+        self.smax = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def mark_begin(self):
+        self.lo = len(self.rows)
+
+    def mark_end(self):
+        self.hi = len(self.rows)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: match by PCI bus id of the torch device
+            import torch
+
+            bus = torch.cuda.get_device_properties(self.gpu).pci_bus_id
+            handle = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                    handle = h
+                    break
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self._nvml = (pynvml, handle)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001 - no NVML: report that, never fail the bench
+            self._nvml = None
+            return
+        self._thread = threading.Thread(target=self._poll, daemon=True)
+        self._thread.start()
+
+    def _poll(self):
+        pynvml, handle = self._nvml
+        while not self._stop.is_set():
+            try:
+                mhz = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                why = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                self.rows.append((float(mhz), int(why)))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.025)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
-            parts = [p.strip() for p in row.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
+        if self._nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        hi = self.hi if self.hi is not None else len(self.rows)
+        window = self.rows[self.lo:max(hi, self.lo + 1)] or self.rows[-1:]
+        reasons = set()
+        for _, why in window:
+            for bit, name in self.REASONS.items():
+                if why & bit:
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [m for m, _ in window]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(reasons), "samples": len(sm),
+                "how": "NVML, 25 ms period, samples inside the timed region only"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -296,6 +329,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # started before the warm-up so that NVML initialisation is not inside a timed region
+    sampler = ClockSampler(local)
+    sampler.start()
+
     # ---- warm-up (also: first-use allocations, lazy scratch, NCCL channels) ---------------
     for i in range(max(args.warmup, 3)):
         step_resident(i)
@@ -318,18 +355,18 @@ def run_ours(args):
         {"call": n, "seq": s, "ms": round(ms, 4)} for ms, n, s, _ in per_call[:8]]
 
     # ---- timed region: `value` (inputs resident in HBM) -----------------------------------
-    sampler = ClockSampler(local)
-    sampler.start()
     sync_all()
     if top is not None:
         # only the dominant ABI function is wrapped, and only every 4th step pays for events
         _abi.prof.arm(top[1], top[2], every=4)
     _abi.prof.records.clear()
     launches0 = _abi.counter.launches
+    sampler.mark_begin()
     wall0 = time.perf_counter()
     step_ms = timed(step_resident, args.steps)
     sync_all()
     wall = time.perf_counter() - wall0
+    sampler.mark_end()
     launches = _abi.counter.launches - launches0
     top_records = list(getattr(_abi.prof, "timed_records", []))
     _abi.prof.disarm()

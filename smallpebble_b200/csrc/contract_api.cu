@@ -58,15 +58,21 @@ IgemmParams base_params() {
   return p;
 }
 
-// The halo-reuse variant moves 4-5x fewer activation bytes from L2 but, with one k-block per
-// pipeline step, is bound by the fixed per-step cost of its MMA-issuing thread (~490 cycles,
-// profiles/r01_halo_trace_v1_issue_bound.log) and measures slower than the im2col kernel with
-// 64-wide stages on every shape tried (profiles/r01_tma2_halo_b2b.txt).  It is correct and
-// tested, and stays opt-in (policy bit 7) until its stages carry two taps per step.
+// The halo-reuse variant moves 4-5x fewer activation bytes from L2.  Measured back to back
+// (profiles/r01_tma2_halo_b2b.txt) it wins on every N <= 128 layer with a real window
+// (VGG 64->64, 64->128, 128->128, CIFAR conv2) and loses at N = 256, where the per-tap B tiles
+// are the larger stream and the halo rows only add MMA work.
 bool use_halo(int mode, const IgemmParams& p, int precision) {
-  if (precision != SP_PRECISION_TF32 || g_umma_policy == 2 || g_halo_policy != 1) return false;
+  if (precision != SP_PRECISION_TF32 || g_umma_policy == 2 || g_halo_policy == 2) return false;
   if (mode != kFprop && mode != kDgrad) return false;
-  return conv_halo2_supported(mode, p);
+  if (!conv_halo2_supported(mode, p)) return false;
+  if (g_halo_policy == 1) return true;
+  if (g_umma_policy == 1 || g_tma2_policy != 0) return false;  // tests pinned another kernel
+  const sp_conv_geom& g = p.g;
+  if (g.KH * g.KW < 4 || p.N > 128) return false;
+  if (conv_halo2_efficiency(mode, p) < 0.5) return false;
+  const double flop = 2.0 * (double)p.M * (double)p.N * (double)p.K;
+  return flop >= 2.5e8;
 }
 
 // Deterministic split of the wgrad reduction axis: enough CTAs for ~2 waves, k_chunk a

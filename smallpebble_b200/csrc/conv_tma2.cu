@@ -794,26 +794,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int nb0 = n0 + (int)rank * bnh;
         const uint32_t tx = 2u * (uint32_t)bnh * 128u;
         for (int cb = 0; cb < p.cblocks; ++cb) {
-          for (int tap = 0; tap < T; ++tap) {
+          // one pipeline step = two taps (the last step of an odd tap count carries one)
+          for (int tap = 0; tap < T; tap += 2) {
             const bool mine = rrb == bslot;
             if (++rrb == kBWarps) rrb = 0;
+            const bool two = tap + 1 < T;
             if (mine) {
-            mbar_wait(b_empty(bs), bph ^ 1u);
-            stamp(tr && gkb < kTraceKb, 16 + kTraceKb + gkb);
-            const uint32_t fb = bfull0 + 8u * bs;
-            const uint32_t dst = b_ring + (uint32_t)bs * p.b_bytes;
-            if (elect_one()) {
-              if (leader) mbar_arrive_expect_tx(b_full(bs), tx);
-              if (MODE == kFprop) {
-                // w as [32][KH*KW*C][Kout/32]: rows (tap*C + cb*32) .. +32
-                tma_tile_3d(dst, &tmB, fb, 0, (tap * p.cblocks + cb) * 32, nb0 >> 5);
-              } else {
-                // virtual tap (dy', dx') of the flipped filter = weight tap (KH-1-dy', KW-1-dx')
-                tma_tile_3d(dst, &tmB, fb, cb * 32, nb0, T - 1 - tap);
+              mbar_wait(b_empty(bs), bph ^ 1u);
+              stamp(tr && gkb < kTraceKb, 16 + kTraceKb + gkb);
+              const uint32_t fb = bfull0 + 8u * bs;
+              const uint32_t dst = b_ring + (uint32_t)bs * 2u * p.b_bytes;
+              if (elect_one()) {
+                if (leader) mbar_arrive_expect_tx(b_full(bs), two ? 2u * tx : tx);
+                if (MODE == kFprop) {
+                  // w as [32][KH*KW*C][Kout/32]: rows (tap*C + cb*32) .. +32
+                  tma_tile_3d(dst, &tmB, fb, 0, (tap * p.cblocks + cb) * 32, nb0 >> 5);
+                  if (two)
+                    tma_tile_3d(dst + p.b_bytes, &tmB, fb, 0, ((tap + 1) * p.cblocks + cb) * 32,
+                                nb0 >> 5);
+                } else {
+                  // virtual tap (dy', dx') of the flipped filter = weight tap (KH-1-dy', KW-1-dx')
+                  tma_tile_3d(dst, &tmB, fb, cb * 32, nb0, T - 1 - tap);
+                  if (two) tma_tile_3d(dst + p.b_bytes, &tmB, fb, cb * 32, nb0, T - 2 - tap);
+                }
               }
+              __syncwarp();
             }
-            __syncwarp();
-            }  // mine
             ++gkb;
             if (++bs == SB) {
               bs = 0;
@@ -848,41 +854,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           tc_fence_after();
           const uint32_t strip = strips + (uint32_t)as * p.strip_bytes + (uint32_t)p.L * 128u;
           int dy = 0, dx = 0;
-          for (int tap = 0; tap < T; ++tap) {
+          for (int tap = 0; tap < T; tap += 2) {
             mbar_wait(b_full(bs), bph);
             stamp(tr && gkb < kTraceKb, 16 + 2 * kTraceKb + gkb);
             ++gkb;
             tc_fence_after();
-            const uint32_t a_view = strip + (uint32_t)(dy * p.Wv + dx) * 128u;
-            const uint32_t b_tile = b_ring + (uint32_t)bs * p.b_bytes;
-            const bool last_tap = tap == T - 1;
-            const bool last_kb = last_tap && cb == p.cblocks - 1;
-            if (elect_one()) {
-            const uint32_t a_lo = desc_lo(a_view, 16u);
-            const uint32_t b_lo = B_MN ? desc_lo(b_tile, 4096u) : desc_lo(b_tile, 16u);
-            constexpr uint32_t b_step = B_MN ? (1024u >> 4) : (32u >> 4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_tf32_2sm(tmem_d, desc_join(a_lo + (uint32_t)k * 2u, a_hi),
-                            desc_join(b_lo + (uint32_t)k * b_step, b_hi), idesc,
-                            (first | (uint32_t)k) ? 1u : 0u);
-            }
-            if (p.trace != nullptr && cluster_id == 0 && gkb <= 30)
-              p.trace[352 + 3 * (gkb - 1) + 1] = clock64();
-            umma_commit_2sm(b_empty(bs));
-            if (last_tap) umma_commit_2sm(a_empty(as));  // every tap of this strip was issued
-            if (last_kb) umma_commit_2sm(tmem_full_bar(acc));
-            }  // elect_one
-            __syncwarp();
-            first = 1u;
-            stamp(tr && gkb <= 30, 352 + 3 * (gkb - 1) + 2);
-            if (++bs == SB) {
-              bs = 0;
-              bph ^= 1u;
-            }
+            // row shifts of the two taps of this step
+            const uint32_t shift0 = (uint32_t)(dy * p.Wv + dx);
             if (++dx == p.KW) {
               dx = 0;
               ++dy;
+            }
+            const uint32_t shift1 = (uint32_t)(dy * p.Wv + dx);
+            if (++dx == p.KW) {
+              dx = 0;
+              ++dy;
+            }
+            const bool two = tap + 1 < T;
+            const uint32_t b_tile = b_ring + (uint32_t)bs * 2u * p.b_bytes;
+            const bool last_step = tap + 2 >= T;
+            const bool last_kb = last_step && cb == p.cblocks - 1;
+            if (elect_one()) {
+              const uint32_t a_lo = desc_lo(strip, 16u);
+              const uint32_t b_lo = B_MN ? desc_lo(b_tile, 4096u) : desc_lo(b_tile, 16u);
+              const uint32_t b_next = p.b_bytes >> 4;
+              constexpr uint32_t b_step = B_MN ? (1024u >> 4) : (32u >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_tf32_2sm(tmem_d, desc_join(a_lo + shift0 * 8u + (uint32_t)k * 2u, a_hi),
+                              desc_join(b_lo + (uint32_t)k * b_step, b_hi), idesc,
+                              (first | (uint32_t)k) ? 1u : 0u);
+              if (two) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_tf32_2sm(tmem_d, desc_join(a_lo + shift1 * 8u + (uint32_t)k * 2u, a_hi),
+                                desc_join(b_lo + b_next + (uint32_t)k * b_step, b_hi), idesc, 1u);
+              }
+              umma_commit_2sm(b_empty(bs));
+              if (last_step) umma_commit_2sm(a_empty(as));  // every tap of this strip was issued
+              if (last_kb) umma_commit_2sm(tmem_full_bar(acc));
+            }
+            __syncwarp();
+            first = 1u;
+            if (++bs == SB) {
+              bs = 0;
+              bph ^= 1u;
             }
           }
           as ^= 1;
@@ -1267,14 +1283,15 @@ HaloPlan halo_plan(int mode, const sp_conv_geom& g, int N) {
   const int bn = N >= 256 ? 256 : N;
   h.b_bytes = (uint32_t)(bn / 2) * 128u;
   const size_t budget = 200 * 1024;
-  if (2 * (size_t)h.strip_bytes + 3 * (size_t)h.b_bytes > budget || h.Wv > 256 || h.pad_t < 0 ||
+  // one B stage holds the tiles of two taps
+  if (2 * (size_t)h.strip_bytes + 3 * 2 * (size_t)h.b_bytes > budget || h.Wv > 256 || h.pad_t < 0 ||
       h.pad_l < 0) {
     h.ok = false;
     return h;
   }
-  size_t nb = (budget - 2 * (size_t)h.strip_bytes) / h.b_bytes;
+  size_t nb = (budget - 2 * (size_t)h.strip_bytes) / (2 * (size_t)h.b_bytes);
   h.b_stages = (int)std::min<size_t>(nb, kMaxBStages);
-  h.smem = 1024 + 2 * (size_t)h.strip_bytes + (size_t)h.b_stages * h.b_bytes;
+  h.smem = 1024 + 2 * (size_t)h.strip_bytes + (size_t)h.b_stages * 2 * h.b_bytes;
   h.ok = true;
   return h;
 }
