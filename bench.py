@@ -244,8 +244,22 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        sp.distributed.init()
         import torch.distributed as dist
+
+        # NCCL announces its version on STDOUT when the first communicator comes up; rank 0's
+        # stdout must carry exactly one JSON line, so park fd 1 on stderr until that is over
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            sp.distributed.init()
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     sp.set_precision(args.precision)
     _abi.load(build_if_missing=False)
     peaks_early = load_peaks()
