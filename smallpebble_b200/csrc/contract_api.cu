@@ -180,6 +180,13 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
     SP_CHECK_LAUNCH("gemm");
     return 0;
   }
+  // N <= 16 (10-way classifier, its weight gradient): one-launch kernels that spread the long
+  // axis over the chip instead of a 64 x 64 tile kernel plus a split-K pass
+  if (sp::g_umma_policy != 1 && sp::gemm_skinny_supported(p)) {
+    if (int rc = sp::launch_gemm_skinny(p, st)) return rc;
+    SP_CHECK_LAUNCH("gemm(skinny)");
+    return 0;
+  }
   // CUDA-core kernel.  A long inner dimension with only a few output tiles (the 10-way
   // classifier: 128 x 10 x 1152) would leave the chip idle: split K over CTAs into the
   // library scratch and sum the partial tiles in a fixed order.

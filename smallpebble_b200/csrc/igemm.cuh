@@ -58,6 +58,10 @@ int launch_conv_halo2(int mode, const IgemmParams& p, cudaStream_t stream);
 // bring-up: cluster 0 writes clock64 stamps into `device_buffer` (>= 512 int64), null = off
 void conv_tma2_set_trace(long long* device_buffer);
 
+// N <= 16 GEMMs (the 10-way classifier and its weight gradient), gemm_skinny.cu: exact fp32
+bool gemm_skinny_supported(const IgemmParams& p);
+int launch_gemm_skinny(const IgemmParams& p, cudaStream_t stream);
+
 // First-layer (C <= 4) CUDA-core kernels, conv_smallc.cu
 bool small_c_supported(const sp_conv_geom& g);
 int small_c_wgrad_blocks(const sp_conv_geom& g);

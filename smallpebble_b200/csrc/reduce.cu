@@ -408,7 +408,8 @@ int reduce_sum_impl(const float* x, float* out, int64_t outer, int64_t reduce, i
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const int64_t col_blocks = vec ? (inner / 4 + 31) / 32 : (inner + 31) / 32;
     int splits = 1;
-    if (col_blocks * outer < 4 * sms && reduce >= 128) {
+    // tiny inputs (a [128, 10] bias gradient) are one block's work: no second pass
+    if (col_blocks * outer < 4 * sms && reduce >= 128 && outer * reduce * inner >= (1 << 16)) {
       splits = (int)std::min<int64_t>((4 * sms) / (col_blocks * outer), reduce / 32);
       if (splits < 1) splits = 1;
       if ((size_t)(outer * splits * inner) > kScratchFloats) splits = 1;
