@@ -696,7 +696,8 @@ int small_c_wgrad_blocks(const sp_conv_geom& g) {
   const bool fixed = fixed_window(g) && (g.K % 4 == 0);
   const int tile = fixed ? kWgTile : kPixTile;
   int64_t blocks = std::min<int64_t>((fixed ? 4 : 2) * sms, (n_pix + tile - 1) / tile);
-  // single-launch cooperative kernel: one block per SM
+  // single-launch cooperative kernel: one block per SM (two per SM measured no faster:
+  // 21.5 vs 20.7 us on the CIFAR layer)
   if (rgb_tile_wgrad(g)) blocks = std::min<int64_t>(sms, (n_pix + tile - 1) / tile);
   return (int)std::max<int64_t>(blocks, 1);
 }
@@ -757,6 +758,13 @@ int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial, fl
                     (void*)&n_tiles, (void*)&words};
     const void* fn = needs_bounds_check(g) ? (const void*)conv_wgrad_rgb3x3_coop_kernel<true>
                                            : (const void*)conv_wgrad_rgb3x3_coop_kernel<false>;
+    // a cooperative grid must be co-resident: never ask for more blocks than fit at once
+    int per_sm = 0;
+    const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem) != cudaSuccess ||
+        per_sm < 1)
+      per_sm = 1;
+    blocks = std::min(blocks, per_sm * sms);
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(kThreads), args,
                                                 smem, st);
     if (e != cudaSuccess)
