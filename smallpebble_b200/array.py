@@ -521,6 +521,23 @@ _DIRECT_DTYPES = {np.dtype(np.float32), np.dtype(np.float64)}
 _in_flight_sources = []  # (event, ndarray): caller arrays an async H2D is still reading
 
 
+def pinned_empty(shape, dtype):
+    """A fresh NumPy array in page-locked memory (None when there is no CUDA device).  Used by
+    `sp.batch`: a minibatch gathered into it is uploaded by DMA straight from the array the
+    user holds (see `from_host`), and it is an ordinary ndarray in every other respect -- the
+    pinned block goes back to torch's host allocator when the array is garbage collected."""
+    if not _pinned.available():
+        return None
+    torch = _lazy_torch()
+    dtype = np.dtype(dtype)
+    nbytes = max(math.prod(shape), 1) * dtype.itemsize
+    try:
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    except RuntimeError:
+        return None
+    return t.numpy()[:math.prod(shape) * dtype.itemsize].view(dtype).reshape(shape)
+
+
 def _is_pinned(a: np.ndarray) -> bool:
     flag = C.c_int(0)
     F.sp_host_is_pinned(a.ctypes.data, flag)

@@ -189,13 +189,27 @@ def sgd_step(variables, gradients, learning_rate: float = 0.001) -> None:
 
 
 def batch(X: np.ndarray, y: np.ndarray, size: int, seed=None):
-    "Yield sub-batches of X,y, randomly selecting with replacement (sp.py:586-593)."
+    """Yield sub-batches of X,y, randomly selecting with replacement (sp.py:586-593).
+
+    Same draws from the global NumPy RNG and the same values as the reference.  With a GPU
+    present a floating-point batch of 64 KB or more is gathered straight into a fresh
+    page-locked array (the input pipeline): `sp.Variable(xbatch)` then uploads
+    it by DMA without a staging pass and narrows float64 on the device."""
     assert (y.ndim == 1) and (X.shape[0] == y.size), "unexpected dimensions."
     if seed:
         np.random.seed(seed)
+    X = np.asarray(X)
+    row_bytes = (X.size // max(X.shape[0], 1)) * X.dtype.itemsize
+    pin = (X.dtype in (np.float32, np.float64) and X.ndim >= 1
+           and row_bytes * size >= A._PIN_THRESHOLD and X.flags.c_contiguous)
     while True:
         idx = np.random.randint(0, y.size, size)
-        yield X[idx, ...], y[idx]
+        xb = A.pinned_empty((size,) + X.shape[1:], X.dtype) if pin else None
+        if xb is not None:
+            np.take(X, idx, axis=0, out=xb)
+        else:
+            xb = X[idx, ...]
+        yield xb, y[idx]
 
 
 def convlayer(height: int, width: int, depth: int, n_kernels: int, padding: str = "VALID",

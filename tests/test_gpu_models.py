@@ -154,3 +154,26 @@ def test_device_array_free_list_never_aliases_live_buffers():
     assert np.all(np.asarray(y) == 2.0)
     del b, c, x, y
     trim_pool()
+
+
+def test_batch_yields_pinned_minibatches_with_reference_values():
+    """sp.batch (sp.py:586-593): same RNG draws and values as the reference; on a GPU box the
+    batch lives in page-locked memory so that Variable(xbatch) is a direct DMA."""
+    from smallpebble_b200.array import _is_pinned
+
+    rng = np.random.default_rng(3)
+    X, y = rng.random((500, 32, 32, 3)), rng.integers(0, 10, 500)
+    np.random.seed(7)   # what the reference's generator draws from the global RNG
+    idx = np.random.randint(0, y.size, 128)
+    idx2 = np.random.randint(0, y.size, 128)
+    gen = sp.batch(X, y, 128, seed=7)
+    xb, yb = next(gen)
+    assert np.array_equal(xb, X[idx]) and np.array_equal(yb, y[idx])
+    assert xb.dtype == np.float64 and _is_pinned(xb)
+    xb2, _ = next(gen)
+    assert np.array_equal(xb2, X[idx2]) and xb2 is not xb   # a fresh array per batch
+    v = sp.Variable(xb)
+    assert v.array._host is xb
+    assert np.array_equal(np.asarray(v.array), X[idx].astype(np.float32))
+    small = next(sp.batch(np.arange(20.0).reshape(10, 2), np.arange(10), 4, seed=1))[0]
+    assert small.shape == (4, 2)   # below the pinning threshold: plain fancy indexing
