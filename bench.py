@@ -31,6 +31,7 @@ METRIC = "train_images_per_sec"
 UNIT = "images/s"
 L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
 RESIDENT_BATCHES = 96       # x 1.57 MB fp32 = 151 MB of inputs: larger than the 126 MB L2
+WARMUP_FLOOR = 25           # untimed steps run directly before the timed region (see below)
 
 
 def load_peaks():
@@ -369,6 +370,12 @@ def run_ours(args):
         {"call": n, "seq": s, "ms": round(ms, 4)} for ms, n, s, _ in per_call[:8]]
 
     # ---- timed region: `value` (inputs resident in HBM) -----------------------------------
+    # The host side of the loop speeds up over its first ~25 steps (CPU clocks, warm caches,
+    # CPython's adaptive specialisation: 290 -> 200 us of issue time per step, measured by
+    # scripts/step_transient.py), so the warm-up directly in front of the timed region is at
+    # least 25 steps whatever --warmup says; the JSON reports the number actually run.
+    for i in range(WARMUP_FLOOR):
+        step_resident(i)
     sync_all()
     if top is not None:
         # only the dominant ABI function is wrapped, and only every 4th step pays for events
@@ -390,7 +397,7 @@ def run_ours(args):
     value = global_batch * args.steps / (total_ms / 1e3)
 
     # ---- e2e: host batch -> H2D -> step -> loss D2H, every step ----------------------------
-    for i in range(3):
+    for i in range(10):
         step_e2e(i)
     sync_all()
     tc = transfer_counters()
@@ -569,6 +576,10 @@ def run_ours(args):
             "timing": "one CUDA-event pair on the launch stream around exactly K consecutive "
                       "steps (training steady state: host issue overlaps device execution); "
                       "max over ranks",
+            "extra_warmup_steps": WARMUP_FLOOR,
+            "extra_warmup_note": "untimed steps run directly before each timed region on top of "
+                                 "--warmup: the host side of the loop needs ~25 steps to reach "
+                                 "its steady issue rate (scripts/step_transient.py)",
             "e2e_input": "float64 NumPy batches in pinned host memory, one H2D per step; "
                          "np.isnan(loss) read back every step (README.md:319)",
             "input_image_gradient": "deferred (computed only if read; the loop never reads it)",
