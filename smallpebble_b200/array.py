@@ -70,6 +70,7 @@ def reset_device_cache():
     _device = None
     _raw_stream = None
     trim_pool()  # recycled buffers belong to the previous device
+    _upload_ring.reset()
 
 
 _raw_stream = None
@@ -289,14 +290,9 @@ class DeviceArray:
         dev = require_cuda()
         host = self._host
         if host.dtype != self.dtype:
-            # pinned float64 source: raw DMA, then narrow on the device
-            raw = _torch.empty(host.nbytes, dtype=_torch.uint8, device=dev)
+            # pinned float64 source: raw DMA (copy stream), then narrow on the device
             buf = _torch.empty(host.size * 4, dtype=_torch.uint8, device=dev)
-            st = stream()
-            F.sp_memcpy_h2d(raw.data_ptr(), host.ctypes.data, host.nbytes, st)
-            F.sp_cast_f64_f32(raw.data_ptr(), buf.data_ptr(), host.size, st)
-            _counters["h2d_bytes"] += host.nbytes
-            _keep_alive_until_copied(host)
+            upload_f64_narrowed(host, buf.data_ptr())
             self._buf, self._ptr, self._host = buf, buf.data_ptr(), None
             return
         nbytes = max(host.size, 1) * host.dtype.itemsize
@@ -519,6 +515,68 @@ _pinned = _PinnedPool()
 _PIN_THRESHOLD = 64 * 1024
 _DIRECT_DTYPES = {np.dtype(np.float32), np.dtype(np.float64)}
 _in_flight_sources = []  # (event, ndarray): caller arrays an async H2D is still reading
+
+
+class _UploadRing:
+    """Raw host->device uploads of page-locked float64 batches on a dedicated COPY stream, so
+    that the DMA of step i+1's batch overlaps the kernels of step i that are still queued on
+    the compute stream (the README loop calls `sp.Variable(xbatch)` while the previous step's
+    backward pass is in flight).  Three library-owned staging buffers, reused round-robin:
+    the copy stream waits for the event recorded after a slot's last consumer (the narrowing
+    kernel on the compute stream) before overwriting it, and the compute stream waits for the
+    copy's event before reading it.  The buffers never go back to torch's allocator while in
+    use, so no cross-stream reuse hazard exists."""
+
+    SLOTS = 3
+
+    def __init__(self):
+        self.stream = None
+        self.slots = [{"buf": None, "nbytes": 0, "free": None} for _ in range(self.SLOTS)]
+        self.next = 0
+
+    def reset(self):
+        self.__init__()
+
+    def upload(self, host_ptr: int, nbytes: int):
+        torch = _lazy_torch()
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        slot = self.slots[self.next]
+        self.next = (self.next + 1) % self.SLOTS
+        if slot["nbytes"] < nbytes:
+            if slot["free"] is not None:
+                slot["free"].synchronize()  # rare: the slot grows; its last reader must be done
+            slot["buf"] = torch.empty(nbytes, dtype=torch.uint8, device=require_cuda())
+            slot["nbytes"] = nbytes
+            slot["free"] = None
+            # the new block may be a recycled one: order the copy after everything queued so far
+            self.stream.wait_stream(torch.cuda.current_stream())
+        if slot["free"] is not None:
+            self.stream.wait_event(slot["free"])
+        F.sp_memcpy_h2d(slot["buf"].data_ptr(), host_ptr, nbytes, self.stream.cuda_stream)
+        landed = torch.cuda.Event()
+        landed.record(self.stream)
+        torch.cuda.current_stream().wait_event(landed)
+        return slot
+
+    @staticmethod
+    def consumed(slot):
+        ev = _lazy_torch().cuda.Event()
+        ev.record()  # on the compute stream, after the kernel that read the slot
+        slot["free"] = ev
+
+
+_upload_ring = _UploadRing()
+
+
+def upload_f64_narrowed(host: np.ndarray, dst_ptr: int) -> None:
+    """float64 page-locked `host` -> fp32 at `dst_ptr`: raw DMA on the copy stream, narrowing
+    kernel on the compute stream."""
+    slot = _upload_ring.upload(host.ctypes.data, host.nbytes)
+    F.sp_cast_f64_f32(slot["buf"].data_ptr(), dst_ptr, host.size, stream())
+    _UploadRing.consumed(slot)
+    _counters["h2d_bytes"] += host.nbytes
+    _keep_alive_until_copied(host)
 
 
 def pinned_empty(shape, dtype):

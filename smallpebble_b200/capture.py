@@ -57,12 +57,11 @@ def _copy_into(dst: DeviceArray, value) -> None:
         return
     st = A.stream()
     if host.dtype != dst.dtype:
-        # caller's pinned float64 batch: raw DMA into scratch, narrowed into the static buffer
-        raw = DeviceArray.empty((host.nbytes,), np.uint8)
-        F.sp_memcpy_h2d(raw.ptr, host.ctypes.data, host.nbytes, st)
-        F.sp_cast_f64_f32(raw.ptr, dst.ptr, host.size, st)
-    else:
-        F.sp_memcpy_h2d(dst.ptr, host.ctypes.data, host.nbytes, st)
+        # caller's pinned float64 batch: raw DMA on the copy stream, narrowed into the static
+        # buffer on the compute stream (in front of the graph launch)
+        A.upload_f64_narrowed(host, dst.ptr)
+        return
+    F.sp_memcpy_h2d(dst.ptr, host.ctypes.data, host.nbytes, st)
     A._counters["h2d_bytes"] += host.nbytes
     if host.ctypes.data in A._pinned.owned:
         A._pinned.release(host)
