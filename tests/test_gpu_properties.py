@@ -186,3 +186,51 @@ def test_empty_and_ragged_inputs():
     assert np.array_equal(np.asarray(s.array), np.zeros(5))
     m = sp.matmul(sp.Variable(np.zeros((4, 0))), sp.Variable(np.zeros((0, 3))))
     assert np.array_equal(np.asarray(m.array), np.zeros((4, 3)))
+
+
+def _random_geometries(seed, count):
+    """Random conv geometries whose channel counts make them eligible for the 2-SM kernels:
+    odd image sizes, windows up to 5x4, both paddings, strides 1-3, tiny and ragged batches."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        n = int(rng.choice([1, 2, 3, 5]))
+        h, w = int(rng.integers(1, 20)), int(rng.integers(1, 20))
+        kh, kw = int(rng.integers(1, 6)), int(rng.integers(1, 5))
+        c = int(rng.choice([32, 64, 96]))
+        k = int(rng.choice([64, 128, 192]))
+        pad = str(rng.choice(["SAME", "VALID"]))
+        s = (int(rng.integers(1, 4)), int(rng.integers(1, 4))) if rng.random() < 0.3 else (1, 1)
+        if pad == "VALID" and (kh > h or kw > w):
+            continue
+        out.append((n, h, w, c, kh, kw, k, pad, s))
+    return out
+
+
+@pytest.mark.parametrize("policy", [32 + 256, 32 + 128], ids=["im2col", "halo"])
+def test_two_sm_kernels_on_random_geometries(policy):
+    """Fuzz the 2-SM TMA kernels (im2col walk and halo-reuse strips) against the float64 oracle:
+    40 random geometries per variant -- image sizes that are not multiples of anything, windows
+    wider than the image under SAME padding, single-pixel images, strides (which send dgrad /
+    the halo variant back to the other kernels: the dispatch is part of what is tested)."""
+    from oracle import numpy_path as orc
+
+    old = sp.get_precision()
+    sp.set_precision("tf32")
+    core.debug_set_kernel_policy(policy)
+    try:
+        for i, (n, h, w, c, kh, kw, k, pad, s) in enumerate(_random_geometries(2024, 40)):
+            rng = np.random.default_rng(100 + i)
+            x, wt = rng.random((n, h, w, c)) - 0.5, rng.random((kh, kw, c, k)) - 0.5
+            xv, wv = sp.Variable(x), sp.Variable(wt)
+            y = sp.conv2d(xv, wv, pad, s)
+            gy = rng.random(y.shape) - 0.5
+            g = sp.get_gradients(sp.mul(y, sp.Variable(gy)))
+            y0, dx0, dw0 = orc.conv2d_grads(x, wt, gy, pad, s)
+            what = f"geometry {i}: x{(n, h, w, c)} w{(kh, kw, c, k)} {pad} s{s}"
+            assert_close(y.array, y0, RTOL["tf32"], what + " y")
+            assert_close(g[xv], dx0, RTOL["tf32"], what + " dX")
+            assert_close(g[wv], dw0, RTOL["tf32"], what + " dW")
+    finally:
+        core.debug_set_kernel_policy(0)
+        sp.set_precision(old)
