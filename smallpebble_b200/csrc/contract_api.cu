@@ -311,7 +311,7 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
                            workspace_bytes, need);
     bool reduced = false;
     if (int rc = sp::launch_conv_wgrad_smallc(x, gy, static_cast<float*>(workspace), dw, *g, blocks,
-                                              sp::as_stream(stream), &reduced))
+                                              precision, sp::as_stream(stream), &reduced))
       return rc;
     SP_CHECK_LAUNCH("conv2d_wgrad(small C)");
     if (reduced) return 0;

@@ -659,6 +659,187 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rgb3x3_coop_kernel(
   }
 }
 
+
+// Tensor-core RGB 3x3 filter gradient (SP_PRECISION_TF32, stride 1): the CUDA-core kernel
+// above issues ~37 warp instructions per output pixel (7.3 M for the CIFAR layer, which is
+// what bounds it -- 12 k issue cycles per scheduler for 2.5 us worth of HBM traffic).  Here
+// dW^T[K, 27] = dY^T[K, P] * patches[P, 27] runs on mma.sync.m16n8k8.tf32 (the warp-level
+// tensor path: 27 x 32-64 outputs are far too small for a tcgen05 tile), ~28 instructions
+// per EIGHT pixels:
+//   * a tile is R output rows of one image walked in "padded-linear" order q = r * Wv + xv over
+//     a virtual width Wv = W + pad_l + pad_r, so the patch element (q, (dy, dx, c)) is simply
+//     x_s[3 q + (dy Wv + dx) 3 + c]: the B fragments are read straight from the zero-padded
+//     input rows in shared memory, no im2col staging; virtual pixels xv >= OW carry dY = 0;
+//   * dY rows land in shared memory by 16-byte cp.async (zero-filled for virtual pixels) with a
+//     row stride of K + 8 floats, which makes the A fragment loads bank-conflict free;
+//   * two-stage cp.async pipeline over the block's tiles, per-warp accumulators (K/16 x 4 MMA
+//     tiles), fixed-order reduction over warps, then over blocks behind a grid barrier.
+struct RgbMmaPlan {
+  int rows;           // output rows per tile
+  int wv;             // virtual (padded) row width
+  int q_pad;          // virtual pixels per tile, rounded up to 8
+  int tiles_per_img;
+  int n_tiles;
+  int x_staged;       // floats of x staged per tile: (rows + 2) * wv * 3
+  int x_floats;       // staged + zeroed slack read by the virtual tail pixels
+  int stage_floats;   // q_pad * (K + 8) + x_floats
+};
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+__device__ __forceinline__ void mma_tf32_m16n8k8(float (&d)[4], const uint32_t (&a)[4],
+                                                 const uint32_t (&b)[2]) {
+  // fp32 bit patterns are consumed as tf32 (low 13 mantissa bits ignored), like kind::tf32
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int KT>  // K = 16 * KT output channels
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rgb3x3_mma_kernel(
+    const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partial,
+    float* __restrict__ dw, const __grid_constant__ sp_conv_geom g,
+    const __grid_constant__ RgbMmaPlan pl, unsigned int* __restrict__ sync_words) {
+  constexpr int K = 16 * KT, K4 = K / 4, GS = K + 8, KC = 27;
+  constexpr int DQ = kThreads / K4;  // virtual pixels covered by one pass of the dY copy
+  extern __shared__ __align__(16) float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int gy_floats = pl.q_pad * GS;
+
+  // slack behind the staged input rows: read (times dY = 0) by the virtual tail pixels,
+  // never written by the pipeline
+  for (int s = 0; s < 2; ++s)
+    for (int i = pl.x_staged + threadIdx.x; i < pl.x_floats; i += kThreads)
+      sm[s * pl.stage_floats + gy_floats + i] = 0.f;
+
+  auto prefetch = [&](int tile_idx, int stage) {
+    const int n = tile_idx / pl.tiles_per_img;
+    const int oy0 = (tile_idx - n * pl.tiles_per_img) * pl.rows;
+    float* gy_s = sm + stage * pl.stage_floats;
+    float* x_s = gy_s + gy_floats;
+    {
+      int q = threadIdx.x / K4;
+      const int part = threadIdx.x % K4;
+      int r = q / pl.wv, xv = q - r * pl.wv;
+      for (; q < pl.q_pad; q += DQ) {
+        const bool valid = r < pl.rows && xv < g.OW && oy0 + r < g.OH;
+        const float* src =
+            valid ? gy + ((int64_t)(n * g.OH + oy0 + r) * g.OW + xv) * K + part * 4 : gy;
+        cp_async16_zfill(&gy_s[q * GS + part * 4], src, valid);
+        xv += DQ;
+        while (xv >= pl.wv) {
+          xv -= pl.wv;
+          ++r;
+        }
+      }
+    }
+    const int xrow = pl.wv * 3, w3 = g.W * 3;
+    for (int i = threadIdx.x; i < pl.x_staged; i += kThreads) {
+      const int pr = i / xrow;
+      const int col3 = i - pr * xrow - 3 * g.pad_l;
+      const int iy = oy0 + pr - g.pad_t;
+      const bool in = (unsigned)iy < (unsigned)g.H && (unsigned)col3 < (unsigned)w3;
+      cp_async4_zfill(&x_s[i], in ? x + (int64_t)(n * g.H + iy) * w3 + col3 : x, in);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // B fragment column n = 8 j + gq = (dy, dx, c)  ->  offset inside the padded rows
+  int off[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = 8 * j + gq;
+    off[j] = n < KC ? (n / 9) * pl.wv * 3 + n % 9 : 0;
+  }
+
+  float acc[KT][4][4];
+#pragma unroll
+  for (int m = 0; m < KT; ++m)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[m][j][c] = 0.f;
+
+  const int n_groups = pl.q_pad >> 3;
+  int stage = 0;
+  if ((int)blockIdx.x < pl.n_tiles) prefetch(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < pl.n_tiles; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    if (next < pl.n_tiles) {
+      prefetch(next, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t* gy_u = reinterpret_cast<const uint32_t*>(sm + stage * pl.stage_floats);
+    const uint32_t* x_u = gy_u + gy_floats;
+    for (int grp = warp; grp < n_groups; grp += kThreads / 32) {
+      const int p0 = grp * 8;
+      const uint32_t* ab = gy_u + (p0 + t) * GS + gq;
+      uint32_t a[KT][4];
+#pragma unroll
+      for (int m = 0; m < KT; ++m) {
+        a[m][0] = ab[m * 16];
+        a[m][1] = ab[m * 16 + 8];
+        a[m][2] = ab[4 * GS + m * 16];
+        a[m][3] = ab[4 * GS + m * 16 + 8];
+      }
+      const uint32_t* bb = x_u + 3 * (p0 + t);
+      uint32_t b[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        b[j][0] = bb[off[j]];
+        b[j][1] = bb[off[j] + 12];
+      }
+#pragma unroll
+      for (int m = 0; m < KT; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_tf32_m16n8k8(acc[m][j], a[m], b[j]);
+    }
+    __syncthreads();
+    stage ^= 1;
+  }
+
+  // fixed-order sum over the warps through shared memory (aliases the drained stages):
+  // red[warp][n][k], n = (dy, dx, c) < 27
+  float* red = sm;
+#pragma unroll
+  for (int m = 0; m < KT; ++m)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = m * 16 + gq + ((c & 2) ? 8 : 0);
+        const int n = 8 * j + 2 * t + (c & 1);
+        if (n < KC) red[(warp * KC + n) * K + k] = acc[m][j][c];
+      }
+  __syncthreads();
+  float* out = partial + (int64_t)blockIdx.x * KC * K;
+  for (int i = threadIdx.x; i < KC * K; i += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w * KC * K + i];
+    out[i] = s;
+  }
+
+  grid_barrier(sync_words + 32, gridDim.x);
+  const int warps = kThreads / 32;
+  for (int o = blockIdx.x * warps + warp; o < KC * K; o += gridDim.x * warps) {
+    float s = 0.f;
+    for (int j = lane; j < (int)gridDim.x; j += 32) s += __ldcg(partial + (int64_t)j * KC * K + o);
+    s = warp_sum(s);
+    if (lane == 0) dw[o] = s;
+  }
+}
+
 }  // namespace
 
 bool small_c_supported(const sp_conv_geom& g) {
@@ -688,6 +869,76 @@ static size_t rgb_tile_wgrad_smem(const sp_conv_geom& g) {
   const size_t shares = kThreads / (7 * (g.K / 8));
   const size_t red = shares * 28 * g.K;
   return std::max(stages, red) * sizeof(float);
+}
+
+// plan of the tensor-core RGB filter gradient; rows == 0 when the geometry does not qualify
+static RgbMmaPlan rgb_mma_plan(const sp_conv_geom& g, int max_blocks) {
+  RgbMmaPlan pl = {};
+  if (!fixed_window(g) || g.sy != 1 || g.sx != 1 || !(g.K == 16 || g.K == 32 || g.K == 64))
+    return pl;
+  const int wv = g.OW + 2;  // == W + pad_l + pad_r for a stride-1 3x3 window
+  const int gs = g.K + 8;
+  auto stage_floats = [&](int rows, int* q_pad, int* x_staged, int* x_floats) {
+    *q_pad = (rows * wv + 7) / 8 * 8;
+    *x_staged = (rows + 2) * wv * 3;
+    *x_floats = ((*q_pad + 2 * wv + 3) * 3 + 16 + 3) / 4 * 4;
+    if (*x_floats < *x_staged) *x_floats = (*x_staged + 3) / 4 * 4;
+    return *q_pad * gs + *x_floats;
+  };
+  const int max_stage = 100 * 1024 / 4;
+  double best = -1.0;
+  for (int rows = std::min(g.OH, 64); rows >= 1; --rows) {
+    int q_pad, x_staged, x_floats;
+    const int sf = stage_floats(rows, &q_pad, &x_staged, &x_floats);
+    if (sf > max_stage) continue;
+    const int per_img = (g.OH + rows - 1) / rows;
+    const int64_t tiles = (int64_t)g.N * per_img;
+    if (tiles > 0x7fffffff) continue;
+    const int64_t blocks = std::min<int64_t>(max_blocks, tiles);
+    const int64_t waves = (tiles + blocks - 1) / blocks;
+    // useful rows over row slots, times a fixed per-tile cost of ~64 pixels
+    const double eff = (double)g.N * g.OH / ((double)waves * blocks * rows) *
+                       ((double)rows * wv / (rows * wv + 64.0));
+    if (eff > best) {
+      best = eff;
+      pl.rows = rows;
+      pl.wv = wv;
+      pl.q_pad = q_pad;
+      pl.tiles_per_img = per_img;
+      pl.n_tiles = (int)tiles;
+      pl.x_staged = x_staged;
+      pl.x_floats = x_floats;
+      pl.stage_floats = sf;
+    }
+  }
+  return pl;
+}
+
+template <int KT>
+static int launch_rgb_mma(const float* x, const float* gy, float* partial, float* dw,
+                          const sp_conv_geom& g, const RgbMmaPlan& pl, int blocks,
+                          cudaStream_t st) {
+  const size_t smem = std::max<size_t>(2 * (size_t)pl.stage_floats, (size_t)8 * 27 * g.K) * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_wgrad_rgb3x3_mma_kernel<KT>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    attr_done = true;
+  }
+  unsigned int* words = sync_words_for_current_device();
+  if (!words) return set_error(SP_ERR_WORKSPACE, "conv2d_wgrad: no sync words");
+  sp_conv_geom gg = g;
+  RgbMmaPlan pp = pl;
+  void* args[] = {(void*)&x, (void*)&gy, (void*)&partial, (void*)&dw, (void*)&gg, (void*)&pp,
+                  (void*)&words};
+  const void* fn = (const void*)conv_wgrad_rgb3x3_mma_kernel<KT>;
+  blocks = std::min(blocks, pl.n_tiles);
+  cudaError_t e =
+      cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(kThreads), args, smem, st);
+  if (e != cudaSuccess)
+    return set_error((int)e, "cooperative launch of conv_wgrad_rgb3x3_mma failed: %s",
+                     cudaGetErrorString(e));
+  return 0;
 }
 
 int small_c_wgrad_blocks(const sp_conv_geom& g) {
@@ -730,8 +981,21 @@ int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_
 
 // partial must hold small_c_wgrad_blocks(g) * KH*KW*C * K floats
 int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial, float* dw,
-                             const sp_conv_geom& g, int blocks, cudaStream_t st, bool* reduced) {
+                             const sp_conv_geom& g, int blocks, int precision, cudaStream_t st,
+                             bool* reduced) {
   *reduced = false;
+  if (precision == SP_PRECISION_TF32 && ((reinterpret_cast<uintptr_t>(gy) & 15) == 0)) {
+    const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+    const RgbMmaPlan pl = rgb_mma_plan(g, std::min(blocks, sms));
+    if (pl.rows > 0) {
+      const int nb = std::min(blocks, sms);
+      int rc = g.K == 16   ? launch_rgb_mma<1>(x, gy, partial, dw, g, pl, nb, st)
+               : g.K == 32 ? launch_rgb_mma<2>(x, gy, partial, dw, g, pl, nb, st)
+                           : launch_rgb_mma<4>(x, gy, partial, dw, g, pl, nb, st);
+      if (rc == 0) *reduced = true;
+      return rc;
+    }
+  }
   const int kc = g.KH * g.KW * g.C;
   const int64_t n_pix = (int64_t)g.N * g.OH * g.OW;
   const bool fixed = fixed_window(g) && (g.K % 4 == 0) &&

@@ -7,7 +7,11 @@
 //                                         block-wide tree reduction of the N partial sums;
 //   cols kernel (A's m axis contiguous):  one thread per output row (coalesced along m), the
 //                                         k axis split over 8 thread groups + smem reduction.
+#include <cooperative_groups.h>
+
 #include "igemm.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sp {
 namespace {
@@ -15,34 +19,69 @@ namespace {
 constexpr int kMaxN = 16;
 constexpr int kThreads = 256;
 
-template <int NN>
+// R rows per block: every B value fetched feeds R rows (a block per row re-read all of B --
+// 168 MB of L2 traffic for the VGG classifier [256, 16384] x [16384, 10]).  A long k axis is
+// split over the gridDim.y CTAs of a thread-block cluster (1, S, 1); rank 0 adds the S partial
+// tiles out of its peers' shared memory in rank order, so the result stays deterministic and
+// needs neither a workspace nor a second launch.
+template <int NN, int R>
 __global__ void __launch_bounds__(kThreads) gemm_skinny_rows_kernel(const IgemmParams p) {
-  __shared__ float red[kThreads / 32][NN];
-  const int64_t m = blockIdx.x;
-  const float* __restrict__ a = p.A + m * p.a_rs;
-  float acc[NN];
+  __shared__ float red[kThreads / 32][R][NN];
+  __shared__ float part[R][NN];
+  const int64_t m0 = (int64_t)blockIdx.x * R;
+  const int splits = (int)gridDim.y, rank = (int)blockIdx.y;
+  const int64_t k_chunk = ((p.K + splits - 1) / splits + kThreads - 1) / kThreads * kThreads;
+  const int64_t k_begin = rank * k_chunk;
+  const int64_t k_end = (k_begin + k_chunk < p.K) ? k_begin + k_chunk : p.K;
+  float acc[R][NN];
 #pragma unroll
-  for (int n = 0; n < NN; ++n) acc[n] = 0.f;
-  for (int64_t k = threadIdx.x; k < p.K; k += kThreads) {
-    const float av = __ldg(a + k);
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int n = 0; n < NN; ++n) acc[r][n] = 0.f;
+  for (int64_t k = k_begin + threadIdx.x; k < k_end; k += kThreads) {
+    float av[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) av[r] = (m0 + r < p.M) ? __ldg(p.A + (m0 + r) * p.a_rs + k) : 0.f;
     const float* __restrict__ b = p.B + k * p.b_rs;
 #pragma unroll
-    for (int n = 0; n < NN; ++n)
-      if (n < p.N) acc[n] = fmaf(av, __ldg(b + n * p.b_cs), acc[n]);
+    for (int n = 0; n < NN; ++n) {
+      if (n < p.N) {
+        const float bv = __ldg(b + n * p.b_cs);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r][n] = fmaf(av[r], bv, acc[r][n]);
+      }
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int n = 0; n < NN; ++n) {
-    const float v = warp_sum(acc[n]);
-    if (lane == 0) red[warp][n] = v;
-  }
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int n = 0; n < NN; ++n) {
+      const float v = warp_sum(acc[r][n]);
+      if (lane == 0) red[warp][r][n] = v;
+    }
   __syncthreads();
-  if (threadIdx.x < p.N) {
+  for (int i = threadIdx.x; i < R * NN; i += kThreads) {
+    const int r = i / NN, n = i - r * NN;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
-    p.C[m * p.ldc + threadIdx.x] = s;
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w][r][n];
+    part[r][n] = s;
   }
+  cg::cluster_group cluster = cg::this_cluster();
+  if (splits > 1) cluster.sync();  // every rank's part[][] is written
+  else __syncthreads();
+  if (rank == 0) {
+    for (int i = threadIdx.x; i < R * (int)p.N; i += kThreads) {
+      const int r = i / (int)p.N, n = i - r * (int)p.N;
+      if (m0 + r < p.M) {
+        float s = part[r][n];
+        for (int q = 1; q < splits; ++q) s += *cluster.map_shared_rank(&part[r][n], q);
+        p.C[(m0 + r) * p.ldc + n] = s;
+      }
+    }
+  }
+  if (splits > 1) cluster.sync();  // peers keep their shared memory alive until rank 0 has read it
 }
 
 template <int NN>
@@ -55,7 +94,21 @@ __global__ void __launch_bounds__(kThreads) gemm_skinny_cols_kernel(const IgemmP
 #pragma unroll
   for (int n = 0; n < NN; ++n) acc[n] = 0.f;
   if (m < p.M) {
-    for (int64_t k = ty; k < p.K; k += KG) {
+    int64_t k = ty;
+    // four independent A loads in flight per thread before the dependent FMA chains
+    for (; k + 3 * KG < p.K; k += 4 * KG) {
+      float av[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) av[u] = __ldg(p.A + (k + u * KG) * p.a_cs + m);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* __restrict__ b = p.B + (k + u * KG) * p.b_rs;
+#pragma unroll
+        for (int n = 0; n < NN; ++n)
+          if (n < p.N) acc[n] = fmaf(av[u], __ldg(b + n * p.b_cs), acc[n]);
+      }
+    }
+    for (; k < p.K; k += KG) {
       const float av = __ldg(p.A + k * p.a_cs + m);  // a_rs == 1: coalesced along m
       const float* __restrict__ b = p.B + k * p.b_rs;
 #pragma unroll
@@ -92,10 +145,27 @@ int launch_gemm_skinny(const IgemmParams& p, cudaStream_t st) {
   if (!gemm_skinny_supported(p)) return set_error(SP_ERR_UNSUPPORTED, "gemm_skinny: unsupported");
   const bool wide = p.N > 8;
   if (p.a_cs == 1) {
-    if (wide)
-      gemm_skinny_rows_kernel<16><<<(unsigned)p.M, kThreads, 0, st>>>(p);
-    else
-      gemm_skinny_rows_kernel<8><<<(unsigned)p.M, kThreads, 0, st>>>(p);
+    // Long k axes: 4 rows per block (B is fetched once per 4 rows) and a cluster of up to 8
+    // CTAs over k, as long as every CTA keeps >= 1024 k values.
+    const bool tile_rows = p.K >= 4096 && p.M >= 64;
+    const unsigned blocks = (unsigned)(tile_rows ? (p.M + 3) / 4 : p.M);
+    unsigned splits = 1;
+    while (splits < 8 && (int64_t)(splits * 2) * 1024 <= p.K && blocks * splits < 2 * 148) splits *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks, splits, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = splits;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    auto kernel = wide ? (tile_rows ? gemm_skinny_rows_kernel<16, 4> : gemm_skinny_rows_kernel<16, 1>)
+                       : (tile_rows ? gemm_skinny_rows_kernel<8, 4> : gemm_skinny_rows_kernel<8, 1>);
+    if (cudaLaunchKernelEx(&cfg, kernel, p) != cudaSuccess)
+      return set_error(SP_ERR_DRIVER, "gemm_skinny: launch failed");
   } else {
     const unsigned blocks = (unsigned)((p.M + 31) / 32);
     if (wide)

@@ -69,6 +69,7 @@ int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_
                              cudaStream_t st);
 // `*reduced` = true when the kernel already summed its partial filters into dw
 int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial, float* dw,
-                             const sp_conv_geom& g, int blocks, cudaStream_t st, bool* reduced);
+                             const sp_conv_geom& g, int blocks, int precision, cudaStream_t st,
+                             bool* reduced);
 
 }  // namespace sp

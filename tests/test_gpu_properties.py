@@ -160,6 +160,24 @@ def test_matmul_full_size_vs_float64(precision):
     assert_close(g[bv], a.T @ ones, RTOL[precision], "dB")
 
 
+@pytest.mark.parametrize("m,k,n", [(256, 16384, 10), (67, 4100, 16), (700, 5000, 3), (8, 9000, 10)])
+def test_skinny_matmul_long_k(m, k, n):
+    """N <= 16 classifier GEMMs with a long k axis: cluster split-K rows kernel (forward, dA
+    goes to the tiled kernels) and the cols kernel (dB = A^T g), against float64."""
+    rng = np.random.default_rng(m + k + n)
+    a, b = rng.random((m, k)) - 0.5, rng.random((k, n)) - 0.5
+    av, bv = sp.Variable(a), sp.Variable(b)
+    y = sp.matmul(av, bv)
+    assert_close(y.array, a @ b, 2e-5, f"skinny {m}x{k}x{n}")
+    gy = rng.random((m, n)) - 0.5
+    g = sp.get_gradients(sp.mul(y, sp.Variable(gy)))
+    assert_close(g[bv], a.T @ gy, 2e-5, "skinny dB")
+    assert_close(g[av], gy @ b.T, 2e-3, "skinny dA")
+    # deterministic: a second evaluation is bit-identical
+    y2 = sp.matmul(av, bv)
+    assert np.array_equal(np.asarray(y.array), np.asarray(y2.array))
+
+
 def test_elementwise_checksums_full_size():
     rng = np.random.default_rng(2)
     x = rng.random((128, 30, 30, 32)) - 0.5
@@ -233,4 +251,42 @@ def test_two_sm_kernels_on_random_geometries(policy):
             assert_close(g[wv], dw0, RTOL["tf32"], what + " dW")
     finally:
         core.debug_set_kernel_policy(0)
+        sp.set_precision(old)
+
+
+def test_rgb_first_layer_kernels_on_random_geometries():
+    """Fuzz the first-layer (C = 3, 3x3) kernels in TF32 mode -- the tensor-core filter gradient
+    (mma.sync over padded-linear rows) and the CUDA-core forward -- against the float64 oracle:
+    image sizes from 1x1 up, both paddings, every eligible K, batches that leave tiles ragged.
+    Stride-2 and K = 8 cases exercise the dispatch back to the CUDA-core gradient kernel."""
+    from oracle import numpy_path as orc
+
+    old = sp.get_precision()
+    sp.set_precision("tf32")
+    core.debug_set_kernel_policy(0)
+    rng0 = np.random.default_rng(77)
+    try:
+        for i in range(36):
+            n = int(rng0.choice([1, 2, 7, 33]))
+            h, w = int(rng0.integers(1, 41)), int(rng0.integers(1, 41))
+            k = int(rng0.choice([8, 16, 32, 64]))
+            pad = str(rng0.choice(["SAME", "VALID"]))
+            s = (2, 2) if rng0.random() < 0.15 else (1, 1)
+            if pad == "VALID" and (h < 3 or w < 3):
+                continue
+            rng = np.random.default_rng(500 + i)
+            x, wt = rng.random((n, h, w, 3)) - 0.5, rng.random((3, 3, 3, k)) - 0.5
+            xv, wv = sp.Variable(x), sp.Variable(wt)
+            y = sp.conv2d(xv, wv, pad, s)
+            gy = rng.random(y.shape) - 0.5
+            g = sp.get_gradients(sp.mul(y, sp.Variable(gy)))
+            y0, dx0, dw0 = orc.conv2d_grads(x, wt, gy, pad, s)
+            what = f"rgb geometry {i}: x{(n, h, w, 3)} k{k} {pad} s{s}"
+            assert_close(y.array, y0, RTOL["tf32"], what + " y")
+            assert_close(g[wv], dw0, RTOL["tf32"], what + " dW")
+            assert_close(g[xv], dx0, RTOL["tf32"], what + " dX")
+            # deterministic: fixed-order reductions
+            g2 = sp.get_gradients(sp.mul(sp.conv2d(xv, wv, pad, s), sp.Variable(gy)))
+            assert np.array_equal(np.asarray(g[wv]), np.asarray(g2[wv])), what
+    finally:
         sp.set_precision(old)
