@@ -36,7 +36,10 @@ def main():
     st = stream()
     rng = np.random.default_rng(0)
     rows = []
+    only = os.environ.get("SP_PROBE_ONLY")
     for name, xs, k, pad in SHAPES:
+        if only and name not in only.split(","):
+            continue
         x = rng.random(xs, dtype=np.float32) - 0.5
         w = rng.random((3, 3, 3, k), dtype=np.float32) - 0.5
         geom = _conv_plan(xs, w.shape, pad, (1, 1))[0]

@@ -230,7 +230,7 @@ int sp_conv2d_fprop(const float* x, const float* w, float* y, const sp_conv_geom
   if (p.M == 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
   if (sp::g_umma_policy == 0 && sp::small_c_supported(*g)) {
-    if (int rc = sp::launch_conv_fprop_smallc(x, w, y, *g, st)) return rc;
+    if (int rc = sp::launch_conv_fprop_smallc(x, w, y, *g, precision, st)) return rc;
     SP_CHECK_LAUNCH("conv2d_fprop(small C)");
     return 0;
   }

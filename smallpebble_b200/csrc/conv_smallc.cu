@@ -13,6 +13,7 @@
 //
 // Used for both precision modes when small_c_supported() holds (results are fp32-exact).
 #include <algorithm>
+#include <cstdlib>
 
 #include "igemm.cuh"
 
@@ -840,6 +841,116 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rgb3x3_mma_kernel(
   }
 }
 
+
+// Tensor-core RGB 3x3 forward (SP_PRECISION_TF32, stride 1): y[P, K] = patches[P, 27] * w[27, K]
+// on mma.sync.m16n8k8.tf32 with the same padded-linear input rows as the filter gradient above.
+// The whole filter lives in registers as B fragments (4 k-steps x K/8 n-tiles), a warp owns
+// 16 consecutive pixels of one output row per step: 16 shared loads + 4 K/8 MMAs + K/4 8-byte
+// stores per 16 pixels, against ~45 warp instructions per PIXEL for the CUDA-core kernel.
+struct RgbFpropPlan {
+  int rows;        // output rows per tile
+  int wv;          // virtual (padded) row width
+  int chunks;      // 16-pixel chunks per output row
+  int tiles_per_img;
+  int n_tiles;
+  int x_staged;    // (rows + 2) * wv * 3
+  int x_floats;    // staged + zeroed slack (one stage)
+};
+
+template <int KT>
+__global__ void __launch_bounds__(kThreads, KT == 4 ? 1 : 2) conv_fprop_rgb3x3_mma_kernel(
+    const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+    const __grid_constant__ sp_conv_geom g, const __grid_constant__ RgbFpropPlan pl) {
+  constexpr int K = 16 * KT, NJ = K / 8, KC = 27;
+  extern __shared__ __align__(16) float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+
+  for (int s = 0; s < 2; ++s)
+    for (int i = pl.x_staged + threadIdx.x; i < pl.x_floats; i += kThreads)
+      sm[s * pl.x_floats + i] = 0.f;
+
+  auto prefetch = [&](int tile_idx, int stage) {
+    const int n = tile_idx / pl.tiles_per_img;
+    const int oy0 = (tile_idx - n * pl.tiles_per_img) * pl.rows;
+    float* x_s = sm + stage * pl.x_floats;
+    const int xrow = pl.wv * 3, w3 = g.W * 3;
+    for (int i = threadIdx.x; i < pl.x_staged; i += kThreads) {
+      const int pr = i / xrow;
+      const int col3 = i - pr * xrow - 3 * g.pad_l;
+      const int iy = oy0 + pr - g.pad_t;
+      const bool in = (unsigned)iy < (unsigned)g.H && (unsigned)col3 < (unsigned)w3;
+      cp_async4_zfill(&x_s[i], in ? x + (int64_t)(n * g.H + iy) * w3 + col3 : x, in);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < pl.n_tiles) prefetch(blockIdx.x, 0);
+
+  // B fragments: b0 = w[8 s + t][8 j + gq], b1 = w[8 s + t + 4][8 j + gq]; rows >= 27 are zero
+  uint32_t bf[4][NJ][2];
+  int offa[4][2];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = 8 * s + t + 4 * h;
+      offa[s][h] = kk < KC ? (kk / 9) * pl.wv * 3 + kk % 9 : 0;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        bf[s][j][h] = kk < KC ? __float_as_uint(__ldg(w + kk * K + 8 * j + gq)) : 0u;
+    }
+  }
+
+  int stage = 0;
+  for (int tile = blockIdx.x; tile < pl.n_tiles; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    if (next < pl.n_tiles) {
+      prefetch(next, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t* x_u = reinterpret_cast<const uint32_t*>(sm + stage * pl.x_floats);
+    const int n = tile / pl.tiles_per_img;
+    const int oy0 = (tile - n * pl.tiles_per_img) * pl.rows;
+    const int units = min(pl.rows, g.OH - oy0) * pl.chunks;
+    for (int u = warp; u < units; u += kThreads / 32) {
+      const int r = u / pl.chunks;
+      const int xv0 = (u - r * pl.chunks) * 16;
+      const uint32_t* ab = x_u + 3 * (r * pl.wv + xv0 + gq);
+      float acc[NJ][4];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        uint32_t a[4];
+        a[0] = ab[offa[s][0]];
+        a[1] = ab[offa[s][0] + 24];
+        a[2] = ab[offa[s][1]];
+        a[3] = ab[offa[s][1] + 24];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) mma_tf32_m16n8k8(acc[j], a, bf[s][j]);
+      }
+      float* yrow = y + ((int64_t)(n * g.OH + oy0 + r) * g.OW + xv0 + gq) * K + 2 * t;
+      if (xv0 + gq < g.OW) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          *reinterpret_cast<float2*>(yrow + 8 * j) = make_float2(acc[j][0], acc[j][1]);
+      }
+      if (xv0 + gq + 8 < g.OW) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          *reinterpret_cast<float2*>(yrow + 8 * K + 8 * j) = make_float2(acc[j][2], acc[j][3]);
+      }
+    }
+    __syncthreads();
+    stage ^= 1;
+  }
+}
+
 }  // namespace
 
 bool small_c_supported(const sp_conv_geom& g) {
@@ -887,7 +998,12 @@ static RgbMmaPlan rgb_mma_plan(const sp_conv_geom& g, int max_blocks) {
   };
   const int max_stage = 100 * 1024 / 4;
   double best = -1.0;
+  static const int forced_rows = [] {  // bring-up knob: SP_RGB_WGRAD_ROWS=<rows per tile>
+    const char* e = getenv("SP_RGB_WGRAD_ROWS");
+    return e ? atoi(e) : 0;
+  }();
   for (int rows = std::min(g.OH, 64); rows >= 1; --rows) {
+    if (forced_rows > 0 && rows != std::min(forced_rows, g.OH)) continue;
     int q_pad, x_staged, x_floats;
     const int sf = stage_floats(rows, &q_pad, &x_staged, &x_floats);
     if (sf > max_stage) continue;
@@ -941,6 +1057,56 @@ static int launch_rgb_mma(const float* x, const float* gy, float* partial, float
   return 0;
 }
 
+static RgbFpropPlan rgb_fprop_plan(const sp_conv_geom& g, int slots) {
+  RgbFpropPlan pl = {};
+  if (!fixed_window(g) || g.sy != 1 || g.sx != 1 || !(g.K == 16 || g.K == 32 || g.K == 64))
+    return pl;
+  const int wv = g.OW + 2, chunks = (g.OW + 15) / 16, warps = kThreads / 32;
+  int64_t best = -1;
+  for (int rows = std::min(g.OH, 32); rows >= 1; --rows) {
+    const int x_staged = (rows + 2) * wv * 3;
+    const int x_floats = (3 * ((rows + 1) * wv + 16 * chunks) + 16 + 3) / 4 * 4;
+    if (std::max(x_staged, x_floats) * 2 * 4 > 96 * 1024) continue;
+    const int per_img = (g.OH + rows - 1) / rows;
+    const int64_t tiles = (int64_t)g.N * per_img;
+    if (tiles > 0x7fffffff) continue;
+    const int64_t blocks = std::min<int64_t>(slots, tiles);
+    const int64_t waves = (tiles + blocks - 1) / blocks;
+    // serial steps of the busiest warp: units per warp and ~1 unit of per-tile overhead
+    const int64_t cost = waves * ((rows * chunks + warps - 1) / warps + 1);
+    if (best < 0 || cost < best) {
+      best = cost;
+      pl.rows = rows;
+      pl.wv = wv;
+      pl.chunks = chunks;
+      pl.tiles_per_img = per_img;
+      pl.n_tiles = (int)tiles;
+      pl.x_staged = x_staged;
+      pl.x_floats = std::max(x_staged + 4, x_floats) / 4 * 4;
+    }
+  }
+  return pl;
+}
+
+template <int KT>
+static int launch_rgb_fprop_mma(const float* x, const float* w, float* y, const sp_conv_geom& g,
+                                cudaStream_t st) {
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int per_sm = KT == 4 ? 1 : 2;
+  const RgbFpropPlan pl = rgb_fprop_plan(g, per_sm * sms);
+  if (pl.rows == 0) return 1;
+  const size_t smem = (size_t)2 * pl.x_floats * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_fprop_rgb3x3_mma_kernel<KT>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_done = true;
+  }
+  const int blocks = std::min(per_sm * sms, pl.n_tiles);
+  conv_fprop_rgb3x3_mma_kernel<KT><<<blocks, kThreads, smem, st>>>(x, w, y, g, pl);
+  return 0;
+}
+
 int small_c_wgrad_blocks(const sp_conv_geom& g) {
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int64_t n_pix = (int64_t)g.N * g.OH * g.OW;
@@ -954,7 +1120,15 @@ int small_c_wgrad_blocks(const sp_conv_geom& g) {
 }
 
 int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_conv_geom& g,
-                             cudaStream_t st) {
+                             int precision, cudaStream_t st) {
+  if (precision == SP_PRECISION_TF32 && (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
+    // tensor-core kernel when the geometry qualifies (returns 1 when it does not)
+    const int rc = g.K == 16   ? launch_rgb_fprop_mma<1>(x, w, y, g, st)
+                   : g.K == 32 ? launch_rgb_fprop_mma<2>(x, w, y, g, st)
+                   : g.K == 64 ? launch_rgb_fprop_mma<4>(x, w, y, g, st)
+                               : 1;
+    if (rc <= 0) return rc;
+  }
   const int kc = g.KH * g.KW * g.C;
   const int k8 = (g.K + 7) / 8;
   const int pix_per_block = kThreads / k8;

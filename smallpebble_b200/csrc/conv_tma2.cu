@@ -41,18 +41,19 @@ namespace sp {
 namespace {
 
 constexpr int kStages = 6;                // most stages any mode uses (barrier array size)
-constexpr uint32_t kStageBytes = 32768;   // fprop/dgrad: A 16 KB + B <= 16 KB, 6 stages;
-                                          // wgrad: 64-pixel stages of 2 x 32 KB, 3 stages
+constexpr uint32_t kRingBytes = 208u * 1024u;  // stage ring: A 32 KB + B (N/2 x 64 k x 4 B) per
+                                               // stage -> 3 stages at N = 256, 4 at 128, 5 at 64
 constexpr int kThreads = 384;
 constexpr int kAccumCols = 256;           // TMEM columns per accumulator stage
-constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes;
+constexpr size_t kSmemBytes = 1024 + (size_t)kRingBytes + 4 * 4096;  // + epilogue tiles
 
 struct Tma2Params {
   int mode;            // kFprop / kDgrad / kWgrad
   int M;               // GEMM rows: output pixels (fprop), input pixels (dgrad), KH*KW*C (wgrad)
   int N;               // GEMM columns: Kout (fprop, wgrad), C (dgrad)
   int m_pairs;         // ceil(M / 256)
-  int n_tiles;         // ceil(N / 256)
+  int n_tiles;         // ceil(N / bn_tile)
+  int bn_tile;         // tile width: 256, or narrower when that would leave SM pairs idle
   int splits;          // wgrad: slices of the pixel (reduction) axis; else 1
   int total_tiles;
   int kblocks;         // k-blocks (of 32) per tile: taps * inner/32, or k_chunk/32 for wgrad
@@ -64,6 +65,8 @@ struct Tma2Params {
   int k_chunk;         // wgrad: pixels per split (multiple of 32)
   int k_total;         // wgrad: N*OH*OW
   int debug;           // experiments (SP_TMA2_DEBUG), unused by default
+  int stages;          // ring depth: narrow tiles are bound by the load round trip, not by the
+  uint32_t stage_bytes;  // tensor core, so whatever B does not need buys more stages in flight
   long long* trace;    // sp_debug_tma2_trace: clock64 stamps of cluster 0's leader CTA, or null
   float* C;
   int64_t ldc;
@@ -286,6 +289,32 @@ __device__ __forceinline__ void trace_at(const Tma2Params& p, bool on, int slot)
   if (on) p.trace[slot] = clock64();
 }
 
+// Epilogue store of one 32 x 32 accumulator block.  After tcgen05.ld lane i holds row i; storing
+// that directly makes every st.global.v4 touch 32 rows x 16 bytes (half-sector writes, 32 L2
+// requests per instruction: ~1200 cycles per block measured -- the exposed tail of small
+// problems, and write-request pressure on large ones).  The block is turned through a 4 KB
+// XOR-swizzled shared tile (conflict-free both ways) so that one instruction writes 4 rows x
+// 128 contiguous bytes.  rp[r] = address of row (lane / 8 + 4 r) at the tile's first column.
+constexpr uint32_t kEpiBytes = 4u * 4096u;  // one 4 KB tile per epilogue warp
+__device__ __forceinline__ void store_block_rows(uint8_t* tile, const uint32_t (&v)[32], int lane,
+                                                 float* const (&rp)[8], uint32_t ok_mask, int cb) {
+  float4* t4 = reinterpret_cast<float4*>(tile);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    t4[lane * 8 + (j ^ (lane & 7))] =
+        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+  __syncwarp();
+  const int chunk = lane & 7;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = (lane >> 3) + 4 * r;
+    const float4 val = t4[row * 8 + (chunk ^ (row & 7))];
+    if ((ok_mask >> r) & 1u) *reinterpret_cast<float4*>(rp[r] + cb + chunk * 4) = val;
+  }
+  __syncwarp();
+}
+
 struct TileCoord {
   int m_pair, n_tile, split, n0, bn, kblocks;
 };
@@ -295,8 +324,8 @@ __device__ __forceinline__ TileCoord tile_coord(const Tma2Params& p, int t) {
   const int r = t / p.m_pairs;
   c.n_tile = r % p.n_tiles;
   c.split = r / p.n_tiles;
-  c.n0 = c.n_tile * 256;
-  c.bn = min(256, p.N - c.n0);
+  c.n0 = c.n_tile * p.bn_tile;
+  c.bn = min(p.bn_tile, p.N - c.n0);
   c.kblocks = p.kblocks;
   if (p.mode == kWgrad) {
     // the last split stops at the end of the pixel axis: no k-block starts out of range
@@ -337,8 +366,6 @@ struct ModeCfg {
   static constexpr int kKStage = 64;
   static constexpr uint32_t kABytes = 128u * kKStage * 4u;            // 32 KB
   static constexpr uint32_t kHalfA = kABytes / 2;                     // one K-major 128 x 32 box
-  static constexpr uint32_t kStage = 2u * kABytes;                    // A + B (<= A bytes)
-  static constexpr int kStages = 3;
   static constexpr uint32_t kMnBlock = 128u * kKStage;                // bytes of one MN block
 };
 
@@ -349,7 +376,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   using Cfg = ModeCfg<MODE>;
   constexpr bool A_MN = (MODE == kWgrad);
   constexpr bool B_MN = (MODE != kDgrad);
-  constexpr int kS = Cfg::kStages;
+  const int kS = p.stages;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kStages + 4];
   __shared__ uint32_t tmem_slot;
@@ -438,7 +465,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
           const bool valid1 = MODE != kWgrad && (2 * st + 1) < tc.kblocks;
           const uint32_t fb = full0 + 8u * s;
-          const uint32_t a_tile = tiles + (uint32_t)s * Cfg::kStage;
+          const uint32_t a_tile = tiles + (uint32_t)s * p.stage_bytes;
           const uint32_t b_tile = a_tile + Cfg::kABytes;
           if (is_b) {
             if (rrb == bslot) {
@@ -541,7 +568,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           trace_at(p, tr && gkb < kTraceKb, 16 + 2 * kTraceKb + gkb);
           ++gkb;
           tc_fence_after();
-          const uint32_t a_tile = tiles + (uint32_t)s * Cfg::kStage;
+          const uint32_t a_tile = tiles + (uint32_t)s * p.stage_bytes;
           const uint32_t b_tile = a_tile + Cfg::kABytes;
           const bool valid1 = MODE == kWgrad || (2 * st + 1) < tc.kblocks;
           if (elect_one()) {
@@ -583,7 +610,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     // TMEM lane == tile row; warp w may only touch lane quadrant w % 4.
     const int quad = warp & 3;
     const uint32_t empty_leader0 = mapa(tmem_empty_bar(0), 0);
-    const bool vec_store = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool vec_store = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                           ((p.split_stride & 3) == 0);
+    uint8_t* epi_tile = smem_raw + (tiles - smem_u32(smem_raw)) + kRingBytes + quad * 4096;
     int it = 0;
     for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
       const TileCoord tc = tile_coord(p, tile);
@@ -591,25 +620,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       mbar_wait(tmem_full_bar(acc), ((uint32_t)it >> 1) & 1u);
       trace_at(p, tr && warp == kWarpEpi0 && it < 4, 6 + it);
       tc_fence_after();
-      const int m = (tc.m_pair * 2 + (int)rank) * 128 + quad * 32 + lane;
-      float* __restrict__ crow =
-          p.C + (int64_t)tc.split * p.split_stride + (int64_t)m * p.ldc + tc.n0;
+      const int m_base = (tc.m_pair * 2 + (int)rank) * 128 + quad * 32;
+      const int m = m_base + lane;
+      float* __restrict__ cbase =
+          p.C + (int64_t)tc.split * p.split_stride + (int64_t)m_base * p.ldc + tc.n0;
+      float* __restrict__ crow = cbase + (int64_t)lane * p.ldc;
+      float* rp[8];
+      uint32_t ok_mask = 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int row = (lane >> 3) + 4 * r;
+        rp[r] = cbase + (int64_t)row * p.ldc;
+        ok_mask |= (m_base + row < p.M ? 1u : 0u) << r;
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccumCols);
       for (int cb = 0; cb < tc.bn; cb += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
         tmem_ld_wait();
-        if (m < p.M) {
-          if (vec_store) {
+        if (vec_store) {
+          store_block_rows(epi_tile, v, lane, rp, ok_mask, cb);
+        } else if (m < p.M) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(crow + cb + j) =
-                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) crow[cb + j] = __uint_as_float(v[j]);
-          }
+          for (int j = 0; j < 32; ++j) crow[cb + j] = __uint_as_float(v[j]);
         }
       }
       tc_fence_before();
@@ -912,6 +945,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const int quad = warp & 3;
     const uint32_t empty_leader0 = mapa(tmem_empty_bar(0), 0);
     const bool vec_store = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    uint8_t* epi_tile = smem_raw + (strips - smem_u32(smem_raw)) + 2u * p.strip_bytes +
+                        (uint32_t)SB * 2u * p.b_bytes + quad * 4096;
     int it = 0;
     for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
       const int m_pair = tile % p.m_pairs;
@@ -931,22 +966,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const bool valid = n < p.N_img && yv < p.OHo && xv < p.OWo;
       float* __restrict__ crow =
           p.C + ((int64_t)(n * p.OHo + yv) * p.OWo + xv) * p.ldc + n0;
+      // row (lane / 8 + 4 r) of this warp's block belongs to that lane: fetch its address
+      float* rp[8];
+      uint32_t ok_mask = 0;
+      {
+        const unsigned long long mine = reinterpret_cast<unsigned long long>(crow);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int src = (lane >> 3) + 4 * r;
+          rp[r] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, mine, src));
+          ok_mask |= (__shfl_sync(0xffffffffu, valid ? 1u : 0u, src)) << r;
+        }
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccumCols);
       for (int cb = 0; cb < bn; cb += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
         tmem_ld_wait();
-        if (valid) {
-          if (vec_store) {
+        if (vec_store) {
+          store_block_rows(epi_tile, v, lane, rp, ok_mask, cb);
+        } else if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(crow + cb + j) =
-                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) crow[cb + j] = __uint_as_float(v[j]);
-          }
+          for (int j = 0; j < 32; ++j) crow[cb + j] = __uint_as_float(v[j]);
         }
       }
       tc_fence_before();
@@ -1150,7 +1191,19 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
   p.M = (int)ip.M;
   p.N = (int)ip.N;
   p.m_pairs = (p.M + 255) / 256;
-  p.n_tiles = (p.N + 255) / 256;
+  p.bn_tile = p.N >= 256 ? 256 : p.N;
+  {
+    // Narrower tiles were tried for under-filled grids (CIFAR conv3: 13 tiles on 74 pairs) and
+    // measured no faster (12.4 vs 12.5 us): the k loop of a lone tile runs at the fixed
+    // per-stage cost of the MMA-issuing thread, not at the tensor pipe.  Kept as a knob.
+    static const int forced = [] {  // SP_TMA2_BN=<tile width, multiple of 64 dividing N>
+      const char* e = getenv("SP_TMA2_BN");
+      return e ? atoi(e) : 0;
+    }();
+    if (forced >= 64 && forced < p.bn_tile && forced % 64 == 0 && p.N % forced == 0)
+      p.bn_tile = forced;
+  }
+  p.n_tiles = (p.N + p.bn_tile - 1) / p.bn_tile;
   p.splits = ip.k_splits > 1 ? ip.k_splits : 1;
   p.total_tiles = p.m_pairs * p.n_tiles * p.splits;
   p.KW = g.KW;
@@ -1160,11 +1213,20 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
   p.split_stride = ip.k_splits > 1 ? ip.split_stride_c : 0;
   alignas(64) CUtensorMap tmA, tmB;
   bool ok = true;
-  // every tile has the same width: N <= 256, or N a multiple of 256 (conv_tma2_supported)
-  const int bnh_max = (p.N >= 256 ? 256 : p.N) / 2;
+  // every tile has the same width: N <= 256, or N a multiple of the tile width
+  const int bnh_max = p.bn_tile / 2;
   {
     const char* dbg = getenv("SP_TMA2_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
+  }
+  p.stage_bytes = 32768u + (uint32_t)bnh_max * 256u;
+  p.stages = std::min<int>(kStages, (int)(kRingBytes / p.stage_bytes));
+  {
+    static const int forced = [] {  // bring-up knob: SP_TMA2_STAGES=<ring depth>
+      const char* e = getenv("SP_TMA2_STAGES");
+      return e ? atoi(e) : 0;
+    }();
+    if (forced >= 2 && forced < p.stages) p.stages = forced;
   }
   p.trace = g_trace;
   const int up_h = (g.OH - 1) * g.sy + 1 - g.H - g.pad_t, up_w = (g.OW - 1) * g.sx + 1 - g.W - g.pad_l;
@@ -1291,7 +1353,7 @@ HaloPlan halo_plan(int mode, const sp_conv_geom& g, int N) {
   }
   size_t nb = (budget - 2 * (size_t)h.strip_bytes) / (2 * (size_t)h.b_bytes);
   h.b_stages = (int)std::min<size_t>(nb, kMaxBStages);
-  h.smem = 1024 + 2 * (size_t)h.strip_bytes + (size_t)h.b_stages * 2 * h.b_bytes;
+  h.smem = 1024 + 2 * (size_t)h.strip_bytes + (size_t)h.b_stages * 2 * h.b_bytes + kEpiBytes;
   h.ok = true;
   return h;
 }
@@ -1382,9 +1444,9 @@ int launch_conv_halo2(int mode, const IgemmParams& ip, cudaStream_t st) {
     cudaError_t e =
         mode == kFprop
             ? cudaFuncSetAttribute(conv_halo2_kernel<kFprop>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024)
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024)
             : cudaFuncSetAttribute(conv_halo2_kernel<kDgrad>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
     if (e != cudaSuccess)
       return set_error((int)e, "cudaFuncSetAttribute(conv_halo2) failed: %s", cudaGetErrorString(e));
     attr_done[which] = true;

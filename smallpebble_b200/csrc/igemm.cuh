@@ -66,7 +66,7 @@ int launch_gemm_skinny(const IgemmParams& p, cudaStream_t stream);
 bool small_c_supported(const sp_conv_geom& g);
 int small_c_wgrad_blocks(const sp_conv_geom& g);
 int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_conv_geom& g,
-                             cudaStream_t st);
+                             int precision, cudaStream_t st);
 // `*reduced` = true when the kernel already summed its partial filters into dw
 int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial, float* dw,
                              const sp_conv_geom& g, int blocks, int precision, cudaStream_t st,

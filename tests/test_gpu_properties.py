@@ -160,7 +160,7 @@ def test_matmul_full_size_vs_float64(precision):
     assert_close(g[bv], a.T @ ones, RTOL[precision], "dB")
 
 
-@pytest.mark.parametrize("m,k,n", [(256, 16384, 10), (67, 4100, 16), (700, 5000, 3), (8, 9000, 10)])
+@pytest.mark.parametrize("m,k,n", [(256, 16384, 10), (67, 4100, 13), (700, 5000, 3), (8, 9000, 10)])
 def test_skinny_matmul_long_k(m, k, n):
     """N <= 16 classifier GEMMs with a long k axis: cluster split-K rows kernel (forward, dA
     goes to the tiled kernels) and the cols kernel (dB = A^T g), against float64."""
