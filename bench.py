@@ -330,9 +330,11 @@ def run_ours(args):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(steps):
             _abi.prof.begin_step()
             step_fn(i)
+        timed.host_issue_ms = (time.perf_counter() - t0) * 1e3 / max(steps, 1)
         e1.record()
         torch.cuda.synchronize()
         return [e0.elapsed_time(e1)]
@@ -385,6 +387,7 @@ def run_ours(args):
     sampler.mark_begin()
     wall0 = time.perf_counter()
     step_ms = timed(step_resident, args.steps)
+    host_issue_ms = timed.host_issue_ms
     sync_all()
     wall = time.perf_counter() - wall0
     sampler.mark_end()
@@ -590,6 +593,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "abi_calls_per_step": calls_per_step,
         "wall_s_timed_region": wall,
+        "host_issue_ms_per_step": host_issue_ms,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "top_calls_one_step_ms": profile_summary,

@@ -84,3 +84,45 @@ t0 = time.perf_counter()
 for _ in range(50):
     float(loss.array)
 print(f"scalar D2H read: {1e6 * (time.perf_counter() - t0) / 50:.1f} us")
+
+# ---- where the HOST time of a step goes: C-ABI calls (driver launch included) vs Python --------
+# Each step is followed by a sync so the launch queue never fills: the per-step wall time up to
+# the last call is pure host issue time.
+from smallpebble_b200 import _abi  # noqa: E402
+
+acc = {}
+
+
+def _timed(name, fn):
+    def call(*a):
+        t = time.perf_counter_ns()
+        fn(*a)
+        d = time.perf_counter_ns() - t
+        e = acc.setdefault(name, [0, 0])
+        e[0] += d
+        e[1] += 1
+    return call
+
+
+torch.cuda.synchronize()
+n = 200
+host_ns = 0
+for _ in range(n):
+    t0 = time.perf_counter_ns()
+    step()
+    host_ns += time.perf_counter_ns() - t0
+    torch.cuda.synchronize()
+print(f"host issue time, device idle at step start: {host_ns / n / 1e3:.1f} us/step")
+for name in [k for k in _abi.f.__dict__ if k in _abi.SIGNATURES]:
+    setattr(_abi.f, name, _timed(name, getattr(_abi.f, name)))
+host_ns = 0
+for _ in range(n):
+    t0 = time.perf_counter_ns()
+    step()
+    host_ns += time.perf_counter_ns() - t0
+    torch.cuda.synchronize()
+total_abi = sum(v[0] for v in acc.values())
+print(f"with call timers: {host_ns / n / 1e3:.1f} us/step; inside C-ABI calls {total_abi / n / 1e3:.1f} us/step "
+      f"({sum(v[1] for v in acc.values()) / n:.0f} calls/step)")
+for name, (ns, cnt) in sorted(acc.items(), key=lambda kv: -kv[1][0]):
+    print(f"   {name:28s} {cnt / n:5.1f} calls/step  {ns / cnt / 1e3:6.2f} us/call  {ns / n / 1e3:6.1f} us/step")

@@ -16,7 +16,6 @@ import ctypes as C
 import functools
 import math
 import numbers
-import sys
 import weakref
 
 import numpy as np
@@ -94,17 +93,70 @@ def _host_dtype(a: np.ndarray) -> np.dtype:
 
 # Free list in front of torch's caching allocator.  A training step allocates the same ~35
 # buffer sizes over and over; recycling the torch buffers by exact byte size turns each
-# `DeviceArray.empty` from a ~2 us torch.empty call into a dict lookup (the README loop is
-# host-bound on a B200).  Safety: a buffer goes back only when the dying DeviceArray holds the
-# LAST reference to it (views and in-place rebinding share buffers), everything runs on one
-# stream so reuse is stream-ordered, and the list is bypassed while a CUDA graph is being
-# recorded (graph-private memory must come from torch's capture pool).
-_free_blocks = {}            # nbytes -> [torch uint8 tensor]
-_free_bytes = 0
+# `DeviceArray.empty` from a ~2 us torch.empty call into a stack pop (the README loop is
+# host-bound on a B200).  A recyclable buffer is held through a Block object (`_buf`): arrays
+# and views share the Block, and when the LAST reference to it dies the Block's destructor
+# hands the torch tensor to the per-size stack instead of freeing it.  Everything runs on one
+# stream, so reuse is stream-ordered; the pool is bypassed while a CUDA graph is being recorded
+# (graph-private memory must come from torch's capture pool).  The Block type and the stacks
+# live in C (csrc/fastcall.c: no Python-level __del__ on the hot path); `_PyBlock` below is the
+# same thing in Python for when that module is not built.
 _POOL_MAX_BLOCK = 64 << 20
 _POOL_MAX_TOTAL = 2 << 30
 _pool_bypass = 0
-_getrefcount = sys.getrefcount
+
+
+class _PyBlock:
+    __slots__ = ("tensor", "ptr", "nbytes", "recycle")
+
+    def __init__(self, tensor, ptr, nbytes, recycle):
+        self.tensor, self.ptr, self.nbytes, self.recycle = tensor, ptr, nbytes, recycle
+
+    def __del__(self):
+        try:
+            if self.recycle and not _pool_bypass and _py_pool["bytes"] + self.nbytes <= _POOL_MAX_TOTAL:
+                _py_pool["blocks"].setdefault(self.nbytes, []).append((self.tensor, self.ptr))
+                _py_pool["bytes"] += self.nbytes
+        except Exception:  # interpreter shutdown: module globals may be gone
+            pass
+
+
+_py_pool = {"blocks": {}, "bytes": 0}
+
+
+def _py_pool_alloc(nbytes):
+    if _pool_bypass:
+        return None
+    bucket = _py_pool["blocks"].get(nbytes)
+    if not bucket:
+        return None
+    tensor, ptr = bucket.pop()
+    _py_pool["bytes"] -= nbytes
+    return _PyBlock(tensor, ptr, nbytes, 1)
+
+
+def _py_pool_trim():
+    _py_pool["blocks"].clear()
+    _py_pool["bytes"] = 0
+
+
+def _py_pool_stats():
+    return sum(len(v) for v in _py_pool["blocks"].values()), _py_pool["bytes"]
+
+
+_fast = _abi._load_fast()
+if _fast is not None and hasattr(_fast, "pool_alloc"):
+    _pool_alloc, _block_new = _fast.pool_alloc, _fast.block_new
+    _pool_trim, _pool_stats, _pool_set_bypass = _fast.pool_trim, _fast.pool_stats, _fast.pool_bypass
+else:
+    _pool_alloc, _block_new = _py_pool_alloc, _PyBlock
+    _pool_trim, _pool_stats = _py_pool_trim, _py_pool_stats
+    _pool_set_bypass = lambda delta: None  # noqa: E731 - the Python pool reads _pool_bypass
+
+
+def pool_stats():
+    """(buffers, bytes) currently waiting in the free list."""
+    return _pool_stats()
 
 
 class pool_bypass:
@@ -113,17 +165,17 @@ class pool_bypass:
     def __enter__(self):
         global _pool_bypass
         _pool_bypass += 1
+        _pool_set_bypass(1)
 
     def __exit__(self, *exc):
         global _pool_bypass
         _pool_bypass -= 1
+        _pool_set_bypass(-1)
 
 
 def trim_pool() -> None:
     """Hand every recycled buffer back to torch's allocator."""
-    global _free_bytes
-    _free_blocks.clear()
-    _free_bytes = 0
+    _pool_trim()
     _scalar_ones.clear()
 
 
@@ -142,8 +194,12 @@ def scalar_one(shape):
     return arr, False
 
 
+_new_array = object.__new__
+_prod = math.prod
+
+
 class DeviceArray:
-    __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "_pk", "_thunk", "_tag",
+    __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "_thunk", "_tag",
                  "__weakref__")
     __array_priority__ = 1000.0
 
@@ -154,52 +210,35 @@ class DeviceArray:
         self._buf = buf
         self._ptr = ptr
         self._host = host
-        self._pk = 0
         self._thunk = None
         self._tag = None
-
-    def __del__(self):
-        # recycle the buffer if this was its last user (refs: slot, local, getrefcount arg)
-        global _free_bytes
-        try:
-            pk = self._pk
-            if pk and not _pool_bypass:
-                buf = self._buf
-                if buf is not None and _getrefcount(buf) == 3 and _free_bytes + pk <= _POOL_MAX_TOTAL:
-                    bucket = _free_blocks.get(pk)
-                    if bucket is None:
-                        _free_blocks[pk] = [buf]
-                    else:
-                        bucket.append(buf)
-                    _free_bytes += pk
-        except Exception:  # interpreter shutdown: module globals may be gone
-            pass
 
     # ---- construction ---------------------------------------------------------------------
     @staticmethod
     def empty(shape, dtype=FLOAT) -> "DeviceArray":
         dev = _device if _device is not None else require_cuda()
-        self = object.__new__(DeviceArray)
-        self.shape = shape = tuple(shape)
-        self.dtype = dtype = dtype if dtype is FLOAT else np.dtype(dtype)
-        self.size = size = math.prod(shape)
+        self = _new_array(DeviceArray)
+        if type(shape) is not tuple:
+            shape = tuple(shape)
+        self.shape = shape
+        if dtype is not FLOAT:
+            dtype = np.dtype(dtype)
+        self.dtype = dtype
+        self.size = size = _prod(shape)
         self._host = None
         self._thunk = None
         self._tag = None
         nbytes = (size or 1) * dtype.itemsize
         if _pool_bypass or nbytes > _POOL_MAX_BLOCK:
-            self._pk = 0
             self._buf = buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
+            self._ptr = buf.data_ptr()
         else:
-            self._pk = nbytes
-            bucket = _free_blocks.get(nbytes)
-            if bucket:
-                global _free_bytes
-                _free_bytes -= nbytes
-                self._buf = buf = bucket.pop()
-            else:
-                self._buf = buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
-        self._ptr = buf.data_ptr()
+            blk = _pool_alloc(nbytes)
+            if blk is None:
+                buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
+                blk = _block_new(buf, buf.data_ptr(), nbytes, 1)
+            self._buf = blk  # shared by views; the last holder's death recycles the buffer
+            self._ptr = blk.ptr
         return self
 
     @staticmethod
@@ -216,7 +255,6 @@ class DeviceArray:
         self._buf = None
         self._ptr = None
         self._host = None
-        self._pk = 0
         self._thunk = thunk
         self._tag = tag
         return self
@@ -230,9 +268,7 @@ class DeviceArray:
         thunk = self._thunk
         out = DeviceArray.empty(self.shape)
         thunk(out)
-        # adopt the buffer (the temporary `out` must not hand it to the free list when it dies)
-        self._buf, self._ptr, self._pk = out._buf, out._ptr, out._pk
-        out._pk = 0
+        self._buf, self._ptr = out._buf, out._ptr  # adopt the buffer
         self._thunk = None
         self._tag = None
 
@@ -379,7 +415,6 @@ class DeviceArray:
         if self._ptr is None:
             return DeviceArray(shape, self.dtype, host=self._host.reshape(shape))
         out = DeviceArray(shape, self.dtype, self._buf, self._ptr)  # shares the buffer
-        out._pk = self._pk  # whichever of the two dies last recycles it
         return out
 
     def copy(self) -> "DeviceArray":
@@ -444,7 +479,6 @@ class DeviceArray:
 
     def _rebind(self, other: "DeviceArray"):
         self._buf, self._ptr, self._host = other._buf, other.ptr, None
-        self._pk = other._pk
         return self
 
     def __iadd__(self, o):
@@ -725,11 +759,11 @@ def _norm_axes(axis, ndim):
     return tuple(axes)
 
 
-def reduce_sum(a: DeviceArray, axis=None, keepdims=False) -> DeviceArray:
-    """np.sum(a, axis): runs of adjacent reduced axes are folded one kernel at a time."""
-    axes = _norm_axes(axis, a.ndim)
-    shape = list(a.shape)
-    cur = a
+@functools.lru_cache(maxsize=1024)
+def _reduce_plan(shape, axis, keepdims):
+    """((outer, red, inner) per kernel, final shape, any axis reduced?) of np.sum(a, axis)."""
+    axes = _norm_axes(axis, len(shape))
+    shape = list(shape)
     # fold runs from the last axis backwards so earlier axis numbers stay valid
     runs, i = [], len(axes) - 1
     while i >= 0:
@@ -739,20 +773,31 @@ def reduce_sum(a: DeviceArray, axis=None, keepdims=False) -> DeviceArray:
             lo = axes[i]
         runs.append((lo, hi))
         i -= 1
+    steps = []
     for lo, hi in runs:
-        outer = math.prod(shape[:lo])
-        red = math.prod(shape[lo:hi + 1])
-        inner = math.prod(shape[hi + 1:])
-        out = DeviceArray.empty((outer, inner))
-        if outer * inner:
-            F.sp_reduce_sum(cur.ptr, out._ptr, outer, red, inner, stream())
+        steps.append((math.prod(shape[:lo]), math.prod(shape[lo:hi + 1]), math.prod(shape[hi + 1:])))
         shape[lo:hi + 1] = [1] * (hi + 1 - lo)
-        cur = out
     if keepdims:
         final = tuple(shape)
     else:
         final = tuple(n for i, n in enumerate(shape) if i not in axes)
-    return cur.reshape(final) if axes else a.copy()
+    return tuple(steps), final, bool(axes)
+
+
+def reduce_sum(a: DeviceArray, axis=None, keepdims=False) -> DeviceArray:
+    """np.sum(a, axis): runs of adjacent reduced axes are folded one kernel at a time."""
+    if axis is not None and not isinstance(axis, (tuple, numbers.Integral)):
+        axis = tuple(int(ax) for ax in axis)  # lists / arrays of axes: hashable for the cache
+    steps, final, any_axis = _reduce_plan(a.shape, axis, bool(keepdims))
+    if not any_axis:
+        return a.copy()
+    cur = a
+    for outer, red, inner in steps:
+        out = DeviceArray.empty((outer, inner))
+        if outer * inner:
+            F.sp_reduce_sum(cur.ptr, out._ptr, outer, red, inner, stream())
+        cur = out
+    return cur.reshape(final)
 
 
 def max_all(a: DeviceArray) -> DeviceArray:

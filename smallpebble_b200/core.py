@@ -21,7 +21,9 @@ Differences from the reference, all internal:
 from __future__ import annotations
 
 import functools
+import itertools
 import math
+import operator
 import os
 
 import numpy as np
@@ -79,13 +81,18 @@ def set_fusion(enabled: bool) -> None:
 # --------------------------------------------------------------------------------------------
 
 
+_serials = itertools.count()
+_serial_of = operator.attrgetter("_serial")
+
+
 class Variable:
     """A value in a differentiable computation: `.array` (a DeviceArray) and
     `.local_gradients = [(child_variable, fn(path_value) -> array), ...]` (sp.py:36-54)."""
 
     def __init__(self, array, local_gradients=None) -> None:
-        self.array = array
+        self._array = array if isinstance(array, DeviceArray) else DeviceArray.from_host(array)
         self.local_gradients = local_gradients if local_gradients else []
+        self._serial = next(_serials)  # construction order: get_gradients sorts the tape by it
 
     @property
     def array(self):
@@ -179,12 +186,8 @@ def _accumulate(gradients, owned, child, value):
 _eager_leaf_grads = os.environ.get("SP_EAGER_LEAF_GRADS", "0") == "1"
 
 
-def get_gradients(variable: Variable) -> dict:
-    """d(sum of `variable`)/d(node) for every node reachable from `variable` (sp.py:57-87).
-
-    Returns {Variable: DeviceArray}, keyed by identity, including `variable` itself (ones).
-    """
-    # reverse post-order of the tape DAG = parents before children
+def _tape_order_dfs(variable):
+    """Op nodes reachable from `variable`, parents before children (reverse post-order)."""
     order, seen, stack = [], {id(variable)}, [(variable, iter(variable.local_gradients))]
     while stack:
         node, it = stack[-1]
@@ -196,9 +199,38 @@ def get_gradients(variable: Variable) -> dict:
                 advanced = True
                 break
         if not advanced:
-            order.append(node)
+            if node.local_gradients:
+                order.append(node)
             stack.pop()
     order.reverse()
+    return order
+
+
+def get_gradients(variable: Variable) -> dict:
+    """d(sum of `variable`)/d(node) for every node reachable from `variable` (sp.py:57-87).
+
+    Returns {Variable: DeviceArray}, keyed by identity, including `variable` itself (ones).
+    """
+    # Parents before children.  Every Variable is numbered at construction and an op's result is
+    # constructed after its inputs, so descending serial numbers ARE a reverse topological order
+    # of the tape: collect the reachable op nodes with a plain stack and sort them (leaves have
+    # no edges to walk and are skipped).
+    seen, stack, order = {id(variable)}, [variable], []
+    while stack:
+        node = stack.pop()
+        edges = node.local_gradients
+        if edges:
+            order.append(node)
+            for child, _ in edges:
+                key = id(child)
+                if key not in seen:
+                    seen.add(key)
+                    if child.local_gradients:  # leaves have nothing to walk
+                        stack.append(child)
+    try:
+        order.sort(key=_serial_of, reverse=True)
+    except AttributeError:  # a Variable subclass that skipped Variable.__init__
+        order = _tape_order_dfs(variable)
 
     gradients = Gradients()
     seed_shape = variable.array.shape
@@ -210,8 +242,6 @@ def get_gradients(variable: Variable) -> dict:
     # gradient buffers nobody else aliases: safe to accumulate in place
     owned = {variable} if fresh else set()
     for node in order:
-        if not node.local_gradients:
-            continue
         path_value = dict.__getitem__(gradients, node)
         for child, multiply_by_locgrad in node.local_gradients:
             if (not child.local_gradients and not getattr(child, "is_learnable", False)
@@ -229,6 +259,11 @@ def get_gradients(variable: Variable) -> dict:
 
 def broadcastinfo(a_shape, b_shape):
     "Get which dimensions are added or repeated when `a` and `b` are broadcast (sp.py:659-684)."
+    return _broadcastinfo(tuple(a_shape), tuple(b_shape))
+
+
+@functools.lru_cache(maxsize=1024)
+def _broadcastinfo(a_shape, b_shape):
     ndim = max(len(a_shape), len(b_shape))
     pad_a, pad_b = ndim - len(a_shape), ndim - len(b_shape)
     ea = (1,) * pad_a + tuple(a_shape)
@@ -706,20 +741,31 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
     return Variable(y, [(images, grad_images), (kernels, grad_kernels)])
 
 
+_UINT8 = np.dtype(np.uint8)
+
+
+@functools.lru_cache(maxsize=256)
+def _pool_plan(x_shape, kernheight, kernwidth, stride_y, stride_x, padding):
+    """(kernel geometry arguments, output shape) of a pooling call: host integer logic that
+    is the same every step of a training loop."""
+    n_images, imheight, imwidth, n_channels = x_shape
+    pt, _, pl, _, outh, outw = _window_geometry(
+        imheight, imwidth, kernheight, kernwidth, stride_y, stride_x, padding)
+    geom = (n_images, imheight, imwidth, n_channels, kernheight, kernwidth, stride_y, stride_x,
+            pt, pl, outh, outw)
+    return geom, (n_images, outh, outw, n_channels)
+
+
 def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = "SAME",
               strides=[1, 1]) -> Variable:  # noqa: B006 (signature kept from sp.py:282-288)
     """Maxpooling on a `variable` of shape [n_images, imheight, imwidth, n_channels]
     (sp.py:282-300).  Zero padding takes part in the max and the first maximum in (dy, dx)
     order wins -- exactly what np.pad + np.argmax give the reference."""
     x = images.array
-    n_images, imheight, imwidth, n_channels = x.shape
     stride_y, stride_x = strides
-    pt, _, pl, _, outh, outw = _window_geometry(
-        imheight, imwidth, kernheight, kernwidth, stride_y, stride_x, padding)
-    y = DeviceArray.empty((n_images, outh, outw, n_channels))
-    idx = DeviceArray.empty((n_images, outh, outw, n_channels), np.uint8)
-    geom = (n_images, imheight, imwidth, n_channels, kernheight, kernwidth, stride_y, stride_x,
-            pt, pl, outh, outw)
+    geom, out_shape = _pool_plan(x.shape, kernheight, kernwidth, stride_y, stride_x, padding)
+    y = DeviceArray.empty(out_shape)
+    idx = DeviceArray.empty(out_shape, _UINT8)
     tag = x.pending_tag
     fused = tag is not None and tag[0] == "leaky_relu" and y.size > 0
     if fused:

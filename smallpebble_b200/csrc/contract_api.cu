@@ -10,6 +10,7 @@
 #include "igemm.cuh"
 
 namespace sp {
+int g_pdl = 1;  // programmatic dependent launch (common.cuh); set from SP_PDL below
 namespace {
 
 // 0 = policy (default), 1 = always tcgen05 when the shape is supported (tests),
@@ -19,6 +20,12 @@ int g_umma_policy = 0;
 int g_tma2_policy = 0;
 // halo-reuse variant of the 2-SM kernel: 0 = policy, 1 = whenever supported, 2 = never
 int g_halo_policy = 0;
+const int g_pdl_default = [] {
+  const char* e = getenv("SP_PDL");
+  const int on = (e && e[0] == '0') ? 0 : 1;
+  g_pdl = on;
+  return on;
+}();
 
 // The 2-SM TMA kernel (74 persistent CTA pairs over 256-row tiles) beats the 1-SM cp.async
 // kernel on every eligible shape measured back to back (profiles/r01_tma2_vs_umma1_b2b.txt:
@@ -59,9 +66,11 @@ IgemmParams base_params() {
 }
 
 // The halo-reuse variant moves 4-5x fewer activation bytes from L2.  Measured back to back
-// (profiles/r01_tma2_halo_b2b.txt) it wins on every N <= 128 layer with a real window
-// (VGG 64->64, 64->128, 128->128, CIFAR conv2) and loses at N = 256, where the per-tap B tiles
-// are the larger stream and the halo rows only add MMA work.
+// (profiles/r01_conv_b2b_v9.txt) it wins at N = 128 and at N = 64 when the activation tensor
+// has no more channels than that (VGG 64->64, 64->128 fprop, 128->128, CIFAR conv2 fprop); it
+// loses at N = 256, where the per-tap B tiles are the larger stream and the halo rows only add
+// MMA work, on narrow-N / wide-channel data gradients (VGG 64->128 dgrad: 101 vs 90 us, CIFAR
+// conv2 dgrad) and on grids that do not even fill the SM pairs once (CIFAR conv3).
 bool use_halo(int mode, const IgemmParams& p, int precision) {
   if (precision != SP_PRECISION_TF32 || g_umma_policy == 2 || g_halo_policy == 2) return false;
   if (mode != kFprop && mode != kDgrad) return false;
@@ -70,6 +79,10 @@ bool use_halo(int mode, const IgemmParams& p, int precision) {
   if (g_umma_policy == 1 || g_tma2_policy != 0) return false;  // tests pinned another kernel
   const sp_conv_geom& g = p.g;
   if (g.KH * g.KW < 4 || p.N > 128) return false;
+  const int a_channels = mode == kFprop ? g.C : g.K;
+  if (p.N < 128 && a_channels > p.N) return false;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  if ((p.M + 255) / 256 < sms / 2) return false;
   if (conv_halo2_efficiency(mode, p) < 0.5) return false;
   const double flop = 2.0 * (double)p.M * (double)p.N * (double)p.K;
   return flop >= 2.5e8;
@@ -128,7 +141,7 @@ extern "C" {
 int sp_debug_set_umma_policy(int policy) {
   // bits 0-1: kernel family policy; bit 4: conservative producer synchronisation;
   // bits 5-6: 2-SM TMA conv kernel (0 = size policy, 1 = whenever supported, 2 = never);
-  // bits 7-8: its halo-reuse variant (same encoding)
+  // bits 7-8: its halo-reuse variant (same encoding); bit 9: no programmatic dependent launch
   const int family = policy & 3;
   const int tma2 = (policy >> 5) & 3;
   const int halo = (policy >> 7) & 3;
@@ -137,6 +150,7 @@ int sp_debug_set_umma_policy(int policy) {
   sp::g_umma_policy = family;
   sp::g_tma2_policy = tma2;
   sp::g_halo_policy = halo;
+  sp::g_pdl = ((policy >> 9) & 1) ? 0 : sp::g_pdl_default;
   sp::igemm_umma_set_sync_mode((policy >> 4) & 1);
   return 0;
 }

@@ -334,6 +334,7 @@ template <bool CHECK>
 __global__ void __launch_bounds__(kThreads) conv_fprop_rgb3x3_tile4_kernel(
     const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
     const __grid_constant__ sp_conv_geom g, int k8) {
+  pdl_entry();
   constexpr int KC = 27, PX = 4, IN_W = (PX + 2) * 3;  // stride-1 only: 6 input pixels per row
   extern __shared__ float w_s[];                       // [KC][k8 * 8] zero padded
   const int kpad = k8 * 8;
@@ -861,6 +862,7 @@ template <int KT>
 __global__ void __launch_bounds__(kThreads, KT == 4 ? 1 : 2) conv_fprop_rgb3x3_mma_kernel(
     const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
     const __grid_constant__ sp_conv_geom g, const __grid_constant__ RgbFpropPlan pl) {
+  pdl_entry();
   constexpr int K = 16 * KT, NJ = K / 8, KC = 27;
   extern __shared__ __align__(16) float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1103,7 +1105,7 @@ static int launch_rgb_fprop_mma(const float* x, const float* w, float* y, const 
     attr_done = true;
   }
   const int blocks = std::min(per_sm * sms, pl.n_tiles);
-  conv_fprop_rgb3x3_mma_kernel<KT><<<blocks, kThreads, smem, st>>>(x, w, y, g, pl);
+  sp::launch_pdl(conv_fprop_rgb3x3_mma_kernel<KT>, dim3(blocks), dim3(kThreads), smem, st, x, w, y, g, pl);
   return 0;
 }
 
@@ -1139,9 +1141,9 @@ int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_
     const int64_t n_groups = (int64_t)g.N * g.OH * ((g.OW + 3) / 4);
     const int grid4 = wave_grid(n_groups, kThreads / k8, 4);
     if (needs_bounds_check(g))
-      conv_fprop_rgb3x3_tile4_kernel<true><<<grid4, kThreads, smem, st>>>(x, w, y, g, k8);
+      sp::launch_pdl(conv_fprop_rgb3x3_tile4_kernel<true>, dim3(grid4), dim3(kThreads), smem, st, x, w, y, g, k8);
     else
-      conv_fprop_rgb3x3_tile4_kernel<false><<<grid4, kThreads, smem, st>>>(x, w, y, g, k8);
+      sp::launch_pdl(conv_fprop_rgb3x3_tile4_kernel<false>, dim3(grid4), dim3(kThreads), smem, st, x, w, y, g, k8);
   } else if (fixed_window(g)) {
     if (needs_bounds_check(g))
       conv_fprop_smallc_fixed_kernel<3, 3, 3, true><<<grid, kThreads, smem, st>>>(x, w, y, g, k8);

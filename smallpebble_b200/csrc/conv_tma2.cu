@@ -395,6 +395,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   auto tmem_full_bar = [&](int a) { return bar0 + 8u * (2 * kStages + a); };
   auto tmem_empty_bar = [&](int a) { return bar0 + 8u * (2 * kStages + 2 + a); };
   const bool tr = p.trace != nullptr && cluster_id == 0 && leader && lane == 0;
+  pdl_trigger();  // launch_pdl(): the next kernel may start launching; it waits for us itself
   trace_at(p, tr && warp == 0, 0);
 
   if (t == 0) {
@@ -416,6 +417,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = uniform(tmem_slot);
+  // barriers, TMEM and descriptors are set up while the previous kernel was still running;
+  // nothing has touched global memory yet
+  pdl_wait();
   trace_at(p, tr && warp == 0, 1);
 
   if (warp < kAWarps || b_warp_slot(warp) >= 0) {
@@ -725,6 +729,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   auto stamp = [&](bool on, int slot) {
     if (on) p.trace[slot] = clock64();
   };
+  pdl_trigger();
   stamp(tr && warp == 0, 0);
 
   const uint32_t strips = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1302,7 +1307,7 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
                          cudaGetErrorString(e));                                                \
       attr_done = true;                                                                         \
     }                                                                                           \
-    kern<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, p);                                      \
+    launch_pdl(kern, grid, dim3(kThreads), kSmemBytes, st, tmA, tmB, p);                        \
   } while (0)
   if (mode == kFprop)
     SP_TMA2_LAUNCH(kFprop);
@@ -1452,9 +1457,9 @@ int launch_conv_halo2(int mode, const IgemmParams& ip, cudaStream_t st) {
     attr_done[which] = true;
   }
   if (mode == kFprop)
-    conv_halo2_kernel<kFprop><<<grid, kThreads, h.smem, st>>>(tmA, tmB, p);
+    launch_pdl(conv_halo2_kernel<kFprop>, grid, dim3(kThreads), h.smem, st, tmA, tmB, p);
   else
-    conv_halo2_kernel<kDgrad><<<grid, kThreads, h.smem, st>>>(tmA, tmB, p);
+    launch_pdl(conv_halo2_kernel<kDgrad>, grid, dim3(kThreads), h.smem, st, tmA, tmB, p);
   return 0;
 }
 

@@ -89,6 +89,7 @@ template <int OP>
 __global__ void __launch_bounds__(kThreads) unary_kernel(const float* __restrict__ x,
                                                          float* __restrict__ y, int64_t n,
                                                          float p, bool vec) {
+  pdl_entry();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kThreads) binary_flat_kernel(const float* __re
                                                                const float* __restrict__ b,
                                                                float* __restrict__ out,
                                                                int64_t n, bool vec) {
+  pdl_entry();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(kThreads) binary_rowvec_kernel(const float* __
                                                                  float* __restrict__ out,
                                                                  int64_t rows, int64_t cols4,
                                                                  bool swap) {
+  pdl_entry();
   const int64_t total = rows * cols4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(kThreads) binary_strided_kernel(const float* _
                                                                   const float* __restrict__ b,
                                                                   float* __restrict__ out,
                                                                   int64_t n, Dims d) {
+  pdl_entry();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     int64_t rem = i, oa = 0, ob = 0;
@@ -224,6 +228,7 @@ __global__ void __launch_bounds__(kThreads) strided_copy_kernel(const float* __r
 __global__ void __launch_bounds__(kThreads) accumulate_kernel(float* __restrict__ dst,
                                                               const float* __restrict__ src,
                                                               int64_t n, bool vec) {
+  pdl_entry();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(kThreads) accumulate_kernel(float* __restrict_
 __global__ void __launch_bounds__(kThreads) leaky_fwd_kernel(const float* __restrict__ x,
                                                              float* __restrict__ y, int64_t n,
                                                              float alpha, bool vec) {
+  pdl_entry();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
@@ -272,6 +278,7 @@ __global__ void __launch_bounds__(kThreads) leaky_bwd_kernel(const float* __rest
                                                              const float* __restrict__ x,
                                                              float* __restrict__ dx, int64_t n,
                                                              float alpha, bool vec) {
+  pdl_entry();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
@@ -300,7 +307,7 @@ inline int ew_grid(int64_t n) { return sp::wave_grid(n, kThreads * 4, 8); }
 template <int OP>
 int launch_unary(const float* x, float* y, int64_t n, float p, cudaStream_t st) {
   const bool vec = aligned16(x) && aligned16(y);
-  unary_kernel<OP><<<ew_grid(n), kThreads, 0, st>>>(x, y, n, p, vec);
+  sp::launch_pdl(unary_kernel<OP>, dim3(ew_grid(n)), dim3(kThreads), 0, st, x, y, n, p, vec);
   return 0;
 }
 
@@ -310,17 +317,17 @@ int launch_binary(const float* a, const float* b, float* out, const Dims& d, cud
   for (int i = 0; i < d.ndim; ++i) n *= d.shape[i];
   const bool al = aligned16(a) && aligned16(b) && aligned16(out);
   if (d.ndim == 1 && d.s0[0] == 1 && d.s1[0] == 1) {
-    binary_flat_kernel<OP><<<ew_grid(n), kThreads, 0, st>>>(a, b, out, n, al);
+    sp::launch_pdl(binary_flat_kernel<OP>, dim3(ew_grid(n)), dim3(kThreads), 0, st, a, b, out, n, al);
   } else if (d.ndim == 2 && al && d.shape[1] % 4 == 0 && d.s0[1] == 1 && d.s1[1] == 1 &&
              d.s0[0] == d.shape[1] && d.s1[0] == 0) {
-    binary_rowvec_kernel<OP><<<ew_grid(n), kThreads, 0, st>>>(a, b, out, d.shape[0],
+    sp::launch_pdl(binary_rowvec_kernel<OP>, dim3(ew_grid(n)), dim3(kThreads), 0, st, a, b, out, d.shape[0],
                                                             d.shape[1] / 4, false);
   } else if (d.ndim == 2 && al && d.shape[1] % 4 == 0 && d.s0[1] == 1 && d.s1[1] == 1 &&
              d.s1[0] == d.shape[1] && d.s0[0] == 0) {
-    binary_rowvec_kernel<OP><<<ew_grid(n), kThreads, 0, st>>>(b, a, out, d.shape[0],
+    sp::launch_pdl(binary_rowvec_kernel<OP>, dim3(ew_grid(n)), dim3(kThreads), 0, st, b, a, out, d.shape[0],
                                                             d.shape[1] / 4, true);
   } else {
-    binary_strided_kernel<OP><<<ew_grid(n), kThreads, 0, st>>>(a, b, out, n, d);
+    sp::launch_pdl(binary_strided_kernel<OP>, dim3(ew_grid(n)), dim3(kThreads), 0, st, a, b, out, n, d);
   }
   return 0;
 }
@@ -375,16 +382,14 @@ int sp_ewise_binary(int op, const float* a, const int64_t* stride_a, const float
 
 int sp_accumulate(float* dst, const float* src, int64_t n, sp_stream_t stream) {
   if (n <= 0) return 0;
-  accumulate_kernel<<<ew_grid(n), kThreads, 0, sp::as_stream(stream)>>>(
-      dst, src, n, aligned16(dst) && aligned16(src));
+  sp::launch_pdl(accumulate_kernel, dim3(ew_grid(n)), dim3(kThreads), 0, sp::as_stream(stream), dst, src, n, aligned16(dst) && aligned16(src));
   SP_CHECK_LAUNCH("accumulate");
   return 0;
 }
 
 int sp_leaky_relu_fwd(const float* x, float* y, int64_t n, float alpha, sp_stream_t stream) {
   if (n <= 0) return 0;
-  leaky_fwd_kernel<<<ew_grid(n), kThreads, 0, sp::as_stream(stream)>>>(
-      x, y, n, alpha, aligned16(x) && aligned16(y));
+  sp::launch_pdl(leaky_fwd_kernel, dim3(ew_grid(n)), dim3(kThreads), 0, sp::as_stream(stream), x, y, n, alpha, aligned16(x) && aligned16(y));
   SP_CHECK_LAUNCH("leaky_relu_fwd");
   return 0;
 }
@@ -392,8 +397,7 @@ int sp_leaky_relu_fwd(const float* x, float* y, int64_t n, float alpha, sp_strea
 int sp_leaky_relu_bwd(const float* g, const float* x, float* dx, int64_t n, float alpha,
                       sp_stream_t stream) {
   if (n <= 0) return 0;
-  leaky_bwd_kernel<<<ew_grid(n), kThreads, 0, sp::as_stream(stream)>>>(
-      g, x, dx, n, alpha, aligned16(g) && aligned16(x) && aligned16(dx));
+  sp::launch_pdl(leaky_bwd_kernel, dim3(ew_grid(n)), dim3(kThreads), 0, sp::as_stream(stream), g, x, dx, n, alpha, aligned16(g) && aligned16(x) && aligned16(dx));
   SP_CHECK_LAUNCH("leaky_relu_bwd");
   return 0;
 }

@@ -9,6 +9,13 @@
  *   fn = _sp_fastcall.bind(address, "ppplf p", name, on_error, counts_launch)
  *   fn(x_ptr, y_ptr, n, alpha, stream)      -> None, or calls on_error(name, rc)
  *
+ * It also holds the free list in front of torch's caching allocator (array.py): a Block owns
+ * one device buffer (a reference to the torch tensor + its address); when the LAST reference
+ * to a Block goes away -- the arrays and views sharing it are all dead -- its tp_dealloc hands
+ * the buffer to a per-size stack instead of freeing it, and pool_alloc() pops from there.
+ * Doing this in tp_dealloc replaces a Python-level __del__ on every DeviceArray (38 per
+ * training step) and a refcount heuristic with the reference count itself.
+ *
  * Signature letters: 'p' pointer / integer of any width (int, None = NULL, or an object with
  * the buffer protocol such as a ctypes array or struct -> its address), 'f' float.
  * Calling convention: System V x86-64 and AAPCS64 both pass the first integer arguments and
@@ -17,6 +24,7 @@
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
+#include <stdlib.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
@@ -173,6 +181,165 @@ static PyObject* sp_bind(PyObject* mod, PyObject* args) {
   return (PyObject*)f;
 }
 
+/* ---------------------------------------------------------------------------------------
+ * Block pool
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  PyObject* tensor;
+  uint64_t ptr;
+} Slot;
+
+typedef struct {
+  Py_ssize_t nbytes; /* 0 = unused bucket */
+  Slot* slots;
+  int count, cap;
+} Bucket;
+
+#define SP_POOL_BUCKETS 512 /* distinct buffer sizes (open addressing); beyond that: no recycling */
+static Bucket g_buckets[SP_POOL_BUCKETS];
+static long long g_pool_bytes = 0;
+static long long g_pool_max_bytes = 2LL << 30;
+static int g_pool_bypass = 0;
+
+static Bucket* bucket_for(Py_ssize_t nbytes, int create) {
+  size_t h = ((size_t)nbytes * 0x9E3779B97F4A7C15ull) >> 40;
+  for (int probe = 0; probe < SP_POOL_BUCKETS; ++probe) {
+    Bucket* b = &g_buckets[(h + (size_t)probe) % SP_POOL_BUCKETS];
+    if (b->nbytes == nbytes) return b;
+    if (b->nbytes == 0) {
+      if (!create) return NULL;
+      b->nbytes = nbytes;
+      return b;
+    }
+  }
+  return NULL;
+}
+
+typedef struct {
+  PyObject_HEAD
+  PyObject* tensor;
+  unsigned long long ptr;
+  Py_ssize_t nbytes;
+  int recycle;
+} Block;
+
+static void block_dealloc(Block* self) {
+  PyObject* tensor = self->tensor;
+  self->tensor = NULL;
+  if (tensor && self->recycle && !g_pool_bypass &&
+      g_pool_bytes + (long long)self->nbytes <= g_pool_max_bytes) {
+    Bucket* b = bucket_for(self->nbytes, 1);
+    if (b) {
+      if (b->count == b->cap) {
+        const int cap = b->cap ? 2 * b->cap : 8;
+        Slot* grown = (Slot*)realloc(b->slots, (size_t)cap * sizeof(Slot));
+        if (grown) {
+          b->slots = grown;
+          b->cap = cap;
+        }
+      }
+      if (b->count < b->cap) {
+        b->slots[b->count].tensor = tensor; /* the reference moves into the pool */
+        b->slots[b->count].ptr = self->ptr;
+        ++b->count;
+        g_pool_bytes += (long long)self->nbytes;
+        tensor = NULL;
+      }
+    }
+  }
+  Py_XDECREF(tensor);
+  Py_TYPE(self)->tp_free((PyObject*)self);
+}
+
+static PyMemberDef block_members[] = {
+    {"ptr", Py_T_ULONGLONG, offsetof(Block, ptr), Py_READONLY, "device address"},
+    {"tensor", Py_T_OBJECT_EX, offsetof(Block, tensor), Py_READONLY, "owning torch tensor"},
+    {"nbytes", Py_T_PYSSIZET, offsetof(Block, nbytes), Py_READONLY, "size in bytes"},
+    {NULL, 0, 0, 0, NULL}};
+
+static PyTypeObject BlockType = {
+    PyVarObject_HEAD_INIT(NULL, 0).tp_name = "_sp_fastcall.Block",
+    .tp_basicsize = sizeof(Block),
+    .tp_dealloc = (destructor)block_dealloc,
+    .tp_flags = Py_TPFLAGS_DEFAULT,
+    .tp_members = block_members,
+    .tp_doc = "one recyclable device buffer",
+};
+
+static PyObject* make_block(PyObject* tensor /* stolen */, unsigned long long ptr,
+                            Py_ssize_t nbytes, int recycle) {
+  Block* blk = PyObject_New(Block, &BlockType);
+  if (!blk) {
+    Py_DECREF(tensor);
+    return NULL;
+  }
+  blk->tensor = tensor;
+  blk->ptr = ptr;
+  blk->nbytes = nbytes;
+  blk->recycle = recycle;
+  return (PyObject*)blk;
+}
+
+/* pool_alloc(nbytes) -> Block from the free list, or None (caller allocates + block_new) */
+static PyObject* sp_pool_alloc(PyObject* mod, PyObject* arg) {
+  (void)mod;
+  const Py_ssize_t nbytes = PyLong_AsSsize_t(arg);
+  if (nbytes == -1 && PyErr_Occurred()) return NULL;
+  if (!g_pool_bypass) {
+    Bucket* b = bucket_for(nbytes, 0);
+    if (b && b->count > 0) {
+      --b->count;
+      g_pool_bytes -= (long long)nbytes;
+      return make_block(b->slots[b->count].tensor, b->slots[b->count].ptr, nbytes, 1);
+    }
+  }
+  Py_RETURN_NONE;
+}
+
+/* block_new(tensor, ptr, nbytes, recycle) -> Block */
+static PyObject* sp_block_new(PyObject* mod, PyObject* args) {
+  (void)mod;
+  PyObject* tensor;
+  unsigned long long ptr;
+  Py_ssize_t nbytes;
+  int recycle;
+  if (!PyArg_ParseTuple(args, "OKnp", &tensor, &ptr, &nbytes, &recycle)) return NULL;
+  Py_INCREF(tensor);
+  return make_block(tensor, ptr, nbytes, recycle);
+}
+
+static PyObject* sp_pool_trim(PyObject* mod, PyObject* noargs) {
+  (void)mod;
+  (void)noargs;
+  for (int i = 0; i < SP_POOL_BUCKETS; ++i) {
+    Bucket* b = &g_buckets[i];
+    while (b->count > 0) {
+      --b->count;
+      PyObject* t = b->slots[b->count].tensor;
+      b->slots[b->count].tensor = NULL;
+      Py_XDECREF(t);
+    }
+  }
+  g_pool_bytes = 0;
+  Py_RETURN_NONE;
+}
+
+static PyObject* sp_pool_bypass(PyObject* mod, PyObject* arg) {
+  (void)mod;
+  const long v = PyLong_AsLong(arg);
+  if (v == -1 && PyErr_Occurred()) return NULL;
+  g_pool_bypass += (int)v; /* +1 on enter, -1 on exit (nests) */
+  return PyLong_FromLong(g_pool_bypass);
+}
+
+static PyObject* sp_pool_stats(PyObject* mod, PyObject* noargs) {
+  (void)mod;
+  (void)noargs;
+  long long blocks = 0;
+  for (int i = 0; i < SP_POOL_BUCKETS; ++i) blocks += g_buckets[i].count;
+  return Py_BuildValue("LL", blocks, g_pool_bytes);
+}
+
 static PyObject* sp_launches(PyObject* mod, PyObject* noargs) {
   (void)mod;
   (void)noargs;
@@ -191,6 +358,11 @@ static PyMethodDef methods[] = {
     {"bind", sp_bind, METH_VARARGS, "bind(address, signature, name, on_error, counts_launch)"},
     {"launches", sp_launches, METH_NOARGS, "kernel-launching ABI calls made through FastFn objects"},
     {"add_launches", sp_add_launches, METH_O, "account for launches replayed by a CUDA graph"},
+    {"pool_alloc", sp_pool_alloc, METH_O, "pool_alloc(nbytes) -> recycled Block or None"},
+    {"block_new", sp_block_new, METH_VARARGS, "block_new(tensor, ptr, nbytes, recycle) -> Block"},
+    {"pool_trim", sp_pool_trim, METH_NOARGS, "release every pooled buffer"},
+    {"pool_bypass", sp_pool_bypass, METH_O, "pool_bypass(+1 / -1): nestable bypass of the pool"},
+    {"pool_stats", sp_pool_stats, METH_NOARGS, "(pooled blocks, pooled bytes)"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, "_sp_fastcall",
@@ -199,5 +371,6 @@ static struct PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, "_sp_fastcall",
 
 PyMODINIT_FUNC PyInit__sp_fastcall(void) {
   if (PyType_Ready(&FastFnType) < 0) return NULL;
+  if (PyType_Ready(&BlockType) < 0) return NULL;
   return PyModule_Create(&moduledef);
 }

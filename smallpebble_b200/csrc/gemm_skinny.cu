@@ -26,6 +26,7 @@ constexpr int kThreads = 256;
 // needs neither a workspace nor a second launch.
 template <int NN, int R>
 __global__ void __launch_bounds__(kThreads) gemm_skinny_rows_kernel(const IgemmParams p) {
+  pdl_entry();
   __shared__ float red[kThreads / 32][R][NN];
   __shared__ float part[R][NN];
   const int64_t m0 = (int64_t)blockIdx.x * R;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(kThreads) gemm_skinny_rows_kernel(const IgemmP
 
 template <int NN>
 __global__ void __launch_bounds__(kThreads) gemm_skinny_cols_kernel(const IgemmParams p) {
+  pdl_entry();
   constexpr int KG = 8;  // k groups (threadIdx.y)
   __shared__ float red[KG][32][NN + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -155,13 +157,15 @@ int launch_gemm_skinny(const IgemmParams& p, cudaStream_t st) {
     cfg.gridDim = dim3(blocks, splits, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = splits;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     auto kernel = wide ? (tile_rows ? gemm_skinny_rows_kernel<16, 4> : gemm_skinny_rows_kernel<16, 1>)
                        : (tile_rows ? gemm_skinny_rows_kernel<8, 4> : gemm_skinny_rows_kernel<8, 1>);
     if (cudaLaunchKernelEx(&cfg, kernel, p) != cudaSuccess)
@@ -169,9 +173,9 @@ int launch_gemm_skinny(const IgemmParams& p, cudaStream_t st) {
   } else {
     const unsigned blocks = (unsigned)((p.M + 31) / 32);
     if (wide)
-      gemm_skinny_cols_kernel<16><<<blocks, kThreads, 0, st>>>(p);
+      sp::launch_pdl(gemm_skinny_cols_kernel<16>, dim3(blocks), dim3(kThreads), 0, st, p);
     else
-      gemm_skinny_cols_kernel<8><<<blocks, kThreads, 0, st>>>(p);
+      sp::launch_pdl(gemm_skinny_cols_kernel<8>, dim3(blocks), dim3(kThreads), 0, st, p);
   }
   return 0;
 }

@@ -73,6 +73,7 @@ __device__ __forceinline__ float load_b(const IgemmParams& p, int64_t k, int64_t
 // A_KFAST / B_KFAST: which index of the operand is contiguous in memory (coalescing)
 template <int MODE, bool A_KFAST, bool B_KFAST>
 __global__ void __launch_bounds__(kThreads) igemm_simt_kernel(const __grid_constant__ IgemmParams p) {
+  pdl_entry();
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
 
@@ -169,7 +170,7 @@ int launch(const IgemmParams& p, cudaStream_t st) {
   const int64_t gy = (p.N + BN - 1) / BN;
   if (gy > 65535) return set_error(SP_ERR_UNSUPPORTED, "igemm: N too large");
   dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)gy, (unsigned)z);
-  igemm_simt_kernel<MODE, AK, BK_><<<grid, kThreads, 0, st>>>(p);
+  sp::launch_pdl(igemm_simt_kernel<MODE, AK, BK_>, dim3(grid), dim3(kThreads), 0, st, p);
   return 0;
 }
 

@@ -689,6 +689,7 @@ template <int MODE, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
     igemm_umma_kernel(const __grid_constant__ IgemmParams p, const int bn, const int a_vec,
                       const int b_vec, const int sync_mode) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kStages + 1];
   __shared__ uint32_t tmem_slot;
@@ -734,6 +735,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // barriers and TMEM are set up: now wait for the producers of A and B
   const uint32_t tmem_base = tmem_slot;
 
   if (warp < kProducerWarps) {
@@ -969,7 +971,8 @@ int launch(const IgemmParams& p, cudaStream_t st, bool a_vec, bool b_vec) {
   const int64_t gy = (p.N + bn - 1) / bn;
   if (z > 65535 || gy > 65535) return set_error(SP_ERR_UNSUPPORTED, "igemm_umma: grid too large");
   dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)gy, (unsigned)z);
-  kern<<<grid, kThreads, smem, st>>>(p, bn, a_vec ? 1 : 0, b_vec ? 1 : 0, g_sync_mode);
+  sp::launch_pdl(kern, grid, dim3(kThreads), smem, st, p, bn, a_vec ? 1 : 0, b_vec ? 1 : 0,
+                 g_sync_mode);
   return 0;
 }
 

@@ -42,6 +42,7 @@ const DeviceInfo& device_info() {
 namespace {
 
 __global__ void fill_f32_kernel(float* __restrict__ dst, int64_t n, float v) {
+  pdl_entry();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n >> 2;
   float4* d4 = reinterpret_cast<float4*>(dst);
@@ -53,6 +54,7 @@ __global__ void fill_f32_kernel(float* __restrict__ dst, int64_t n, float v) {
 
 __global__ void cast_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst,
                                     int64_t n) {
+  pdl_entry();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = (float)src[i];
@@ -60,6 +62,7 @@ __global__ void cast_f64_f32_kernel(const double* __restrict__ src, float* __res
 
 __global__ void cast_i64_i32_kernel(const int64_t* __restrict__ src, int32_t* __restrict__ dst,
                                     int64_t n) {
+  pdl_entry();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = (int32_t)src[i];
@@ -120,21 +123,21 @@ int sp_memcpy_d2d(void* dst, const void* src, size_t bytes, sp_stream_t stream) 
 int sp_fill_f32(float* dst, int64_t n, float value, sp_stream_t stream) {
   if (n <= 0) return 0;
   SP_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "dst must be 16-byte aligned");
-  fill_f32_kernel<<<sp::wave_grid(n, 256 * 4 * 4, 8), 256, 0, sp::as_stream(stream)>>>(dst, n, value);
+  sp::launch_pdl(fill_f32_kernel, dim3(sp::wave_grid(n, 256 * 4 * 4, 8)), dim3(256), 0, sp::as_stream(stream), dst, n, value);
   SP_CHECK_LAUNCH("fill_f32");
   return 0;
 }
 
 int sp_cast_f64_f32(const double* src, float* dst, int64_t n, sp_stream_t stream) {
   if (n <= 0) return 0;
-  cast_f64_f32_kernel<<<sp::wave_grid(n, 256 * 4, 8), 256, 0, sp::as_stream(stream)>>>(src, dst, n);
+  sp::launch_pdl(cast_f64_f32_kernel, dim3(sp::wave_grid(n, 256 * 4, 8)), dim3(256), 0, sp::as_stream(stream), src, dst, n);
   SP_CHECK_LAUNCH("cast_f64_f32");
   return 0;
 }
 
 int sp_cast_i64_i32(const int64_t* src, int32_t* dst, int64_t n, sp_stream_t stream) {
   if (n <= 0) return 0;
-  cast_i64_i32_kernel<<<sp::wave_grid(n, 256 * 4, 8), 256, 0, sp::as_stream(stream)>>>(src, dst, n);
+  sp::launch_pdl(cast_i64_i32_kernel, dim3(sp::wave_grid(n, 256 * 4, 8)), dim3(256), 0, sp::as_stream(stream), src, dst, n);
   SP_CHECK_LAUNCH("cast_i64_i32");
   return 0;
 }

@@ -60,6 +60,7 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
 __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_constant__ AdamArgs a,
                                                               float alpha, float b1, float b2,
                                                               float lnb1, float lnb2, float eps) {
+  pdl_entry();
   const int t = find_tensor(a, blockIdx.x);
   const float step = (float)(*a.step[t] + 1);
   const float ic1 = 1.f / -expm1f(step * lnb1);
@@ -110,6 +111,7 @@ __global__ void adam_advance_kernel(const __grid_constant__ AdamArgs a) {
 
 __global__ void __launch_bounds__(kThreads) sgd_multi_kernel(const __grid_constant__ AxpyArgs a,
                                                              float lr) {
+  pdl_entry();
   const int t = find_tensor(a, blockIdx.x);
   const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * kChunk;
   const int64_t end = min(a.n[t], base + kChunk);
@@ -185,7 +187,7 @@ int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_
       // beta as the double nearest to what the caller wrote (0.9f -> 0.9), like the reference
       const double b1 = strtod_round(beta1);
       const double b2 = strtod_round(beta2);
-      adam_multi_kernel<<<blocks, kThreads, 0, st>>>(a, alpha, (float)b1, (float)b2,
+      sp::launch_pdl(adam_multi_kernel, dim3(blocks), dim3(kThreads), 0, st, a, alpha, (float)b1, (float)b2,
                                                      (float)log(b1), (float)log(b2), eps);
       SP_CHECK_LAUNCH("adam_multi");
     }
@@ -217,7 +219,7 @@ int sp_sgd_multi(int n_tensors, float* const* host_p, const float* const* host_g
     }
     if (a.count == 0) continue;
     a.block_start[a.count] = blocks;
-    sgd_multi_kernel<<<blocks, kThreads, 0, st>>>(a, lr);
+    sp::launch_pdl(sgd_multi_kernel, dim3(blocks), dim3(kThreads), 0, st, a, lr);
     SP_CHECK_LAUNCH("sgd_multi");
   }
   return 0;

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_vec4(const float* __rest
                                                              float* __restrict__ y,
                                                              uint8_t* __restrict__ idx,
                                                              PoolGeom g) {
+  pdl_entry();
   const int C4 = g.C >> 2;
   const int row_len = g.OW * C4;
   const int n_rows = g.N * g.OH;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_vec4_fixed(const float* 
                                                                    float* __restrict__ y,
                                                                    uint8_t* __restrict__ idx,
                                                                    PoolGeom g) {
+  pdl_entry();
   const int C4 = g.C >> 2;
   const int row_len = g.OW * C4;
   const int n_rows = g.N * g.OH;
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_tile_vec4(const float* _
                                                                   float* __restrict__ dx,
                                                                   const float* __restrict__ xl,
                                                                   PoolGeom g, int VOH, int VOW) {
+  pdl_entry();
   const int C4 = g.C >> 2;
   const int row_len = VOW * C4;
   const int n_rows = g.N * VOH;
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_vec4(const float* __rest
                                                              float* __restrict__ dx,
                                                              const float* __restrict__ xl,
                                                              PoolGeom g) {
+  pdl_entry();
   const int C4 = g.C >> 2;
   const int row_len = g.W * C4;
   const int n_rows = g.N * g.H;
@@ -359,11 +363,11 @@ static int maxpool2d_fwd_impl(const float* x, float* y, uint8_t* idx, int N, int
   if (C % 4 == 0 && aligned16(x) && aligned16(y) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0) {
     const dim3 grid = row_grid(N * OH, OW * (C / 4));
     if (KH == 2 && KW == 2)
-      maxpool_fwd_vec4_fixed<2, 2><<<grid, kThreads, 0, st>>>(x, y, idx, g);
+      sp::launch_pdl(maxpool_fwd_vec4_fixed<2, 2>, dim3(grid), dim3(kThreads), 0, st, x, y, idx, g);
     else if (KH == 3 && KW == 3)
-      maxpool_fwd_vec4_fixed<3, 3><<<grid, kThreads, 0, st>>>(x, y, idx, g);
+      sp::launch_pdl(maxpool_fwd_vec4_fixed<3, 3>, dim3(grid), dim3(kThreads), 0, st, x, y, idx, g);
     else
-      maxpool_fwd_vec4<<<grid, kThreads, 0, st>>>(x, y, idx, g);
+      sp::launch_pdl(maxpool_fwd_vec4, dim3(grid), dim3(kThreads), 0, st, x, y, idx, g);
   } else
     maxpool_fwd_scalar<<<sp::wave_grid(outs, kThreads, 8), kThreads, 0, st>>>(x, y, idx, g);
   SP_CHECK_LAUNCH("maxpool2d_fwd");
@@ -399,15 +403,13 @@ static int maxpool2d_bwd_impl(const float* gy, const uint8_t* idx, float* dx, co
     // virtual window grid that tiles the whole (top/left padded) image
     const int VOH = (H + pad_t + KH - 1) / KH, VOW = (W + pad_l + KW - 1) / KW;
     if (sy == KH && sx == KW && KH == 2 && KW == 2)
-      maxpool_bwd_tile_vec4<2, 2><<<row_grid(N * VOH, VOW * (C / 4)), kThreads, 0, st>>>(
-          gy, idx, dx, xl, g, VOH, VOW);
+      sp::launch_pdl(maxpool_bwd_tile_vec4<2, 2>, dim3(row_grid(N * VOH, VOW * (C / 4))), dim3(kThreads), 0, st, gy, idx, dx, xl, g, VOH, VOW);
     else if (sy == KH && sx == KW && KH == 3 && KW == 3)
-      maxpool_bwd_tile_vec4<3, 3><<<row_grid(N * VOH, VOW * (C / 4)), kThreads, 0, st>>>(
-          gy, idx, dx, xl, g, VOH, VOW);
+      sp::launch_pdl(maxpool_bwd_tile_vec4<3, 3>, dim3(row_grid(N * VOH, VOW * (C / 4))), dim3(kThreads), 0, st, gy, idx, dx, xl, g, VOH, VOW);
     else if (sy == KH && sx == KW)
-      maxpool_bwd_vec4<true><<<row_grid(N * H, W * (C / 4)), kThreads, 0, st>>>(gy, idx, dx, xl, g);
+      sp::launch_pdl(maxpool_bwd_vec4<true>, dim3(row_grid(N * H, W * (C / 4))), dim3(kThreads), 0, st, gy, idx, dx, xl, g);
     else
-      maxpool_bwd_vec4<false><<<row_grid(N * H, W * (C / 4)), kThreads, 0, st>>>(gy, idx, dx, xl, g);
+      sp::launch_pdl(maxpool_bwd_vec4<false>, dim3(row_grid(N * H, W * (C / 4))), dim3(kThreads), 0, st, gy, idx, dx, xl, g);
   }
   else
     maxpool_bwd_scalar<<<sp::wave_grid(ins, kThreads, 8), kThreads, 0, st>>>(gy, idx, dx, xl, g);

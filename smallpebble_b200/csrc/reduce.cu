@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kThreads) rowsum_kernel(const float* __restric
                                                           float* __restrict__ out,
                                                           int64_t reduce, int64_t chunk,
                                                           int splits) {
+  pdl_entry();
   __shared__ float red[32];
   const int64_t row = blockIdx.y;
   const int split = blockIdx.x;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restric
                                                           float* __restrict__ out,
                                                           int64_t reduce, int64_t inner,
                                                           int64_t chunk, int splits) {
+  pdl_entry();
   __shared__ float tile[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t col = (int64_t)blockIdx.x * 32 + tx;
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(kThreads) colsum_vec4_kernel(const float* __re
                                                                float* __restrict__ out,
                                                                int64_t reduce, int64_t inner,
                                                                int64_t chunk, int splits) {
+  pdl_entry();
   __shared__ float4 tile[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t inner4 = inner >> 2;
@@ -178,6 +181,7 @@ __global__ void __launch_bounds__(kThreads) maxall_final_kernel(const float* __r
 __global__ void __launch_bounds__(kThreads) softmax_rows_kernel(const float* __restrict__ x,
                                                                 float* __restrict__ y,
                                                                 int64_t rows, int64_t n) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows;
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(kThreads) softmax_rows_bwd_kernel(const float*
                                                                     const float* __restrict__ g,
                                                                     float* __restrict__ dx,
                                                                     int64_t rows, int64_t n) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows;
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(kThreads) xent_fwd_kernel(const float* __restr
                                                             const int32_t* __restrict__ labels,
                                                             float* __restrict__ part,
                                                             int64_t rows, int64_t cols) {
+  pdl_entry();
   __shared__ float red[32];
   float acc = 0.f;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
@@ -266,6 +272,7 @@ __global__ void __launch_bounds__(kThreads) xent_bwd_kernel(const float* __restr
                                                             const float* __restrict__ gloss,
                                                             float* __restrict__ dprobs,
                                                             int64_t rows, int64_t cols) {
+  pdl_entry();
   const float g = gloss[0];
   const int64_t total = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -283,6 +290,7 @@ __global__ void __launch_bounds__(kThreads) xent_bwd_kernel(const float* __restr
 __global__ void __launch_bounds__(1024) softmax_xent_fwd_kernel(
     const float* __restrict__ logits, const int32_t* __restrict__ labels,
     float* __restrict__ probs, float* __restrict__ part, int64_t rows, int64_t cols) {
+  pdl_entry();
   __shared__ float red[32];
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
@@ -335,6 +343,7 @@ __global__ void __launch_bounds__(1024) softmax_xent_fwd_kernel(
 __global__ void __launch_bounds__(kThreads) softmax_xent_bwd_kernel(
     const float* __restrict__ probs, const int32_t* __restrict__ labels,
     const float* __restrict__ gloss, float* __restrict__ dlogits, int64_t rows, int64_t cols) {
+  pdl_entry();
   const float g = gloss[0];
   const int64_t total = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -347,6 +356,7 @@ __global__ void __launch_bounds__(kThreads) softmax_xent_bwd_kernel(
 
 __global__ void __launch_bounds__(kThreads) sum_partials_kernel(const float* __restrict__ part,
                                                                 float* __restrict__ out, int n) {
+  pdl_entry();
   __shared__ float red[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
@@ -361,6 +371,7 @@ __global__ void __launch_bounds__(kThreads) sum_partials_kernel(const float* __r
 __global__ void __launch_bounds__(kThreads) colsum_final_vec4_kernel(const float* __restrict__ part,
                                                                      float* __restrict__ out,
                                                                      int64_t splits, int64_t inner) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t inner4 = inner >> 2;
   const int64_t col4 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -395,13 +406,13 @@ int reduce_sum_impl(const float* x, float* out, int64_t outer, int64_t reduce, i
     chunk = (chunk + 3) & ~int64_t(3);
     splits = (int)((reduce + chunk - 1) / chunk);
     if (splits == 1) {
-      rowsum_kernel<<<dim3(1, (unsigned)outer), kThreads, 0, st>>>(x, out, reduce, chunk, 1);
+      sp::launch_pdl(rowsum_kernel, dim3(dim3(1, (unsigned)outer)), dim3(kThreads), 0, st, x, out, reduce, chunk, 1);
     } else {
       float* part = scratch_for_current_device();
       if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_reduce_sum: no scratch");
-      rowsum_kernel<<<dim3(splits, (unsigned)outer), kThreads, 0, st>>>(x, part, reduce, chunk,
+      sp::launch_pdl(rowsum_kernel, dim3(dim3(splits, (unsigned)outer)), dim3(kThreads), 0, st, x, part, reduce, chunk,
                                                                          splits);
-      rowsum_kernel<<<dim3(1, (unsigned)outer), kThreads, 0, st>>>(part, out, splits, splits, 1);
+      sp::launch_pdl(rowsum_kernel, dim3(dim3(1, (unsigned)outer)), dim3(kThreads), 0, st, part, out, splits, splits, 1);
     }
   } else {
     const bool vec = (inner % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
@@ -421,9 +432,9 @@ int reduce_sum_impl(const float* x, float* out, int64_t outer, int64_t reduce, i
     dim3 grid((unsigned)col_blocks, (unsigned)splits, (unsigned)outer);
     auto launch = [&](const float* src, float* dst, int64_t red, int64_t ch, int sp_, dim3 gr) {
       if (vec)
-        colsum_vec4_kernel<<<gr, kThreads, 0, st>>>(src, dst, red, inner, ch, sp_);
+        sp::launch_pdl(colsum_vec4_kernel, dim3(gr), dim3(kThreads), 0, st, src, dst, red, inner, ch, sp_);
       else
-        colsum_kernel<<<gr, kThreads, 0, st>>>(src, dst, red, inner, ch, sp_);
+        sp::launch_pdl(colsum_kernel, dim3(gr), dim3(kThreads), 0, st, src, dst, red, inner, ch, sp_);
     };
     if (splits == 1) {
       launch(x, out, reduce, chunk, 1, grid);
@@ -433,7 +444,7 @@ int reduce_sum_impl(const float* x, float* out, int64_t outer, int64_t reduce, i
       launch(x, part, reduce, chunk, splits, grid);
       if (vec && col_blocks * outer < sms && splits > 8) {
         dim3 gridw((unsigned)((inner / 4 + kThreads / 32 - 1) / (kThreads / 32)), 1, (unsigned)outer);
-        colsum_final_vec4_kernel<<<gridw, kThreads, 0, st>>>(part, out, splits, inner);
+        sp::launch_pdl(colsum_final_vec4_kernel, dim3(gridw), dim3(kThreads), 0, st, part, out, splits, inner);
       } else {
         dim3 grid2((unsigned)col_blocks, 1, (unsigned)outer);
         launch(part, out, splits, splits, 1, grid2);
@@ -474,7 +485,7 @@ int sp_softmax_fwd(const float* x, float* y, int64_t outer, int64_t n, int64_t i
   if (outer * n * inner <= 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
   if (inner == 1)
-    softmax_rows_kernel<<<sp::wave_grid(outer, kThreads / 32, 8), kThreads, 0, st>>>(x, y, outer, n);
+    sp::launch_pdl(softmax_rows_kernel, dim3(sp::wave_grid(outer, kThreads / 32, 8)), dim3(kThreads), 0, st, x, y, outer, n);
   else
     softmax_strided_kernel<<<sp::wave_grid(outer * inner, kThreads, 8), kThreads, 0, st>>>(
         x, y, outer, n, inner);
@@ -487,8 +498,7 @@ int sp_softmax_bwd(const float* y, const float* g, float* dx, int64_t outer, int
   if (outer * n * inner <= 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
   if (inner == 1)
-    softmax_rows_bwd_kernel<<<sp::wave_grid(outer, kThreads / 32, 8), kThreads, 0, st>>>(
-        y, g, dx, outer, n);
+    sp::launch_pdl(softmax_rows_bwd_kernel, dim3(sp::wave_grid(outer, kThreads / 32, 8)), dim3(kThreads), 0, st, y, g, dx, outer, n);
   else
     softmax_strided_bwd_kernel<<<sp::wave_grid(outer * inner, kThreads, 8), kThreads, 0, st>>>(
         y, g, dx, outer, n, inner);
@@ -503,12 +513,12 @@ int sp_xent_fwd(const float* probs, const int32_t* labels, float* loss, int64_t 
   if (rows == 0) return sp_fill_f32(loss, 1, 0.f, stream);
   const int blocks = rows <= 4096 ? 1 : sp::wave_grid(rows, kThreads, 2);
   if (blocks == 1) {
-    xent_fwd_kernel<<<1, kThreads, 0, st>>>(probs, labels, loss, rows, cols);
+    sp::launch_pdl(xent_fwd_kernel, dim3(1), dim3(kThreads), 0, st, probs, labels, loss, rows, cols);
   } else {
     float* part = scratch_for_current_device();
     if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_xent_fwd: no scratch");
-    xent_fwd_kernel<<<blocks, kThreads, 0, st>>>(probs, labels, part, rows, cols);
-    sum_partials_kernel<<<1, kThreads, 0, st>>>(part, loss, blocks);
+    sp::launch_pdl(xent_fwd_kernel, dim3(blocks), dim3(kThreads), 0, st, probs, labels, part, rows, cols);
+    sp::launch_pdl(sum_partials_kernel, dim3(1), dim3(kThreads), 0, st, part, loss, blocks);
   }
   SP_CHECK_LAUNCH("xent_fwd");
   return 0;
@@ -517,8 +527,7 @@ int sp_xent_fwd(const float* probs, const int32_t* labels, float* loss, int64_t 
 int sp_xent_bwd(const float* probs, const int32_t* labels, const float* gloss, float* dprobs,
                 int64_t rows, int64_t cols, sp_stream_t stream) {
   if (rows * cols <= 0) return 0;
-  xent_bwd_kernel<<<sp::wave_grid(rows * cols, kThreads, 8), kThreads, 0, sp::as_stream(stream)>>>(
-      probs, labels, gloss, dprobs, rows, cols);
+  sp::launch_pdl(xent_bwd_kernel, dim3(sp::wave_grid(rows * cols, kThreads, 8)), dim3(kThreads), 0, sp::as_stream(stream), probs, labels, gloss, dprobs, rows, cols);
   SP_CHECK_LAUNCH("xent_bwd");
   return 0;
 }
@@ -531,13 +540,13 @@ int sp_softmax_xent_fwd(const float* logits, const int32_t* labels, float* probs
   const int blocks = rows <= 2048 ? 1 : sp::wave_grid(rows, kThreads / 32, 4);
   if (blocks == 1) {
     // one block so the loss needs no second pass; 32 warps = 32 rows in flight
-    softmax_xent_fwd_kernel<<<1, rows > 64 ? 1024 : kThreads, 0, st>>>(logits, labels, probs, loss,
+    sp::launch_pdl(softmax_xent_fwd_kernel, dim3(1), dim3(rows > 64 ? 1024 : kThreads), 0, st, logits, labels, probs, loss,
                                                                       rows, cols);
   } else {
     float* part = scratch_for_current_device();
     if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_softmax_xent_fwd: no scratch");
-    softmax_xent_fwd_kernel<<<blocks, kThreads, 0, st>>>(logits, labels, probs, part, rows, cols);
-    sum_partials_kernel<<<1, kThreads, 0, st>>>(part, loss, blocks);
+    sp::launch_pdl(softmax_xent_fwd_kernel, dim3(blocks), dim3(kThreads), 0, st, logits, labels, probs, part, rows, cols);
+    sp::launch_pdl(sum_partials_kernel, dim3(1), dim3(kThreads), 0, st, part, loss, blocks);
   }
   SP_CHECK_LAUNCH("softmax_xent_fwd");
   return 0;
@@ -546,8 +555,7 @@ int sp_softmax_xent_fwd(const float* logits, const int32_t* labels, float* probs
 int sp_softmax_xent_bwd(const float* probs, const int32_t* labels, const float* gloss,
                         float* dlogits, int64_t rows, int64_t cols, sp_stream_t stream) {
   if (rows * cols <= 0) return 0;
-  softmax_xent_bwd_kernel<<<sp::wave_grid(rows * cols, kThreads, 8), kThreads, 0,
-                            sp::as_stream(stream)>>>(probs, labels, gloss, dlogits, rows, cols);
+  sp::launch_pdl(softmax_xent_bwd_kernel, dim3(sp::wave_grid(rows * cols, kThreads, 8)), dim3(kThreads), 0, sp::as_stream(stream), probs, labels, gloss, dlogits, rows, cols);
   SP_CHECK_LAUNCH("softmax_xent_bwd");
   return 0;
 }

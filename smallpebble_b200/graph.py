@@ -34,6 +34,8 @@ class Lazy:
     def __init__(self, function) -> None:
         self.function = function
         self.arguments = []
+        self._flag_args = None  # the (immutable) argument tuple `_flags` was computed for
+        self._flags = ()
 
     def __call__(self, *args):
         if self.arguments:
@@ -42,10 +44,16 @@ class Lazy:
         return self
 
     def run(self):
-        if not self.arguments:
+        args = self.arguments
+        if not args:
             raise AssignmentError(f"No arguments have been assigned to {self}.")
-        argvals = (a.run() if hasattr(a, "run") else a for a in self.arguments)
-        return self.function(*argvals)
+        if type(args) is tuple:
+            # which arguments are lazy nodes is fixed for a tuple: decide once, not per run
+            if args is not self._flag_args:
+                self._flags = tuple(hasattr(a, "run") for a in args)
+                self._flag_args = args
+            return self.function(*[a.run() if lazy else a for a, lazy in zip(args, self._flags)])
+        return self.function(*[a.run() if hasattr(a, "run") else a for a in args])
 
 
 class Placeholder(Lazy):
@@ -56,6 +64,15 @@ class Placeholder(Lazy):
 
     def assign_value(self, variable) -> None:
         self.arguments = [variable]
+
+    def run(self):
+        args = self.arguments
+        if not args:
+            raise AssignmentError(f"No arguments have been assigned to {self}.")
+        if len(args) != 1:
+            return super().run()
+        a = args[0]
+        return a.run() if hasattr(a, "run") else a
 
 
 # ---------------- LEARNABLES (sp.py:526-543)
