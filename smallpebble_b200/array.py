@@ -268,7 +268,12 @@ class DeviceArray:
         thunk = self._thunk
         out = DeviceArray.empty(self.shape)
         thunk(out)
-        self._buf, self._ptr = out._buf, out._ptr  # adopt the buffer
+        self._adopt(out)
+
+    def _adopt(self, out):
+        """A deferred array takes over `out`'s buffer: whoever calls this fills it instead of
+        the pending thunk (a consumer that fused the producing op into its own kernel)."""
+        self._buf, self._ptr = out._buf, out._ptr
         self._thunk = None
         self._tag = None
 

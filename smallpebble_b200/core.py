@@ -806,9 +806,20 @@ def softmax(a: Variable, axis: int = -1) -> Variable:
     nd = x.ndim
     ax = axis if axis >= 0 else nd + axis
     outer, n, inner = math.prod(x.shape[:ax]), x.shape[ax], math.prod(x.shape[ax + 1:])
-    y = DeviceArray.empty(x.shape)
-    if y.size:
-        F.sp_softmax_fwd(x.ptr, y.ptr, outer, n, inner, A.stream())
+    fusable = inner == 1 and nd == 2
+
+    def launch(out):
+        if out.size:
+            F.sp_softmax_fwd(x.ptr, out.ptr, outer, n, inner, A.stream())
+
+    if fusable and _fuse_softmax_xent and a.local_gradients and x.size:
+        # Not launched yet: cross_entropy computes the probabilities and the loss from the
+        # logits in ONE kernel and hands this array its buffer; anything else that touches the
+        # probabilities first launches the ordinary kernel (bitwise the same values).
+        y = DeviceArray.deferred(x.shape, launch, ("softmax", x))
+    else:
+        y = DeviceArray.empty(x.shape)
+        launch(y)
 
     def multiply_by_locgrad(g):
         dx = DeviceArray.empty(x.shape)
@@ -817,7 +828,7 @@ def softmax(a: Variable, axis: int = -1) -> Variable:
         return dx
 
     out = Variable(y, [(a, multiply_by_locgrad)])
-    if inner == 1 and nd == 2:
+    if fusable:
         out._softmax_of = a  # lets cross_entropy fuse forward and backward with this node
     return out
 
@@ -851,7 +862,10 @@ def cross_entropy(y_pred: Variable, y_true: np.ndarray, axis: int = -1) -> Varia
 
     if logits_var is not None:
         logits = logits_var.array
-        # recomputes probs into the existing buffer (bitwise the same values) + the loss
+        if probs.pending_tag is not None:
+            # the softmax has not been launched: this kernel produces its output as well
+            probs._adopt(DeviceArray.empty(probs.shape))
+        # (re)computes probs into the softmax node's buffer (bitwise the same values) + the loss
         F.sp_softmax_xent_fwd(logits.ptr, labels.ptr, probs.ptr, loss.ptr, rows, cols, A.stream())
 
         def grad_logits(g):

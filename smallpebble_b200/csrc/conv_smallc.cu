@@ -714,12 +714,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rgb3x3_mma_kernel(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;
   const int gy_floats = pl.q_pad * GS;
+  pdl_trigger();
 
   // slack behind the staged input rows: read (times dY = 0) by the virtual tail pixels,
   // never written by the pipeline
   for (int s = 0; s < 2; ++s)
     for (int i = pl.x_staged + threadIdx.x; i < pl.x_floats; i += kThreads)
       sm[s * pl.stage_floats + gy_floats + i] = 0.f;
+  pdl_wait();
 
   auto prefetch = [&](int tile_idx, int stage) {
     const int n = tile_idx / pl.tiles_per_img;
@@ -1051,8 +1053,31 @@ static int launch_rgb_mma(const float* x, const float* gy, float* partial, float
                   (void*)&words};
   const void* fn = (const void*)conv_wgrad_rgb3x3_mma_kernel<KT>;
   blocks = std::min(blocks, pl.n_tiles);
-  cudaError_t e =
-      cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(kThreads), args, smem, st);
+  // cooperative (co-resident grid: the kernel ends in a grid barrier) AND programmatic
+  // dependent launch; a driver that refuses the combination gets the plain cooperative launch
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  static bool combo_ok = true;
+  cudaError_t e = cudaErrorNotSupported;
+  if (combo_ok) {
+    e = cudaLaunchKernelExC(&cfg, fn, args);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      combo_ok = false;
+    }
+  }
+  if (e != cudaSuccess)
+    e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(kThreads), args, smem, st);
   if (e != cudaSuccess)
     return set_error((int)e, "cooperative launch of conv_wgrad_rgb3x3_mma failed: %s",
                      cudaGetErrorString(e));
