@@ -70,7 +70,9 @@ int sp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int sp_debug_set_umma_policy(int policy);
 /* bits 5-6 of `policy` steer the 2-SM TMA conv kernels (csrc/conv_tma2.cu): 0 = by problem
  * size, 1 (+32) = whenever the geometry is eligible, 2 (+64) = never; bits 7-8 (+128 / +256)
- * do the same for their halo-reuse variant (stride-1 fprop / dgrad).
+ * do the same for their halo-reuse variant (stride-1 fprop / dgrad); bit 9 (+512) launches
+ * every kernel the ordinary way instead of with programmatic dependent launch
+ * (griddepcontrol; also SP_PDL=0 in the environment).
  * bring-up hook: cluster 0 of those kernels writes clock64 stamps into `device_buffer`
  * (>= 512 int64, layout in scripts/tma2_trace.py); NULL switches tracing off */
 int sp_debug_tma2_trace(void* device_buffer);

@@ -177,3 +177,65 @@ def test_batch_yields_pinned_minibatches_with_reference_values():
     assert np.array_equal(np.asarray(v.array), X[idx].astype(np.float32))
     small = next(sp.batch(np.arange(20.0).reshape(10, 2), np.arange(10), 4, seed=1))[0]
     assert small.shape == (4, 2)   # below the pinning threshold: plain fancy indexing
+
+
+def test_programmatic_dependent_launch_changes_no_bits():
+    """Kernels are chained with programmatic dependent launch (griddepcontrol: the next kernel's
+    launch and prologue overlap the current one, common.cuh).  Five Adam steps of the CIFAR CNN
+    with it on and off (policy bit 9) must leave bit-identical weights and losses: the overlap
+    never lets a kernel read or overwrite anything before its producer / last reader is done."""
+    from smallpebble_b200 import core
+
+    x, y = workloads.synthetic_batch("cnn", 32)
+
+    def run(policy):
+        core.debug_set_kernel_policy(policy)
+        try:
+            wl = workloads.cifar_cnn(seed=0)
+            adam = sp.Adam()
+            losses = []
+            for _ in range(5):
+                loss_val, _ = wl.train_step(adam, x, y)
+                losses.append(np.asarray(loss_val.array))
+            return losses, [np.asarray(p.array) for p in wl.learnables]
+        finally:
+            core.debug_set_kernel_policy(0)
+
+    losses_on, weights_on = run(0)
+    losses_off, weights_off = run(512)
+    for a, b in zip(losses_on, losses_off):
+        assert np.array_equal(a, b)
+    for a, b in zip(weights_on, weights_off):
+        assert np.array_equal(a, b)
+
+
+def test_softmax_is_folded_into_cross_entropy_and_still_readable():
+    """softmax(op_result) is a deferred array: cross_entropy's kernel fills it (one launch for
+    probabilities + loss); reading it first launches the ordinary kernel.  Same bits both ways."""
+    from smallpebble_b200 import _abi
+
+    rng = np.random.default_rng(3)
+    logits = rng.random((64, 10)) * 6 - 3
+    labels = rng.integers(0, 10, 64)
+    w = sp.Variable(np.eye(10))
+
+    def run(read_first):
+        z = sp.matmul(sp.Variable(logits), w)   # an op result feeds softmax
+        p = sp.softmax(z)
+        assert p.array.pending_tag is not None
+        probs_early = np.asarray(p.array) if read_first else None
+        before = _abi.counter.launches
+        loss = sp.cross_entropy(p, labels)
+        launched = _abi.counter.launches - before
+        assert p.array.pending_tag is None
+        g = sp.get_gradients(loss)
+        return np.asarray(p.array), np.asarray(loss.array), np.asarray(g[z]), probs_early, launched
+
+    p1, l1, g1, _, n1 = run(False)
+    p2, l2, g2, early, _ = run(True)
+    assert n1 == 1                       # probabilities and loss came out of one launch
+    assert np.array_equal(p1, p2) and np.array_equal(p2, early)
+    assert np.array_equal(l1, l2) and np.array_equal(g1, g2)
+    ref = np.exp(logits - logits.max(1, keepdims=True))
+    ref /= ref.sum(1, keepdims=True)
+    assert_close(p1, ref, 1e-5, "probs")
