@@ -158,6 +158,12 @@ int sp_softmax_xent_fwd(const float* logits, const int32_t* labels, float* probs
 /* dlogits = gloss[0] * (probs - onehot(labels)) */
 int sp_softmax_xent_bwd(const float* probs, const int32_t* labels, const float* gloss,
                         float* dlogits, int64_t rows, int64_t cols, sp_stream_t stream);
+/* the same, plus colsum[c] = sum over rows of dlogits[r, c]: the gradient of a bias row
+ * vector added to the logits (add's unbroadcast-sum closure, sp.py:100-108 + 183-189) out of
+ * the kernel that produces dlogits, fixed summation order */
+int sp_softmax_xent_bwd_colsum(const float* probs, const int32_t* labels, const float* gloss,
+                               float* dlogits, float* colsum, int64_t rows, int64_t cols,
+                               sp_stream_t stream);
 
 /* ---- maxpool2d (sp.py:282-300 + maxax 257-279) ------------------------------------- */
 /* x [N,H,W,C] -> y [N,OH,OW,C], idx[N,OH,OW,C] = dy*KW+dx of the FIRST maximum of the
@@ -187,6 +193,11 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
             int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB,
             float* C, int64_t ldc, int64_t strideC, int64_t batch, int precision,
             sp_stream_t stream);
+/* C[M,N] = A[M,K] * B[K,N] + bias[N], all dense row-major: add(matmul(x, w), b) of the layer
+ * constructors (sp.py:630-635) in one call -- one kernel for the N <= 16 classifier, the GEMM
+ * plus an in-place row-vector add otherwise; same bits as the two separate ops */
+int sp_gemm_bias(int64_t M, int64_t N, int64_t K, const float* A, const float* B,
+                 const float* bias, float* C, int precision, sp_stream_t stream);
 
 /* ---- conv2d (sp.py:124-163 and the closures it composes: 244-245, 384-387, 325-327) -- */
 typedef struct sp_conv_geom {

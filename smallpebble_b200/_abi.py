@@ -67,6 +67,8 @@ SIGNATURES = {
     "sp_xent_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
     "sp_softmax_xent_fwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
     "sp_softmax_xent_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
+    "sp_softmax_xent_bwd_colsum": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp]),
+    "sp_gemm_bias": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, C.c_int, vp]),
     "sp_maxpool2d_fwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [vp]),
     "sp_maxpool2d_bwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [vp]),
     "sp_maxpool2d_leaky_fwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [f32, vp]),

@@ -199,7 +199,7 @@ _prod = math.prod
 
 
 class DeviceArray:
-    __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "_thunk", "_tag",
+    __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "_thunk", "_tag", "_aux",
                  "__weakref__")
     __array_priority__ = 1000.0
 
@@ -212,6 +212,7 @@ class DeviceArray:
         self._host = host
         self._thunk = None
         self._tag = None
+        self._aux = None  # by-product of the producing kernel, e.g. ("colsum0", column sums)
 
     # ---- construction ---------------------------------------------------------------------
     @staticmethod
@@ -228,6 +229,7 @@ class DeviceArray:
         self._host = None
         self._thunk = None
         self._tag = None
+        self._aux = None
         nbytes = (size or 1) * dtype.itemsize
         if _pool_bypass or nbytes > _POOL_MAX_BLOCK:
             self._buf = buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
@@ -255,6 +257,7 @@ class DeviceArray:
         self._buf = None
         self._ptr = None
         self._host = None
+        self._aux = None
         self._thunk = thunk
         self._tag = tag
         return self
@@ -749,6 +752,7 @@ def _binary_any(op, a, b):
 def accumulate_(dst: DeviceArray, src: DeviceArray) -> DeviceArray:
     """dst += src in place (same shape)."""
     F.sp_accumulate(dst.ptr, src.ptr, dst.size, stream())
+    dst._aux = None  # by-products described the old contents
     return dst
 
 

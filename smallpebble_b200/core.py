@@ -65,15 +65,17 @@ _fuse_softmax_xent = os.environ.get("SP_FUSE_SOFTMAX_XENT", "1") != "0"
 
 
 _fuse_leaky_pool = os.environ.get("SP_FUSE_LEAKY_POOL", "1") != "0"
+_fuse_bias = os.environ.get("SP_FUSE_BIAS", "1") != "0"
 
 
 def set_fusion(enabled: bool) -> None:
     """Fuse cross_entropy(softmax(x)) into one forward and one backward kernel (default on).
     With fusion the loss's tape edge goes straight to the logits, so `get_gradients` has no
     entry for the intermediate probability node; turn it off to get that entry."""
-    global _fuse_softmax_xent, _fuse_leaky_pool
+    global _fuse_softmax_xent, _fuse_leaky_pool, _fuse_bias
     _fuse_softmax_xent = bool(enabled)
     _fuse_leaky_pool = bool(enabled)
+    _fuse_bias = bool(enabled)
 
 
 # --------------------------------------------------------------------------------------------
@@ -357,6 +359,10 @@ def _unbroadcast(g: DeviceArray, shape, repeat_axes) -> DeviceArray:
     sp.py:183-189) -- skipped entirely when nothing was broadcast."""
     if g.shape == tuple(shape):
         return g
+    aux = g._aux
+    if aux is not None and aux[0] == "colsum0" and repeat_axes == (0,) and g.ndim == 2:
+        # the kernel that produced `g` already summed it over its rows (bias gradient)
+        return aux[1].reshape(shape)
     return A.reduce_sum(g, repeat_axes).reshape(shape) if repeat_axes else g.reshape(shape)
 
 
@@ -368,8 +374,18 @@ def _unbroadcast(g: DeviceArray, shape, repeat_axes) -> DeviceArray:
 def add(a: Variable, b: Variable) -> Variable:
     "Elementwise addition (sp.py:100-108)."
     ra, rb = broadcastinfo(a.array.shape, b.array.shape)
-    value = A.binary("add", a.array, b.array)
     sa, sb = a.array.shape, b.array.shape
+    tag = a.array.pending_tag
+    if (tag is not None and tag[0] == "matmul" and len(sa) == 2 and b.array.dtype == A.FLOAT
+            and (sb == sa[1:] or sb == (1,) + sa[1:])):
+        # the left operand is a layer matmul that has not been launched and the right one a
+        # row vector: matmul + bias in one call (sp.py:630-635); the matmul node's own value
+        # stays deferred unless somebody reads it
+        _, av, bv, rows, n, k = tag
+        value = DeviceArray.empty(sa)
+        F.sp_gemm_bias(rows, n, k, av.ptr, bv.ptr, b.array.ptr, value.ptr, _precision, A.stream())
+    else:
+        value = A.binary("add", a.array, b.array)
     return Variable(value, [
         (a, lambda g: _unbroadcast(g, sa, ra)),
         (b, lambda g: _unbroadcast(g, sb, rb)),
@@ -657,7 +673,16 @@ def matmul(a: Variable, b: Variable) -> Variable:
     if not b_batch:
         # [..., M, K] x [K, N]: one GEMM over the flattened rows (the layer case)
         rows = math.prod(a_batch) * M
-        value = _gemm(0, 0, rows, N, K, av, K, 0, bv, N, 0, 1, a_batch + (M, N))
+        if _fuse_bias and N <= 16 and a.local_gradients and len(a_batch) == 0 and rows and K:
+            # the 10-way classifier: deferred so that `+ bias` (core.add) can run as part of
+            # the same kernel; anything else that touches the product launches it as usual
+            value = DeviceArray.deferred(
+                (M, N),
+                lambda out: F.sp_gemm(0, 0, rows, N, K, av.ptr, K, 0, bv.ptr, N, 0, out.ptr, N,
+                                      rows * N, 1, _precision, A.stream()),
+                ("matmul", av, bv, rows, N, K))
+        else:
+            value = _gemm(0, 0, rows, N, K, av, K, 0, bv, N, 0, 1, a_batch + (M, N))
 
         def grad_a(g):  # g . b^T
             return _gemm(0, 1, rows, K, N, g, N, 0, bv, N, 0, 1, av.shape)
@@ -870,7 +895,14 @@ def cross_entropy(y_pred: Variable, y_true: np.ndarray, axis: int = -1) -> Varia
 
         def grad_logits(g):
             dlogits = DeviceArray.empty(logits.shape)
-            if dlogits.size:
+            if dlogits.size and _fuse_bias and rows * cols <= 32768:
+                # also emits the column sums: the gradient of a bias added to the logits, which
+                # core._unbroadcast picks up instead of launching a reduction
+                colsum = DeviceArray.empty((cols,))
+                F.sp_softmax_xent_bwd_colsum(probs.ptr, labels.ptr, g.ptr, dlogits.ptr, colsum.ptr,
+                                             rows, cols, A.stream())
+                dlogits._aux = ("colsum0", colsum)
+            elif dlogits.size:
                 F.sp_softmax_xent_bwd(probs.ptr, labels.ptr, g.ptr, dlogits.ptr, rows, cols,
                                       A.stream())
             return dlogits

@@ -161,6 +161,41 @@ int sp_debug_tma2_trace(void* device_buffer) {
   return 0;
 }
 
+// C[M, N] = A[M, K] . B[K, N] + bias[N] (row-major, dense): the linear layer of sp.py:630-635,
+// `add(matmul(x, w), b)`, in one call.  N <= 16 with a long K runs as ONE kernel (skinny rows
+// kernel, bias added after the complete sum: bit-identical to matmul followed by add);
+// anything else is the ordinary GEMM followed by an in-place row-vector add.
+int sp_gemm_bias(int64_t M, int64_t N, int64_t K, const float* A, const float* B,
+                 const float* bias, float* C, int precision, sp_stream_t stream) {
+  SP_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative extent");
+  SP_REQUIRE(precision == SP_PRECISION_FP32 || precision == SP_PRECISION_TF32, "bad precision");
+  if (M == 0 || N == 0) return 0;
+  if (K > 0) {
+    sp::IgemmParams p = sp::base_params();
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.A = A;
+    p.B = B;
+    p.C = C;
+    p.ldc = N;
+    p.a_rs = K;
+    p.a_cs = 1;
+    p.b_rs = N;
+    p.b_cs = 1;
+    p.bias = bias;
+    if (!sp::use_umma(sp::kGemm, p, precision) && sp::g_umma_policy != 1 &&
+        sp::gemm_skinny_supported(p)) {
+      if (int rc = sp::launch_gemm_skinny(p, sp::as_stream(stream))) return rc;
+      SP_CHECK_LAUNCH("gemm_bias(skinny)");
+      return 0;
+    }
+  }
+  if (int rc = sp_gemm(0, 0, M, N, K, A, K, 0, B, N, 0, C, N, M * N, 1, precision, stream)) return rc;
+  const int64_t shape[2] = {M, N}, sc[2] = {N, 1}, sb[2] = {0, 1};
+  return sp_ewise_binary(SP_BINARY_ADD, C, sc, bias, sb, C, 2, shape, stream);
+}
+
 int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
             int64_t strideA, const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc,
             int64_t strideC, int64_t batch, int precision, sp_stream_t stream) {

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kThreads) gemm_skinny_rows_kernel(const IgemmP
       if (m0 + r < p.M) {
         float s = part[r][n];
         for (int q = 1; q < splits; ++q) s += *cluster.map_shared_rank(&part[r][n], q);
+        if (p.bias) s += p.bias[n];  // after the full sum: the same bits as a separate add
         p.C[(m0 + r) * p.ldc + n] = s;
       }
     }

@@ -27,6 +27,7 @@ struct IgemmParams {
   const float* B;
   float* C;
   int64_t ldc;
+  const float* bias;  // optional row vector added to every output row (skinny GEMM only)
   // dense operand strides (kGemm)
   int64_t a_rs, a_cs, b_rs, b_cs;
   // strided batch (kGemm): blockIdx.z selects the batch

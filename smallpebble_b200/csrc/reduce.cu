@@ -354,6 +354,33 @@ __global__ void __launch_bounds__(kThreads) softmax_xent_bwd_kernel(
   }
 }
 
+// softmax-cross-entropy backward that also returns the column sums of its output -- the bias
+// gradient of the classifier layer (add's unbroadcast-sum, sp.py:183-189) -- so the tiny
+// [batch, classes] gradient is not re-read by a reduction launch of its own.  One block: the
+// gradient is written, then warp w sums columns w, w + warps, ... over the rows in a fixed
+// shuffle-tree order (deterministic).
+__global__ void __launch_bounds__(1024) softmax_xent_bwd_colsum_kernel(
+    const float* __restrict__ probs, const int32_t* __restrict__ labels,
+    const float* __restrict__ gloss, float* __restrict__ dlogits, float* __restrict__ colsum,
+    int rows, int cols) {
+  pdl_entry();
+  const float g = gloss[0];
+  const int total = rows * cols;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int r = i / cols;
+    const int c = i - r * cols;
+    dlogits[i] = g * (probs[i] - ((c == labels[r]) ? 1.f : 0.f));
+  }
+  __syncthreads();  // block-scope visibility of the global writes above
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  for (int c = warp; c < cols; c += warps) {
+    float acc = 0.f;
+    for (int r = lane; r < rows; r += 32) acc += dlogits[r * cols + c];
+    acc = warp_sum(acc);
+    if (lane == 0) colsum[c] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) sum_partials_kernel(const float* __restrict__ part,
                                                                 float* __restrict__ out, int n) {
   pdl_entry();
@@ -558,6 +585,22 @@ int sp_softmax_xent_bwd(const float* probs, const int32_t* labels, const float* 
   sp::launch_pdl(softmax_xent_bwd_kernel, dim3(sp::wave_grid(rows * cols, kThreads, 8)), dim3(kThreads), 0, sp::as_stream(stream), probs, labels, gloss, dlogits, rows, cols);
   SP_CHECK_LAUNCH("softmax_xent_bwd");
   return 0;
+}
+
+int sp_softmax_xent_bwd_colsum(const float* probs, const int32_t* labels, const float* gloss,
+                               float* dlogits, float* colsum, int64_t rows, int64_t cols,
+                               sp_stream_t stream) {
+  if (cols <= 0) return 0;
+  if (rows <= 0) return sp_fill_f32(colsum, cols, 0.f, stream);
+  if (rows * cols <= 32768) {
+    sp::launch_pdl(softmax_xent_bwd_colsum_kernel, dim3(1), dim3(rows * cols > 4096 ? 1024 : 256),
+                   0, sp::as_stream(stream), probs, labels, gloss, dlogits, colsum, (int)rows,
+                   (int)cols);
+    SP_CHECK_LAUNCH("softmax_xent_bwd_colsum");
+    return 0;
+  }
+  if (int rc = sp_softmax_xent_bwd(probs, labels, gloss, dlogits, rows, cols, stream)) return rc;
+  return sp_reduce_sum(dlogits, colsum, 1, rows, cols, stream);
 }
 
 }  // extern "C"

@@ -239,3 +239,49 @@ def test_softmax_is_folded_into_cross_entropy_and_still_readable():
     ref = np.exp(logits - logits.max(1, keepdims=True))
     ref /= ref.sum(1, keepdims=True)
     assert_close(p1, ref, 1e-5, "probs")
+
+
+@pytest.mark.parametrize("rows,k,n,bias_shape", [(128, 1152, 10, (10,)), (37, 300, 16, (1, 16)),
+                                                  (256, 4608, 10, (10,))])
+def test_classifier_bias_fusions_match_the_separate_ops(rows, k, n, bias_shape):
+    """matmul(op_result, w) + bias for N <= 16 is ONE kernel (deferred matmul consumed by add),
+    and the bias gradient comes out of the softmax-cross-entropy backward kernel as a
+    by-product.  Values and the weight / input gradients are bit-identical to the separate
+    launches; the bias gradient is the same sum in a different (fixed) order."""
+    from smallpebble_b200 import _abi
+
+    rng = np.random.default_rng(rows + k)
+    x = rng.random((rows, k)) - 0.5
+    w = (rng.random((k, n)) - 0.5) / np.sqrt(k)
+    b = rng.random(bias_shape) - 0.5
+    labels = rng.integers(0, n, rows)
+
+    from smallpebble_b200 import core
+
+    def run(fuse):
+        core._fuse_bias = fuse  # only these two fusions: the loss kernels stay the same
+        try:
+            xv, wv, bv = sp.Variable(x), sp.Variable(w), sp.Variable(b)
+            pre = sp.mul(xv, sp.Variable(np.full(x.shape, 1.25)))  # an op result feeds matmul
+            before = _abi.counter.launches
+            z = sp.matmul(pre, wv)
+            logits = sp.add(z, bv)
+            fwd_launches = _abi.counter.launches - before
+            assert (z.array.pending_tag is not None) == fuse  # never launched when fused
+            loss = sp.cross_entropy(sp.softmax(logits), labels)
+            g = sp.get_gradients(loss)
+            out = [np.asarray(logits.array), np.asarray(loss.array), np.asarray(g[wv]),
+                   np.asarray(g[xv]), np.asarray(g[bv]), np.asarray(z.array)]
+            return out, fwd_launches
+        finally:
+            core._fuse_bias = True
+
+    fused, n_fused = run(True)
+    plain, n_plain = run(False)
+    assert n_fused == 1 and n_plain == 2
+    for i in (0, 1, 2, 3, 5):
+        assert np.array_equal(fused[i], plain[i]), i
+    assert fused[4].shape == bias_shape
+    assert_close(fused[4], plain[4], 1e-6, "bias gradient")
+    ref = (x * 1.25) @ w
+    assert_close(fused[5], ref, 2e-5 if n < 16 else 2e-3, "deferred matmul value, read after the fact")
