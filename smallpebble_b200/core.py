@@ -123,6 +123,10 @@ class Gradients(dict):
         super().__init__()
         self._deferred = {}
 
+    # plain dict access for get_gradients' own sweep (no deferred-leaf handling)
+    get_plain = dict.get
+    put_plain = dict.__setitem__
+
     def _defer(self, child, fn, path_value):
         self._deferred.setdefault(child, []).append((fn, path_value))
 
@@ -243,14 +247,21 @@ def get_gradients(variable: Variable) -> dict:
     dict.__setitem__(gradients, variable, seed)
     # gradient buffers nobody else aliases: safe to accumulate in place
     owned = {variable} if fresh else set()
+    get, put = gradients.get_plain, gradients.put_plain
     for node in order:
-        path_value = dict.__getitem__(gradients, node)
+        path_value = get(node)
         for child, multiply_by_locgrad in node.local_gradients:
             if (not child.local_gradients and not getattr(child, "is_learnable", False)
                     and not _eager_leaf_grads):
                 gradients._defer(child, multiply_by_locgrad, path_value)
                 continue
-            _accumulate(gradients, owned, child, _as_device(multiply_by_locgrad(path_value)))
+            value = multiply_by_locgrad(path_value)
+            if type(value) is not DeviceArray:
+                value = _as_device(value)
+            if get(child) is None:
+                put(child, value)  # first contribution: may alias the upstream buffer
+            else:
+                _accumulate(gradients, owned, child, value)
     return gradients
 
 

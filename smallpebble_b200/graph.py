@@ -152,6 +152,7 @@ class Adam:
         self._step = {}  # Variable -> device int32[1]: completed steps (read by the kernel)
         self.t = _StepCounts(self._step)
         self._tables = {}  # ids of the parameter arrays -> cached ctypes pointer tables
+        self._g_ptrs, self._g_tab = None, None  # last step's gradient pointers and their table
 
     def training_step(self, variables, gradients) -> None:
         from . import distributed
@@ -179,8 +180,13 @@ class Adam:
                 _ptr_table([self._step[v].ptr for v in variables]),
             )
         p_tab, m_tab, v_tab, numel, step_tab = static
-        F.sp_adam_multi(n, p_tab, _ptr_table([g.ptr for g in grads]), m_tab, v_tab, numel,
-                        step_tab, self.alpha, self.beta1, self.beta2, self.eps, A.stream())
+        # gradient buffers come out of the recycling pool in the same order every step: the
+        # pointer table of the previous step is usually still right
+        g_ptrs = tuple([g.ptr for g in grads])
+        if g_ptrs != self._g_ptrs:
+            self._g_ptrs, self._g_tab = g_ptrs, _ptr_table(g_ptrs)
+        F.sp_adam_multi(n, p_tab, self._g_tab, m_tab, v_tab, numel, step_tab, self.alpha,
+                        self.beta1, self.beta2, self.eps, A.stream())
 
 
 def sgd_step(variables, gradients, learning_rate: float = 0.001) -> None:
