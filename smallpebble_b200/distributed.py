@@ -160,6 +160,15 @@ def _direct_nccl():
         if int(flag.item()) != 1:
             return None
         _nccl["lib"], _nccl["comm"] = lib, comm
+        # the same vectorcall trampoline the C ABI uses (7 integer-class arguments): ~0.3 us
+        # per call instead of ~4 us of ctypes argument conversion
+        fast = _abi._load_fast()
+        if fast is not None:
+            def _nccl_failed(name, rc):
+                raise RuntimeError(f"{name} failed with code {rc}")
+
+            _nccl["fast"] = fast.bind(C.cast(lib.ncclAllReduce, C.c_void_p).value, "ppppppp",
+                                      "ncclAllReduce", _nccl_failed, False)
         return lib, comm
     except Exception:  # noqa: BLE001 - any trouble: torch.distributed does the exchange
         _nccl["comm"] = None
@@ -173,11 +182,15 @@ def _allreduce_sum_f32(ptr: int, count: int, tensor_view) -> None:
     direct = _direct_nccl()
     if direct is not None:
         lib, comm = direct
-        rc = lib.ncclAllReduce(ptr, ptr, count, 7, 0, comm, A.stream())  # ncclFloat32, ncclSum
+        call = _nccl.get("fast")
+        if call is not None:
+            call(ptr, ptr, count, 7, 0, comm.value, A.stream())  # ncclFloat32, ncclSum
+            return
+        rc = lib.ncclAllReduce(ptr, ptr, count, 7, 0, comm, A.stream())
         if rc != 0:
             raise RuntimeError(f"ncclAllReduce failed with code {rc}")
         return
-    dist.all_reduce(tensor_view, op=dist.ReduceOp.SUM)
+    dist.all_reduce(tensor_view[:count], op=dist.ReduceOp.SUM)
 
 
 def bucket_layout(sizes) -> list[int]:
@@ -190,28 +203,51 @@ def bucket_layout(sizes) -> list[int]:
     return offsets + [cur]
 
 
+_plans = {}  # gradient shapes -> (layout, total, ctypes size / offset tables)
+
+
+def _bucket_plan(shapes, sizes):
+    plan = _plans.get(shapes)
+    if plan is None:
+        layout = bucket_layout(sizes)
+        plan = _plans[shapes] = (layout, layout[-1], _abi.dims(sizes), _abi.dims(layout[:-1]),
+                                 {"ptrs": None, "table": None, "views": None, "base": None})
+    return plan
+
+
 def allreduce_gradients(grads):
     """Sum each gradient over all ranks.  Returns arrays that alias the flat bucket."""
     import torch
     import torch.distributed as dist
 
     sizes = [g.size for g in grads]
-    layout = bucket_layout(sizes)
-    total = layout[-1]
     on_gpu = _state["backend"] == "nccl"
     if on_gpu:
+        # everything that is the same every step is built once per set of gradient shapes: the
+        # bucket layout, the size / offset tables of the pack kernel, its pointer table (the
+        # gradient buffers come out of the recycling pool in the same order every step) and
+        # the views of the bucket that are handed to the optimiser
+        layout, total, c_sizes, c_offsets, cache = _bucket_plan(tuple([g.shape for g in grads]),
+                                                               sizes)
         bucket = _state["bucket"]
         if bucket is None or bucket.numel() < total:
             bucket = torch.empty(max(total, 1), dtype=torch.float32, device=A.require_cuda())
             _state["bucket"] = bucket
         base = bucket.data_ptr()
-        import ctypes as C
+        ptrs = tuple([g.ptr for g in grads])
+        if ptrs != cache["ptrs"]:
+            import ctypes as C
 
-        _abi.f.sp_pack_multi(len(grads), (C.c_void_p * len(grads))(*[g.ptr for g in grads]),
-                             _abi.dims(sizes), _abi.dims(layout[:-1]), base, A.stream())
-        _allreduce_sum_f32(base, total, bucket[:total])
-        return [DeviceArray(g.shape, A.FLOAT, bucket, base + 4 * off)
-                for g, off in zip(grads, layout)]
+            cache["ptrs"], cache["table"] = ptrs, (C.c_void_p * len(ptrs))(*ptrs)
+        _abi.f.sp_pack_multi(len(grads), cache["table"], c_sizes, c_offsets, base, A.stream())
+        _allreduce_sum_f32(base, total, bucket)
+        if cache["base"] != base:
+            cache["base"] = base
+            cache["views"] = [DeviceArray(g.shape, A.FLOAT, bucket, base + 4 * off)
+                              for g, off in zip(grads, layout)]
+        return cache["views"]
+    layout = bucket_layout(sizes)
+    total = layout[-1]
     # host path (gloo): plumbing tests on machines without a GPU
     bucket = torch.zeros(max(total, 1), dtype=torch.float32)
     view = bucket.numpy()
