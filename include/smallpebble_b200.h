@@ -211,6 +211,11 @@ typedef struct sp_conv_geom {
 /* y = im2col(x) * w           (implicit GEMM M=N*OH*OW, N=K, K=KH*KW*C)  */
 int sp_conv2d_fprop(const float* x, const float* w, float* y, const sp_conv_geom* g,
                     int precision, sp_stream_t stream);
+/* leaky_relu(conv2d(x, w), alpha) in one call (sp.py:231-236 applied in the kernel's epilogue
+ * where the kernel has one, the ordinary leaky kernel in place otherwise): bit-identical to
+ * sp_conv2d_fprop followed by sp_leaky_relu_fwd */
+int sp_conv2d_fprop_leaky(const float* x, const float* w, float* y, const sp_conv_geom* g,
+                          int precision, float alpha, sp_stream_t stream);
 /* dx = col2im(gy * w^T) in gather form (replaces np.add.at, sp.py:384-387) */
 int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_geom* g,
                     int precision, sp_stream_t stream);

@@ -66,16 +66,18 @@ _fuse_softmax_xent = os.environ.get("SP_FUSE_SOFTMAX_XENT", "1") != "0"
 
 _fuse_leaky_pool = os.environ.get("SP_FUSE_LEAKY_POOL", "1") != "0"
 _fuse_bias = os.environ.get("SP_FUSE_BIAS", "1") != "0"
+_fuse_conv_leaky = os.environ.get("SP_FUSE_CONV_LEAKY", "1") != "0"
 
 
 def set_fusion(enabled: bool) -> None:
     """Fuse cross_entropy(softmax(x)) into one forward and one backward kernel (default on).
     With fusion the loss's tape edge goes straight to the logits, so `get_gradients` has no
     entry for the intermediate probability node; turn it off to get that entry."""
-    global _fuse_softmax_xent, _fuse_leaky_pool, _fuse_bias
+    global _fuse_softmax_xent, _fuse_leaky_pool, _fuse_bias, _fuse_conv_leaky
     _fuse_softmax_xent = bool(enabled)
     _fuse_leaky_pool = bool(enabled)
     _fuse_bias = bool(enabled)
+    _fuse_conv_leaky = bool(enabled)
 
 
 # --------------------------------------------------------------------------------------------
@@ -471,7 +473,14 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
     alpha = float(alpha)
 
     def launch(out):
-        F.sp_leaky_relu_fwd(x.ptr, out.ptr, x.size, alpha, A.stream())
+        tag = x.pending_tag
+        if tag is not None and tag[0] == "conv2d" and alpha > 0:
+            # the input is a conv2d that has not been launched: the activation is applied in
+            # the conv kernel's epilogue and the pre-activation tensor is never written
+            _, cx, cw, geom, prec = tag
+            F.sp_conv2d_fprop_leaky(cx.ptr, cw.ptr, out.ptr, geom, prec, alpha, A.stream())
+        else:
+            F.sp_leaky_relu_fwd(x.ptr, out.ptr, x.size, alpha, A.stream())
 
     if _fuse_leaky_pool and a.local_gradients and x.ndim == 4 and x.size:
         y = DeviceArray.deferred(x.shape, launch, ("leaky_relu", x, alpha))
@@ -489,7 +498,10 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
             F.sp_maxpool2d_leaky_bwd(g0.ptr, idx.ptr, x.ptr, dx.ptr, *geom, alpha, A.stream())
             return dx
         g = _as_device(g)
-        F.sp_leaky_relu_bwd(g.ptr, x.ptr, dx.ptr, x.size, alpha, A.stream())
+        # the slope depends on the sign of the input only; when the input was never stored
+        # (conv + leaky ran as one kernel, alpha > 0) the output has the same sign
+        src = y if (x.pending_tag is not None and y.pending_tag is None and alpha > 0) else x
+        F.sp_leaky_relu_bwd(g.ptr, src.ptr, dx.ptr, x.size, alpha, A.stream())
         return dx
 
     return Variable(y, [(a, multiply_by_locgrad)])
@@ -754,9 +766,19 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
     x, w = images.array, kernels.array
     plan = _conv_plan(x.shape, w.shape, padding, tuple(strides))
     geom, out_shape = plan[0], plan[1]
-    y = DeviceArray.empty(out_shape)
-    if y.size:
-        F.sp_conv2d_fprop(x.ptr, w.ptr, y.ptr, geom, _precision, A.stream())
+    prec = _precision
+
+    def launch(out):
+        if out.size:
+            F.sp_conv2d_fprop(x.ptr, w.ptr, out.ptr, geom, prec, A.stream())
+
+    if _fuse_conv_leaky and math.prod(out_shape):
+        # not launched yet: a leaky_relu consumer folds its activation into this kernel's
+        # epilogue (core.leaky_relu); anything else that touches the result launches it as usual
+        y = DeviceArray.deferred(out_shape, launch, ("conv2d", x, w, geom, prec))
+    else:
+        y = DeviceArray.empty(out_shape)
+        launch(y)
 
     def grad_images(g):
         dx = DeviceArray.empty(x.shape)

@@ -264,8 +264,12 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   return 0;
 }
 
-int sp_conv2d_fprop(const float* x, const float* w, float* y, const sp_conv_geom* g,
-                    int precision, sp_stream_t stream) {
+// conv2d forward, optionally with leaky_relu applied to the result in the kernel's epilogue
+// (leaky != 0): `leaky_relu(conv2d(x, w))` of the VGG-style models without the extra read and
+// write of the activation.  Kernels without that epilogue run the ordinary leaky kernel in
+// place afterwards -- the values are the same bits either way.
+static int conv2d_fprop_impl(const float* x, const float* w, float* y, const sp_conv_geom* g,
+                             int precision, int leaky, float alpha, sp_stream_t stream) {
   if (int rc = sp::check_geom(g)) return rc;
   sp::IgemmParams p = sp::base_params();
   p.g = *g;
@@ -276,20 +280,42 @@ int sp_conv2d_fprop(const float* x, const float* w, float* y, const sp_conv_geom
   p.B = w;
   p.C = y;
   p.ldc = g->K;
+  p.leaky = leaky;
+  p.leaky_alpha = alpha;
   if (p.M == 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
+  bool fused = false;
   if (sp::g_umma_policy == 0 && sp::small_c_supported(*g)) {
-    if (int rc = sp::launch_conv_fprop_smallc(x, w, y, *g, precision, st)) return rc;
+    if (int rc = sp::launch_conv_fprop_smallc(x, w, y, *g, precision, st, leaky, alpha, &fused))
+      return rc;
     SP_CHECK_LAUNCH("conv2d_fprop(small C)");
-    return 0;
+  } else {
+    int rc;
+    if (sp::use_halo(sp::kFprop, p, precision)) {
+      rc = sp::launch_conv_halo2(sp::kFprop, p, st);
+      fused = true;
+    } else if (sp::use_tma2(sp::kFprop, p, precision)) {
+      rc = sp::launch_conv_tma2(sp::kFprop, p, st);
+      fused = true;
+    } else {
+      rc = sp::use_umma(sp::kFprop, p, precision) ? sp::launch_igemm_umma(sp::kFprop, p, st)
+                                                  : sp::launch_igemm_simt(sp::kFprop, p, st);
+    }
+    if (rc) return rc;
+    SP_CHECK_LAUNCH("conv2d_fprop");
   }
-  int rc = sp::use_halo(sp::kFprop, p, precision)   ? sp::launch_conv_halo2(sp::kFprop, p, st)
-           : sp::use_tma2(sp::kFprop, p, precision) ? sp::launch_conv_tma2(sp::kFprop, p, st)
-           : sp::use_umma(sp::kFprop, p, precision) ? sp::launch_igemm_umma(sp::kFprop, p, st)
-                                                    : sp::launch_igemm_simt(sp::kFprop, p, st);
-  if (rc) return rc;
-  SP_CHECK_LAUNCH("conv2d_fprop");
+  if (leaky && !fused) return sp_leaky_relu_fwd(y, y, p.M * p.N, alpha, stream);
   return 0;
+}
+
+int sp_conv2d_fprop(const float* x, const float* w, float* y, const sp_conv_geom* g,
+                    int precision, sp_stream_t stream) {
+  return conv2d_fprop_impl(x, w, y, g, precision, 0, 0.f, stream);
+}
+
+int sp_conv2d_fprop_leaky(const float* x, const float* w, float* y, const sp_conv_geom* g,
+                          int precision, float alpha, sp_stream_t stream) {
+  return conv2d_fprop_impl(x, w, y, g, precision, 1, alpha, stream);
 }
 
 int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_geom* g,

@@ -863,7 +863,8 @@ struct RgbFpropPlan {
 template <int KT>
 __global__ void __launch_bounds__(kThreads, KT == 4 ? 1 : 2) conv_fprop_rgb3x3_mma_kernel(
     const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
-    const __grid_constant__ sp_conv_geom g, const __grid_constant__ RgbFpropPlan pl) {
+    const __grid_constant__ sp_conv_geom g, const __grid_constant__ RgbFpropPlan pl,
+    const int leaky, const float alpha) {
   pdl_entry();
   constexpr int K = 16 * KT, NJ = K / 8, KC = 27;
   extern __shared__ __align__(16) float sm[];
@@ -937,6 +938,12 @@ __global__ void __launch_bounds__(kThreads, KT == 4 ? 1 : 2) conv_fprop_rgb3x3_m
         a[3] = ab[offa[s][1] + 24];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) mma_tf32_m16n8k8(acc[j], a, bf[s][j]);
+      }
+      if (leaky) {  // fused leaky_relu epilogue: the same bits as a separate launch
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[j][c] = acc[j][c] > 0.f ? acc[j][c] : alpha * acc[j][c];
       }
       float* yrow = y + ((int64_t)(n * g.OH + oy0 + r) * g.OW + xv0 + gq) * K + 2 * t;
       if (xv0 + gq < g.OW) {
@@ -1117,7 +1124,7 @@ static RgbFpropPlan rgb_fprop_plan(const sp_conv_geom& g, int slots) {
 
 template <int KT>
 static int launch_rgb_fprop_mma(const float* x, const float* w, float* y, const sp_conv_geom& g,
-                                cudaStream_t st) {
+                                cudaStream_t st, int leaky, float alpha) {
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int per_sm = KT == 4 ? 1 : 2;
   const RgbFpropPlan pl = rgb_fprop_plan(g, per_sm * sms);
@@ -1130,7 +1137,8 @@ static int launch_rgb_fprop_mma(const float* x, const float* w, float* y, const 
     attr_done = true;
   }
   const int blocks = std::min(per_sm * sms, pl.n_tiles);
-  sp::launch_pdl(conv_fprop_rgb3x3_mma_kernel<KT>, dim3(blocks), dim3(kThreads), smem, st, x, w, y, g, pl);
+  sp::launch_pdl(conv_fprop_rgb3x3_mma_kernel<KT>, dim3(blocks), dim3(kThreads), smem, st, x, w, y,
+                 g, pl, leaky, alpha);
   return 0;
 }
 
@@ -1147,13 +1155,16 @@ int small_c_wgrad_blocks(const sp_conv_geom& g) {
 }
 
 int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_conv_geom& g,
-                             int precision, cudaStream_t st) {
+                             int precision, cudaStream_t st, int leaky, float alpha,
+                             bool* fused_leaky) {
+  if (fused_leaky) *fused_leaky = false;
   if (precision == SP_PRECISION_TF32 && (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
     // tensor-core kernel when the geometry qualifies (returns 1 when it does not)
-    const int rc = g.K == 16   ? launch_rgb_fprop_mma<1>(x, w, y, g, st)
-                   : g.K == 32 ? launch_rgb_fprop_mma<2>(x, w, y, g, st)
-                   : g.K == 64 ? launch_rgb_fprop_mma<4>(x, w, y, g, st)
+    const int rc = g.K == 16   ? launch_rgb_fprop_mma<1>(x, w, y, g, st, leaky, alpha)
+                   : g.K == 32 ? launch_rgb_fprop_mma<2>(x, w, y, g, st, leaky, alpha)
+                   : g.K == 64 ? launch_rgb_fprop_mma<4>(x, w, y, g, st, leaky, alpha)
                                : 1;
+    if (rc == 0 && fused_leaky) *fused_leaky = leaky != 0;
     if (rc <= 0) return rc;
   }
   const int kc = g.KH * g.KW * g.C;

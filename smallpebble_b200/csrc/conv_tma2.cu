@@ -68,6 +68,8 @@ struct Tma2Params {
   int stages;          // ring depth: narrow tiles are bound by the load round trip, not by the
   uint32_t stage_bytes;  // tensor core, so whatever B does not need buys more stages in flight
   long long* trace;    // sp_debug_tma2_trace: clock64 stamps of cluster 0's leader CTA, or null
+  int leaky;           // fprop epilogue: out = v > 0 ? v : alpha * v
+  float alpha;
   float* C;
   int64_t ldc;
   int64_t split_stride;
@@ -296,6 +298,13 @@ __device__ __forceinline__ void trace_at(const Tma2Params& p, bool on, int slot)
 // XOR-swizzled shared tile (conflict-free both ways) so that one instruction writes 4 rows x
 // 128 contiguous bytes.  rp[r] = address of row (lane / 8 + 4 r) at the tile's first column.
 constexpr uint32_t kEpiBytes = 4u * 4096u;  // one 4 KB tile per epilogue warp
+__device__ __forceinline__ void leaky_block(uint32_t (&v)[32], float alpha) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float f = __uint_as_float(v[j]);
+    v[j] = __float_as_uint(f > 0.f ? f : alpha * f);
+  }
+}
 __device__ __forceinline__ void store_block_rows(uint8_t* tile, const uint32_t (&v)[32], int lane,
                                                  float* const (&rp)[8], uint32_t ok_mask, int cb) {
   float4* t4 = reinterpret_cast<float4*>(tile);
@@ -642,6 +651,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
         tmem_ld_wait();
+        if (p.leaky) leaky_block(v, p.alpha);
         if (vec_store) {
           store_block_rows(epi_tile, v, lane, rp, ok_mask, cb);
         } else if (m < p.M) {
@@ -702,6 +712,8 @@ struct HaloParams {
   uint32_t b_bytes;      // one B stage (BN/2 rows or columns x 128 B)
   int b_stages;
   long long* trace;    // sp_debug_tma2_trace (cluster 0, leader CTA), or null
+  int leaky;           // fprop epilogue: out = v > 0 ? v : alpha * v
+  float alpha;
   float* C;
   int64_t ldc;
 };
@@ -988,6 +1000,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
         tmem_ld_wait();
+        if (p.leaky) leaky_block(v, p.alpha);
         if (vec_store) {
           store_block_rows(epi_tile, v, lane, rp, ok_mask, cb);
         } else if (valid) {
@@ -1234,6 +1247,8 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
     if (forced >= 2 && forced < p.stages) p.stages = forced;
   }
   p.trace = g_trace;
+  p.leaky = (mode == kFprop) ? ip.leaky : 0;
+  p.alpha = ip.leaky_alpha;
   const int up_h = (g.OH - 1) * g.sy + 1 - g.H - g.pad_t, up_w = (g.OW - 1) * g.sx + 1 - g.W - g.pad_l;
   if (mode == kFprop) {
     p.cblocks = g.C / 32;
@@ -1412,6 +1427,8 @@ int launch_conv_halo2(int mode, const IgemmParams& ip, cudaStream_t st) {
   p.C = ip.C;
   p.ldc = ip.ldc;
   p.trace = g_trace;
+  p.leaky = (mode == kFprop) ? ip.leaky : 0;
+  p.alpha = ip.leaky_alpha;
   const int bnh_max = (p.N >= 256 ? 256 : p.N) / 2;
   alignas(64) CUtensorMap tmA, tmB;
   bool ok = true;

@@ -28,6 +28,10 @@ struct IgemmParams {
   float* C;
   int64_t ldc;
   const float* bias;  // optional row vector added to every output row (skinny GEMM only)
+  // optional leaky_relu epilogue (conv fprop in the 2-SM and first-layer kernels):
+  // out = v > 0 ? v : leaky_alpha * v, the same bits as a separate leaky_relu launch
+  int leaky;
+  float leaky_alpha;
   // dense operand strides (kGemm)
   int64_t a_rs, a_cs, b_rs, b_cs;
   // strided batch (kGemm): blockIdx.z selects the batch
@@ -66,8 +70,10 @@ int launch_gemm_skinny(const IgemmParams& p, cudaStream_t stream);
 // First-layer (C <= 4) CUDA-core kernels, conv_smallc.cu
 bool small_c_supported(const sp_conv_geom& g);
 int small_c_wgrad_blocks(const sp_conv_geom& g);
+// *fused_leaky = true when the kernel applied the leaky_relu epilogue itself (leaky != 0)
 int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_conv_geom& g,
-                             int precision, cudaStream_t st);
+                             int precision, cudaStream_t st, int leaky = 0, float alpha = 0.f,
+                             bool* fused_leaky = nullptr);
 // `*reduced` = true when the kernel already summed its partial filters into dw
 int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial, float* dw,
                              const sp_conv_geom& g, int blocks, int precision, cudaStream_t st,

@@ -285,3 +285,52 @@ def test_classifier_bias_fusions_match_the_separate_ops(rows, k, n, bias_shape):
     assert_close(fused[4], plain[4], 1e-6, "bias gradient")
     ref = (x * 1.25) @ w
     assert_close(fused[5], ref, 2e-5 if n < 16 else 2e-3, "deferred matmul value, read after the fact")
+
+
+@pytest.mark.parametrize("policy", [0, 32 + 256, 32 + 128], ids=["policy", "tma2", "halo"])
+@pytest.mark.parametrize("alpha", [0.02, 0.0])
+def test_conv_leaky_epilogue_fusion_is_bit_identical(policy, alpha):
+    """leaky_relu(conv2d(...)) feeding another conv runs as ONE kernel (activation in the conv
+    epilogue: the 2-SM kernels, the first-layer tensor-core kernel, or conv + in-place leaky for
+    the others) and the pre-activation tensor is never stored; leaky's gradient then takes the
+    sign from the activation's output.  Everything must equal the separate launches bit for
+    bit; alpha = 0 (sign no longer preserved) must not take the fused path."""
+    from smallpebble_b200 import core
+
+    rng = np.random.default_rng(11)
+    x = rng.random((4, 12, 12, 3)) - 0.5
+    w1 = (rng.random((3, 3, 3, 32)) - 0.5) * 0.4
+    w2 = (rng.random((3, 3, 32, 64)) - 0.5) * 0.1
+    w3 = (rng.random((3, 3, 64, 64)) - 0.5) * 0.1
+    seed = rng.random((4, 6, 6, 64)) - 0.5
+
+    def run(fuse):
+        old = sp.get_precision()
+        sp.set_precision("tf32")
+        core._fuse_conv_leaky = fuse
+        core.debug_set_kernel_policy(policy)
+        try:
+            xv, v1, v2, v3 = (sp.Variable(a) for a in (x, w1, w2, w3))
+            c1 = sp.conv2d(xv, v1, "SAME")
+            a1 = sp.leaky_relu(c1, alpha)               # -> conv: epilogue fusion
+            c2 = sp.conv2d(a1, v2, "SAME")
+            a2 = sp.leaky_relu(c2, alpha)               # -> pool: pool fusion, conv stored
+            p2 = sp.maxpool2d(a2, 2, 2, strides=[2, 2])
+            c3 = sp.conv2d(p2, v3, "SAME")
+            a3 = sp.leaky_relu(c3, alpha)               # -> mul: plain materialisation
+            out = sp.mul(a3, sp.Variable(seed))
+            g = sp.get_gradients(out)
+            fused_c1 = c1.array.pending_tag is not None  # never launched on its own
+            res = [np.asarray(t) for t in (out.array, a1.array, a2.array, a3.array, g[xv], g[v1],
+                                           g[v2], g[v3], g[c1], g[a1], c1.array)]
+            return res, fused_c1
+        finally:
+            core.debug_set_kernel_policy(0)
+            core._fuse_conv_leaky = True
+            sp.set_precision(old)
+
+    fused, was_fused = run(True)
+    plain, was_plain = run(False)
+    assert was_fused == (alpha > 0) and not was_plain
+    for i, (a, b) in enumerate(zip(fused, plain)):
+        assert np.array_equal(a, b), i
