@@ -219,6 +219,12 @@ int sp_conv2d_fprop_leaky(const float* x, const float* w, float* y, const sp_con
 /* dx = col2im(gy * w^T) in gather form (replaces np.add.at, sp.py:384-387) */
 int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_geom* g,
                     int precision, sp_stream_t stream);
+/* the same, times the gradient of a leaky_relu: dx = dgrad(gy, w) * (act > 0 ? 1 : alpha), `act`
+ * laid out like dx (the leaky_relu's output, or its input: same sign for alpha > 0) -- the
+ * backward of conv2d(leaky_relu(z)) w.r.t. z in one pass; bit-identical to sp_conv2d_dgrad
+ * followed by sp_leaky_relu_bwd */
+int sp_conv2d_dgrad_leaky(const float* gy, const float* w, const float* act, float* dx,
+                          const sp_conv_geom* g, int precision, float alpha, sp_stream_t stream);
 /* dw = im2col(x)^T * gy, split over the N*OH*OW reduction; workspace from
  * sp_conv2d_wgrad_workspace() (may be 0 bytes) */
 size_t sp_conv2d_wgrad_workspace(const sp_conv_geom* g, int precision);

@@ -78,6 +78,7 @@ SIGNATURES = {
     "sp_conv2d_fprop": (C.c_int, [vp, vp, vp, C.POINTER(ConvGeom), C.c_int, vp]),
     "sp_conv2d_fprop_leaky": (C.c_int, [vp, vp, vp, C.POINTER(ConvGeom), C.c_int, f32, vp]),
     "sp_conv2d_dgrad": (C.c_int, [vp, vp, vp, C.POINTER(ConvGeom), C.c_int, vp]),
+    "sp_conv2d_dgrad_leaky": (C.c_int, [vp, vp, vp, vp, C.POINTER(ConvGeom), C.c_int, f32, vp]),
     "sp_conv2d_wgrad_workspace": (sz, [C.POINTER(ConvGeom), C.c_int]),
     "sp_conv2d_wgrad": (C.c_int, [vp, vp, vp, C.POINTER(ConvGeom), C.c_int, vp, sz, vp]),
     "sp_adam_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),

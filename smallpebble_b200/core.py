@@ -497,10 +497,16 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
             _, _, g0, idx, geom = tag
             F.sp_maxpool2d_leaky_bwd(g0.ptr, idx.ptr, x.ptr, dx.ptr, *geom, alpha, A.stream())
             return dx
-        g = _as_device(g)
         # the slope depends on the sign of the input only; when the input was never stored
         # (conv + leaky ran as one kernel, alpha > 0) the output has the same sign
         src = y if (x.pending_tag is not None and y.pending_tag is None and alpha > 0) else x
+        if tag is not None and tag[0] == "conv2d_dgrad":
+            # the upstream gradient is a conv data gradient that has not been launched: the
+            # conv kernel multiplies by this op's slope as it stores
+            _, g0, cw, cgeom, cprec = tag
+            F.sp_conv2d_dgrad_leaky(g0.ptr, cw.ptr, src.ptr, dx.ptr, cgeom, cprec, alpha, A.stream())
+            return dx
+        g = _as_device(g)
         F.sp_leaky_relu_bwd(g.ptr, src.ptr, dx.ptr, x.size, alpha, A.stream())
         return dx
 
@@ -781,9 +787,18 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
         launch(y)
 
     def grad_images(g):
+        prec_b = _precision
+
+        def launch_dgrad(out):
+            if out.size:
+                F.sp_conv2d_dgrad(g.ptr, w.ptr, out.ptr, geom, prec_b, A.stream())
+
+        if _fuse_conv_leaky and x.size and isinstance(g, DeviceArray):
+            # not launched yet: when the consumer is a leaky_relu's gradient closure, the slope
+            # is applied as the data gradient is stored (sp_conv2d_dgrad_leaky)
+            return DeviceArray.deferred(x.shape, launch_dgrad, ("conv2d_dgrad", g, w, geom, prec_b))
         dx = DeviceArray.empty(x.shape)
-        if dx.size:
-            F.sp_conv2d_dgrad(g.ptr, w.ptr, dx.ptr, geom, _precision, A.stream())
+        launch_dgrad(dx)
         return dx
 
     def grad_kernels(g):

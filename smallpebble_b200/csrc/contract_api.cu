@@ -304,7 +304,10 @@ static int conv2d_fprop_impl(const float* x, const float* w, float* y, const sp_
     if (rc) return rc;
     SP_CHECK_LAUNCH("conv2d_fprop");
   }
-  if (leaky && !fused) return sp_leaky_relu_fwd(y, y, p.M * p.N, alpha, stream);
+  if (leaky && !fused) {
+    if (int rc = sp::launch_leaky_fwd_inplace(y, p.M * p.N, alpha, st)) return rc;
+    SP_CHECK_LAUNCH("conv2d_fprop(leaky)");
+  }
   return 0;
 }
 
@@ -318,8 +321,12 @@ int sp_conv2d_fprop_leaky(const float* x, const float* w, float* y, const sp_con
   return conv2d_fprop_impl(x, w, y, g, precision, 1, alpha, stream);
 }
 
-int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_geom* g,
-                    int precision, sp_stream_t stream) {
+// conv2d data gradient, optionally multiplied by the gradient of a leaky_relu whose OUTPUT (or
+// input: same sign for alpha > 0) is `act`, laid out like dx: the backward of
+// conv2d(leaky_relu(z)) with respect to z in one pass.  The 2-SM kernels apply the mask as
+// they store; the others run the ordinary leaky backward kernel in place afterwards.
+static int conv2d_dgrad_impl(const float* gy, const float* w, float* dx, const sp_conv_geom* g,
+                             int precision, const float* act, float alpha, sp_stream_t stream) {
   if (int rc = sp::check_geom(g)) return rc;
   sp::IgemmParams p = sp::base_params();
   p.g = *g;
@@ -330,16 +337,41 @@ int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_ge
   p.B = w;
   p.C = dx;
   p.ldc = g->C;
+  p.act = act;
+  p.leaky_alpha = alpha;
   if (p.M == 0) return 0;
   if ((int64_t)g->OH * g->OW == 0) return sp_fill_f32(dx, p.M * p.N, 0.f, stream);
   cudaStream_t st = sp::as_stream(stream);
-  int rc = sp::use_halo(sp::kDgrad, p, precision)   ? sp::launch_conv_halo2(sp::kDgrad, p, st)
-           : sp::use_tma2(sp::kDgrad, p, precision) ? sp::launch_conv_tma2(sp::kDgrad, p, st)
-           : sp::use_umma(sp::kDgrad, p, precision) ? sp::launch_igemm_umma(sp::kDgrad, p, st)
-                                                    : sp::launch_igemm_simt(sp::kDgrad, p, st);
+  bool fused = false;
+  int rc;
+  if (sp::use_halo(sp::kDgrad, p, precision)) {
+    rc = sp::launch_conv_halo2(sp::kDgrad, p, st);
+    fused = true;
+  } else if (sp::use_tma2(sp::kDgrad, p, precision)) {
+    rc = sp::launch_conv_tma2(sp::kDgrad, p, st);
+    fused = true;
+  } else {
+    rc = sp::use_umma(sp::kDgrad, p, precision) ? sp::launch_igemm_umma(sp::kDgrad, p, st)
+                                                : sp::launch_igemm_simt(sp::kDgrad, p, st);
+  }
   if (rc) return rc;
   SP_CHECK_LAUNCH("conv2d_dgrad");
+  if (act && !fused) {
+    if (int rc = sp::launch_leaky_bwd_inplace(dx, act, p.M * p.N, alpha, st)) return rc;
+    SP_CHECK_LAUNCH("conv2d_dgrad(leaky)");
+  }
   return 0;
+}
+
+int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_geom* g,
+                    int precision, sp_stream_t stream) {
+  return conv2d_dgrad_impl(gy, w, dx, g, precision, nullptr, 0.f, stream);
+}
+
+int sp_conv2d_dgrad_leaky(const float* gy, const float* w, const float* act, float* dx,
+                          const sp_conv_geom* g, int precision, float alpha, sp_stream_t stream) {
+  if (!act) return sp::set_error(SP_ERR_INVALID_ARGUMENT, "conv2d_dgrad_leaky: act is null");
+  return conv2d_dgrad_impl(gy, w, dx, g, precision, act, alpha, stream);
 }
 
 size_t sp_conv2d_wgrad_workspace(const sp_conv_geom* g, int precision) {

@@ -70,6 +70,7 @@ struct Tma2Params {
   long long* trace;    // sp_debug_tma2_trace: clock64 stamps of cluster 0's leader CTA, or null
   int leaky;           // fprop epilogue: out = v > 0 ? v : alpha * v
   float alpha;
+  const float* act;    // dgrad epilogue: out = v * (act > 0 ? 1 : alpha), act laid out like C
   float* C;
   int64_t ldc;
   int64_t split_stride;
@@ -305,8 +306,28 @@ __device__ __forceinline__ void leaky_block(uint32_t (&v)[32], float alpha) {
     v[j] = __float_as_uint(f > 0.f ? f : alpha * f);
   }
 }
+// leaky_relu-backward epilogue: the activation values a block's stores will be masked with,
+// fetched with the same (row, chunk) ownership as the stores.  Issued one block AHEAD (the first
+// block before the accumulator is even ready): eight independent 16-byte loads whose DRAM
+// latency hides behind the TMEM load, the shared-memory turn and the stores of the previous
+// block -- loaded at the point of use they made the epilogue, not the MMA loop, the bound.
+__device__ __forceinline__ void load_act_rows(float4 (&a)[8], float* const (&rp)[8],
+                                              uint32_t ok_mask, int cb, int lane,
+                                              int64_t act_delta) {
+  const int chunk = lane & 7;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    a[r] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if ((ok_mask >> r) & 1u)
+      a[r] = *reinterpret_cast<const float4*>(
+          reinterpret_cast<const char*>(rp[r] + cb + chunk * 4) + act_delta);
+  }
+}
+
 __device__ __forceinline__ void store_block_rows(uint8_t* tile, const uint32_t (&v)[32], int lane,
-                                                 float* const (&rp)[8], uint32_t ok_mask, int cb) {
+                                                 float* const (&rp)[8], uint32_t ok_mask, int cb,
+                                                 bool use_act, const float4 (&act)[8],
+                                                 float alpha) {
   float4* t4 = reinterpret_cast<float4*>(tile);
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -318,7 +339,13 @@ __device__ __forceinline__ void store_block_rows(uint8_t* tile, const uint32_t (
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int row = (lane >> 3) + 4 * r;
-    const float4 val = t4[row * 8 + (chunk ^ (row & 7))];
+    float4 val = t4[row * 8 + (chunk ^ (row & 7))];
+    if (use_act) {
+      val.x *= act[r].x > 0.f ? 1.f : alpha;
+      val.y *= act[r].y > 0.f ? 1.f : alpha;
+      val.z *= act[r].z > 0.f ? 1.f : alpha;
+      val.w *= act[r].w > 0.f ? 1.f : alpha;
+    }
     if ((ok_mask >> r) & 1u) *reinterpret_cast<float4*>(rp[r] + cb + chunk * 4) = val;
   }
   __syncwarp();
@@ -378,7 +405,9 @@ struct ModeCfg {
   static constexpr uint32_t kMnBlock = 128u * kKStage;                // bytes of one MN block
 };
 
-template <int MODE>
+// ACT: the dgrad instantiation with the leaky_relu-backward epilogue (its prefetch registers
+// would otherwise cost the plain data gradient 2-3 %)
+template <int MODE, bool ACT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_tma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ Tma2Params p) {
@@ -625,14 +654,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const uint32_t empty_leader0 = mapa(tmem_empty_bar(0), 0);
     const bool vec_store = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                            ((p.split_stride & 3) == 0);
+    // leaky_relu backward epilogue: byte distance from an output element to its activation
+    const int64_t act_delta =
+        p.act ? reinterpret_cast<const char*>(p.act) - reinterpret_cast<const char*>(p.C) : 0;
     uint8_t* epi_tile = smem_raw + (tiles - smem_u32(smem_raw)) + kRingBytes + quad * 4096;
     int it = 0;
     for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
       const TileCoord tc = tile_coord(p, tile);
       const int acc = it & 1;
-      mbar_wait(tmem_full_bar(acc), ((uint32_t)it >> 1) & 1u);
-      trace_at(p, tr && warp == kWarpEpi0 && it < 4, 6 + it);
-      tc_fence_after();
       const int m_base = (tc.m_pair * 2 + (int)rank) * 128 + quad * 32;
       const int m = m_base + lane;
       float* __restrict__ cbase =
@@ -646,17 +675,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         rp[r] = cbase + (int64_t)row * p.ldc;
         ok_mask |= (m_base + row < p.M ? 1u : 0u) << r;
       }
+      const bool use_act = ACT && vec_store && act_delta != 0;
+      float4 act_cur[8], act_next[8];
+      if (use_act) load_act_rows(act_cur, rp, ok_mask, 0, lane, act_delta);
+      mbar_wait(tmem_full_bar(acc), ((uint32_t)it >> 1) & 1u);
+      trace_at(p, tr && warp == kWarpEpi0 && it < 4, 6 + it);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccumCols);
       for (int cb = 0; cb < tc.bn; cb += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
+        if (use_act && cb + 32 < tc.bn) load_act_rows(act_next, rp, ok_mask, cb + 32, lane, act_delta);
         tmem_ld_wait();
-        if (p.leaky) leaky_block(v, p.alpha);
+        if (MODE == kFprop && p.leaky) leaky_block(v, p.alpha);
         if (vec_store) {
-          store_block_rows(epi_tile, v, lane, rp, ok_mask, cb);
+          store_block_rows(epi_tile, v, lane, rp, ok_mask, cb, use_act, act_cur, p.alpha);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) act_cur[r] = act_next[r];
         } else if (m < p.M) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) crow[cb + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) {
+            float f = __uint_as_float(v[j]);
+            if (ACT && p.act) f *= p.act[(crow - p.C) + cb + j] > 0.f ? 1.f : p.alpha;
+            crow[cb + j] = f;
+          }
         }
       }
       tc_fence_before();
@@ -714,13 +756,14 @@ struct HaloParams {
   long long* trace;    // sp_debug_tma2_trace (cluster 0, leader CTA), or null
   int leaky;           // fprop epilogue: out = v > 0 ? v : alpha * v
   float alpha;
+  const float* act;    // dgrad epilogue: out = v * (act > 0 ? 1 : alpha), act laid out like C
   float* C;
   int64_t ldc;
 };
 
 constexpr int kMaxBStages = 8;
 
-template <int MODE>
+template <int MODE, bool ACT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ HaloParams p) {
@@ -962,6 +1005,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const int quad = warp & 3;
     const uint32_t empty_leader0 = mapa(tmem_empty_bar(0), 0);
     const bool vec_store = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    // leaky_relu backward epilogue: byte distance from an output element to its activation
+    const int64_t act_delta =
+        p.act ? reinterpret_cast<const char*>(p.act) - reinterpret_cast<const char*>(p.C) : 0;
     uint8_t* epi_tile = smem_raw + (strips - smem_u32(smem_raw)) + 2u * p.strip_bytes +
                         (uint32_t)SB * 2u * p.b_bytes + quad * 4096;
     int it = 0;
@@ -971,9 +1017,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int n0 = n_tile * 256;
       const int bn = min(256, p.N - n0);
       const int acc = it & 1;
-      mbar_wait(tmem_full_bar(acc), ((uint32_t)it >> 1) & 1u);
-      stamp(tr && warp == kWarpEpi0 && it < 4, 6 + it);
-      tc_fence_after();
       // this thread's row: virtual pixel q -> (image, yv, xv); rows of the halo are dropped
       const int q = m_pair * 256 + (int)rank * 128 + quad * 32 + lane;
       const int r = q / p.Wv;
@@ -995,17 +1038,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           ok_mask |= (__shfl_sync(0xffffffffu, valid ? 1u : 0u, src)) << r;
         }
       }
+      const bool use_act = ACT && vec_store && act_delta != 0;
+      float4 act_cur[8], act_next[8];
+      if (use_act) load_act_rows(act_cur, rp, ok_mask, 0, lane, act_delta);
+      mbar_wait(tmem_full_bar(acc), ((uint32_t)it >> 1) & 1u);
+      stamp(tr && warp == kWarpEpi0 && it < 4, 6 + it);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccumCols);
       for (int cb = 0; cb < bn; cb += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
+        if (use_act && cb + 32 < bn) load_act_rows(act_next, rp, ok_mask, cb + 32, lane, act_delta);
         tmem_ld_wait();
-        if (p.leaky) leaky_block(v, p.alpha);
+        if (MODE == kFprop && p.leaky) leaky_block(v, p.alpha);
         if (vec_store) {
-          store_block_rows(epi_tile, v, lane, rp, ok_mask, cb);
+          store_block_rows(epi_tile, v, lane, rp, ok_mask, cb, use_act, act_cur, p.alpha);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) act_cur[r] = act_next[r];
         } else if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) crow[cb + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) {
+            float f = __uint_as_float(v[j]);
+            if (ACT && p.act) f *= p.act[(crow - p.C) + cb + j] > 0.f ? 1.f : p.alpha;
+            crow[cb + j] = f;
+          }
         }
       }
       tc_fence_before();
@@ -1249,6 +1305,7 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
   p.trace = g_trace;
   p.leaky = (mode == kFprop) ? ip.leaky : 0;
   p.alpha = ip.leaky_alpha;
+  p.act = (mode == kDgrad) ? ip.act : nullptr;
   const int up_h = (g.OH - 1) * g.sy + 1 - g.H - g.pad_t, up_w = (g.OW - 1) * g.sx + 1 - g.W - g.pad_l;
   if (mode == kFprop) {
     p.cblocks = g.C / 32;
@@ -1310,10 +1367,10 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int clusters = std::min(p.total_tiles, sms / 2);
   dim3 grid((unsigned)(2 * clusters));
-#define SP_TMA2_LAUNCH(MODE_)                                                                   \
+#define SP_TMA2_LAUNCH(MODE_, ACT_)                                                             \
   do {                                                                                          \
     static bool attr_done = false;                                                              \
-    auto kern = conv_tma2_kernel<MODE_>;                                                        \
+    auto kern = conv_tma2_kernel<MODE_, ACT_>;                                                  \
     if (!attr_done) {                                                                           \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                            (int)kSmemBytes);                                    \
@@ -1325,11 +1382,13 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
     launch_pdl(kern, grid, dim3(kThreads), kSmemBytes, st, tmA, tmB, p);                        \
   } while (0)
   if (mode == kFprop)
-    SP_TMA2_LAUNCH(kFprop);
+    SP_TMA2_LAUNCH(kFprop, false);
+  else if (mode == kDgrad && p.act)
+    SP_TMA2_LAUNCH(kDgrad, true);
   else if (mode == kDgrad)
-    SP_TMA2_LAUNCH(kDgrad);
+    SP_TMA2_LAUNCH(kDgrad, false);
   else
-    SP_TMA2_LAUNCH(kWgrad);
+    SP_TMA2_LAUNCH(kWgrad, false);
 #undef SP_TMA2_LAUNCH
   return 0;
 }
@@ -1429,6 +1488,7 @@ int launch_conv_halo2(int mode, const IgemmParams& ip, cudaStream_t st) {
   p.trace = g_trace;
   p.leaky = (mode == kFprop) ? ip.leaky : 0;
   p.alpha = ip.leaky_alpha;
+  p.act = (mode == kDgrad) ? ip.act : nullptr;
   const int bnh_max = (p.N >= 256 ? 256 : p.N) / 2;
   alignas(64) CUtensorMap tmA, tmB;
   bool ok = true;
@@ -1460,23 +1520,27 @@ int launch_conv_halo2(int mode, const IgemmParams& ip, cudaStream_t st) {
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int clusters = std::min(p.total_tiles, sms / 2);
   dim3 grid((unsigned)(2 * clusters));
-  static bool attr_done[2] = {false, false};
-  const int which = mode == kFprop ? 0 : 1;
-  if (!attr_done[which]) {
-    cudaError_t e =
-        mode == kFprop
-            ? cudaFuncSetAttribute(conv_halo2_kernel<kFprop>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024)
-            : cudaFuncSetAttribute(conv_halo2_kernel<kDgrad>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
-    if (e != cudaSuccess)
-      return set_error((int)e, "cudaFuncSetAttribute(conv_halo2) failed: %s", cudaGetErrorString(e));
-    attr_done[which] = true;
-  }
+#define SP_HALO_LAUNCH(MODE_, ACT_)                                                             \
+  do {                                                                                          \
+    static bool attr_done = false;                                                              \
+    auto kern = conv_halo2_kernel<MODE_, ACT_>;                                                 \
+    if (!attr_done) {                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                           218 * 1024);                                         \
+      if (e != cudaSuccess)                                                                     \
+        return set_error((int)e, "cudaFuncSetAttribute(conv_halo2) failed: %s",                 \
+                         cudaGetErrorString(e));                                                \
+      attr_done = true;                                                                         \
+    }                                                                                           \
+    launch_pdl(kern, grid, dim3(kThreads), h.smem, st, tmA, tmB, p);                            \
+  } while (0)
   if (mode == kFprop)
-    launch_pdl(conv_halo2_kernel<kFprop>, grid, dim3(kThreads), h.smem, st, tmA, tmB, p);
+    SP_HALO_LAUNCH(kFprop, false);
+  else if (p.act)
+    SP_HALO_LAUNCH(kDgrad, true);
   else
-    launch_pdl(conv_halo2_kernel<kDgrad>, grid, dim3(kThreads), h.smem, st, tmA, tmB, p);
+    SP_HALO_LAUNCH(kDgrad, false);
+#undef SP_HALO_LAUNCH
   return 0;
 }
 

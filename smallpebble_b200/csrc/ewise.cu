@@ -298,6 +298,27 @@ __global__ void __launch_bounds__(kThreads) leaky_bwd_kernel(const float* __rest
   for (int64_t i = done + tid; i < n; i += stride) dx[i] = g[i] * ((x[i] > 0.f) ? 1.f : alpha);
 }
 
+// In-place variants for the conv kernels without a fused epilogue (contract_api.cu): ordinary
+// loads, because the buffer being read is the one being written (the streaming kernels above
+// read through the non-coherent path, which assumes read-only data).
+__global__ void __launch_bounds__(kThreads) leaky_fwd_inplace_kernel(float* y, int64_t n,
+                                                                     float alpha) {
+  pdl_entry();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = y[i];
+    y[i] = v * ((v > 0.f) ? 1.f : alpha);
+  }
+}
+__global__ void __launch_bounds__(kThreads) leaky_bwd_inplace_kernel(float* dx,
+                                                                     const float* __restrict__ x,
+                                                                     int64_t n, float alpha) {
+  pdl_entry();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = dx[i] * ((x[i] > 0.f) ? 1.f : alpha);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // 8 resident blocks of 256 threads per SM, 4 float4 per thread per trip
@@ -333,6 +354,19 @@ int launch_binary(const float* a, const float* b, float* out, const Dims& d, cud
 }
 
 }  // namespace
+
+namespace sp {
+int launch_leaky_fwd_inplace(float* y, int64_t n, float alpha, cudaStream_t st) {
+  if (n <= 0) return 0;
+  launch_pdl(leaky_fwd_inplace_kernel, dim3(ew_grid(n)), dim3(kThreads), 0, st, y, n, alpha);
+  return 0;
+}
+int launch_leaky_bwd_inplace(float* dx, const float* x, int64_t n, float alpha, cudaStream_t st) {
+  if (n <= 0) return 0;
+  launch_pdl(leaky_bwd_inplace_kernel, dim3(ew_grid(n)), dim3(kThreads), 0, st, dx, x, n, alpha);
+  return 0;
+}
+}  // namespace sp
 
 extern "C" {
 

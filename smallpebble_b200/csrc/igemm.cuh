@@ -32,6 +32,10 @@ struct IgemmParams {
   // out = v > 0 ? v : leaky_alpha * v, the same bits as a separate leaky_relu launch
   int leaky;
   float leaky_alpha;
+  // optional leaky_relu BACKWARD epilogue (conv dgrad in the 2-SM kernels): out = v * (act > 0 ?
+  // 1 : leaky_alpha) with `act` laid out like the output -- the gradient of leaky_relu applied
+  // to the data gradient as it is stored
+  const float* act;
   // dense operand strides (kGemm)
   int64_t a_rs, a_cs, b_rs, b_cs;
   // strided batch (kGemm): blockIdx.z selects the batch
@@ -62,6 +66,10 @@ double conv_halo2_efficiency(int mode, const IgemmParams& p);
 int launch_conv_halo2(int mode, const IgemmParams& p, cudaStream_t stream);
 // bring-up: cluster 0 writes clock64 stamps into `device_buffer` (>= 512 int64), null = off
 void conv_tma2_set_trace(long long* device_buffer);
+
+// in-place leaky_relu forward / backward (ewise.cu) for conv kernels without a fused epilogue
+int launch_leaky_fwd_inplace(float* y, int64_t n, float alpha, cudaStream_t st);
+int launch_leaky_bwd_inplace(float* dx, const float* x, int64_t n, float alpha, cudaStream_t st);
 
 // N <= 16 GEMMs (the 10-way classifier and its weight gradient), gemm_skinny.cu: exact fp32
 bool gemm_skinny_supported(const IgemmParams& p);
