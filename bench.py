@@ -31,7 +31,7 @@ METRIC = "train_images_per_sec"
 UNIT = "images/s"
 L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
 RESIDENT_BATCHES = 96       # x 1.57 MB fp32 = 151 MB of inputs: larger than the 126 MB L2
-WARMUP_FLOOR = 25           # untimed steps run directly before the timed region (see below)
+WARMUP_FLOOR = int(os.environ.get("SP_BENCH_WARMUP_FLOOR", "25"))           # untimed steps run directly before the timed region (see below)
 
 
 def load_peaks():
