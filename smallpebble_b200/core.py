@@ -86,6 +86,7 @@ def set_fusion(enabled: bool) -> None:
 
 
 _serials = itertools.count()
+_rebind_epoch = 0  # bumped by every `variable.array = ...` after construction
 _serial_of = operator.attrgetter("_serial")
 
 
@@ -104,6 +105,8 @@ class Variable:
 
     @array.setter
     def array(self, value):
+        global _rebind_epoch
+        _rebind_epoch += 1  # optimisers cache parameter pointers until some array is rebound
         self._array = value if isinstance(value, DeviceArray) else DeviceArray.from_host(value)
 
     dtype = property(lambda self: self._array.dtype)  # sp.py:459-461

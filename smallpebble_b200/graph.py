@@ -14,6 +14,7 @@ import numpy as np
 from . import _abi
 from . import array as A
 from . import core
+from . import distributed as _distributed
 from .array import DeviceArray
 from .core import Variable
 
@@ -153,33 +154,47 @@ class Adam:
         self.t = _StepCounts(self._step)
         self._tables = {}  # ids of the parameter arrays -> cached ctypes pointer tables
         self._g_ptrs, self._g_tab = None, None  # last step's gradient pointers and their table
+        self._static = None  # (variable ids, rebind epoch, pointer tables, variables kept alive)
 
     def training_step(self, variables, gradients) -> None:
-        from . import distributed
-
         variables = list(variables)
         if not variables:
             return
-        grads = [_device_gradient(v, gradients) for v in variables]
-        if distributed.is_initialized() and distributed.world_size() > 1:
-            grads = distributed.allreduce_gradients(grads)
+        grads = []
         for v in variables:
-            if v not in self._step:
-                self.m[v] = DeviceArray.zeros(v.array.shape)
-                self.v[v] = DeviceArray.zeros(v.array.shape)
-                self._step[v] = DeviceArray.from_host(np.zeros(1, np.int32), dtype=np.int32)
+            g = gradients[v]  # KeyError when missing, like the reference
+            if type(g) is not DeviceArray or g.shape != v._array.shape:
+                g = _device_gradient(v, gradients)
+            grads.append(g)
+        if _distributed.is_initialized() and _distributed.world_size() > 1:
+            grads = _distributed.allreduce_gradients(grads)
         n = len(variables)
-        key = tuple((id(v), v.array.ptr) for v in variables)
-        static = self._tables.get(key)
-        if static is None:  # pointer tables of everything that does not change step to step
-            static = self._tables[key] = (
-                _ptr_table([v.array.ptr for v in variables]),
-                _ptr_table([self.m[v].ptr for v in variables]),
-                _ptr_table([self.v[v].ptr for v in variables]),
-                _abi.dims([v.array.size for v in variables]),
-                _ptr_table([self._step[v].ptr for v in variables]),
-            )
-        p_tab, m_tab, v_tab, numel, step_tab = static
+        # Everything below that does not change from step to step -- state creation, the
+        # pointer tables of parameters / moments / step counters -- is keyed by the identity of
+        # the variables and stays valid until some `variable.array` is rebound (core counts
+        # those); the fused kernel updates the parameters in place.
+        ids = tuple([id(v) for v in variables])
+        cached = self._static
+        if cached is None or cached[0] != ids or cached[1] != core._rebind_epoch:
+            for v in variables:
+                if v not in self._step:
+                    self.m[v] = DeviceArray.zeros(v.array.shape)
+                    self.v[v] = DeviceArray.zeros(v.array.shape)
+                    self._step[v] = DeviceArray.from_host(np.zeros(1, np.int32), dtype=np.int32)
+            key = tuple((id(v), v.array.ptr) for v in variables)
+            static = self._tables.get(key)
+            if static is None:
+                static = self._tables[key] = (
+                    _ptr_table([v.array.ptr for v in variables]),
+                    _ptr_table([self.m[v].ptr for v in variables]),
+                    _ptr_table([self.v[v].ptr for v in variables]),
+                    _abi.dims([v.array.size for v in variables]),
+                    _ptr_table([self._step[v].ptr for v in variables]),
+                )
+            # the epoch is read after the lazy uploads above (`.ptr` may rebind nothing, but
+            # Variable construction elsewhere does not count either)
+            cached = self._static = (ids, core._rebind_epoch, static, tuple(variables))
+        p_tab, m_tab, v_tab, numel, step_tab = cached[2]
         # gradient buffers come out of the recycling pool in the same order every step: the
         # pointer table of the previous step is usually still right
         g_ptrs = tuple([g.ptr for g in grads])

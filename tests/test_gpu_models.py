@@ -334,3 +334,27 @@ def test_conv_leaky_epilogue_fusion_is_bit_identical(policy, alpha):
     assert was_fused == (alpha > 0) and not was_plain
     for i, (a, b) in enumerate(zip(fused, plain)):
         assert np.array_equal(a, b), i
+
+
+def test_adam_follows_a_rebound_parameter_array():
+    """Adam caches the parameter / moment pointer tables between steps; rebinding
+    `variable.array` (what the reference's own optimiser does every step, sp.py:583, and what a
+    user does to load weights) must invalidate that cache: a run that swaps every parameter for
+    a copy of itself half-way must end with exactly the same weights as one that does not."""
+    x, y = workloads.synthetic_batch("mlp", 64)
+
+    def run(rebind):
+        wl = workloads.mnist_mlp(seed=0)
+        adam = sp.Adam()
+        for step in range(4):
+            if rebind and step == 2:
+                for p in wl.learnables:
+                    p.array = np.asarray(p.array).copy()
+            wl.train_step(adam, x, y)
+        return [np.asarray(p.array) for p in wl.learnables], [adam.t[p] for p in wl.learnables]
+
+    w_plain, t_plain = run(False)
+    w_rebound, t_rebound = run(True)
+    assert t_plain == t_rebound == [4] * len(t_plain)
+    for a, b in zip(w_plain, w_rebound):
+        assert np.array_equal(a, b)
