@@ -1,17 +1,23 @@
 // First-layer convolutions: tiny channel count (RGB, C = 3) and a short reduction
-// (KH*KW*C = 27).  As implicit GEMMs these are the worst case for the tensor-core kernel --
-// 12-byte pixels rule out 16-byte copies, M or K pads 27 -> 128/32 -- while the arithmetic is
-// negligible (0.2 GFLOP for the CIFAR layer): they are HBM-bound (read x, write y: 16 MB).
-// So they run on CUDA cores in exact fp32, organised around coalesced memory traffic:
+// (KH*KW*C = 27).  As implicit GEMMs these are the worst case for the tcgen05 kernels --
+// 12-byte pixels rule out TMA and 16-byte copies, M or K pads 27 -> 128/32 -- while the
+// arithmetic is negligible (0.2 GFLOP for the CIFAR layer): they are HBM-bound (read x, write
+// y: 16 MB).  Two families live here:
 //
-//   fprop: weights (KH*KW*C x K, a few KB) live in shared memory; a thread produces 8 output
-//          channels of one pixel, so a pixel's K outputs are written as one contiguous run.
-//   wgrad: a block owns a slice of the N*OH*OW reduction; pixel tiles (patches and dY rows)
-//          are staged in shared memory with coalesced loads; each thread accumulates 4
-//          filter taps in registers; per-block partial filters are summed by a second,
-//          fixed-order pass (deterministic, like the tensor-core split-K path).
+//   SP_PRECISION_TF32, 3x3 stride-1 windows, K in {16, 32, 64}: warp-level tensor-core kernels
+//   (mma.sync.m16n8k8.tf32) that read their fragments straight out of zero-padded input rows in
+//   shared memory ("padded-linear" order, no im2col staging) -- conv_fprop_rgb3x3_mma_kernel,
+//   conv_wgrad_rgb3x3_mma_kernel, ~10x fewer instructions than the CUDA-core kernels, which were
+//   issue-bound (7.3 M warp instructions for the CIFAR filter gradient);
 //
-// Used for both precision modes when small_c_supported() holds (results are fp32-exact).
+//   everything else with C <= 4 (SP_PRECISION_FP32, strides, other windows): exact-fp32
+//   CUDA-core kernels organised around coalesced traffic --
+//     fprop: weights (KH*KW*C x K, a few KB) in shared memory; a thread produces 8 output
+//            channels of 1 or 4 pixels, so a pixel's K outputs are one contiguous run;
+//     wgrad: a block owns a slice of the N*OH*OW reduction; pixel tiles (patches and dY rows)
+//            are staged in shared memory; each thread accumulates a 4 x 8 register tile;
+//            per-block partial filters are summed in a fixed order (deterministic), for the
+//            3x3 RGB case behind a grid barrier of a cooperative launch.
 #include <algorithm>
 #include <cstdlib>
 
