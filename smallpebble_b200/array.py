@@ -195,6 +195,7 @@ def scalar_one(shape):
 
 
 _new_array = object.__new__
+_np_dtype = type(FLOAT)
 _prod = math.prod
 
 
@@ -216,16 +217,20 @@ class DeviceArray:
 
     # ---- construction ---------------------------------------------------------------------
     @staticmethod
-    def empty(shape, dtype=FLOAT) -> "DeviceArray":
+    def empty(shape, dtype=FLOAT, size=None) -> "DeviceArray":
+        """Uninitialised device array.  `size` (= prod(shape)) may be passed by callers that
+        already know it -- this is the most frequent call of a training step."""
         dev = _device if _device is not None else require_cuda()
         self = _new_array(DeviceArray)
         if type(shape) is not tuple:
             shape = tuple(shape)
         self.shape = shape
-        if dtype is not FLOAT:
+        if dtype is not FLOAT and type(dtype) is not _np_dtype:
             dtype = np.dtype(dtype)
         self.dtype = dtype
-        self.size = size = _prod(shape)
+        if size is None:
+            size = _prod(shape)
+        self.size = size
         self._host = None
         self._thunk = None
         self._tag = None
@@ -244,16 +249,21 @@ class DeviceArray:
         return self
 
     @staticmethod
-    def deferred(shape, thunk, tag) -> "DeviceArray":
+    def empty_like(other) -> "DeviceArray":
+        "float32 array of `other`'s shape (gradient buffers)."
+        return DeviceArray.empty(other.shape, FLOAT, other.size)
+
+    @staticmethod
+    def deferred(shape, thunk, tag, size=None) -> "DeviceArray":
         """A float32 array whose producing kernel has not been launched yet.  `thunk(out)` fills
         a freshly allocated `out`; it runs the first time anything needs the data (`.ptr`,
         `.numpy()`, ...).  `tag` describes the pending op so that a consumer able to fuse it
         (core.maxpool2d after core.leaky_relu, and their gradients) can skip it altogether --
         the fusion across the API seam of SURVEY.md 8(f)."""
-        self = object.__new__(DeviceArray)
-        self.shape = tuple(shape)
+        self = _new_array(DeviceArray)
+        self.shape = shape if type(shape) is tuple else tuple(shape)
         self.dtype = FLOAT
-        self.size = math.prod(self.shape)
+        self.size = _prod(self.shape) if size is None else size
         self._buf = None
         self._ptr = None
         self._host = None
@@ -269,7 +279,7 @@ class DeviceArray:
 
     def _materialize(self):
         thunk = self._thunk
-        out = DeviceArray.empty(self.shape)
+        out = DeviceArray.empty(self.shape, FLOAT, self.size)
         thunk(out)
         self._adopt(out)
 
@@ -417,12 +427,21 @@ class DeviceArray:
     def reshape(self, *shape) -> "DeviceArray":
         if len(shape) == 1 and not isinstance(shape[0], numbers.Integral):
             shape = tuple(shape[0])
-        shape = _resolve_shape(shape, self.size)
+        shape = _reshape_plan(shape, self.size)
         if self._ptr is None and self._thunk is not None:
             self._materialize()
         if self._ptr is None:
             return DeviceArray(shape, self.dtype, host=self._host.reshape(shape))
-        out = DeviceArray(shape, self.dtype, self._buf, self._ptr)  # shares the buffer
+        out = _new_array(DeviceArray)  # a view: shares the buffer (and its Block)
+        out.shape = shape
+        out.dtype = self.dtype
+        out.size = self.size
+        out._buf = self._buf
+        out._ptr = self._ptr
+        out._host = None
+        out._thunk = None
+        out._tag = None
+        out._aux = None
         return out
 
     def copy(self) -> "DeviceArray":
@@ -663,6 +682,12 @@ def asarray(x) -> DeviceArray:
     if isinstance(x, DeviceArray):
         return x
     return DeviceArray.from_host(x)
+
+
+@functools.lru_cache(maxsize=4096)
+def _reshape_plan(shape, size):
+    """The validated target shape of a reshape (the same few every training step)."""
+    return _resolve_shape(shape, size)
 
 
 def _resolve_shape(shape, size):

@@ -95,7 +95,7 @@ class Variable:
     `.local_gradients = [(child_variable, fn(path_value) -> array), ...]` (sp.py:36-54)."""
 
     def __init__(self, array, local_gradients=None) -> None:
-        self._array = array if isinstance(array, DeviceArray) else DeviceArray.from_host(array)
+        self._array = array if type(array) is DeviceArray else DeviceArray.from_host(array)
         self.local_gradients = local_gradients if local_gradients else []
         self._serial = next(_serials)  # construction order: get_gradients sorts the tape by it
 
@@ -486,13 +486,13 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
             F.sp_leaky_relu_fwd(x.ptr, out.ptr, x.size, alpha, A.stream())
 
     if _fuse_leaky_pool and a.local_gradients and x.ndim == 4 and x.size:
-        y = DeviceArray.deferred(x.shape, launch, ("leaky_relu", x, alpha))
+        y = DeviceArray.deferred(x.shape, launch, ("leaky_relu", x, alpha), x.size)
     else:
-        y = DeviceArray.empty(x.shape)
+        y = DeviceArray.empty_like(x)
         launch(y)
 
     def multiply_by_locgrad(g):
-        dx = DeviceArray.empty(x.shape)
+        dx = DeviceArray.empty_like(x)
         tag = g.pending_tag if isinstance(g, DeviceArray) else None
         if tag is not None and tag[0] == "maxpool2d_bwd" and tag[1] is y:
             # the upstream gradient is a pool gradient that has not been launched: one kernel
@@ -688,19 +688,25 @@ def _broadcast_to(x: DeviceArray, shape) -> DeviceArray:
     return A.binary("add", DeviceArray.zeros(shape), x)
 
 
+@functools.lru_cache(maxsize=1024)
+def _matmul_plan(a_shape, b_shape):
+    """Shape logic of a matmul call (validation, batch broadcasting), once per pair of shapes."""
+    if len(a_shape) < 2 or len(b_shape) < 2:
+        raise ValueError("matmul operands must have at least 2 dimensions")
+    M, K = a_shape[-2:]
+    K2, N = b_shape[-2:]
+    if K != K2:
+        raise ValueError(f"matmul: shapes {a_shape} and {b_shape} not aligned")
+    a_batch, b_batch = a_shape[:-2], b_shape[:-2]
+    ra, rb = broadcastinfo(a_batch, b_batch)
+    batch_shape = tuple(np.broadcast_shapes(a_batch, b_batch))
+    return M, K, N, a_batch, b_batch, ra, rb, batch_shape, math.prod(batch_shape)
+
+
 def matmul(a: Variable, b: Variable) -> Variable:
     "Matrix multiplication (sp.py:239-247)."
     av, bv = a.array, b.array
-    if av.ndim < 2 or bv.ndim < 2:
-        raise ValueError("matmul operands must have at least 2 dimensions")
-    M, K = av.shape[-2:]
-    K2, N = bv.shape[-2:]
-    if K != K2:
-        raise ValueError(f"matmul: shapes {av.shape} and {bv.shape} not aligned")
-    a_batch, b_batch = av.shape[:-2], bv.shape[:-2]
-    ra, rb = broadcastinfo(a_batch, b_batch)
-    batch_shape = np.broadcast_shapes(a_batch, b_batch)
-    nb = math.prod(batch_shape)
+    M, K, N, a_batch, b_batch, ra, rb, batch_shape, nb = _matmul_plan(av.shape, bv.shape)
 
     if not b_batch:
         # [..., M, K] x [K, N]: one GEMM over the flattened rows (the layer case)
@@ -761,7 +767,8 @@ def _conv_plan(x_shape, w_shape, padding, strides):
         imheight, imwidth, kernheight, kernwidth, stride_y, stride_x, padding)
     geom = _conv_geom(n_images, imheight, imwidth, channels, kernheight, kernwidth, channels_out,
                       stride_y, stride_x, pt, pl, outh, outw)
-    return geom, (n_images, outh, outw, channels_out), {}
+    out_shape = (n_images, outh, outw, channels_out)
+    return geom, out_shape, {}, math.prod(out_shape)
 
 
 def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(1, 1)) -> Variable:
@@ -781,12 +788,13 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
         if out.size:
             F.sp_conv2d_fprop(x.ptr, w.ptr, out.ptr, geom, prec, A.stream())
 
-    if _fuse_conv_leaky and math.prod(out_shape):
+    out_size = plan[3]
+    if _fuse_conv_leaky and out_size:
         # not launched yet: a leaky_relu consumer folds its activation into this kernel's
         # epilogue (core.leaky_relu); anything else that touches the result launches it as usual
-        y = DeviceArray.deferred(out_shape, launch, ("conv2d", x, w, geom, prec))
+        y = DeviceArray.deferred(out_shape, launch, ("conv2d", x, w, geom, prec), out_size)
     else:
-        y = DeviceArray.empty(out_shape)
+        y = DeviceArray.empty(out_shape, A.FLOAT, out_size)
         launch(y)
 
     def grad_images(g):
@@ -799,13 +807,14 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
         if _fuse_conv_leaky and x.size and isinstance(g, DeviceArray):
             # not launched yet: when the consumer is a leaky_relu's gradient closure, the slope
             # is applied as the data gradient is stored (sp_conv2d_dgrad_leaky)
-            return DeviceArray.deferred(x.shape, launch_dgrad, ("conv2d_dgrad", g, w, geom, prec_b))
-        dx = DeviceArray.empty(x.shape)
+            return DeviceArray.deferred(x.shape, launch_dgrad, ("conv2d_dgrad", g, w, geom, prec_b),
+                                        x.size)
+        dx = DeviceArray.empty_like(x)
         launch_dgrad(dx)
         return dx
 
     def grad_kernels(g):
-        dw = DeviceArray.empty(w.shape)
+        dw = DeviceArray.empty_like(w)
         ws_bytes = plan[2].get(_precision)
         if ws_bytes is None:
             ws_bytes = plan[2][_precision] = _abi.load().sp_conv2d_wgrad_workspace(geom, _precision)
@@ -829,7 +838,8 @@ def _pool_plan(x_shape, kernheight, kernwidth, stride_y, stride_x, padding):
         imheight, imwidth, kernheight, kernwidth, stride_y, stride_x, padding)
     geom = (n_images, imheight, imwidth, n_channels, kernheight, kernwidth, stride_y, stride_x,
             pt, pl, outh, outw)
-    return geom, (n_images, outh, outw, n_channels)
+    out_shape = (n_images, outh, outw, n_channels)
+    return geom, out_shape, math.prod(out_shape)
 
 
 def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = "SAME",
@@ -839,9 +849,10 @@ def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = 
     order wins -- exactly what np.pad + np.argmax give the reference."""
     x = images.array
     stride_y, stride_x = strides
-    geom, out_shape = _pool_plan(x.shape, kernheight, kernwidth, stride_y, stride_x, padding)
-    y = DeviceArray.empty(out_shape)
-    idx = DeviceArray.empty(out_shape, _UINT8)
+    geom, out_shape, out_size = _pool_plan(x.shape, kernheight, kernwidth, stride_y, stride_x,
+                                           padding)
+    y = DeviceArray.empty(out_shape, A.FLOAT, out_size)
+    idx = DeviceArray.empty(out_shape, _UINT8, out_size)
     tag = x.pending_tag
     fused = tag is not None and tag[0] == "leaky_relu" and y.size > 0
     if fused:
@@ -859,8 +870,8 @@ def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = 
 
         if fused and x.size:
             # deferred: leaky_relu's gradient closure folds this scatter into its own kernel
-            return DeviceArray.deferred(x.shape, launch, ("maxpool2d_bwd", x, g, idx, geom))
-        dx = DeviceArray.empty(x.shape)
+            return DeviceArray.deferred(x.shape, launch, ("maxpool2d_bwd", x, g, idx, geom), x.size)
+        dx = DeviceArray.empty_like(x)
         launch(dx)
         return dx
 
@@ -892,13 +903,13 @@ def softmax(a: Variable, axis: int = -1) -> Variable:
         # Not launched yet: cross_entropy computes the probabilities and the loss from the
         # logits in ONE kernel and hands this array its buffer; anything else that touches the
         # probabilities first launches the ordinary kernel (bitwise the same values).
-        y = DeviceArray.deferred(x.shape, launch, ("softmax", x))
+        y = DeviceArray.deferred(x.shape, launch, ("softmax", x), x.size)
     else:
-        y = DeviceArray.empty(x.shape)
+        y = DeviceArray.empty_like(x)
         launch(y)
 
     def multiply_by_locgrad(g):
-        dx = DeviceArray.empty(x.shape)
+        dx = DeviceArray.empty_like(x)
         if dx.size:
             F.sp_softmax_bwd(y.ptr, g.ptr, dx.ptr, outer, n, inner, A.stream())
         return dx
@@ -940,12 +951,12 @@ def cross_entropy(y_pred: Variable, y_true: np.ndarray, axis: int = -1) -> Varia
         logits = logits_var.array
         if probs.pending_tag is not None:
             # the softmax has not been launched: this kernel produces its output as well
-            probs._adopt(DeviceArray.empty(probs.shape))
+            probs._adopt(DeviceArray.empty_like(probs))
         # (re)computes probs into the softmax node's buffer (bitwise the same values) + the loss
         F.sp_softmax_xent_fwd(logits.ptr, labels.ptr, probs.ptr, loss.ptr, rows, cols, A.stream())
 
         def grad_logits(g):
-            dlogits = DeviceArray.empty(logits.shape)
+            dlogits = DeviceArray.empty_like(logits)
             if dlogits.size and _fuse_bias and rows * cols <= 32768:
                 # also emits the column sums: the gradient of a bias added to the logits, which
                 # core._unbroadcast picks up instead of launching a reduction
@@ -965,7 +976,7 @@ def cross_entropy(y_pred: Variable, y_true: np.ndarray, axis: int = -1) -> Varia
     F.sp_xent_fwd(probs.ptr, labels.ptr, loss.ptr, rows, cols, A.stream())
 
     def grad_probs(g):
-        dprobs = DeviceArray.empty(probs.shape)
+        dprobs = DeviceArray.empty_like(probs)
         if dprobs.size:
             F.sp_xent_bwd(probs.ptr, labels.ptr, g.ptr, dprobs.ptr, rows, cols, A.stream())
         return dprobs
