@@ -602,6 +602,7 @@ def run_ours(args):
         "abi_calls_per_step": calls_per_step,
         "wall_s_timed_region": wall,
         "host_issue_ms_per_step": host_issue_ms,
+        "dp_overlapped_allreduce_steps": (int(sp.distributed._overlap["used"]) if world > 1 else None),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "top_calls_one_step_ms": profile_summary,

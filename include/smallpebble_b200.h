@@ -83,6 +83,13 @@ int sp_memcpy_h2d(void* dst, const void* host_src, size_t bytes, sp_stream_t str
  * of the caller's batch (sp.batch / X[indices], sp.py:586-593) and narrows float64 -> fp32 on
  * the device instead of converting on a host core */
 int sp_host_is_pinned(const void* host_ptr, int* pinned);
+/* side stream + events of the data-parallel exchange (smallpebble_b200/distributed.py): the early
+ * part of the gradient bucket is reduced on a side stream while the compute stream finishes
+ * the backward pass; the reference has no counterpart (it is single-process) */
+int sp_stream_create(sp_stream_t* out);
+int sp_event_create(void** out);
+int sp_event_record(void* event, sp_stream_t stream);
+int sp_stream_wait_event(sp_stream_t stream, void* event);
 /* copies and waits for the stream: the only blocking call of the ABI (sp.py users read
  * `.array`, e.g. np.isnan(loss_val.array), README.md:156) */
 int sp_memcpy_d2h(void* host_dst, const void* src, size_t bytes, sp_stream_t stream);

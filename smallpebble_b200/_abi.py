@@ -67,6 +67,10 @@ SIGNATURES = {
     "sp_xent_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
     "sp_softmax_xent_fwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
     "sp_softmax_xent_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
+    "sp_stream_create": (C.c_int, [vp]),
+    "sp_event_create": (C.c_int, [vp]),
+    "sp_event_record": (C.c_int, [vp, vp]),
+    "sp_stream_wait_event": (C.c_int, [vp, vp]),
     "sp_softmax_xent_bwd_colsum": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp]),
     "sp_gemm_bias": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, C.c_int, vp]),
     "sp_maxpool2d_fwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [vp]),
@@ -93,7 +97,8 @@ _lib = None
 _LAUNCHING = {
     n for n in SIGNATURES
     if n not in ("sp_abi_version", "sp_last_error", "sp_device_info", "sp_debug_set_umma_policy",
-                 "sp_debug_tma2_trace", "sp_host_is_pinned", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
+                 "sp_debug_tma2_trace", "sp_host_is_pinned", "sp_stream_create", "sp_event_create",
+                 "sp_event_record", "sp_stream_wait_event", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
                  "sp_conv2d_wgrad_workspace")
 }
 

@@ -195,6 +195,7 @@ def _accumulate(gradients, owned, child, value):
 
 
 _eager_leaf_grads = os.environ.get("SP_EAGER_LEAF_GRADS", "0") == "1"
+_dp_hook = None  # distributed.py: called after every write to a leaf's gradient
 
 
 def _tape_order_dfs(variable):
@@ -253,6 +254,7 @@ def get_gradients(variable: Variable) -> dict:
     # gradient buffers nobody else aliases: safe to accumulate in place
     owned = {variable} if fresh else set()
     get, put = gradients.get_plain, gradients.put_plain
+    hook = _dp_hook
     for node in order:
         path_value = get(node)
         for child, multiply_by_locgrad in node.local_gradients:
@@ -267,6 +269,10 @@ def get_gradients(variable: Variable) -> dict:
                 put(child, value)  # first contribution: may alias the upstream buffer
             else:
                 _accumulate(gradients, owned, child, value)
+            if hook is not None and not child.local_gradients and getattr(child, "is_learnable", False):
+                # data parallel: the exchange of the early gradients overlaps the rest of this
+                # sweep (distributed._on_gradient_written)
+                hook(child, get(child))
     return gradients
 
 

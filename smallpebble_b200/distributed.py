@@ -74,6 +74,12 @@ def shutdown() -> None:
     import torch.distributed as dist
 
     _nccl.update(comm=None, tried=False)  # the communicator dies with the process
+    _nccl.pop("fast", None)
+    if _overlap["side"] is not None:
+        _install_hook(False)
+    _overlap.update(side=None, mark=None, e_early=None, e_all=None, e_done=None)
+    _overlap_reset()
+    _plans.clear()
     if _state["owns_group"] and dist.is_initialized():
         dist.destroy_process_group()
     _state.update(initialized=False, rank=0, world=1, backend=None, bucket=None, owns_group=False)
@@ -175,8 +181,9 @@ def _direct_nccl():
         return None
 
 
-def _allreduce_sum_f32(ptr: int, count: int, tensor_view) -> None:
-    """In-place sum over ranks of `count` floats at device pointer `ptr` on the compute stream."""
+def _allreduce_sum_f32(ptr: int, count: int, tensor_view, stream=None) -> None:
+    """In-place sum over ranks of `count` floats at device pointer `ptr`, on the compute stream
+    or (direct communicator only) on the raw stream handle `stream`."""
     import torch.distributed as dist
 
     direct = _direct_nccl()
@@ -184,9 +191,10 @@ def _allreduce_sum_f32(ptr: int, count: int, tensor_view) -> None:
         lib, comm = direct
         call = _nccl.get("fast")
         if call is not None:
-            call(ptr, ptr, count, 7, 0, comm.value, A.stream())  # ncclFloat32, ncclSum
+            call(ptr, ptr, count, 7, 0, comm.value,  # ncclFloat32, ncclSum
+                 A.stream() if stream is None else stream)
             return
-        rc = lib.ncclAllReduce(ptr, ptr, count, 7, 0, comm, A.stream())
+        rc = lib.ncclAllReduce(ptr, ptr, count, 7, 0, comm, A.stream() if stream is None else stream)
         if rc != 0:
             raise RuntimeError(f"ncclAllReduce failed with code {rc}")
         return
@@ -203,20 +211,147 @@ def bucket_layout(sizes) -> list[int]:
     return offsets + [cur]
 
 
-_plans = {}  # gradient shapes -> (layout, total, ctypes size / offset tables)
+_plans = {}  # gradient shapes -> bucket plan
 
 
 def _bucket_plan(shapes, sizes):
     plan = _plans.get(shapes)
     if plan is None:
         layout = bucket_layout(sizes)
-        plan = _plans[shapes] = (layout, layout[-1], _abi.dims(sizes), _abi.dims(layout[:-1]),
-                                 {"ptrs": None, "table": None, "views": None, "base": None})
+        plan = _plans[shapes] = {
+            "layout": layout, "total": layout[-1], "c_sizes": _abi.dims(sizes),
+            "c_offsets": _abi.dims(layout[:-1]), "ptrs": None, "table": None, "views": None,
+            "base": None, "split": None}
     return plan
 
 
-def allreduce_gradients(grads):
-    """Sum each gradient over all ranks.  Returns arrays that alias the flat bucket."""
+# --------------------------------------------------------------------------------------------
+# Overlap of the exchange with the backward pass.  The collective is latency-bound (29 us for
+# the README CNN's 0.79 MB bucket on 8 GPUs) and at N = 8 the step is device-bound by exactly
+# that, while most of the bucket -- the classifier and the last conv layer's filters, the
+# first gradients the sweep produces -- is ready long before the backward pass ends.  So the
+# bucket is split in two by PRODUCTION order: core.get_gradients reports every write to a
+# learnable's gradient (core._dp_hook); after the write that completes the early part an event
+# is recorded, and the side stream packs + all-reduces that part while the main stream is
+# still computing the remaining gradients; the late part follows on the same side stream (one
+# stream for all NCCL calls: same order on every rank), and the optimiser waits for both.
+# The split is planned from the first step's observed order and re-validated every step
+# (every early gradient must be the very array the sweep last wrote before the event);
+# anything unexpected -- a different tape, gradients built outside the sweep, CUDA-graph
+# capture -- takes the single all-reduce on the compute stream.
+# --------------------------------------------------------------------------------------------
+# "auto": only for buckets of >= _OVERLAP_MIN_FLOATS -- the overlapped path costs ~25 us more
+# host time per step (write hook, two packs, two NCCL calls, four event operations), which a
+# host-bound loop like the README CNN's (0.79 MB bucket) cannot afford: measured at N = 2,
+# 0.177 -> 0.192 ms per step.  "1" forces it (tests), "0" disables it.
+_OVERLAP_MIN_FLOATS = 1 << 19
+_overlap = {"enabled": os.environ.get("SP_DP_OVERLAP", "auto"), "seq": 0, "written": {},
+            "mark": None, "event_seq": -1, "e_early": None, "e_all": None, "e_done": None,
+            "side": None, "used": 0}
+
+
+def _on_gradient_written(var, value) -> None:
+    """core.get_gradients calls this after every write to a learnable leaf's gradient."""
+    o = _overlap
+    o["seq"] = seq = o["seq"] + 1
+    o["written"][var] = (seq, id(value))
+    if var is o["mark"]:
+        value.ptr  # a deferred gradient is launched now, before the event
+        _abi.f.sp_event_record(o["e_early"], A.stream())
+        o["event_seq"] = seq
+
+
+def _overlap_reset() -> None:
+    o = _overlap
+    o["seq"] = 0
+    o["written"].clear()
+    o["event_seq"] = -1
+
+
+def _install_hook(enable: bool) -> None:
+    from . import core
+
+    core._dp_hook = _on_gradient_written if enable else None
+
+
+def _plan_split(plan, grads, variables):
+    """Split the bucket by production order: (order, k) = gradient indices sorted by the
+    sequence number of their last write, the first k of them (>= half of the bytes, at least
+    one left over) forming the early part.  None when the order is unknown."""
+    written = _overlap["written"]
+    n = len(grads)
+    if n < 2 or any(v not in written for v in variables):
+        return None
+    order = sorted(range(n), key=lambda i: written[variables[i]][0])
+    total = sum(g.size for g in grads)
+    acc, k = 0, 0
+    while k < n - 1 and acc * 2 < total:
+        acc += grads[order[k]].size
+        k += 1
+    if k == 0 or k >= n:
+        return None
+    sizes = [grads[i].size for i in order]
+    layout = bucket_layout(sizes)
+    offsets = [0] * n
+    for pos, i in enumerate(order):
+        offsets[i] = layout[pos]
+    return {
+        "order": order, "k": k, "offsets": offsets, "total": layout[-1],
+        "early_count": layout[k], "late_off": layout[k], "late_count": layout[-1] - layout[k],
+        "c_sizes_a": _abi.dims(sizes[:k]), "c_off_a": _abi.dims(layout[:k]),
+        "c_sizes_b": _abi.dims(sizes[k:]), "c_off_b": _abi.dims(layout[k:-1]),
+        "mark": variables[order[k - 1]], "ptrs": None, "tab_a": None, "tab_b": None,
+        "views": None, "base": None,
+    }
+
+
+def _allreduce_overlapped(plan, split, grads, variables, bucket):
+    """Early part on the side stream behind the marker event, late part behind the end of the
+    backward pass; the compute stream waits for both.  Returns the bucket views or None when
+    this step does not match the plan (the caller then uses the single all-reduce)."""
+    import ctypes as C
+
+    o = _overlap
+    written = o["written"]
+    k, order = split["k"], split["order"]
+    if o["event_seq"] <= 0:
+        return None
+    for pos in range(k):
+        i = order[pos]
+        rec = written.get(variables[i])
+        if rec is None or rec[0] > o["event_seq"] or rec[1] != id(grads[i]):
+            return None
+    side_raw = o["side"]
+    base = bucket.data_ptr()
+    ptrs = tuple([grads[i].ptr for i in order])
+    if ptrs != split["ptrs"]:
+        split["ptrs"] = ptrs
+        split["tab_a"] = (C.c_void_p * k)(*ptrs[:k])
+        split["tab_b"] = (C.c_void_p * (len(ptrs) - k))(*ptrs[k:])
+    F = _abi.f
+    main = A.stream()
+    F.sp_event_record(o["e_all"], main)  # every gradient kernel has been enqueued before this
+    F.sp_stream_wait_event(side_raw, o["e_early"])
+    F.sp_pack_multi(k, split["tab_a"], split["c_sizes_a"], split["c_off_a"], base, side_raw)
+    _allreduce_sum_f32(base, split["early_count"], bucket, side_raw)
+    F.sp_stream_wait_event(side_raw, o["e_all"])
+    F.sp_pack_multi(len(ptrs) - k, split["tab_b"], split["c_sizes_b"], split["c_off_b"], base,
+                    side_raw)
+    _allreduce_sum_f32(base + 4 * split["late_off"], split["late_count"], bucket, side_raw)
+    F.sp_event_record(o["e_done"], side_raw)
+    F.sp_stream_wait_event(main, o["e_done"])
+    o["used"] += 1
+    if split["base"] != base:
+        split["base"] = base
+        split["views"] = [DeviceArray(g.shape, A.FLOAT, bucket, base + 4 * off)
+                          for g, off in zip(grads, split["offsets"])]
+    return split["views"]
+
+
+def allreduce_gradients(grads, variables=None):
+    """Sum each gradient over all ranks.  Returns arrays that alias the flat bucket.
+    `variables` (the learnables the gradients belong to, same order) lets the exchange overlap
+    the backward pass (see above); without it the whole bucket is reduced in one call."""
     import torch
     import torch.distributed as dist
 
@@ -227,25 +362,52 @@ def allreduce_gradients(grads):
         # bucket layout, the size / offset tables of the pack kernel, its pointer table (the
         # gradient buffers come out of the recycling pool in the same order every step) and
         # the views of the bucket that are handed to the optimiser
-        layout, total, c_sizes, c_offsets, cache = _bucket_plan(tuple([g.shape for g in grads]),
-                                                               sizes)
+        plan = _bucket_plan(tuple([g.shape for g in grads]), sizes)
+        total = plan["total"]
         bucket = _state["bucket"]
-        if bucket is None or bucket.numel() < total:
-            bucket = torch.empty(max(total, 1), dtype=torch.float32, device=A.require_cuda())
+        if bucket is None or bucket.numel() < total + 64:
+            bucket = torch.empty(max(total, 1) + 64, dtype=torch.float32, device=A.require_cuda())
             _state["bucket"] = bucket
         base = bucket.data_ptr()
+        o = _overlap
+        wanted = o["enabled"] == "1" or (o["enabled"] == "auto" and total >= _OVERLAP_MIN_FLOATS)
+        if (wanted and variables is not None and world_size() > 1 and not A._pool_bypass
+                and _direct_nccl() is not None):
+            if o["side"] is None:
+                import ctypes as C
+
+                slot = (C.c_void_p * 1)()  # an array: both bindings pass its address
+                _abi.f.sp_stream_create(slot)
+                o["side"] = slot[0]
+                for name in ("e_early", "e_all", "e_done"):
+                    _abi.f.sp_event_create(slot)
+                    o[name] = slot[0]
+                _install_hook(True)
+            split = plan["split"]
+            views = None
+            if split is not None and split["mark"] is o["mark"]:
+                views = _allreduce_overlapped(plan, split, grads, variables, bucket)
+            elif o["written"]:
+                # first step with this set of gradients (or another model took the marker):
+                # plan the split from the order the sweep just produced them in
+                split = plan["split"] = _plan_split(plan, grads, variables)
+                o["mark"] = split["mark"] if split is not None else None
+            _overlap_reset()
+            if views is not None:
+                return views
         ptrs = tuple([g.ptr for g in grads])
-        if ptrs != cache["ptrs"]:
+        if ptrs != plan["ptrs"]:
             import ctypes as C
 
-            cache["ptrs"], cache["table"] = ptrs, (C.c_void_p * len(ptrs))(*ptrs)
-        _abi.f.sp_pack_multi(len(grads), cache["table"], c_sizes, c_offsets, base, A.stream())
+            plan["ptrs"], plan["table"] = ptrs, (C.c_void_p * len(ptrs))(*ptrs)
+        _abi.f.sp_pack_multi(len(grads), plan["table"], plan["c_sizes"], plan["c_offsets"], base,
+                             A.stream())
         _allreduce_sum_f32(base, total, bucket)
-        if cache["base"] != base:
-            cache["base"] = base
-            cache["views"] = [DeviceArray(g.shape, A.FLOAT, bucket, base + 4 * off)
-                              for g, off in zip(grads, layout)]
-        return cache["views"]
+        if plan["base"] != base:
+            plan["base"] = base
+            plan["views"] = [DeviceArray(g.shape, A.FLOAT, bucket, base + 4 * off)
+                             for g, off in zip(grads, plan["layout"])]
+        return plan["views"]
     layout = bucket_layout(sizes)
     total = layout[-1]
     # host path (gloo): plumbing tests on machines without a GPU

@@ -167,7 +167,7 @@ class Adam:
                 g = _device_gradient(v, gradients)
             grads.append(g)
         if _distributed.is_initialized() and _distributed.world_size() > 1:
-            grads = _distributed.allreduce_gradients(grads)
+            grads = _distributed.allreduce_gradients(grads, variables)
         n = len(variables)
         # Everything below that does not change from step to step -- state creation, the
         # pointer tables of parameters / moments / step counters -- is keyed by the identity of
@@ -213,7 +213,7 @@ def sgd_step(variables, gradients, learning_rate: float = 0.001) -> None:
         return
     grads = [_device_gradient(v, gradients) for v in variables]
     if distributed.is_initialized() and distributed.world_size() > 1:
-        grads = distributed.allreduce_gradients(grads)
+        grads = distributed.allreduce_gradients(grads, variables)
     F.sp_sgd_multi(
         len(variables),
         _ptr_table([v.array.ptr for v in variables]),

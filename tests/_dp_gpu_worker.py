@@ -19,7 +19,7 @@ def main():
     sp.set_precision("fp32")
     sp.distributed.init()
     rank, world = sp.distributed.rank(), sp.distributed.world_size()
-    steps, per_gpu = 3, 16
+    steps, per_gpu = 6, 16  # step 1: single all-reduce, 2: split planned, 3+: overlapped
     wl = workloads.cifar_cnn(seed=0)
     adam = sp.Adam()
     losses = []
@@ -28,7 +28,9 @@ def main():
         xs, ys = sp.distributed.shard(x, y)
         loss_val, _ = wl.train_step(adam, xs, ys)
         losses.append(sp.distributed.allreduce_scalar(float(loss_val.array)))
+    overlapped = sp.distributed._overlap["used"]
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), losses=np.array(losses),
+             overlapped_steps=np.array(overlapped),
              **{f"w{i}": np.asarray(p.array) for i, p in enumerate(wl.learnables)})
     sp.distributed.barrier()
     sp.distributed.shutdown()
