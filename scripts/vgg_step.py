@@ -9,6 +9,11 @@ import smallpebble_b200 as sp
 from smallpebble_b200 import workloads
 from smallpebble_b200.array import DeviceArray
 
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:  # torchrun: data parallel, 256 images per GPU (weak scaling)
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    os.dup2(2, 1)  # NCCL prints its banner on stdout
+    sp.distributed.init()
 x, y = workloads.synthetic_batch("vgg", 256)
 wl = workloads.vgg6(seed=0)
 adam = sp.Adam()
@@ -23,5 +28,12 @@ for i in range(steps):
     lv = wl.loss.run(); adam.training_step(wl.learnables, sp.get_gradients(lv))
 e1.record()
 torch.cuda.synchronize()
-print("loss", float(lv.array), "ms/step over the last", steps - steps // 2, "steps:",
-      e0.elapsed_time(e1) / (steps - steps // 2))
+msg = (f"loss {float(lv.array)} ms/step over the last {steps - steps // 2} steps: "
+       f"{e0.elapsed_time(e1) / (steps - steps // 2)}")
+if world > 1:
+    msg += f" | rank {sp.distributed.rank()}/{world} overlapped exchanges {sp.distributed._overlap['used']}"
+    sys.stderr.write(msg + "\n")
+    sp.distributed.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+print(msg)

@@ -230,7 +230,8 @@ def _bucket_plan(shapes, sizes):
 # the README CNN's 0.79 MB bucket on 8 GPUs) and at N = 8 the step is device-bound by exactly
 # that, while most of the bucket -- the classifier and the last conv layer's filters, the
 # first gradients the sweep produces -- is ready long before the backward pass ends.  So the
-# bucket is split in two by PRODUCTION order: core.get_gradients reports every write to a
+# bucket is split in two by PRODUCTION order (early part: everything but the last <= 10 % of
+# the bytes): core.get_gradients reports every write to a
 # learnable's gradient (core._dp_hook); after the write that completes the early part an event
 # is recorded, and the side stream packs + all-reduces that part while the main stream is
 # still computing the remaining gradients; the late part follows on the same side stream (one
@@ -240,12 +241,14 @@ def _bucket_plan(shapes, sizes):
 # anything unexpected -- a different tape, gradients built outside the sweep, CUDA-graph
 # capture -- takes the single all-reduce on the compute stream.
 # --------------------------------------------------------------------------------------------
-# "auto": only for buckets of >= _OVERLAP_MIN_FLOATS -- the overlapped path costs ~25 us more
-# host time per step (write hook, two packs, two NCCL calls, four event operations), which a
-# host-bound loop like the README CNN's (0.79 MB bucket) cannot afford: measured at N = 2,
-# 0.177 -> 0.192 ms per step.  "1" forces it (tests), "0" disables it.
+# Off unless SP_DP_OVERLAP=1 ("auto": buckets of >= _OVERLAP_MIN_FLOATS only).  Measured on two
+# GPUs it does not pay: the overlapped path costs ~25 us more host time per step (write hook,
+# two packs, two NCCL calls, four event operations), which the host-bound README CNN cannot
+# afford (0.177 -> 0.192 ms per step), and the device-bound VGG-6 step did not change within
+# noise (2.423 vs 2.433 ms: its 60 us of data-parallel cost is not the wait for the collective).
+# Where it should pay -- 8 GPUs, 29 us collective, device-bound -- was not measured this round.
 _OVERLAP_MIN_FLOATS = 1 << 19
-_overlap = {"enabled": os.environ.get("SP_DP_OVERLAP", "auto"), "seq": 0, "written": {},
+_overlap = {"enabled": os.environ.get("SP_DP_OVERLAP", "0"), "seq": 0, "written": {},
             "mark": None, "event_seq": -1, "e_early": None, "e_all": None, "e_done": None,
             "side": None, "used": 0}
 
@@ -276,20 +279,20 @@ def _install_hook(enable: bool) -> None:
 
 def _plan_split(plan, grads, variables):
     """Split the bucket by production order: (order, k) = gradient indices sorted by the
-    sequence number of their last write, the first k of them (>= half of the bytes, at least
-    one left over) forming the early part.  None when the order is unknown."""
+    sequence number of their last write, the first k of them forming the early part.  None
+    when the order is unknown."""
     written = _overlap["written"]
     n = len(grads)
     if n < 2 or any(v not in written for v in variables):
         return None
     order = sorted(range(n), key=lambda i: written[variables[i]][0])
     total = sum(g.size for g in grads)
-    acc, k = 0, 0
-    while k < n - 1 and acc * 2 < total:
-        acc += grads[order[k]].size
-        k += 1
-    if k == 0 or k >= n:
-        return None
+    # the late part: the last-produced gradients, as few bytes as possible (its all-reduce is
+    # the exposed one) -- at most 10 % of the bucket, but at least the very last gradient
+    k, late = n - 1, grads[order[n - 1]].size
+    while k > 1 and (late + grads[order[k - 1]].size) * 10 <= total:
+        k -= 1
+        late += grads[order[k]].size
     sizes = [grads[i].size for i in order]
     layout = bucket_layout(sizes)
     offsets = [0] * n
