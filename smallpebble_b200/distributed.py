@@ -246,7 +246,10 @@ def _bucket_plan(shapes, sizes):
 # two packs, two NCCL calls, four event operations), which the host-bound README CNN cannot
 # afford (0.177 -> 0.192 ms per step), and the device-bound VGG-6 step did not change within
 # noise (2.423 vs 2.433 ms: its 60 us of data-parallel cost is not the wait for the collective).
-# Where it should pay -- 8 GPUs, 29 us collective, device-bound -- was not measured this round.
+# On 8 GPUs, where the README CNN's step IS device-bound by the 29 us collective, two
+# latency-bound collectives cost more than the one they replace: 0.198 -> 0.232 ms per step.
+# What would pay there is a cheaper collective (one-shot reduction over NVLink peer memory),
+# not a split one.
 _OVERLAP_MIN_FLOATS = 1 << 19
 _overlap = {"enabled": os.environ.get("SP_DP_OVERLAP", "0"), "seq": 0, "written": {},
             "mark": None, "event_seq": -1, "e_early": None, "e_all": None, "e_done": None,
