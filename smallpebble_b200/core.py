@@ -218,15 +218,11 @@ def _tape_order_dfs(variable):
     return order
 
 
-def get_gradients(variable: Variable) -> dict:
-    """d(sum of `variable`)/d(node) for every node reachable from `variable` (sp.py:57-87).
-
-    Returns {Variable: DeviceArray}, keyed by identity, including `variable` itself (ones).
-    """
-    # Parents before children.  Every Variable is numbered at construction and an op's result is
-    # constructed after its inputs, so descending serial numbers ARE a reverse topological order
-    # of the tape: collect the reachable op nodes with a plain stack and sort them (leaves have
-    # no edges to walk and are skipped).
+def _tape_order(variable):
+    """Op nodes reachable from `variable`, parents before children.  Every Variable is numbered
+    at construction and an op's result is constructed after its inputs, so descending serial
+    numbers ARE a reverse topological order of the tape: collect the reachable op nodes with a
+    plain stack and sort them (leaves have no edges to walk and are skipped)."""
     seen, stack, order = {id(variable)}, [variable], []
     while stack:
         node = stack.pop()
@@ -243,6 +239,15 @@ def get_gradients(variable: Variable) -> dict:
         order.sort(key=_serial_of, reverse=True)
     except AttributeError:  # a Variable subclass that skipped Variable.__init__
         order = _tape_order_dfs(variable)
+    return order
+
+
+def get_gradients(variable: Variable) -> dict:
+    """d(sum of `variable`)/d(node) for every node reachable from `variable` (sp.py:57-87).
+
+    Returns {Variable: DeviceArray}, keyed by identity, including `variable` itself (ones).
+    """
+    order = _tape_order(variable)
 
     gradients = Gradients()
     seed_shape = variable.array.shape

@@ -159,3 +159,144 @@ def test_compute_fails_loudly_without_gpu():
         sp.add(v, v)
     with pytest.raises(_abi.SmallPebbleCudaError):
         sp.get_gradients(v)
+
+
+# ---- host-side machinery added for the launch-bound README loop (no kernel runs) -------------
+
+
+def _random_tape(rng, n_leaves=4, n_ops=14):
+    """A random DAG of Variables with dummy gradient closures (never called here)."""
+    from smallpebble_b200 import core
+
+    nodes = [core.Variable(np.zeros(1)) for _ in range(n_leaves)]
+    for _ in range(n_ops):
+        k = int(rng.integers(1, 4))
+        children = [nodes[int(i)] for i in rng.integers(0, len(nodes), k)]
+        nodes.append(core.Variable(np.zeros(1), [(c, None) for c in children]))
+    return nodes
+
+
+def test_tape_order_puts_every_parent_before_its_children():
+    """get_gradients sweeps the tape in descending construction order (core._tape_order);
+    on random DAGs that order must be a reverse topological order covering exactly the op
+    nodes the iterator-based DFS (the fallback) reaches."""
+    from smallpebble_b200 import core
+
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        nodes = _random_tape(rng)
+        root = nodes[-1]
+        order = core._tape_order(root)
+        assert {id(n) for n in order} == {id(n) for n in core._tape_order_dfs(root)}
+        position = {id(n): i for i, n in enumerate(order)}
+        for n in order:
+            for child, _ in n.local_gradients:
+                if child.local_gradients:
+                    assert position[id(n)] < position[id(child)]
+    # a Variable that bypassed __init__ (no serial number) falls back to the DFS
+    odd = core.Variable.__new__(core.Variable)
+    odd._array, odd.local_gradients = nodes[0].array, [(nodes[0], None)]
+    top = core.Variable(np.zeros(1), [(odd, None)])
+    assert [id(n) for n in core._tape_order(top)] == [id(top), id(odd)]
+
+
+def test_lazy_run_decides_once_per_argument_tuple_and_follows_reassignment():
+    calls = []
+    a, b = sp.Placeholder(), sp.Placeholder()
+    node = sp.Lazy(lambda x, y, k: calls.append((x, y, k)) or x + y + k)(a, b, 10)
+    a.assign_value(1)
+    b.assign_value(2)
+    assert node.run() == 13
+    a.assign_value(5)                       # placeholders are re-read on every run
+    assert node.run() == 17
+    inner = sp.Lazy(lambda x: x * 2)(a)
+    outer = sp.Lazy(lambda x, y: x - y)(inner, b)
+    assert outer.run() == 8
+    with pytest.raises(sp.AssignmentError):
+        sp.Lazy(lambda: 0).run()
+    with pytest.raises(sp.AssignmentError):
+        sp.Placeholder().run()
+
+
+def test_shape_plans_are_cached_and_validated():
+    from smallpebble_b200 import array as A
+    from smallpebble_b200 import core
+
+    assert core._matmul_plan((5, 4, 3), (3, 2))[:5] == (4, 3, 2, (5,), ())
+    assert core._matmul_plan((2, 1, 4, 3), (7, 3, 6))[7:] == ((2, 7), 14)
+    with pytest.raises(ValueError, match="not aligned"):
+        core._matmul_plan((4, 3), (2, 5))
+    with pytest.raises(ValueError, match="at least 2 dimensions"):
+        core._matmul_plan((3,), (3, 2))
+    assert A._reshape_plan((-1, 6), 24) == (4, 6)
+    with pytest.raises(ValueError, match="cannot reshape"):
+        A._reshape_plan((5, 5), 24)
+    steps, final, any_axis = A._reduce_plan((4, 5, 6), (0, 1), False)
+    assert steps == ((1, 20, 6),) and final == (6,) and any_axis
+    steps, final, _ = A._reduce_plan((4, 5, 6), (0, 2), True)
+    assert steps == ((20, 6, 1), (1, 4, 5)) and final == (1, 5, 1)
+    geom, out_shape, n_out = core._pool_plan((2, 7, 7, 3), 2, 2, 2, 2, "SAME")
+    assert out_shape == (2, 4, 4, 3) and n_out == 96 and geom[-2:] == (4, 4)
+
+
+def test_block_pool_recycles_on_last_reference_only():
+    """csrc/fastcall.c: a Block hands its buffer to the per-size free list when the LAST
+    reference dies (views share the Block), pool_alloc pops it, bypass and trim work.  Any
+    Python object stands in for the torch tensor here."""
+    fast = _abi._load_fast()
+    if fast is None or not hasattr(fast, "pool_alloc"):
+        pytest.skip("_sp_fastcall not built")
+    fast.pool_trim()
+    assert fast.pool_alloc(4096) is None
+    payload = object()
+    blk = fast.block_new(payload, 0xABC000, 4096, 1)
+    assert (blk.ptr, blk.nbytes, blk.tensor) == (0xABC000, 4096, payload)
+    view = blk                                  # a second holder
+    del blk
+    assert fast.pool_stats() == (0, 0)          # still referenced: not recycled
+    del view
+    assert fast.pool_stats() == (1, 4096)
+    again = fast.pool_alloc(4096)
+    assert again.ptr == 0xABC000 and again.tensor is payload and fast.pool_stats() == (0, 0)
+    assert fast.pool_alloc(8192) is None        # exact size match only
+    fast.pool_bypass(1)
+    del again
+    assert fast.pool_stats() == (0, 0)          # bypassed (CUDA-graph capture): freed, not pooled
+    fast.pool_bypass(-1)
+    once = fast.block_new(payload, 0x1000, 64, 0)
+    del once
+    assert fast.pool_stats() == (0, 0)          # recycle flag off
+    keep = fast.block_new(payload, 0x2000, 64, 1)
+    del keep
+    fast.pool_trim()
+    assert fast.pool_stats() == (0, 0)
+
+
+def test_data_parallel_bucket_split_follows_production_order():
+    """distributed._plan_split: the early part is everything but the last-produced <= 10 % of
+    the bucket (at least the very last gradient); offsets stay 16-byte aligned and cover the
+    bucket exactly once."""
+    class G:
+        def __init__(self, size):
+            self.size, self.shape = size, (size,)
+
+    variables = [object() for _ in range(5)]          # learnables in get_learnables order
+    sizes = [864, 36864, 147456, 11520, 10]           # conv1, conv2, conv3, fc w, fc b
+    grads = [G(n) for n in sizes]
+    dist._overlap["written"].clear()
+    for seq, i in enumerate([2, 3, 4, 1, 0], start=1):
+        dist._overlap["written"][variables[i]] = (seq, id(grads[i]))
+    try:
+        split = dist._plan_split({}, grads, variables)
+    finally:
+        dist._overlap["written"].clear()
+    assert split["order"] == [2, 3, 4, 1, 0] and split["k"] == 4
+    assert split["mark"] is variables[1]              # conv2's gradient completes the early part
+    assert all(off % 4 == 0 for off in split["offsets"])
+    spans = sorted((split["offsets"][i], split["offsets"][i] + (sizes[i] + 3) // 4 * 4)
+                   for i in range(5))
+    assert spans[0][0] == 0 and spans[-1][1] == split["total"]
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert split["early_count"] + split["late_count"] == split["total"]
+    assert split["late_count"] == 864                 # conv1's filters alone
+    assert dist._plan_split({}, grads[:1], variables[:1]) is None
