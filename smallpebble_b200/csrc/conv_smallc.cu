@@ -413,117 +413,11 @@ __global__ void __launch_bounds__(kThreads) conv_fprop_rgb3x3_tile4_kernel(
   }
 }
 
-// wgrad: a thread owns a 4 (tap-channel) x 8 (output channel) register tile and a 1/S share of
-// the staged pixels: 3 shared-memory quads feed 32 FMAs (the kernel above: 2 loads per 4).
-// The S pixel shares are summed through shared memory in a fixed order at the end, then the
-// per-block partial filter goes to the usual deterministic second pass.
-template <bool CHECK>
-__global__ void __launch_bounds__(kThreads) conv_wgrad_rgb3x3_tile_kernel(
-    const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partial,
-    const __grid_constant__ sp_conv_geom g, int pix_per_block) {
-  constexpr int KC = 27, KCP = 28, RG = 7;       // 7 row groups of 4 (row 27 is a zero pad)
-  extern __shared__ __align__(16) float sm[];
-  const int K = g.K, k8 = K >> 3;
-  float* patch_s = sm;                             // [kWgTile][KCP]
-  float* gy_s = sm + kWgTile * KCP;                // [kWgTile][K]
-  const int per_share = RG * k8;                   // threads working on one pixel share
-  const int S = kThreads / per_share;              // pixel shares
-  const int share = threadIdx.x / per_share;
-  const int rem = threadIdx.x - share * per_share;
-  const int rg = rem / k8, kg = rem - rg * k8;
-  const bool worker = share < S;
-  const int n_pix = g.N * g.OH * g.OW;
-  const int p_begin = blockIdx.x * pix_per_block;
-  const int p_end = min(n_pix, p_begin + pix_per_block);
-  const int row_stride = g.W * 3;
-  float acc[4][8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-  for (int pt = p_begin; pt < p_end; pt += kWgTile) {
-    const int tile = min(kWgTile, p_end - pt);
-    __syncthreads();  // previous tile consumed
-    const int k4 = K >> 2;
-    for (int i = threadIdx.x; i < tile * k4; i += kThreads) {
-      const int pp = i / k4, q = i - pp * k4;
-      *reinterpret_cast<float4*>(&gy_s[pp * K + q * 4]) =
-          __ldg(reinterpret_cast<const float4*>(gy + (int64_t)(pt + pp) * K) + q);
-    }
-    {
-      // thread (pixel, half): rows dy = 0,1 (18 values) or dy = 2 plus the pad (10 values)
-      const int pp = threadIdx.x >> 1, h = threadIdx.x & 1;
-      if (pp < tile) {
-        const int p = pt + pp;
-        const int ox = p % g.OW;
-        const int r = p / g.OW;
-        const int oy = r % g.OH, n = r / g.OH;
-        const int iy0 = oy * g.sy - g.pad_t, ix0 = ox * g.sx - g.pad_l;
-        const float* px = x + ((int64_t)(n * g.H + iy0) * g.W + ix0) * 3;
-        float* dst = patch_s + pp * KCP;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          if ((dy < 2) == (h == 0)) {
-            const bool row_in = !CHECK || (unsigned)(iy0 + dy) < (unsigned)g.H;
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const bool in = row_in && (!CHECK || (unsigned)(ix0 + dx) < (unsigned)g.W);
-#pragma unroll
-              for (int c = 0; c < 3; ++c)
-                dst[(dy * 3 + dx) * 3 + c] = in ? __ldg(px + dy * row_stride + dx * 3 + c) : 0.f;
-            }
-          }
-        }
-        if (h == 1) dst[KC] = 0.f;
-      }
-    }
-    __syncthreads();
-    if (worker) {
-      for (int pp = share; pp < tile; pp += S) {
-        const float4 a = *reinterpret_cast<const float4*>(&patch_s[pp * KCP + rg * 4]);
-        const float4 d0 = *reinterpret_cast<const float4*>(&gy_s[pp * K + kg * 8]);
-        const float4 d1 = *reinterpret_cast<const float4*>(&gy_s[pp * K + kg * 8 + 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[i][0] = fmaf(av[i], d0.x, acc[i][0]);
-          acc[i][1] = fmaf(av[i], d0.y, acc[i][1]);
-          acc[i][2] = fmaf(av[i], d0.z, acc[i][2]);
-          acc[i][3] = fmaf(av[i], d0.w, acc[i][3]);
-          acc[i][4] = fmaf(av[i], d1.x, acc[i][4]);
-          acc[i][5] = fmaf(av[i], d1.y, acc[i][5]);
-          acc[i][6] = fmaf(av[i], d1.z, acc[i][6]);
-          acc[i][7] = fmaf(av[i], d1.w, acc[i][7]);
-        }
-      }
-    }
-  }
-  // fixed-order sum of the S pixel shares: red[share][row][K] aliases the staging buffers
-  __syncthreads();
-  float* red = sm;
-  if (worker) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float* dst = red + ((share * KCP) + rg * 4 + i) * K + kg * 8;
-      *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-    }
-  }
-  __syncthreads();
-  float* out = partial + (int64_t)blockIdx.x * KC * K;
-  for (int i = threadIdx.x; i < KC * K; i += kThreads) {
-    float s = 0.f;
-    for (int sh = 0; sh < S; ++sh) s += red[sh * KCP * K + i];
-    out[i] = s;
-  }
-}
-
 // Single-launch RGB 3x3 filter gradient (cooperative grid, one block per SM):
 //   * the block walks its pixel tiles with a two-stage cp.async pipeline (dY rows as 16-byte
 //     copies, patches as zero-filling 4-byte copies): the next tile streams in while the
 //     current one is multiplied, so no thread ever waits on a global round trip;
-//   * register tiling as in conv_wgrad_rgb3x3_tile_kernel (4 x 8 accumulators per thread);
+//   * register tiling: 4 x 8 accumulators per thread (4 filter taps x 8 output channels);
 //   * per-block partial filters meet at a grid barrier and are summed in a fixed order by
 //     one warp per filter element -- deterministic, and no second kernel launch.
 __device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const float* src, bool valid) {
