@@ -408,7 +408,7 @@ def run_ours(args):
     value = global_batch * args.steps / (total_ms / 1e3)
 
     # ---- e2e: host batch -> H2D -> step -> loss D2H, every step ----------------------------
-    for i in range(10):
+    for i in range(max(10, WARMUP_FLOOR)):  # same untimed run-in as the `value` region
         step_e2e(i)
     sync_all()
     tc = transfer_counters()
