@@ -34,6 +34,15 @@ extern "C" {
 /* math mode of the contraction kernels */
 #define SP_PRECISION_FP32 0 /* CUDA-core FFMA, fp32 accumulate: rel err ~1e-6 vs float64 */
 #define SP_PRECISION_TF32 1 /* tcgen05.mma kind::tf32, TMEM fp32 accumulate: ~1e-3       */
+/* error-compensated tensor-core product a.b ~= a_r.b_r + a_l.b_r + a_r.b_l with r = the
+ * nearest TF32 value, l = x - r ("3xTF32", relative error ~2^-21; see csrc/tf32.cu for why
+ * the FORWARD contractions need it: the discrete routing of leaky_relu / maxpool2d).
+ * TF32X3: raw operands, for the entry points that can split in registers or are exact anyway
+ * (first-layer conv kernels, N <= 16 GEMMs; other GEMMs run the exact CUDA-core kernel);
+ * TF32_SPLIT: sp_conv2d_fprop[_leaky] only, operands pre-split by sp_tf32_split(SP_SPLIT_RL)
+ * and geom.C doubled -- which of the two to use: sp_conv2d_x3_plan */
+#define SP_PRECISION_TF32X3 2
+#define SP_PRECISION_TF32_SPLIT 3
 
 /* unary ops (sp.py:196-200 exp, 224-228 log, 314-318 neg, 367-375 square) */
 #define SP_UNARY_EXP 0
@@ -239,6 +248,36 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
                     int precision, void* workspace, size_t workspace_bytes,
                     sp_stream_t stream);
 
+/* ---- TF32 error compensation (no reference counterpart: the reference computes in float64;
+ * this is what keeps the tensor-core path within the stated 2e-3 of it, csrc/tf32.cu) ------ */
+#define SP_SPLIT_RL 0  /* parts (r, l)                                                        */
+#define SP_SPLIT_RLR 1 /* parts (r, l, r): left operand of a K-concatenated 3xTF32 product    */
+#define SP_SPLIT_RRL 2 /* parts (r, r, l): right operand                                      */
+#define SP_X3_NATIVE 0
+#define SP_X3_SPLIT2 2
+#define SP_X3_CONCAT3 3
+/* dst = the split of src: src viewed as [n / block_elems][block_elems] becomes
+ * [n / block_elems][parts][block_elems]; r = nearest TF32 of x (ties away), l = x - r.
+ * block_elems = 32 * inner for 32-channel blocks of a tensor [outer, C, inner] (activations
+ * NHWC: inner = 1; kernels HWIO: inner = K), or C * inner for whole-C blocks */
+int sp_tf32_split(const float* src, float* dst, int64_t n, int64_t block_elems, int kind,
+                  sp_stream_t stream);
+/* dst = nearest TF32 of src (the right operand of the single-pass backward contractions) */
+int sp_tf32_round(const float* src, float* dst, int64_t n, sp_stream_t stream);
+/* both of the above for many tensors in ONE launch (the weights' shadows, once per optimiser
+ * step): host tables of device pointers; host_rounded[i] / host_split[i] may be NULL */
+int sp_tf32_shadow_multi(int n_tensors, const float* const* host_src, float* const* host_rounded,
+                         float* const* host_split, const int64_t* host_numel,
+                         const int64_t* host_block_elems, const int32_t* host_kind,
+                         sp_stream_t stream);
+/* on != 0: the kernels that produce operands of the backward contractions (sp_leaky_relu_bwd,
+ * sp_maxpool2d_bwd, sp_maxpool2d_leaky_bwd, sp_softmax_bwd over the last axis,
+ * sp_softmax_xent_bwd[_colsum], sp_conv2d_dgrad_leaky) round what they store to the nearest TF32
+ * value, turning the tensor core's operand truncation into an unbiased rounding */
+int sp_set_tf32_output_rounding(int on);
+/* *plan = SP_X3_*: how sp_conv2d_fprop of this geometry is run error-compensated */
+int sp_conv2d_x3_plan(const sp_conv_geom* g, int* plan);
+
 /* ---- optimisers (sp.py:552-583 Adam, 645-653 SGD), multi-tensor ---------------------- */
 /* All pointer tables are HOST arrays of device pointers (passed by value to the kernel).
  * host_step[i] points to a DEVICE int32 holding the number of completed steps of tensor i;
@@ -250,6 +289,13 @@ int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_
                   float* const* host_m, float* const* host_v, const int64_t* host_numel,
                   int32_t* const* host_step, float alpha, float beta1, float beta2, float eps,
                   sp_stream_t stream);
+/* the same update written to host_p_out[i] instead of over host_p[i] (the two may be equal):
+ * the reference REBINDS variable.array to a new array (sp.py:583), so anything that still
+ * holds the old array -- a not-yet-evaluated gradient closure, say -- keeps the old values */
+int sp_adam_multi_out(int n_tensors, float* const* host_p, float* const* host_p_out,
+                      const float* const* host_g, float* const* host_m, float* const* host_v,
+                      const int64_t* host_numel, int32_t* const* host_step, float alpha,
+                      float beta1, float beta2, float eps, sp_stream_t stream);
 int sp_sgd_multi(int n_tensors, float* const* host_p, const float* const* host_g,
                  const int64_t* host_numel, float lr, sp_stream_t stream);
 /* gather many gradient tensors into one flat bucket (the data-parallel all-reduce payload):

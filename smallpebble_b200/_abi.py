@@ -14,6 +14,10 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libsmallpebble_b200.so")
 
 PRECISION_FP32 = 0
 PRECISION_TF32 = 1
+PRECISION_TF32X3 = 2      # error-compensated, raw operands (kernels that split in registers)
+PRECISION_TF32_SPLIT = 3  # error-compensated, operands pre-split by sp_tf32_split
+SPLIT_RL, SPLIT_RLR, SPLIT_RRL = 0, 1, 2
+X3_NATIVE, X3_SPLIT2, X3_CONCAT3 = 0, 2, 3
 
 UNARY = {"exp": 0, "log": 1, "neg": 2, "square": 3, "scale": 4, "add_scalar": 5, "recip": 6,
          "sqrt": 7, "copy": 8}
@@ -87,7 +91,16 @@ SIGNATURES = {
     "sp_conv2d_wgrad": (C.c_int, [vp, vp, vp, C.POINTER(ConvGeom), C.c_int, vp, sz, vp]),
     "sp_adam_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                 C.POINTER(vp), p_i64, C.POINTER(vp), f32, f32, f32, f32, vp]),
+    "sp_adam_multi_out": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                    C.POINTER(vp), C.POINTER(vp), p_i64, C.POINTER(vp), f32, f32,
+                                    f32, f32, vp]),
     "sp_sgd_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), p_i64, f32, vp]),
+    "sp_tf32_split": (C.c_int, [vp, vp, i64, i64, C.c_int, vp]),
+    "sp_tf32_round": (C.c_int, [vp, vp, i64, vp]),
+    "sp_tf32_shadow_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                       p_i64, p_i64, C.POINTER(C.c_int32), vp]),
+    "sp_set_tf32_output_rounding": (C.c_int, [C.c_int]),
+    "sp_conv2d_x3_plan": (C.c_int, [C.POINTER(ConvGeom), C.POINTER(C.c_int)]),
     "sp_pack_multi": (C.c_int, [C.c_int, C.POINTER(vp), p_i64, p_i64, vp, vp]),
 }
 
@@ -99,7 +112,7 @@ _LAUNCHING = {
     if n not in ("sp_abi_version", "sp_last_error", "sp_device_info", "sp_debug_set_umma_policy",
                  "sp_debug_tma2_trace", "sp_host_is_pinned", "sp_stream_create", "sp_event_create",
                  "sp_event_record", "sp_stream_wait_event", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
-                 "sp_conv2d_wgrad_workspace")
+                 "sp_conv2d_wgrad_workspace", "sp_set_tf32_output_rounding", "sp_conv2d_x3_plan")
 }
 
 

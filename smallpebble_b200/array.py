@@ -60,7 +60,23 @@ def require_cuda():
     _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
     if _raw_stream is None:  # older torch: slower, same handle
         _raw_stream = lambda idx: torch.cuda.current_stream(idx).cuda_stream  # noqa: E731
+    for hook in _ready_hooks:
+        hook()
     return _device
+
+
+_ready_hooks = []
+
+
+def on_device_ready(hook) -> None:
+    """Run `hook()` once the CUDA library is bound to a device (library-global settings)."""
+    _ready_hooks.append(hook)
+    if _device is not None:
+        hook()
+
+
+def device_ready() -> bool:
+    return _device is not None
 
 
 def reset_device_cache():
@@ -173,6 +189,28 @@ class pool_bypass:
         _pool_set_bypass(-1)
 
 
+def capturing() -> bool:
+    """True while a CUDA graph is being recorded (sp.capture): buffers must be static."""
+    return _pool_bypass > 0
+
+
+# Deferred arrays (their pending kernel may read a PARAMETER buffer: conv2d / matmul outputs
+# waiting for a fusing consumer).  An optimiser that updates parameters in place launches them
+# first (graph._settle_before_inplace_update); the out-of-place Adam never needs to.
+_pending_refs = []
+_weakref = weakref.ref
+
+
+def flush_pending_parameter_readers() -> None:
+    """Launch every deferred array that is still pending (in creation order)."""
+    refs = list(_pending_refs)
+    del _pending_refs[:]
+    for ref in refs:
+        arr = ref()
+        if arr is not None and arr._ptr is None and arr._thunk is not None:
+            arr._materialize()
+
+
 def trim_pool() -> None:
     """Hand every recycled buffer back to torch's allocator."""
     _pool_trim()
@@ -201,7 +239,7 @@ _prod = math.prod
 
 class DeviceArray:
     __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "_thunk", "_tag", "_aux",
-                 "__weakref__")
+                 "_tf32", "_shadow", "__weakref__")
     __array_priority__ = 1000.0
 
     def __init__(self, shape, dtype=FLOAT, buf=None, ptr=None, host=None):
@@ -214,6 +252,8 @@ class DeviceArray:
         self._thunk = None
         self._tag = None
         self._aux = None  # by-product of the producing kernel, e.g. ("colsum0", column sums)
+        self._tf32 = None    # True: every value is TF32-representable (rounded by its producer)
+        self._shadow = None  # [epoch, rounded copy, {(kind, block): split copy}] (tf32_shadows)
 
     # ---- construction ---------------------------------------------------------------------
     @staticmethod
@@ -235,6 +275,8 @@ class DeviceArray:
         self._thunk = None
         self._tag = None
         self._aux = None
+        self._tf32 = None
+        self._shadow = None
         nbytes = (size or 1) * dtype.itemsize
         if _pool_bypass or nbytes > _POOL_MAX_BLOCK:
             self._buf = buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
@@ -268,8 +310,14 @@ class DeviceArray:
         self._ptr = None
         self._host = None
         self._aux = None
+        self._tf32 = None
+        self._shadow = None
         self._thunk = thunk
         self._tag = tag
+        if len(_pending_refs) > 512:  # drop the dead and the launched
+            _pending_refs[:] = [r for r in _pending_refs
+                                if (a := r()) is not None and a._ptr is None]
+        _pending_refs.append(_weakref(self))
         return self
 
     @property
@@ -287,6 +335,7 @@ class DeviceArray:
         """A deferred array takes over `out`'s buffer: whoever calls this fills it instead of
         the pending thunk (a consumer that fused the producing op into its own kernel)."""
         self._buf, self._ptr = out._buf, out._ptr
+        self._tf32 = out._tf32
         self._thunk = None
         self._tag = None
 
@@ -442,6 +491,8 @@ class DeviceArray:
         out._thunk = None
         out._tag = None
         out._aux = None
+        out._tf32 = self._tf32
+        out._shadow = None
         return out
 
     def copy(self) -> "DeviceArray":
@@ -506,6 +557,7 @@ class DeviceArray:
 
     def _rebind(self, other: "DeviceArray"):
         self._buf, self._ptr, self._host = other._buf, other.ptr, None
+        self._tf32, self._shadow = other._tf32, None
         return self
 
     def __iadd__(self, o):
@@ -778,6 +830,8 @@ def accumulate_(dst: DeviceArray, src: DeviceArray) -> DeviceArray:
     """dst += src in place (same shape)."""
     F.sp_accumulate(dst.ptr, src.ptr, dst.size, stream())
     dst._aux = None  # by-products described the old contents
+    dst._tf32 = None  # a sum of TF32 values is not a TF32 value
+    dst._shadow = None
     return dst
 
 
@@ -956,3 +1010,100 @@ def where(cond, a: DeviceArray, b: DeviceArray) -> DeviceArray:
         F.sp_where(c.ptr, _abi.dims(strides(cond.shape)), a.ptr, _abi.dims(strides(a.shape)),
                    b.ptr, _abi.dims(strides(b.shape)), out._ptr, nd, _abi.dims(shape), stream())
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# TF32 error compensation (csrc/tf32.cu): rounded / split shadows of contraction operands
+# --------------------------------------------------------------------------------------------
+
+inplace_epoch = 0  # bumped by whoever overwrites parameter buffers IN PLACE (sgd_step, a
+                   # captured Adam step): shadows made before that are stale
+
+
+def note_inplace_update() -> None:
+    global inplace_epoch
+    inplace_epoch += 1
+
+
+def _shadow_slot(a: DeviceArray):
+    sh = a._shadow
+    if sh is None or sh[0] != inplace_epoch:
+        sh = a._shadow = [inplace_epoch, None, {}]
+    return sh
+
+
+def tf32_round(a: DeviceArray) -> DeviceArray:
+    """`a` rounded to the nearest TF32 values (itself when its producer already rounded it):
+    the operand form of the single-pass backward contractions.  Cached on the array."""
+    if a._tf32:
+        return a
+    sh = _shadow_slot(a)
+    out = sh[1]
+    if out is None:
+        out = DeviceArray.empty(a.shape, FLOAT, a.size)
+        if a.size:
+            F.sp_tf32_round(a.ptr, out._ptr, a.size, stream())
+        out._tf32 = True
+        sh[1] = out
+    return out
+
+
+def tf32_split(a: DeviceArray, kind: int, block_elems: int) -> DeviceArray:
+    """The (r, l[, r]) split of `a` for an error-compensated forward contraction, flat
+    [a.size / block_elems, parts, block_elems].  Cached on the array."""
+    sh = _shadow_slot(a)
+    key = (kind, block_elems)
+    out = sh[2].get(key)
+    if out is None:
+        parts = 2 if kind == _abi.SPLIT_RL else 3
+        out = DeviceArray.empty((a.size * parts,), FLOAT, a.size * parts)
+        if a.size:
+            F.sp_tf32_split(a.ptr, out._ptr, a.size, block_elems, kind, stream())
+        sh[2][key] = out
+    return out
+
+
+def tf32_shadow_requests(a: DeviceArray):
+    """(wants rounded copy?, [(kind, block_elems), ...]) that were made for `a`: the optimiser
+    re-creates the same shadows for the array that replaces it, all tensors in one launch."""
+    sh = a._shadow
+    if sh is None:
+        return False, ()
+    return sh[1] is not None, tuple(sh[2])
+
+
+def tf32_shadows_multi(jobs) -> None:
+    """jobs: [(array, want_rounded, [(kind, block_elems), ...])].  Fills the shadow slots of
+    every array with ONE launch per 24 tensors (a job with two split kinds takes two rows)."""
+    rows = []
+    for a, want_round, kinds in jobs:
+        if not a.size:
+            continue
+        sh = _shadow_slot(a)
+        rounded = None
+        if want_round and sh[1] is None and not a._tf32:
+            rounded = DeviceArray.empty(a.shape, FLOAT, a.size)
+            rounded._tf32 = True
+            sh[1] = rounded
+        first = True
+        for kind, block in kinds:
+            if (kind, block) in sh[2]:
+                continue
+            parts = 2 if kind == _abi.SPLIT_RL else 3
+            sp = DeviceArray.empty((a.size * parts,), FLOAT, a.size * parts)
+            sh[2][(kind, block)] = sp
+            rows.append((a, rounded if first else None, sp, block, kind))
+            first = False
+        if first and rounded is not None:
+            rows.append((a, rounded, None, 1, 0))
+    if not rows:
+        return
+    n = len(rows)
+    vp = C.c_void_p
+    src = (vp * n)(*[r[0].ptr for r in rows])
+    rnd = (vp * n)(*[(r[1]._ptr if r[1] is not None else None) for r in rows])
+    spl = (vp * n)(*[(r[2]._ptr if r[2] is not None else None) for r in rows])
+    numel = (C.c_int64 * n)(*[r[0].size for r in rows])
+    blocks = (C.c_int64 * n)(*[r[3] for r in rows])
+    kinds = (C.c_int32 * n)(*[r[4] for r in rows])
+    F.sp_tf32_shadow_multi(n, src, rnd, spl, numel, blocks, kinds, stream())

@@ -20,6 +20,7 @@ Differences from the reference, all internal:
 
 from __future__ import annotations
 
+import ctypes as C
 import functools
 import itertools
 import math
@@ -38,19 +39,86 @@ F = _abi.f
 # configuration
 # --------------------------------------------------------------------------------------------
 
-_PRECISIONS = {"fp32": _abi.PRECISION_FP32, "tf32": _abi.PRECISION_TF32}
-_precision = _PRECISIONS[os.environ.get("SP_PRECISION", "tf32").lower()]
+# name -> (precision code of a single-pass contraction, error compensation on?)
+_PRECISIONS = {"fp32": (_abi.PRECISION_FP32, False), "tf32": (_abi.PRECISION_TF32, True),
+               "tf32x1": (_abi.PRECISION_TF32, False)}
+_precision_name = os.environ.get("SP_PRECISION", "tf32").lower()
+_precision, _compensate = _PRECISIONS[_precision_name]
+
+
+# Library-global switch "round what the gradient kernels store to TF32" (csrc/common.cuh),
+# mirrored here so that the ABI is only called when it changes -- in a training step it never
+# does: see _want_rounding().
+_rounding_state = False
+
+
+def _apply_rounding_mode():
+    F.sp_set_tf32_output_rounding(1 if _rounding_state else 0)
+
+
+A.on_device_ready(_apply_rounding_mode)
+
+
+def _reset_rounding() -> None:
+    """Back to exact stores (used between tests that call the ABI directly)."""
+    global _rounding_state
+    if _rounding_state:
+        _rounding_state = False
+        if A.device_ready():
+            _apply_rounding_mode()
+
+
+def _want_rounding(child) -> bool:
+    """Called by a gradient closure right before it launches the kernel that produces the
+    gradient of `child`: when that gradient is going to be an operand of a tensor-core
+    contraction (`child` is the output of conv2d / matmul, possibly through `+ bias` or a
+    reshape) and the mode compensates, the kernel rounds what it stores to the nearest TF32
+    value -- the tensor core would otherwise TRUNCATE it, a coherent bias.  Gradients that feed
+    anything else are stored exactly."""
+    global _rounding_state
+    want = _compensate and getattr(child, "_to_contraction", False)
+    if want != _rounding_state:
+        _rounding_state = want
+        _apply_rounding_mode()
+    return want
 
 
 def set_precision(name: str) -> None:
-    """'tf32': contractions on tcgen05 tensor cores (rel. tol 2e-3 vs the float64 reference);
-    'fp32': CUDA-core FFMA (rel. tol 1e-5)."""
-    global _precision
-    _precision = _PRECISIONS[name.lower()]
+    """Math mode of the contractions (conv2d, matmul and their gradients).
+
+    'tf32'   tcgen05 tensor cores, error-compensated where it matters: FORWARD contractions
+             run as 3xTF32 (operands split into a TF32 value and its remainder, three products),
+             so the discrete routing downstream -- leaky_relu's sign, maxpool2d's argmax --
+             agrees with the float64 reference; backward contractions are single-pass with
+             operands rounded to nearest instead of truncated.  Forward values ~1e-6, model
+             gradients within 2e-3 of the float64 reference (csrc/tf32.cu).
+    'tf32x1' every contraction a single tcgen05 pass on raw fp32 operands (the hardware
+             truncates them to TF32): 2e-3 per op, but model-level gradients drift by a few
+             percent because ~1e-4 of the routing decisions flip.  Fastest.
+    'fp32'   CUDA-core FFMA (rel. tol 1e-5)."""
+    global _precision, _compensate, _precision_name
+    _precision, _compensate = _PRECISIONS[name.lower()]
+    _precision_name = name.lower()
+    _conv_plan.cache_clear()
+    _reset_rounding()
 
 
 def get_precision() -> str:
-    return "tf32" if _precision == _abi.PRECISION_TF32 else "fp32"
+    return _precision_name
+
+
+def _fwd_native_precision() -> int:
+    """Precision code of a FORWARD contraction for entry points that reach full accuracy by
+    themselves (first-layer conv kernels, N <= 16 GEMMs): 3xTF32 when compensating."""
+    return _abi.PRECISION_TF32X3 if _compensate else _precision
+
+
+def _bwd_operand(g: DeviceArray) -> DeviceArray:
+    """Operand of a single-pass BACKWARD contraction: rounded to the nearest TF32 values when
+    compensating (most gradients arrive rounded by the kernel that produced them: no launch)."""
+    if _compensate and not g._tf32:
+        return A.tf32_round(g)
+    return g
 
 
 def debug_set_kernel_policy(policy: int) -> None:
@@ -410,13 +478,17 @@ def add(a: Variable, b: Variable) -> Variable:
         # stays deferred unless somebody reads it
         _, av, bv, rows, n, k = tag
         value = DeviceArray.empty(sa)
-        F.sp_gemm_bias(rows, n, k, av.ptr, bv.ptr, b.array.ptr, value.ptr, _precision, A.stream())
+        F.sp_gemm_bias(rows, n, k, av.ptr, bv.ptr, b.array.ptr, value.ptr, _fwd_native_precision(),
+                       A.stream())
     else:
         value = A.binary("add", a.array, b.array)
-    return Variable(value, [
+    out = Variable(value, [
         (a, lambda g: _unbroadcast(g, sa, ra)),
         (b, lambda g: _unbroadcast(g, sb, rb)),
     ])
+    if sa == value.shape and getattr(a, "_to_contraction", False):
+        out._to_contraction = True  # `matmul(x, w) + bias`: the gradient passes through to a
+    return out
 
 
 def sub(a: Variable, b: Variable) -> Variable:
@@ -491,8 +563,7 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
         if tag is not None and tag[0] == "conv2d" and alpha > 0:
             # the input is a conv2d that has not been launched: the activation is applied in
             # the conv kernel's epilogue and the pre-activation tensor is never written
-            _, cx, cw, geom, prec = tag
-            F.sp_conv2d_fprop_leaky(cx.ptr, cw.ptr, out.ptr, geom, prec, alpha, A.stream())
+            tag[1](out, alpha)
         else:
             F.sp_leaky_relu_fwd(x.ptr, out.ptr, x.size, alpha, A.stream())
 
@@ -504,12 +575,14 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
 
     def multiply_by_locgrad(g):
         dx = DeviceArray.empty_like(x)
+        rounded = _want_rounding(a)
         tag = g.pending_tag if isinstance(g, DeviceArray) else None
         if tag is not None and tag[0] == "maxpool2d_bwd" and tag[1] is y:
             # the upstream gradient is a pool gradient that has not been launched: one kernel
             # scatters it and applies this op's slope
             _, _, g0, idx, geom = tag
             F.sp_maxpool2d_leaky_bwd(g0.ptr, idx.ptr, x.ptr, dx.ptr, *geom, alpha, A.stream())
+            dx._tf32 = rounded  # rounded as stored: an operand of the conv gradients
             return dx
         # the slope depends on the sign of the input only; when the input was never stored
         # (conv + leaky ran as one kernel, alpha > 0) the output has the same sign
@@ -519,9 +592,11 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
             # conv kernel multiplies by this op's slope as it stores
             _, g0, cw, cgeom, cprec = tag
             F.sp_conv2d_dgrad_leaky(g0.ptr, cw.ptr, src.ptr, dx.ptr, cgeom, cprec, alpha, A.stream())
+            dx._tf32 = rounded
             return dx
         g = _as_device(g)
         F.sp_leaky_relu_bwd(g.ptr, src.ptr, dx.ptr, x.size, alpha, A.stream())
+        dx._tf32 = rounded
         return dx
 
     return Variable(y, [(a, multiply_by_locgrad)])
@@ -551,7 +626,10 @@ def where(condition: np.ndarray, a: Variable, b: Variable) -> Variable:
 def reshape(a: Variable, shape) -> Variable:
     "Reshape `a` into shape `shape` (sp.py:333-337): metadata only on device."
     src_shape = a.array.shape
-    return Variable(a.array.reshape(shape), [(a, lambda g: g.reshape(src_shape))])
+    out = Variable(a.array.reshape(shape), [(a, lambda g: g.reshape(src_shape))])
+    if getattr(a, "_to_contraction", False):
+        out._to_contraction = True
+    return out
 
 
 def expand_dims(a: Variable, axis) -> Variable:
@@ -685,11 +763,11 @@ def maxax(a: Variable, axis: int) -> Variable:
 # --------------------------------------------------------------------------------------------
 
 
-def _gemm(ta, tb, m, n, k, a, lda, sa, b, ldb, sb, batch, out_shape) -> DeviceArray:
+def _gemm(ta, tb, m, n, k, a, lda, sa, b, ldb, sb, batch, out_shape, precision=None) -> DeviceArray:
     out = DeviceArray.empty(out_shape)
     if out.size:
         F.sp_gemm(ta, tb, m, n, k, a.ptr, lda, sa, b.ptr, ldb, sb, out.ptr, n, m * n, batch,
-                  _precision, A.stream())
+                  _precision if precision is None else precision, A.stream())
     return out
 
 
@@ -725,36 +803,62 @@ def matmul(a: Variable, b: Variable) -> Variable:
         if _fuse_bias and N <= 16 and a.local_gradients and len(a_batch) == 0 and rows and K:
             # the 10-way classifier: deferred so that `+ bias` (core.add) can run as part of
             # the same kernel; anything else that touches the product launches it as usual
+            # (N <= 16 runs on the exact-fp32 skinny kernel: already fully accurate)
+            fwd_prec = _fwd_native_precision()
             value = DeviceArray.deferred(
                 (M, N),
                 lambda out: F.sp_gemm(0, 0, rows, N, K, av.ptr, K, 0, bv.ptr, N, 0, out.ptr, N,
-                                      rows * N, 1, _precision, A.stream()),
+                                      rows * N, 1, fwd_prec, A.stream()),
                 ("matmul", av, bv, rows, N, K))
+        elif _compensate and N > 16 and rows and K:
+            # error-compensated forward product (3xTF32) as ONE tensor-core GEMM over a
+            # contraction axis of 3K: [a_r | a_l | a_r] . [b_r ; b_r ; b_l]  (csrc/tf32.cu)
+            a3 = A.tf32_split(av, _abi.SPLIT_RLR, K)
+            b3 = A.tf32_split(bv, _abi.SPLIT_RRL, K * N)
+            value = _gemm(0, 0, rows, N, 3 * K, a3, 3 * K, 0, b3, N, 0, 1, a_batch + (M, N))
         else:
-            value = _gemm(0, 0, rows, N, K, av, K, 0, bv, N, 0, 1, a_batch + (M, N))
+            value = _gemm(0, 0, rows, N, K, av, K, 0, bv, N, 0, 1, a_batch + (M, N),
+                          _fwd_native_precision())
+
+        # N <= 16 (the classifier): all three products are tiny and run exactly -- the skinny
+        # kernels are fp32 already, g . b^T contracts over N only -- so nothing is rounded
+        exact = _compensate and N <= 16
 
         def grad_a(g):  # g . b^T
-            return _gemm(0, 1, rows, K, N, g, N, 0, bv, N, 0, 1, av.shape)
+            if exact:
+                return _gemm(0, 1, rows, K, N, g, N, 0, bv, N, 0, 1, av.shape, _abi.PRECISION_FP32)
+            g, bw = _bwd_operand(g), _bwd_operand(bv)
+            return _gemm(0, 1, rows, K, N, g, N, 0, bw, N, 0, 1, av.shape)
 
         def grad_b(g):  # a^T . g   (the sum over the batch is inside the contraction)
-            return _gemm(1, 0, K, N, rows, av, K, 0, g, N, 0, 1, bv.shape)
+            if exact:
+                return _gemm(1, 0, K, N, rows, av, K, 0, g, N, 0, 1, bv.shape, _fwd_native_precision())
+            return _gemm(1, 0, K, N, rows, av, K, 0, _bwd_operand(g), N, 0, 1, bv.shape)
 
-        return Variable(value, [(a, grad_a), (b, grad_b)])
+        out = Variable(value, [(a, grad_a), (b, grad_b)])
+        out._to_contraction = not exact
+        return out
 
     # general case: materialise broadcast batch dims, then strided-batched GEMMs
+    # (compensated mode: the forward product takes the exact CUDA-core kernel)
     af = _broadcast_to(av, batch_shape + (M, K)) if a_batch != batch_shape else av
     bf = _broadcast_to(bv, batch_shape + (K, N)) if b_batch != batch_shape else bv
-    value = _gemm(0, 0, M, N, K, af, K, M * K, bf, N, K * N, nb, batch_shape + (M, N))
+    value = _gemm(0, 0, M, N, K, af, K, M * K, bf, N, K * N, nb, batch_shape + (M, N),
+                  _fwd_native_precision())
 
     def grad_a(g):
-        full = _gemm(0, 1, M, K, N, g, N, M * N, bf, N, K * N, nb, batch_shape + (M, K))
+        full = _gemm(0, 1, M, K, N, _bwd_operand(g), N, M * N, _bwd_operand(bf), N, K * N, nb,
+                     batch_shape + (M, K))
         return _unbroadcast(full, av.shape, ra)
 
     def grad_b(g):
-        full = _gemm(1, 0, K, N, M, af, K, M * K, g, N, M * N, nb, batch_shape + (K, N))
+        full = _gemm(1, 0, K, N, M, af, K, M * K, _bwd_operand(g), N, M * N, nb,
+                     batch_shape + (K, N))
         return _unbroadcast(full, bv.shape, rb)
 
-    return Variable(value, [(a, grad_a), (b, grad_b)])
+    out = Variable(value, [(a, grad_a), (b, grad_b)])
+    out._to_contraction = True
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -779,7 +883,33 @@ def _conv_plan(x_shape, w_shape, padding, strides):
     geom = _conv_geom(n_images, imheight, imwidth, channels, kernheight, kernwidth, channels_out,
                       stride_y, stride_x, pt, pl, outh, outw)
     out_shape = (n_images, outh, outw, channels_out)
-    return geom, out_shape, {}, math.prod(out_shape)
+    return geom, out_shape, {}, math.prod(out_shape), {}
+
+
+def _conv_x3(plan):
+    """How the forward contraction of this geometry runs error-compensated (csrc/tf32.cu):
+    (X3 plan code, geometry the kernel sees, precision code, split kind / block of the images,
+    split kind / block of the kernels) -- decided once per geometry by the library."""
+    x3 = plan[4].get("x3")
+    if x3 is None:
+        g = plan[0]
+        code = C.c_int(0)
+        _abi.f.sp_conv2d_x3_plan(g, code)
+        code = code.value
+        if code == _abi.X3_NATIVE:
+            x3 = (code, g, _abi.PRECISION_TF32X3, None, None)
+        else:
+            parts = 2 if code == _abi.X3_SPLIT2 else 3
+            g2 = _conv_geom(g.N, g.H, g.W, parts * g.C, g.KH, g.KW, g.K, g.sy, g.sx, g.pad_t,
+                            g.pad_l, g.OH, g.OW)
+            if code == _abi.X3_SPLIT2:  # (r, l) interleaved per 32 channels, split-aware kernel
+                x3 = (code, g2, _abi.PRECISION_TF32_SPLIT, (_abi.SPLIT_RL, 32),
+                      (_abi.SPLIT_RL, 32 * g.K))
+            else:                       # plain K-concatenation: [r | l | r] . [r ; r ; l]
+                x3 = (code, g2, _abi.PRECISION_TF32, (_abi.SPLIT_RLR, g.C),
+                      (_abi.SPLIT_RRL, g.C * g.K))
+        plan[4]["x3"] = x3
+    return x3
 
 
 def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(1, 1)) -> Variable:
@@ -794,31 +924,49 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
     plan = _conv_plan(x.shape, w.shape, padding, tuple(strides))
     geom, out_shape = plan[0], plan[1]
     prec = _precision
+    compensate = _compensate
 
-    def launch(out):
-        if out.size:
-            F.sp_conv2d_fprop(x.ptr, w.ptr, out.ptr, geom, prec, A.stream())
+    def launch(out, alpha=None):
+        """y = conv2d(x, w), or leaky_relu(conv2d(x, w), alpha) in the kernel's epilogue."""
+        if not out.size:
+            return
+        xa, wa, g, pr = x, w, geom, prec
+        if compensate:
+            # forward contraction error-compensated (3xTF32): the routing decisions taken on
+            # this tensor (leaky_relu sign, maxpool argmax) must match the float64 reference
+            _, g, pr, xsplit, wsplit = _conv_x3(plan)
+            if xsplit is not None:
+                xa = A.tf32_split(x, *xsplit)
+                wa = A.tf32_split(w, *wsplit)
+        if alpha is None:
+            F.sp_conv2d_fprop(xa.ptr, wa.ptr, out.ptr, g, pr, A.stream())
+        else:
+            F.sp_conv2d_fprop_leaky(xa.ptr, wa.ptr, out.ptr, g, pr, alpha, A.stream())
 
     out_size = plan[3]
     if _fuse_conv_leaky and out_size:
         # not launched yet: a leaky_relu consumer folds its activation into this kernel's
         # epilogue (core.leaky_relu); anything else that touches the result launches it as usual
-        y = DeviceArray.deferred(out_shape, launch, ("conv2d", x, w, geom, prec), out_size)
+        y = DeviceArray.deferred(out_shape, launch, ("conv2d", launch), out_size)
     else:
         y = DeviceArray.empty(out_shape, A.FLOAT, out_size)
         launch(y)
 
     def grad_images(g):
         prec_b = _precision
+        # single-pass contraction g . w^T: operands rounded to nearest when compensating (the
+        # gradient usually arrives rounded by its producer, the weights from their shadow)
+        g = _bwd_operand(_as_device(g))
+        wr = _bwd_operand(w)
 
         def launch_dgrad(out):
             if out.size:
-                F.sp_conv2d_dgrad(g.ptr, w.ptr, out.ptr, geom, prec_b, A.stream())
+                F.sp_conv2d_dgrad(g.ptr, wr.ptr, out.ptr, geom, prec_b, A.stream())
 
-        if _fuse_conv_leaky and x.size and isinstance(g, DeviceArray):
+        if _fuse_conv_leaky and x.size:
             # not launched yet: when the consumer is a leaky_relu's gradient closure, the slope
             # is applied as the data gradient is stored (sp_conv2d_dgrad_leaky)
-            return DeviceArray.deferred(x.shape, launch_dgrad, ("conv2d_dgrad", g, w, geom, prec_b),
+            return DeviceArray.deferred(x.shape, launch_dgrad, ("conv2d_dgrad", g, wr, geom, prec_b),
                                         x.size)
         dx = DeviceArray.empty_like(x)
         launch_dgrad(dx)
@@ -826,6 +974,7 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
 
     def grad_kernels(g):
         dw = DeviceArray.empty_like(w)
+        g = _bwd_operand(_as_device(g))
         ws_bytes = plan[2].get(_precision)
         if ws_bytes is None:
             ws_bytes = plan[2][_precision] = _abi.load().sp_conv2d_wgrad_workspace(geom, _precision)
@@ -834,7 +983,9 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
                           ws.ptr if ws is not None else None, ws_bytes, A.stream())
         return dw
 
-    return Variable(y, [(images, grad_images), (kernels, grad_kernels)])
+    out = Variable(y, [(images, grad_images), (kernels, grad_kernels)])
+    out._to_contraction = True  # gradients w.r.t. this tensor are operands of contractions
+    return out
 
 
 _UINT8 = np.dtype(np.uint8)
@@ -877,7 +1028,9 @@ def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = 
 
         def launch(out):
             if out.size:
+                rounded = _want_rounding(images)
                 F.sp_maxpool2d_bwd(g.ptr, idx.ptr, out.ptr, *geom, A.stream())
+                out._tf32 = rounded
 
         if fused and x.size:
             # deferred: leaky_relu's gradient closure folds this scatter into its own kernel
@@ -922,7 +1075,9 @@ def softmax(a: Variable, axis: int = -1) -> Variable:
     def multiply_by_locgrad(g):
         dx = DeviceArray.empty_like(x)
         if dx.size:
+            rounded = _want_rounding(a)
             F.sp_softmax_bwd(y.ptr, g.ptr, dx.ptr, outer, n, inner, A.stream())
+            dx._tf32 = rounded and inner == 1
         return dx
 
     out = Variable(y, [(a, multiply_by_locgrad)])
@@ -968,6 +1123,7 @@ def cross_entropy(y_pred: Variable, y_true: np.ndarray, axis: int = -1) -> Varia
 
         def grad_logits(g):
             dlogits = DeviceArray.empty_like(logits)
+            rounded = _want_rounding(logits_var)
             if dlogits.size and _fuse_bias and rows * cols <= 32768:
                 # also emits the column sums: the gradient of a bias added to the logits, which
                 # core._unbroadcast picks up instead of launching a reduction
@@ -978,6 +1134,7 @@ def cross_entropy(y_pred: Variable, y_true: np.ndarray, axis: int = -1) -> Varia
             elif dlogits.size:
                 F.sp_softmax_xent_bwd(probs.ptr, labels.ptr, g.ptr, dlogits.ptr, rows, cols,
                                       A.stream())
+            dlogits._tf32 = rounded  # rounded as stored: operand of the classifier's grads
             return dlogits
 
         out = Variable(loss, [(logits_var, grad_logits)])

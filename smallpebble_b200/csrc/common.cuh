@@ -62,6 +62,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// TF32 error compensation (tf32.cu): when set, the kernels that produce operands of the
+// BACKWARD contractions (pool / leaky_relu / softmax-xent gradients, the conv data gradient's
+// leaky epilogue) round what they store to the nearest TF32 value, so that the tensor core's
+// operand truncation becomes an unbiased rounding.  sp_set_tf32_output_rounding().
+extern int g_round_tf32_outputs;
+
 // grid sized in whole waves of the SM count (B200: 148 SMs)
 inline int wave_grid(int64_t work_items, int items_per_block, int blocks_per_sm) {
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
@@ -125,6 +131,18 @@ __device__ __forceinline__ void grid_barrier(unsigned int* words, unsigned int n
     __threadfence();
   }
   __syncthreads();
+}
+
+// nearest TF32 value (10 mantissa bits, ties away from zero), as an fp32 with 13 zero low bits
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float round_out(float x, int rnd) { return rnd ? rna_tf32(x) : x; }
+__device__ __forceinline__ float4 round_out4(float4 v, int rnd) {
+  if (rnd) v = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+  return v;
 }
 
 __device__ __forceinline__ float4 ld_stream_f4(const float* p) {

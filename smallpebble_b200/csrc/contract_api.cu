@@ -168,7 +168,8 @@ int sp_debug_tma2_trace(void* device_buffer) {
 int sp_gemm_bias(int64_t M, int64_t N, int64_t K, const float* A, const float* B,
                  const float* bias, float* C, int precision, sp_stream_t stream) {
   SP_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative extent");
-  SP_REQUIRE(precision == SP_PRECISION_FP32 || precision == SP_PRECISION_TF32, "bad precision");
+  SP_REQUIRE(precision == SP_PRECISION_FP32 || precision == SP_PRECISION_TF32 ||
+                 precision == SP_PRECISION_TF32X3, "bad precision");
   if (M == 0 || N == 0) return 0;
   if (K > 0) {
     sp::IgemmParams p = sp::base_params();
@@ -200,7 +201,8 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
             int64_t strideA, const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc,
             int64_t strideC, int64_t batch, int precision, sp_stream_t stream) {
   SP_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, "negative extent");
-  SP_REQUIRE(precision == SP_PRECISION_FP32 || precision == SP_PRECISION_TF32, "bad precision");
+  SP_REQUIRE(precision == SP_PRECISION_FP32 || precision == SP_PRECISION_TF32 ||
+                 precision == SP_PRECISION_TF32X3, "bad precision");
   if (M == 0 || N == 0 || batch == 0) return 0;
   if (K == 0) {
     // empty inner dimension: np.matmul yields zeros
@@ -271,6 +273,35 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
 static int conv2d_fprop_impl(const float* x, const float* w, float* y, const sp_conv_geom* g,
                              int precision, int leaky, float alpha, sp_stream_t stream) {
   if (int rc = sp::check_geom(g)) return rc;
+  SP_REQUIRE(precision >= SP_PRECISION_FP32 && precision <= SP_PRECISION_TF32_SPLIT, "bad precision");
+  if (precision == SP_PRECISION_TF32_SPLIT) {
+    // operands are (r, l) TF32 pairs interleaved per 32 channels, g->C counts both parts:
+    // the 2-SM TMA kernel walks them as one contraction axis and issues r.r + l.r + r.l
+    sp::IgemmParams p = sp::base_params();
+    p.g = *g;
+    p.M = (int64_t)g->N * g->OH * g->OW;
+    p.N = g->K;
+    p.K = (int64_t)g->KH * g->KW * g->C;
+    p.A = x;
+    p.B = w;
+    p.C = y;
+    p.ldc = g->K;
+    p.leaky = leaky;
+    p.leaky_alpha = alpha;
+    p.split3 = 1;
+    if (p.M == 0) return 0;
+    if (g->C % 64 != 0 || !sp::conv_tma2_supported(sp::kFprop, p))
+      return sp::set_error(SP_ERR_UNSUPPORTED,
+                           "conv2d_fprop: split operands need the 2-SM TMA kernel (C %% 64 == 0 "
+                           "after splitting, K %% 64 == 0); use sp_conv2d_x3_plan");
+    if (int rc = sp::launch_conv_tma2(sp::kFprop, p, sp::as_stream(stream))) return rc;
+    SP_CHECK_LAUNCH("conv2d_fprop(split)");
+    return 0;
+  }
+  if (precision == SP_PRECISION_TF32X3 && !(sp::g_umma_policy == 0 && sp::small_c_supported(*g)))
+    return sp::set_error(SP_ERR_UNSUPPORTED,
+                         "conv2d_fprop: native 3xTF32 only for the first-layer (C <= 4) kernels; "
+                         "use sp_conv2d_x3_plan and pre-split operands");
   sp::IgemmParams p = sp::base_params();
   p.g = *g;
   p.M = (int64_t)g->N * g->OH * g->OW;
@@ -372,6 +403,37 @@ int sp_conv2d_dgrad_leaky(const float* gy, const float* w, const float* act, flo
                           const sp_conv_geom* g, int precision, float alpha, sp_stream_t stream) {
   if (!act) return sp::set_error(SP_ERR_INVALID_ARGUMENT, "conv2d_dgrad_leaky: act is null");
   return conv2d_dgrad_impl(gy, w, dx, g, precision, act, alpha, stream);
+}
+
+// How the forward contraction of this geometry is error-compensated (3xTF32, tf32.cu):
+//   SP_X3_NATIVE  pass the raw operands with SP_PRECISION_TF32X3 (first-layer kernels split in
+//                 registers or compute in exact fp32)
+//   SP_X3_SPLIT2  pre-split both operands with sp_tf32_split(kind SP_SPLIT_RL, 32-channel
+//                 blocks), double geom.C, SP_PRECISION_TF32_SPLIT (the 2-SM TMA kernel)
+//   SP_X3_CONCAT3 pre-split with SP_SPLIT_RLR (images) / SP_SPLIT_RRL (kernels) over whole-C
+//                 blocks, triple geom.C, SP_PRECISION_TF32 (any kernel: plain K-concatenation)
+int sp_conv2d_x3_plan(const sp_conv_geom* g, int* plan) {
+  if (int rc = sp::check_geom(g)) return rc;
+  SP_REQUIRE(plan != nullptr, "null plan");
+  if (sp::g_umma_policy == 0 && sp::small_c_supported(*g)) {
+    *plan = SP_X3_NATIVE;
+    return 0;
+  }
+  *plan = SP_X3_CONCAT3;
+  if (g->C % 32 == 0 && sp::g_umma_policy != 2 && sp::g_tma2_policy != 2) {
+    sp::IgemmParams p = sp::base_params();
+    p.g = *g;
+    p.g.C = 2 * g->C;
+    p.M = (int64_t)g->N * g->OH * g->OW;
+    p.N = g->K;
+    p.K = (int64_t)g->KH * g->KW * p.g.C;
+    const double flop = 3.0 * (double)p.M * (double)p.N * (double)g->KH * g->KW * g->C;
+    // (operand pointers are unknown here; device allocations are 256-byte aligned)
+    if (sp::conv_tma2_supported(sp::kFprop, p) && (flop >= 2.5e8 || sp::g_tma2_policy == 1) &&
+        !(sp::g_umma_policy == 1 && sp::g_tma2_policy != 1))
+      *plan = SP_X3_SPLIT2;
+  }
+  return 0;
 }
 
 size_t sp_conv2d_wgrad_workspace(const sp_conv_geom* g, int precision) {

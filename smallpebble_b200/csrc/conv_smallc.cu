@@ -603,6 +603,17 @@ __device__ __forceinline__ void mma_tf32_m16n8k8(float (&d)[4], const uint32_t (
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+__device__ __forceinline__ uint32_t rna_bits(uint32_t fp32_bits) {
+  return __float_as_uint(rna_tf32(__uint_as_float(fp32_bits)));
+}
+// x = r + l with r the nearest TF32 value: the two operands of an error-compensated product
+__device__ __forceinline__ void split_bits(uint32_t x, uint32_t& r, uint32_t& l) {
+  const float xf = __uint_as_float(x);
+  const float rf = rna_tf32(xf);
+  r = __float_as_uint(rf);
+  l = __float_as_uint(xf - rf);
+}
+
 template <int KT>  // K = 16 * KT output channels
 __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rgb3x3_mma_kernel(
     const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partial,
@@ -688,20 +699,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rgb3x3_mma_kernel(
     for (int grp = warp; grp < n_groups; grp += kThreads / 32) {
       const int p0 = grp * 8;
       const uint32_t* ab = gy_u + (p0 + t) * GS + gq;
+      // operands rounded to the nearest TF32 in registers (the tensor core would truncate
+      // them: a coherent bias on the filter gradient, tf32.cu)
       uint32_t a[KT][4];
 #pragma unroll
       for (int m = 0; m < KT; ++m) {
-        a[m][0] = ab[m * 16];
-        a[m][1] = ab[m * 16 + 8];
-        a[m][2] = ab[4 * GS + m * 16];
-        a[m][3] = ab[4 * GS + m * 16 + 8];
+        a[m][0] = rna_bits(ab[m * 16]);
+        a[m][1] = rna_bits(ab[m * 16 + 8]);
+        a[m][2] = rna_bits(ab[4 * GS + m * 16]);
+        a[m][3] = rna_bits(ab[4 * GS + m * 16 + 8]);
       }
       const uint32_t* bb = x_u + 3 * (p0 + t);
       uint32_t b[4][2];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        b[j][0] = bb[off[j]];
-        b[j][1] = bb[off[j] + 12];
+        b[j][0] = rna_bits(bb[off[j]]);
+        b[j][1] = rna_bits(bb[off[j] + 12]);
       }
 #pragma unroll
       for (int m = 0; m < KT; ++m)
@@ -760,7 +773,11 @@ struct RgbFpropPlan {
   int x_floats;    // staged + zeroed slack (one stage)
 };
 
-template <int KT>
+// X3: error-compensated product (SP_PRECISION_TF32X3): both operands are split in registers,
+// acc += x_r.w_r + x_l.w_r + x_r.w_l -- fp32-grade results (the discrete routing downstream,
+// leaky_relu sign and maxpool argmax, must agree with the float64 reference: tf32.cu); the
+// layer is HBM-bound (27-deep reduction), so three MMAs per tile instead of one cost little.
+template <int KT, bool X3>
 __global__ void __launch_bounds__(kThreads, KT == 4 ? 1 : 2) conv_fprop_rgb3x3_mma_kernel(
     const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
     const __grid_constant__ sp_conv_geom g, const __grid_constant__ RgbFpropPlan pl,
@@ -793,6 +810,7 @@ __global__ void __launch_bounds__(kThreads, KT == 4 ? 1 : 2) conv_fprop_rgb3x3_m
 
   // B fragments: b0 = w[8 s + t][8 j + gq], b1 = w[8 s + t + 4][8 j + gq]; rows >= 27 are zero
   uint32_t bf[4][NJ][2];
+  uint32_t bl[4][X3 ? NJ : 1][2];  // low parts of the filter (X3 only)
   int offa[4][2];
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
@@ -801,8 +819,13 @@ __global__ void __launch_bounds__(kThreads, KT == 4 ? 1 : 2) conv_fprop_rgb3x3_m
       const int kk = 8 * s + t + 4 * h;
       offa[s][h] = kk < KC ? (kk / 9) * pl.wv * 3 + kk % 9 : 0;
 #pragma unroll
-      for (int j = 0; j < NJ; ++j)
-        bf[s][j][h] = kk < KC ? __float_as_uint(__ldg(w + kk * K + 8 * j + gq)) : 0u;
+      for (int j = 0; j < NJ; ++j) {
+        const uint32_t wv = kk < KC ? __float_as_uint(__ldg(w + kk * K + 8 * j + gq)) : 0u;
+        if (X3)
+          split_bits(wv, bf[s][j][h], bl[s][j][h]);
+        else
+          bf[s][j][h] = wv;
+      }
     }
   }
 
@@ -836,6 +859,17 @@ __global__ void __launch_bounds__(kThreads, KT == 4 ? 1 : 2) conv_fprop_rgb3x3_m
         a[1] = ab[offa[s][0] + 24];
         a[2] = ab[offa[s][1]];
         a[3] = ab[offa[s][1] + 24];
+        if (X3) {
+          uint32_t al[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_bits(a[i], a[i], al[i]);
+          // small terms first, then the leading product
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            mma_tf32_m16n8k8(acc[j], al, bf[s][j]);
+            mma_tf32_m16n8k8(acc[j], a, bl[s][j]);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) mma_tf32_m16n8k8(acc[j], a, bf[s][j]);
       }
@@ -1022,7 +1056,7 @@ static RgbFpropPlan rgb_fprop_plan(const sp_conv_geom& g, int slots) {
   return pl;
 }
 
-template <int KT>
+template <int KT, bool X3>
 static int launch_rgb_fprop_mma(const float* x, const float* w, float* y, const sp_conv_geom& g,
                                 cudaStream_t st, int leaky, float alpha) {
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
@@ -1032,12 +1066,12 @@ static int launch_rgb_fprop_mma(const float* x, const float* w, float* y, const 
   const size_t smem = (size_t)2 * pl.x_floats * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(conv_fprop_rgb3x3_mma_kernel<KT>,
+    cudaFuncSetAttribute(conv_fprop_rgb3x3_mma_kernel<KT, X3>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_done = true;
   }
   const int blocks = std::min(per_sm * sms, pl.n_tiles);
-  sp::launch_pdl(conv_fprop_rgb3x3_mma_kernel<KT>, dim3(blocks), dim3(kThreads), smem, st, x, w, y,
+  sp::launch_pdl(conv_fprop_rgb3x3_mma_kernel<KT, X3>, dim3(blocks), dim3(kThreads), smem, st, x, w, y,
                  g, pl, leaky, alpha);
   return 0;
 }
@@ -1060,9 +1094,18 @@ int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_
   if (fused_leaky) *fused_leaky = false;
   if (precision == SP_PRECISION_TF32 && (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
     // tensor-core kernel when the geometry qualifies (returns 1 when it does not)
-    const int rc = g.K == 16   ? launch_rgb_fprop_mma<1>(x, w, y, g, st, leaky, alpha)
-                   : g.K == 32 ? launch_rgb_fprop_mma<2>(x, w, y, g, st, leaky, alpha)
-                   : g.K == 64 ? launch_rgb_fprop_mma<4>(x, w, y, g, st, leaky, alpha)
+    const int rc = g.K == 16   ? launch_rgb_fprop_mma<1, false>(x, w, y, g, st, leaky, alpha)
+                   : g.K == 32 ? launch_rgb_fprop_mma<2, false>(x, w, y, g, st, leaky, alpha)
+                   : g.K == 64 ? launch_rgb_fprop_mma<4, false>(x, w, y, g, st, leaky, alpha)
+                               : 1;
+    if (rc == 0 && fused_leaky) *fused_leaky = leaky != 0;
+    if (rc <= 0) return rc;
+  } else if (precision == SP_PRECISION_TF32X3 && (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
+    // error-compensated tensor-core kernel; geometries it does not take fall through to the
+    // exact-fp32 CUDA-core kernels below, which meet the same accuracy
+    const int rc = g.K == 16   ? launch_rgb_fprop_mma<1, true>(x, w, y, g, st, leaky, alpha)
+                   : g.K == 32 ? launch_rgb_fprop_mma<2, true>(x, w, y, g, st, leaky, alpha)
+                   : g.K == 64 ? launch_rgb_fprop_mma<4, true>(x, w, y, g, st, leaky, alpha)
                                : 1;
     if (rc == 0 && fused_leaky) *fused_leaky = leaky != 0;
     if (rc <= 0) return rc;

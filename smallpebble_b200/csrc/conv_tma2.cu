@@ -71,6 +71,10 @@ struct Tma2Params {
   int leaky;           // fprop epilogue: out = v > 0 ? v : alpha * v
   float alpha;
   const float* act;    // dgrad epilogue: out = v * (act > 0 ? 1 : alpha), act laid out like C
+  int round_out;       // with `act`: round the stored gradient to the nearest TF32 (common.cuh)
+  int split3;          // fprop, SP_PRECISION_TF32_SPLIT: operands are (r, l) pairs interleaved per
+                       // 32 channels; a stage holds A = (x_r | x_l), B = (w_r | w_l) of ONE
+                       // (tap, channel block) and takes 12 MMAs: r.r + l.r + r.l  (3xTF32)
   float* C;
   int64_t ldc;
   int64_t split_stride;
@@ -327,7 +331,7 @@ __device__ __forceinline__ void load_act_rows(float4 (&a)[8], float* const (&rp)
 __device__ __forceinline__ void store_block_rows(uint8_t* tile, const uint32_t (&v)[32], int lane,
                                                  float* const (&rp)[8], uint32_t ok_mask, int cb,
                                                  bool use_act, const float4 (&act)[8],
-                                                 float alpha) {
+                                                 float alpha, int rnd = 0) {
   float4* t4 = reinterpret_cast<float4*>(tile);
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -345,6 +349,7 @@ __device__ __forceinline__ void store_block_rows(uint8_t* tile, const uint32_t (
       val.y *= act[r].y > 0.f ? 1.f : alpha;
       val.z *= act[r].z > 0.f ? 1.f : alpha;
       val.w *= act[r].w > 0.f ? 1.f : alpha;
+      val = round_out4(val, rnd);
     }
     if ((ok_mask >> r) & 1u) *reinterpret_cast<float4*>(rp[r] + cb + chunk * 4) = val;
   }
@@ -628,7 +633,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               umma_tf32_2sm(tmem_d, desc_join(a_lo + (uint32_t)k * a_step, a_hi),
                             desc_join(b_lo + (uint32_t)k * b_step, b_hi), idesc,
                             (st > 0 || k > 0) ? 1u : 0u);
-            if (valid1) {
+            if (MODE == kFprop && p.split3) {
+              // halves are (r, l) of the same 32 channels: r.r was issued above, now l.r + r.l
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_tf32_2sm(tmem_d, desc_join(a_lo + a_half + (uint32_t)k * a_step, a_hi),
+                              desc_join(b_lo + (uint32_t)k * b_step, b_hi), idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_tf32_2sm(tmem_d, desc_join(a_lo + (uint32_t)k * a_step, a_hi),
+                              desc_join(b_lo + b_half + (uint32_t)k * b_step, b_hi), idesc, 1u);
+            } else if (valid1) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_tf32_2sm(tmem_d, desc_join(a_lo + a_half + (uint32_t)k * a_step, a_hi),
@@ -689,14 +704,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         tmem_ld_wait();
         if (MODE == kFprop && p.leaky) leaky_block(v, p.alpha);
         if (vec_store) {
-          store_block_rows(epi_tile, v, lane, rp, ok_mask, cb, use_act, act_cur, p.alpha);
+          store_block_rows(epi_tile, v, lane, rp, ok_mask, cb, use_act, act_cur, p.alpha,
+                           p.round_out);
 #pragma unroll
           for (int r = 0; r < 8; ++r) act_cur[r] = act_next[r];
         } else if (m < p.M) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float f = __uint_as_float(v[j]);
-            if (ACT && p.act) f *= p.act[(crow - p.C) + cb + j] > 0.f ? 1.f : p.alpha;
+            if (ACT && p.act)
+              f = round_out(f * (p.act[(crow - p.C) + cb + j] > 0.f ? 1.f : p.alpha), p.round_out);
             crow[cb + j] = f;
           }
         }
@@ -757,6 +774,7 @@ struct HaloParams {
   int leaky;           // fprop epilogue: out = v > 0 ? v : alpha * v
   float alpha;
   const float* act;    // dgrad epilogue: out = v * (act > 0 ? 1 : alpha), act laid out like C
+  int round_out;       // with `act`: round the stored gradient to the nearest TF32 (common.cuh)
   float* C;
   int64_t ldc;
 };
@@ -785,7 +803,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     if (on) p.trace[slot] = clock64();
   };
   pdl_trigger();
-  stamp(tr && warp == 0, 0);
 
   const uint32_t strips = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_ring = strips + 2u * p.strip_bytes;
@@ -820,6 +837,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = uniform(tmem_slot);
+  // launched with launch_pdl(): the producer of our inputs may still be running -- nothing
+  // may touch global memory (TMA loads included) before the prerequisite grid has completed
+  pdl_wait();
 
   stamp(tr && warp == 0, 1);
   // rows this CTA's strip needs for the pair tile that starts at pixel q0
@@ -1052,14 +1072,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         tmem_ld_wait();
         if (MODE == kFprop && p.leaky) leaky_block(v, p.alpha);
         if (vec_store) {
-          store_block_rows(epi_tile, v, lane, rp, ok_mask, cb, use_act, act_cur, p.alpha);
+          store_block_rows(epi_tile, v, lane, rp, ok_mask, cb, use_act, act_cur, p.alpha,
+                           p.round_out);
 #pragma unroll
           for (int r = 0; r < 8; ++r) act_cur[r] = act_next[r];
         } else if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float f = __uint_as_float(v[j]);
-            if (ACT && p.act) f *= p.act[(crow - p.C) + cb + j] > 0.f ? 1.f : p.alpha;
+            if (ACT && p.act)
+              f = round_out(f * (p.act[(crow - p.C) + cb + j] > 0.f ? 1.f : p.alpha), p.round_out);
             crow[cb + j] = f;
           }
         }
@@ -1306,6 +1328,8 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
   p.leaky = (mode == kFprop) ? ip.leaky : 0;
   p.alpha = ip.leaky_alpha;
   p.act = (mode == kDgrad) ? ip.act : nullptr;
+  p.round_out = g_round_tf32_outputs;
+  p.split3 = (mode == kFprop) ? ip.split3 : 0;
   const int up_h = (g.OH - 1) * g.sy + 1 - g.H - g.pad_t, up_w = (g.OW - 1) * g.sx + 1 - g.W - g.pad_l;
   if (mode == kFprop) {
     p.cblocks = g.C / 32;
@@ -1489,6 +1513,7 @@ int launch_conv_halo2(int mode, const IgemmParams& ip, cudaStream_t st) {
   p.leaky = (mode == kFprop) ? ip.leaky : 0;
   p.alpha = ip.leaky_alpha;
   p.act = (mode == kDgrad) ? ip.act : nullptr;
+  p.round_out = g_round_tf32_outputs;
   const int bnh_max = (p.N >= 256 ? 256 : p.N) / 2;
   alignas(64) CUtensorMap tmA, tmB;
   bool ok = true;

@@ -274,10 +274,12 @@ __global__ void __launch_bounds__(kThreads) leaky_fwd_kernel(const float* __rest
   }
 }
 
+// `rnd`: round the stored gradient to the nearest TF32 value -- it is an operand of the
+// backward contractions (common.cuh: g_round_tf32_outputs)
 __global__ void __launch_bounds__(kThreads) leaky_bwd_kernel(const float* __restrict__ g,
                                                              const float* __restrict__ x,
                                                              float* __restrict__ dx, int64_t n,
-                                                             float alpha, bool vec) {
+                                                             float alpha, bool vec, int rnd) {
   pdl_entry();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -291,11 +293,12 @@ __global__ void __launch_bounds__(kThreads) leaky_bwd_kernel(const float* __rest
       r.y *= (v.y > 0.f) ? 1.f : alpha;
       r.z *= (v.z > 0.f) ? 1.f : alpha;
       r.w *= (v.w > 0.f) ? 1.f : alpha;
-      reinterpret_cast<float4*>(dx)[i] = r;
+      reinterpret_cast<float4*>(dx)[i] = round_out4(r, rnd);
     }
     done = n4 << 2;
   }
-  for (int64_t i = done + tid; i < n; i += stride) dx[i] = g[i] * ((x[i] > 0.f) ? 1.f : alpha);
+  for (int64_t i = done + tid; i < n; i += stride)
+    dx[i] = round_out(g[i] * ((x[i] > 0.f) ? 1.f : alpha), rnd);
 }
 
 // In-place variants for the conv kernels without a fused epilogue (contract_api.cu): ordinary
@@ -312,11 +315,12 @@ __global__ void __launch_bounds__(kThreads) leaky_fwd_inplace_kernel(float* y, i
 }
 __global__ void __launch_bounds__(kThreads) leaky_bwd_inplace_kernel(float* dx,
                                                                      const float* __restrict__ x,
-                                                                     int64_t n, float alpha) {
+                                                                     int64_t n, float alpha,
+                                                                     int rnd) {
   pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
-    dx[i] = dx[i] * ((x[i] > 0.f) ? 1.f : alpha);
+    dx[i] = round_out(dx[i] * ((x[i] > 0.f) ? 1.f : alpha), rnd);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -363,7 +367,8 @@ int launch_leaky_fwd_inplace(float* y, int64_t n, float alpha, cudaStream_t st) 
 }
 int launch_leaky_bwd_inplace(float* dx, const float* x, int64_t n, float alpha, cudaStream_t st) {
   if (n <= 0) return 0;
-  launch_pdl(leaky_bwd_inplace_kernel, dim3(ew_grid(n)), dim3(kThreads), 0, st, dx, x, n, alpha);
+  launch_pdl(leaky_bwd_inplace_kernel, dim3(ew_grid(n)), dim3(kThreads), 0, st, dx, x, n, alpha,
+             g_round_tf32_outputs);
   return 0;
 }
 }  // namespace sp
@@ -431,7 +436,7 @@ int sp_leaky_relu_fwd(const float* x, float* y, int64_t n, float alpha, sp_strea
 int sp_leaky_relu_bwd(const float* g, const float* x, float* dx, int64_t n, float alpha,
                       sp_stream_t stream) {
   if (n <= 0) return 0;
-  sp::launch_pdl(leaky_bwd_kernel, dim3(ew_grid(n)), dim3(kThreads), 0, sp::as_stream(stream), g, x, dx, n, alpha, aligned16(g) && aligned16(x) && aligned16(dx));
+  sp::launch_pdl(leaky_bwd_kernel, dim3(ew_grid(n)), dim3(kThreads), 0, sp::as_stream(stream), g, x, dx, n, alpha, aligned16(g) && aligned16(x) && aligned16(dx), sp::g_round_tf32_outputs);
   SP_CHECK_LAUNCH("leaky_relu_bwd");
   return 0;
 }

@@ -36,6 +36,9 @@ struct IgemmParams {
   // 1 : leaky_alpha) with `act` laid out like the output -- the gradient of leaky_relu applied
   // to the data gradient as it is stored
   const float* act;
+  // conv fprop with SP_PRECISION_TF32_SPLIT: operands are (r, l) TF32 split pairs interleaved
+  // per 32 channels and g.C counts both parts (tf32.cu); only the 2-SM TMA kernel takes it
+  int split3;
   // dense operand strides (kGemm)
   int64_t a_rs, a_cs, b_rs, b_cs;
   // strided batch (kGemm): blockIdx.z selects the batch

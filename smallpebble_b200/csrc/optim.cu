@@ -15,7 +15,8 @@ constexpr int kChunkSmall = kThreads * 4;  // small models: one 128-bit access p
 constexpr int kMaxTensors = 24;
 
 struct AdamArgs {
-  float* p[kMaxTensors];
+  const float* p[kMaxTensors];
+  float* po[kMaxTensors];      // updated parameters: == p (in place) or a fresh buffer
   const float* g[kMaxTensors];
   float* m[kMaxTensors];
   float* v[kMaxTensors];
@@ -67,15 +68,17 @@ __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_const
   const float ic2 = 1.f / -expm1f(step * lnb2);
   const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * a.chunk;
   const int64_t n = a.n[t];
-  float* __restrict__ p = a.p[t];
+  const float* p = a.p[t];  // (may alias po: no __restrict__)
+  float* po = a.po[t];
   const float* __restrict__ g = a.g[t];
   float* __restrict__ m = a.m[t];
   float* __restrict__ v = a.v[t];
-  const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  const bool vec =
+      (((uintptr_t)p | (uintptr_t)po | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
   const int64_t end = min(n, base + a.chunk);
   if (vec) {
     for (int64_t i = base + 4 * threadIdx.x; i + 3 < end; i += 4 * kThreads) {
-      float4 pp = *reinterpret_cast<float4*>(p + i);
+      float4 pp = *reinterpret_cast<const float4*>(p + i);
       const float4 gg = ld_stream_f4(g + i);
       float4 mm = *reinterpret_cast<float4*>(m + i);
       float4 vv = *reinterpret_cast<float4*>(v + i);
@@ -83,17 +86,23 @@ __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_const
       adam1(pp.y, gg.y, mm.y, vv.y, b1, b2, ic1, ic2, alpha, eps);
       adam1(pp.z, gg.z, mm.z, vv.z, b1, b2, ic1, ic2, alpha, eps);
       adam1(pp.w, gg.w, mm.w, vv.w, b1, b2, ic1, ic2, alpha, eps);
-      *reinterpret_cast<float4*>(p + i) = pp;
+      *reinterpret_cast<float4*>(po + i) = pp;
       *reinterpret_cast<float4*>(m + i) = mm;
       *reinterpret_cast<float4*>(v + i) = vv;
     }
     // tail of a tensor whose length is not a multiple of 4 (only the last chunk has one)
     const int64_t tail = end - ((end - base) & 3);
-    for (int64_t i = tail + threadIdx.x; i < end; i += kThreads)
-      adam1(p[i], g[i], m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
+    for (int64_t i = tail + threadIdx.x; i < end; i += kThreads) {
+      float pv = p[i];
+      adam1(pv, g[i], m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
+      po[i] = pv;
+    }
   } else {
-    for (int64_t i = base + threadIdx.x; i < end; i += kThreads)
-      adam1(p[i], g[i], m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
+    for (int64_t i = base + threadIdx.x; i < end; i += kThreads) {
+      float pv = p[i];
+      adam1(pv, g[i], m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
+      po[i] = pv;
+    }
   }
   // all threads of this block have read the step count (it feeds ic1/ic2 used above)
   __syncthreads();
@@ -153,6 +162,14 @@ int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_
                   float* const* host_m, float* const* host_v, const int64_t* host_numel,
                   int32_t* const* host_step, float alpha, float beta1, float beta2, float eps,
                   sp_stream_t stream) {
+  return sp_adam_multi_out(n_tensors, host_p, host_p, host_g, host_m, host_v, host_numel,
+                           host_step, alpha, beta1, beta2, eps, stream);
+}
+
+int sp_adam_multi_out(int n_tensors, float* const* host_p, float* const* host_p_out,
+                      const float* const* host_g, float* const* host_m, float* const* host_v,
+                      const int64_t* host_numel, int32_t* const* host_step, float alpha,
+                      float beta1, float beta2, float eps, sp_stream_t stream) {
   SP_REQUIRE(n_tensors >= 0, "negative tensor count");
   cudaStream_t st = sp::as_stream(stream);
   unsigned int* counters = adam_counters();
@@ -172,6 +189,7 @@ int sp_adam_multi(int n_tensors, float* const* host_p, const float* const* host_
       SP_REQUIRE(host_step[i] != nullptr, "missing device step counter");
       const int k = a.count++;
       a.p[k] = host_p[i];
+      a.po[k] = host_p_out[i];
       a.g[k] = host_g[i];
       a.m[k] = host_m[i];
       a.v[k] = host_v[i];

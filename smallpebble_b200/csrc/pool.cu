@@ -18,6 +18,9 @@ struct PoolGeom {
   // ever storing it, backward multiplies by leaky's slope at x.  leaky == 0: plain max-pool.
   int leaky;
   float alpha;
+  // backward only: round the stored gradient to the nearest TF32 value (it is an operand of
+  // the conv filter / data gradient contractions; sp_set_tf32_output_rounding)
+  int rnd;
 };
 
 __device__ __forceinline__ float lrelu(float v, float alpha) { return v > 0.f ? v : alpha * v; }
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_tile_vec4(const float* _
               out.z *= slope(xv.z, g.alpha);
               out.w *= slope(xv.w, g.alpha);
             }
-            *reinterpret_cast<float4*>(dimg + off) = out;
+            *reinterpret_cast<float4*>(dimg + off) = round_out4(out, g.rnd);
           }
         }
       }
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_vec4(const float* __rest
         acc.z *= slope(xv.z, g.alpha);
         acc.w *= slope(xv.w, g.alpha);
       }
-      reinterpret_cast<float4*>(dx)[(int64_t)row * row_len + e] = acc;
+      reinterpret_cast<float4*>(dx)[(int64_t)row * row_len + e] = round_out4(acc, g.rnd);
     }
   }
 }
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_scalar(const float* __re
       }
     }
     if (g.leaky) acc *= slope(xl[t], g.alpha);
-    dx[t] = acc;
+    dx[t] = round_out(acc, g.rnd);
   }
 }
 
@@ -355,7 +358,7 @@ extern "C" {
 static int maxpool2d_fwd_impl(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C,
                               int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
                               int leaky, float alpha, sp_stream_t stream) {
-  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, leaky, alpha};
+  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, leaky, alpha, 0};
   if (int rc = check(g)) return rc;
   const int64_t outs = (int64_t)N * OH * OW * C;
   if (outs == 0) return 0;
@@ -392,7 +395,8 @@ static int maxpool2d_bwd_impl(const float* gy, const uint8_t* idx, float* dx, co
                               int N, int H, int W, int C, int KH, int KW, int sy, int sx,
                               int pad_t, int pad_l, int OH, int OW, int leaky, float alpha,
                               sp_stream_t stream) {
-  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, leaky, alpha};
+  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, leaky, alpha,
+                   sp::g_round_tf32_outputs};
   if (int rc = check(g)) return rc;
   const int64_t ins = (int64_t)N * H * W * C;
   if (ins == 0) return 0;

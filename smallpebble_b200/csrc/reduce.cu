@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(kThreads) softmax_rows_kernel(const float* __r
 __global__ void __launch_bounds__(kThreads) softmax_rows_bwd_kernel(const float* __restrict__ y,
                                                                     const float* __restrict__ g,
                                                                     float* __restrict__ dx,
-                                                                    int64_t rows, int64_t n) {
+                                                                    int64_t rows, int64_t n,
+                                                                    int rnd) {
   pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
@@ -212,7 +213,9 @@ __global__ void __launch_bounds__(kThreads) softmax_rows_bwd_kernel(const float*
     float dot = 0.f;
     for (int64_t j = lane; j < n; j += 32) dot += py[j] * pg[j];
     dot = warp_sum(dot);
-    for (int64_t j = lane; j < n; j += 32) dx[row * n + j] = py[j] * (pg[j] - dot);
+    // (rnd: the logits' gradient feeds the classifier's backward contractions, common.cuh)
+    for (int64_t j = lane; j < n; j += 32)
+      dx[row * n + j] = round_out(py[j] * (pg[j] - dot), rnd);
   }
 }
 
@@ -342,7 +345,8 @@ __global__ void __launch_bounds__(1024) softmax_xent_fwd_kernel(
 
 __global__ void __launch_bounds__(kThreads) softmax_xent_bwd_kernel(
     const float* __restrict__ probs, const int32_t* __restrict__ labels,
-    const float* __restrict__ gloss, float* __restrict__ dlogits, int64_t rows, int64_t cols) {
+    const float* __restrict__ gloss, float* __restrict__ dlogits, int64_t rows, int64_t cols,
+    int rnd) {
   pdl_entry();
   const float g = gloss[0];
   const int64_t total = rows * cols;
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(kThreads) softmax_xent_bwd_kernel(
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols;
     const int64_t c = i - r * cols;
-    dlogits[i] = g * (probs[i] - ((c == labels[r]) ? 1.f : 0.f));
+    dlogits[i] = round_out(g * (probs[i] - ((c == labels[r]) ? 1.f : 0.f)), rnd);
   }
 }
 
@@ -362,20 +366,21 @@ __global__ void __launch_bounds__(kThreads) softmax_xent_bwd_kernel(
 __global__ void __launch_bounds__(1024) softmax_xent_bwd_colsum_kernel(
     const float* __restrict__ probs, const int32_t* __restrict__ labels,
     const float* __restrict__ gloss, float* __restrict__ dlogits, float* __restrict__ colsum,
-    int rows, int cols) {
+    int rows, int cols, int rnd) {
   pdl_entry();
   const float g = gloss[0];
   const int total = rows * cols;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int r = i / cols;
     const int c = i - r * cols;
-    dlogits[i] = g * (probs[i] - ((c == labels[r]) ? 1.f : 0.f));
+    dlogits[i] = round_out(g * (probs[i] - ((c == labels[r]) ? 1.f : 0.f)), rnd);
   }
-  __syncthreads();  // block-scope visibility of the global writes above
+  // the column sums (a parameter gradient, not a contraction operand) use the unrounded values
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   for (int c = warp; c < cols; c += warps) {
     float acc = 0.f;
-    for (int r = lane; r < rows; r += 32) acc += dlogits[r * cols + c];
+    for (int r = lane; r < rows; r += 32)
+      acc += g * (probs[r * cols + c] - ((c == labels[r]) ? 1.f : 0.f));
     acc = warp_sum(acc);
     if (lane == 0) colsum[c] = acc;
   }
@@ -525,7 +530,7 @@ int sp_softmax_bwd(const float* y, const float* g, float* dx, int64_t outer, int
   if (outer * n * inner <= 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
   if (inner == 1)
-    sp::launch_pdl(softmax_rows_bwd_kernel, dim3(sp::wave_grid(outer, kThreads / 32, 8)), dim3(kThreads), 0, st, y, g, dx, outer, n);
+    sp::launch_pdl(softmax_rows_bwd_kernel, dim3(sp::wave_grid(outer, kThreads / 32, 8)), dim3(kThreads), 0, st, y, g, dx, outer, n, sp::g_round_tf32_outputs);
   else
     softmax_strided_bwd_kernel<<<sp::wave_grid(outer * inner, kThreads, 8), kThreads, 0, st>>>(
         y, g, dx, outer, n, inner);
@@ -582,7 +587,7 @@ int sp_softmax_xent_fwd(const float* logits, const int32_t* labels, float* probs
 int sp_softmax_xent_bwd(const float* probs, const int32_t* labels, const float* gloss,
                         float* dlogits, int64_t rows, int64_t cols, sp_stream_t stream) {
   if (rows * cols <= 0) return 0;
-  sp::launch_pdl(softmax_xent_bwd_kernel, dim3(sp::wave_grid(rows * cols, kThreads, 8)), dim3(kThreads), 0, sp::as_stream(stream), probs, labels, gloss, dlogits, rows, cols);
+  sp::launch_pdl(softmax_xent_bwd_kernel, dim3(sp::wave_grid(rows * cols, kThreads, 8)), dim3(kThreads), 0, sp::as_stream(stream), probs, labels, gloss, dlogits, rows, cols, sp::g_round_tf32_outputs);
   SP_CHECK_LAUNCH("softmax_xent_bwd");
   return 0;
 }
@@ -595,7 +600,7 @@ int sp_softmax_xent_bwd_colsum(const float* probs, const int32_t* labels, const 
   if (rows * cols <= 32768) {
     sp::launch_pdl(softmax_xent_bwd_colsum_kernel, dim3(1), dim3(rows * cols > 4096 ? 1024 : 256),
                    0, sp::as_stream(stream), probs, labels, gloss, dlogits, colsum, (int)rows,
-                   (int)cols);
+                   (int)cols, sp::g_round_tf32_outputs);
     SP_CHECK_LAUNCH("softmax_xent_bwd_colsum");
     return 0;
   }

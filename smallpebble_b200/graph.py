@@ -135,12 +135,40 @@ class _StepCounts:
         return len(self._counters)
 
 
+_table_cache = {}  # tuple of device pointers -> ctypes pointer table (buffers are recycled:
+                   # a training loop cycles through a handful of distinct tuples)
+
+
+def _cached_table(ptrs):
+    tab = _table_cache.get(ptrs)
+    if tab is None:
+        if len(_table_cache) > 256:
+            _table_cache.clear()
+        tab = _table_cache[ptrs] = _ptr_table(ptrs)
+    return tab
+
+
+def _settle_before_inplace_update(gradients) -> None:
+    """Parameters are about to be overwritten IN PLACE: everything that was deferred and would
+    read them later must run now, or it would see the updated values (the reference evaluates
+    every gradient inside get_gradients, sp.py:77-87)."""
+    materialise = getattr(gradients, "_materialise", None)
+    if materialise is not None:
+        materialise()
+    A.flush_pending_parameter_readers()
+
+
 class Adam:
     """Adam optimization for SmallPebble variables (sp.py:552-583; Kingma & Ba, Algorithm 1).
 
     Per-variable step count / first / second moment, as in the reference.  One fused kernel
-    updates every variable in place (the reference rebinds `variable.array` to a new array;
-    the `Variable` objects -- what callers hold -- are the same either way)."""
+    updates every variable.  Like the reference (sp.py:583) the update is written to a NEW
+    array that `variable.array` is rebound to: whatever still holds the old array -- a
+    gradient closure that has not been evaluated yet (`Gradients` defers the gradient of
+    non-learnable leaves until somebody reads it), a deferred forward op -- keeps seeing the
+    weights the step was computed with.  Only while a CUDA graph is being recorded
+    (`sp.capture`), where buffers must be static, the update is in place (pending work that
+    reads the parameters is settled first)."""
 
     def __init__(self, alpha: float = 0.001, beta1: float = 0.9, beta2: float = 0.999,
                  eps: float = 1e-8) -> None:
@@ -152,9 +180,7 @@ class Adam:
         self.v = {}
         self._step = {}  # Variable -> device int32[1]: completed steps (read by the kernel)
         self.t = _StepCounts(self._step)
-        self._tables = {}  # ids of the parameter arrays -> cached ctypes pointer tables
-        self._g_ptrs, self._g_tab = None, None  # last step's gradient pointers and their table
-        self._static = None  # (variable ids, rebind epoch, pointer tables, variables kept alive)
+        self._static = None  # (variable ids, moment / step-count / size tables, variables)
 
     def training_step(self, variables, gradients) -> None:
         variables = list(variables)
@@ -169,39 +195,51 @@ class Adam:
         if _distributed.is_initialized() and _distributed.world_size() > 1:
             grads = _distributed.allreduce_gradients(grads, variables)
         n = len(variables)
-        # Everything below that does not change from step to step -- state creation, the
-        # pointer tables of parameters / moments / step counters -- is keyed by the identity of
-        # the variables and stays valid until some `variable.array` is rebound (core counts
-        # those); the fused kernel updates the parameters in place.
+        # state creation and the pointer tables of moments / step counters are keyed by the
+        # identity of the variables: they never change once made
         ids = tuple([id(v) for v in variables])
         cached = self._static
-        if cached is None or cached[0] != ids or cached[1] != core._rebind_epoch:
+        if cached is None or cached[0] != ids:
             for v in variables:
                 if v not in self._step:
                     self.m[v] = DeviceArray.zeros(v.array.shape)
                     self.v[v] = DeviceArray.zeros(v.array.shape)
                     self._step[v] = DeviceArray.from_host(np.zeros(1, np.int32), dtype=np.int32)
-            key = tuple((id(v), v.array.ptr) for v in variables)
-            static = self._tables.get(key)
-            if static is None:
-                static = self._tables[key] = (
-                    _ptr_table([v.array.ptr for v in variables]),
-                    _ptr_table([self.m[v].ptr for v in variables]),
-                    _ptr_table([self.v[v].ptr for v in variables]),
-                    _abi.dims([v.array.size for v in variables]),
-                    _ptr_table([self._step[v].ptr for v in variables]),
-                )
-            # the epoch is read after the lazy uploads above (`.ptr` may rebind nothing, but
-            # Variable construction elsewhere does not count either)
-            cached = self._static = (ids, core._rebind_epoch, static, tuple(variables))
-        p_tab, m_tab, v_tab, numel, step_tab = cached[2]
-        # gradient buffers come out of the recycling pool in the same order every step: the
-        # pointer table of the previous step is usually still right
-        g_ptrs = tuple([g.ptr for g in grads])
-        if g_ptrs != self._g_ptrs:
-            self._g_ptrs, self._g_tab = g_ptrs, _ptr_table(g_ptrs)
-        F.sp_adam_multi(n, p_tab, self._g_tab, m_tab, v_tab, numel, step_tab, self.alpha,
-                        self.beta1, self.beta2, self.eps, A.stream())
+            cached = self._static = (
+                ids,
+                _ptr_table([self.m[v].ptr for v in variables]),
+                _ptr_table([self.v[v].ptr for v in variables]),
+                _abi.dims([v.array.size for v in variables]),
+                _ptr_table([self._step[v].ptr for v in variables]),
+                tuple(variables),
+            )
+        _, m_tab, v_tab, numel, step_tab, _ = cached
+        olds = [v._array for v in variables]
+        p_tab = _cached_table(tuple([a.ptr for a in olds]))
+        g_tab = _cached_table(tuple([g.ptr for g in grads]))
+        if A.capturing():
+            # static buffers: update in place.  (Nothing is settled first: every buffer of a
+            # captured step is overwritten by the next replay anyway, so values that were not
+            # evaluated inside the captured function cannot be read afterwards -- capture.py.)
+            F.sp_adam_multi_out(n, p_tab, p_tab, g_tab, m_tab, v_tab, numel, step_tab, self.alpha,
+                                self.beta1, self.beta2, self.eps, A.stream())
+            A.note_inplace_update()
+            return
+        news = [DeviceArray.empty(a.shape, A.FLOAT, a.size) for a in olds]
+        o_tab = _cached_table(tuple([a._ptr for a in news]))
+        F.sp_adam_multi_out(n, p_tab, o_tab, g_tab, m_tab, v_tab, numel, step_tab, self.alpha,
+                            self.beta1, self.beta2, self.eps, A.stream())
+        # rebind (sp.py:583) and give the new arrays the TF32 shadows the contractions asked of
+        # the old ones (rounded copy for the data gradients, split copy for the compensated
+        # forward pass): all tensors in one launch instead of one per weight and use
+        jobs = []
+        for v, old, new in zip(variables, olds, news):
+            v._array = new
+            want_round, kinds = A.tf32_shadow_requests(old)
+            if want_round or kinds:
+                jobs.append((new, want_round, kinds))
+        if jobs:
+            A.tf32_shadows_multi(jobs)
 
 
 def sgd_step(variables, gradients, learning_rate: float = 0.001) -> None:
@@ -214,6 +252,8 @@ def sgd_step(variables, gradients, learning_rate: float = 0.001) -> None:
     grads = [_device_gradient(v, gradients) for v in variables]
     if distributed.is_initialized() and distributed.world_size() > 1:
         grads = distributed.allreduce_gradients(grads, variables)
+    # in place, like the reference: settle deferred work that reads the parameters first
+    _settle_before_inplace_update(gradients)
     F.sp_sgd_multi(
         len(variables),
         _ptr_table([v.array.ptr for v in variables]),
@@ -221,6 +261,7 @@ def sgd_step(variables, gradients, learning_rate: float = 0.001) -> None:
         _abi.dims([v.array.size for v in variables]),
         learning_rate, A.stream(),
     )
+    A.note_inplace_update()
 
 
 # ---------------- NEURAL NETWORK HELPERS (sp.py:586-642)

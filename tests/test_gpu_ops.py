@@ -8,7 +8,7 @@ import pytest
 
 import cases as C
 import smallpebble_b200 as sp
-from conftest import RTOL, assert_close
+from conftest import FWD_RTOL, RTOL, assert_close
 from oracle import numpy_path as orc
 from smallpebble_b200 import _abi, core
 
@@ -38,16 +38,19 @@ def umma_policy(request):
 def test_conv2d(case, precision, umma_policy, golden):
     if precision == "fp32" and umma_policy not in (0, 2):
         pytest.skip("tcgen05 kernels are only selected in TF32 mode")
+    if precision == "tf32" and umma_policy == 32 + 128:
+        pytest.skip("the halo kernel has no split-operand mode: compensated forward passes "
+                    "take the im2col 2-SM kernel (force_tma2 covers it)")
     name, xs, ws, strides, pad = case
     x, w, gy = C.conv_inputs(case)
     tol = RTOL[precision]
     y, (dx, dw) = grads_of(lambda a, b: sp.conv2d(a, b, pad, strides), [x, w], gy)
     y0, dx0, dw0 = orc.conv2d_grads(x, w, gy, pad, strides)
     assert y.shape == y0.shape
-    assert_close(y.array, y0, tol, "y vs oracle")
+    assert_close(y.array, y0, FWD_RTOL[precision], "y vs oracle")
     assert_close(dx, dx0, tol, "dX vs oracle")
     assert_close(dw, dw0, tol, "dW vs oracle")
-    assert_close(y.array, golden[f"conv/{name}/y"], tol, "y vs golden")
+    assert_close(y.array, golden[f"conv/{name}/y"], FWD_RTOL[precision], "y vs golden")
     assert_close(dx, golden[f"conv/{name}/dx"], tol, "dX vs golden")
     assert_close(dw, golden[f"conv/{name}/dw"], tol, "dW vs golden")
 
@@ -96,10 +99,10 @@ def test_matmul(case, precision, umma_policy, golden):
     tol = RTOL[precision]
     y, (da, db) = grads_of(sp.matmul, [a, b], gy)
     y0, da0, db0 = orc.matmul_grads(a, b, gy)
-    assert_close(y.array, y0, tol, "y")
+    assert_close(y.array, y0, FWD_RTOL[precision], "y")
     assert_close(da, da0, tol, "dA")
     assert_close(db, db0, tol, "dB")
-    assert_close(y.array, golden[f"matmul/{case[0]}/y"], tol, "y vs golden")
+    assert_close(y.array, golden[f"matmul/{case[0]}/y"], FWD_RTOL[precision], "y vs golden")
     assert_close(da, golden[f"matmul/{case[0]}/da"], tol, "dA vs golden")
     assert_close(db, golden[f"matmul/{case[0]}/db"], tol, "dB vs golden")
 
