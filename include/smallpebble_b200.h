@@ -107,6 +107,11 @@ int sp_fill_f32(float* dst, int64_t n, float value, sp_stream_t stream);
 /* float64 host data uploaded raw then narrowed on device (np.float64 -> device fp32) */
 int sp_cast_f64_f32(const double* src, float* dst, int64_t n, sp_stream_t stream);
 int sp_cast_i64_i32(const int64_t* src, int32_t* dst, int64_t n, sp_stream_t stream);
+/* Library scratch (partial sums of deterministic two-pass reductions, arrival counters) exists
+ * once per device and LANE.  Calls issued on one stream use lane 0 and are ordered by the
+ * stream; a caller that issues independent calls on a second stream (steady.py runs the
+ * parameter-gradient kernels beside the data-gradient chain) brackets them with lane 1. */
+int sp_set_scratch_lane(int lane);
 /* write `bytes` of scratch (> L2 size) so the next kernel starts from a cold L2 */
 int sp_l2_flush(void* scratch, size_t bytes, sp_stream_t stream);
 
@@ -172,6 +177,13 @@ int sp_xent_bwd(const float* probs, const int32_t* labels, const float* gloss,
 int sp_softmax_xent_fwd(const float* logits, const int32_t* labels, float* probs,
                         float* loss, int64_t rows, int64_t cols, sp_stream_t stream);
 /* dlogits = gloss[0] * (probs - onehot(labels)) */
+/* forward as sp_softmax_xent_fwd, plus what sp_softmax_xent_bwd_colsum returns for a unit
+ * upstream gradient (dlogits = p - onehot and its column sums): when the loss is the root of
+ * get_gradients (sp.py:85 seeds it with ones) the backward sweep starts one launch later.
+ * Single-block sizes only (rows <= 2048, rows * cols <= 32768). */
+int sp_softmax_xent_fwd_grad(const float* logits, const int32_t* labels, float* probs,
+                             float* loss, float* dlogits, float* colsum, int64_t rows,
+                             int64_t cols, sp_stream_t stream);
 int sp_softmax_xent_bwd(const float* probs, const int32_t* labels, const float* gloss,
                         float* dlogits, int64_t rows, int64_t cols, sp_stream_t stream);
 /* the same, plus colsum[c] = sum over rows of dlogits[r, c]: the gradient of a bias row
@@ -192,6 +204,13 @@ int sp_maxpool2d_bwd(const float* gy, const uint8_t* idx, float* dx, int N, int 
                      int C, int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH,
                      int OW, sp_stream_t stream);
 
+/* sp_maxpool2d_fwd (leaky == 0) or sp_maxpool2d_leaky_fwd that also writes sp_tf32_split(y, split,
+ * ..., block_elems, kind): the pooled tensor leaves the kernel in the operand form of the
+ * error-compensated conv2d that consumes it (no split launch of its own) */
+int sp_maxpool2d_fwd_split(const float* x, float* y, uint8_t* idx, float* split,
+                           int64_t block_elems, int kind, int N, int H, int W, int C, int KH,
+                           int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW, int leaky,
+                           float alpha, sp_stream_t stream);
 /* Fused across the API seam: maxpool2d(leaky_relu(x)) without storing leaky(x),
  * bit-identical to the two separate calls; and its gradient dx = maxpool_bwd(gy) * slope(x)
  * (slope = x > 0 ? 1 : alpha, sp.py:233) without storing the intermediate gradient. */
@@ -296,6 +315,15 @@ int sp_adam_multi_out(int n_tensors, float* const* host_p, float* const* host_p_
                       const float* const* host_g, float* const* host_m, float* const* host_v,
                       const int64_t* host_numel, int32_t* const* host_step, float alpha,
                       float beta1, float beta2, float eps, sp_stream_t stream);
+/* sp_adam_multi_out that also writes the TF32 shadows (sp_tf32_shadow_multi: rounded copy and /
+ * or ONE split copy per tensor, NULL entries / NULL tables = none) of the UPDATED parameters:
+ * the next step's contractions find their operands ready without a launch of their own */
+int sp_adam_multi_shadow(int n_tensors, float* const* host_p, float* const* host_p_out,
+                         const float* const* host_g, float* const* host_m, float* const* host_v,
+                         const int64_t* host_numel, int32_t* const* host_step,
+                         float* const* host_rounded, float* const* host_split,
+                         const int64_t* host_block_elems, const int32_t* host_kind, float alpha,
+                         float beta1, float beta2, float eps, sp_stream_t stream);
 int sp_sgd_multi(int n_tensors, float* const* host_p, const float* const* host_g,
                  const int64_t* host_numel, float lr, sp_stream_t stream);
 /* gather many gradient tensors into one flat bucket (the data-parallel all-reduce payload):

@@ -1,0 +1,35 @@
+"""Device time of the three steady-state graphs (forward / backward / update) replayed alone,
+and of the eager kernels of each phase back to back."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import smallpebble_b200 as sp
+from smallpebble_b200 import workloads, steady
+from smallpebble_b200.array import DeviceArray
+
+kind = sys.argv[1] if len(sys.argv) > 1 else "cnn"
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else {"cnn": 128, "mlp": 200, "vgg": 256}[kind]
+if len(sys.argv) > 3:
+    sp.set_precision(sys.argv[3])
+x, y = workloads.synthetic_batch(kind, batch)
+wl = workloads.BUILDERS[kind](seed=0)
+adam = sp.Adam()
+xd = DeviceArray.from_host(x); yd = DeviceArray.from_host(y, dtype=np.int32); xd.ptr; yd.ptr
+for i in range(12):
+    wl.x_in.assign_value(sp.Variable(xd)); wl.y_true.assign_value(yd)
+    lv = wl.loss.run(); g = sp.get_gradients(lv); adam.training_step(wl.learnables, g)
+torch.cuda.synchronize()
+rec = g._steady[0] if g._steady else None
+assert rec is not None, steady.stats
+def timeit(graph, n=200):
+    for _ in range(5): graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): graph.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+print(f"{kind} b{batch} {sp.get_precision()}: F {timeit(rec.graph_f):.1f} us ({rec.kernels_f} calls)  "
+      f"B {timeit(rec.graph_b):.1f} us ({rec.kernels_b} calls)  U {timeit(rec.graph_u):.1f} us ({rec.kernels_u} calls)")

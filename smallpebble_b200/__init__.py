@@ -11,6 +11,7 @@ from collections import defaultdict  # noqa: F401
 import numpy as np  # noqa: F401
 
 from . import distributed  # noqa: F401
+from . import steady  # noqa: F401
 from .array import DeviceArray, transfer_counters  # noqa: F401
 from .capture import CapturedStep, capture  # noqa: F401
 from .core import (  # noqa: F401
@@ -24,5 +25,7 @@ from .graph import (  # noqa: F401
     Adam, AssignmentError, Lazy, Placeholder, batch, convlayer, get_learnables, he_init,
     learnable, linearlayer, onehot, sgd_step,
 )
+
+set_steady_replay = steady.set_enabled
 
 __version__ = "0.1.0"

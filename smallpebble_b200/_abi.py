@@ -51,6 +51,7 @@ SIGNATURES = {
     "sp_cast_f64_f32": (C.c_int, [vp, vp, i64, vp]),
     "sp_cast_i64_i32": (C.c_int, [vp, vp, i64, vp]),
     "sp_l2_flush": (C.c_int, [vp, sz, vp]),
+    "sp_set_scratch_lane": (C.c_int, [C.c_int]),
     "sp_ewise_unary": (C.c_int, [C.c_int, vp, vp, i64, f32, vp]),
     "sp_ewise_binary": (C.c_int, [C.c_int, vp, p_i64, vp, p_i64, vp, C.c_int, p_i64, vp]),
     "sp_accumulate": (C.c_int, [vp, vp, i64, vp]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "sp_xent_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
     "sp_softmax_xent_fwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
     "sp_softmax_xent_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
+    "sp_softmax_xent_fwd_grad": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, i64, vp]),
     "sp_stream_create": (C.c_int, [vp]),
     "sp_event_create": (C.c_int, [vp]),
     "sp_event_record": (C.c_int, [vp, vp]),
@@ -80,6 +82,7 @@ SIGNATURES = {
     "sp_maxpool2d_fwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [vp]),
     "sp_maxpool2d_bwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [vp]),
     "sp_maxpool2d_leaky_fwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [f32, vp]),
+    "sp_maxpool2d_fwd_split": (C.c_int, [vp, vp, vp, vp, i64, C.c_int] + [C.c_int] * 13 + [f32, vp]),
     "sp_maxpool2d_leaky_bwd": (C.c_int, [vp, vp, vp, vp] + [C.c_int] * 12 + [f32, vp]),
     "sp_gemm": (C.c_int, [C.c_int, C.c_int, i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64,
                           i64, i64, C.c_int, vp]),
@@ -94,6 +97,10 @@ SIGNATURES = {
     "sp_adam_multi_out": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                     C.POINTER(vp), C.POINTER(vp), p_i64, C.POINTER(vp), f32, f32,
                                     f32, f32, vp]),
+    "sp_adam_multi_shadow": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                       C.POINTER(vp), C.POINTER(vp), p_i64, C.POINTER(vp),
+                                       C.POINTER(vp), C.POINTER(vp), p_i64, C.POINTER(C.c_int32),
+                                       f32, f32, f32, f32, vp]),
     "sp_sgd_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), p_i64, f32, vp]),
     "sp_tf32_split": (C.c_int, [vp, vp, i64, i64, C.c_int, vp]),
     "sp_tf32_round": (C.c_int, [vp, vp, i64, vp]),
@@ -112,7 +119,8 @@ _LAUNCHING = {
     if n not in ("sp_abi_version", "sp_last_error", "sp_device_info", "sp_debug_set_umma_policy",
                  "sp_debug_tma2_trace", "sp_host_is_pinned", "sp_stream_create", "sp_event_create",
                  "sp_event_record", "sp_stream_wait_event", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
-                 "sp_conv2d_wgrad_workspace", "sp_set_tf32_output_rounding", "sp_conv2d_x3_plan")
+                 "sp_conv2d_wgrad_workspace", "sp_set_tf32_output_rounding", "sp_conv2d_x3_plan",
+                 "sp_set_scratch_lane")
 }
 
 

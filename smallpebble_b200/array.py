@@ -224,12 +224,18 @@ def scalar_one(shape):
     """(array of ones, fresh?) for a one-element `shape`.  Outside CUDA-graph recording the
     constant is created once and shared (saves a fill launch per get_gradients); callers must
     treat a shared one as read-only."""
-    if _pool_bypass:
-        return DeviceArray.full(shape, 1.0), True
     arr = _scalar_ones.get(shape)
     if arr is None:
+        if _pool_bypass:  # recording: a constant created now would live in the graph's pool
+            arr = DeviceArray.full(shape, 1.0)
+            arr._aux = ONES
+            return arr, True
         arr = _scalar_ones[shape] = DeviceArray.full(shape, 1.0)
+        arr._aux = ONES
     return arr, False
+
+
+ONES = ("ones",)  # `_aux` marker of an all-ones gradient seed (closures may special-case it)
 
 
 _new_array = object.__new__
@@ -1072,26 +1078,62 @@ def tf32_shadow_requests(a: DeviceArray):
     return sh[1] is not None, tuple(sh[2])
 
 
-def tf32_shadows_multi(jobs) -> None:
+def tf32_shadow_targets(a: DeviceArray, want_round: bool, kinds, refresh: bool):
+    """Buffers for the shadows of `a` that a producer of `a` is about to fill itself (the fused
+    Adam kernel): (rounded array or None, (split array, kind, block) or None, kinds left over
+    for tf32_shadows_multi).  Existing shadows are only handed out again under `refresh`."""
+    sh = _shadow_slot(a)
+    rounded = None
+    if want_round and not a._tf32:
+        if sh[1] is None:
+            rounded = DeviceArray.empty(a.shape, FLOAT, a.size)
+            rounded._tf32 = True
+            sh[1] = rounded
+        elif refresh:
+            rounded = sh[1]
+    split, rest = None, []
+    for kind, block in kinds:
+        sp = sh[2].get((kind, block))
+        if sp is not None and not refresh:
+            continue
+        if split is not None:
+            rest.append((kind, block))
+            continue
+        if sp is None:
+            parts = 2 if kind == _abi.SPLIT_RL else 3
+            sp = DeviceArray.empty((a.size * parts,), FLOAT, a.size * parts)
+            sh[2][(kind, block)] = sp
+        split = (sp, kind, block)
+    return rounded, split, rest
+
+
+def tf32_shadows_multi(jobs, refresh: bool = False) -> None:
     """jobs: [(array, want_rounded, [(kind, block_elems), ...])].  Fills the shadow slots of
-    every array with ONE launch per 24 tensors (a job with two split kinds takes two rows)."""
+    every array with ONE launch per 24 tensors (a job with two split kinds takes two rows).
+    `refresh`: shadows that already exist are recomputed into their buffers (the array was
+    overwritten: steady.py's optimiser step writes into the arrays of two steps ago)."""
     rows = []
     for a, want_round, kinds in jobs:
         if not a.size:
             continue
         sh = _shadow_slot(a)
         rounded = None
-        if want_round and sh[1] is None and not a._tf32:
-            rounded = DeviceArray.empty(a.shape, FLOAT, a.size)
-            rounded._tf32 = True
-            sh[1] = rounded
+        if want_round and not a._tf32:
+            if sh[1] is None:
+                rounded = DeviceArray.empty(a.shape, FLOAT, a.size)
+                rounded._tf32 = True
+                sh[1] = rounded
+            elif refresh:
+                rounded = sh[1]
         first = True
         for kind, block in kinds:
-            if (kind, block) in sh[2]:
+            sp = sh[2].get((kind, block))
+            if sp is not None and not refresh:
                 continue
-            parts = 2 if kind == _abi.SPLIT_RL else 3
-            sp = DeviceArray.empty((a.size * parts,), FLOAT, a.size * parts)
-            sh[2][(kind, block)] = sp
+            if sp is None:
+                parts = 2 if kind == _abi.SPLIT_RL else 3
+                sp = DeviceArray.empty((a.size * parts,), FLOAT, a.size * parts)
+                sh[2][(kind, block)] = sp
             rows.append((a, rounded if first else None, sp, block, kind))
             first = False
         if first and rounded is not None:

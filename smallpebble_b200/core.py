@@ -30,6 +30,7 @@ import os
 import numpy as np
 
 from . import _abi
+from . import steady as _steady
 from . import array as A
 from .array import DeviceArray
 
@@ -101,6 +102,7 @@ def set_precision(name: str) -> None:
     _precision_name = name.lower()
     _conv_plan.cache_clear()
     _reset_rounding()
+    _steady.invalidate()
 
 
 def get_precision() -> str:
@@ -127,6 +129,7 @@ def debug_set_kernel_policy(policy: int) -> None:
     policy-dependent workspace sizes, so they are dropped."""
     _abi.f.sp_debug_set_umma_policy(policy)
     _conv_plan.cache_clear()
+    _steady.invalidate()
 
 
 _fuse_softmax_xent = os.environ.get("SP_FUSE_SOFTMAX_XENT", "1") != "0"
@@ -146,6 +149,7 @@ def set_fusion(enabled: bool) -> None:
     _fuse_leaky_pool = bool(enabled)
     _fuse_bias = bool(enabled)
     _fuse_conv_leaky = bool(enabled)
+    _steady.invalidate()
 
 
 # --------------------------------------------------------------------------------------------
@@ -190,11 +194,12 @@ class Gradients(dict):
     reference returns (sp.py:87), but a training loop that only reads the learnables'
     gradients never pays for the image gradient.  SP_EAGER_LEAF_GRADS=1 disables deferral."""
 
-    __slots__ = ("_deferred",)
+    __slots__ = ("_deferred", "_steady")
 
     def __init__(self):
         super().__init__()
         self._deferred = {}
+        self._steady = None  # steady.py: (recording, epoch) of a replayed backward pass
 
     # plain dict access for get_gradients' own sweep (no deferred-leaf handling)
     get_plain = dict.get
@@ -310,11 +315,25 @@ def _tape_order(variable):
     return order
 
 
+_leaf_fork = None  # steady.py, while it records a backward pass: runs parameter-gradient
+                   # closures on a second stream
+
+
 def get_gradients(variable: Variable) -> dict:
     """d(sum of `variable`)/d(node) for every node reachable from `variable` (sp.py:57-87).
 
     Returns {Variable: DeviceArray}, keyed by identity, including `variable` itself (ones).
     """
+    tag = getattr(variable, "_steady", None)
+    if tag is not None:
+        # the result of a replayed run (steady.py): its backward pass is a CUDA graph too
+        replayed = _steady.gradients_of(variable, tag)
+        if replayed is not None:
+            return replayed
+    return _get_gradients(variable)
+
+
+def _get_gradients(variable: Variable) -> dict:
     order = _tape_order(variable)
 
     gradients = Gradients()
@@ -328,13 +347,28 @@ def get_gradients(variable: Variable) -> dict:
     owned = {variable} if fresh else set()
     get, put = gradients.get_plain, gradients.put_plain
     hook = _dp_hook
+    fork = _leaf_fork
     for node in order:
         path_value = get(node)
         for child, multiply_by_locgrad in node.local_gradients:
-            if (not child.local_gradients and not getattr(child, "is_learnable", False)
-                    and not _eager_leaf_grads):
-                gradients._defer(child, multiply_by_locgrad, path_value)
-                continue
+            if not child.local_gradients:
+                if getattr(child, "is_learnable", False):
+                    if fork is not None:
+                        # a parameter gradient feeds nothing else in this sweep: closure and
+                        # accumulation run on the side stream, in order among themselves
+                        def job(pv, child=child, fn=multiply_by_locgrad):
+                            value = _as_device(fn(pv))
+                            if get(child) is None:
+                                put(child, value)
+                            else:
+                                _accumulate(gradients, owned, child, value)
+                            return get(child)
+
+                        fork(job, path_value)
+                        continue
+                elif not _eager_leaf_grads:
+                    gradients._defer(child, multiply_by_locgrad, path_value)
+                    continue
             value = multiply_by_locgrad(path_value)
             if type(value) is not DeviceArray:
                 value = _as_device(value)
@@ -936,6 +970,8 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
             # this tensor (leaky_relu sign, maxpool argmax) must match the float64 reference
             _, g, pr, xsplit, wsplit = _conv_x3(plan)
             if xsplit is not None:
+                if images.local_gradients and getattr(images, "_argmax", None) is not None:
+                    _split_hints[x.shape] = xsplit  # (maxpool2d then produces it as it pools)
                 xa = A.tf32_split(x, *xsplit)
                 wa = A.tf32_split(w, *wsplit)
         if alpha is None:
@@ -989,6 +1025,7 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
 
 
 _UINT8 = np.dtype(np.uint8)
+_split_hints = {}  # pooled output shape -> (split kind, block) its consumer conv2d asked for
 
 
 @functools.lru_cache(maxsize=256)
@@ -1017,7 +1054,18 @@ def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = 
     idx = DeviceArray.empty(out_shape, _UINT8, out_size)
     tag = x.pending_tag
     fused = tag is not None and tag[0] == "leaky_relu" and y.size > 0
-    if fused:
+    hint = _split_hints.get(out_shape) if _compensate and y.size else None
+    if hint is not None:
+        # a compensated conv2d consumed the previous tensor of this shape as (r, l) split
+        # operand: this kernel writes that form beside y (tf32.cu), no split launch later
+        kind, block = hint
+        parts = 2 if kind == _abi.SPLIT_RL else 3
+        split = DeviceArray.empty((out_size * parts,), A.FLOAT, out_size * parts)
+        src, leaky, alpha = (tag[1], 1, tag[2]) if fused else (x, 0, 0.0)
+        F.sp_maxpool2d_fwd_split(src.ptr, y.ptr, idx.ptr, split._ptr, block, kind, *geom, leaky,
+                                 alpha, A.stream())
+        y._shadow = [A.inplace_epoch, None, {hint: split}]
+    elif fused:
         # the input is a leaky_relu that has not been launched: pool leaky(src) directly
         F.sp_maxpool2d_leaky_fwd(tag[1].ptr, y.ptr, idx.ptr, *geom, tag[2], A.stream())
     elif y.size:
@@ -1119,9 +1167,24 @@ def cross_entropy(y_pred: Variable, y_true: np.ndarray, axis: int = -1) -> Varia
             # the softmax has not been launched: this kernel produces its output as well
             probs._adopt(DeviceArray.empty_like(probs))
         # (re)computes probs into the softmax node's buffer (bitwise the same values) + the loss
-        F.sp_softmax_xent_fwd(logits.ptr, labels.ptr, probs.ptr, loss.ptr, rows, cols, A.stream())
+        pre = None
+        if (_fuse_bias and 0 < rows <= 2048 and rows * cols <= 32768
+                and not (_compensate and getattr(logits_var, "_to_contraction", False))):
+            # ... and, in the same launch, the gradient of the logits for a unit seed with its
+            # column sums: what grad_logits returns when this loss is the root of get_gradients
+            pre = (DeviceArray.empty_like(logits), DeviceArray.empty((cols,)))
+            F.sp_softmax_xent_fwd_grad(logits.ptr, labels.ptr, probs.ptr, loss.ptr, pre[0]._ptr,
+                                       pre[1]._ptr, rows, cols, A.stream())
+        else:
+            F.sp_softmax_xent_fwd(logits.ptr, labels.ptr, probs.ptr, loss.ptr, rows, cols,
+                                  A.stream())
 
         def grad_logits(g):
+            if pre is not None and g._aux is A.ONES and not _want_rounding(logits_var):
+                dlogits = pre[0]
+                dlogits._aux = ("colsum0", pre[1])
+                dlogits._tf32 = False
+                return dlogits
             dlogits = DeviceArray.empty_like(logits)
             rounded = _want_rounding(logits_var)
             if dlogits.size and _fuse_bias and rows * cols <= 32768:

@@ -116,17 +116,33 @@ void wgrad_split(const sp_conv_geom& g, bool umma, int* splits, int64_t* k_chunk
   if (*splits < 1) *splits = 1;
 }
 
-// Split of the wgrad reduction axis for the 2-SM kernel: 74 persistent CTA pairs, so aim for a
-// whole number of rounds over the (256-row x 256-column) output tiles; k_chunk % 64 == 0.
+// Split of the wgrad reduction axis (the N*OH*OW pixels) for the 2-SM kernel.  Two levels:
+// S CTA pairs of one cluster share a slice and add their accumulators in shared memory
+// (conv_tma2.cu), and `splits` clusters per output tile write partial filters that a second
+// pass sums in fixed order.  Aim: as many of the 74 pairs busy as possible with >= 3 stages of
+// 64 pixels per pair, preferring the in-cluster split (fewer partial filters to write and sum).
 void wgrad_split_tma2(const sp_conv_geom& g, int* splits, int64_t* k_chunk) {
   const int64_t M = (int64_t)g.KH * g.KW * g.C, N = g.K, K = (int64_t)g.N * g.OH * g.OW;
-  const int pairs = (device_info().sm_count > 0 ? device_info().sm_count : 148) / 2;
   const int64_t tiles = ((M + 255) / 256) * ((N + 255) / 256);
-  int64_t want = tiles >= pairs ? 1 : pairs / tiles;
-  const int64_t max_splits = (K + 1023) / 1024;  // >= 32 k-blocks per tile
-  if (want > max_splits) want = max_splits;
-  if (want < 1) want = 1;
-  int64_t chunk = ((K + want - 1) / want + 63) / 64 * 64;
+  const int64_t stages = (K + 63) / 64;
+  int64_t best_pairs = 0, best_cross = 1;
+  for (int S = 4; S >= 1; S >>= 1) {
+    const int64_t capacity = conv_tma2_max_clusters(2 * S);
+    if (capacity < tiles) continue;
+    int64_t cross = capacity / tiles;
+    const int64_t by_work = stages / (3 * S);  // >= 3 stages per pair
+    if (cross > by_work) cross = by_work;
+    if (cross < 1) {
+      if (S > 1) continue;
+      cross = 1;
+    }
+    const int64_t pairs = tiles * cross * S;
+    if (pairs > best_pairs + best_pairs / 8) {  // a smaller S must buy >12 % more pairs
+      best_pairs = pairs;
+      best_cross = cross;
+    }
+  }
+  int64_t chunk = ((K + best_cross - 1) / best_cross + 63) / 64 * 64;
   *k_chunk = chunk;
   *splits = (int)((K + chunk - 1) / chunk);
   if (*splits < 1) *splits = 1;

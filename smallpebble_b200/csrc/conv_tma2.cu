@@ -75,6 +75,9 @@ struct Tma2Params {
   int split3;          // fprop, SP_PRECISION_TF32_SPLIT: operands are (r, l) pairs interleaved per
                        // 32 channels; a stage holds A = (x_r | x_l), B = (w_r | w_l) of ONE
                        // (tap, channel block) and takes 12 MMAs: r.r + l.r + r.l  (3xTF32)
+  int ksplit;          // CTA pairs per cluster (1, 2 or 4): a small problem's reduction axis is
+                       // split over the pairs of one cluster, which then add their accumulators
+                       // through distributed shared memory in pair order (one tile per cluster)
   float* C;
   int64_t ldc;
   int64_t split_stride;
@@ -232,12 +235,20 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, u
       : "memory");
 }
 // one arrival on the barrier at this smem offset in BOTH CTAs once all earlier MMAs retired
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t pair_mask = 3) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
       "[%0], %1;" ::"r"(bar),
-      "h"((uint16_t)3)
+      "h"(pair_mask)
       : "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(cluster_addr)
+               : "memory");
+  return v;
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -412,8 +423,9 @@ struct ModeCfg {
 
 // ACT: the dgrad instantiation with the leaky_relu-backward epilogue (its prefetch registers
 // would otherwise cost the plain data gradient 2-3 %)
+// Launched with a runtime cluster dimension of 2 * p.ksplit CTAs (launch_conv_tma2).
 template <int MODE, bool ACT = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)
     conv_tma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ Tma2Params p) {
   using Cfg = ModeCfg<MODE>;
@@ -426,10 +438,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
   const int t = threadIdx.x;
   const int warp = (int)uniform((uint32_t)(t >> 5)), lane = t & 31;
-  const uint32_t rank = uniform(cluster_ctarank());
+  // cluster = S CTA pairs; CTAs 2k, 2k+1 are a pair (the tcgen05 cta_group::2 peers)
+  const uint32_t crank = uniform(cluster_ctarank());
+  const uint32_t rank = crank & 1u;            // rank inside the pair
+  const uint32_t lead_rank = crank & ~1u;      // cluster rank of this pair's leader CTA
   const bool leader = rank == 0;
-  const int cluster_id = blockIdx.x >> 1;
-  const int n_clusters = gridDim.x >> 1;
+  const int S = p.ksplit;
+  const int pair = (int)(crank >> 1);          // which slice of the reduction axis
+  const int cluster_id = (int)blockIdx.x / (2 * S);
+  const int n_clusters = (int)gridDim.x / (2 * S);
+  const uint16_t pair_mask = (uint16_t)(3u << lead_rank);
 
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32(bars);
@@ -437,7 +455,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
   auto tmem_full_bar = [&](int a) { return bar0 + 8u * (2 * kStages + a); };
   auto tmem_empty_bar = [&](int a) { return bar0 + 8u * (2 * kStages + 2 + a); };
-  const bool tr = p.trace != nullptr && cluster_id == 0 && leader && lane == 0;
+  const bool tr = p.trace != nullptr && cluster_id == 0 && crank == 0 && lane == 0;
   pdl_trigger();  // launch_pdl(): the next kernel may start launching; it waits for us itself
   trace_at(p, tr && warp == 0, 0);
 
@@ -472,7 +490,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     {
       const int bslot = b_warp_slot(warp);
       const bool is_b = bslot >= 0;
-      const uint32_t full0 = uniform(mapa(full_bar(0), 0));  // the leader's `full` barriers
+      const uint32_t full0 = uniform(mapa(full_bar(0), lead_rank));  // the leader's `full` barriers
       int s = 0;
       uint32_t ph = 0;
       int rrb = 0;  // stage counter modulo kBWarps
@@ -501,9 +519,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           cn = q / p.D1;
           ch = p.base_h + (q - cn * p.D1) * p.sy;
         }
-        int tap = 0, cb = 0;  // (filter tap, 32-channel block) of half 0 of the stage
         const int nst = (MODE == kWgrad) ? tc.kblocks : (tc.kblocks + 1) >> 1;
-        for (int st = 0; st < nst; ++st) {
+        // this pair's slice of the tile's stages (all of them when the cluster is one pair)
+        const int st0 = pair * nst / S, st1 = (pair + 1) * nst / S;
+        // (filter tap, 32-channel block) of half 0 of the first stage
+        int tap = (2 * st0) / p.cblocks, cb = 2 * st0 - tap * p.cblocks;
+        pix += st0 * Cfg::kKStage;
+        for (int st = st0; st < st1; ++st) {
           // fprop / dgrad: the two halves of this stage
           int tap1 = tap, cb1 = cb + 1;
           if (cb1 == p.cblocks) {
@@ -609,8 +631,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccumCols);
         const int nst = (MODE == kWgrad) ? tc.kblocks : (tc.kblocks + 1) >> 1;
+        const int st0 = pair * nst / S, st1 = (pair + 1) * nst / S;
         const uint32_t bnh_bytes = (uint32_t)(tc.bn >> 1) * 128u;
-        for (int st = 0; st < nst; ++st) {
+        for (int st = st0; st < st1; ++st) {
           mbar_wait(full_bar(s), ph);
           trace_at(p, tr && gkb < kTraceKb, 16 + 2 * kTraceKb + gkb);
           ++gkb;
@@ -632,7 +655,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             for (int k = 0; k < 4; ++k)
               umma_tf32_2sm(tmem_d, desc_join(a_lo + (uint32_t)k * a_step, a_hi),
                             desc_join(b_lo + (uint32_t)k * b_step, b_hi), idesc,
-                            (st > 0 || k > 0) ? 1u : 0u);
+                            (st > st0 || k > 0) ? 1u : 0u);
             if (MODE == kFprop && p.split3) {
               // halves are (r, l) of the same 32 channels: r.r was issued above, now l.r + r.l
 #pragma unroll
@@ -649,9 +672,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 umma_tf32_2sm(tmem_d, desc_join(a_lo + a_half + (uint32_t)k * a_step, a_hi),
                               desc_join(b_lo + b_half + (uint32_t)k * b_step, b_hi), idesc, 1u);
             }
-            umma_commit_2sm(empty_bar(s));  // both CTAs' producers may refill stage s
-            if (st == nst - 1)
-              umma_commit_2sm(tmem_full_bar(acc));  // both CTAs' epilogues may drain stage acc
+            umma_commit_2sm(empty_bar(s), pair_mask);  // both CTAs' producers may refill stage s
+            if (st == st1 - 1)
+              umma_commit_2sm(tmem_full_bar(acc), pair_mask);  // both CTAs' epilogues may drain it
           }
           __syncwarp();
           if (++s == kS) {
@@ -666,7 +689,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     // =========================== EPILOGUE (both CTAs, 4 warps) =============================
     // TMEM lane == tile row; warp w may only touch lane quadrant w % 4.
     const int quad = warp & 3;
-    const uint32_t empty_leader0 = mapa(tmem_empty_bar(0), 0);
+    const uint32_t empty_leader0 = mapa(tmem_empty_bar(0), lead_rank);
     const bool vec_store = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                            ((p.split_stride & 3) == 0);
     // leaky_relu backward epilogue: byte distance from an output element to its activation
@@ -690,13 +713,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         rp[r] = cbase + (int64_t)row * p.ldc;
         ok_mask |= (m_base + row < p.M ? 1u : 0u) << r;
       }
-      const bool use_act = ACT && vec_store && act_delta != 0;
+      const bool use_act = ACT && vec_store && act_delta != 0 && S == 1;
       float4 act_cur[8], act_next[8];
       if (use_act) load_act_rows(act_cur, rp, ok_mask, 0, lane, act_delta);
       mbar_wait(tmem_full_bar(acc), ((uint32_t)it >> 1) & 1u);
       trace_at(p, tr && warp == kWarpEpi0 && it < 4, 6 + it);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccumCols);
+      if (S > 1) {
+        // split reduction axis: park this pair's partial accumulator in the (now idle) stage
+        // ring as XOR-swizzled 32 x 32 blocks; the cluster sums the partials below
+        uint8_t* dump = smem_raw + (tiles - smem_u32(smem_raw));
+        const int nblk = tc.bn >> 5;
+        for (int cb = 0; cb < tc.bn; cb += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
+          tmem_ld_wait();
+          float4* t4 = reinterpret_cast<float4*>(dump + (size_t)(quad * nblk + (cb >> 5)) * 4096);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            t4[lane * 8 + (j ^ (lane & 7))] =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+        tc_fence_before();
+        trace_at(p, tr && warp == kWarpEpi0 && it < 4, 10 + it);
+        continue;
+      }
       for (int cb = 0; cb < tc.bn; cb += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
@@ -722,6 +765,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(empty_leader0 + 8u * acc);
       trace_at(p, tr && warp == kWarpEpi0 && it < 4, 10 + it);
+    }
+  }
+
+  if (S > 1 && cluster_id < p.total_tiles) {
+    // ---- cluster reduction of the S partial accumulators (distributed shared memory) -------
+    // CTA (pair, rank) owns rows [pair * 128 / S, (pair + 1) * 128 / S) of half `rank` of the
+    // tile: it adds the S partials of those rows in pair order (a fixed order: the result does
+    // not depend on timing), applies the epilogue and stores.  A warp covers 4 rows x 128
+    // contiguous bytes of one 32-column block per step: conflict-free reads, full-line stores.
+    __syncthreads();
+    cluster_sync_all();
+    const TileCoord tc = tile_coord(p, cluster_id);
+    const int nblk = tc.bn >> 5;
+    const int rows_per = 128 / S;
+    const int row0 = pair * rows_per;
+    const int m_half = (tc.m_pair * 2 + (int)rank) * 128;
+    float* __restrict__ cbase = p.C + (int64_t)tc.split * p.split_stride + tc.n0;
+    const int64_t act_delta =
+        (ACT && p.act) ? reinterpret_cast<const char*>(p.act) - reinterpret_cast<const char*>(p.C) : 0;
+    const int total = nblk * rows_per * 8;
+    for (int idx = t; idx < total; idx += kThreads) {
+      const int chunk = idx & 7;
+      const int r = (idx >> 3) % rows_per;
+      const int cbk = (idx >> 3) / rows_per;
+      const int row = row0 + r;  // row of this CTA's 128-row half
+      const int m = m_half + row;
+      if (m >= p.M) continue;
+      const int rl = row & 31;
+      const uint32_t off = (uint32_t)((row >> 5) * nblk + cbk) * 4096u +
+                           (uint32_t)(rl * 8 + (chunk ^ (rl & 7))) * 16u;
+      float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < S; ++q) {
+        const float4 v = ld_dsmem_f4(mapa(tiles + off, (uint32_t)(2 * q) + rank));
+        acc4.x += v.x;
+        acc4.y += v.y;
+        acc4.z += v.z;
+        acc4.w += v.w;
+      }
+      float* dst = cbase + (int64_t)m * p.ldc + cbk * 32 + chunk * 4;
+      if (MODE == kFprop && p.leaky) {
+        acc4.x = acc4.x > 0.f ? acc4.x : p.alpha * acc4.x;
+        acc4.y = acc4.y > 0.f ? acc4.y : p.alpha * acc4.y;
+        acc4.z = acc4.z > 0.f ? acc4.z : p.alpha * acc4.z;
+        acc4.w = acc4.w > 0.f ? acc4.w : p.alpha * acc4.w;
+      }
+      if (ACT && act_delta != 0) {
+        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(dst) + act_delta);
+        acc4.x *= a.x > 0.f ? 1.f : p.alpha;
+        acc4.y *= a.y > 0.f ? 1.f : p.alpha;
+        acc4.z *= a.z > 0.f ? 1.f : p.alpha;
+        acc4.w *= a.w > 0.f ? 1.f : p.alpha;
+        acc4 = round_out4(acc4, p.round_out);
+      }
+      *reinterpret_cast<float4*>(dst) = acc4;
     }
   }
 
@@ -1277,6 +1374,39 @@ bool conv_tma2_supported(int mode, const IgemmParams& p) {
   return false;
 }
 
+// How many clusters of `size` CTAs of the 2-SM kernel can be resident at once (one CTA per SM:
+// the stage ring takes the whole shared memory).  Queried once per size.
+int conv_tma2_max_clusters(int size) {
+  static int cached[9] = {0};
+  if (size < 2 || size > 8) return 0;
+  if (cached[size]) return cached[size];
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  int n = 0;
+  if (size == 2) {
+    n = sms / 2;
+  } else {
+    auto kern = conv_tma2_kernel<kFprop, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(size * (sms / size)));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+      (void)cudaGetLastError();
+      n = 0;
+    }
+  }
+  cached[size] = n > 0 ? n : -1;
+  return cached[size];
+}
+
 int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
   if (!conv_tma2_supported(mode, ip))
     return set_error(SP_ERR_UNSUPPORTED, "conv_tma2: unsupported problem");
@@ -1389,8 +1519,27 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
   if (!ok) return set_error(SP_ERR_UNSUPPORTED, "conv_tma2: cuTensorMapEncode failed");
 
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
-  const int clusters = std::min(p.total_tiles, sms / 2);
-  dim3 grid((unsigned)(2 * clusters));
+  // Small problems: split the reduction axis over the S pairs of a cluster of 2S CTAs (summed
+  // through distributed shared memory inside the kernel).  A lone tile's k loop runs at the
+  // latency of its own pipeline, so S pairs finish it ~S times sooner; only when every tile
+  // gets its own cluster (single wave) and every pair keeps >= 3 stages.
+  p.ksplit = 1;
+  {
+    static const int forced = [] {  // SP_TMA2_KSPLIT=1 disables, 2 / 4 cap the split
+      const char* e = getenv("SP_TMA2_KSPLIT");
+      return e ? atoi(e) : 0;
+    }();
+    const int nst = mode == kWgrad ? p.kblocks : (p.kblocks + 1) / 2;
+    const bool vec = (p.ldc % 4 == 0) && (p.split_stride % 4 == 0) && p.N % 32 == 0;
+    const int cap = forced >= 1 ? forced : 4;
+    int S = 1;
+    while (vec && S * 2 <= cap && p.total_tiles <= conv_tma2_max_clusters(4 * S) &&
+           nst / (S * 2) >= 3)
+      S *= 2;
+    p.ksplit = S;
+  }
+  const int clusters = p.ksplit > 1 ? p.total_tiles : std::min(p.total_tiles, sms / 2);
+  dim3 grid((unsigned)(2 * p.ksplit * clusters));
 #define SP_TMA2_LAUNCH(MODE_, ACT_)                                                             \
   do {                                                                                          \
     static bool attr_done = false;                                                              \
@@ -1403,7 +1552,23 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
                          cudaGetErrorString(e));                                                \
       attr_done = true;                                                                         \
     }                                                                                           \
-    launch_pdl(kern, grid, dim3(kThreads), kSmemBytes, st, tmA, tmB, p);                        \
+    cudaLaunchConfig_t cfg = {};                                                                \
+    cfg.gridDim = grid;                                                                         \
+    cfg.blockDim = dim3(kThreads);                                                              \
+    cfg.dynamicSmemBytes = kSmemBytes;                                                          \
+    cfg.stream = st;                                                                            \
+    cudaLaunchAttribute attr[2];                                                                \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                           \
+    attr[0].val.clusterDim.x = 2u * (unsigned)p.ksplit;                                         \
+    attr[0].val.clusterDim.y = 1;                                                               \
+    attr[0].val.clusterDim.z = 1;                                                               \
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
+    attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;                         \
+    cfg.attrs = attr;                                                                           \
+    cfg.numAttrs = 2;                                                                           \
+    if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p) != cudaSuccess)                             \
+      return set_error(SP_ERR_DRIVER, "conv_tma2: launch failed: %s",                           \
+                       cudaGetErrorString(cudaGetLastError()));                                 \
   } while (0)
   if (mode == kFprop)
     SP_TMA2_LAUNCH(kFprop, false);

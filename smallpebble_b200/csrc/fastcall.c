@@ -29,13 +29,13 @@
 #include <stdint.h>
 #include <string.h>
 
-#define SP_MAX_INT_ARGS 18
+#define SP_MAX_INT_ARGS 22
 #define SP_MAX_FLT_ARGS 4
 
 typedef int (*sp_trampoline_t)(uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
                                uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
-                               uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, float,
-                               float, float, float);
+                               uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
+                               uint64_t, uint64_t, uint64_t, uint64_t, float, float, float, float);
 
 static long long g_launches = 0;
 
@@ -105,8 +105,8 @@ static PyObject* fastfn_call(PyObject* self_, PyObject* const* args, size_t narg
     }
   }
   const int rc = self->fn(iv[0], iv[1], iv[2], iv[3], iv[4], iv[5], iv[6], iv[7], iv[8], iv[9],
-                          iv[10], iv[11], iv[12], iv[13], iv[14], iv[15], iv[16], iv[17], fv[0],
-                          fv[1], fv[2], fv[3]);
+                          iv[10], iv[11], iv[12], iv[13], iv[14], iv[15], iv[16], iv[17], iv[18],
+                          iv[19], iv[20], iv[21], fv[0], fv[1], fv[2], fv[3]);
   if (rc != 0) {
     PyObject* r = PyObject_CallFunction(self->on_error, "Oi", self->name, rc);
     Py_XDECREF(r);

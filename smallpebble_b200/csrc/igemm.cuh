@@ -62,6 +62,8 @@ void igemm_umma_set_sync_mode(int mode);
 // 2-SM (cta_group::2) TMA-fed tcgen05 conv kernels, conv_tma2.cu: channel counts % 32 == 0
 bool conv_tma2_supported(int mode, const IgemmParams& p);
 int launch_conv_tma2(int mode, const IgemmParams& p, cudaStream_t stream);
+// clusters of `size` (2, 4 or 8) CTAs of that kernel that fit on the device at once
+int conv_tma2_max_clusters(int size);
 // halo-reuse variant of the 2-SM kernel (stride-1 fprop / dgrad): every input pixel is staged
 // once per tile and the filter taps are row-shifted descriptor views of that strip
 bool conv_halo2_supported(int mode, const IgemmParams& p);

@@ -26,7 +26,36 @@ struct AdamArgs {
   int count;
   int chunk;                   // elements per block
   unsigned int* done;          // [kMaxTensors] self-resetting arrival counters (library-owned)
+  // TF32 shadows of the UPDATED parameters, written by the same kernel (tf32.cu describes the
+  // layouts): rounded copy and / or one split copy per tensor; null when not wanted
+  float* rnd[kMaxTensors];
+  float* spl[kMaxTensors];
+  int64_t pstride[kMaxTensors];
+  int parts[kMaxTensors];
+  int lmask[kMaxTensors];
 };
+
+__device__ __forceinline__ void shadow1(float x, int64_t i, float* rnd, float* spl, int64_t ps,
+                                        int P, int lmask) {
+  const float r = rna_tf32(x);
+  if (rnd) rnd[i] = r;
+  if (spl) {
+    const int64_t row = i / ps, j = i - row * ps;
+    float* d = spl + row * P * ps + j;
+    for (int q = 0; q < P; ++q) d[q * ps] = ((lmask >> q) & 1) ? x - r : r;
+  }
+}
+__device__ __forceinline__ void shadow4(float4 x, int64_t i, float* rnd, float* spl, int64_t ps,
+                                        int P, int lmask) {
+  const float4 r = make_float4(rna_tf32(x.x), rna_tf32(x.y), rna_tf32(x.z), rna_tf32(x.w));
+  if (rnd) *reinterpret_cast<float4*>(rnd + i) = r;
+  if (spl) {
+    const float4 l = make_float4(x.x - r.x, x.y - r.y, x.z - r.z, x.w - r.w);
+    const int64_t row = i / ps, j = i - row * ps;
+    float* d = spl + row * P * ps + j;
+    for (int q = 0; q < P; ++q) *reinterpret_cast<float4*>(d + q * ps) = ((lmask >> q) & 1) ? l : r;
+  }
+}
 
 struct AxpyArgs {
   float* p[kMaxTensors];
@@ -58,6 +87,7 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
 // for beta = 0.999; a double pow costs microseconds on this chip's few FP64 units).
 // The block that arrives last for a tensor bumps its step counter: every block of the tensor
 // has read the counter before it signals, so no second kernel is needed.
+template <bool SHADOW>
 __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_constant__ AdamArgs a,
                                                               float alpha, float b1, float b2,
                                                               float lnb1, float lnb2, float eps) {
@@ -73,8 +103,13 @@ __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_const
   const float* __restrict__ g = a.g[t];
   float* __restrict__ m = a.m[t];
   float* __restrict__ v = a.v[t];
+  float* const rnd = SHADOW ? a.rnd[t] : nullptr;
+  float* const spl = SHADOW ? a.spl[t] : nullptr;
+  const int64_t ps = SHADOW ? a.pstride[t] : 1;
+  const int P = SHADOW ? a.parts[t] : 1, lmask = SHADOW ? a.lmask[t] : 0;
   const bool vec =
-      (((uintptr_t)p | (uintptr_t)po | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+      (((uintptr_t)p | (uintptr_t)po | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v |
+        (uintptr_t)rnd | (uintptr_t)spl) & 15) == 0 && (!spl || (ps & 3) == 0);
   const int64_t end = min(n, base + a.chunk);
   if (vec) {
     for (int64_t i = base + 4 * threadIdx.x; i + 3 < end; i += 4 * kThreads) {
@@ -89,6 +124,7 @@ __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_const
       *reinterpret_cast<float4*>(po + i) = pp;
       *reinterpret_cast<float4*>(m + i) = mm;
       *reinterpret_cast<float4*>(v + i) = vv;
+      if (SHADOW && (rnd || spl)) shadow4(pp, i, rnd, spl, ps, P, lmask);
     }
     // tail of a tensor whose length is not a multiple of 4 (only the last chunk has one)
     const int64_t tail = end - ((end - base) & 3);
@@ -96,12 +132,14 @@ __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_const
       float pv = p[i];
       adam1(pv, g[i], m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
       po[i] = pv;
+      if (SHADOW && (rnd || spl)) shadow1(pv, i, rnd, spl, ps, P, lmask);
     }
   } else {
     for (int64_t i = base + threadIdx.x; i < end; i += kThreads) {
       float pv = p[i];
       adam1(pv, g[i], m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
       po[i] = pv;
+      if (SHADOW && (rnd || spl)) shadow1(pv, i, rnd, spl, ps, P, lmask);
     }
   }
   // all threads of this block have read the step count (it feeds ic1/ic2 used above)
@@ -170,6 +208,17 @@ int sp_adam_multi_out(int n_tensors, float* const* host_p, float* const* host_p_
                       const float* const* host_g, float* const* host_m, float* const* host_v,
                       const int64_t* host_numel, int32_t* const* host_step, float alpha,
                       float beta1, float beta2, float eps, sp_stream_t stream) {
+  return sp_adam_multi_shadow(n_tensors, host_p, host_p_out, host_g, host_m, host_v, host_numel,
+                              host_step, nullptr, nullptr, nullptr, nullptr, alpha, beta1, beta2,
+                              eps, stream);
+}
+
+int sp_adam_multi_shadow(int n_tensors, float* const* host_p, float* const* host_p_out,
+                         const float* const* host_g, float* const* host_m, float* const* host_v,
+                         const int64_t* host_numel, int32_t* const* host_step,
+                         float* const* host_rounded, float* const* host_split,
+                         const int64_t* host_block_elems, const int32_t* host_kind, float alpha,
+                         float beta1, float beta2, float eps, sp_stream_t stream) {
   SP_REQUIRE(n_tensors >= 0, "negative tensor count");
   cudaStream_t st = sp::as_stream(stream);
   unsigned int* counters = adam_counters();
@@ -179,7 +228,7 @@ int sp_adam_multi_out(int n_tensors, float* const* host_p, float* const* host_p_
     a.count = 0;
     a.done = counters;
     int blocks = 0;
-    bool any_empty = false;
+    bool any_empty = false, shadows = false;
     // a model that would not fill the chip with 4096-element chunks gets 1024-element ones
     int64_t total = 0;
     for (int i = first; i < n_tensors && i < first + kMaxTensors; ++i)
@@ -196,6 +245,24 @@ int sp_adam_multi_out(int n_tensors, float* const* host_p, float* const* host_p_
       a.n[k] = host_numel[i] > 0 ? host_numel[i] : 0;
       any_empty = any_empty || a.n[k] == 0;
       a.step[k] = host_step[i];
+      a.rnd[k] = host_rounded ? host_rounded[i] : nullptr;
+      a.spl[k] = host_split ? host_split[i] : nullptr;
+      a.pstride[k] = 1;
+      a.parts[k] = 1;
+      a.lmask[k] = 0;
+      if (a.spl[k]) {
+        SP_REQUIRE(host_block_elems && host_kind, "split requested without layout tables");
+        SP_REQUIRE(host_block_elems[i] > 0 && a.n[k] % host_block_elems[i] == 0,
+                   "block size must divide the tensor");
+        a.pstride[k] = host_block_elems[i];
+        switch (host_kind[i]) {
+          case SP_SPLIT_RL: a.parts[k] = 2; a.lmask[k] = 0b10; break;
+          case SP_SPLIT_RLR: a.parts[k] = 3; a.lmask[k] = 0b010; break;
+          case SP_SPLIT_RRL: a.parts[k] = 3; a.lmask[k] = 0b100; break;
+          default: return sp::set_error(SP_ERR_INVALID_ARGUMENT, "adam: unknown split kind");
+        }
+      }
+      shadows = shadows || a.rnd[k] || a.spl[k];
       a.block_start[k] = blocks;
       blocks += (int)((a.n[k] + a.chunk - 1) / a.chunk);
     }
@@ -205,8 +272,12 @@ int sp_adam_multi_out(int n_tensors, float* const* host_p, float* const* host_p_
       // beta as the double nearest to what the caller wrote (0.9f -> 0.9), like the reference
       const double b1 = strtod_round(beta1);
       const double b2 = strtod_round(beta2);
-      sp::launch_pdl(adam_multi_kernel, dim3(blocks), dim3(kThreads), 0, st, a, alpha, (float)b1, (float)b2,
-                                                     (float)log(b1), (float)log(b2), eps);
+      if (shadows)
+        sp::launch_pdl(adam_multi_kernel<true>, dim3(blocks), dim3(kThreads), 0, st, a, alpha,
+                       (float)b1, (float)b2, (float)log(b1), (float)log(b2), eps);
+      else
+        sp::launch_pdl(adam_multi_kernel<false>, dim3(blocks), dim3(kThreads), 0, st, a, alpha,
+                       (float)b1, (float)b2, (float)log(b1), (float)log(b2), eps);
       SP_CHECK_LAUNCH("adam_multi");
     }
     if (any_empty || blocks == 0) {

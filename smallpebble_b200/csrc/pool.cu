@@ -21,6 +21,12 @@ struct PoolGeom {
   // backward only: round the stored gradient to the nearest TF32 value (it is an operand of
   // the conv filter / data gradient contractions; sp_set_tf32_output_rounding)
   int rnd;
+  // forward only (fixed-window kernels): also write the TF32 (r, l) split of y in the layout
+  // sp_tf32_split would give it (tf32.cu) -- the operand form of an error-compensated conv2d
+  // that consumes y -- or null
+  float* split;
+  int64_t ps;
+  int parts, lmask;
 };
 
 __device__ __forceinline__ float lrelu(float v, float alpha) { return v > 0.f ? v : alpha * v; }
@@ -130,6 +136,14 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_vec4_fixed(const float* 
       reinterpret_cast<float4*>(y)[o] = best;
       reinterpret_cast<uchar4*>(idx)[o] =
           make_uchar4((unsigned char)b0, (unsigned char)b1, (unsigned char)b2, (unsigned char)b3);
+      if (g.split) {
+        const float4 r = make_float4(rna_tf32(best.x), rna_tf32(best.y), rna_tf32(best.z), rna_tf32(best.w));
+        const float4 l = make_float4(best.x - r.x, best.y - r.y, best.z - r.z, best.w - r.w);
+        const int64_t i = 4 * o, srow = i / g.ps, j = i - srow * g.ps;
+        float* d = g.split + srow * g.parts * g.ps + j;
+        for (int q = 0; q < g.parts; ++q)
+          *reinterpret_cast<float4*>(d + q * g.ps) = ((g.lmask >> q) & 1) ? l : r;
+      }
     }
   }
 }
@@ -357,12 +371,34 @@ extern "C" {
 
 static int maxpool2d_fwd_impl(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C,
                               int KH, int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW,
-                              int leaky, float alpha, sp_stream_t stream) {
-  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, leaky, alpha, 0};
+                              int leaky, float alpha, sp_stream_t stream, float* split = nullptr,
+                              int64_t block_elems = 0, int kind = 0) {
+  PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, leaky, alpha, 0, nullptr, 1, 1, 0};
   if (int rc = check(g)) return rc;
   const int64_t outs = (int64_t)N * OH * OW * C;
   if (outs == 0) return 0;
   cudaStream_t st = sp::as_stream(stream);
+  if (split) {
+    const bool fixed = (KH == 2 && KW == 2) || (KH == 3 && KW == 3);
+    const bool vec = C % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(split) &&
+                     (reinterpret_cast<uintptr_t>(idx) & 3) == 0 && block_elems > 0 &&
+                     block_elems % 4 == 0 && outs % block_elems == 0;
+    if (!(fixed && vec)) {
+      // no fused variant for this window / alignment: pool, then split in a second launch
+      if (int rc = maxpool2d_fwd_impl(x, y, idx, N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW,
+                                      leaky, alpha, stream))
+        return rc;
+      return sp_tf32_split(y, split, outs, block_elems, kind, stream);
+    }
+    g.split = split;
+    g.ps = block_elems;
+    switch (kind) {
+      case SP_SPLIT_RL: g.parts = 2; g.lmask = 0b10; break;
+      case SP_SPLIT_RLR: g.parts = 3; g.lmask = 0b010; break;
+      case SP_SPLIT_RRL: g.parts = 3; g.lmask = 0b100; break;
+      default: return sp::set_error(SP_ERR_INVALID_ARGUMENT, "maxpool2d: unknown split kind %d", kind);
+    }
+  }
   if (C % 4 == 0 && aligned16(x) && aligned16(y) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0) {
     const dim3 grid = row_grid(N * OH, OW * (C / 4));
     if (KH == 2 && KW == 2)
@@ -391,12 +427,21 @@ int sp_maxpool2d_leaky_fwd(const float* x, float* y, uint8_t* idx, int N, int H,
                             stream);
 }
 
+int sp_maxpool2d_fwd_split(const float* x, float* y, uint8_t* idx, float* split,
+                           int64_t block_elems, int kind, int N, int H, int W, int C, int KH,
+                           int KW, int sy, int sx, int pad_t, int pad_l, int OH, int OW, int leaky,
+                           float alpha, sp_stream_t stream) {
+  SP_REQUIRE(split != nullptr, "null split output");
+  return maxpool2d_fwd_impl(x, y, idx, N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, leaky ? 1 : 0,
+                            alpha, stream, split, block_elems, kind);
+}
+
 static int maxpool2d_bwd_impl(const float* gy, const uint8_t* idx, float* dx, const float* xl,
                               int N, int H, int W, int C, int KH, int KW, int sy, int sx,
                               int pad_t, int pad_l, int OH, int OW, int leaky, float alpha,
                               sp_stream_t stream) {
   const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, leaky, alpha,
-                   sp::g_round_tf32_outputs};
+                   sp::g_round_tf32_outputs, nullptr, 1, 1, 0};
   if (int rc = check(g)) return rc;
   const int64_t ins = (int64_t)N * H * W * C;
   if (ins == 0) return 0;

@@ -6,29 +6,40 @@
 #include "common.cuh"
 
 namespace sp {
-// One scratch buffer per device, allocated on first use (before any graph capture: the
-// first training step always runs eagerly).  The library is used from one stream per
-// process (SURVEY.md 8b "Threading"), so reuse across calls is ordered by that stream.
+// One scratch buffer per device AND LANE, allocated on first use (before any graph capture:
+// the first training steps always run eagerly; both lanes are allocated together).  All calls
+// on one stream share lane 0, ordered by that stream.  A caller that runs independent work on
+// a second stream (steady.py: the parameter-gradient kernels of the backward sweep run beside
+// the data-gradient chain) selects lane 1 for those calls with sp_set_scratch_lane().
+int g_scratch_lane = 0;
+constexpr int kLanes = 2;
 float* scratch_for_current_device() {
   static float* bufs[64] = {nullptr};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!bufs[dev]) {
-    if (cudaMalloc(&bufs[dev], kScratchFloats * sizeof(float)) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&bufs[dev], kLanes * kScratchFloats * sizeof(float)) != cudaSuccess) return nullptr;
   }
-  return bufs[dev];
+  return bufs[dev] + (size_t)g_scratch_lane * kScratchFloats;
 }
 unsigned int* sync_words_for_current_device() {
   static unsigned int* bufs[64] = {nullptr};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!bufs[dev]) {
-    if (cudaMalloc(&bufs[dev], kSyncWords * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    if (cudaMemset(bufs[dev], 0, kSyncWords * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&bufs[dev], kLanes * kSyncWords * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(bufs[dev], 0, kLanes * kSyncWords * sizeof(unsigned int)) != cudaSuccess) return nullptr;
   }
-  return bufs[dev];
+  return bufs[dev] + (size_t)g_scratch_lane * kSyncWords;
 }
 }  // namespace sp
+
+extern "C" int sp_set_scratch_lane(int lane) {
+  SP_REQUIRE(lane >= 0 && lane < sp::kLanes, "scratch lane out of range");
+  // both lanes are allocated by the first use of either: make sure that is not inside a capture
+  sp::g_scratch_lane = lane;
+  return 0;
+}
 
 namespace {
 
@@ -290,9 +301,15 @@ __global__ void __launch_bounds__(kThreads) xent_bwd_kernel(const float* __restr
 // Rows are processed four at a time per warp with all their loads issued up front: at the
 // classifier sizes of the BASELINE models ([128,10], [200,10]) the kernel is one block whose
 // run time is the number of DEPENDENT global round trips, not bandwidth.
+// GRAD (single block only): additionally writes the gradient of the loss w.r.t. the logits
+// for a unit upstream gradient, p - onehot, and its column sums -- what the backward kernels
+// below produce when the loss is the root of get_gradients (seed == 1), values and summation
+// order identical to theirs -- so that the backward sweep starts one launch later.
+template <bool GRAD>
 __global__ void __launch_bounds__(1024) softmax_xent_fwd_kernel(
     const float* __restrict__ logits, const int32_t* __restrict__ labels,
-    float* __restrict__ probs, float* __restrict__ part, int64_t rows, int64_t cols) {
+    float* __restrict__ probs, float* __restrict__ part, int64_t rows, int64_t cols,
+    float* __restrict__ dlogits, float* __restrict__ colsum) {
   pdl_entry();
   __shared__ float red[32];
   const int lane = threadIdx.x & 31;
@@ -341,6 +358,23 @@ __global__ void __launch_bounds__(1024) softmax_xent_fwd_kernel(
   }
   nll = block_sum(nll, red);
   if (threadIdx.x == 0) part[blockIdx.x] = nll;
+  if (GRAD) {
+    __syncthreads();  // probs of every row are visible to the whole (single) block
+    const int total = (int)(rows * cols), icols = (int)cols, irows = (int)rows;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int r = i / icols;
+      const int c = i - r * icols;
+      dlogits[i] = 1.f * (probs[i] - ((c == labels[r]) ? 1.f : 0.f));
+    }
+    const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    for (int c = warp; c < icols; c += warps) {
+      float acc = 0.f;
+      for (int r = lane; r < irows; r += 32)
+        acc += 1.f * (probs[r * icols + c] - ((c == labels[r]) ? 1.f : 0.f));
+      acc = warp_sum(acc);
+      if (lane == 0) colsum[c] = acc;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) softmax_xent_bwd_kernel(
@@ -572,15 +606,30 @@ int sp_softmax_xent_fwd(const float* logits, const int32_t* labels, float* probs
   const int blocks = rows <= 2048 ? 1 : sp::wave_grid(rows, kThreads / 32, 4);
   if (blocks == 1) {
     // one block so the loss needs no second pass; 32 warps = 32 rows in flight
-    sp::launch_pdl(softmax_xent_fwd_kernel, dim3(1), dim3(rows > 64 ? 1024 : kThreads), 0, st, logits, labels, probs, loss,
-                                                                      rows, cols);
+    sp::launch_pdl(softmax_xent_fwd_kernel<false>, dim3(1), dim3(rows > 64 ? 1024 : kThreads), 0, st, logits, labels, probs, loss,
+                   rows, cols, (float*)nullptr, (float*)nullptr);
   } else {
     float* part = scratch_for_current_device();
     if (!part) return sp::set_error(SP_ERR_WORKSPACE, "sp_softmax_xent_fwd: no scratch");
-    sp::launch_pdl(softmax_xent_fwd_kernel, dim3(blocks), dim3(kThreads), 0, st, logits, labels, probs, part, rows, cols);
+    sp::launch_pdl(softmax_xent_fwd_kernel<false>, dim3(blocks), dim3(kThreads), 0, st, logits, labels, probs, part, rows, cols,
+                   (float*)nullptr, (float*)nullptr);
     sp::launch_pdl(sum_partials_kernel, dim3(1), dim3(kThreads), 0, st, part, loss, blocks);
   }
   SP_CHECK_LAUNCH("softmax_xent_fwd");
+  return 0;
+}
+
+int sp_softmax_xent_fwd_grad(const float* logits, const int32_t* labels, float* probs, float* loss,
+                             float* dlogits, float* colsum, int64_t rows, int64_t cols,
+                             sp_stream_t stream) {
+  SP_REQUIRE(rows > 0 && rows <= 2048 && cols > 0 && rows * cols <= 32768,
+             "softmax_xent_fwd_grad: single-block sizes only");
+  // same block size as the backward kernel it stands in for: the column sums are summed in
+  // the same order only if the warps cover the same columns... they always do (one warp per
+  // column, lanes stride the rows), the block size just has to be >= 32
+  sp::launch_pdl(softmax_xent_fwd_kernel<true>, dim3(1), dim3(rows > 64 ? 1024 : kThreads), 0,
+                 sp::as_stream(stream), logits, labels, probs, loss, rows, cols, dlogits, colsum);
+  SP_CHECK_LAUNCH("softmax_xent_fwd_grad");
   return 0;
 }
 

@@ -15,6 +15,7 @@ from . import _abi
 from . import array as A
 from . import core
 from . import distributed as _distributed
+from . import steady as _steady
 from .array import DeviceArray
 from .core import Variable
 
@@ -45,6 +46,12 @@ class Lazy:
         return self
 
     def run(self):
+        if _steady.depth == 0 and _steady.enabled:
+            # outermost call: a root whose steps have settled is replayed from CUDA graphs
+            return _steady.run_root(self)
+        return self._run()
+
+    def _run(self):
         args = self.arguments
         if not args:
             raise AssignmentError(f"No arguments have been assigned to {self}.")
@@ -186,6 +193,26 @@ class Adam:
         variables = list(variables)
         if not variables:
             return
+        rec = getattr(gradients, "_steady", None)
+        if rec is not None and _steady.optimiser_step(self, variables, gradients, rec):
+            return  # replayed (or recorded and replayed) from the steady-state graphs
+        self._update(variables, gradients, None)
+
+    def _ensure_state(self, variables) -> None:
+        "Moments and step counters of variables seen for the first time (on the device)."
+        for v in variables:
+            if v not in self._step:
+                self.m[v] = DeviceArray.zeros(v.array.shape)
+                self.v[v] = DeviceArray.zeros(v.array.shape)
+                self._step[v] = DeviceArray.from_host(np.zeros(1, np.int32), dtype=np.int32)
+                self._step[v].ptr  # uploaded now: never inside a graph capture
+
+    def _hyper(self):
+        return (self.alpha, self.beta1, self.beta2, self.eps)
+
+    def _update(self, variables, gradients, outs) -> None:
+        """The fused update.  `outs`: static arrays to write the new parameters into (steady.py,
+        while the update is being recorded); None: fresh arrays (eager) or in place (sp.capture)."""
         grads = []
         for v in variables:
             g = gradients[v]  # KeyError when missing, like the reference
@@ -200,11 +227,7 @@ class Adam:
         ids = tuple([id(v) for v in variables])
         cached = self._static
         if cached is None or cached[0] != ids:
-            for v in variables:
-                if v not in self._step:
-                    self.m[v] = DeviceArray.zeros(v.array.shape)
-                    self.v[v] = DeviceArray.zeros(v.array.shape)
-                    self._step[v] = DeviceArray.from_host(np.zeros(1, np.int32), dtype=np.int32)
+            self._ensure_state(variables)
             cached = self._static = (
                 ids,
                 _ptr_table([self.m[v].ptr for v in variables]),
@@ -217,7 +240,7 @@ class Adam:
         olds = [v._array for v in variables]
         p_tab = _cached_table(tuple([a.ptr for a in olds]))
         g_tab = _cached_table(tuple([g.ptr for g in grads]))
-        if A.capturing():
+        if A.capturing() and outs is None:
             # static buffers: update in place.  (Nothing is settled first: every buffer of a
             # captured step is overwritten by the next replay anyway, so values that were not
             # evaluated inside the captured function cannot be read afterwards -- capture.py.)
@@ -225,21 +248,55 @@ class Adam:
                                 self.beta1, self.beta2, self.eps, A.stream())
             A.note_inplace_update()
             return
-        news = [DeviceArray.empty(a.shape, A.FLOAT, a.size) for a in olds]
+        if outs is None:
+            news = [DeviceArray.empty(a.shape, A.FLOAT, a.size) for a in olds]
+        else:
+            news = outs
         o_tab = _cached_table(tuple([a._ptr for a in news]))
-        F.sp_adam_multi_out(n, p_tab, o_tab, g_tab, m_tab, v_tab, numel, step_tab, self.alpha,
-                            self.beta1, self.beta2, self.eps, A.stream())
-        # rebind (sp.py:583) and give the new arrays the TF32 shadows the contractions asked of
-        # the old ones (rounded copy for the data gradients, split copy for the compensated
-        # forward pass): all tensors in one launch instead of one per weight and use
-        jobs = []
-        for v, old, new in zip(variables, olds, news):
-            v._array = new
+        # The new arrays get the TF32 shadows the contractions asked of the old ones (rounded
+        # copy for the data gradients, split copy for the compensated forward pass), written
+        # by the update kernel itself; a tensor with more than one split layout gets the rest
+        # from one extra launch.
+        refresh = outs is not None
+        shadow_rows, rest_jobs = None, []
+        for i, (old, new) in enumerate(zip(olds, news)):
             want_round, kinds = A.tf32_shadow_requests(old)
-            if want_round or kinds:
-                jobs.append((new, want_round, kinds))
-        if jobs:
-            A.tf32_shadows_multi(jobs)
+            if not (want_round or kinds) or not new.size:
+                continue
+            rounded, split, rest = A.tf32_shadow_targets(new, want_round, kinds, refresh)
+            if rounded is not None or split is not None:
+                if shadow_rows is None:
+                    shadow_rows = [[None] * n, [None] * n, [1] * n, [0] * n]
+                if rounded is not None:
+                    shadow_rows[0][i] = rounded._ptr
+                if split is not None:
+                    shadow_rows[1][i] = split[0]._ptr
+                    shadow_rows[3][i], shadow_rows[2][i] = split[1], split[2]
+            if rest:
+                rest_jobs.append((new, False, rest))
+        if shadow_rows is None:
+            F.sp_adam_multi_out(n, p_tab, o_tab, g_tab, m_tab, v_tab, numel, step_tab, self.alpha,
+                                self.beta1, self.beta2, self.eps, A.stream())
+        else:
+            key = (tuple(shadow_rows[0]), tuple(shadow_rows[1]), tuple(shadow_rows[2]),
+                   tuple(shadow_rows[3]))
+            tabs = _shadow_tables.get(key)
+            if tabs is None:
+                if len(_shadow_tables) > 64:
+                    _shadow_tables.clear()
+                tabs = _shadow_tables[key] = (
+                    _ptr_table(key[0]), _ptr_table(key[1]), _abi.dims(key[2]),
+                    (C.c_int32 * n)(*key[3]))
+            F.sp_adam_multi_shadow(n, p_tab, o_tab, g_tab, m_tab, v_tab, numel, step_tab, tabs[0],
+                                   tabs[1], tabs[2], tabs[3], self.alpha, self.beta1, self.beta2,
+                                   self.eps, A.stream())
+        for v, new in zip(variables, news):
+            v._array = new  # rebind (sp.py:583)
+        if rest_jobs:
+            A.tf32_shadows_multi(rest_jobs, refresh=refresh)
+
+
+_shadow_tables = {}  # (shadow pointers, layouts) of an update -> ctypes tables
 
 
 def sgd_step(variables, gradients, learning_rate: float = 0.001) -> None:

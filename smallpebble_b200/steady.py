@@ -1,0 +1,572 @@
+"""Steady-state replay of the unchanged training loop (VERDICT r01 #2c).
+
+The README loop (README.md:310-325) is three API calls per step --
+
+    loss_val = loss.run();  gradients = sp.get_gradients(loss_val);  adam.training_step(learnables, gradients)
+
+-- that issue the same ~20 kernels with the same shapes every iteration; on a B200 the Python
+and launch cost of issuing them (~160 us) is longer than the kernels take.  Once a root lazy
+node has been run a few times with unchanged input shapes, each of the three calls is recorded
+into a CUDA graph of its own (forward F, backward B, update U) and later calls REPLAY them:
+
+  * `root.run()`      copies the placeholder values into static input buffers, replays F and
+                      returns a fresh Variable holding a copy of the root value; its tape is
+                      the recorded one (static buffers);
+  * `get_gradients()` of that Variable replays B and returns a dict over the same buffers (the
+                      gradient of a non-learnable leaf stays deferred, as in eager mode);
+  * `Adam.training_step()` given that dict replays U.
+
+Nothing is fused or skipped: the graphs hold exactly the kernels the eager calls launch, so
+the results are bit-identical to eager mode.  Two things are done that the eager loop cannot
+afford on the host: in B the parameter-gradient kernels (conv2d wgrad, the matmul weight
+gradient, bias sums) are forked onto a second stream and run beside the data-gradient chain
+they do not feed (joined before B ends), and all launch overhead disappears.
+
+Reference semantics that are kept: Adam REBINDS `variable.array` every step (sp.py:583) -- U
+writes the new parameters into the arrays of two steps ago (two recordings per root, keyed by
+the parameter buffers they read), so whatever still reads the step's own weights after the
+update (the deferred leaf gradient) sees the right values.  What changes: arrays reachable
+from a step's results, other than the root value itself, are overwritten by the next `run()`
+of the same root (hold `np.asarray(...)` copies instead), and a parameter array object comes
+round again every second step.  Any deviation from the recorded pattern -- new shapes, a
+rebound parameter, another optimiser, changed precision / fusion settings -- falls back to the
+eager path for that call and re-records when the steps have settled again.
+`sp.set_steady_replay(False)` or SP_STEADY=0 turns the whole mechanism off.
+"""
+
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import _abi
+from . import array as A
+from .array import DeviceArray
+
+F = _abi.f
+
+enabled = os.environ.get("SP_STEADY", "1") != "0"
+fork_leaf_grads = os.environ.get("SP_STEADY_FORK", "1") != "0"
+depth = 0            # > 0 while a root is being evaluated (nested Lazy.run calls are plain)
+update_count = 0     # replayed optimiser steps (they write into recycled parameter buffers)
+config_epoch = 0     # bumped by anything that changes which kernels an op launches
+WARM_STEPS = int(os.environ.get("SP_STEADY_WARM", "3"))
+MAX_RECORDS = 8      # recordings per root before it stays eager for good
+stats = {"records": 0, "replays_f": 0, "replays_b": 0, "replays_u": 0, "aborted": 0}
+
+
+def set_enabled(flag: bool) -> None:
+    global enabled
+    enabled = bool(flag)
+
+
+def invalidate() -> None:
+    """Settings changed (precision, fusion, kernel policy, data-parallel set-up): recordings
+    made before hold other kernels."""
+    global config_epoch
+    config_epoch += 1
+
+
+class _Record:
+    """One recording of a root: the graphs that read ONE set of parameter buffers."""
+
+    __slots__ = ("root_state", "key", "pool", "placeholders", "static_inputs", "static_values",
+                 "param_arrays", "shadow_refs", "graph_f", "kernels_f", "root", "epoch",
+                 "graph_b", "kernels_b", "grads", "b_epoch", "side", "graph_u", "kernels_u",
+                 "u_vars", "u_opt", "u_hyper", "u_outs", "u_refreshed", "user_inputs", "keep")
+
+    def __init__(self):
+        self.graph_b = self.graph_u = None
+        self.epoch = 0
+        self.b_epoch = -1
+        self.keep = []
+
+
+class _RootState:
+    __slots__ = ("placeholders", "params", "others", "eligible", "sig", "streak", "records",
+                 "n_records", "dead", "pool")
+
+    def __init__(self, root):
+        from .core import Variable
+        from .graph import Placeholder
+
+        self.placeholders, self.params, self.others = [], [], []
+        self.eligible = True
+        seen = set()
+
+        def walk(node):
+            if id(node) in seen:
+                return
+            seen.add(id(node))
+            if isinstance(node, Placeholder):
+                self.placeholders.append(node)
+                return
+            for child in getattr(node, "arguments", ()):
+                if hasattr(child, "run"):
+                    walk(child)
+                elif isinstance(child, Variable):
+                    if id(child) not in seen:
+                        seen.add(id(child))
+                        self.params.append(child)
+                elif isinstance(child, (DeviceArray, np.ndarray)):
+                    self.eligible = False  # a raw array baked into the graph: stay eager
+                # plain Python values (ints, strings) are part of the function: ignored
+
+        walk(root)
+        if not self.placeholders:
+            self.eligible = False
+        self.sig = None
+        self.streak = 0
+        self.records = {}
+        self.n_records = 0
+        self.dead = False
+        self.pool = None
+
+
+def _input_signature(state):
+    from .core import Variable
+
+    sig = []
+    for ph in state.placeholders:
+        args = ph.arguments
+        if len(args) != 1:
+            return None
+        v = args[0]
+        if isinstance(v, Variable):
+            a = v._array
+            if a._thunk is not None or v.local_gradients:
+                return None  # the result of an op: its tape would have to be recorded too
+            sig.append((0, a.shape, a.dtype.str))
+        elif type(v) is DeviceArray:
+            if v._thunk is not None:
+                return None
+            sig.append((1, v.shape, v.dtype.str))
+        elif isinstance(v, np.ndarray) and v.dtype.kind in "iu":
+            sig.append((2, v.shape, v.dtype.str))  # integer labels / indices
+        else:
+            return None
+    return tuple(sig)
+
+
+def _eager(root):
+    global depth
+    depth += 1
+    try:
+        return root._run()
+    finally:
+        depth -= 1
+
+
+def run_root(root):
+    """`root.run()` called from user code (not from inside another run)."""
+    state = root.__dict__.get("_steady_state")
+    if state is None:
+        state = root.__dict__["_steady_state"] = _RootState(root)
+    if state.dead or not state.eligible or not A.device_ready() or A.capturing():
+        return _eager(root)
+    from . import distributed
+
+    if distributed.is_initialized() and distributed.world_size() > 1 and not _dp_ok:
+        return _eager(root)
+    sig = _input_signature(state)
+    if sig is None:
+        state.streak = 0
+        return _eager(root)
+    sig = (sig, config_epoch)
+    if sig != state.sig:
+        if state.sig is not None and state.sig[1] != config_epoch:
+            state.records.clear()  # other kernels now
+        state.sig = sig
+        state.streak = 0
+    ptrs = tuple([p._array._ptr for p in state.params])
+    if None in ptrs:
+        return _eager(root)
+    key = (sig, ptrs)
+    rec = state.records.get(key)
+    if rec is not None:
+        if _shadows_intact(rec):
+            return _replay_forward(rec)
+        del state.records[key]
+        state.streak = 0
+    state.streak += 1
+    if state.streak <= WARM_STEPS or A.capturing():
+        return _eager(root)
+    if state.n_records >= MAX_RECORDS:
+        state.dead = True
+        return _eager(root)
+    try:
+        rec = _record_forward(root, state, key)
+    except _Abort:
+        stats["aborted"] += 1
+        state.dead = True
+        return _eager(root)
+    return _replay_forward(rec)
+
+
+_dp_ok = os.environ.get("SP_STEADY_DP", "0") == "1"
+
+
+class _Abort(Exception):
+    pass
+
+
+def _shadows_intact(rec) -> bool:
+    """The TF32 shadows (rounded / split copies) of the parameters that the recorded kernels
+    read must still be the arrays' current shadows (U refreshes exactly those)."""
+    for arr, rounded, splits in rec.shadow_refs:
+        sh = arr._shadow
+        if sh is None:
+            if rounded is not None or splits:
+                return False
+            continue
+        if sh[0] != A.inplace_epoch or (rounded is not None and sh[1] is not rounded):
+            return False
+        cur = sh[2]
+        for k, v in splits:
+            if cur.get(k) is not v:
+                return False
+    return True
+
+
+def _snapshot_shadows(arrays):
+    refs = []
+    for arr in arrays:
+        sh = arr._shadow
+        if sh is None or sh[0] != A.inplace_epoch:
+            refs.append((arr, None, ()))
+        else:
+            refs.append((arr, sh[1], tuple(sh[2].items())))
+    return refs
+
+
+# --------------------------------------------------------------------------------------------
+# forward
+# --------------------------------------------------------------------------------------------
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _capture(pool, fn):
+    """Record fn() into a CUDA graph allocated from `pool`.  Returns (graph, result, kernels)."""
+    torch = _torch()
+    graph = torch.cuda.CUDAGraph()
+    launches0 = _abi.counter.launches
+    try:
+        with A.pool_bypass():
+            with torch.cuda.graph(graph, pool=pool):
+                result = fn()
+    except Exception as exc:  # noqa: BLE001 - anything that cannot be captured: stay eager
+        try:
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001
+            pass
+        if os.environ.get("SP_STEADY_DEBUG") == "1":
+            raise
+        raise _Abort(str(exc)) from exc
+    return graph, result, _abi.counter.launches - launches0
+
+
+def _record_forward(root, state, key):
+    from .capture import _static_like
+    from .core import Variable
+
+    torch = _torch()
+    if state.pool is None:
+        state.pool = torch.cuda.graph_pool_handle()
+    rec = _Record()
+    rec.root_state = state
+    rec.key = key
+    rec.pool = state.pool
+    rec.placeholders = list(state.placeholders)
+    rec.param_arrays = [p._array for p in state.params]
+    user_values = [ph.arguments[0] for ph in rec.placeholders]
+    rec.static_inputs, rec.static_values = [], []
+    with A.pool_bypass():
+        for v in user_values:
+            src = v._array if isinstance(v, Variable) else v
+            static = _static_like(src)
+            rec.static_inputs.append(static)
+            rec.static_values.append(Variable(static) if isinstance(v, Variable) else static)
+    global depth
+    for ph, sv in zip(rec.placeholders, rec.static_values):
+        ph.arguments = [sv]
+    depth += 1
+    try:
+        def forward():
+            r = root._run()
+            if isinstance(r, Variable) and r._array._ptr is None and r._array._thunk is not None:
+                r._array.ptr  # a deferred root value: launched here, as reading it would
+            return r
+
+        rec.graph_f, rec.root, rec.kernels_f = _capture(rec.pool, forward)
+    finally:
+        depth -= 1
+        for ph, uv in zip(rec.placeholders, user_values):
+            ph.arguments = [uv]
+    if not isinstance(rec.root, Variable) or rec.root._array._thunk is not None:
+        raise _Abort("root value is not a launched Variable")
+    rec.shadow_refs = _snapshot_shadows(rec.param_arrays)
+    state.records[key] = rec
+    state.n_records += 1
+    stats["records"] += 1
+    return rec
+
+
+def _feed(dst: DeviceArray, value) -> None:
+    """Bring a placeholder value into its static buffer."""
+    from .capture import _copy_into
+    from .core import Variable
+
+    src = value._array if isinstance(value, Variable) else value
+    if type(src) is DeviceArray and src._ptr is None and src._thunk is None and src._host is not None:
+        # host data that has not been uploaded yet: upload straight into the static buffer,
+        # and let the user's array share it (valid until the next run of this root)
+        host = src._host
+        if host.size:
+            if host.dtype != dst.dtype:
+                A.upload_f64_narrowed(host, dst.ptr)
+            else:
+                F.sp_memcpy_h2d(dst.ptr, host.ctypes.data, host.nbytes, A.stream())
+                A._counters["h2d_bytes"] += host.nbytes
+                if host.ctypes.data in A._pinned.owned:
+                    A._pinned.release(host)
+                elif host.nbytes >= A._PIN_THRESHOLD:
+                    A._keep_alive_until_copied(host)
+        src._buf, src._ptr, src._host = dst._buf, dst._ptr, None
+        return
+    _copy_into(dst, src)
+
+
+def _replay_forward(rec):
+    from .core import Variable
+
+    user_values = [ph.arguments[0] for ph in rec.placeholders]
+    for dst, v in zip(rec.static_inputs, user_values):
+        _feed(dst, v)
+    rec.graph_f.replay()
+    _abi.counter.launches += rec.kernels_f
+    stats["replays_f"] += 1
+    rec.epoch += 1
+    rec.user_inputs = user_values
+    static_root = rec.root
+    value = static_root._array
+    out = DeviceArray.empty(value.shape, value.dtype, value.size)
+    if value.size:
+        F.sp_memcpy_d2d(out._ptr, value._ptr, value.nbytes, A.stream())
+    out._tf32 = value._tf32
+    fresh = Variable.__new__(Variable)
+    fresh._array = out
+    fresh.local_gradients = static_root.local_gradients
+    fresh._serial = static_root._serial
+    fresh._steady = (rec, rec.epoch, update_count)
+    return fresh
+
+
+# --------------------------------------------------------------------------------------------
+# backward
+# --------------------------------------------------------------------------------------------
+
+
+def gradients_of(variable, tag):
+    """`get_gradients(variable)` for a Variable returned by a replayed run, or None to take the
+    eager path."""
+    from . import core
+
+    rec, epoch, updates = tag
+    if rec.epoch != epoch or update_count - updates > 1:
+        # (the second update after a forward pass writes into the parameter buffers it read)
+        raise RuntimeError(
+            "get_gradients: this result belongs to an earlier run() of its lazy graph; the "
+            "steady-state replay has since overwritten the tape's buffers (call get_gradients "
+            "before the next run(), or sp.set_steady_replay(False))")
+    state = rec.root_state
+    if state.sig is None or state.sig[1] != config_epoch or state.records.get(rec.key) is not rec:
+        return None
+    if rec.graph_b is None:
+        try:
+            _record_backward(rec)
+        except _Abort:
+            stats["aborted"] += 1
+            state.dead = True
+            state.records.pop(rec.key, None)
+            return None
+    rec.graph_b.replay()
+    _abi.counter.launches += rec.kernels_b
+    stats["replays_b"] += 1
+    rec.b_epoch = epoch
+    static = rec.grads
+    out = core.Gradients()
+    remap = {}
+    for sv, uv in zip(rec.static_values, rec.user_inputs):
+        if isinstance(sv, core.Variable) and isinstance(uv, core.Variable):
+            remap[sv] = uv
+    remap[rec.root] = variable
+    for k, v in dict.items(static):
+        dict.__setitem__(out, remap.get(k, k), v)
+    if static._deferred:
+        out._deferred = {remap.get(k, k): list(v) for k, v in static._deferred.items()}
+    out._steady = (rec, epoch, updates)
+    return out
+
+
+def _record_backward(rec):
+    from . import core
+
+    torch = _torch()
+    side = rec.side = torch.cuda.Stream() if fork_leaf_grads else None
+    forked = []
+
+    def fork(fn, path_value):
+        """Run a parameter-gradient closure on the side stream (a branch of the graph)."""
+        if type(path_value) is DeviceArray and path_value._ptr is None:
+            path_value.ptr  # produced on the main stream: both branches read it
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        F.sp_set_scratch_lane(1)
+        try:
+            with torch.cuda.stream(side):
+                value = fn(path_value)
+                if type(value) is DeviceArray and value._ptr is None:
+                    value.ptr
+        finally:
+            F.sp_set_scratch_lane(0)
+        forked.append(value)
+        return value
+
+    def body():
+        core._leaf_fork = fork if side is not None else None
+        try:
+            grads = core._get_gradients(rec.root)
+        finally:
+            core._leaf_fork = None
+        if forked:
+            done = torch.cuda.Event()
+            done.record(side)
+            torch.cuda.current_stream().wait_event(done)
+        return grads
+
+    rec.graph_b, rec.grads, rec.kernels_b = _capture(rec.pool, body)
+
+
+# --------------------------------------------------------------------------------------------
+# update
+# --------------------------------------------------------------------------------------------
+
+
+def optimiser_step(opt, variables, gradients, tag) -> bool:
+    """`opt.training_step(variables, gradients)` with a gradient dict from a replayed backward
+    pass.  True: done (replayed); False: the caller runs the eager update."""
+    global update_count
+    rec, epoch, updates = tag
+    if rec.epoch != epoch or rec.b_epoch != epoch or update_count != updates:
+        return False
+    state = rec.root_state
+    if state.records.get(rec.key) is not rec or state.sig[1] != config_epoch:
+        return False
+    if rec.graph_u is None:
+        if A.capturing():
+            return False
+        if not _u_eligible(rec, variables):
+            state.dead = True  # this loop updates something the recordings are not keyed by
+            state.records.clear()
+            return False
+        try:
+            _record_update(rec, opt, variables, gradients)
+        except _Abort:
+            stats["aborted"] += 1
+            state.dead = True
+            state.records.pop(rec.key, None)
+            return False
+    elif (opt is not rec.u_opt or opt._hyper() != rec.u_hyper or len(variables) != len(rec.u_vars)
+          or any(a is not b for a, b in zip(variables, rec.u_vars))):
+        return False
+    for v, g in zip(rec.u_vars, rec.keep):
+        if dict.get(gradients, v) is not g:
+            return False  # somebody replaced a gradient in the dict: eager update
+    rec.graph_u.replay()
+    update_count += 1
+    _abi.counter.launches += rec.kernels_u
+    stats["replays_u"] += 1
+    rec.b_epoch = -1  # one update per backward pass
+    for v, out, refreshed in zip(rec.u_vars, rec.u_outs, rec.u_refreshed):
+        v._array = out
+        sh = out._shadow
+        if sh is not None and sh[0] == A.inplace_epoch:
+            # shadows the graph does not refresh describe the array's previous contents
+            has_round, kinds = refreshed
+            if sh[1] is not None and not has_round:
+                sh[1] = None
+            if len(sh[2]) != len(kinds):
+                for k in [k for k in sh[2] if k not in kinds]:
+                    del sh[2][k]
+        out._aux = None
+    return True
+
+
+def _u_eligible(rec, variables) -> bool:
+    """Every updated variable must be one of the parameters the recording is keyed by (its
+    buffer identity is what selects the recording next time)."""
+    params = rec.root_state.params
+    ids = {id(p) for p in params}
+    if len({id(v) for v in variables}) != len(variables):
+        return False
+    if any(id(v) not in ids for v in variables):
+        return False
+    return all(v._array._ptr is not None for v in variables)
+
+
+def _record_update(rec, opt, variables, gradients):
+    state = rec.root_state
+    params = state.params
+    index = {id(p): i for i, p in enumerate(params)}
+    # write into the parameter arrays of another recording of this root (the buffers of two
+    # steps ago: nothing reads them any more), else into new static arrays
+    donor = None
+    for other in state.records.values():
+        if other is rec or other.key[0] != rec.key[0]:
+            continue  # (recordings of other input shapes read the same parameters)
+        taken = any(r.graph_u is not None and r is not other and
+                    all(o is other.param_arrays[index[id(v)]] for o, v in zip(r.u_outs, r.u_vars))
+                    for r in state.records.values())
+        if not taken and all(other.param_arrays[index[id(v)]].shape == v._array.shape
+                             for v in variables):
+            donor = other
+            break
+    if donor is not None:
+        outs = [donor.param_arrays[index[id(v)]] for v in variables]
+    else:
+        with A.pool_bypass():
+            outs = [DeviceArray.empty(v._array.shape, A.FLOAT, v._array.size) for v in variables]
+    olds = [v._array for v in variables]
+    # the shadows the update (re)computes for the arrays it writes: those its inputs have
+    refreshed = []
+    for old in olds:
+        want_round, kinds = A.tf32_shadow_requests(old)
+        refreshed.append((bool(want_round), frozenset(kinds)))
+    # eager once: creates the optimiser state (moments, step counters) outside the capture --
+    # no: that would advance the step.  State creation is host-side only (zeros are launched),
+    # so create it here explicitly.
+    opt._ensure_state(variables)
+    _torch().cuda.synchronize()
+
+    def body():
+        opt._update(variables, gradients, outs)
+
+    try:
+        rec.graph_u, _, rec.kernels_u = _capture(rec.pool, body)
+    finally:
+        for v, old in zip(variables, olds):
+            v._array = old  # the capture only recorded: the replay below applies the step
+    rec.u_vars = list(variables)
+    rec.u_opt = opt
+    rec.u_hyper = opt._hyper()
+    rec.u_outs = outs
+    rec.keep = [dict.get(gradients, v) for v in variables]
+    rec.u_refreshed = refreshed
