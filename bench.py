@@ -20,6 +20,14 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:]:
+    # The CPU arm uses every host core for np.matmul whatever launched it: torchrun exports
+    # OMP_NUM_THREADS=1 to its workers, which would quietly make the baseline 20-25 % slower
+    # than the same command run directly.  (Must happen before NumPy loads OpenBLAS.)
+    _cores = str(os.cpu_count() or 1)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = _cores
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -31,6 +39,7 @@ METRIC = "train_images_per_sec"
 UNIT = "images/s"
 L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
 RESIDENT_BATCHES = 96       # x 1.57 MB fp32 = 151 MB of inputs: larger than the 126 MB L2
+REGIONS = 5                 # timed regions of K steps each (median reported)
 WARMUP_FLOOR = int(os.environ.get("SP_BENCH_WARMUP_FLOOR", "25"))           # untimed steps run directly before the timed region (see below)
 
 
@@ -69,23 +78,44 @@ def time_cpu_port(steps: int, warmup: int, batch: int = BATCH_PER_GPU):
     return batch * len(times) / sum(times), times
 
 
+def blas_threads() -> int:
+    """Threads NumPy's BLAS actually uses in this process."""
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = [int(p.get("num_threads", 0)) for p in threadpool_info() if p.get("user_api") == "blas"]
+        if n:
+            return max(n)
+    except Exception:  # noqa: BLE001
+        pass
+    return int(os.environ.get("OPENBLAS_NUM_THREADS", os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)))
+
+
+def base_config(world: int) -> dict:
+    """The workload keys both arms report (the driver compares them)."""
+    return {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU * world,
+            "batch_per_gpu": BATCH_PER_GPU, "parallelism": f"dp{world}", "optimizer": "Adam(1e-3)",
+            "image": "32x32x3"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
     ips, times = time_cpu_port(args.steps, args.warmup)
     cores = os.cpu_count() or 1
+    threads = blas_threads()
     sample = (f"{args.steps} timed + {args.warmup} warm-up reference-style steps of the same "
               f"workload at batch {BATCH_PER_GPU}, float64 NumPy ({np.__version__}); np.matmul "
-              f"uses OpenBLAS threads on all {cores} visible cores, every other op one core")
+              f"runs on {threads} BLAS threads ({cores} visible cores), every other op on one core")
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU,
-                   "note": "CPU arm does not shard: one process, batch 128"},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": dict(base_config(1), note="the CPU arm does not shard: one process, batch "
+                                            f"{BATCH_PER_GPU}, whatever --gpus says"),
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -101,7 +131,7 @@ def run_reference_arm(args):
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region by a background thread
     through NVML (pynvml, in-process: a forked `nvidia-smi -lms` poller measurably slowed the
-    launch path it was watching).  One sample every 25 ms; `mark_begin/mark_end` bracket the
+    launch path it was watching).  One sample every 4 ms; `mark_begin/mark_end` bracket the
     timed region, only samples taken inside it are reported."""
 
     # nvmlClocksEventReason* bit -> name (the ones that invalidate a measurement, + power cap)
@@ -158,7 +188,7 @@ class ClockSampler:
                 self.rows.append((float(mhz), int(why)))
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.025)
+            self._stop.wait(0.004)
 
     def stop(self):
         if self._nvml is None:
@@ -167,16 +197,24 @@ class ClockSampler:
         if self._thread is not None:
             self._thread.join(timeout=1.0)
         hi = self.hi if self.hi is not None else len(self.rows)
-        window = self.rows[self.lo:max(hi, self.lo + 1)] or self.rows[-1:]
+        window = self.rows[self.lo:hi]
+        inside = len(window)
+        if not window:
+            # the timed regions were shorter than one polling period: say so, and report the
+            # nearest sample (taken right after the last region) instead of pretending
+            window = self.rows[hi:hi + 1] or self.rows[-1:]
         reasons = set()
         for _, why in window:
             for bit, name in self.REASONS.items():
                 if why & bit:
                     reasons.add(name)
         sm = [m for m, _ in window]
+        how = ("NVML polled every 4 ms by a background thread; samples taken between the start "
+               "of the first and the end of the last timed region")
+        if not inside:
+            how += " -- NONE fell inside: the value is the first sample after the last region"
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.smax,
-                "reasons": sorted(reasons), "samples": len(sm),
-                "how": "NVML, 25 ms period, samples inside the timed region only"}
+                "reasons": sorted(reasons), "samples": inside, "how": how}
 
 
 # ------------------------------------------------------------------------------------------
@@ -356,6 +394,13 @@ def run_ours(args):
     sync_all()
 
     # ---- find the dominant kernel: one instrumented (untimed) step -------------------------
+    # (through the eager path: a replayed step makes no ABI calls that could be bracketed)
+    from smallpebble_b200 import steady
+
+    steady_default = steady.enabled
+    steady.set_enabled(False)
+    for i in range(3):
+        step_resident(i)
     _abi.prof.records.clear()
     _abi.prof.select = None
     _abi.prof.active = True
@@ -376,36 +421,61 @@ def run_ours(args):
     per_call.sort(key=lambda r: -r[0])
     top = next((r for r in per_call if algorithmic_work(r[1], r[3]) is not None), None)
     calls_per_step = len(per_call)
+    steady.set_enabled(steady_default)
     profile_summary = [
         {"call": n, "seq": s, "ms": round(ms, 4)} for ms, n, s, _ in per_call[:8]]
 
-    # ---- timed region: `value` (inputs resident in HBM) -----------------------------------
+    # ---- timed regions: `value` (inputs resident in HBM) ------------------------------------
     # The host side of the loop speeds up over its first ~25 steps (CPU clocks, warm caches,
-    # CPython's adaptive specialisation: 290 -> 200 us of issue time per step, measured by
-    # scripts/step_transient.py), so the warm-up directly in front of the timed region is at
-    # least 25 steps whatever --warmup says; the JSON reports the number actually run.
+    # CPython's adaptive specialisation; scripts/step_transient.py), and the steady-state
+    # replay (smallpebble_b200/steady.py) records its graphs during the first ~6 steps, so the
+    # warm-up directly in front of the timed regions is at least 25 steps whatever --warmup
+    # says; the JSON reports the number actually run.
     for i in range(WARMUP_FLOOR):
         step_resident(i)
     sync_all()
-    if top is not None:
-        # only the dominant ABI function is wrapped, and only every 4th step pays for events
-        _abi.prof.arm(top[1], top[2], every=4)
     _abi.prof.records.clear()
+    replay0 = dict(steady.stats)
     launches0 = _abi.counter.launches
     sampler.mark_begin()
     wall0 = time.perf_counter()
-    step_ms = timed(step_resident, args.steps)
-    host_issue_ms = timed.host_issue_ms
+    # REGIONS regions of exactly K steps each, every one inside its own CUDA-event pair;
+    # `value` is the MEDIAN region, min / max are reported beside it
+    region_ms, host_issue = [], []
+    for _ in range(REGIONS):
+        sync_all()  # barrier + synchronize on both sides of every region
+        region_ms.append(max_over_ranks(sum(timed(step_resident, args.steps))))
+        host_issue.append(timed.host_issue_ms)
     sync_all()
     wall = time.perf_counter() - wall0
     sampler.mark_end()
-    launches = _abi.counter.launches - launches0
-    top_records = list(getattr(_abi.prof, "timed_records", []))
-    _abi.prof.disarm()
+    launches = (_abi.counter.launches - launches0) // REGIONS
+    replayed = {k: steady.stats[k] - replay0[k] for k in replay0}
     clocks = sampler.stop()
-    total_ms = max_over_ranks(sum(step_ms))
+    total_ms = statistics.median(region_ms)
+    host_issue_ms = statistics.median(host_issue)
     ms_per_step = total_ms / args.steps
     value = global_batch * args.steps / (total_ms / 1e3)
+
+    # ---- the dominant kernel, timed in stream -----------------------------------------------
+    # Graph replay admits no events between kernels, so directly after the timed regions the
+    # same steps run once more through the eager path with ONLY the dominant ABI call
+    # bracketed by a CUDA-event pair (every step); its average duration feeds `roofline`.
+    top_records = []
+    if top is not None:
+        was_enabled = steady.enabled
+        steady.set_enabled(False)
+        for i in range(5):
+            step_resident(i)
+        _abi.prof.arm(top[1], top[2], every=1)
+        timed(step_resident, max(min(args.steps, 40), 8))
+        sync_all()
+        top_records = list(getattr(_abi.prof, "timed_records", []))
+        _abi.prof.disarm()
+        steady.set_enabled(was_enabled)
+        for i in range(3):
+            step_resident(i)
+        sync_all()
 
     # ---- e2e: host batch -> H2D -> step -> loss D2H, every step ----------------------------
     for i in range(max(10, WARMUP_FLOOR)):  # same untimed run-in as the `value` region
@@ -413,11 +483,14 @@ def run_ours(args):
     sync_all()
     tc = transfer_counters()
     h2d0, d2h0 = tc["h2d_bytes"], tc["d2h_bytes"]
-    e2e_ms = timed(step_e2e, args.steps)
+    e2e_regions = []
+    for _ in range(REGIONS):
+        sync_all()
+        e2e_regions.append(max_over_ranks(sum(timed(step_e2e, args.steps))))
     sync_all()
-    h2d = (tc["h2d_bytes"] - h2d0) // args.steps
-    d2h = (tc["d2h_bytes"] - d2h0) // args.steps
-    e2e_total = max_over_ranks(sum(e2e_ms))
+    h2d = (tc["h2d_bytes"] - h2d0) // (args.steps * REGIONS)
+    d2h = (tc["d2h_bytes"] - d2h0) // (args.steps * REGIONS)
+    e2e_total = statistics.median(e2e_regions)
     e2e_value = global_batch * args.steps / (e2e_total / 1e3)
 
     # ---- the same step replayed from a CUDA graph (sp.capture): extra, not the headline -------
@@ -470,6 +543,71 @@ def run_ours(args):
         sys.stderr.flush()
         os._exit(0)
 
+    # ---- the other BASELINE configs, briefly: the MNIST MLP at every N (batch 200 per GPU, the
+    # same data-parallel path), the VGG-style net at N=1 ----------------------------------------
+    extras = None
+    if not args.no_extras:
+        extras = {}
+        todo = [("mnist_mlp_784-100-100-10_b200", "mlp", 200, 100)]
+        if world == 1:
+            todo.append(("vgg6_64-64-128-128-256-256_64x64_b256", "vgg", 256, 8))
+        for key, kind, batch, steps in todo:
+            try:
+                xg, yg = workloads.synthetic_batch(kind, batch * world)
+                xb, yb = xg[rank * batch:(rank + 1) * batch], yg[rank * batch:(rank + 1) * batch]
+                w2 = workloads.BUILDERS[kind](seed=0)
+                opt = sp.Adam()
+                xd = DeviceArray.from_host(xb)
+                yd = DeviceArray.from_host(yb, dtype=np.int32)
+                xd.ptr, yd.ptr
+
+                def one(_i=0, w2=w2, opt=opt, xd=xd, yd=yd):
+                    w2.x_in.assign_value(sp.Variable(xd))
+                    w2.y_true.assign_value(yd)
+                    lv = w2.loss.run()
+                    opt.training_step(w2.learnables, sp.get_gradients(lv))
+
+                for _ in range(12):
+                    one()
+                sync_all()
+                runs = []
+                for _ in range(3):
+                    sync_all()
+                    runs.append(max_over_ranks(timed(one, steps)[0]))
+                ms = statistics.median(runs)
+                entry = {"value": batch * world * steps / (ms / 1e3), "unit": UNIT,
+                         "ms_per_step": ms / steps, "batch_per_gpu": batch, "n_gpus": world,
+                         "steps": steps, "regions_ms_per_step": [r / steps for r in runs]}
+                if kind == "vgg":
+                    # conv flops: fprop + dgrad + wgrad per layer, no dgrad for the first layer
+                    chans, hw, fl = [3, 64, 64, 128, 128, 256, 256], 64, 0.0
+                    for i in range(6):
+                        per = 2.0 * batch * hw * hw * 9 * chans[i] * chans[i + 1]
+                        fl += per * (2 if i == 0 else 3)
+                        if i % 2 == 1:
+                            hw //= 2
+                    tfs = fl * steps / (ms / 1e3) / 1e12
+                    entry.update({"conv_tflops": tfs,
+                                  "frac_of_tf32_peak": tfs / (peaks_early["bf16_tflops_sustained"] / 2),
+                                  "peak_used": "1/2 x bf16_tflops_sustained (a whole step, not "
+                                               "an isolated kernel)",
+                                  "note": "ALGORITHMIC conv2d fprop+dgrad+wgrad flops (one product "
+                                          "each: the error-compensated forward pass issues three) "
+                                          "over the whole step (elementwise / pool / Adam time "
+                                          "included in the divisor)"})
+                if kind == "mlp":
+                    # HBM bytes a step must move at least: x, the three weight matrices read
+                    # twice + gradients written + Adam's 28 B/param, activations both ways
+                    params = 784 * 100 + 100 * 100 + 100 * 10 + 210
+                    nbytes = 4.0 * (batch * 784 + 2 * params + 6 * batch * 210) + 28.0 * params
+                    entry.update({"hbm_floor_bytes": nbytes,
+                                  "frac_of_hbm_peak": nbytes / (ms / steps * 1e-3) / 1e9 / peaks_early["hbm_gbs"],
+                                  "note": "latency-bound: the floor is ~0.5 us of HBM traffic"})
+                extras[key] = entry
+                del w2, opt, xd, yd
+            except Exception as exc:  # noqa: BLE001 - an extra must never sink the headline
+                extras[key] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+
     nonlocal_refs = [graph_stats]
     if not args.no_graph:
         gstep._graphs.clear()
@@ -487,9 +625,10 @@ def run_ours(args):
         durs = [e0.elapsed_time(e1) for _, _, _, e0, e1 in top_records]
         avg_ms = sum(durs) / len(durs)
         if kind == "tensor":
-            if args.precision == "tf32":
-                peak = peaks["bf16_tflops_sustained"] / 2.0
-                peak_note = ("TF32 dense = 1/2 x bf16_tflops_sustained of " + peaks["source"])
+            if args.precision in ("tf32", "tf32x1"):
+                # a kernel timed alone with events: the burst figure applies
+                peak = peaks["bf16_tflops"] / 2.0
+                peak_note = ("TF32 dense = 1/2 x bf16_tflops (burst) of " + peaks["source"])
             else:
                 peak = 74.0  # nominal fp32 FFMA: 148 SMs x 128 lanes x 2 x 1.965 GHz
                 peak_note = "fp32 CUDA-core nominal (no measured fp32 peak)"
@@ -516,86 +655,55 @@ def run_ours(args):
             "null when the dominant kernel has no capture", "kernel": desc, "avg_launch_ms": avg_ms, "launches_timed": len(durs),
             "algorithmic_work_per_launch": work, "peak_source": peak_note,
             "share_of_step": avg_ms / ms_per_step,
-            "note": "CUDA events around the ABI call on the launch stream inside the timed "
-                    "region; includes ~2-4 us of event overhead",
+            "note": "CUDA events around the ABI call on the launch stream, every step of an "
+                    "eager pass of the same steps run directly after the timed regions (the "
+                    "timed regions replay CUDA graphs, which admit no events between kernels); "
+                    "includes ~2-4 us of event overhead; share_of_step relates it to the "
+                    "replayed step time",
         })
-
-    # ---- the other BASELINE configs, briefly (N=1 only): MNIST MLP and the VGG-style net ------
-    extras = None
-    if world == 1 and not args.no_extras:
-        extras = {}
-        for key, kind, batch, steps in (("mnist_mlp_784-100-100-10_b200", "mlp", 200, 50),
-                                        ("vgg6_64-64-128-128-256-256_64x64_b256", "vgg", 256, 8)):
-            try:
-                xb, yb = workloads.synthetic_batch(kind, batch)
-                w2 = workloads.BUILDERS[kind](seed=0)
-                opt = sp.Adam()
-                xd = DeviceArray.from_host(xb)
-                yd = DeviceArray.from_host(yb, dtype=np.int32)
-                xd.ptr, yd.ptr
-
-                def one(_i=0, w2=w2, opt=opt, xd=xd, yd=yd):
-                    w2.x_in.assign_value(sp.Variable(xd))
-                    w2.y_true.assign_value(yd)
-                    lv = w2.loss.run()
-                    opt.training_step(w2.learnables, sp.get_gradients(lv))
-
-                for _ in range(3):
-                    one()
-                torch.cuda.synchronize()
-                ms = timed(one, steps)[0]
-                entry = {"value": batch * steps / (ms / 1e3), "unit": UNIT,
-                         "ms_per_step": ms / steps, "batch": batch, "steps": steps}
-                if kind == "vgg":
-                    # conv flops: fprop + dgrad + wgrad per layer, no dgrad for the first layer
-                    chans, hw, fl = [3, 64, 64, 128, 128, 256, 256], 64, 0.0
-                    for i in range(6):
-                        per = 2.0 * batch * hw * hw * 9 * chans[i] * chans[i + 1]
-                        fl += per * (2 if i == 0 else 3)
-                        if i % 2 == 1:
-                            hw //= 2
-                    tfs = fl * steps / (ms / 1e3) / 1e12
-                    entry.update({"conv_tflops": tfs,
-                                  "frac_of_tf32_peak": tfs / (peaks_early["bf16_tflops_sustained"] / 2),
-                                  "note": "conv2d fprop+dgrad+wgrad flops only, over the whole step "
-                                          "(elementwise / pool / Adam time included in the divisor)"})
-                extras[key] = entry
-                del w2, opt, xd, yd
-            except Exception as exc:  # noqa: BLE001 - an extra must never sink the headline
-                extras[key] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     # ---- CPU baseline beside it (N=1 only) ------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         ips, times = time_cpu_port(steps=4, warmup=1)
-        cpu = {"value": ips, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+        cpu = {"value": ips, "unit": UNIT, "cores": blas_threads(), "kind": "port",
                "sample": (f"4 timed + 1 warm-up reference-style float64 NumPy steps of the same "
                           f"workload (batch {BATCH_PER_GPU}); {sum(times):.1f} s of CPU work; "
-                          "np.matmul multi-threaded (OpenBLAS), all other ops single-threaded")}
+                          f"np.matmul on {blas_threads()} BLAS threads ({os.cpu_count()} visible "
+                          "cores), all other ops single-threaded")}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {
-            "workload": WORKLOAD, "global_batch": global_batch, "batch_per_gpu": BATCH_PER_GPU,
-            "parallelism": f"dp{world}", "optimizer": "Adam(1e-3)", "image": "32x32x3",
-            "l2": f"inputs larger than L2: every step reads a different one of "
+        "config": dict(
+            base_config(world),
+            l2=f"inputs larger than L2: every step reads a different one of "
                   f"{RESIDENT_BATCHES} resident batches ({RESIDENT_BATCHES * x_host.size * 4 >> 20}"
                   f" MiB fp32 per GPU); L2 also flushed ({L2_FLUSH_BYTES >> 20} MiB memset) before "
                   "the timed region",
-            "timing": "one CUDA-event pair on the launch stream around exactly K consecutive "
-                      "steps (training steady state: host issue overlaps device execution); "
-                      "max over ranks",
-            "extra_warmup_steps": WARMUP_FLOOR,
-            "extra_warmup_note": "untimed steps run directly before each timed region on top of "
-                                 "--warmup: the host side of the loop needs ~25 steps to reach "
-                                 "its steady issue rate (scripts/step_transient.py)",
-            "e2e_input": "float64 NumPy batches in pinned host memory, one H2D per step; "
-                         "np.isnan(loss) read back every step (README.md:319)",
-            "input_image_gradient": "deferred (computed only if read; the loop never reads it)",
-        },
+            timing=f"{REGIONS} regions of exactly K consecutive steps, each inside one CUDA-event "
+                   "pair on the launch stream with barrier + synchronize on both sides (training "
+                   "steady state: host issue overlaps device execution); max over ranks per "
+                   "region; value = the MEDIAN region",
+            extra_warmup_steps=WARMUP_FLOOR,
+            extra_warmup_note="untimed steps run directly before the timed regions on top of "
+                              "--warmup: the host side of the loop needs ~25 steps to reach its "
+                              "steady issue rate and the steady-state replay records its CUDA "
+                              "graphs during the first ~6",
+            e2e_input="float64 NumPy batches in pinned host memory, one H2D per step; "
+                      "np.isnan(loss) read back every step (README.md:319)",
+            input_image_gradient="deferred (computed only if read; the loop never reads it)",
+            step_execution="unchanged README loop; after a few identical steps run() / "
+                           "get_gradients() / Adam.training_step() replay three CUDA graphs of "
+                           "the same kernels (smallpebble_b200/steady.py)",
+        ),
         "clocks": clocks,
+        "regions": {"ms_per_step": [r / args.steps for r in region_ms],
+                    "min_ms_per_step": min(region_ms) / args.steps,
+                    "max_ms_per_step": max(region_ms) / args.steps,
+                    "e2e_ms_per_step": [r / args.steps for r in e2e_regions]},
+        "steady_replay": {"enabled": bool(steady.enabled), "graph_replays_in_timed_regions": replayed},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_total / args.steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
@@ -620,7 +728,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SP_PRECISION", "tf32"),
-                    choices=["tf32", "fp32"])
+                    choices=["tf32", "tf32x1", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay extra")
     ap.add_argument("--no-extras", action="store_true",

@@ -297,6 +297,17 @@ int sp_set_tf32_output_rounding(int on);
 /* *plan = SP_X3_*: how sp_conv2d_fprop of this geometry is run error-compensated */
 int sp_conv2d_x3_plan(const sp_conv_geom* g, int* plan);
 
+/* ---- gradient all-reduce of the data-parallel path (no reference counterpart:
+ * the reference is single-process).  NCCL is bound at run time (dlopen; an already loaded copy
+ * is reused, `path` / SP_NCCL_LIB name one explicitly).  Rank 0 creates the 128-byte id, every
+ * rank receives it by any transport and joins; the all-reduce is in place, stream-ordered and
+ * capturable in a CUDA graph. ------------------------------------------------------------ */
+int sp_nccl_load(const char* path);
+int sp_nccl_unique_id(void* out128);
+int sp_nccl_init(const void* unique_id128, int nranks, int rank, void** comm_out);
+int sp_allreduce_sum_f32(void* comm, float* buf, int64_t count, sp_stream_t stream);
+int sp_nccl_destroy(void* comm);
+
 /* ---- optimisers (sp.py:552-583 Adam, 645-653 SGD), multi-tensor ---------------------- */
 /* All pointer tables are HOST arrays of device pointers (passed by value to the kernel).
  * host_step[i] points to a DEVICE int32 holding the number of completed steps of tensor i;

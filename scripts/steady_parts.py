@@ -13,6 +13,8 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "cnn"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else {"cnn": 128, "mlp": 200, "vgg": 256}[kind]
 if len(sys.argv) > 3:
     sp.set_precision(sys.argv[3])
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    sp.distributed.init()
 x, y = workloads.synthetic_batch(kind, batch)
 wl = workloads.BUILDERS[kind](seed=0)
 adam = sp.Adam()
@@ -31,5 +33,32 @@ def timeit(graph, n=200):
     for _ in range(n): graph.replay()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
-print(f"{kind} b{batch} {sp.get_precision()}: F {timeit(rec.graph_f):.1f} us ({rec.kernels_f} calls)  "
-      f"B {timeit(rec.graph_b):.1f} us ({rec.kernels_b} calls)  U {timeit(rec.graph_u):.1f} us ({rec.kernels_u} calls)")
+tf_, tb_, tu_ = timeit(rec.graph_f), timeit(rec.graph_b), timeit(rec.graph_u)  # every rank
+if int(os.environ.get("RANK", "0")) == 0:
+    print(f"{kind} b{batch} {sp.get_precision()}: F {tf_:.1f} us ({rec.kernels_f} calls)  "
+          f"B {tb_:.1f} us ({rec.kernels_b} calls)  U {tu_:.1f} us ({rec.kernels_u} calls)")
+
+import time
+def loop(n=300):
+    for i in range(20):
+        wl.x_in.assign_value(sp.Variable(xd)); wl.y_true.assign_value(yd)
+        lv = wl.loss.run(); adam.training_step(wl.learnables, sp.get_gradients(lv))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter(); e0.record()
+    tf = tb = tu = 0.0
+    for i in range(n):
+        wl.x_in.assign_value(sp.Variable(xd)); wl.y_true.assign_value(yd)
+        a = time.perf_counter(); lv = wl.loss.run(); b = time.perf_counter()
+        g = sp.get_gradients(lv); c = time.perf_counter()
+        adam.training_step(wl.learnables, g); d = time.perf_counter()
+        tf += b - a; tb += c - b; tu += d - c
+    host = time.perf_counter() - t0
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3, host / n * 1e6, tf / n * 1e6, tb / n * 1e6, tu / n * 1e6
+r = loop()
+if int(os.environ.get("RANK", "0")) == 0:
+    print("loop: %.1f us/step device, host %.1f us/step (run %.1f, get_gradients %.1f, adam %.1f)" % r)
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    sp.distributed.barrier()
+    os._exit(0)

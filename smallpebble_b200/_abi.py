@@ -108,6 +108,11 @@ SIGNATURES = {
                                        p_i64, p_i64, C.POINTER(C.c_int32), vp]),
     "sp_set_tf32_output_rounding": (C.c_int, [C.c_int]),
     "sp_conv2d_x3_plan": (C.c_int, [C.POINTER(ConvGeom), C.POINTER(C.c_int)]),
+    "sp_nccl_load": (C.c_int, [C.c_char_p]),
+    "sp_nccl_unique_id": (C.c_int, [vp]),
+    "sp_nccl_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "sp_allreduce_sum_f32": (C.c_int, [vp, vp, i64, vp]),
+    "sp_nccl_destroy": (C.c_int, [vp]),
     "sp_pack_multi": (C.c_int, [C.c_int, C.POINTER(vp), p_i64, p_i64, vp, vp]),
 }
 
@@ -120,7 +125,8 @@ _LAUNCHING = {
                  "sp_debug_tma2_trace", "sp_host_is_pinned", "sp_stream_create", "sp_event_create",
                  "sp_event_record", "sp_stream_wait_event", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
                  "sp_conv2d_wgrad_workspace", "sp_set_tf32_output_rounding", "sp_conv2d_x3_plan",
-                 "sp_set_scratch_lane")
+                 "sp_set_scratch_lane", "sp_nccl_load", "sp_nccl_unique_id", "sp_nccl_init",
+                 "sp_allreduce_sum_f32", "sp_nccl_destroy")
 }
 
 

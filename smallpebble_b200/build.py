@@ -86,7 +86,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             fh.write(f"==== {os.path.basename(obj)}\n{log}\n")
     objs = [o for o, _ in results]
     cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-cudart", "static"]
+           "-Xcompiler", "-fPIC", "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -194,12 +194,13 @@ class Gradients(dict):
     reference returns (sp.py:87), but a training loop that only reads the learnables'
     gradients never pays for the image gradient.  SP_EAGER_LEAF_GRADS=1 disables deferral."""
 
-    __slots__ = ("_deferred", "_steady")
+    __slots__ = ("_deferred", "_steady", "_reduced")
 
     def __init__(self):
         super().__init__()
         self._deferred = {}
         self._steady = None  # steady.py: (recording, epoch) of a replayed backward pass
+        self._reduced = False  # steady.py, data parallel: already summed over the ranks
 
     # plain dict access for get_gradients' own sweep (no deferred-leaf handling)
     get_plain = dict.get
@@ -364,6 +365,7 @@ def _get_gradients(variable: Variable) -> dict:
                                 _accumulate(gradients, owned, child, value)
                             return get(child)
 
+                        job.child = child
                         fork(job, path_value)
                         continue
                 elif not _eager_leaf_grads:

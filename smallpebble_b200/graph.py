@@ -219,7 +219,8 @@ class Adam:
             if type(g) is not DeviceArray or g.shape != v._array.shape:
                 g = _device_gradient(v, gradients)
             grads.append(g)
-        if _distributed.is_initialized() and _distributed.world_size() > 1:
+        if (_distributed.is_initialized() and _distributed.world_size() > 1
+                and not getattr(gradients, "_reduced", False)):
             grads = _distributed.allreduce_gradients(grads, variables)
         n = len(variables)
         # state creation and the pointer tables of moments / step counters are keyed by the
@@ -307,7 +308,8 @@ def sgd_step(variables, gradients, learning_rate: float = 0.001) -> None:
     if not variables:
         return
     grads = [_device_gradient(v, gradients) for v in variables]
-    if distributed.is_initialized() and distributed.world_size() > 1:
+    if (distributed.is_initialized() and distributed.world_size() > 1
+            and not getattr(gradients, "_reduced", False)):
         grads = distributed.allreduce_gradients(grads, variables)
     # in place, like the reference: settle deferred work that reads the parameters first
     _settle_before_inplace_update(gradients)

@@ -74,7 +74,8 @@ class _Record:
     __slots__ = ("root_state", "key", "pool", "placeholders", "static_inputs", "static_values",
                  "param_arrays", "shadow_refs", "graph_f", "kernels_f", "root", "epoch",
                  "graph_b", "kernels_b", "grads", "b_epoch", "side", "graph_u", "kernels_u",
-                 "u_vars", "u_opt", "u_hyper", "u_outs", "u_refreshed", "user_inputs", "keep")
+                 "u_vars", "u_opt", "u_hyper", "u_outs", "u_refreshed", "user_inputs", "keep",
+                 "exchange_bucket")
 
     def __init__(self):
         self.graph_b = self.graph_u = None
@@ -204,7 +205,13 @@ def run_root(root):
     return _replay_forward(rec)
 
 
-_dp_ok = os.environ.get("SP_STEADY_DP", "0") == "1"
+_dp_ok = os.environ.get("SP_STEADY_DP", "1") == "1"  # replay with a data-parallel exchange
+# Data parallel: issue the gradient exchange inside the backward graph (two parts, on a stream
+# of their own beside the sweep) instead of inside the update graph.  Measured on 2 GPUs
+# (CIFAR CNN, scripts/steady_parts.py): backward 72 -> 94 us for an update that gets 14 us
+# shorter -- the collective is latency-bound and its CTAs queue behind compute kernels that
+# fill the chip, so two of them cost more than they hide.  Off by default.
+exchange_in_backward = os.environ.get("SP_STEADY_DP_OVERLAP", "0") == "1"
 
 
 class _Abort(Exception):
@@ -411,15 +418,67 @@ def gradients_of(variable, tag):
     if static._deferred:
         out._deferred = {remap.get(k, k): list(v) for k, v in static._deferred.items()}
     out._steady = (rec, epoch, updates)
+    out._reduced = static._reduced
     return out
+
+
+def _count_leaf_jobs(root):
+    """Tape edges into learnable leaves reachable from `root` (= closures `fork` will run)."""
+    from . import core
+
+    n = 0
+    for node in core._tape_order(root):
+        for child, _ in node.local_gradients:
+            if not child.local_gradients and getattr(child, "is_learnable", False):
+                n += 1
+    return n
 
 
 def _record_backward(rec):
     from . import core
+    from . import distributed as dp
 
     torch = _torch()
     side = rec.side = torch.cuda.Stream() if fork_leaf_grads else None
-    forked = []
+    forked = []  # (variable, gradient array) in production order
+    # Data parallel: the exchange moves from the optimiser step into this graph, on the side
+    # stream, in two parts -- everything but the gradient produced last (the first layer's) is
+    # packed and all-reduced while the main stream still computes the rest of the sweep, the
+    # last one right after its kernel -- so only a small latency-bound collective is exposed.
+    comm = None
+    if (side is not None and dp.is_initialized() and dp.world_size() > 1
+            and dp._state["backend"] == "nccl" and exchange_in_backward):
+        comm = dp._direct_nccl()
+    n_jobs = _count_leaf_jobs(rec.root) if comm is not None else 0
+    exchanged = {}  # variable -> view of the bucket holding the summed gradient
+    bucket = [None, 0]  # [DeviceArray, floats used]
+
+    comm_stream = torch.cuda.Stream() if comm is not None else None
+
+    def exchange(pairs):
+        """Pack the gradients of `pairs` (complete on the side stream by now) into the next
+        bucket slots and sum them over the ranks, on a stream of their own: the side stream
+        goes on with the remaining parameter gradients."""
+        import ctypes as C
+
+        pairs = [(v, g) for v, g in pairs if v not in exchanged]
+        if not pairs:
+            return
+        sizes = [g.size for _, g in pairs]
+        layout = dp.bucket_layout(sizes)
+        base_off = bucket[1]
+        base = bucket[0]._ptr + 4 * base_off
+        tab = (C.c_void_p * len(pairs))(*[g.ptr for _, g in pairs])
+        ready = torch.cuda.Event()
+        ready.record(side)
+        comm_stream.wait_event(ready)
+        with torch.cuda.stream(comm_stream):
+            F.sp_pack_multi(len(pairs), tab, _abi.dims(sizes), _abi.dims(layout[:-1]), base,
+                            A.stream())
+            F.sp_allreduce_sum_f32(comm, base, layout[-1], A.stream())
+        for (v, g), off in zip(pairs, layout):
+            exchanged[v] = DeviceArray(g.shape, A.FLOAT, bucket[0]._buf, base + 4 * off)
+        bucket[1] = base_off + layout[-1]
 
     def fork(fn, path_value):
         """Run a parameter-gradient closure on the side stream (a branch of the graph)."""
@@ -432,12 +491,16 @@ def _record_backward(rec):
         F.sp_set_scratch_lane(1)
         try:
             with torch.cuda.stream(side):
+                if comm is not None and len(forked) == n_jobs - 1 and n_jobs > 1:
+                    # every gradient but the last is complete: exchange them now (a variable
+                    # that also receives the last contribution waits for the second part)
+                    exchange([(v, g) for v, g in _latest(forked) if v is not fn.child])
                 value = fn(path_value)
                 if type(value) is DeviceArray and value._ptr is None:
                     value.ptr
         finally:
             F.sp_set_scratch_lane(0)
-        forked.append(value)
+        forked.append((fn.child, value))
         return value
 
     def body():
@@ -447,12 +510,37 @@ def _record_backward(rec):
         finally:
             core._leaf_fork = None
         if forked:
+            if comm is not None:
+                exchange(_latest(forked))
+                for v, view in exchanged.items():
+                    dict.__setitem__(grads, v, view)
+                grads._reduced = True
+                done_comm = torch.cuda.Event()
+                done_comm.record(comm_stream)
+                torch.cuda.current_stream().wait_event(done_comm)
             done = torch.cuda.Event()
             done.record(side)
             torch.cuda.current_stream().wait_event(done)
         return grads
 
+    if comm is not None:
+        total = sum((p._array.size + 3) // 4 * 4 for p in rec.root_state.params
+                    if getattr(p, "is_learnable", False))
+        with A.pool_bypass():
+            bucket[0] = DeviceArray.empty((total + 64,), A.FLOAT, total + 64)
+        rec.keep.append(bucket[0])
     rec.graph_b, rec.grads, rec.kernels_b = _capture(rec.pool, body)
+    rec.keep = []  # (the update step fills it with the gradient arrays it expects)
+    if comm is not None:
+        rec.exchange_bucket = bucket[0]
+
+
+def _latest(forked):
+    """[(variable, its gradient array after the last contribution so far)], production order."""
+    last = {}
+    for v, g in forked:
+        last[v] = g
+    return list(last.items())
 
 
 # --------------------------------------------------------------------------------------------

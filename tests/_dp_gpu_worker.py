@@ -19,7 +19,9 @@ def main():
     sp.set_precision("fp32")
     sp.distributed.init()
     rank, world = sp.distributed.rank(), sp.distributed.world_size()
-    steps, per_gpu = 6, 16  # step 1: single all-reduce, 2: split planned, 3+: overlapped
+    # step 1: single all-reduce, 2: split planned, 3+: overlapped (eager); with the steady-state
+    # replay on, steps 4-5 record the CUDA graphs (NCCL all-reduce inside) and 6+ replay them
+    steps, per_gpu = int(os.environ.get("SP_TEST_STEPS", "6")), 16
     wl = workloads.cifar_cnn(seed=0)
     adam = sp.Adam()
     losses = []
@@ -31,11 +33,13 @@ def main():
     overlapped = sp.distributed._overlap["used"]
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), losses=np.array(losses),
              overlapped_steps=np.array(overlapped),
+             replayed_updates=np.array(sp.steady.stats["replays_u"]),
              **{f"w{i}": np.asarray(p.array) for i, p in enumerate(wl.learnables)})
     sp.distributed.barrier()
     sp.distributed.shutdown()
     if rank == 0:
-        # single-GPU run on the full global batch, same seeds
+        # single-GPU run on the full global batch, same seeds (eager path)
+        sp.set_steady_replay(False)
         wl1 = workloads.cifar_cnn(seed=0)
         adam1 = sp.Adam()
         losses1 = []

@@ -23,8 +23,9 @@ def _free_port():
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
                     reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("overlap", ["1", "0"], ids=["overlapped", "single_allreduce"])
-def test_data_parallel_equals_single_gpu(tmp_path, overlap):
+@pytest.mark.parametrize("overlap,steady,steps", [("1", "0", 6), ("0", "0", 6), ("0", "1", 12)],
+                         ids=["overlapped", "single_allreduce", "steady_replay"])
+def test_data_parallel_equals_single_gpu(tmp_path, overlap, steady, steps):
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
@@ -32,13 +33,18 @@ def test_data_parallel_equals_single_gpu(tmp_path, overlap):
            str(tmp_path)]
     # "1" forces the two-part exchange overlapped with the backward pass (by default only
     # large gradient buckets use it), "0" the single all-reduce on the compute stream
-    env = dict(os.environ, SP_DP_OVERLAP=overlap)
+    # steady "1": the loop is replayed from CUDA graphs that contain the NCCL all-reduce
+    env = dict(os.environ, SP_DP_OVERLAP=overlap, SP_STEADY=steady, SP_TEST_STEPS=str(steps))
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     single = np.load(tmp_path / "single.npz")
     ranks = [np.load(tmp_path / f"rank{i}.npz") for i in range(world)]
     # overlapped: the early gradients were reduced on the side stream from the third step on
     assert all(int(r["overlapped_steps"]) == (4 if overlap == "1" else 0) for r in ranks)
+    if steady == "1":
+        assert all(int(r["replayed_updates"]) >= steps - 6 for r in ranks)
+    else:
+        assert all(int(r["replayed_updates"]) == 0 for r in ranks)
     for key in single.files:
         # every rank ends with identical weights ...
         assert np.array_equal(ranks[0][key], ranks[1][key]), key
