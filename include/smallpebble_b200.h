@@ -137,6 +137,13 @@ int sp_strided_copy(const float* src, const int64_t* stride_src, float* dst,
                     const int64_t* stride_dst, int ndim, const int64_t* shape,
                     sp_stream_t stream);
 
+/* dst[i . stride_dst] += src[i . stride_src] over `shape`, np.add.at semantics (destinations
+ * named several times accumulate): the backward pass of strided_sliding_view (sp.py:384-387)
+ * and of basic-slice getitem, straight from the view's strides -- no index map */
+int sp_strided_add(const float* src, const int64_t* stride_src, float* dst,
+                   const int64_t* stride_dst, int ndim, const int64_t* shape,
+                   sp_stream_t stream);
+
 /* ---- reductions (sp.py:404-415 sum; 183-189 unbroadcast-sum) ------------------------ */
 /* x viewed as [outer, reduce, inner] -> out[outer, inner] */
 int sp_reduce_sum(const float* x, float* out, int64_t outer, int64_t reduce, int64_t inner,

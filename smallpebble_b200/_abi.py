@@ -59,6 +59,7 @@ SIGNATURES = {
     "sp_leaky_relu_bwd": (C.c_int, [vp, vp, vp, i64, f32, vp]),
     "sp_where": (C.c_int, [vp, p_i64, vp, p_i64, vp, p_i64, vp, C.c_int, p_i64, vp]),
     "sp_strided_copy": (C.c_int, [vp, p_i64, vp, p_i64, C.c_int, p_i64, vp]),
+    "sp_strided_add": (C.c_int, [vp, p_i64, vp, p_i64, C.c_int, p_i64, vp]),
     "sp_reduce_sum": (C.c_int, [vp, vp, i64, i64, i64, vp]),
     "sp_reduce_max_all": (C.c_int, [vp, vp, i64, vp]),
     "sp_argmax_rows_fwd": (C.c_int, [vp, vp, vp, i64, i64, vp]),

@@ -955,14 +955,75 @@ def _norm_pad(pad_width, ndim):
     return [(int(lo), int(hi)) for lo, hi in pw]
 
 
-@functools.lru_cache(maxsize=256)
+_ARANGE_CACHE_BYTES = 16 << 20
+_arange_cache = {}  # shape -> arange, at most _ARANGE_CACHE_BYTES in total
+
+
 def _arange_index(shape):
-    return np.arange(math.prod(shape), dtype=np.int64).reshape(shape)
+    """np.arange(prod(shape)).reshape(shape); small ones are cached (a (60000, 784) source would
+    pin 376 MB: those are rebuilt on demand and never kept)."""
+    shape = tuple(shape)
+    arr = _arange_cache.get(shape)
+    if arr is None:
+        arr = np.arange(math.prod(shape), dtype=np.int64).reshape(shape)
+        if arr.nbytes <= _ARANGE_CACHE_BYTES // 4:
+            if sum(a.nbytes for a in _arange_cache.values()) + arr.nbytes > _ARANGE_CACHE_BYTES:
+                _arange_cache.clear()
+            _arange_cache[shape] = arr
+    return arr
 
 
 def flat_index(shape, index) -> np.ndarray:
-    """int64 array of flat source offsets selected by the NumPy index expression `index`."""
+    """int64 array of flat source offsets selected by the NumPy index expression `index`
+    (advanced indexing: integer / boolean arrays; basic indices never come here, see
+    basic_view)."""
     return np.asarray(_arange_index(tuple(shape))[index], order="C")
+
+
+def basic_view(shape, index):
+    """(element offset, strides, shape) of `a[index]` as a strided view of a contiguous array of
+    `shape`, when `index` is BASIC (ints, slices, Ellipsis, None) -- NumPy's own rule for "this
+    is a view".  None for advanced indices.  The device then moves the data straight from the
+    view geometry: no index map is built, uploaded or cached."""
+    if not isinstance(index, tuple):
+        index = (index,)
+    for it in index:
+        if not (it is None or it is Ellipsis or isinstance(it, (slice, numbers.Integral))):
+            return None
+    if builtins_sum(1 for it in index if it is Ellipsis) > 1:
+        return None
+    n_real = builtins_sum(1 for it in index if it is not None and it is not Ellipsis)
+    if n_real > len(shape):
+        raise IndexError("too many indices for array")
+    if Ellipsis in index:
+        k = index.index(Ellipsis)
+        index = index[:k] + (slice(None),) * (len(shape) - n_real) + index[k + 1:]
+    else:
+        index = index + (slice(None),) * (len(shape) - n_real)
+    src_strides = _contig_strides(shape)
+    offset, out_shape, out_strides, axis = 0, [], [], 0
+    for it in index:
+        if it is None:
+            out_shape.append(1)
+            out_strides.append(0)
+            continue
+        dim, st = shape[axis], src_strides[axis]
+        if isinstance(it, numbers.Integral):
+            i = int(it)
+            if i < -dim or i >= dim:
+                raise IndexError(f"index {i} is out of bounds for axis {axis} with size {dim}")
+            offset += (i % dim) * st
+        else:
+            start, stop, step = it.indices(dim)
+            n = max(0, (stop - start + (step - (1 if step > 0 else -1))) // step)
+            offset += start * st if n else 0
+            out_shape.append(n)
+            out_strides.append(step * st)
+        axis += 1
+    return offset, tuple(out_strides), tuple(out_shape)
+
+
+builtins_sum = sum
 
 
 def gather_flat(a: DeviceArray, flat: np.ndarray) -> DeviceArray:
@@ -973,8 +1034,39 @@ def gather_flat(a: DeviceArray, flat: np.ndarray) -> DeviceArray:
     return out
 
 
+def view_gather(a: DeviceArray, view) -> DeviceArray:
+    """Contiguous copy of a strided view (offset, strides, shape) of `a`."""
+    offset, strides_, shape = view
+    out = DeviceArray.empty(shape)
+    strided_copy(a, strides_, offset, out, _contig_strides(shape), 0, shape)
+    return out
+
+
+def view_scatter(dst: DeviceArray, view, src: DeviceArray, accumulate: bool = False):
+    """dst.view (=|+=) src, src broadcast to the view's shape.  `accumulate`: np.add.at
+    semantics (a view may name an element more than once: sliding windows)."""
+    offset, strides_, shape = view
+    if math.prod(shape) == 0:
+        return
+    if len(shape) > _abi.MAX_DIMS:
+        raise ValueError(f"arrays with more than {_abi.MAX_DIMS} dimensions are not supported")
+    # broadcast src by stride 0 (trailing-aligned, NumPy rules)
+    sshape = (1,) * (len(shape) - src.ndim) + tuple(src.shape)
+    if len(sshape) != len(shape) or any(x != 1 and x != y for x, y in zip(sshape, shape)):
+        raise ValueError(f"could not broadcast input array from shape {src.shape} into shape {shape}")
+    cst = _contig_strides(sshape)
+    sst = tuple(0 if x == 1 else c for x, c in zip(sshape, cst))
+    fn = F.sp_strided_add if accumulate else F.sp_strided_copy
+    fn(src.ptr, _abi.dims(sst), dst.ptr + 4 * offset, _abi.dims(strides_), len(shape),
+       _abi.dims(shape), stream())
+
+
 def take(a: DeviceArray, index) -> DeviceArray:
-    """a[index] for any NumPy index expression (host builds the index map, device gathers)."""
+    """a[index] for any NumPy index expression: a basic index is a strided copy straight from
+    the view geometry; an advanced one gathers through a host-built index map."""
+    view = basic_view(a.shape, index)
+    if view is not None:
+        return view_gather(a, view)
     return gather_flat(a, flat_index(a.shape, index))
 
 

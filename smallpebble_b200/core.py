@@ -700,8 +700,20 @@ def sum(a: Variable, axis=None) -> Variable:  # noqa: A001 (shadows builtin like
 
 
 def getitem(a: Variable, indices) -> Variable:
-    "Get elements of `a` using NumPy indexing (sp.py:210-221)."
+    """Get elements of `a` using NumPy indexing (sp.py:210-221).  Basic indices (ints, slices,
+    Ellipsis, None) are strided copies straight from the view geometry, forward and backward;
+    advanced indices go through a flat index map (gather / scatter-add)."""
     src_shape = a.array.shape
+    view = A.basic_view(src_shape, indices)
+    if view is not None:
+        value = A.view_gather(a.array, view)
+
+        def scatter_view(g):
+            result = DeviceArray.zeros(src_shape)
+            A.view_scatter(result, view, _as_device(g))  # a basic view names no element twice
+            return result
+
+        return Variable(value, [(a, scatter_view)])
     flat = A.flat_index(src_shape, indices)
     value = A.gather_flat(a.array, flat)
 
@@ -714,59 +726,93 @@ def getitem(a: Variable, indices) -> Variable:
     return Variable(value, [(a, multiply_by_locgrad)])
 
 
+def _pick_like(g, b_shape, picked):
+    if picked.shape == b_shape:
+        return picked
+    return _unbroadcast(picked, b_shape, broadcastinfo(b_shape, picked.shape)[0])
+
+
 def add_at(a: Variable, indices, b: Variable) -> Variable:
     """Add the elements of `b` to the locations in `a` specified by `indices`; repeated
     indices accumulate (sp.py:111-121)."""
-    flat = A.flat_index(a.array.shape, indices)
-    value = a.array.copy()
-    A.scatter_add_flat(value, flat, b.array)
     b_shape = b.array.shape
-
-    def grad_b(g):
-        picked = A.gather_flat(g, flat)
-        if picked.shape == b_shape:
-            return picked
-        rb = broadcastinfo(b_shape, picked.shape)[0]
-        return _unbroadcast(picked, b_shape, rb)
-
-    return Variable(value, [(a, lambda g: g), (b, grad_b)])
+    value = a.array.copy()
+    view = A.basic_view(a.array.shape, indices)
+    if view is not None:
+        A.view_scatter(value, view, b.array, accumulate=True)
+        return Variable(value, [(a, lambda g: g),
+                                (b, lambda g: _pick_like(g, b_shape, A.view_gather(_as_device(g), view)))])
+    flat = A.flat_index(a.array.shape, indices)
+    A.scatter_add_flat(value, flat, b.array)
+    return Variable(value, [(a, lambda g: g),
+                            (b, lambda g: _pick_like(g, b_shape, A.gather_flat(g, flat)))])
 
 
 def setat(a: Variable, indices, b: Variable) -> Variable:
     """Similar to NumPy's `setitem`: a copy of `a` with `a[indices] = b` (sp.py:340-354)."""
-    flat = A.flat_index(a.array.shape, indices)
-    value = a.array.copy()
-    A.scatter_set_flat(value, flat, b.array)
     b_shape = b.array.shape
+    value = a.array.copy()
+    view = A.basic_view(a.array.shape, indices)
+    if view is not None:
+        A.view_scatter(value, view, b.array)
+
+        def grad_a_view(g):
+            out = _as_device(g).copy()  # the reference zeroes path_value in place; we do not
+            A.view_scatter(out, view, DeviceArray.zeros(()))
+            return out
+
+        return Variable(value, [(a, grad_a_view),
+                                (b, lambda g: _pick_like(g, b_shape, A.view_gather(_as_device(g), view)))])
+    flat = A.flat_index(a.array.shape, indices)
+    A.scatter_set_flat(value, flat, b.array)
 
     def grad_a(g):
         out = g.copy()  # the reference zeroes path_value in place; we leave it untouched
         A.scatter_set_flat(out, flat, DeviceArray.zeros(()))
         return out
 
-    def grad_b(g):
-        picked = A.gather_flat(g, flat)
-        if picked.shape == b_shape:
-            return picked
-        return _unbroadcast(picked, b_shape, broadcastinfo(b_shape, picked.shape)[0])
-
-    return Variable(value, [(a, grad_a), (b, grad_b)])
+    return Variable(value, [(a, grad_a),
+                            (b, lambda g: _pick_like(g, b_shape, A.gather_flat(g, flat)))])
 
 
 def strided_sliding_view(a: Variable, window_shape, strides) -> Variable:
-    """Sliding window view with strides in index units (sp.py:378-390).  On device this is a
-    gather through a host-built index map; the backward pass is the matching scatter-add
-    (np.add.at semantics: overlapping windows accumulate)."""
-    src_shape = a.array.shape
-    index_map = np.array(
-        np_strided_sliding_view(A._arange_index(tuple(src_shape)), tuple(window_shape), tuple(strides)),
-        order="C",
-    )
-    value = A.gather_flat(a.array, index_map)
+    """Sliding window view with strides in index units (sp.py:378-390).  The view is described
+    by strides alone -- positions x window, both walking the source -- so the device copies it
+    out directly and the backward pass adds the gradient back through the same strides
+    (np.add.at semantics: overlapping windows accumulate); no index map exists on either side."""
+    src_shape = tuple(a.array.shape)
+    window_shape, strides = tuple(window_shape), tuple(strides)
+    # the reference's own checks and messages (sp.py:696-711)
+    if len(window_shape) != len(src_shape):
+        raise ValueError("Must provide one window size for each dimension of x.")
+    if len(strides) != len(src_shape):
+        raise ValueError("Must provide one stride size for each dimension of x.")
+    if any(size < 0 for size in window_shape):
+        raise ValueError("`window_shape` cannot contain negative values")
+    if any(stride < 0 for stride in strides):
+        raise ValueError("`strides` cannot contain negative values")
+    if any(w > n for w, n in zip(window_shape, src_shape)):
+        raise ValueError("window shape cannot be larger than input array shape")
+    if 2 * len(src_shape) > _abi.MAX_DIMS:
+        # more dimensions than the strided kernels take: gather through an index map
+        index_map = np.array(np_strided_sliding_view(A._arange_index(src_shape), window_shape,
+                                                     strides), order="C")
+        value = A.gather_flat(a.array, index_map)
+
+        def scatter_map(g):
+            result = DeviceArray.zeros(src_shape)
+            A.scatter_add_flat(result, index_map, g)
+            return result
+
+        return Variable(value, [(a, scatter_map)])
+    cst = A._contig_strides(src_shape)
+    positions = tuple((n - w) // s + 1 for n, w, s in zip(src_shape, window_shape, strides))
+    view = (0, tuple(s * c for s, c in zip(strides, cst)) + tuple(cst), positions + window_shape)
+    value = A.view_gather(a.array, view)
 
     def multiply_by_locgrad(g):
         result = DeviceArray.zeros(src_shape)
-        A.scatter_add_flat(result, index_map, g)
+        A.view_scatter(result, view, _as_device(g), accumulate=True)
         return result
 
     return Variable(value, [(a, multiply_by_locgrad)])
@@ -787,8 +833,12 @@ def maxax(a: Variable, axis: int) -> Variable:
     moved_shape = moved.shape
 
     def multiply_by_locgrad(g):
+        # the reference multiplies the upstream gradient, in its NATURAL layout, by the one-hot
+        # swapped back to a's shape (sp.py:269-276): bring g into the row order of `moved`
+        g = _as_device(g)
+        gm = g if axis == nd - 1 else A.swapaxes(g.reshape(out_shape), axis, -1)
         dx = DeviceArray.empty(moved_shape)
-        F.sp_argmax_rows_bwd(g.ptr, idx.ptr, dx.ptr, rows, n, A.stream())
+        F.sp_argmax_rows_bwd(gm.ptr, idx.ptr, dx.ptr, rows, n, A.stream())
         return dx if axis == nd - 1 else A.swapaxes(dx, axis, -1)
 
     return Variable(best.reshape(out_shape), [(a, multiply_by_locgrad)])

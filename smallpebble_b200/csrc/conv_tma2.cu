@@ -75,6 +75,15 @@ struct Tma2Params {
   int split3;          // fprop, SP_PRECISION_TF32_SPLIT: operands are (r, l) pairs interleaved per
                        // 32 channels; a stage holds A = (x_r | x_l), B = (w_r | w_l) of ONE
                        // (tap, channel block) and takes 12 MMAs: r.r + l.r + r.l  (3xTF32)
+  // dgrad of a STRIDED conv runs as sy * sx stride-1 sub-problems, one per phase
+  // ((iy + pad_t) mod sy, (ix + pad_l) mod sx) of the input pixels: a phase's pixels see only
+  // the filter taps dy = py + sy * a, dx = px + sx * b.  The kernel then walks the phase's own
+  // (Hp x Wp) pixel grid (D1, D2) and KH x KW below are the phase's tap counts; these fields
+  // say where the taps sit in the real filter and where row m lands in the real tensor:
+  int b_s_y, b_s_x, b_py, b_px;  // filter tap (a, b) of the phase = real tap (py + sy*a, px + sx*b)
+  int out_sy, out_sx;            // output pixel (u, v) of the phase = real pixel
+  int out_oy, out_ox;            //   (out_oy + out_sy * u, out_ox + out_sx * v)
+  int out_H, out_W;              // of an image of out_H x out_W pixels (out_sy == 0: dense rows)
   int ksplit;          // CTA pairs per cluster (1, 2 or 4): a small problem's reduction axis is
                        // split over the pairs of one cluster, which then add their accumulators
                        // through distributed shared memory in pair order (one tile per cluster)
@@ -387,6 +396,16 @@ __device__ __forceinline__ TileCoord tile_coord(const Tma2Params& p, int t) {
   return c;
 }
 
+// Row m of the GEMM -> row of the output tensor (pixels x ldc).  Dense except for the phase
+// sub-problems of a strided data gradient, whose pixels are every out_s-th of the real image.
+__device__ __forceinline__ int64_t out_row(const Tma2Params& p, int m) {
+  if (p.out_sy == 0) return m;
+  const int hw = p.D1 * p.D2;
+  const int n = m / hw, r = m - n * hw;
+  const int u = r / p.D2, v = r - u * p.D2;
+  return ((int64_t)n * p.out_H + p.out_oy + p.out_sy * u) * p.out_W + p.out_ox + p.out_sx * v;
+}
+
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
@@ -545,9 +564,16 @@ __global__ void __launch_bounds__(kThreads, 1)
                   // w as [32][KH*KW*C][Kout/32]: rows st*64 .. +64 (rows past the end read 0)
                   tma_tile_3d(b_tile, &tmB, fb, 0, st * 64, nb0 >> 5);
                 } else if (MODE == kDgrad) {
-                  // w as [tap][c][ko]: rows = this CTA's input channels, 32 ko per half
-                  tma_tile_3d(b_tile, &tmB, fb, cb * 32, nb0, tap);
-                  if (valid1) tma_tile_3d(b_tile + (uint32_t)bnh * 128u, &tmB, fb, cb1 * 32, nb0, tap1);
+                  // w as [dy][dx][c][ko]: rows = this CTA's input channels, 32 ko per half;
+                  // tap (a, b) of a phase is real tap (py + sy * a, px + sx * b)
+                  const int ta = tap / p.KW, tb = tap - ta * p.KW;
+                  tma_tile_4d(b_tile, &tmB, fb, cb * 32, nb0, p.b_px + p.b_s_x * tb,
+                              p.b_py + p.b_s_y * ta);
+                  if (valid1) {
+                    const int ta1 = tap1 / p.KW, tb1 = tap1 - ta1 * p.KW;
+                    tma_tile_4d(b_tile + (uint32_t)bnh * 128u, &tmB, fb, cb1 * 32, nb0,
+                                p.b_px + p.b_s_x * tb1, p.b_py + p.b_s_y * ta1);
+                  }
                 } else {
                   // gy as [32][N*OH*OW][Kout/32]
                   tma_tile_3d(b_tile, &tmB, fb, 0, pix, nb0 >> 5);
@@ -702,15 +728,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int acc = it & 1;
       const int m_base = (tc.m_pair * 2 + (int)rank) * 128 + quad * 32;
       const int m = m_base + lane;
-      float* __restrict__ cbase =
-          p.C + (int64_t)tc.split * p.split_stride + (int64_t)m_base * p.ldc + tc.n0;
-      float* __restrict__ crow = cbase + (int64_t)lane * p.ldc;
+      float* __restrict__ ctile = p.C + (int64_t)tc.split * p.split_stride + tc.n0;
+      float* __restrict__ crow = ctile + out_row(p, m) * p.ldc;
       float* rp[8];
       uint32_t ok_mask = 0;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int row = (lane >> 3) + 4 * r;
-        rp[r] = cbase + (int64_t)row * p.ldc;
+        rp[r] = ctile + out_row(p, m_base + row) * p.ldc;
         ok_mask |= (m_base + row < p.M ? 1u : 0u) << r;
       }
       const bool use_act = ACT && vec_store && act_delta != 0 && S == 1;
@@ -803,7 +828,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         acc4.z += v.z;
         acc4.w += v.w;
       }
-      float* dst = cbase + (int64_t)m * p.ldc + cbk * 32 + chunk * 4;
+      float* dst = cbase + out_row(p, m) * p.ldc + cbk * 32 + chunk * 4;
       if (MODE == kFprop && p.leaky) {
         acc4.x = acc4.x > 0.f ? acc4.x : p.alpha * acc4.x;
         acc4.y = acc4.y > 0.f ? acc4.y : p.alpha * acc4.y;
@@ -1337,6 +1362,33 @@ bool cached_map(const void* ptr, int kind, const sp_conv_geom& g, int extra, CUt
 
 long long* g_trace = nullptr;
 
+// One phase of the data gradient of a (possibly strided) conv, as a stride-1 problem.
+// 1-D: dx[i] = sum over (o, d) with s*o - pad + d = i of gy[o] * w[d].  With t = i + pad,
+// py = t mod s, q = t div s: d = py + s*a and o = q - a, so the pixels of phase py
+// (i = i0 + s*u, u = q - q0) see   dx_p[u] = sum_a gy[u + q0 - a] * w[py + s*a]   -- the data
+// gradient of a stride-1 conv with A taps and padding q0 over an "image" of Hp pixels.
+struct DgradPhase {
+  int py, px;      // phase
+  int A, B;        // taps of the phase (rows, columns)
+  int q0h, q0w;    // padding of the equivalent stride-1 problem
+  int i0, j0;      // first real pixel of the phase
+  int Hp, Wp;      // pixels of the phase
+};
+inline void phase_1d(int H, int KH, int s, int pad, int py, int* A, int* q0, int* i0, int* Hp) {
+  *A = py < KH ? (KH - py + s - 1) / s : 0;
+  *q0 = pad > py ? (pad - py + s - 1) / s : 0;
+  *i0 = s * *q0 + py - pad;
+  *Hp = *i0 < H ? (H - *i0 + s - 1) / s : 0;
+}
+inline DgradPhase dgrad_phase(const sp_conv_geom& g, int py, int px) {
+  DgradPhase ph;
+  ph.py = py;
+  ph.px = px;
+  phase_1d(g.H, g.KH, g.sy, g.pad_t, py, &ph.A, &ph.q0h, &ph.i0, &ph.Hp);
+  phase_1d(g.W, g.KW, g.sx, g.pad_l, px, &ph.B, &ph.q0w, &ph.j0, &ph.Wp);
+  return ph;
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline bool corner_ok(int v) { return v >= -128 && v <= 127; }
 
@@ -1365,10 +1417,19 @@ bool conv_tma2_supported(int mode, const IgemmParams& p) {
       return g.C % 32 == 0 && g.K % 64 == 0 && corner_ok(-g.pad_t) && corner_ok(-g.pad_l) &&
              corner_ok(up_h) && corner_ok(up_w) && (p.k_splits <= 1 || p.k_chunk % 64 == 0);
     case kDgrad: {
-      if (g.sy != 1 || g.sx != 1) return false;
-      const int lo_h = g.pad_t - (g.KH - 1), lo_w = g.pad_l - (g.KW - 1);
-      return g.K % 32 == 0 && g.C % 32 == 0 && corner_ok(lo_h) && corner_ok(lo_w) &&
-             corner_ok(g.H - g.OH + lo_h) && corner_ok(g.W - g.OW + lo_w);
+      if (g.K % 32 != 0 || g.C % 32 != 0) return false;
+      // every phase sub-problem (one for a stride-1 conv) must fit the im2col corner range
+      for (int py = 0; py < g.sy; ++py)
+        for (int px = 0; px < g.sx; ++px) {
+          const DgradPhase ph = dgrad_phase(g, py, px);
+          if (ph.Hp <= 0 || ph.Wp <= 0 || ph.A <= 0 || ph.B <= 0) continue;
+          const int lo_h = ph.q0h - (ph.A - 1), lo_w = ph.q0w - (ph.B - 1);
+          if (!(corner_ok(lo_h) && corner_ok(lo_w) && corner_ok(ph.Hp - g.OH + lo_h) &&
+                corner_ok(ph.Wp - g.OW + lo_w)))
+            return false;
+          if ((int64_t)g.N * ph.Hp * ph.Wp > lim) return false;
+        }
+      return true;
     }
   }
   return false;
@@ -1407,14 +1468,45 @@ int conv_tma2_max_clusters(int size) {
   return cached[size];
 }
 
+static int launch_conv_tma2_one(int mode, const IgemmParams& ip, cudaStream_t st,
+                                const DgradPhase* ph);
+
 int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
   if (!conv_tma2_supported(mode, ip))
     return set_error(SP_ERR_UNSUPPORTED, "conv_tma2: unsupported problem");
   const sp_conv_geom& g = ip.g;
+  if (mode != kDgrad) return launch_conv_tma2_one(mode, ip, st, nullptr);
+  if (g.sy == 1 && g.sx == 1) {
+    const DgradPhase ph = dgrad_phase(g, 0, 0);
+    return launch_conv_tma2_one(mode, ip, st, &ph);
+  }
+  // strided: one stride-1 sub-problem per phase; pixels of phases without taps (stride larger
+  // than the window) receive no gradient at all
+  bool holes = false;
+  for (int py = 0; py < g.sy; ++py)
+    for (int px = 0; px < g.sx; ++px) {
+      const DgradPhase ph = dgrad_phase(g, py, px);
+      if (ph.Hp > 0 && ph.Wp > 0 && (ph.A <= 0 || ph.B <= 0)) holes = true;
+    }
+  if (holes &&
+      cudaMemsetAsync(ip.C, 0, (size_t)g.N * g.H * g.W * g.C * sizeof(float), st) != cudaSuccess)
+    return set_error(SP_ERR_DRIVER, "conv_tma2: memset failed");
+  for (int py = 0; py < g.sy; ++py)
+    for (int px = 0; px < g.sx; ++px) {
+      const DgradPhase ph = dgrad_phase(g, py, px);
+      if (ph.Hp <= 0 || ph.Wp <= 0 || ph.A <= 0 || ph.B <= 0) continue;
+      if (int rc = launch_conv_tma2_one(mode, ip, st, &ph)) return rc;
+    }
+  return 0;
+}
+
+static int launch_conv_tma2_one(int mode, const IgemmParams& ip, cudaStream_t st,
+                                const DgradPhase* ph) {
+  const sp_conv_geom& g = ip.g;
   Tma2Params p;
   memset(&p, 0, sizeof(p));
   p.mode = mode;
-  p.M = (int)ip.M;
+  p.M = mode == kDgrad ? g.N * ph->Hp * ph->Wp : (int)ip.M;
   p.N = (int)ip.N;
   p.m_pairs = (p.M + 255) / 256;
   p.bn_tile = p.N >= 256 ? 256 : p.N;
@@ -1478,24 +1570,44 @@ int launch_conv_tma2(int mode, const IgemmParams& ip, cudaStream_t st) {
       return encode_mn_blocks(m, ip.B, (int64_t)g.KH * g.KW * g.C, g.K, 64, bnh_max / 32);
     });
   } else if (mode == kDgrad) {
+    // the phase's stride-1 problem (the whole problem when the conv has stride 1)
+    p.KH = ph->A;
+    p.KW = ph->B;
     p.cblocks = g.K / 32;
-    p.kblocks = g.KH * g.KW * p.cblocks;
-    p.D1 = g.H;
-    p.D2 = g.W;
+    p.kblocks = p.KH * p.KW * p.cblocks;
+    p.D1 = ph->Hp;
+    p.D2 = ph->Wp;
     p.sy = 1;
     p.sx = 1;
-    const int lo_h = g.pad_t - (g.KH - 1), lo_w = g.pad_l - (g.KW - 1);
+    const int lo_h = ph->q0h - (ph->A - 1), lo_w = ph->q0w - (ph->B - 1);
     p.base_h = lo_h;
     p.base_w = lo_w;
-    ok = cached_map(ip.A, 2, g, 128, &tmA, [&](CUtensorMap* m) {
-      return encode_im2col(m, ip.A, g.N, g.OH, g.OW, g.K, lo_w, lo_h, g.W - g.OW + lo_w,
-                           g.H - g.OH + lo_h, 1, 1, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    p.b_s_y = g.sy;
+    p.b_s_x = g.sx;
+    p.b_py = ph->py;
+    p.b_px = ph->px;
+    if (g.sy > 1 || g.sx > 1) {
+      p.out_sy = g.sy;
+      p.out_sx = g.sx;
+      p.out_oy = ph->i0;
+      p.out_ox = ph->j0;
+      p.out_H = g.H;
+      p.out_W = g.W;
+    }
+    // the map depends on the phase only through its four corners (each in [-128, 127])
+    const int up_h = ph->Hp - g.OH + lo_h, up_w = ph->Wp - g.OW + lo_w;
+    const int phase_key = (int)(((uint32_t)(lo_h + 128)) | ((uint32_t)(lo_w + 128) << 8) |
+                                ((uint32_t)(up_h + 128) << 16) | ((uint32_t)(up_w + 128) << 24));
+    ok = cached_map(ip.A, 2, g, phase_key, &tmA, [&](CUtensorMap* m) {
+      return encode_im2col(m, ip.A, g.N, g.OH, g.OW, g.K, lo_w, lo_h, up_w, up_h, 1, 1, 128,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
     });
-    // rows of B per CTA: half the N tile (a multiple of 16); one box covers them
-    ok = ok && cached_map(ip.B, 3, g, bnh_max, &tmB, [&](CUtensorMap* m) {
-      const cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.C, (cuuint64_t)g.KH * g.KW};
-      const cuuint32_t box[3] = {32, (cuuint32_t)bnh_max, 1};
-      return encode_tiled(m, ip.B, 3, dims, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    // w as [KH][KW][C][K]; rows of B per CTA: half the N tile (a multiple of 16), one tap
+    ok = ok && cached_map(ip.B, 9, g, bnh_max, &tmB, [&](CUtensorMap* m) {
+      const cuuint64_t dims[4] = {(cuuint64_t)g.K, (cuuint64_t)g.C, (cuuint64_t)g.KW,
+                                  (cuuint64_t)g.KH};
+      const cuuint32_t box[4] = {32, (cuuint32_t)bnh_max, 1, 1};
+      return encode_tiled(m, ip.B, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_128B);
     });
   } else {
     p.cblocks = g.C / 32;

@@ -225,6 +225,26 @@ __global__ void __launch_bounds__(kThreads) strided_copy_kernel(const float* __r
   }
 }
 
+// dst[i . stride_dst] += src[i . stride_src] with np.add.at semantics: several i may name the
+// same destination (overlapping windows of strided_sliding_view, sp.py:386) and accumulate.
+__global__ void __launch_bounds__(kThreads) strided_add_kernel(const float* __restrict__ src,
+                                                               float* __restrict__ dst, int64_t n,
+                                                               Dims d) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t rem = i, os = 0, od = 0;
+#pragma unroll 1
+    for (int k = d.ndim - 1; k >= 0; --k) {
+      const int64_t q = rem / d.shape[k];
+      const int64_t r = rem - q * d.shape[k];
+      os += r * d.s0[k];
+      od += r * d.so[k];
+      rem = q;
+    }
+    atomicAdd(dst + od, src[os]);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) accumulate_kernel(float* __restrict__ dst,
                                                               const float* __restrict__ src,
                                                               int64_t n, bool vec) {
@@ -466,6 +486,21 @@ int sp_strided_copy(const float* src, const int64_t* stride_src, float* dst,
   const Dims d = collapse(ndim, shape, stride_src, nullptr, nullptr, stride_dst);
   strided_copy_kernel<<<ew_grid(n), kThreads, 0, sp::as_stream(stream)>>>(src, dst, n, d);
   SP_CHECK_LAUNCH("strided_copy");
+  return 0;
+}
+
+int sp_strided_add(const float* src, const int64_t* stride_src, float* dst,
+                   const int64_t* stride_dst, int ndim, const int64_t* shape,
+                   sp_stream_t stream) {
+  SP_REQUIRE(ndim >= 0 && ndim <= SP_MAX_DIMS, "ndim out of range");
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  if (n <= 0) return 0;
+  // (no collapsing of dimensions that merge in BOTH stride sets is lost by passing them as they
+  // are: `collapse` only merges when source and destination agree)
+  const Dims d = collapse(ndim, shape, stride_src, nullptr, nullptr, stride_dst);
+  strided_add_kernel<<<ew_grid(n), kThreads, 0, sp::as_stream(stream)>>>(src, dst, n, d);
+  SP_CHECK_LAUNCH("strided_add");
   return 0;
 }
 

@@ -30,6 +30,12 @@ CONV_CASES = [
     ("c128_k256_valid", (2, 9, 9, 128), (3, 3, 128, 256), (1, 1), "VALID"),
     ("c32_k192_k2x3", (3, 9, 10, 32), (2, 3, 32, 192), (1, 1), "SAME"),
     ("c512_k64_k1", (1, 10, 13, 512), (1, 1, 512, 64), (1, 1), "SAME"),
+    # strided convs with channel counts % 32 == 0: the data gradient runs as one stride-1
+    # sub-problem per phase of the input pixels (conv_tma2.cu)
+    ("c32_k64_k3_s2_valid", (3, 13, 12, 32), (3, 3, 32, 64), (2, 2), "VALID"),
+    ("c64_k64_k1_s2_same", (2, 9, 8, 64), (1, 1, 64, 64), (2, 2), "SAME"),  # pixels without taps
+    ("c32_k64_k4_s3_same", (2, 14, 11, 32), (4, 4, 32, 64), (3, 3), "SAME"),
+    ("c32_k64_k3x2_s2x1_valid", (2, 10, 9, 32), (3, 2, 32, 64), (2, 1), "VALID"),
     # RGB 3x3 first layers: register-tiled CUDA-core kernels (csrc/conv_smallc.cu)
     ("k3_c3_same_k64", (2, 9, 7, 3), (3, 3, 3, 64), (1, 1), "SAME"),
     ("k3_c3_s2_k16", (2, 11, 10, 3), (3, 3, 3, 16), (2, 2), "SAME"),
@@ -60,6 +66,11 @@ MATMUL_CASES = [
     ("cnn_fc", (128, 1152), (1152, 10)),
     ("odd", (37, 53), (53, 19)),
 ]
+
+# name, shape, axis (sp.py:257-279: for axis != last the reference lays the result out in
+# swapped-row order without swapping back -- the golden vectors pin that, values and gradient)
+MAXAX_CASES = [("last", (4, 6), -1), ("axis0_3d", (3, 4, 5), 0), ("axis1_3d", (3, 4, 5), 1),
+               ("axis0_2d", (5, 7), 0)]
 
 SOFTMAX_CASES = [("rows", (100, 10), -1), ("cols", (7, 5), 0), ("mid", (3, 4, 6), 1)]
 
@@ -102,6 +113,14 @@ def matmul_inputs(case):
     a, b = r.random(sa) - 0.5, r.random(sb) - 0.5
     gy = r.random(np.broadcast_shapes(sa[:-2], sb[:-2]) + (sa[-2], sb[-1])) - 0.5
     return a, b, gy
+
+
+def maxax_inputs(case):
+    name, shape, axis = case
+    r = _rng("maxax/" + name)
+    x = r.random(shape) - 0.5
+    out_shape = tuple(1 if i == (axis % len(shape)) else v for i, v in enumerate(shape))
+    return x, r.random(out_shape) - 0.5
 
 
 def softmax_inputs(case):

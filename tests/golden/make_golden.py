@@ -76,6 +76,11 @@ def main():
         a, b, gy = C.matmul_inputs(case)
         y, (da, db) = grads_of(ref.matmul, [a, b], gy)
         out[f"matmul/{name}/y"], out[f"matmul/{name}/da"], out[f"matmul/{name}/db"] = y, da, db
+    for case in C.MAXAX_CASES:
+        name, shape, axis = case
+        x, gy = C.maxax_inputs(case)
+        y, (dx,) = grads_of(lambda a: ref.maxax(a, axis), [x], gy)
+        out[f"maxax/{name}/y"], out[f"maxax/{name}/dx"] = y, dx
     for case in C.SOFTMAX_CASES:
         name, shape, axis = case
         x, gy = C.softmax_inputs(case)

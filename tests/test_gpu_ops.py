@@ -116,6 +116,19 @@ def test_softmax(case, golden):
     assert_close(dx, golden[f"softmax/{name}/dx"], 1e-5, "dx")
 
 
+@pytest.mark.parametrize("case", C.MAXAX_CASES, ids=[c[0] for c in C.MAXAX_CASES])
+def test_maxax(case, golden):
+    """Values AND gradient layout of the reference for axis != last (sp.py:257-279: the result is
+    reshaped without swapping back; the gradient multiplies the upstream gradient in its natural
+    layout by the swapped-back one-hot) -- ADVICE r01."""
+    name, shape, axis = case
+    x, gy = C.maxax_inputs(case)
+    y, (dx,) = grads_of(lambda a: sp.maxax(a, axis), [x], gy)
+    assert y.shape == golden[f"maxax/{name}/y"].shape
+    assert_close(y.array, golden[f"maxax/{name}/y"], 1e-6, "y")
+    assert_close(dx, golden[f"maxax/{name}/dx"], 1e-6, "dx")
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_softmax_cross_entropy(fused, golden):
     sp.set_fusion(fused)
@@ -241,3 +254,59 @@ def test_leaky_relu_maxpool_fusion_is_bit_identical(pool, alpha):
     y0, idx0 = orc.maxpool2d_forward(act0, kh, kw, pad, strides)
     assert np.array_equal(fused[0], y0.astype(np.float32)) and np.array_equal(fused[1], idx0)
     del gy_seed
+
+
+_VIEW_INDICES = [1, -1, slice(1, 4), slice(None, None, 2), slice(4, 0, -1), (1, 2), (slice(1, 3), 0),
+                 (Ellipsis, 2), (None, 1), (slice(None), None, slice(2, 6, 3)),
+                 (0, Ellipsis, slice(None, None, -2)), slice(3, 3), (2, 3, 4),
+                 (np.array([0, 2, 2, 4]), slice(1, 3)), (np.arange(5), np.arange(5), 0)]
+
+
+@pytest.mark.parametrize("index", _VIEW_INDICES, ids=[str(i)[:40] for i in _VIEW_INDICES])
+def test_getitem_add_at_setat_match_numpy(index):
+    """f3: basic indices run as strided copies straight from the view geometry, advanced ones
+    through an index map; both must be NumPy's `a[index]`, `np.add.at` and `a[index] = b`
+    (sp.py:111-121, 210-221, 340-354), forward and gradient."""
+    rng = np.random.default_rng(3)
+    x = rng.random((5, 6, 7)).astype(np.float32)
+    picked = x[index]
+    gy = rng.random(picked.shape).astype(np.float32)
+    y, (dx,) = grads_of(lambda a: sp.getitem(a, index), [x], gy)
+    assert y.shape == picked.shape
+    assert np.array_equal(np.asarray(y.array), picked)
+    want = np.zeros_like(x)
+    np.add.at(want, index, gy)
+    assert_close(dx, want, 1e-6, "getitem gradient")
+    b = rng.random(picked.shape).astype(np.float32)
+    gfull = rng.random(x.shape).astype(np.float32)
+    y, (da, db) = grads_of(lambda a, c: sp.add_at(a, index, c), [x, b], gfull)
+    want = x.copy()
+    np.add.at(want, index, b)
+    assert_close(y.array, want, 1e-6, "add_at")
+    assert np.array_equal(np.asarray(da), gfull)
+    assert np.array_equal(np.asarray(db), gfull[index])
+    y, (da, db) = grads_of(lambda a, c: sp.setat(a, index, c), [x, b], gfull)
+    want = x.copy()
+    want[index] = b
+    if not isinstance(index, tuple) or not any(isinstance(i, np.ndarray) for i in index):
+        assert np.array_equal(np.asarray(y.array), want)  # (repeated advanced indices: any writer may win)
+    keep = gfull.copy()
+    keep[index] = 0
+    assert np.array_equal(np.asarray(da), keep)
+    assert np.array_equal(np.asarray(db), gfull[index])
+
+
+@pytest.mark.parametrize("shape,window,strides", [((9, 10), (3, 4), (2, 3)),
+                                                  ((2, 7, 8, 3), (1, 3, 2, 1), (1, 2, 3, 1)),
+                                                  ((6,), (6,), (1,))])
+def test_strided_sliding_view_matches_numpy(shape, window, strides):
+    rng = np.random.default_rng(4)
+    x = rng.random(shape).astype(np.float32)
+    ref = core.np_strided_sliding_view(x, window, strides)
+    gy = rng.random(ref.shape).astype(np.float32)
+    y, (dx,) = grads_of(lambda a: sp.strided_sliding_view(a, window, strides), [x], gy)
+    assert np.array_equal(np.asarray(y.array), ref)
+    want = np.zeros(x.shape, np.float64)
+    idx = core.np_strided_sliding_view(np.arange(x.size).reshape(shape), window, strides)
+    np.add.at(want.reshape(-1), idx.reshape(-1), gy.reshape(-1).astype(np.float64))
+    assert_close(dx, want, 1e-6, "overlapping windows accumulate")
