@@ -342,6 +342,29 @@ int sp_adam_multi_shadow(int n_tensors, float* const* host_p, float* const* host
                          float* const* host_rounded, float* const* host_split,
                          const int64_t* host_block_elems, const int32_t* host_kind, float alpha,
                          float beta1, float beta2, float eps, sp_stream_t stream);
+/* ---- data parallel without a collective library: one-shot all-reduce over NVLink peer memory,
+ * fused into the Adam kernel (one node, 2..8 ranks; no reference counterpart).  Every rank
+ * allocates an exchange block of 256 + 2 * 4 * half_floats bytes with sp_peer_alloc, ships the
+ * 64-byte handle to its peers (any transport), maps theirs with sp_peer_open and creates the
+ * exchange from the world's block pointers (its own at [rank]).  sp_adam_multi_peer is
+ * sp_adam_multi_shadow whose gradients are the SUM over all ranks: it packs host_g into this
+ * rank's block (host_offsets: element offset of each tensor inside a bucket half, multiples of
+ * 4), signals the peers, waits for them, adds the world's buckets in rank order (bit-identical
+ * weights on every replica) and updates.  Step-independent launch: CUDA graphs replay it. */
+int sp_peer_alloc(size_t bytes, void** dev_ptr, void* handle64);
+int sp_peer_open(const void* handle64, void** dev_ptr);
+int sp_peer_close(void* dev_ptr);
+int sp_peer_free(void* dev_ptr);
+int sp_peer_exchange_create(int world, int rank, int64_t half_floats, void* const* blocks,
+                            void** out);
+int sp_peer_exchange_destroy(void* exchange);
+int sp_adam_multi_peer(void* exchange, int n_tensors, float* const* host_p, float* const* host_p_out,
+                       const float* const* host_g, const int64_t* host_offsets,
+                       float* const* host_m, float* const* host_v, const int64_t* host_numel,
+                       int32_t* const* host_step, float* const* host_rounded,
+                       float* const* host_split, const int64_t* host_block_elems,
+                       const int32_t* host_kind, float alpha, float beta1, float beta2, float eps,
+                       sp_stream_t stream);
 int sp_sgd_multi(int n_tensors, float* const* host_p, const float* const* host_g,
                  const int64_t* host_numel, float lr, sp_stream_t stream);
 /* gather many gradient tensors into one flat bucket (the data-parallel all-reduce payload):

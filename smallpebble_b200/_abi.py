@@ -102,6 +102,16 @@ SIGNATURES = {
                                        C.POINTER(vp), C.POINTER(vp), p_i64, C.POINTER(vp),
                                        C.POINTER(vp), C.POINTER(vp), p_i64, C.POINTER(C.c_int32),
                                        f32, f32, f32, f32, vp]),
+    "sp_peer_alloc": (C.c_int, [sz, vp, vp]),
+    "sp_peer_open": (C.c_int, [vp, vp]),
+    "sp_peer_close": (C.c_int, [vp]),
+    "sp_peer_free": (C.c_int, [vp]),
+    "sp_peer_exchange_create": (C.c_int, [C.c_int, C.c_int, i64, C.POINTER(vp), vp]),
+    "sp_peer_exchange_destroy": (C.c_int, [vp]),
+    "sp_adam_multi_peer": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), p_i64,
+                                     C.POINTER(vp), C.POINTER(vp), p_i64, C.POINTER(vp),
+                                     C.POINTER(vp), C.POINTER(vp), p_i64, C.POINTER(C.c_int32),
+                                     f32, f32, f32, f32, vp]),
     "sp_sgd_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), p_i64, f32, vp]),
     "sp_tf32_split": (C.c_int, [vp, vp, i64, i64, C.c_int, vp]),
     "sp_tf32_round": (C.c_int, [vp, vp, i64, vp]),
@@ -127,7 +137,9 @@ _LAUNCHING = {
                  "sp_event_record", "sp_stream_wait_event", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
                  "sp_conv2d_wgrad_workspace", "sp_set_tf32_output_rounding", "sp_conv2d_x3_plan",
                  "sp_set_scratch_lane", "sp_nccl_load", "sp_nccl_unique_id", "sp_nccl_init",
-                 "sp_allreduce_sum_f32", "sp_nccl_destroy")
+                 "sp_allreduce_sum_f32", "sp_nccl_destroy", "sp_peer_alloc", "sp_peer_open",
+                 "sp_peer_close", "sp_peer_free", "sp_peer_exchange_create",
+                 "sp_peer_exchange_destroy")
 }
 
 

@@ -242,6 +242,77 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   p.batch_b = strideB;
   p.batch_c = strideC;
   cudaStream_t st = sp::as_stream(stream);
+  // A dense GEMM is a 1 x 1 convolution over a one-row "image" of M pixels: NN = its forward
+  // pass, NT = its data gradient, TN = its filter gradient.  Shapes the 2-SM TMA kernels take
+  // (contraction and output widths in whole 32 / 64-channel blocks, large enough to matter) run
+  // there: tcgen05.mma.cta_group::2 fed by TMA (conv_tma2.cu) instead of the cp.async producers
+  // of the 1-SM kernel.
+  if (precision == SP_PRECISION_TF32 && batch == 1 && ldc == N && M <= 0x7fffffff) {
+    sp::IgemmParams q = sp::base_params();
+    int mode = -1;
+    sp_conv_geom g;
+    memset(&g, 0, sizeof(g));
+    g.N = 1;
+    g.H = g.OH = 1;
+    g.KH = g.KW = 1;
+    g.sy = g.sx = 1;
+    if (!transA && !transB && lda == K && ldb == N) {  // C[M,N] = A[M,K] . B[K,N]
+      mode = sp::kFprop;
+      g.W = g.OW = (int)M;
+      g.C = (int)K;
+      g.K = (int)N;
+      q.M = M;
+      q.N = N;
+      q.K = K;
+    } else if (!transA && transB && lda == K && ldb == K) {  // C[M,N] = A[M,K] . B[N,K]^T
+      mode = sp::kDgrad;
+      g.W = g.OW = (int)M;
+      g.C = (int)N;
+      g.K = (int)K;
+      q.M = M;
+      q.N = N;
+      q.K = K;
+    } else if (transA && !transB && lda == M && ldb == N) {  // C[M,N] = A[K,M]^T . B[K,N]
+      mode = sp::kWgrad;
+      g.W = g.OW = (int)K;
+      g.C = (int)M;
+      g.K = (int)N;
+      q.M = M;
+      q.N = N;
+      q.K = K;
+    }
+    if (mode >= 0 && K <= 0x7fffffff && N <= 0x7fffffff) {
+      q.g = g;
+      q.A = A;
+      q.B = B;
+      q.C = C;
+      q.ldc = N;
+      if (sp::use_tma2(mode, q, precision)) {
+        if (mode != sp::kWgrad) {
+          if (int rc = sp::launch_conv_tma2(mode, q, st)) return rc;
+          SP_CHECK_LAUNCH("gemm(2-SM TMA)");
+          return 0;
+        }
+        int splits;
+        int64_t chunk;
+        sp::wgrad_split_tma2(g, &splits, &chunk);
+        float* scratch = sp::scratch_for_current_device();
+        const int64_t cap = (int64_t)(sp::kScratchFloats / 2);
+        if (splits <= 1 || (scratch && (int64_t)splits * M * N <= cap)) {
+          if (splits > 1) {
+            q.k_splits = splits;
+            q.k_chunk = chunk;
+            q.split_stride_c = M * N;
+            q.C = scratch + sp::kScratchFloats / 2;
+          }
+          if (int rc = sp::launch_conv_tma2(mode, q, st)) return rc;
+          SP_CHECK_LAUNCH("gemm(2-SM TMA, TN)");
+          if (splits > 1) return sp_reduce_sum(q.C, C, 1, splits, M * N, stream);
+          return 0;
+        }
+      }
+    }
+  }
   if (sp::use_umma(sp::kGemm, p, precision)) {
     if (int rc = sp::launch_igemm_umma(sp::kGemm, p, st)) return rc;
     SP_CHECK_LAUNCH("gemm");

@@ -150,6 +150,154 @@ __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_const
   }
 }
 
+// ---- data parallel: one-shot all-reduce over NVLink peer memory, fused into the update -------
+// Every rank owns an exchange block in IPC-shared device memory:
+//     [64 x uint32 flags][bucket half 0][bucket half 1]
+// Step e (1-based, counted on the device: the launch carries nothing step-dependent, so CUDA
+// graphs replay it) uses half e & 1.  The pack kernel has written this rank's gradients into
+// its own half; this kernel (1) tells every peer "rank r has published step e" with a
+// system-scope release store into the peer's flag r, (2) waits until all local flags show
+// >= e, (3) reads every rank's half over NVLink and adds them IN RANK ORDER -- the same order
+// on every rank, so all replicas compute bit-identical weights -- and applies Adam.  Double
+// buffering makes a "done reading" handshake unnecessary: a rank packs step e + 1 only after
+// its step-e kernel has seen every peer's flag >= e, i.e. after every peer has finished reading
+// step e - 1, the previous user of that half.  Waits are bounded (a lost peer traps the kernel
+// instead of hanging the GPU).
+struct PeerArgs {
+  const float* bucket[8];    // each rank's exchange block, as mapped into THIS process
+  uint32_t* flags[8];        // each rank's flag array (first 256 bytes of its block)
+  int world, rank;
+  int64_t half_floats;       // floats per bucket half
+  int64_t offset[kMaxTensors];  // element offset of each tensor inside a half
+  uint32_t* epoch;           // device counter of completed exchanges (local)
+  unsigned int* arrivals;    // self-resetting: the last block of the grid bumps `epoch`
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer_f1(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <bool SHADOW>
+__global__ void __launch_bounds__(kThreads) adam_multi_peer_kernel(
+    const __grid_constant__ AdamArgs a, const __grid_constant__ PeerArgs x, float alpha, float b1,
+    float b2, float lnb1, float lnb2, float eps) {
+  pdl_entry();  // the pack kernel (this rank's half) has completed
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) {
+    const uint32_t e = *x.epoch + 1u;
+    s_epoch = e;
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      for (int r = 0; r < x.world; ++r)
+        if (r != x.rank) st_release_sys(x.flags[r] + x.rank, e);
+    }
+    const uint64_t t0 = timer_ns();
+    for (int r = 0; r < x.world; ++r) {
+      if (r == x.rank) continue;
+      while ((int32_t)(ld_acquire_sys(x.flags[x.rank] + r) - e) < 0) {
+        if (timer_ns() - t0 > 4000000000ull) __trap();  // a peer never arrived
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t e = s_epoch;
+  const int64_t half = (int64_t)(e & 1u) * x.half_floats;
+  const int t = find_tensor(a, blockIdx.x);
+  const float step = (float)(*a.step[t] + 1);
+  const float ic1 = 1.f / -expm1f(step * lnb1);
+  const float ic2 = 1.f / -expm1f(step * lnb2);
+  const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * a.chunk;
+  const int64_t n = a.n[t];
+  const float* p = a.p[t];
+  float* po = a.po[t];
+  float* __restrict__ m = a.m[t];
+  float* __restrict__ v = a.v[t];
+  float* const rnd = SHADOW ? a.rnd[t] : nullptr;
+  float* const spl = SHADOW ? a.spl[t] : nullptr;
+  const int64_t ps = SHADOW ? a.pstride[t] : 1;
+  const int P = SHADOW ? a.parts[t] : 1, lmask = SHADOW ? a.lmask[t] : 0;
+  const int64_t goff = 64 + half + x.offset[t];  // floats past the start of a block
+  const bool vec = (((uintptr_t)p | (uintptr_t)po | (uintptr_t)m | (uintptr_t)v | (uintptr_t)rnd |
+                     (uintptr_t)spl) & 15) == 0 && (!spl || (ps & 3) == 0) && (goff & 3) == 0;
+  const int64_t end = min(n, base + a.chunk);
+  if (vec) {
+    for (int64_t i = base + 4 * threadIdx.x; i + 3 < end; i += 4 * kThreads) {
+      float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < x.world; ++r) {  // rank order: identical sums on every replica
+        const float4 q = ld_peer_f4(x.bucket[r] + goff + i);
+        gg.x += q.x;
+        gg.y += q.y;
+        gg.z += q.z;
+        gg.w += q.w;
+      }
+      float4 pp = *reinterpret_cast<const float4*>(p + i);
+      float4 mm = *reinterpret_cast<float4*>(m + i);
+      float4 vv = *reinterpret_cast<float4*>(v + i);
+      adam1(pp.x, gg.x, mm.x, vv.x, b1, b2, ic1, ic2, alpha, eps);
+      adam1(pp.y, gg.y, mm.y, vv.y, b1, b2, ic1, ic2, alpha, eps);
+      adam1(pp.z, gg.z, mm.z, vv.z, b1, b2, ic1, ic2, alpha, eps);
+      adam1(pp.w, gg.w, mm.w, vv.w, b1, b2, ic1, ic2, alpha, eps);
+      *reinterpret_cast<float4*>(po + i) = pp;
+      *reinterpret_cast<float4*>(m + i) = mm;
+      *reinterpret_cast<float4*>(v + i) = vv;
+      if (SHADOW && (rnd || spl)) shadow4(pp, i, rnd, spl, ps, P, lmask);
+    }
+  }
+  const int64_t tail = vec ? end - ((end - base) & 3) : base;
+  for (int64_t i = tail + threadIdx.x; i < end; i += kThreads) {
+    float g = 0.f;
+    for (int r = 0; r < x.world; ++r) g += ld_peer_f1(x.bucket[r] + goff + i);
+    float pv = p[i];
+    adam1(pv, g, m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
+    po[i] = pv;
+    if (SHADOW && (rnd || spl)) shadow1(pv, i, rnd, spl, ps, P, lmask);
+  }
+  // every thread of this block has read the step count and the epoch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int blocks_t = (unsigned int)(a.block_start[t + 1] - a.block_start[t]);
+    if (atomicInc(&a.done[t], blocks_t - 1) == blocks_t - 1) *a.step[t] += 1;
+    if (atomicInc(x.arrivals, gridDim.x - 1) == gridDim.x - 1) *x.epoch = e;
+  }
+}
+
+// this rank's gradients -> its own bucket half of the NEXT exchange (epoch + 1)
+__global__ void __launch_bounds__(kThreads) pack_multi_peer_kernel(const __grid_constant__ AxpyArgs a,
+                                                                   const uint32_t* __restrict__ epoch,
+                                                                   int64_t half_floats) {
+  pdl_entry();
+  const int t = find_tensor(a, blockIdx.x);
+  const int64_t half = (int64_t)((*epoch + 1u) & 1u) * half_floats;
+  const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * kChunkSmall;
+  const int64_t end = min(a.n[t], base + kChunkSmall);
+  float* __restrict__ dst = a.p[t] + 64 + half + a.dst_offset[t];
+  const float* __restrict__ src = a.g[t];
+  for (int64_t i = base + threadIdx.x; i < end; i += kThreads) dst[i] = src[i];
+}
+
 // tensors without elements still count their steps
 __global__ void adam_advance_kernel(const __grid_constant__ AdamArgs a) {
   for (int t = threadIdx.x; t < a.count; t += blockDim.x)
@@ -213,12 +361,144 @@ int sp_adam_multi_out(int n_tensors, float* const* host_p, float* const* host_p_
                               eps, stream);
 }
 
+struct sp_peer_exchange_t {
+  int world, rank;
+  int64_t half_floats;
+  float* blocks[8];
+  uint32_t* epoch;        // device
+  unsigned int* arrivals; // device
+};
+
+static int adam_impl(int n_tensors, float* const* host_p, float* const* host_p_out,
+                     const float* const* host_g, float* const* host_m, float* const* host_v,
+                     const int64_t* host_numel, int32_t* const* host_step,
+                     float* const* host_rounded, float* const* host_split,
+                     const int64_t* host_block_elems, const int32_t* host_kind, float alpha,
+                     float beta1, float beta2, float eps, sp_stream_t stream,
+                     const sp_peer_exchange_t* peer, const int64_t* host_offsets);
+
 int sp_adam_multi_shadow(int n_tensors, float* const* host_p, float* const* host_p_out,
                          const float* const* host_g, float* const* host_m, float* const* host_v,
                          const int64_t* host_numel, int32_t* const* host_step,
                          float* const* host_rounded, float* const* host_split,
                          const int64_t* host_block_elems, const int32_t* host_kind, float alpha,
                          float beta1, float beta2, float eps, sp_stream_t stream) {
+  return adam_impl(n_tensors, host_p, host_p_out, host_g, host_m, host_v, host_numel, host_step,
+                   host_rounded, host_split, host_block_elems, host_kind, alpha, beta1, beta2, eps,
+                   stream, nullptr, nullptr);
+}
+
+// ---- peer-memory exchange: set-up ---------------------------------------------------------
+int sp_peer_alloc(size_t bytes, void** dev_ptr, void* handle64) {
+  SP_REQUIRE(dev_ptr && handle64 && bytes > 0, "bad argument");
+  void* p = nullptr;
+  SP_CHECK_CUDA(cudaMalloc(&p, bytes));
+  SP_CHECK_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return sp::set_error(SP_ERR_DRIVER, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return 0;
+}
+int sp_peer_open(const void* handle64, void** dev_ptr) {
+  SP_REQUIRE(dev_ptr && handle64, "bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess)
+    return sp::set_error(SP_ERR_DRIVER, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  *dev_ptr = p;
+  return 0;
+}
+int sp_peer_close(void* dev_ptr) {
+  if (dev_ptr) cudaIpcCloseMemHandle(dev_ptr);
+  return 0;
+}
+int sp_peer_free(void* dev_ptr) {
+  if (dev_ptr) cudaFree(dev_ptr);
+  return 0;
+}
+int sp_peer_exchange_create(int world, int rank, int64_t half_floats, void* const* blocks,
+                            void** out) {
+  SP_REQUIRE(out && blocks && world >= 2 && world <= 8 && rank >= 0 && rank < world,
+             "peer exchange: 2..8 ranks of one node");
+  SP_REQUIRE(half_floats > 0 && half_floats % 4 == 0, "half size must be a multiple of 4 floats");
+  auto* x = new sp_peer_exchange_t();
+  x->world = world;
+  x->rank = rank;
+  x->half_floats = half_floats;
+  for (int r = 0; r < world; ++r) x->blocks[r] = static_cast<float*>(blocks[r]);
+  void* words = nullptr;
+  if (cudaMalloc(&words, 64) != cudaSuccess || cudaMemset(words, 0, 64) != cudaSuccess) {
+    delete x;
+    return sp::set_error(SP_ERR_DRIVER, "peer exchange: counter allocation failed");
+  }
+  x->epoch = static_cast<uint32_t*>(words);
+  x->arrivals = static_cast<unsigned int*>(words) + 4;
+  *out = x;
+  return 0;
+}
+int sp_peer_exchange_destroy(void* exchange) {
+  auto* x = static_cast<sp_peer_exchange_t*>(exchange);
+  if (!x) return 0;
+  cudaFree(x->epoch);
+  delete x;
+  return 0;
+}
+
+int sp_adam_multi_peer(void* exchange, int n_tensors, float* const* host_p, float* const* host_p_out,
+                       const float* const* host_g, const int64_t* host_offsets,
+                       float* const* host_m, float* const* host_v, const int64_t* host_numel,
+                       int32_t* const* host_step, float* const* host_rounded,
+                       float* const* host_split, const int64_t* host_block_elems,
+                       const int32_t* host_kind, float alpha, float beta1, float beta2, float eps,
+                       sp_stream_t stream) {
+  auto* x = static_cast<sp_peer_exchange_t*>(exchange);
+  SP_REQUIRE(x != nullptr && host_offsets != nullptr, "peer exchange not set up");
+  SP_REQUIRE(n_tensors >= 1 && n_tensors <= kMaxTensors, "peer exchange: 1..24 tensors per call");
+  // this rank's gradients -> its half of the next exchange
+  {
+    AxpyArgs a;
+    a.count = 0;
+    int blocks = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+      const int64_t n = host_numel[i];
+      if (n <= 0) continue;
+      SP_REQUIRE(host_offsets[i] >= 0 && host_offsets[i] + n <= x->half_floats,
+                 "gradient does not fit the exchange bucket");
+      const int k = a.count++;
+      a.p[k] = x->blocks[x->rank];
+      a.g[k] = host_g[i];
+      a.n[k] = n;
+      a.dst_offset[k] = host_offsets[i];
+      a.block_start[k] = blocks;
+      blocks += (int)((n + kChunkSmall - 1) / kChunkSmall);
+    }
+    a.block_start[a.count] = blocks;
+    if (blocks > 0) {
+      sp::launch_pdl(pack_multi_peer_kernel, dim3(blocks), dim3(kThreads), 0, sp::as_stream(stream),
+                     a, (const uint32_t*)x->epoch, x->half_floats);
+      SP_CHECK_LAUNCH("pack_multi_peer");
+    }
+  }
+  return adam_impl(n_tensors, host_p, host_p_out, host_g, host_m, host_v, host_numel, host_step,
+                   host_rounded, host_split, host_block_elems, host_kind, alpha, beta1, beta2, eps,
+                   stream, x, host_offsets);
+}
+
+static int adam_impl(int n_tensors, float* const* host_p, float* const* host_p_out,
+                     const float* const* host_g, float* const* host_m, float* const* host_v,
+                     const int64_t* host_numel, int32_t* const* host_step,
+                     float* const* host_rounded, float* const* host_split,
+                     const int64_t* host_block_elems, const int32_t* host_kind, float alpha,
+                     float beta1, float beta2, float eps, sp_stream_t stream,
+                     const sp_peer_exchange_t* peer, const int64_t* host_offsets) {
   SP_REQUIRE(n_tensors >= 0, "negative tensor count");
   cudaStream_t st = sp::as_stream(stream);
   unsigned int* counters = adam_counters();
@@ -272,7 +552,25 @@ int sp_adam_multi_shadow(int n_tensors, float* const* host_p, float* const* host
       // beta as the double nearest to what the caller wrote (0.9f -> 0.9), like the reference
       const double b1 = strtod_round(beta1);
       const double b2 = strtod_round(beta2);
-      if (shadows)
+      if (peer) {
+        PeerArgs x;
+        x.world = peer->world;
+        x.rank = peer->rank;
+        x.half_floats = peer->half_floats;
+        for (int r = 0; r < peer->world; ++r) {
+          x.bucket[r] = peer->blocks[r];
+          x.flags[r] = reinterpret_cast<uint32_t*>(peer->blocks[r]);
+        }
+        for (int k = 0; k < a.count; ++k) x.offset[k] = host_offsets[first + k];
+        x.epoch = peer->epoch;
+        x.arrivals = peer->arrivals;
+        if (shadows)
+          sp::launch_pdl(adam_multi_peer_kernel<true>, dim3(blocks), dim3(kThreads), 0, st, a, x,
+                         alpha, (float)b1, (float)b2, (float)log(b1), (float)log(b2), eps);
+        else
+          sp::launch_pdl(adam_multi_peer_kernel<false>, dim3(blocks), dim3(kThreads), 0, st, a, x,
+                         alpha, (float)b1, (float)b2, (float)log(b1), (float)log(b2), eps);
+      } else if (shadows)
         sp::launch_pdl(adam_multi_kernel<true>, dim3(blocks), dim3(kThreads), 0, st, a, alpha,
                        (float)b1, (float)b2, (float)log(b1), (float)log(b2), eps);
       else

@@ -83,6 +83,7 @@ def shutdown() -> None:
     import torch.distributed as dist
 
     _nccl.update(comm=None, tried=False)  # the communicator dies with the process
+    _peer.update(tried=False, handle=None, half=0, blocks=None, own=None, plans={})
     _nccl.pop("fast", None)
     if _overlap["side"] is not None:
         _install_hook(False)
@@ -177,6 +178,94 @@ def _allreduce_sum_f32(ptr: int, count: int, tensor_view, stream=None) -> None:
         _abi.f.sp_allreduce_sum_f32(comm, ptr, count, A.stream() if stream is None else stream)
         return
     dist.all_reduce(tensor_view[:count], op=dist.ReduceOp.SUM)
+
+
+# --------------------------------------------------------------------------------------------
+# Peer-memory exchange: for small gradient buckets (both README models) the all-reduce is not a
+# library call at all -- every rank publishes its gradients in an IPC-shared block, and the
+# fused Adam kernel of every rank reads all blocks over NVLink and adds them in rank order
+# (csrc/optim.cu: adam_multi_peer_kernel).  One kernel does collective + update; nothing is
+# latency-bound on a ring or tree.  NCCL stays the path for large buckets, for sgd_step and
+# whenever this cannot be set up (SP_DP_PEER=0 turns it off).
+# --------------------------------------------------------------------------------------------
+_peer = {"tried": False, "handle": None, "half": 0, "blocks": None, "own": None, "plans": {}}
+_PEER_MAX_FLOATS = int(os.environ.get("SP_DP_PEER_MAX_FLOATS", str(1 << 20)))
+
+
+def _peer_exchange(total_floats: int):
+    """The exchange handle (an int) if one exists that carries `total_floats`, else None.
+    Created collectively on first use (every rank calls this at the same point of the same
+    program with the same size)."""
+    if total_floats > _PEER_MAX_FLOATS:
+        return None
+    if _peer["tried"]:
+        return _peer["handle"] if total_floats <= _peer["half"] else None
+    _peer["tried"] = True
+    world = _state["world"]
+    if (os.environ.get("SP_DP_PEER", "1") == "0" or _state["backend"] != "nccl" or world < 2
+            or world > 8 or int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) != world):
+        return None
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    ok = 1
+    own = C.c_void_p()
+    handle = (C.c_byte * 64)()
+    half = _PEER_MAX_FLOATS
+    lib = _abi.load()
+    try:
+        if lib.sp_peer_alloc(256 + 8 * half, C.byref(own), handle) != 0:
+            ok = 0
+    except Exception:  # noqa: BLE001
+        ok = 0
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bytes(handle) if ok else None)
+    blocks = (C.c_void_p * world)()
+    if ok and all(g is not None for g in gathered):
+        for r, raw in enumerate(gathered):
+            if r == _state["rank"]:
+                blocks[r] = own.value
+                continue
+            h = (C.c_byte * 64).from_buffer_copy(raw)
+            p = C.c_void_p()
+            if lib.sp_peer_open(h, C.byref(p)) != 0:
+                ok = 0
+                break
+            blocks[r] = p.value
+    else:
+        ok = 0
+    ex = C.c_void_p()
+    if ok and lib.sp_peer_exchange_create(world, _state["rank"], half, blocks, C.byref(ex)) != 0:
+        ok = 0
+    flag = torch.tensor([ok], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all or nobody (also: nobody starts a step early)
+    if int(flag.item()) != 1:
+        return None
+    _peer.update(handle=ex.value, half=half, blocks=blocks, own=own.value)
+    return _peer["handle"] if total_floats <= half else None
+
+
+def peer_plan(grads):
+    """(exchange handle, int64 offsets table) when the gradients of this update travel through
+    the peer-memory exchange, else None (the caller all-reduces them with NCCL)."""
+    if not (_state["initialized"] and _state["world"] > 1) or len(grads) > 24:
+        return None
+    shapes = tuple([g.shape for g in grads])
+    plan = _peer["plans"].get(shapes)
+    if plan is None:
+        layout = bucket_layout([g.size for g in grads])
+        handle = _peer_exchange(layout[-1])
+        plan = _peer["plans"][shapes] = (handle, _abi.dims(layout[:-1])) if handle else False
+    return plan or None
+
+
+def exchange_description() -> str:
+    if _peer["handle"] is not None:
+        return ("one-shot all-reduce over NVLink peer memory fused into the Adam kernel "
+                "(buckets <= %d floats); NCCL all-reduce otherwise" % _peer["half"])
+    return "NCCL all-reduce of one flat gradient bucket"
 
 
 def bucket_layout(sizes) -> list[int]:

@@ -219,9 +219,14 @@ class Adam:
             if type(g) is not DeviceArray or g.shape != v._array.shape:
                 g = _device_gradient(v, gradients)
             grads.append(g)
+        peer = None
         if (_distributed.is_initialized() and _distributed.world_size() > 1
                 and not getattr(gradients, "_reduced", False)):
-            grads = _distributed.allreduce_gradients(grads, variables)
+            # small buckets: the sum over the ranks happens inside the update kernel, over
+            # NVLink peer memory; otherwise NCCL all-reduces the bucket first
+            peer = _distributed.peer_plan(grads)
+            if peer is None:
+                grads = _distributed.allreduce_gradients(grads, variables)
         n = len(variables)
         # state creation and the pointer tables of moments / step counters are keyed by the
         # identity of the variables: they never change once made
@@ -245,8 +250,13 @@ class Adam:
             # static buffers: update in place.  (Nothing is settled first: every buffer of a
             # captured step is overwritten by the next replay anyway, so values that were not
             # evaluated inside the captured function cannot be read afterwards -- capture.py.)
-            F.sp_adam_multi_out(n, p_tab, p_tab, g_tab, m_tab, v_tab, numel, step_tab, self.alpha,
-                                self.beta1, self.beta2, self.eps, A.stream())
+            if peer is not None:
+                F.sp_adam_multi_peer(peer[0], n, p_tab, p_tab, g_tab, peer[1], m_tab, v_tab, numel,
+                                     step_tab, None, None, None, None, self.alpha, self.beta1,
+                                     self.beta2, self.eps, A.stream())
+            else:
+                F.sp_adam_multi_out(n, p_tab, p_tab, g_tab, m_tab, v_tab, numel, step_tab,
+                                    self.alpha, self.beta1, self.beta2, self.eps, A.stream())
             A.note_inplace_update()
             return
         if outs is None:
@@ -276,8 +286,13 @@ class Adam:
             if rest:
                 rest_jobs.append((new, False, rest))
         if shadow_rows is None:
-            F.sp_adam_multi_out(n, p_tab, o_tab, g_tab, m_tab, v_tab, numel, step_tab, self.alpha,
-                                self.beta1, self.beta2, self.eps, A.stream())
+            if peer is not None:
+                F.sp_adam_multi_peer(peer[0], n, p_tab, o_tab, g_tab, peer[1], m_tab, v_tab, numel,
+                                     step_tab, None, None, None, None, self.alpha, self.beta1,
+                                     self.beta2, self.eps, A.stream())
+            else:
+                F.sp_adam_multi_out(n, p_tab, o_tab, g_tab, m_tab, v_tab, numel, step_tab,
+                                    self.alpha, self.beta1, self.beta2, self.eps, A.stream())
         else:
             key = (tuple(shadow_rows[0]), tuple(shadow_rows[1]), tuple(shadow_rows[2]),
                    tuple(shadow_rows[3]))
@@ -288,9 +303,14 @@ class Adam:
                 tabs = _shadow_tables[key] = (
                     _ptr_table(key[0]), _ptr_table(key[1]), _abi.dims(key[2]),
                     (C.c_int32 * n)(*key[3]))
-            F.sp_adam_multi_shadow(n, p_tab, o_tab, g_tab, m_tab, v_tab, numel, step_tab, tabs[0],
-                                   tabs[1], tabs[2], tabs[3], self.alpha, self.beta1, self.beta2,
-                                   self.eps, A.stream())
+            if peer is not None:
+                F.sp_adam_multi_peer(peer[0], n, p_tab, o_tab, g_tab, peer[1], m_tab, v_tab, numel,
+                                     step_tab, tabs[0], tabs[1], tabs[2], tabs[3], self.alpha,
+                                     self.beta1, self.beta2, self.eps, A.stream())
+            else:
+                F.sp_adam_multi_shadow(n, p_tab, o_tab, g_tab, m_tab, v_tab, numel, step_tab,
+                                       tabs[0], tabs[1], tabs[2], tabs[3], self.alpha, self.beta1,
+                                       self.beta2, self.eps, A.stream())
         for v, new in zip(variables, news):
             v._array = new  # rebind (sp.py:583)
         if rest_jobs:

@@ -34,6 +34,7 @@ def main():
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), losses=np.array(losses),
              overlapped_steps=np.array(overlapped),
              replayed_updates=np.array(sp.steady.stats["replays_u"]),
+             peer_exchange=np.array(int(sp.distributed._peer["handle"] is not None)),
              **{f"w{i}": np.asarray(p.array) for i, p in enumerate(wl.learnables)})
     sp.distributed.barrier()
     sp.distributed.shutdown()

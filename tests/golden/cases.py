@@ -65,6 +65,8 @@ MATMUL_CASES = [
     ("mlp_fc1", (200, 784), (784, 100)),
     ("cnn_fc", (128, 1152), (1152, 10)),
     ("odd", (37, 53), (53, 19)),
+    # whole 32 / 64-column blocks: eligible for the 2-SM TMA kernels (a GEMM is a 1 x 1 conv)
+    ("tma_small", (300, 96), (96, 128)),
 ]
 
 # name, shape, axis (sp.py:257-279: for axis != last the reference lays the result out in

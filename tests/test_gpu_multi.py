@@ -23,9 +23,12 @@ def _free_port():
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
                     reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("overlap,steady,steps", [("1", "0", 6), ("0", "0", 6), ("0", "1", 12)],
-                         ids=["overlapped", "single_allreduce", "steady_replay"])
-def test_data_parallel_equals_single_gpu(tmp_path, overlap, steady, steps):
+@pytest.mark.parametrize("overlap,steady,steps,peer",
+                         [("1", "0", 6, "0"), ("0", "0", 6, "0"), ("0", "1", 12, "0"),
+                          ("0", "0", 6, "1"), ("0", "1", 12, "1")],
+                         ids=["nccl_overlapped", "nccl_single_allreduce", "nccl_steady_replay",
+                              "peer_memory_eager", "peer_memory_steady_replay"])
+def test_data_parallel_equals_single_gpu(tmp_path, overlap, steady, steps, peer):
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
@@ -34,7 +37,10 @@ def test_data_parallel_equals_single_gpu(tmp_path, overlap, steady, steps):
     # "1" forces the two-part exchange overlapped with the backward pass (by default only
     # large gradient buckets use it), "0" the single all-reduce on the compute stream
     # steady "1": the loop is replayed from CUDA graphs that contain the NCCL all-reduce
-    env = dict(os.environ, SP_DP_OVERLAP=overlap, SP_STEADY=steady, SP_TEST_STEPS=str(steps))
+    # peer "1": no collective library call at all -- the fused Adam kernel of each rank sums the
+    # ranks' gradient buckets over NVLink peer memory (csrc/optim.cu)
+    env = dict(os.environ, SP_DP_OVERLAP=overlap, SP_STEADY=steady, SP_TEST_STEPS=str(steps),
+               SP_DP_PEER=peer)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     single = np.load(tmp_path / "single.npz")
@@ -45,6 +51,7 @@ def test_data_parallel_equals_single_gpu(tmp_path, overlap, steady, steps):
         assert all(int(r["replayed_updates"]) >= steps - 6 for r in ranks)
     else:
         assert all(int(r["replayed_updates"]) == 0 for r in ranks)
+    assert all(int(r["peer_exchange"]) == int(peer) for r in ranks)
     for key in single.files:
         # every rank ends with identical weights ...
         assert np.array_equal(ranks[0][key], ranks[1][key]), key

@@ -178,6 +178,26 @@ def test_skinny_matmul_long_k(m, k, n):
     assert np.array_equal(np.asarray(y.array), np.asarray(y2.array))
 
 
+@pytest.mark.parametrize("m,k,n", [(2048, 512, 256), (1000, 1024, 192), (4096, 256, 512)])
+def test_matmul_on_the_two_sm_tma_kernels(m, k, n):
+    """Dense GEMMs with whole 32 / 64-column blocks and enough work run as 1 x 1 convolutions on
+    the 2-SM TMA-fed tcgen05 kernels (NN = fprop, NT = dgrad, TN = wgrad; contract_api.cu):
+    forward and both gradients against float64, in the single-pass TF32 mode that takes them."""
+    sp.set_precision("tf32x1")
+    try:
+        rng = np.random.default_rng(m + k + n)
+        a, b = rng.random((m, k)) - 0.5, rng.random((k, n)) - 0.5
+        av, bv = sp.Variable(a), sp.Variable(b)
+        y = sp.matmul(av, bv)
+        assert_close(y.array, a @ b, 2e-3, "y")
+        gy = rng.random((m, n)) - 0.5
+        g = sp.get_gradients(sp.mul(y, sp.Variable(gy)))
+        assert_close(g[av], gy @ b.T, 2e-3, "dA")
+        assert_close(g[bv], a.T @ gy, 2e-3, "dB")
+    finally:
+        sp.set_precision("tf32")
+
+
 def test_elementwise_checksums_full_size():
     rng = np.random.default_rng(2)
     x = rng.random((128, 30, 30, 32)) - 0.5
