@@ -154,10 +154,11 @@ __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const __grid_const
 // Every rank owns an exchange block in IPC-shared device memory:
 //     [64 x uint32 flags][bucket half 0][bucket half 1]
 // Step e (1-based, counted on the device: the launch carries nothing step-dependent, so CUDA
-// graphs replay it) uses half e & 1.  The pack kernel has written this rank's gradients into
-// its own half; this kernel (1) tells every peer "rank r has published step e" with a
-// system-scope release store into the peer's flag r, (2) waits until all local flags show
-// >= e, (3) reads every rank's half over NVLink and adds them IN RANK ORDER -- the same order
+// graphs replay it) uses half e & 1.  The kernel (0) copies this rank's gradients into its own
+// half, block by block; the block that completes it (1) tells every peer "rank r has published
+// step e" with a system-scope release store into the peer's flag r; every block (2) waits
+// until all local flags show >= e, (3) reads every rank's half over NVLink and adds them IN
+// RANK ORDER -- the same order
 // on every rank, so all replicas compute bit-identical weights -- and applies Adam.  Double
 // buffering makes a "done reading" handshake unnecessary: a rank packs step e + 1 only after
 // its step-e kernel has seen every peer's flag >= e, i.e. after every peer has finished reading
@@ -171,6 +172,9 @@ struct PeerArgs {
   int64_t offset[kMaxTensors];  // element offset of each tensor inside a half
   uint32_t* epoch;           // device counter of completed exchanges (local)
   unsigned int* arrivals;    // self-resetting: the last block of the grid bumps `epoch`
+  unsigned int* packed;      // self-resetting: the last block to have published its chunk of
+                             // this rank's gradients signals the peers
+  const float* grad[kMaxTensors];  // this rank's own gradients (published by this kernel)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -204,28 +208,45 @@ template <bool SHADOW>
 __global__ void __launch_bounds__(kThreads) adam_multi_peer_kernel(
     const __grid_constant__ AdamArgs a, const __grid_constant__ PeerArgs x, float alpha, float b1,
     float b2, float lnb1, float lnb2, float eps) {
-  pdl_entry();  // the pack kernel (this rank's half) has completed
+  pdl_entry();
   __shared__ uint32_t s_epoch;
-  if (threadIdx.x == 0) {
-    const uint32_t e = *x.epoch + 1u;
-    s_epoch = e;
-    if (blockIdx.x == 0) {
-      __threadfence_system();
-      for (int r = 0; r < x.world; ++r)
-        if (r != x.rank) st_release_sys(x.flags[r] + x.rank, e);
-    }
-    const uint64_t t0 = timer_ns();
-    for (int r = 0; r < x.world; ++r) {
-      if (r == x.rank) continue;
-      while ((int32_t)(ld_acquire_sys(x.flags[x.rank] + r) - e) < 0) {
-        if (timer_ns() - t0 > 4000000000ull) __trap();  // a peer never arrived
-      }
-    }
-  }
+  if (threadIdx.x == 0) s_epoch = *x.epoch + 1u;
   __syncthreads();
   const uint32_t e = s_epoch;
   const int64_t half = (int64_t)(e & 1u) * x.half_floats;
   const int t = find_tensor(a, blockIdx.x);
+  {
+    // phase 1: publish this block's chunk of this rank's gradients in its own bucket half;
+    // the block that completes the rank's bucket tells the peers
+    const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * a.chunk;
+    const int64_t end = min(a.n[t], base + a.chunk);
+    float* __restrict__ mine = const_cast<float*>(x.bucket[x.rank]) + 64 + half + x.offset[t];
+    const float* __restrict__ g = x.grad[t];
+    if ((((uintptr_t)g | (uintptr_t)mine) & 15) == 0) {
+      for (int64_t i = base + 4 * threadIdx.x; i + 3 < end; i += 4 * kThreads)
+        *reinterpret_cast<float4*>(mine + i) = ld_stream_f4(g + i);
+      for (int64_t i = end - ((end - base) & 3) + threadIdx.x; i < end; i += kThreads) mine[i] = g[i];
+    } else {
+      for (int64_t i = base + threadIdx.x; i < end; i += kThreads) mine[i] = g[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicInc(x.packed, gridDim.x - 1) == gridDim.x - 1) {
+        __threadfence_system();
+        for (int r = 0; r < x.world; ++r)
+          if (r != x.rank) st_release_sys(x.flags[r] + x.rank, e);
+      }
+      const uint64_t t0 = timer_ns();
+      for (int r = 0; r < x.world; ++r) {
+        if (r == x.rank) continue;
+        while ((int32_t)(ld_acquire_sys(x.flags[x.rank] + r) - e) < 0) {
+          if (timer_ns() - t0 > 4000000000ull) __trap();  // a peer never arrived
+        }
+      }
+    }
+    __syncthreads();
+  }
   const float step = (float)(*a.step[t] + 1);
   const float ic1 = 1.f / -expm1f(step * lnb1);
   const float ic2 = 1.f / -expm1f(step * lnb2);
@@ -245,14 +266,21 @@ __global__ void __launch_bounds__(kThreads) adam_multi_peer_kernel(
   const int64_t end = min(n, base + a.chunk);
   if (vec) {
     for (int64_t i = base + 4 * threadIdx.x; i + 3 < end; i += 4 * kThreads) {
+      // all NVLink loads are issued before the first add (an in-order warp would otherwise
+      // pay one peer round trip per rank: 38 us per update at 8 ranks, measured)
+      float4 q[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < x.world) q[r] = ld_peer_f4(x.bucket[r] + goff + i);
       float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < x.world; ++r) {  // rank order: identical sums on every replica
-        const float4 q = ld_peer_f4(x.bucket[r] + goff + i);
-        gg.x += q.x;
-        gg.y += q.y;
-        gg.z += q.z;
-        gg.w += q.w;
-      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)  // rank order: identical sums on every replica
+        if (r < x.world) {
+          gg.x += q[r].x;
+          gg.y += q[r].y;
+          gg.z += q[r].z;
+          gg.w += q[r].w;
+        }
       float4 pp = *reinterpret_cast<const float4*>(p + i);
       float4 mm = *reinterpret_cast<float4*>(m + i);
       float4 vv = *reinterpret_cast<float4*>(v + i);
@@ -268,8 +296,14 @@ __global__ void __launch_bounds__(kThreads) adam_multi_peer_kernel(
   }
   const int64_t tail = vec ? end - ((end - base) & 3) : base;
   for (int64_t i = tail + threadIdx.x; i < end; i += kThreads) {
+    float q1[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < x.world) q1[r] = ld_peer_f1(x.bucket[r] + goff + i);
     float g = 0.f;
-    for (int r = 0; r < x.world; ++r) g += ld_peer_f1(x.bucket[r] + goff + i);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < x.world) g += q1[r];
     float pv = p[i];
     adam1(pv, g, m[i], v[i], b1, b2, ic1, ic2, alpha, eps);
     po[i] = pv;
@@ -282,20 +316,6 @@ __global__ void __launch_bounds__(kThreads) adam_multi_peer_kernel(
     if (atomicInc(&a.done[t], blocks_t - 1) == blocks_t - 1) *a.step[t] += 1;
     if (atomicInc(x.arrivals, gridDim.x - 1) == gridDim.x - 1) *x.epoch = e;
   }
-}
-
-// this rank's gradients -> its own bucket half of the NEXT exchange (epoch + 1)
-__global__ void __launch_bounds__(kThreads) pack_multi_peer_kernel(const __grid_constant__ AxpyArgs a,
-                                                                   const uint32_t* __restrict__ epoch,
-                                                                   int64_t half_floats) {
-  pdl_entry();
-  const int t = find_tensor(a, blockIdx.x);
-  const int64_t half = (int64_t)((*epoch + 1u) & 1u) * half_floats;
-  const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * kChunkSmall;
-  const int64_t end = min(a.n[t], base + kChunkSmall);
-  float* __restrict__ dst = a.p[t] + 64 + half + a.dst_offset[t];
-  const float* __restrict__ src = a.g[t];
-  for (int64_t i = base + threadIdx.x; i < end; i += kThreads) dst[i] = src[i];
 }
 
 // tensors without elements still count their steps
@@ -462,30 +482,11 @@ int sp_adam_multi_peer(void* exchange, int n_tensors, float* const* host_p, floa
   auto* x = static_cast<sp_peer_exchange_t*>(exchange);
   SP_REQUIRE(x != nullptr && host_offsets != nullptr, "peer exchange not set up");
   SP_REQUIRE(n_tensors >= 1 && n_tensors <= kMaxTensors, "peer exchange: 1..24 tensors per call");
-  // this rank's gradients -> its half of the next exchange
-  {
-    AxpyArgs a;
-    a.count = 0;
-    int blocks = 0;
-    for (int i = 0; i < n_tensors; ++i) {
-      const int64_t n = host_numel[i];
-      if (n <= 0) continue;
-      SP_REQUIRE(host_offsets[i] >= 0 && host_offsets[i] + n <= x->half_floats,
-                 "gradient does not fit the exchange bucket");
-      const int k = a.count++;
-      a.p[k] = x->blocks[x->rank];
-      a.g[k] = host_g[i];
-      a.n[k] = n;
-      a.dst_offset[k] = host_offsets[i];
-      a.block_start[k] = blocks;
-      blocks += (int)((n + kChunkSmall - 1) / kChunkSmall);
-    }
-    a.block_start[a.count] = blocks;
-    if (blocks > 0) {
-      sp::launch_pdl(pack_multi_peer_kernel, dim3(blocks), dim3(kThreads), 0, sp::as_stream(stream),
-                     a, (const uint32_t*)x->epoch, x->half_floats);
-      SP_CHECK_LAUNCH("pack_multi_peer");
-    }
+  for (int i = 0; i < n_tensors; ++i) {
+    const int64_t n = host_numel[i] > 0 ? host_numel[i] : 0;
+    SP_REQUIRE(host_offsets[i] >= 0 && host_offsets[i] % 4 == 0 &&
+                   host_offsets[i] + n <= x->half_floats,
+               "gradient does not fit the exchange bucket");
   }
   return adam_impl(n_tensors, host_p, host_p_out, host_g, host_m, host_v, host_numel, host_step,
                    host_rounded, host_split, host_block_elems, host_kind, alpha, beta1, beta2, eps,
@@ -561,9 +562,13 @@ static int adam_impl(int n_tensors, float* const* host_p, float* const* host_p_o
           x.bucket[r] = peer->blocks[r];
           x.flags[r] = reinterpret_cast<uint32_t*>(peer->blocks[r]);
         }
-        for (int k = 0; k < a.count; ++k) x.offset[k] = host_offsets[first + k];
+        for (int k = 0; k < a.count; ++k) {
+          x.offset[k] = host_offsets[first + k];
+          x.grad[k] = host_g[first + k];
+        }
         x.epoch = peer->epoch;
         x.arrivals = peer->arrivals;
+        x.packed = peer->arrivals + 4;
         if (shadows)
           sp::launch_pdl(adam_multi_peer_kernel<true>, dim3(blocks), dim3(kThreads), 0, st, a, x,
                          alpha, (float)b1, (float)b2, (float)log(b1), (float)log(b2), eps);
