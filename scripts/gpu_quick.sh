@@ -1,5 +1,5 @@
 #!/bin/bash
-for bn in 0 64; do
-echo "== SP_TMA2_BN=$bn"
-SP_TMA2_BN=$bn python scripts/steady_parts.py cnn 128 2>&1 | tail -2
-done
+mkdir -p gpurun_out
+timeout 1500 python scripts/op_sweep_grid.py --out gpurun_out/r02_op_sweep_grid_v2.json > gpurun_out/r02_op_sweep_grid_v2.log 2>&1; echo sweep rc=$?
+tail -2 gpurun_out/r02_op_sweep_grid_v2.log | cut -c1-600
+bash scripts/gpu_round.sh
