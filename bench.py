@@ -643,7 +643,7 @@ def run_ours(args):
                         "frac": achieved / peak}
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
                 for prefix, row in json.load(fh).items():
                     if desc.startswith(prefix):
                         traffic = row["dram_bytes_per_launch"]
@@ -651,7 +651,7 @@ def run_ours(args):
             traffic = None
         roofline.update({
             "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
-            "ncu --set full capture of this kernel at this shape (profiles/r01_ncu_traffic.json); "
+            "ncu --set full capture of this kernel at this shape (profiles/r02_ncu_traffic.json); "
             "null when the dominant kernel has no capture", "kernel": desc, "avg_launch_ms": avg_ms, "launches_timed": len(durs),
             "algorithmic_work_per_launch": work, "peak_source": peak_note,
             "share_of_step": avg_ms / ms_per_step,

@@ -1,9 +1,9 @@
 #!/bin/bash
-# ncu --set full of one training step (24 kernels) of a short bench run; only after the same
-# command exited 0 without ncu
+# ncu --set full of one eager CIFAR training step (21 kernels, compensated TF32); only after the
+# same command exited 0 without ncu
 mkdir -p gpurun_out
-timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph --no-extras > gpurun_out/ncu_plain.log 2>&1 && \
-timeout 1200 ncu --set full --clock-control none --import-source on -s 779 -c 24 \
-   -o gpurun_out/prof_step_v4 -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph --no-extras > gpurun_out/ncu_full4.log 2>&1
-tail -2 gpurun_out/ncu_full4.log | cut -c1-200
-ls -la gpurun_out/prof_step_v4.ncu-rep
+timeout 300 python scripts/ncu_step.py cnn 128 8 > gpurun_out/ncu_plain.log 2>&1 && \
+timeout 1500 ncu --set full --clock-control none --import-source on -s 126 -c 21 \
+   -o gpurun_out/r02_prof_step -f python scripts/ncu_step.py cnn 128 8 > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log | cut -c1-200
+ls -la gpurun_out/r02_prof_step.ncu-rep
