@@ -878,6 +878,9 @@ def _matmul_plan(a_shape, b_shape):
     return M, K, N, a_batch, b_batch, ra, rb, batch_shape, math.prod(batch_shape)
 
 
+_X3_MIN_FLOP = float(os.environ.get("SP_X3_MIN_FLOP", "2e8"))  # below: exact fp32 forward GEMM
+
+
 def matmul(a: Variable, b: Variable) -> Variable:
     "Matrix multiplication (sp.py:239-247)."
     av, bv = a.array, b.array
@@ -896,6 +899,12 @@ def matmul(a: Variable, b: Variable) -> Variable:
                 lambda out: F.sp_gemm(0, 0, rows, N, K, av.ptr, K, 0, bv.ptr, N, 0, out.ptr, N,
                                       rows * N, 1, fwd_prec, A.stream()),
                 ("matmul", av, bv, rows, N, K))
+        elif _compensate and N > 16 and rows and K and 2.0 * rows * N * K < _X3_MIN_FLOP:
+            # a small product (the README MLP's layers: 31 MFLOP): exact fp32 on CUDA cores,
+            # K split over the chip -- one launch pair instead of operand splits plus a
+            # tensor-core kernel that would run its 3K-long loop on two CTAs
+            value = _gemm(0, 0, rows, N, K, av, K, 0, bv, N, 0, 1, a_batch + (M, N),
+                          _abi.PRECISION_FP32)
         elif _compensate and N > 16 and rows and K:
             # error-compensated forward product (3xTF32) as ONE tensor-core GEMM over a
             # contraction axis of 3K: [a_r | a_l | a_r] . [b_r ; b_r ; b_l]  (csrc/tf32.cu)
