@@ -274,6 +274,17 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
                     int precision, void* workspace, size_t workspace_bytes,
                     sp_stream_t stream);
 
+/* Filter gradient of a conv whose output went through leaky_relu and a 2x2 / stride-2 maxpool2d
+ * (sp.py:231-236, 282-300), straight from the POOLED gradient: what sp_maxpool2d_leaky_bwd
+ * followed by sp_conv2d_wgrad compute, without the full-resolution gradient tensor in between
+ * (bit-identical).  y_pooled: the pool's output (its sign is leaky's slope at the argmax).
+ * Only geometries for which sp_conv2d_wgrad_pooled_supported sets *supported = 1. */
+int sp_conv2d_wgrad_pooled_supported(const sp_conv_geom* g, int precision, int* supported);
+int sp_conv2d_wgrad_pooled(const float* x, const float* g_pooled, const uint8_t* argmax,
+                           const float* y_pooled, float* dw, const sp_conv_geom* g, float alpha,
+                           int precision, void* workspace, size_t workspace_bytes,
+                           sp_stream_t stream);
+
 /* ---- TF32 error compensation (no reference counterpart: the reference computes in float64;
  * this is what keeps the tensor-core path within the stated 2e-3 of it, csrc/tf32.cu) ------ */
 #define SP_SPLIT_RL 0  /* parts (r, l)                                                        */

@@ -1,3 +1,3 @@
 #!/bin/bash
-python scripts/steady_parts.py mlp 200 2>&1 | tail -2
-SP_STEADY=0 python scripts/step_profile.py mlp 200 2>&1 | tail -30
+timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -6
+SP_STEADY_SPECULATE=1 timeout 600 python -m pytest tests/test_gpu_steady.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3

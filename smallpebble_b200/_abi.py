@@ -93,6 +93,9 @@ SIGNATURES = {
     "sp_conv2d_dgrad_leaky": (C.c_int, [vp, vp, vp, vp, C.POINTER(ConvGeom), C.c_int, f32, vp]),
     "sp_conv2d_wgrad_workspace": (sz, [C.POINTER(ConvGeom), C.c_int]),
     "sp_conv2d_wgrad": (C.c_int, [vp, vp, vp, C.POINTER(ConvGeom), C.c_int, vp, sz, vp]),
+    "sp_conv2d_wgrad_pooled_supported": (C.c_int, [C.POINTER(ConvGeom), C.c_int, C.POINTER(C.c_int)]),
+    "sp_conv2d_wgrad_pooled": (C.c_int, [vp, vp, vp, vp, vp, C.POINTER(ConvGeom), f32, C.c_int, vp,
+                                         sz, vp]),
     "sp_adam_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                 C.POINTER(vp), p_i64, C.POINTER(vp), f32, f32, f32, f32, vp]),
     "sp_adam_multi_out": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
@@ -136,7 +139,7 @@ _LAUNCHING = {
                  "sp_debug_tma2_trace", "sp_host_is_pinned", "sp_stream_create", "sp_event_create",
                  "sp_event_record", "sp_stream_wait_event", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
                  "sp_conv2d_wgrad_workspace", "sp_set_tf32_output_rounding", "sp_conv2d_x3_plan",
-                 "sp_set_scratch_lane", "sp_nccl_load", "sp_nccl_unique_id", "sp_nccl_init",
+                 "sp_set_scratch_lane", "sp_conv2d_wgrad_pooled_supported", "sp_nccl_load", "sp_nccl_unique_id", "sp_nccl_init",
                  "sp_allreduce_sum_f32", "sp_nccl_destroy", "sp_peer_alloc", "sp_peer_open",
                  "sp_peer_close", "sp_peer_free", "sp_peer_exchange_create",
                  "sp_peer_exchange_destroy")

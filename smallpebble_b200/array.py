@@ -217,6 +217,25 @@ def trim_pool() -> None:
     _scalar_ones.clear()
 
 
+_read_side = {}
+
+
+def _read_stream() -> int:
+    """A non-blocking stream of our own for early host reads (one per device)."""
+    st = _read_side.get(_device_index)
+    if st is None:
+        slot = (C.c_void_p * 1)()
+        F.sp_stream_create(slot)
+        st = _read_side[_device_index] = slot[0]
+    return st
+
+
+def new_event() -> int:
+    slot = (C.c_void_p * 1)()
+    F.sp_event_create(slot)
+    return slot[0]
+
+
 _scalar_ones = {}  # shape -> read-only device constant 1.0 (the gradient seed of a scalar loss)
 
 
@@ -245,7 +264,7 @@ _prod = math.prod
 
 class DeviceArray:
     __slots__ = ("_buf", "_ptr", "shape", "dtype", "size", "_host", "_thunk", "_tag", "_aux",
-                 "_tf32", "_shadow", "__weakref__")
+                 "_tf32", "_shadow", "_ready", "__weakref__")
     __array_priority__ = 1000.0
 
     def __init__(self, shape, dtype=FLOAT, buf=None, ptr=None, host=None):
@@ -260,6 +279,7 @@ class DeviceArray:
         self._aux = None  # by-product of the producing kernel, e.g. ("colsum0", column sums)
         self._tf32 = None    # True: every value is TF32-representable (rounded by its producer)
         self._shadow = None  # [epoch, rounded copy, {(kind, block): split copy}] (tf32_shadows)
+        self._ready = None   # event after which the contents are final (steady.py: read early)
 
     # ---- construction ---------------------------------------------------------------------
     @staticmethod
@@ -283,6 +303,7 @@ class DeviceArray:
         self._aux = None
         self._tf32 = None
         self._shadow = None
+        self._ready = None
         nbytes = (size or 1) * dtype.itemsize
         if _pool_bypass or nbytes > _POOL_MAX_BLOCK:
             self._buf = buf = _torch.empty(nbytes, dtype=_torch.uint8, device=dev)
@@ -318,6 +339,7 @@ class DeviceArray:
         self._aux = None
         self._tf32 = None
         self._shadow = None
+        self._ready = None
         self._thunk = thunk
         self._tag = tag
         if len(_pending_refs) > 512:  # drop the dead and the launched
@@ -429,7 +451,15 @@ class DeviceArray:
         if self._ptr is None:
             return np.array(self._host, dtype=self.dtype, copy=True)
         out = np.empty(self.shape, self.dtype)
-        F.sp_memcpy_d2h(out.ctypes.data, self._ptr, out.nbytes, stream())
+        if self._ready is not None:
+            # the contents were final at this event (the result of a replayed forward pass):
+            # read them on the copy stream as soon as it has fired, without waiting for work
+            # enqueued behind it on the compute stream (steady.py's speculative backward pass)
+            side = _read_stream()
+            F.sp_stream_wait_event(side, self._ready)
+            F.sp_memcpy_d2h(out.ctypes.data, self._ptr, out.nbytes, side)
+        else:
+            F.sp_memcpy_d2h(out.ctypes.data, self._ptr, out.nbytes, stream())
         _counters["d2h_bytes"] += out.nbytes
         return out
 
@@ -499,6 +529,7 @@ class DeviceArray:
         out._aux = None
         out._tf32 = self._tf32
         out._shadow = None
+        out._ready = self._ready
         return out
 
     def copy(self) -> "DeviceArray":
@@ -563,7 +594,7 @@ class DeviceArray:
 
     def _rebind(self, other: "DeviceArray"):
         self._buf, self._ptr, self._host = other._buf, other.ptr, None
-        self._tf32, self._shadow = other._tf32, None
+        self._tf32, self._shadow, self._ready = other._tf32, None, None
         return self
 
     def __iadd__(self, o):
@@ -838,6 +869,7 @@ def accumulate_(dst: DeviceArray, src: DeviceArray) -> DeviceArray:
     dst._aux = None  # by-products described the old contents
     dst._tf32 = None  # a sum of TF32 values is not a TF32 value
     dst._shadow = None
+    dst._ready = None
     return dst
 
 

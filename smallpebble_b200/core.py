@@ -366,6 +366,7 @@ def _get_gradients(variable: Variable) -> dict:
                             return get(child)
 
                         job.child = child
+                        job.fuses = getattr(multiply_by_locgrad, "fuses_pending", None)
                         fork(job, path_value)
                         continue
                 elif not _eager_leaf_grads:
@@ -616,9 +617,20 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
         if tag is not None and tag[0] == "maxpool2d_bwd" and tag[1] is y:
             # the upstream gradient is a pool gradient that has not been launched: one kernel
             # scatters it and applies this op's slope
-            _, _, g0, idx, geom = tag
-            F.sp_maxpool2d_leaky_bwd(g0.ptr, idx.ptr, x.ptr, dx.ptr, *geom, alpha, A.stream())
-            dx._tf32 = rounded  # rounded as stored: an operand of the conv gradients
+            _, _, g0, idx, geom, ypool = tag
+
+            def launch_pool_bwd(out):
+                r = _want_rounding(a)  # (the library-global switch may have moved since)
+                F.sp_maxpool2d_leaky_bwd(g0.ptr, idx.ptr, x.ptr, out.ptr, *geom, alpha, A.stream())
+                out._tf32 = r  # rounded as stored: an operand of the conv gradients
+
+            if alpha > 0 and getattr(a, "_pooled_wgrad", None) == geom:
+                # `a` is a first-layer conv2d whose filter gradient can expand the POOLED
+                # gradient itself (sp_conv2d_wgrad_pooled): not launched unless somebody else
+                # needs the full-resolution gradient
+                return DeviceArray.deferred(x.shape, launch_pool_bwd,
+                                            ("pool_leaky_bwd", g0, idx, ypool, alpha), x.size)
+            launch_pool_bwd(dx)
             return dx
         # the slope depends on the sign of the input only; when the input was never stored
         # (conv + leaky ran as one kernel, alpha > 0) the output has the same sign
@@ -1069,20 +1081,57 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
         launch_dgrad(dx)
         return dx
 
+    def fuses_pending(g):
+        "True when grad_kernels consumes this not-yet-launched gradient without launching it."
+        tag = g.pending_tag if type(g) is DeviceArray else None
+        return tag is not None and tag[0] == "pool_leaky_bwd" and pooled_geom is not None
+
     def grad_kernels(g):
         dw = DeviceArray.empty_like(w)
-        g = _bwd_operand(_as_device(g))
         ws_bytes = plan[2].get(_precision)
         if ws_bytes is None:
             ws_bytes = plan[2][_precision] = _abi.load().sp_conv2d_wgrad_workspace(geom, _precision)
         ws = DeviceArray.empty((ws_bytes // 4,)) if ws_bytes else None
+        if fuses_pending(g):
+            # the gradient is leaky_relu + 2x2 maxpool2d's, still pooled: the kernel scatters it
+            # to the argmax positions as it stages its tiles (bit-identical to the two launches)
+            _, g0, idx, ypool, alpha = g.pending_tag
+            F.sp_conv2d_wgrad_pooled(x.ptr, g0.ptr, idx.ptr, ypool.ptr, dw.ptr, geom, alpha,
+                                     _precision, ws.ptr if ws is not None else None, ws_bytes,
+                                     A.stream())
+            return dw
+        g = _bwd_operand(_as_device(g))
         F.sp_conv2d_wgrad(x.ptr, g.ptr, dw.ptr, geom, _precision,
                           ws.ptr if ws is not None else None, ws_bytes, A.stream())
         return dw
 
+    grad_kernels.fuses_pending = fuses_pending
     out = Variable(y, [(images, grad_images), (kernels, grad_kernels)])
     out._to_contraction = True  # gradients w.r.t. this tensor are operands of contractions
+    # geometry of the 2x2 / stride-2 pool whose (leaky_relu'd) gradient the filter gradient can
+    # take in pooled form (first-layer convs, TF32): core.leaky_relu then leaves it pooled
+    pooled_geom = _pooled_wgrad_geom(plan, out_shape) if (_fuse_leaky_pool and _pooled_wgrad) else None
+    if pooled_geom is not None:
+        out._pooled_wgrad = pooled_geom
     return out
+
+
+_pooled_wgrad = os.environ.get("SP_POOLED_WGRAD", "1") != "0"
+
+
+def _pooled_wgrad_geom(plan, out_shape):
+    key = ("pooled", _precision)
+    cached = plan[4].get(key, 0)
+    if cached == 0:
+        cached = None
+        n, oh, ow, k = out_shape
+        if _precision == _abi.PRECISION_TF32 and oh % 2 == 0 and ow % 2 == 0 and oh and ow:
+            flag = C.c_int(0)
+            _abi.f.sp_conv2d_wgrad_pooled_supported(plan[0], _precision, flag)
+            if flag.value:
+                cached = (n, oh, ow, k, 2, 2, 2, 2, 0, 0, oh // 2, ow // 2)
+        plan[4][key] = cached
+    return cached
 
 
 _UINT8 = np.dtype(np.uint8)
@@ -1143,7 +1192,8 @@ def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = 
 
         if fused and x.size:
             # deferred: leaky_relu's gradient closure folds this scatter into its own kernel
-            return DeviceArray.deferred(x.shape, launch, ("maxpool2d_bwd", x, g, idx, geom), x.size)
+            return DeviceArray.deferred(x.shape, launch, ("maxpool2d_bwd", x, g, idx, geom, y),
+                                        x.size)
         dx = DeviceArray.empty_like(x)
         launch(dx)
         return dx

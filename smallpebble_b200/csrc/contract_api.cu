@@ -605,4 +605,36 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
   return 0;
 }
 
+// Filter gradient of a conv whose output went through leaky_relu and a 2 x 2 / stride-2 maxpool2d
+// (no padding), computed straight from the POOLED gradient: dY -- the pooled gradient scattered
+// to each window's argmax, times leaky's slope there -- is expanded tile by tile inside the
+// kernel instead of being written by sp_maxpool2d_leaky_bwd and read back (three quarters of it
+// zeros).  Bit-identical to the two separate calls.  First-layer (C <= 4, 3 x 3, stride 1) convs
+// in TF32 only: ask sp_conv2d_wgrad_pooled_supported first.  Workspace as for sp_conv2d_wgrad.
+int sp_conv2d_wgrad_pooled_supported(const sp_conv_geom* g, int precision, int* supported) {
+  if (int rc = sp::check_geom(g)) return rc;
+  SP_REQUIRE(supported != nullptr, "null output");
+  *supported = (sp::g_umma_policy == 0 && sp::conv_wgrad_pooled_supported(*g, precision)) ? 1 : 0;
+  return 0;
+}
+
+int sp_conv2d_wgrad_pooled(const float* x, const float* g_pooled, const uint8_t* argmax,
+                           const float* y_pooled, float* dw, const sp_conv_geom* g, float alpha,
+                           int precision, void* workspace, size_t workspace_bytes,
+                           sp_stream_t stream) {
+  if (int rc = sp::check_geom(g)) return rc;
+  if (sp::g_umma_policy != 0 || !sp::conv_wgrad_pooled_supported(*g, precision))
+    return sp::set_error(SP_ERR_UNSUPPORTED, "conv2d_wgrad_pooled: unsupported geometry");
+  const size_t need = (size_t)sp::small_c_wgrad_blocks(*g) * g->KH * g->KW * g->C * g->K * sizeof(float);
+  if (!workspace || workspace_bytes < need)
+    return sp::set_error(SP_ERR_WORKSPACE, "conv2d_wgrad_pooled: workspace %zu < required %zu",
+                         workspace_bytes, need);
+  if (int rc = sp::launch_conv_wgrad_pooled(x, g_pooled, argmax, y_pooled,
+                                            static_cast<float*>(workspace), dw, *g, alpha,
+                                            sp::as_stream(stream)))
+    return rc;
+  SP_CHECK_LAUNCH("conv2d_wgrad_pooled");
+  return 0;
+}
+
 }  // extern "C"

@@ -584,7 +584,22 @@ struct RgbMmaPlan {
   int n_tiles;
   int x_staged;       // floats of x staged per tile: (rows + 2) * wv * 3
   int x_floats;       // staged + zeroed slack read by the virtual tail pixels
-  int stage_floats;   // q_pad * (K + 8) + x_floats
+  int stage_floats;   // q_pad * (K + 8) + x_floats (+ pool_floats)
+  int pool_floats;    // POOLED: staging of the pooled rows a tile expands (g, y, argmax), else 0
+};
+
+// POOLED filter gradient: the output gradient dY of the conv is never materialised.  The conv
+// feeds leaky_relu -> maxpool2d (2x2, stride 2, no padding), so dY is the pooled gradient
+// scattered to each window's argmax times leaky's slope there: three quarters zeros.  The
+// kernel stages the POOLED rows (gradient g, pooled output y for the slope's sign, uint8 argmax)
+// and expands them into the dense dY tile in shared memory -- the same values the separate
+// sp_maxpool2d_leaky_bwd launch writes, so the result is bit-identical to the unfused path.
+struct PooledGy {
+  const float* g;      // [N, PH, PW, K] gradient w.r.t. the pooled tensor (null: dense gy)
+  const float* ypool;  // [N, PH, PW, K] pooled output: its sign is the sign at the argmax
+  const uint8_t* idx;  // [N, PH, PW, K] dy * 2 + dx
+  int PH, PW;
+  float alpha;
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const float* src, bool valid) {
@@ -614,11 +629,12 @@ __device__ __forceinline__ void split_bits(uint32_t x, uint32_t& r, uint32_t& l)
   l = __float_as_uint(xf - rf);
 }
 
-template <int KT>  // K = 16 * KT output channels
+template <int KT, bool POOLED>  // K = 16 * KT output channels
 __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rgb3x3_mma_kernel(
     const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partial,
     float* __restrict__ dw, const __grid_constant__ sp_conv_geom g,
-    const __grid_constant__ RgbMmaPlan pl, unsigned int* __restrict__ sync_words) {
+    const __grid_constant__ RgbMmaPlan pl, unsigned int* __restrict__ sync_words,
+    const __grid_constant__ PooledGy pg) {
   constexpr int K = 16 * KT, K4 = K / 4, GS = K + 8, KC = 27;
   constexpr int DQ = kThreads / K4;  // virtual pixels covered by one pass of the dY copy
   extern __shared__ __align__(16) float sm[];
@@ -639,7 +655,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rgb3x3_mma_kernel(
     const int oy0 = (tile_idx - n * pl.tiles_per_img) * pl.rows;
     float* gy_s = sm + stage * pl.stage_floats;
     float* x_s = gy_s + gy_floats;
-    {
+    if (POOLED) {
+      // the pooled rows this tile expands are whole rows of the pooled tensors: linear copies
+      const int prow = pg.PW * K;                        // floats per pooled row
+      const int py0 = oy0 >> 1;
+      const int nrows = min(pl.rows >> 1, pg.PH - py0);
+      const int nfl = nrows * prow;
+      float* pg_s = x_s + pl.x_floats;                   // g rows
+      float* py_s = pg_s + (pl.rows >> 1) * prow;        // y rows
+      uint8_t* pi_s = reinterpret_cast<uint8_t*>(py_s + (pl.rows >> 1) * prow);
+      const int64_t base = (int64_t)(n * pg.PH + py0) * prow;
+      for (int i = 4 * threadIdx.x; i < nfl; i += 4 * kThreads) {
+        cp_async16_zfill(&pg_s[i], pg.g + base + i, true);
+        cp_async16_zfill(&py_s[i], pg.ypool + base + i, true);
+      }
+      for (int i = 16 * threadIdx.x; i < nfl; i += 16 * kThreads)
+        cp_async16_zfill(&pi_s[i], reinterpret_cast<const float*>(pg.idx + base + i), true);
+    } else {
       int q = threadIdx.x / K4;
       const int part = threadIdx.x % K4;
       int r = q / pl.wv, xv = q - r * pl.wv;
@@ -694,6 +726,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_rgb3x3_mma_kernel(
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    if (POOLED) {
+      // expand the staged pooled rows into the dense dY tile (zeros off the argmax)
+      float* gy_w = sm + stage * pl.stage_floats;
+      const float* pg_s = gy_w + gy_floats + pl.x_floats;
+      const int prow = pg.PW * K;
+      const float* py_s = pg_s + (pl.rows >> 1) * prow;
+      const uint8_t* pi_s = reinterpret_cast<const uint8_t*>(py_s + (pl.rows >> 1) * prow);
+      const int tn = tile / pl.tiles_per_img;
+      const int toy0 = (tile - tn * pl.tiles_per_img) * pl.rows;
+      int q = threadIdx.x / K4;
+      const int part = threadIdx.x % K4;
+      int r = q / pl.wv, xv = q - r * pl.wv;
+      for (; q < pl.q_pad; q += DQ) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < pl.rows && xv < g.OW && toy0 + r < g.OH) {
+          const int src = ((r >> 1) * pg.PW + (xv >> 1)) * K + part * 4;
+          const uint32_t sel = (uint32_t)(((r & 1) << 1) | (xv & 1));
+          const float4 gg = *reinterpret_cast<const float4*>(pg_s + src);
+          const float4 yy = *reinterpret_cast<const float4*>(py_s + src);
+          const uint32_t ii = *reinterpret_cast<const uint32_t*>(pi_s + src);
+          if ((ii & 0xffu) == sel) v.x = gg.x * (yy.x > 0.f ? 1.f : pg.alpha);
+          if (((ii >> 8) & 0xffu) == sel) v.y = gg.y * (yy.y > 0.f ? 1.f : pg.alpha);
+          if (((ii >> 16) & 0xffu) == sel) v.z = gg.z * (yy.z > 0.f ? 1.f : pg.alpha);
+          if ((ii >> 24) == sel) v.w = gg.w * (yy.w > 0.f ? 1.f : pg.alpha);
+        }
+        *reinterpret_cast<float4*>(&gy_w[q * GS + part * 4]) = v;
+        xv += DQ;
+        while (xv >= pl.wv) {
+          xv -= pl.wv;
+          ++r;
+        }
+      }
+      __syncthreads();
+    }
     const uint32_t* gy_u = reinterpret_cast<const uint32_t*>(sm + stage * pl.stage_floats);
     const uint32_t* x_u = gy_u + gy_floats;
     for (int grp = warp; grp < n_groups; grp += kThreads / 32) {
@@ -928,8 +994,11 @@ static size_t rgb_tile_wgrad_smem(const sp_conv_geom& g) {
 }
 
 // plan of the tensor-core RGB filter gradient; rows == 0 when the geometry does not qualify
-static RgbMmaPlan rgb_mma_plan(const sp_conv_geom& g, int max_blocks) {
+static RgbMmaPlan rgb_mma_plan(const sp_conv_geom& g, int max_blocks, int pooled_pw = 0) {
   RgbMmaPlan pl = {};
+  // pooled_pw > 0: the POOLED variant (tiles of an even number of rows starting at even rows,
+  // plus staging for rows / 2 pooled rows of pooled_pw pixels: g, y as floats, argmax as bytes)
+  if (pooled_pw > 0 && ((g.OH & 1) || (g.OW & 1) || pooled_pw * 2 != g.OW)) return pl;
   if (!fixed_window(g) || g.sy != 1 || g.sx != 1 || !(g.K == 16 || g.K == 32 || g.K == 64))
     return pl;
   const int wv = g.OW + 2;  // == W + pad_l + pad_r for a stride-1 3x3 window
@@ -950,7 +1019,15 @@ static RgbMmaPlan rgb_mma_plan(const sp_conv_geom& g, int max_blocks) {
   for (int rows = std::min(g.OH, 64); rows >= 1; --rows) {
     if (forced_rows > 0 && rows != std::min(forced_rows, g.OH)) continue;
     int q_pad, x_staged, x_floats;
-    const int sf = stage_floats(rows, &q_pad, &x_staged, &x_floats);
+    int sf = stage_floats(rows, &q_pad, &x_staged, &x_floats);
+    int pool_floats = 0;
+    if (pooled_pw > 0) {
+      if (rows & 1) continue;
+      const int per_array = (rows / 2) * pooled_pw * g.K;  // floats of g (and of y)
+      pool_floats = 2 * per_array + (per_array + 3) / 4 + 4;
+      pool_floats = (pool_floats + 3) / 4 * 4;
+      sf += pool_floats;
+    }
     if (sf > max_stage) continue;
     const int per_img = (g.OH + rows - 1) / rows;
     const int64_t tiles = (int64_t)g.N * per_img;
@@ -970,19 +1047,20 @@ static RgbMmaPlan rgb_mma_plan(const sp_conv_geom& g, int max_blocks) {
       pl.x_staged = x_staged;
       pl.x_floats = x_floats;
       pl.stage_floats = sf;
+      pl.pool_floats = pool_floats;
     }
   }
   return pl;
 }
 
-template <int KT>
+template <int KT, bool POOLED = false>
 static int launch_rgb_mma(const float* x, const float* gy, float* partial, float* dw,
                           const sp_conv_geom& g, const RgbMmaPlan& pl, int blocks,
-                          cudaStream_t st) {
+                          cudaStream_t st, PooledGy pg = PooledGy{}) {
   const size_t smem = std::max<size_t>(2 * (size_t)pl.stage_floats, (size_t)8 * 27 * g.K) * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(conv_wgrad_rgb3x3_mma_kernel<KT>,
+    cudaFuncSetAttribute(conv_wgrad_rgb3x3_mma_kernel<KT, POOLED>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     attr_done = true;
   }
@@ -991,8 +1069,8 @@ static int launch_rgb_mma(const float* x, const float* gy, float* partial, float
   sp_conv_geom gg = g;
   RgbMmaPlan pp = pl;
   void* args[] = {(void*)&x, (void*)&gy, (void*)&partial, (void*)&dw, (void*)&gg, (void*)&pp,
-                  (void*)&words};
-  const void* fn = (const void*)conv_wgrad_rgb3x3_mma_kernel<KT>;
+                  (void*)&words, (void*)&pg};
+  const void* fn = (const void*)conv_wgrad_rgb3x3_mma_kernel<KT, POOLED>;
   blocks = std::min(blocks, pl.n_tiles);
   // cooperative (co-resident grid: the kernel ends in a grid barrier) AND programmatic
   // dependent launch; a driver that refuses the combination gets the plain cooperative launch
@@ -1201,6 +1279,30 @@ int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial, fl
     conv_wgrad_smallc_kernel<<<blocks, kThreads, 0, st>>>(x, gy, partial, g, kc, per);
   }
   return 0;
+}
+
+// The POOLED first-layer filter gradient (see PooledGy): eligibility and launch.
+bool conv_wgrad_pooled_supported(const sp_conv_geom& g, int precision) {
+  if (precision != SP_PRECISION_TF32 || !small_c_supported(g)) return false;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int blocks = std::min(small_c_wgrad_blocks(g), sms);
+  return rgb_mma_plan(g, blocks, g.OW / 2).rows > 0;
+}
+
+int launch_conv_wgrad_pooled(const float* x, const float* g_pooled, const uint8_t* idx,
+                             const float* y_pooled, float* partial, float* dw,
+                             const sp_conv_geom& g, float alpha, cudaStream_t st) {
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int nb = std::min(small_c_wgrad_blocks(g), sms);
+  const RgbMmaPlan pl = rgb_mma_plan(g, nb, g.OW / 2);
+  if (pl.rows == 0) return set_error(SP_ERR_UNSUPPORTED, "conv2d_wgrad_pooled: unsupported geometry");
+  const bool aligned = ((reinterpret_cast<uintptr_t>(g_pooled) | reinterpret_cast<uintptr_t>(y_pooled) |
+                         reinterpret_cast<uintptr_t>(idx)) & 15) == 0;
+  if (!aligned) return set_error(SP_ERR_UNSUPPORTED, "conv2d_wgrad_pooled: unaligned operands");
+  PooledGy pg{g_pooled, y_pooled, idx, g.OH / 2, g.OW / 2, alpha};
+  return g.K == 16   ? launch_rgb_mma<1, true>(x, nullptr, partial, dw, g, pl, nb, st, pg)
+         : g.K == 32 ? launch_rgb_mma<2, true>(x, nullptr, partial, dw, g, pl, nb, st, pg)
+                     : launch_rgb_mma<4, true>(x, nullptr, partial, dw, g, pl, nb, st, pg);
 }
 
 }  // namespace sp

@@ -88,6 +88,12 @@ int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_
                              int precision, cudaStream_t st, int leaky = 0, float alpha = 0.f,
                              bool* fused_leaky = nullptr);
 // `*reduced` = true when the kernel already summed its partial filters into dw
+// first-layer filter gradient straight from the POOLED gradient of a leaky_relu -> 2x2 / stride-2
+// maxpool2d that follows the conv (conv_smallc.cu: PooledGy)
+bool conv_wgrad_pooled_supported(const sp_conv_geom& g, int precision);
+int launch_conv_wgrad_pooled(const float* x, const float* g_pooled, const uint8_t* idx,
+                             const float* y_pooled, float* partial, float* dw,
+                             const sp_conv_geom& g, float alpha, cudaStream_t st);
 int launch_conv_wgrad_smallc(const float* x, const float* gy, float* partial, float* dw,
                              const sp_conv_geom& g, int blocks, int precision, cudaStream_t st,
                              bool* reduced);

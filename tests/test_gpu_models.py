@@ -398,3 +398,56 @@ def test_leaf_gradient_read_after_the_update_sees_the_old_weights(optimiser):
     assert np.abs(before).max() > 0
     assert np.array_equal(before, after)
     assert np.array_equal(before, late)
+
+
+@pytest.mark.parametrize("shape,k", [((16, 32, 32, 3), 32), ((5, 14, 18, 3), 16), ((3, 10, 10, 3), 64)])
+def test_first_layer_filter_gradient_from_the_pooled_gradient_is_bit_identical(shape, k):
+    """conv2d (3x3, C = 3) -> leaky_relu -> maxpool2d(2, 2, stride 2): the filter gradient expands
+    the POOLED gradient inside its own kernel (sp_conv2d_wgrad_pooled) instead of reading the
+    full-resolution gradient sp_maxpool2d_leaky_bwd would write -- the same products (summed
+    over differently shaped tiles), and the image gradient, which needs the full-resolution
+    tensor, still comes out bit-identical."""
+    from smallpebble_b200 import _abi
+
+    rng = np.random.default_rng(11)
+    x = rng.random(shape) - 0.5
+    w = (rng.random((3, 3, 3, k)) - 0.5) * 0.5
+    sp.set_precision("tf32")
+    calls = []
+    orig = _abi.f.sp_conv2d_wgrad_pooled
+
+    def spy(*args):
+        calls.append(1)
+        return orig(*args)
+
+    def run(fuse, read_dx):
+        sp.set_fusion(fuse)
+        xv, wv = sp.Variable(x), sp.Variable(w)
+        sp.learnable(wv)
+        h = sp.conv2d(xv, wv, "VALID")
+        h = sp.maxpool2d(sp.leaky_relu(h, 0.1), 2, 2, strides=[2, 2])
+        gy = np.random.default_rng(12).random(h.shape) - 0.5
+        g = sp.get_gradients(sp.mul(h, sp.Variable(gy)))
+        dw = np.asarray(g[wv])
+        dx = np.asarray(g[xv]) if read_dx else None
+        return np.asarray(h.array), dw, dx
+
+    _abi.f.sp_conv2d_wgrad_pooled = spy
+    try:
+        y1, dw1, dx1 = run(True, True)
+        n_fused = len(calls)
+        y0, dw0, dx0 = run(False, True)
+    finally:
+        _abi.f.sp_conv2d_wgrad_pooled = orig
+        sp.set_fusion(True)
+    assert n_fused == 1 and len(calls) == 1  # taken when fusing, never otherwise
+    assert np.array_equal(y1, y0) and np.array_equal(dx1, dx0)
+    # same products, but tiles of an even number of rows: the fp32 summation order differs
+    assert_close(dw1, dw0, 2e-6, "fused vs separate launches")
+    # and against the float64 oracle
+    xo, wo = orc.Node(x), orc.Node(w)
+    ho = orc.op_maxpool2d(orc.op_leaky_relu(orc.op_conv2d(xo, wo, "VALID"), 0.1), 2, 2, "SAME", (2, 2))
+    gy = np.random.default_rng(12).random(ho.value.shape) - 0.5
+    go = orc.backprop(orc.op_mul(ho, orc.Node(gy)))
+    assert_close(dw1, go[wo], 2e-3, "dW vs oracle")
+    assert_close(dx1, go[xo], 2e-3, "dX vs oracle")
