@@ -85,6 +85,10 @@ int sp_debug_set_umma_policy(int policy);
  * bring-up hook: cluster 0 of those kernels writes clock64 stamps into `device_buffer`
  * (>= 512 int64, layout in scripts/tma2_trace.py); NULL switches tracing off */
 int sp_debug_tma2_trace(void* device_buffer);
+/* bring-up hook (SP_PEER_TRACE=1 at sp_peer_exchange_create): eight globaltimer stamps (ns) of
+ * block 0 of the last sp_adam_multi_peer kernel: entry, own bucket written, fenced, all peer
+ * flags seen, update done */
+int sp_debug_peer_trace(void* exchange, unsigned long long* host_out8);
 
 /* ---- memory helpers (replace NumPy array construction / copies) -------------------- */
 int sp_memcpy_h2d(void* dst, const void* host_src, size_t bytes, sp_stream_t stream);

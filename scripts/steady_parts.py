@@ -59,6 +59,15 @@ def loop(n=300):
 r = loop()
 if int(os.environ.get("RANK", "0")) == 0:
     print("loop: %.1f us/step device, host %.1f us/step (run %.1f, get_gradients %.1f, adam %.1f)" % r)
+if os.environ.get("SP_PEER_TRACE") == "1" and sp.distributed._peer["handle"]:
+    import ctypes as C
+    from smallpebble_b200 import _abi
+    torch.cuda.synchronize()
+    out = (C.c_uint64 * 8)()
+    _abi.load().sp_debug_peer_trace(sp.distributed._peer["handle"], out)
+    t = list(out)
+    print("rank", os.environ.get("RANK"), "peer kernel block 0 (us from entry): bucket written %.1f | fenced %.1f | "
+          "flags seen %.1f | update done %.1f" % tuple((t[i] - t[0]) / 1e3 for i in (1, 2, 3, 4)), flush=True)
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
     sp.distributed.barrier()
     os._exit(0)

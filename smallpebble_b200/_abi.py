@@ -43,6 +43,7 @@ SIGNATURES = {
     "sp_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "sp_debug_set_umma_policy": (C.c_int, [C.c_int]),
     "sp_debug_tma2_trace": (C.c_int, [vp]),
+    "sp_debug_peer_trace": (C.c_int, [vp, vp]),
     "sp_memcpy_h2d": (C.c_int, [vp, vp, sz, vp]),
     "sp_host_is_pinned": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "sp_memcpy_d2h": (C.c_int, [vp, vp, sz, vp]),
@@ -136,7 +137,7 @@ _lib = None
 _LAUNCHING = {
     n for n in SIGNATURES
     if n not in ("sp_abi_version", "sp_last_error", "sp_device_info", "sp_debug_set_umma_policy",
-                 "sp_debug_tma2_trace", "sp_host_is_pinned", "sp_stream_create", "sp_event_create",
+                 "sp_debug_tma2_trace", "sp_debug_peer_trace", "sp_host_is_pinned", "sp_stream_create", "sp_event_create",
                  "sp_event_record", "sp_stream_wait_event", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
                  "sp_conv2d_wgrad_workspace", "sp_set_tf32_output_rounding", "sp_conv2d_x3_plan",
                  "sp_set_scratch_lane", "sp_conv2d_wgrad_pooled_supported", "sp_nccl_load", "sp_nccl_unique_id", "sp_nccl_init",

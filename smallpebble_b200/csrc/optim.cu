@@ -175,6 +175,7 @@ struct PeerArgs {
   unsigned int* packed;      // self-resetting: the last block to have published its chunk of
                              // this rank's gradients signals the peers
   const float* grad[kMaxTensors];  // this rank's own gradients (published by this kernel)
+  unsigned long long* trace;       // bring-up: globaltimer stamps of block 0, or null
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -217,6 +218,8 @@ __global__ void __launch_bounds__(kThreads) adam_multi_peer_kernel(
     const __grid_constant__ AdamArgs a, const __grid_constant__ PeerArgs x, float alpha, float b1,
     float b2, float lnb1, float lnb2, float eps) {
   pdl_entry();
+  const bool tr = x.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tr) x.trace[0] = timer_ns();
   __shared__ uint32_t s_epoch;
   if (threadIdx.x == 0) s_epoch = *x.epoch + 1u;
   __syncthreads();
@@ -238,12 +241,19 @@ __global__ void __launch_bounds__(kThreads) adam_multi_peer_kernel(
       for (int64_t i = base + threadIdx.x; i < end; i += kThreads) mine[i] = g[i];
     }
     __syncthreads();
+    if (tr) x.trace[1] = timer_ns();
     if (threadIdx.x == 0) {
-      __threadfence_system();
+      // device-scope fence + arrival per block; the block that completes the bucket issues
+      // ONE system-scope fence (cumulative over everything it observed through the counter)
+      // and plain system-scope flag stores behind it.  In-kernel stamps (SP_PEER_TRACE): a
+      // system fence costs 2-4 us here, so one instead of (1 per block + 1 + 1 per store)
+      // moves the flag from ~10 to ~6 us after kernel entry.
+      __threadfence();
+      if (tr) x.trace[2] = timer_ns();
       if (atomicInc(x.packed, gridDim.x - 1) == gridDim.x - 1) {
         __threadfence_system();
         for (int r = 0; r < x.world; ++r)
-          if (r != x.rank) st_release_sys(x.flags[r] + x.rank, e);
+          if (r != x.rank) st_relaxed_sys(x.flags[r] + x.rank, e);
       }
     }
     if (threadIdx.x == 0) {
@@ -256,6 +266,7 @@ __global__ void __launch_bounds__(kThreads) adam_multi_peer_kernel(
           if (timer_ns() - t0 > 4000000000ull) __trap();  // a peer never arrived
         }
       }
+      if (tr) x.trace[3] = timer_ns();
     }
     __syncthreads();
   }
@@ -323,6 +334,7 @@ __global__ void __launch_bounds__(kThreads) adam_multi_peer_kernel(
   }
   // every thread of this block has read the step count and the epoch
   __syncthreads();
+  if (tr) x.trace[4] = timer_ns();
   if (threadIdx.x == 0) {
     const unsigned int blocks_t = (unsigned int)(a.block_start[t + 1] - a.block_start[t]);
     if (atomicInc(&a.done[t], blocks_t - 1) == blocks_t - 1) *a.step[t] += 1;
@@ -399,6 +411,7 @@ struct sp_peer_exchange_t {
   float* blocks[8];
   uint32_t* epoch;        // device
   unsigned int* arrivals; // device
+  unsigned long long* trace;  // device, 8 stamps (SP_PEER_TRACE=1), else null
 };
 
 static int adam_impl(int n_tensors, float* const* host_p, float* const* host_p_out,
@@ -473,9 +486,22 @@ int sp_peer_exchange_create(int world, int rank, int64_t half_floats, void* cons
   }
   x->epoch = static_cast<uint32_t*>(words);
   x->arrivals = static_cast<unsigned int*>(words) + 4;
+  x->trace = nullptr;
+  if (const char* e = getenv("SP_PEER_TRACE")) {
+    if (atoi(e) == 1 && cudaMalloc(reinterpret_cast<void**>(&x->trace), 64) == cudaSuccess)
+      cudaMemset(x->trace, 0, 64);
+  }
   *out = x;
   return 0;
 }
+// bring-up hook (SP_PEER_TRACE=1): globaltimer stamps of block 0 of the last update kernel
+int sp_debug_peer_trace(void* exchange, unsigned long long* host_out8) {
+  auto* x = static_cast<sp_peer_exchange_t*>(exchange);
+  if (!x || !x->trace || !host_out8) return sp::set_error(SP_ERR_UNSUPPORTED, "no trace buffer");
+  SP_CHECK_CUDA(cudaMemcpy(host_out8, x->trace, 64, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int sp_peer_exchange_destroy(void* exchange) {
   auto* x = static_cast<sp_peer_exchange_t*>(exchange);
   if (!x) return 0;
@@ -581,6 +607,7 @@ static int adam_impl(int n_tensors, float* const* host_p, float* const* host_p_o
         x.epoch = peer->epoch;
         x.arrivals = peer->arrivals;
         x.packed = peer->arrivals + 4;
+        x.trace = peer->trace;
         if (shadows)
           sp::launch_pdl(adam_multi_peer_kernel<true>, dim3(blocks), dim3(kThreads), 0, st, a, x,
                          alpha, (float)b1, (float)b2, (float)log(b1), (float)log(b2), eps);
