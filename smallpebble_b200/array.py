@@ -236,6 +236,9 @@ def new_event() -> int:
     return slot[0]
 
 
+forbid_uploads = False  # set by steady.py around its graph captures
+
+
 _scalar_ones = {}  # shape -> read-only device constant 1.0 (the gradient seed of a scalar loss)
 
 
@@ -418,6 +421,11 @@ class DeviceArray:
         if self._thunk is not None:
             self._materialize()
             return
+        if forbid_uploads:
+            # steady.py is recording this call into a CUDA graph: host data created inside the
+            # step (a random mask, say) would be baked into the graph.  Refuse: the recording is
+            # abandoned and the step keeps running eagerly.
+            raise RuntimeError("host data uploaded inside a step that is being recorded")
         dev = require_cuda()
         host = self._host
         if host.dtype != self.dtype:

@@ -273,11 +273,13 @@ def _capture(pool, fn):
     torch = _torch()
     graph = torch.cuda.CUDAGraph()
     launches0 = _abi.counter.launches
+    A.forbid_uploads = True
     try:
         with A.pool_bypass():
             with torch.cuda.graph(graph, pool=pool):
                 result = fn()
     except Exception as exc:  # noqa: BLE001 - anything that cannot be captured: stay eager
+        A.forbid_uploads = False
         try:
             torch.cuda.synchronize()
         except Exception:  # noqa: BLE001
@@ -285,6 +287,7 @@ def _capture(pool, fn):
         if os.environ.get("SP_STEADY_DEBUG") == "1":
             raise
         raise _Abort(str(exc)) from exc
+    A.forbid_uploads = False
     return graph, result, _abi.counter.launches - launches0
 
 
@@ -444,17 +447,25 @@ def gradients_of(variable, tag):
         _abi.counter.launches += rec.kernels_b
         stats["replays_b"] += 1
         rec.b_epoch = epoch
+    # this step's view of the recorded gradients: the same buffers, with the recorded root and
+    # input Variables replaced by the ones the caller holds (one C-level dict copy, then the
+    # few keys that differ)
     static = rec.grads
     out = core.Gradients()
-    remap = {}
+    dict.update(out, dict.items(static))  # (the raw items: Gradients' own views materialise)
+    swaps = [(rec.root, variable)]
     for sv, uv in zip(rec.static_values, rec.user_inputs):
         if isinstance(sv, core.Variable) and isinstance(uv, core.Variable):
-            remap[sv] = uv
-    remap[rec.root] = variable
-    for k, v in dict.items(static):
-        dict.__setitem__(out, remap.get(k, k), v)
+            swaps.append((sv, uv))
+    for sv, uv in swaps:
+        if dict.__contains__(out, sv):
+            dict.__setitem__(out, uv, dict.pop(out, sv))
     if static._deferred:
-        out._deferred = {remap.get(k, k): list(v) for k, v in static._deferred.items()}
+        deferred = {k: list(v) for k, v in static._deferred.items()}
+        for sv, uv in swaps:
+            if sv in deferred:
+                deferred[uv] = deferred.pop(sv)
+        out._deferred = deferred
     out._steady = (rec, epoch, updates)
     out._reduced = static._reduced
     return out

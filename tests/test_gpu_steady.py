@@ -113,3 +113,28 @@ def test_stale_result_is_refused(replay_on):
     if getattr(old, "_steady", None) is not None:
         with pytest.raises(RuntimeError):
             sp.get_gradients(old)
+
+
+def test_host_data_created_inside_the_step_keeps_the_loop_eager(replay_on):
+    """A lazy function that builds a Variable from fresh host data every run (a random mask)
+    must not be frozen into a graph: the recording is abandoned and every step stays eager."""
+    steady.set_enabled(True)
+    rng = np.random.default_rng(1)
+    masks = []
+
+    def masked(a):
+        m = (rng.random((4, 6)) > 0.5).astype(np.float64)
+        masks.append(m)
+        return sp.mul(a, sp.Variable(m))
+
+    x_in = sp.Placeholder()
+    w = sp.learnable(sp.Variable(np.ones((4, 6))))
+    out = sp.Lazy(masked)(sp.Lazy(sp.mul)(x_in, w))
+    before = steady.stats["aborted"]
+    for i in range(8):
+        x = np.full((4, 6), float(i + 1))
+        x_in.assign_value(sp.Variable(x))
+        y = out.run()
+        assert np.array_equal(np.asarray(y.array), (x * masks[-1]).astype(np.float32)), i
+    assert len(masks) == 8 or steady.stats["aborted"] > before
+    assert steady.stats["aborted"] == before + 1
