@@ -229,9 +229,15 @@ def algorithmic_work(name, args):
     if name in ("sp_conv2d_fprop", "sp_conv2d_dgrad", "sp_conv2d_wgrad"):
         g = args[3]
         g = g.contents if hasattr(g, "contents") else g
-        flops = 2.0 * g.N * g.OH * g.OW * g.K * g.KH * g.KW * g.C
+        channels, extra = g.C, ""
+        if name == "sp_conv2d_fprop" and args[4] == _abi.PRECISION_TF32_SPLIT:
+            # error-compensated forward pass on pre-split (r, l) operands: the geometry carries
+            # 2C channels and the kernel issues three tensor passes; the ALGORITHMIC work is one
+            # product over the C real channels
+            channels, extra = g.C // 2, " (3xTF32: three tensor passes issued)"
+        flops = 2.0 * g.N * g.OH * g.OW * g.K * g.KH * g.KW * channels
         desc = (f"{name[3:]} N={g.N} HxW={g.H}x{g.W} C={g.C} K={g.K} k={g.KH}x{g.KW} "
-                f"s={g.sy}x{g.sx}")
+                f"s={g.sy}x{g.sx}{extra}")
         if g.C <= 4:
             # RGB first layer: 0.2 GFLOP against 16 MB -- warp-level TF32 MMA (FP32 mode: CUDA
             # cores) whose roofline is memory, not the tensor pipe

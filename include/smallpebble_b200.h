@@ -245,6 +245,16 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
 int sp_gemm_bias(int64_t M, int64_t N, int64_t K, const float* A, const float* B,
                  const float* bias, float* C, int precision, sp_stream_t stream);
 
+/* The classifier head of the README models in one call (README.md:132-137, 277-281;
+ * sp.py:239-247, 100-108, 612-621): logits = A . B + bias, probs = softmax(logits), loss = summed
+ * cross entropy against labels, dlogits = probs - onehot with its column sums (the gradients
+ * for a unit upstream gradient).  M <= 2048, M * N <= 32768.  One kernel for N <= 16; bit-identical
+ * to sp_gemm_bias followed by sp_softmax_xent_fwd_grad. */
+int sp_gemm_bias_softmax_xent(int64_t M, int64_t N, int64_t K, const float* A, const float* B,
+                              const float* bias, const int32_t* labels, float* logits,
+                              float* probs, float* loss, float* dlogits, float* colsum,
+                              int precision, sp_stream_t stream);
+
 /* ---- conv2d (sp.py:124-163 and the closures it composes: 244-245, 384-387, 325-327) -- */
 typedef struct sp_conv_geom {
   int32_t N, H, W, C;        /* images  [N,H,W,C]                        */
@@ -277,6 +287,17 @@ size_t sp_conv2d_wgrad_workspace(const sp_conv_geom* g, int precision);
 int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_geom* g,
                     int precision, void* workspace, size_t workspace_bytes,
                     sp_stream_t stream);
+
+/* maxpool2d(leaky_relu(conv2d(x, w), alpha), 2, 2, strides = [2, 2]) in one kernel
+ * (sp.py:124-163, 231-236, 282-300; the first layer of the README CNN, README.md:261-266): the
+ * full-resolution activation is never written.  y_pooled [N, OH/2, OW/2, K], argmax uint8
+ * (dy*2+dx), split: NULL or the SP_SPLIT_RL split of y_pooled in blocks of K floats.
+ * Bit-identical to sp_conv2d_fprop + sp_maxpool2d_leaky_fwd / sp_maxpool2d_fwd_split.  Only
+ * geometries / precisions for which sp_conv2d_leaky_pool2_supported sets *supported = 1. */
+int sp_conv2d_leaky_pool2_supported(const sp_conv_geom* g, int precision, int* supported);
+int sp_conv2d_leaky_pool2_fwd(const float* x, const float* w, float* y_pooled, uint8_t* argmax,
+                              float* split, const sp_conv_geom* g, int precision, float alpha,
+                              sp_stream_t stream);
 
 /* Filter gradient of a conv whose output went through leaky_relu and a 2x2 / stride-2 maxpool2d
  * (sp.py:231-236, 282-300), straight from the POOLED gradient: what sp_maxpool2d_leaky_bwd

@@ -81,6 +81,7 @@ SIGNATURES = {
     "sp_stream_wait_event": (C.c_int, [vp, vp]),
     "sp_softmax_xent_bwd_colsum": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp]),
     "sp_gemm_bias": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, C.c_int, vp]),
+    "sp_gemm_bias_softmax_xent": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
     "sp_maxpool2d_fwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [vp]),
     "sp_maxpool2d_bwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [vp]),
     "sp_maxpool2d_leaky_fwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [f32, vp]),
@@ -95,6 +96,8 @@ SIGNATURES = {
     "sp_conv2d_wgrad_workspace": (sz, [C.POINTER(ConvGeom), C.c_int]),
     "sp_conv2d_wgrad": (C.c_int, [vp, vp, vp, C.POINTER(ConvGeom), C.c_int, vp, sz, vp]),
     "sp_conv2d_wgrad_pooled_supported": (C.c_int, [C.POINTER(ConvGeom), C.c_int, C.POINTER(C.c_int)]),
+    "sp_conv2d_leaky_pool2_supported": (C.c_int, [C.POINTER(ConvGeom), C.c_int, C.POINTER(C.c_int)]),
+    "sp_conv2d_leaky_pool2_fwd": (C.c_int, [vp, vp, vp, vp, vp, C.POINTER(ConvGeom), C.c_int, f32, vp]),
     "sp_conv2d_wgrad_pooled": (C.c_int, [vp, vp, vp, vp, vp, C.POINTER(ConvGeom), f32, C.c_int, vp,
                                          sz, vp]),
     "sp_adam_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
@@ -140,7 +143,7 @@ _LAUNCHING = {
                  "sp_debug_tma2_trace", "sp_debug_peer_trace", "sp_host_is_pinned", "sp_stream_create", "sp_event_create",
                  "sp_event_record", "sp_stream_wait_event", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
                  "sp_conv2d_wgrad_workspace", "sp_set_tf32_output_rounding", "sp_conv2d_x3_plan",
-                 "sp_set_scratch_lane", "sp_conv2d_wgrad_pooled_supported", "sp_nccl_load", "sp_nccl_unique_id", "sp_nccl_init",
+                 "sp_set_scratch_lane", "sp_conv2d_wgrad_pooled_supported", "sp_conv2d_leaky_pool2_supported", "sp_nccl_load", "sp_nccl_unique_id", "sp_nccl_init",
                  "sp_allreduce_sum_f32", "sp_nccl_destroy", "sp_peer_alloc", "sp_peer_open",
                  "sp_peer_close", "sp_peer_free", "sp_peer_exchange_create",
                  "sp_peer_exchange_destroy")

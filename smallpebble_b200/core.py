@@ -514,9 +514,19 @@ def add(a: Variable, b: Variable) -> Variable:
         # row vector: matmul + bias in one call (sp.py:630-635); the matmul node's own value
         # stays deferred unless somebody reads it
         _, av, bv, rows, n, k = tag
-        value = DeviceArray.empty(sa)
-        F.sp_gemm_bias(rows, n, k, av.ptr, bv.ptr, b.array.ptr, value.ptr, _fwd_native_precision(),
-                       A.stream())
+        bias, fwd_prec = b.array, _fwd_native_precision()
+
+        def launch_gemm_bias(out):
+            F.sp_gemm_bias(rows, n, k, av.ptr, bv.ptr, bias.ptr, out.ptr, fwd_prec, A.stream())
+
+        if _fuse_head and n <= 16 and rows * n:
+            # the 10-way classifier: still not launched -- softmax + cross_entropy may take the
+            # whole head into one kernel (core.cross_entropy); anything else launches it here
+            value = DeviceArray.deferred(sa, launch_gemm_bias,
+                                         ("gemm_bias", av, bv, bias, rows, n, k, fwd_prec), rows * n)
+        else:
+            value = DeviceArray.empty(sa)
+            launch_gemm_bias(value)
     else:
         value = A.binary("add", a.array, b.array)
     out = Variable(value, [
@@ -1052,11 +1062,34 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
         else:
             F.sp_conv2d_fprop_leaky(xa.ptr, wa.ptr, out.ptr, g, pr, alpha, A.stream())
 
+    def launch_pooled(ypool, idx, split, alpha):
+        """maxpool2d(leaky_relu(conv2d(x, w), alpha), 2, 2, strides [2, 2]) in ONE kernel
+        (sp_conv2d_leaky_pool2_fwd: first-layer geometries) -- the full-resolution tensor stays
+        unlaunched.  False: no such kernel for this conv, the caller pools the usual way."""
+        g, pr = geom, prec
+        if compensate:
+            code, g, pr, xsplit, _ = _conv_x3(plan)
+            if xsplit is not None:
+                return False
+        key = ("pool2", pr)
+        ok = plan[4].get(key)
+        if ok is None:
+            flag = C.c_int(0)
+            _abi.f.sp_conv2d_leaky_pool2_supported(g, pr, flag)
+            ok = plan[4][key] = bool(flag.value)
+        if not ok:
+            return False
+        F.sp_conv2d_leaky_pool2_fwd(x.ptr, w.ptr, ypool.ptr, idx.ptr,
+                                    split._ptr if split is not None else None, g, pr, alpha,
+                                    A.stream())
+        return True
+
     out_size = plan[3]
     if _fuse_conv_leaky and out_size:
         # not launched yet: a leaky_relu consumer folds its activation into this kernel's
-        # epilogue (core.leaky_relu); anything else that touches the result launches it as usual
-        y = DeviceArray.deferred(out_shape, launch, ("conv2d", launch), out_size)
+        # epilogue (core.leaky_relu), a leaky_relu + 2x2 maxpool2d consumer the pooling too
+        # (core.maxpool2d); anything else that touches the result launches it as usual
+        y = DeviceArray.deferred(out_shape, launch, ("conv2d", launch, launch_pooled), out_size)
     else:
         y = DeviceArray.empty(out_shape, A.FLOAT, out_size)
         launch(y)
@@ -1117,6 +1150,8 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
 
 
 _pooled_wgrad = os.environ.get("SP_POOLED_WGRAD", "1") != "0"
+_fuse_conv_pool = os.environ.get("SP_FUSE_CONV_POOL", "1") != "0"  # conv + leaky + pool, one kernel
+_fuse_head = os.environ.get("SP_FUSE_HEAD", "1") != "0"  # matmul + bias + softmax + cross_entropy
 
 
 def _pooled_wgrad_geom(plan, out_shape):
@@ -1165,7 +1200,22 @@ def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = 
     tag = x.pending_tag
     fused = tag is not None and tag[0] == "leaky_relu" and y.size > 0
     hint = _split_hints.get(out_shape) if _compensate and y.size else None
-    if hint is not None:
+    conv_pool = None
+    if fused and _fuse_conv_pool and tag[2] > 0 and geom[4:10] == (2, 2, 2, 2, 0, 0):
+        ctag = tag[1].pending_tag
+        if ctag is not None and ctag[0] == "conv2d" and len(ctag) > 2:
+            conv_pool = ctag[2]  # the conv that feeds the leaky_relu has not been launched
+    done = False
+    if conv_pool is not None and (hint is None or hint == (_abi.SPLIT_RL, out_shape[3])):
+        # conv2d + leaky_relu + this pool as one kernel (first-layer convs); the (r, l) split
+        # comes out of the same kernel when its blocks are whole pixels
+        split = DeviceArray.empty((out_size * 2,), A.FLOAT, out_size * 2) if hint is not None else None
+        done = conv_pool(y, idx, split, tag[2])
+        if done and split is not None:
+            y._shadow = [A.inplace_epoch, None, {hint: split}]
+    if done:
+        pass
+    elif hint is not None:
         # a compensated conv2d consumed the previous tensor of this shape as (r, l) split
         # operand: this kernel writes that form beside y (tf32.cu), no split launch later
         kind, block = hint
@@ -1284,8 +1334,18 @@ def cross_entropy(y_pred: Variable, y_true: np.ndarray, axis: int = -1) -> Varia
             # ... and, in the same launch, the gradient of the logits for a unit seed with its
             # column sums: what grad_logits returns when this loss is the root of get_gradients
             pre = (DeviceArray.empty_like(logits), DeviceArray.empty((cols,)))
-            F.sp_softmax_xent_fwd_grad(logits.ptr, labels.ptr, probs.ptr, loss.ptr, pre[0]._ptr,
-                                       pre[1]._ptr, rows, cols, A.stream())
+            ltag = logits.pending_tag
+            if ltag is not None and ltag[0] == "gemm_bias" and _fuse_head:
+                # ... and the classifier's matmul + bias, which has not been launched either:
+                # the whole head is one kernel (the GEMM's last block runs the softmax)
+                _, av, bv, bias, m, n, k, fwd_prec = ltag
+                logits._adopt(DeviceArray.empty_like(logits))
+                F.sp_gemm_bias_softmax_xent(m, n, k, av.ptr, bv.ptr, bias.ptr, labels.ptr,
+                                            logits._ptr, probs.ptr, loss.ptr, pre[0]._ptr,
+                                            pre[1]._ptr, fwd_prec, A.stream())
+            else:
+                F.sp_softmax_xent_fwd_grad(logits.ptr, labels.ptr, probs.ptr, loss.ptr,
+                                           pre[0]._ptr, pre[1]._ptr, rows, cols, A.stream())
         else:
             F.sp_softmax_xent_fwd(logits.ptr, labels.ptr, probs.ptr, loss.ptr, rows, cols,
                                   A.stream())

@@ -30,6 +30,7 @@ float* scratch_for_current_device();
 // Library-owned, zero-initialised synchronisation words (one set per device): self-resetting
 // arrival counters of single-launch "last block finishes the job" kernels.
 //   [0, 24)  fused Adam: per-tensor arrivals          [32], [33] grid barrier (count, generation)
+//   [40]     classifier head: arrivals of the skinny GEMM's row blocks (gemm_skinny.cu)
 constexpr int kSyncWords = 64;
 unsigned int* sync_words_for_current_device();
 

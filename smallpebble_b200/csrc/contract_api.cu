@@ -213,6 +213,53 @@ int sp_gemm_bias(int64_t M, int64_t N, int64_t K, const float* A, const float* B
   return sp_ewise_binary(SP_BINARY_ADD, C, sc, bias, sb, C, 2, shape, stream);
 }
 
+// The classifier head in one call: logits = A . B + bias, probs = softmax(logits), loss = the
+// summed cross entropy against `labels` (sp.py:612-621), dlogits = probs - onehot and its
+// column sums (the gradients for a unit upstream gradient).  One kernel when the skinny rows
+// kernel takes the product (N <= 16: the last block to finish runs the softmax); otherwise
+// sp_gemm_bias followed by sp_softmax_xent_fwd_grad.  Bit-identical either way.
+int sp_gemm_bias_softmax_xent(int64_t M, int64_t N, int64_t K, const float* A, const float* B,
+                              const float* bias, const int32_t* labels, float* logits,
+                              float* probs, float* loss, float* dlogits, float* colsum,
+                              int precision, sp_stream_t stream) {
+  SP_REQUIRE(M > 0 && N > 0 && K > 0, "empty problem");
+  SP_REQUIRE(M <= 2048 && M * N <= 32768, "gemm_bias_softmax_xent: single-block sizes only");
+  SP_REQUIRE(A && B && bias && labels && logits && probs && loss && dlogits && colsum, "null operand");
+  SP_REQUIRE(precision == SP_PRECISION_FP32 || precision == SP_PRECISION_TF32 ||
+                 precision == SP_PRECISION_TF32X3, "bad precision");
+  sp::IgemmParams p = sp::base_params();
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.A = A;
+  p.B = B;
+  p.C = logits;
+  p.ldc = N;
+  p.a_rs = K;
+  p.a_cs = 1;
+  p.b_rs = N;
+  p.b_cs = 1;
+  p.bias = bias;
+  if (!sp::use_umma(sp::kGemm, p, precision) && sp::g_umma_policy != 1 &&
+      sp::gemm_skinny_xent_supported(p)) {
+    unsigned int* words = sp::sync_words_for_current_device();
+    if (!words) return sp::set_error(SP_ERR_WORKSPACE, "gemm_bias_softmax_xent: no sync words");
+    p.xent_labels = labels;
+    p.xent_probs = probs;
+    p.xent_loss = loss;
+    p.xent_dlogits = dlogits;
+    p.xent_colsum = colsum;
+    p.tail_counter = words + 40;
+    p.xent_row_nll = sp::scratch_for_current_device();
+    if (!p.xent_row_nll) return sp::set_error(SP_ERR_WORKSPACE, "gemm_bias_softmax_xent: no scratch");
+    if (int rc = sp::launch_gemm_skinny(p, sp::as_stream(stream))) return rc;
+    SP_CHECK_LAUNCH("gemm_bias_softmax_xent");
+    return 0;
+  }
+  if (int rc = sp_gemm_bias(M, N, K, A, B, bias, logits, precision, stream)) return rc;
+  return sp_softmax_xent_fwd_grad(logits, labels, probs, loss, dlogits, colsum, M, N, stream);
+}
+
 int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
             int64_t strideA, const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc,
             int64_t strideC, int64_t batch, int precision, sp_stream_t stream) {
@@ -602,6 +649,32 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
     rc = sp_reduce_sum(static_cast<const float*>(workspace), dw, 1, splits, p.M * p.N, stream);
     if (rc) return rc;
   }
+  return 0;
+}
+
+// maxpool2d(leaky_relu(conv2d(x, w), alpha), 2, 2, strides 2) in ONE kernel for first-layer
+// geometries (RGB, 3 x 3, stride 1, even output grid, 16 / 32 filters; SP_PRECISION_TF32 or
+// SP_PRECISION_TF32X3): the full-resolution activation tensor is never written.  Bit-identical
+// to sp_conv2d_fprop followed by sp_maxpool2d_leaky_fwd / sp_maxpool2d_fwd_split.
+int sp_conv2d_leaky_pool2_supported(const sp_conv_geom* g, int precision, int* supported) {
+  if (int rc = sp::check_geom(g)) return rc;
+  SP_REQUIRE(supported != nullptr, "null output");
+  *supported = (sp::g_umma_policy == 0 && sp::conv_leaky_pool2_supported(*g, precision)) ? 1 : 0;
+  return 0;
+}
+
+int sp_conv2d_leaky_pool2_fwd(const float* x, const float* w, float* y_pooled, uint8_t* argmax,
+                              float* split, const sp_conv_geom* g, int precision, float alpha,
+                              sp_stream_t stream) {
+  if (int rc = sp::check_geom(g)) return rc;
+  SP_REQUIRE(x && w && y_pooled && argmax, "null operand");
+  if (sp::g_umma_policy != 0)
+    return sp::set_error(SP_ERR_UNSUPPORTED, "conv2d_leaky_pool2: kernel policy pins another kernel");
+  if ((int64_t)g->N * g->OH * g->OW * g->K == 0) return 0;
+  if (int rc = sp::launch_conv_leaky_pool2(x, w, y_pooled, argmax, split, *g, precision, alpha,
+                                           sp::as_stream(stream)))
+    return rc;
+  SP_CHECK_LAUNCH("conv2d_leaky_pool2_fwd");
   return 0;
 }
 

@@ -962,6 +962,172 @@ __global__ void __launch_bounds__(kThreads, KT == 4 ? 1 : 2) conv_fprop_rgb3x3_m
   }
 }
 
+
+// conv2d (RGB, 3x3, stride 1) + leaky_relu + maxpool2d(2, 2, strides 2) in ONE kernel
+// (sp.py:124-163, 231-236, 282-300): the CIFAR first layer writes 16.7 MB of activations that
+// the pool reads straight back; here a warp computes the same 16-pixel MMA tiles as the kernel
+// above for TWO vertically adjacent output rows, applies leaky_relu, and pools in registers --
+// the horizontal neighbour of a pixel lives in lane ^ 4 (accumulator row gq ^ 1), so the pair
+// of lanes swaps halves (even lane keeps the window of pixels gq, gq+1, odd lane the window of
+// pixels gq+7, gq+8) and each lane finishes one whole 2x2 window of 2 channels per n-tile.
+// Written: the pooled tensor, its uint8 argmax (dy*2+dx, first maximum wins, NaN wins: the
+// `take` rule of pool.cu) and optionally the TF32 (r, l) split of the pooled tensor that an
+// error-compensated conv2d consumes (tf32.cu) -- bit for bit what sp_conv2d_fprop followed
+// by sp_maxpool2d_fwd_split(leaky = 1) produce, without the full-resolution tensor.
+__device__ __forceinline__ void take_first_max(float v, int k, float& best, int& bi) {
+  if (v > best || (v != v && best == best)) {
+    best = v;
+    bi = k;
+  }
+}
+
+template <int KT, bool X3>
+__global__ void __launch_bounds__(kThreads, 2) conv_rgb3x3_leaky_pool2_mma_kernel(
+    const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ yp,
+    uint8_t* __restrict__ idx, float* __restrict__ split, const __grid_constant__ sp_conv_geom g,
+    const __grid_constant__ RgbFpropPlan pl, const float alpha) {
+  pdl_entry();
+  constexpr int K = 16 * KT, NJ = K / 8, KC = 27;
+  extern __shared__ __align__(16) float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+
+  for (int s = 0; s < 2; ++s)
+    for (int i = pl.x_staged + threadIdx.x; i < pl.x_floats; i += kThreads)
+      sm[s * pl.x_floats + i] = 0.f;
+
+  auto prefetch = [&](int tile_idx, int stage) {
+    const int n = tile_idx / pl.tiles_per_img;
+    const int oy0 = (tile_idx - n * pl.tiles_per_img) * pl.rows;
+    float* x_s = sm + stage * pl.x_floats;
+    const int xrow = pl.wv * 3, w3 = g.W * 3;
+    for (int i = threadIdx.x; i < pl.x_staged; i += kThreads) {
+      const int pr = i / xrow;
+      const int col3 = i - pr * xrow - 3 * g.pad_l;
+      const int iy = oy0 + pr - g.pad_t;
+      const bool in = (unsigned)iy < (unsigned)g.H && (unsigned)col3 < (unsigned)w3;
+      cp_async4_zfill(&x_s[i], in ? x + (int64_t)(n * g.H + iy) * w3 + col3 : x, in);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < pl.n_tiles) prefetch(blockIdx.x, 0);
+
+  uint32_t bf[4][NJ][2];
+  uint32_t bl[4][X3 ? NJ : 1][2];
+  int offa[4][2];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = 8 * s + t + 4 * h;
+      offa[s][h] = kk < KC ? (kk / 9) * pl.wv * 3 + kk % 9 : 0;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const uint32_t wv = kk < KC ? __float_as_uint(__ldg(w + kk * K + 8 * j + gq)) : 0u;
+        if (X3)
+          split_bits(wv, bf[s][j][h], bl[s][j][h]);
+        else
+          bf[s][j][h] = wv;
+      }
+    }
+  }
+
+  const int POH = g.OH >> 1, POW = g.OW >> 1;
+  const bool odd = (gq & 1) != 0;
+  int stage = 0;
+  for (int tile = blockIdx.x; tile < pl.n_tiles; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    if (next < pl.n_tiles) {
+      prefetch(next, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t* x_u = reinterpret_cast<const uint32_t*>(sm + stage * pl.x_floats);
+    const int n = tile / pl.tiles_per_img;
+    const int oy0 = (tile - n * pl.tiles_per_img) * pl.rows;
+    const int units = (min(pl.rows, g.OH - oy0) >> 1) * pl.chunks;
+    for (int u = warp; u < units; u += kThreads / 32) {
+      const int rp = u / pl.chunks;
+      const int xv0 = (u - rp * pl.chunks) * 16;
+      float v[2][NJ][4];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const uint32_t* ab = x_u + 3 * ((2 * rp + rr) * pl.wv + xv0 + gq);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[rr][j][c] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          uint32_t a[4];
+          a[0] = ab[offa[s][0]];
+          a[1] = ab[offa[s][0] + 24];
+          a[2] = ab[offa[s][1]];
+          a[3] = ab[offa[s][1] + 24];
+          if (X3) {
+            uint32_t al[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_bits(a[i], a[i], al[i]);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+              mma_tf32_m16n8k8(v[rr][j], al, bf[s][j]);
+              mma_tf32_m16n8k8(v[rr][j], a, bl[s][j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) mma_tf32_m16n8k8(v[rr][j], a, bf[s][j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            v[rr][j][c] = v[rr][j][c] > 0.f ? v[rr][j][c] : alpha * v[rr][j][c];
+      }
+      // this lane's window: even lane -> pixels (xv0 + gq, + 1), odd lane -> (xv0 + gq + 7, + 8)
+      const int px = (xv0 >> 1) + (gq >> 1) + (odd ? 4 : 0);
+      const int py = (oy0 >> 1) + rp;
+      const int64_t o = ((int64_t)(n * POH + py) * POW + px) * K + 2 * t;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float best[2];
+        int bi[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float win[4];
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const float mine = odd ? v[rr][j][2 + e] : v[rr][j][e];
+            const float send = odd ? v[rr][j][e] : v[rr][j][2 + e];
+            const float got = __shfl_xor_sync(0xffffffffu, send, 4);
+            win[2 * rr] = odd ? got : mine;       // the even pixel of the window (dx = 0)
+            win[2 * rr + 1] = odd ? mine : got;   // the odd pixel (dx = 1)
+          }
+          best[e] = win[0];
+          bi[e] = 0;
+          take_first_max(win[1], 1, best[e], bi[e]);
+          take_first_max(win[2], 2, best[e], bi[e]);
+          take_first_max(win[3], 3, best[e], bi[e]);
+        }
+        if (px < POW) {
+          *reinterpret_cast<float2*>(yp + o + 8 * j) = make_float2(best[0], best[1]);
+          *reinterpret_cast<uchar2*>(idx + o + 8 * j) =
+              make_uchar2((unsigned char)bi[0], (unsigned char)bi[1]);
+          if (split) {
+            const float r0 = rna_tf32(best[0]), r1 = rna_tf32(best[1]);
+            float* d = split + 2 * (o - 2 * t) + 2 * t + 8 * j;  // [pixel][r (K) | l (K)]
+            *reinterpret_cast<float2*>(d) = make_float2(r0, r1);
+            *reinterpret_cast<float2*>(d + K) = make_float2(best[0] - r0, best[1] - r1);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    stage ^= 1;
+  }
+}
+
 }  // namespace
 
 bool small_c_supported(const sp_conv_geom& g) {
@@ -1103,13 +1269,17 @@ static int launch_rgb_mma(const float* x, const float* gy, float* partial, float
   return 0;
 }
 
-static RgbFpropPlan rgb_fprop_plan(const sp_conv_geom& g, int slots) {
+// pool2: the fused conv + leaky_relu + 2x2 / stride-2 maxpool2d kernel -- tiles of an even number
+// of rows (they start at even rows), a warp's unit is a PAIR of rows x 16 pixels
+static RgbFpropPlan rgb_fprop_plan(const sp_conv_geom& g, int slots, bool pool2 = false) {
   RgbFpropPlan pl = {};
   if (!fixed_window(g) || g.sy != 1 || g.sx != 1 || !(g.K == 16 || g.K == 32 || g.K == 64))
     return pl;
+  if (pool2 && ((g.OH | g.OW) & 1)) return pl;
   const int wv = g.OW + 2, chunks = (g.OW + 15) / 16, warps = kThreads / 32;
   int64_t best = -1;
   for (int rows = std::min(g.OH, 32); rows >= 1; --rows) {
+    if (pool2 && (rows & 1)) continue;
     const int x_staged = (rows + 2) * wv * 3;
     const int x_floats = (3 * ((rows + 1) * wv + 16 * chunks) + 16 + 3) / 4 * 4;
     if (std::max(x_staged, x_floats) * 2 * 4 > 96 * 1024) continue;
@@ -1119,7 +1289,8 @@ static RgbFpropPlan rgb_fprop_plan(const sp_conv_geom& g, int slots) {
     const int64_t blocks = std::min<int64_t>(slots, tiles);
     const int64_t waves = (tiles + blocks - 1) / blocks;
     // serial steps of the busiest warp: units per warp and ~1 unit of per-tile overhead
-    const int64_t cost = waves * ((rows * chunks + warps - 1) / warps + 1);
+    const int units = pool2 ? (rows / 2) * chunks * 2 : rows * chunks;  // (a pair costs two rows)
+    const int64_t cost = waves * ((units + warps - 1) / warps + 1);
     if (best < 0 || cost < best) {
       best = cost;
       pl.rows = rows;
@@ -1153,6 +1324,53 @@ static int launch_rgb_fprop_mma(const float* x, const float* w, float* y, const 
                  g, pl, leaky, alpha);
   return 0;
 }
+
+template <int KT, bool X3>
+static int launch_rgb_leaky_pool2(const float* x, const float* w, float* yp, uint8_t* idx,
+                                  float* split, const sp_conv_geom& g, cudaStream_t st,
+                                  float alpha) {
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const RgbFpropPlan pl = rgb_fprop_plan(g, 2 * sms, true);
+  if (pl.rows == 0) return set_error(SP_ERR_UNSUPPORTED, "conv2d_leaky_pool2: unsupported geometry");
+  const size_t smem = (size_t)2 * pl.x_floats * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_rgb3x3_leaky_pool2_mma_kernel<KT, X3>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_done = true;
+  }
+  const int blocks = std::min(2 * sms, pl.n_tiles);
+  sp::launch_pdl(conv_rgb3x3_leaky_pool2_mma_kernel<KT, X3>, dim3(blocks), dim3(kThreads), smem, st,
+                 x, w, yp, idx, split, g, pl, alpha);
+  return 0;
+}
+
+// conv2d + leaky_relu + 2x2 / stride-2 maxpool2d in one kernel: first-layer (RGB, 3x3, stride 1)
+// geometries with an even output grid and 16 or 32 filters, tensor-core precisions
+bool conv_leaky_pool2_supported(const sp_conv_geom& g, int precision) {
+  if (precision != SP_PRECISION_TF32 && precision != SP_PRECISION_TF32X3) return false;
+  if (!small_c_supported(g) || !(g.K == 16 || g.K == 32)) return false;
+  if ((int64_t)g.N * g.OH * g.OW * g.K >= 0x7fffffffLL) return false;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  return rgb_fprop_plan(g, 2 * sms, true).rows > 0;
+}
+
+int launch_conv_leaky_pool2(const float* x, const float* w, float* y_pooled, uint8_t* idx,
+                            float* split, const sp_conv_geom& g, int precision, float alpha,
+                            cudaStream_t st) {
+  if (!conv_leaky_pool2_supported(g, precision))
+    return set_error(SP_ERR_UNSUPPORTED, "conv2d_leaky_pool2: unsupported geometry / precision");
+  if ((reinterpret_cast<uintptr_t>(y_pooled) & 7) || (reinterpret_cast<uintptr_t>(idx) & 1) ||
+      (reinterpret_cast<uintptr_t>(split) & 7))
+    return set_error(SP_ERR_UNSUPPORTED, "conv2d_leaky_pool2: unaligned outputs");
+  const bool x3 = precision == SP_PRECISION_TF32X3;
+  if (g.K == 16)
+    return x3 ? launch_rgb_leaky_pool2<1, true>(x, w, y_pooled, idx, split, g, st, alpha)
+              : launch_rgb_leaky_pool2<1, false>(x, w, y_pooled, idx, split, g, st, alpha);
+  return x3 ? launch_rgb_leaky_pool2<2, true>(x, w, y_pooled, idx, split, g, st, alpha)
+            : launch_rgb_leaky_pool2<2, false>(x, w, y_pooled, idx, split, g, st, alpha);
+}
+
 
 int small_c_wgrad_blocks(const sp_conv_geom& g) {
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;

@@ -19,16 +19,67 @@ namespace {
 constexpr int kMaxN = 16;
 constexpr int kThreads = 256;
 
+// Classifier head in the same launch (p.xent_labels set): softmax + cross entropy of the logits
+// this kernel produces, with the per-row arithmetic and the summation ORDER of
+// softmax_xent_fwd_kernel<true> (reduce.cu) so that the results are bit-identical to the
+// separate launch:
+//   * every block finishes ITS OWN rows as soon as their logits are complete (one warp per
+//     row: max, exp, sum, probabilities, the row's loss term, p - onehot);
+//   * the block that arrives LAST (arrival counter) adds the row losses -- lane w of warp 0
+//     adds rows w, w + W, ... and a shuffle tree adds the W totals, exactly what lane 0 of warp
+//     w and block_sum() do in a W-warp block there (W = 32 for more than 64 rows, else 8) --
+//     and the column sums of p - onehot (one warp per column, lanes stride the rows).
+__device__ __forceinline__ void softmax_xent_row(const IgemmParams& p, int64_t r, const float* lg,
+                                                 float* row_nll) {
+  const int cols = (int)p.N, lane = threadIdx.x & 31;
+  const float v = lane < cols ? lg[lane] : -INFINITY;
+  const int l = p.xent_labels[r];
+  const float m = warp_max(v);
+  const float e = lane < cols ? expf(v - m) : 0.f;
+  const float ssum = warp_sum(e);
+  const float pr = e * (1.f / ssum);
+  const float at = __shfl_sync(0xffffffffu, v, l & 31);
+  if (lane < cols) {
+    p.xent_probs[r * cols + lane] = pr;
+    p.xent_dlogits[r * cols + lane] = 1.f * (pr - ((lane == l) ? 1.f : 0.f));
+  }
+  if (lane == 0) row_nll[r] = (logf(ssum) + m) - at;
+}
+
+__device__ void softmax_xent_tail(const IgemmParams& p, const float* row_nll) {
+  const int rows = (int)p.M, cols = (int)p.N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = kThreads / 32;
+  if (warp == warps - 1) {
+    const int W = rows > 64 ? 32 : 8;
+    float t = 0.f;
+    if (lane < W)
+      for (int r = lane; r < rows; r += W) t += __ldcg(row_nll + r);
+    t = warp_sum(t);
+    if (lane == 0) p.xent_loss[0] = t;
+  }
+  for (int c = warp; c < cols; c += warps) {
+    float acc = 0.f;
+    for (int r = lane; r < rows; r += 32) acc += __ldcg(p.xent_dlogits + r * cols + c);
+    acc = warp_sum(acc);
+    if (lane == 0) p.xent_colsum[c] = acc;
+  }
+}
+
+constexpr int kTailMaxRows = 2048;
+
 // R rows per block: every B value fetched feeds R rows (a block per row re-read all of B --
 // 168 MB of L2 traffic for the VGG classifier [256, 16384] x [16384, 10]).  A long k axis is
 // split over the gridDim.y CTAs of a thread-block cluster (1, S, 1); rank 0 adds the S partial
 // tiles out of its peers' shared memory in rank order, so the result stays deterministic and
 // needs neither a workspace nor a second launch.
+// With p.xent_labels set the block that finishes LAST (arrival counter) runs the classifier's
+// softmax + cross entropy over the complete logits: the whole head in one launch.
 template <int NN, int R>
 __global__ void __launch_bounds__(kThreads) gemm_skinny_rows_kernel(const IgemmParams p) {
   pdl_entry();
   __shared__ float red[kThreads / 32][R][NN];
   __shared__ float part[R][NN];
+  __shared__ float lg[R][NN];  // this block's finished rows of C (the head's logits)
   const int64_t m0 = (int64_t)blockIdx.x * R;
   const int splits = (int)gridDim.y, rank = (int)blockIdx.y;
   const int64_t k_chunk = ((p.K + splits - 1) / splits + kThreads - 1) / kThreads * kThreads;
@@ -80,7 +131,26 @@ __global__ void __launch_bounds__(kThreads) gemm_skinny_rows_kernel(const IgemmP
         for (int q = 1; q < splits; ++q) s += *cluster.map_shared_rank(&part[r][n], q);
         if (p.bias) s += p.bias[n];  // after the full sum: the same bits as a separate add
         p.C[(m0 + r) * p.ldc + n] = s;
+        lg[r][n] = s;
       }
+    }
+  }
+  if (p.xent_labels != nullptr && rank == 0) {
+    __shared__ int is_last;
+    __syncthreads();  // lg[][] complete
+    if (warp < R && m0 + warp < p.M) softmax_xent_row(p, m0 + warp, lg[warp], p.xent_row_nll);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(p.tail_counter, 1u);
+      is_last = prev == gridDim.x - 1;
+      if (is_last) *p.tail_counter = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (is_last) {
+      // every row's loss term and p - onehot are in memory: finish the sums
+      __threadfence();
+      softmax_xent_tail(p, p.xent_row_nll);
     }
   }
   if (splits > 1) cluster.sync();  // peers keep their shared memory alive until rank 0 has read it
@@ -144,8 +214,15 @@ bool gemm_skinny_supported(const IgemmParams& p) {
   return p.a_cs == 1 || p.a_rs == 1;
 }
 
+bool gemm_skinny_xent_supported(const IgemmParams& p) {
+  return gemm_skinny_supported(p) && p.a_cs == 1 && p.ldc == p.N && p.M <= kTailMaxRows &&
+         p.M * p.N <= 32768;
+}
+
 int launch_gemm_skinny(const IgemmParams& p, cudaStream_t st) {
   if (!gemm_skinny_supported(p)) return set_error(SP_ERR_UNSUPPORTED, "gemm_skinny: unsupported");
+  if (p.xent_labels && !(gemm_skinny_xent_supported(p) && p.tail_counter))
+    return set_error(SP_ERR_UNSUPPORTED, "gemm_skinny: no softmax-xent tail for this problem");
   const bool wide = p.N > 8;
   if (p.a_cs == 1) {
     // Long k axes: 4 rows per block (B is fetched once per 4 rows) and a cluster of up to 8

@@ -48,10 +48,27 @@ struct IgemmParams {
   int k_splits;
   int64_t k_chunk;  // multiple of the kernel's K tile
   int64_t split_stride_c;
+  // CUDA-core GEMM only: K split over the CTAs of a thread-block cluster (1, 1, cluster_k <= 8),
+  // partial tiles added through distributed shared memory in rank order, then `bias` (if any)
+  // and the leaky epilogue: a small linear layer in ONE launch (launch_igemm_simt_cluster)
+  int cluster_k;
+  // skinny rows kernel only (gemm_skinny.cu): C are the logits of a classifier whose
+  // softmax + cross_entropy (sp.py:612-621) the LAST block to finish computes in the same
+  // launch -- probabilities, the summed loss, p - onehot and its column sums, bit-identical to
+  // sp_softmax_xent_fwd_grad.  xent_labels == null: plain GEMM.
+  const int32_t* xent_labels;
+  float* xent_probs;
+  float* xent_loss;
+  float* xent_dlogits;
+  float* xent_colsum;
+  float* xent_row_nll;          // scratch, M floats: the rows' loss terms
+  unsigned int* tail_counter;  // zero-initialised, self-resetting arrival counter
   sp_conv_geom g;
 };
 
 int launch_igemm_simt(int mode, const IgemmParams& p, cudaStream_t stream);
+// kGemm with p.cluster_k > 1 (K split over a cluster, bias / leaky epilogue)
+int launch_igemm_simt_cluster(const IgemmParams& p, cudaStream_t stream);
 int launch_igemm_umma(int mode, const IgemmParams& p, cudaStream_t stream);
 // true when the tcgen05 kernel supports this problem (shape / alignment constraints)
 bool igemm_umma_supported(int mode, const IgemmParams& p);
@@ -79,6 +96,8 @@ int launch_leaky_bwd_inplace(float* dx, const float* x, int64_t n, float alpha, 
 // N <= 16 GEMMs (the 10-way classifier and its weight gradient), gemm_skinny.cu: exact fp32
 bool gemm_skinny_supported(const IgemmParams& p);
 int launch_gemm_skinny(const IgemmParams& p, cudaStream_t stream);
+// true when launch_gemm_skinny would run p (with p.xent_* set) as ONE kernel including the tail
+bool gemm_skinny_xent_supported(const IgemmParams& p);
 
 // First-layer (C <= 4) CUDA-core kernels, conv_smallc.cu
 bool small_c_supported(const sp_conv_geom& g);
@@ -87,6 +106,12 @@ int small_c_wgrad_blocks(const sp_conv_geom& g);
 int launch_conv_fprop_smallc(const float* x, const float* w, float* y, const sp_conv_geom& g,
                              int precision, cudaStream_t st, int leaky = 0, float alpha = 0.f,
                              bool* fused_leaky = nullptr);
+// conv2d + leaky_relu + maxpool2d(2, 2, strides 2) in one kernel (first-layer geometries):
+// pooled tensor, uint8 argmax and (split != null) the TF32 (r, l) split of the pooled tensor
+bool conv_leaky_pool2_supported(const sp_conv_geom& g, int precision);
+int launch_conv_leaky_pool2(const float* x, const float* w, float* y_pooled, uint8_t* idx,
+                            float* split, const sp_conv_geom& g, int precision, float alpha,
+                            cudaStream_t st);
 // `*reduced` = true when the kernel already summed its partial filters into dw
 // first-layer filter gradient straight from the POOLED gradient of a leaky_relu -> 2x2 / stride-2
 // maxpool2d that follows the conv (conv_smallc.cu: PooledGy)

@@ -270,6 +270,7 @@ def test_classifier_bias_fusions_match_the_separate_ops(rows, k, n, bias_shape):
 
     def run(fuse):
         core._fuse_bias = fuse  # only these two fusions: the loss kernels stay the same
+        core._fuse_head = False  # (the whole-head kernel has its own test below)
         try:
             xv, wv, bv = sp.Variable(x), sp.Variable(w), sp.Variable(b)
             pre = sp.mul(xv, sp.Variable(np.full(x.shape, 1.25)))  # an op result feeds matmul
@@ -285,6 +286,7 @@ def test_classifier_bias_fusions_match_the_separate_ops(rows, k, n, bias_shape):
             return out, fwd_launches
         finally:
             core._fuse_bias = True
+            core._fuse_head = True
 
     fused, n_fused = run(True)
     plain, n_plain = run(False)
@@ -295,6 +297,56 @@ def test_classifier_bias_fusions_match_the_separate_ops(rows, k, n, bias_shape):
     assert_close(fused[4], plain[4], 1e-6, "bias gradient")
     ref = (x * 1.25) @ w
     assert_close(fused[5], ref, 2e-5 if n < 16 else 2e-3, "deferred matmul value, read after the fact")
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x1", "fp32"])
+@pytest.mark.parametrize("rows,k,n", [(128, 1152, 10), (200, 100, 10), (37, 300, 16), (256, 16384, 10),
+                                      (64, 512, 3), (1500, 64, 12)])
+def test_classifier_head_in_one_kernel_is_bit_identical(rows, k, n, precision):
+    """cross_entropy(softmax(matmul(h, w) + b), y) for N <= 16 is ONE kernel
+    (sp_gemm_bias_softmax_xent: the last block of the skinny GEMM runs the softmax, the loss
+    sum, p - onehot and its column sums).  Logits, probabilities, loss and every gradient equal
+    the separate launches bit for bit -- repeatedly (the arrival counter resets itself)."""
+    from smallpebble_b200 import _abi, core
+
+    rng = np.random.default_rng(rows + k + n)
+    x = rng.random((rows, k)) - 0.5
+    w = (rng.random((k, n)) - 0.5) * 4 / np.sqrt(k)
+    b = rng.random((n,)) - 0.5
+    labels = rng.integers(0, n, rows)
+    sp.set_precision(precision)
+
+    def run(fuse):
+        core._fuse_head = fuse
+        try:
+            xv, wv, bv = sp.Variable(x), sp.Variable(w), sp.Variable(b)
+            pre = sp.mul(xv, sp.Variable(np.full(x.shape, 1.25)))  # an op result feeds matmul
+            before = _abi.counter.launches
+            logits = sp.add(sp.matmul(pre, wv), bv)
+            probs = sp.softmax(logits)
+            loss = sp.cross_entropy(probs, labels)
+            fwd_launches = _abi.counter.launches - before
+            g = sp.get_gradients(loss)
+            out = [np.asarray(logits.array), np.asarray(probs.array), np.asarray(loss.array),
+                   np.asarray(g[wv]), np.asarray(g[xv]), np.asarray(g[bv])]
+            return out, fwd_launches
+        finally:
+            core._fuse_head = True
+
+    try:
+        fused, n_fused = run(True)
+        again, _ = run(True)
+        plain, n_plain = run(False)
+    finally:
+        sp.set_precision("tf32")
+    assert n_plain == 2
+    assert n_fused == 1
+    for a, c, d in zip(fused, again, plain):
+        assert np.array_equal(a, d) and np.array_equal(c, d)
+    z = (x * 1.25) @ w + b
+    e = np.exp(z - z.max(1, keepdims=True))
+    ref = -np.log(e[np.arange(rows), labels] / e.sum(1)).sum()
+    assert_close(fused[2], ref, 2e-5 if precision != "tf32x1" else 2e-3, "loss")
 
 
 @pytest.mark.parametrize("policy", [0, 32 + 256, 32 + 128], ids=["policy", "tma2", "halo"])
@@ -398,6 +450,69 @@ def test_leaf_gradient_read_after_the_update_sees_the_old_weights(optimiser):
     assert np.abs(before).max() > 0
     assert np.array_equal(before, after)
     assert np.array_equal(before, late)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x1"])
+@pytest.mark.parametrize("shape,k,padding", [((16, 32, 32, 3), 32, "SAME"), ((5, 14, 18, 3), 16, "VALID"),
+                                             ((3, 40, 36, 3), 32, "SAME"), ((2, 10, 10, 3), 64, "VALID")])
+def test_first_layer_conv_leaky_pool_in_one_kernel_is_bit_identical(shape, k, padding, precision):
+    """conv2d (3x3, C = 3) -> leaky_relu -> maxpool2d(2, 2, stride 2) as ONE forward kernel
+    (sp_conv2d_leaky_pool2_fwd): pooled values, argmax bytes, the (r, l) split the next
+    compensated conv2d consumes and every gradient equal the separate launches bit for bit; the
+    64-filter case has no such kernel and must take the old path."""
+    from smallpebble_b200 import _abi, core
+
+    rng = np.random.default_rng(21)
+    x = rng.random(shape) - 0.5
+    w = (rng.random((3, 3, 3, k)) - 0.5) * 0.5
+    w2 = (rng.random((3, 3, k, 128)) - 0.5) * 0.2  # (shape0: the README CNN's second conv)
+    sp.set_precision(precision)
+    calls = []
+    orig = _abi.f.sp_conv2d_leaky_pool2_fwd
+
+    def spy(*args):
+        calls.append(args[4])  # the split pointer (None the first time: no hint yet)
+        return orig(*args)
+
+    def run(read_dx):
+        xv, wv, w2v = sp.Variable(x), sp.Variable(w), sp.Variable(w2)
+        sp.learnable(wv), sp.learnable(w2v)
+        h = sp.conv2d(xv, wv, padding)
+        p = sp.maxpool2d(sp.leaky_relu(h, 0.1), 2, 2, strides=[2, 2])
+        out = sp.conv2d(p, w2v, "VALID")
+        gy = np.random.default_rng(22).random(out.shape) - 0.5
+        g = sp.get_gradients(sp.mul(out, sp.Variable(gy)))
+        res = [np.asarray(p.array), np.asarray(p._argmax), np.asarray(out.array),
+               np.asarray(g[wv]), np.asarray(g[w2v])]
+        if read_dx:
+            res.append(np.asarray(g[xv]))
+            res.append(np.asarray(h.array))  # the full-resolution tensor, launched on demand
+        return res
+
+    _abi.f.sp_conv2d_leaky_pool2_fwd = spy
+    try:
+        core._fuse_conv_pool = True
+        fused_a = run(False)
+        fused_b = run(True)   # second run: the split hint of the consumer conv is known
+        n_fused = len(calls)
+        core._fuse_conv_pool = False
+        plain = run(True)
+    finally:
+        _abi.f.sp_conv2d_leaky_pool2_fwd = orig
+        core._fuse_conv_pool = True
+        sp.set_precision("tf32")
+    assert len(calls) == n_fused
+    if k <= 32:
+        # (a pooled tensor whose consumer wants another split layout is pooled the old way)
+        assert n_fused >= 1
+        if precision == "tf32" and shape[0] == 16:
+            assert n_fused == 2 and calls[1] is not None  # the split comes out of the same kernel
+    else:
+        assert n_fused == 0
+    for a, b in zip(fused_a, plain):
+        assert np.array_equal(a, b)
+    for a, b in zip(fused_b, plain):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("shape,k", [((16, 32, 32, 3), 32), ((5, 14, 18, 3), 16), ((3, 10, 10, 3), 64)])
