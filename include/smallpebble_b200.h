@@ -106,6 +106,11 @@ int sp_stream_wait_event(sp_stream_t stream, void* event);
 /* copies and waits for the stream: the only blocking call of the ABI (sp.py users read
  * `.array`, e.g. np.isnan(loss_val.array), README.md:156) */
 int sp_memcpy_d2h(void* host_dst, const void* src, size_t bytes, sp_stream_t stream);
+/* the non-blocking form, into page-locked host memory, and the wait that goes with it: a
+ * replayed forward pass mirrors its (scalar) result to the host so that the loop's
+ * np.isnan(loss_val.array) (README.md:319) costs one event wait, not a copy of its own */
+int sp_memcpy_d2h_async(void* pinned_dst, const void* src, size_t bytes, sp_stream_t stream);
+int sp_event_synchronize(void* event);
 int sp_memcpy_d2d(void* dst, const void* src, size_t bytes, sp_stream_t stream);
 int sp_fill_f32(float* dst, int64_t n, float value, sp_stream_t stream);
 /* float64 host data uploaded raw then narrowed on device (np.float64 -> device fp32) */
@@ -281,6 +286,19 @@ int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_ge
  * followed by sp_leaky_relu_bwd */
 int sp_conv2d_dgrad_leaky(const float* gy, const float* w, const float* act, float* dx,
                           const sp_conv_geom* g, int precision, float alpha, sp_stream_t stream);
+/* Backward of conv2d(maxpool2d(leaky_relu(z), 2, 2, strides = [2, 2])) with respect to z in one
+ * pass (sp.py:142-158 col2im gradient, 384-387 pool scatter, 231-236): the conv's data gradient
+ * is scattered to each window's argmax and multiplied by leaky_relu's slope as the kernel
+ * stores; the pooled gradient is never written.  dx_full [N, up_H, up_W, C]; argmax / y_pooled
+ * (the pool's outputs) are laid out like the conv's input [N, H, W, C], H = ceil(up_H / 2).
+ * Bit-identical to sp_conv2d_dgrad followed by sp_maxpool2d_leaky_bwd (alpha > 0).  Only
+ * problems for which sp_conv2d_dgrad_unpool_supported sets *supported = 1. */
+int sp_conv2d_dgrad_unpool_supported(const sp_conv_geom* g, int up_H, int up_W, int precision,
+                                     int* supported);
+int sp_conv2d_dgrad_unpool_leaky(const float* gy, const float* w, const uint8_t* argmax,
+                                 const float* y_pooled, float* dx_full, const sp_conv_geom* g,
+                                 int up_H, int up_W, int precision, float alpha,
+                                 sp_stream_t stream);
 /* dw = im2col(x)^T * gy, split over the N*OH*OW reduction; workspace from
  * sp_conv2d_wgrad_workspace() (may be 0 bytes) */
 size_t sp_conv2d_wgrad_workspace(const sp_conv_geom* g, int precision);

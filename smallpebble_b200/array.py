@@ -16,6 +16,7 @@ import ctypes as C
 import functools
 import math
 import numbers
+import os
 import weakref
 
 import numpy as np
@@ -86,6 +87,7 @@ def reset_device_cache():
     _raw_stream = None
     trim_pool()  # recycled buffers belong to the previous device
     _upload_ring.reset()
+    _prestaged.clear()
 
 
 _raw_stream = None
@@ -387,6 +389,8 @@ class DeviceArray:
                 # The upload DMAs the raw bytes from it and float64 is narrowed on the device.
                 # Like the reference's Variable(array), this aliases the caller's array until
                 # the copy has run (the array is kept alive; do not overwrite it in between).
+                if eager_staging and a.dtype == np.float64 and a.size and _device is not None:
+                    _prestage(a)  # the DMA starts now, on the copy stream
                 return DeviceArray(a.shape, dtype, host=a)
             host = _pinned.take(a.shape, dtype)
             np.copyto(host, a, casting="unsafe")  # one pass: convert + stage
@@ -459,12 +463,23 @@ class DeviceArray:
         if self._ptr is None:
             return np.array(self._host, dtype=self.dtype, copy=True)
         out = np.empty(self.shape, self.dtype)
-        if self._ready is not None:
+        ready = self._ready
+        if type(ready) is tuple:
+            # (event, host mirror, slot generations, slot, generation): the producer also copied
+            # the contents into page-locked host memory before the event -- one wait, no copy
+            # of our own -- unless the ring has come round to this slot since
+            ready, mirror, gens, slot, gen = ready
+            if gens[slot] == gen:
+                F.sp_event_synchronize(ready)
+                out.reshape(-1).view(np.uint8)[:] = mirror[:out.nbytes]
+                _counters["d2h_bytes"] += out.nbytes
+                return out
+        if ready is not None:
             # the contents were final at this event (the result of a replayed forward pass):
             # read them on the copy stream as soon as it has fired, without waiting for work
             # enqueued behind it on the compute stream (steady.py's speculative backward pass)
             side = _read_stream()
-            F.sp_stream_wait_event(side, self._ready)
+            F.sp_stream_wait_event(side, ready)
             F.sp_memcpy_d2h(out.ctypes.data, self._ptr, out.nbytes, side)
         else:
             F.sp_memcpy_d2h(out.ctypes.data, self._ptr, out.nbytes, stream())
@@ -683,58 +698,98 @@ class _UploadRing:
     the copy stream waits for the event recorded after a slot's last consumer (the narrowing
     kernel on the compute stream) before overwriting it, and the compute stream waits for the
     copy's event before reading it.  The buffers never go back to torch's allocator while in
-    use, so no cross-stream reuse hazard exists."""
+    use, so no cross-stream reuse hazard exists.  Stream and events are raw handles driven
+    through the C ABI (an upload is on the README loop's critical path: a torch.cuda.Event
+    costs more host time than the copy call), two events per slot, re-recorded."""
 
     SLOTS = 3
 
     def __init__(self):
         self.stream = None
-        self.slots = [{"buf": None, "nbytes": 0, "free": None} for _ in range(self.SLOTS)]
+        self.slots = [{"buf": None, "ptr": 0, "nbytes": 0, "landed": None, "free": None,
+                       "free_valid": False, "host": None, "gen": 0} for _ in range(self.SLOTS)]
         self.next = 0
 
     def reset(self):
         self.__init__()
 
-    def upload(self, host_ptr: int, nbytes: int):
-        torch = _lazy_torch()
+    def upload(self, host: np.ndarray, wait: bool = True):
+        """Start the DMA of `host` into the next slot; `wait`: order the compute stream behind
+        it now (else the caller does, later: `slot["landed"]`).  The slot keeps `host` alive
+        until it is reused, which first makes sure that copy has completed."""
         if self.stream is None:
-            self.stream = torch.cuda.Stream()
+            st = (C.c_void_p * 1)()
+            F.sp_stream_create(st)
+            self.stream = st[0]
         slot = self.slots[self.next]
         self.next = (self.next + 1) % self.SLOTS
+        slot["gen"] += 1  # (a pre-staged upload of an older generation is gone)
+        nbytes = host.nbytes
+        if slot["landed"] is None:
+            slot["landed"], slot["free"] = new_event(), new_event()
+        elif slot["host"] is not None:
+            F.sp_event_synchronize(slot["landed"])  # three uploads ago: long complete
         if slot["nbytes"] < nbytes:
-            if slot["free"] is not None:
-                slot["free"].synchronize()  # rare: the slot grows; its last reader must be done
+            torch = _lazy_torch()
+            if slot["free_valid"]:
+                F.sp_event_synchronize(slot["free"])  # rare: the slot grows; its last reader must be done
             slot["buf"] = torch.empty(nbytes, dtype=torch.uint8, device=require_cuda())
+            slot["ptr"] = slot["buf"].data_ptr()
             slot["nbytes"] = nbytes
-            slot["free"] = None
+            slot["free_valid"] = False
             # the new block may be a recycled one: order the copy after everything queued so far
-            self.stream.wait_stream(torch.cuda.current_stream())
-        if slot["free"] is not None:
-            self.stream.wait_event(slot["free"])
-        F.sp_memcpy_h2d(slot["buf"].data_ptr(), host_ptr, nbytes, self.stream.cuda_stream)
-        landed = torch.cuda.Event()
-        landed.record(self.stream)
-        torch.cuda.current_stream().wait_event(landed)
+            F.sp_event_record(slot["free"], stream())
+            F.sp_stream_wait_event(self.stream, slot["free"])
+        if slot["free_valid"]:
+            F.sp_stream_wait_event(self.stream, slot["free"])
+        F.sp_memcpy_h2d(slot["ptr"], host.ctypes.data, nbytes, self.stream)
+        F.sp_event_record(slot["landed"], self.stream)
+        slot["host"] = host
+        if wait:
+            F.sp_stream_wait_event(stream(), slot["landed"])
         return slot
 
     @staticmethod
     def consumed(slot):
-        ev = _lazy_torch().cuda.Event()
-        ev.record()  # on the compute stream, after the kernel that read the slot
-        slot["free"] = ev
+        F.sp_event_record(slot["free"], stream())  # after the kernel that read the slot
+        slot["free_valid"] = True
 
 
 _upload_ring = _UploadRing()
 
 
+# Uploads whose DMA was started when the caller wrapped its page-locked float64 batch
+# (`sp.Variable(xbatch)`), before the array was first needed on the device: host data pointer ->
+# (slot, slot generation, bytes).  In the README loop the batch is wrapped a few API calls before
+# `run()` reaches the upload, and the host-to-device copy is on the loop's critical path.
+_prestaged = {}
+eager_staging = os.environ.get("SP_EAGER_UPLOAD", "1") != "0"
+
+
+def _prestage(host: np.ndarray) -> None:
+    if forbid_uploads or capturing():
+        return
+    if len(_prestaged) >= 8:  # wrapped but never used: their slots have been recycled
+        for k in [k for k, (sl, gen, _) in _prestaged.items() if sl["gen"] != gen]:
+            del _prestaged[k]
+        if len(_prestaged) >= 8:
+            return
+    slot = _upload_ring.upload(host, wait=False)
+    _prestaged[host.ctypes.data] = (slot, slot["gen"], host.nbytes)
+
+
 def upload_f64_narrowed(host: np.ndarray, dst_ptr: int) -> None:
-    """float64 page-locked `host` -> fp32 at `dst_ptr`: raw DMA on the copy stream, narrowing
-    kernel on the compute stream."""
-    slot = _upload_ring.upload(host.ctypes.data, host.nbytes)
-    F.sp_cast_f64_f32(slot["buf"].data_ptr(), dst_ptr, host.size, stream())
+    """float64 page-locked `host` -> fp32 at `dst_ptr`: raw DMA on the copy stream (already
+    under way when the array was pre-staged), narrowing kernel on the compute stream."""
+    pre = _prestaged.pop(host.ctypes.data, None) if _prestaged else None
+    if pre is not None and pre[0]["gen"] == pre[1] and pre[2] == host.nbytes:
+        slot = pre[0]
+        F.sp_stream_wait_event(stream(), slot["landed"])
+    else:
+        slot = _upload_ring.upload(host)
+    F.sp_cast_f64_f32(slot["ptr"], dst_ptr, host.size, stream())
     _UploadRing.consumed(slot)
     _counters["h2d_bytes"] += host.nbytes
-    _keep_alive_until_copied(host)
 
 
 def pinned_empty(shape, dtype):

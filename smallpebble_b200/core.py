@@ -594,6 +594,24 @@ def square(a: Variable) -> Variable:
                     [(a, lambda g: A.binary("mul", g, A.unary("scale", av, 2.0)))])
 
 
+_dgrad_unpool_cache = {}
+
+
+def _dgrad_unpool_ok(cgeom, up_h, up_w, prec) -> bool:
+    """Does the library scatter this conv's data gradient through a 2x2 max-pool in its own
+    epilogue (sp_conv2d_dgrad_unpool_supported)?  Asked once per geometry."""
+    key = (cgeom.N, cgeom.H, cgeom.W, cgeom.C, cgeom.KH, cgeom.KW, cgeom.K, cgeom.sy, cgeom.sx,
+           cgeom.pad_t, cgeom.pad_l, cgeom.OH, cgeom.OW, up_h, up_w, prec, _steady.config_epoch)
+    ok = _dgrad_unpool_cache.get(key)
+    if ok is None:
+        flag = C.c_int(0)
+        _abi.f.sp_conv2d_dgrad_unpool_supported(cgeom, up_h, up_w, prec, flag)
+        if len(_dgrad_unpool_cache) > 256:
+            _dgrad_unpool_cache.clear()
+        ok = _dgrad_unpool_cache[key] = bool(flag.value)
+    return ok
+
+
 def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
     """Elementwise leaky relu (sp.py:231-236): x > 0 ? x : alpha*x; the slope at 0 is alpha.
 
@@ -640,6 +658,19 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
                 # needs the full-resolution gradient
                 return DeviceArray.deferred(x.shape, launch_pool_bwd,
                                             ("pool_leaky_bwd", g0, idx, ypool, alpha), x.size)
+            gtag = g0.pending_tag if type(g0) is DeviceArray else None
+            if (gtag is not None and gtag[0] == "conv2d_dgrad" and alpha > 0 and _fuse_dgrad_unpool
+                    and geom[4:10] == (2, 2, 2, 2, 0, 0)):
+                # ... and the pooled gradient is itself a conv data gradient that has not been
+                # launched: the conv kernel scatters through the argmax as it stores
+                # (sp_conv2d_dgrad_unpool_leaky); the pooled gradient stays unlaunched
+                _, cg, cw, cgeom, cprec = gtag
+                if _dgrad_unpool_ok(cgeom, geom[1], geom[2], cprec):
+                    rounded = _want_rounding(a)
+                    F.sp_conv2d_dgrad_unpool_leaky(cg.ptr, cw.ptr, idx.ptr, ypool.ptr, dx.ptr, cgeom,
+                                                   geom[1], geom[2], cprec, alpha, A.stream())
+                    dx._tf32 = rounded
+                    return dx
             launch_pool_bwd(dx)
             return dx
         # the slope depends on the sign of the input only; when the input was never stored
@@ -1152,6 +1183,13 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
 _pooled_wgrad = os.environ.get("SP_POOLED_WGRAD", "1") != "0"
 _fuse_conv_pool = os.environ.get("SP_FUSE_CONV_POOL", "1") != "0"  # conv + leaky + pool, one kernel
 _fuse_head = os.environ.get("SP_FUSE_HEAD", "1") != "0"  # matmul + bias + softmax + cross_entropy
+# conv data gradient scattered through the following pool / leaky_relu backward in the conv
+# kernel's epilogue (sp_conv2d_dgrad_unpool_leaky).  OFF by default: alone the fused kernel beats
+# the two launches (15.1 vs 18.2 us on the README CNN's conv3), but inside the backward graph the
+# step gets 2.4 us LONGER -- the heavy one-CTA-per-SM conv kernels of the two streams queue for
+# SMs, and the light pool kernel used to run beside them while the fused epilogue keeps 100 SMs
+# 3.6 us longer (scripts/steady_parts.py).
+_fuse_dgrad_unpool = os.environ.get("SP_FUSE_DGRAD_UNPOOL", "0") == "1"
 
 
 def _pooled_wgrad_geom(plan, out_shape):

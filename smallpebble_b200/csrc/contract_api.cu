@@ -528,6 +528,70 @@ static int conv2d_dgrad_impl(const float* gy, const float* w, float* dx, const s
   return 0;
 }
 
+// conv2d data gradient scattered straight through the 2 x 2 / stride-2 maxpool2d (no padding on
+// the top / left, windows tiling the whole image) and the leaky_relu that produced the conv's
+// input: what sp_conv2d_dgrad followed by sp_maxpool2d_leaky_bwd compute, as the epilogue of the
+// 2-SM TMA kernel -- the pooled gradient is never stored.  dx_full [N, up_H, up_W, C] with
+// ceil(up_H / 2) == g->H, ceil(up_W / 2) == g->W; argmax / y_pooled laid out like the conv's
+// input.  Only where sp_conv2d_dgrad_unpool_supported says so (the problems the TMA kernel
+// takes by policy); bit-identical to the two launches.
+static bool dgrad_unpool_params(const sp_conv_geom* g, int up_H, int up_W, int precision,
+                                sp::IgemmParams* out) {
+  sp::IgemmParams p = sp::base_params();
+  p.g = *g;
+  p.M = (int64_t)g->N * g->H * g->W;
+  p.N = g->C;
+  p.K = (int64_t)g->KH * g->KW * g->K;
+  p.ldc = g->C;
+  *out = p;
+  if (g->sy != 1 || g->sx != 1 || g->C % 32 != 0 || p.M == 0 || (int64_t)g->OH * g->OW == 0)
+    return false;
+  if ((up_H + 1) / 2 != g->H || (up_W + 1) / 2 != g->W) return false;
+  if ((int64_t)g->N * up_H * up_W * g->C >= 0x7fffffffLL) return false;
+  // Small problems only (at most half a wave of 256-row tiles): there the scatter rides on the
+  // cluster reduction that already ends the kernel (CIFAR conv3's data gradient: 15.1 us against
+  // 11.5 + 6.7 us for the two launches).  On a full grid the four epilogue warps of a CTA cannot
+  // issue four times the stores plus the argmax reads fast enough (batch 400, 256 channels:
+  // 91 us against 19 + 44 us; scripts/unpool_probe.py).
+  const int sms = sp::device_info().sm_count > 0 ? sp::device_info().sm_count : 148;
+  if ((p.M + 255) / 256 > sms / 4) return false;
+  return !sp::use_halo(sp::kDgrad, p, precision) && sp::use_tma2(sp::kDgrad, p, precision);
+}
+
+int sp_conv2d_dgrad_unpool_supported(const sp_conv_geom* g, int up_H, int up_W, int precision,
+                                     int* supported) {
+  if (int rc = sp::check_geom(g)) return rc;
+  SP_REQUIRE(supported != nullptr, "null output");
+  sp::IgemmParams p;
+  *supported = dgrad_unpool_params(g, up_H, up_W, precision, &p) ? 1 : 0;
+  return 0;
+}
+
+int sp_conv2d_dgrad_unpool_leaky(const float* gy, const float* w, const uint8_t* argmax,
+                                 const float* y_pooled, float* dx_full, const sp_conv_geom* g,
+                                 int up_H, int up_W, int precision, float alpha,
+                                 sp_stream_t stream) {
+  if (int rc = sp::check_geom(g)) return rc;
+  SP_REQUIRE(gy && w && argmax && y_pooled && dx_full, "null operand");
+  sp::IgemmParams p;
+  if (!dgrad_unpool_params(g, up_H, up_W, precision, &p))
+    return sp::set_error(SP_ERR_UNSUPPORTED, "conv2d_dgrad_unpool: unsupported problem");
+  if ((reinterpret_cast<uintptr_t>(dx_full) | reinterpret_cast<uintptr_t>(y_pooled)) & 15 ||
+      reinterpret_cast<uintptr_t>(argmax) & 3)
+    return sp::set_error(SP_ERR_UNSUPPORTED, "conv2d_dgrad_unpool: unaligned operands");
+  p.A = gy;
+  p.B = w;
+  p.C = dx_full;
+  p.leaky_alpha = alpha;
+  p.up_idx = argmax;
+  p.up_y = y_pooled;
+  p.up_H = up_H;
+  p.up_W = up_W;
+  if (int rc = sp::launch_conv_tma2(sp::kDgrad, p, sp::as_stream(stream))) return rc;
+  SP_CHECK_LAUNCH("conv2d_dgrad_unpool_leaky");
+  return 0;
+}
+
 int sp_conv2d_dgrad(const float* gy, const float* w, float* dx, const sp_conv_geom* g,
                     int precision, sp_stream_t stream) {
   return conv2d_dgrad_impl(gy, w, dx, g, precision, nullptr, 0.f, stream);

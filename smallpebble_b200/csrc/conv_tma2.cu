@@ -84,6 +84,13 @@ struct Tma2Params {
   int out_sy, out_sx;            // output pixel (u, v) of the phase = real pixel
   int out_oy, out_ox;            //   (out_oy + out_sy * u, out_ox + out_sx * v)
   int out_H, out_W;              // of an image of out_H x out_W pixels (out_sy == 0: dense rows)
+  // dgrad, EPI == 2: the data gradient is the gradient of a 2 x 2 / stride-2 max-pooled tensor
+  // (sp.py:282-300) whose input went through leaky_relu: row m = pooled pixel (n, u, v) is
+  // scattered to its window's argmax in the FULL-resolution gradient C [N, up_H, up_W, ldc],
+  // times leaky's slope there (the sign of the pooled output), the other window pixels get 0
+  const uint8_t* up_idx;  // argmax bytes (dy * 2 + dx), laid out like the pooled tensor
+  const float* up_y;      // the pool's output, laid out like the pooled tensor
+  int up_H, up_W;
   int ksplit;          // CTA pairs per cluster (1, 2 or 4): a small problem's reduction axis is
                        // split over the pairs of one cluster, which then add their accumulators
                        // through distributed shared memory in pair order (one tile per cluster)
@@ -406,6 +413,84 @@ __device__ __forceinline__ int64_t out_row(const Tma2Params& p, int m) {
   return ((int64_t)n * p.out_H + p.out_oy + p.out_sy * u) * p.out_W + p.out_ox + p.out_sx * v;
 }
 
+// EPI == 2: where pooled pixel m lands in the full-resolution gradient.  base = element offset of
+// window pixel (0, 0); flags bit 0 / 1: the window's second column / row is inside the image.
+__device__ __forceinline__ void unpool_row(const Tma2Params& p, int m, int64_t& base, int& flags) {
+  const int hw = p.D1 * p.D2;
+  const int n = m / hw, r = m - n * hw;
+  const int u = r / p.D2, v = r - u * p.D2;
+  base = (((int64_t)n * p.up_H + 2 * u) * p.up_W + 2 * v) * p.ldc;
+  flags = ((2 * v + 1 < p.up_W) ? 1 : 0) | ((2 * u + 1 < p.up_H) ? 2 : 0);
+}
+// four channels of pooled pixel m (element offset `pooled` in the pooled tensor): the argmax bytes
+// and the pool output are fetched EARLY (they do not depend on the accumulator: their latency
+// hides behind the TMEM / distributed-shared-memory reads), then slope, rounding and one 16-byte
+// store per window pixel -- the bits sp_maxpool2d_leaky_bwd writes
+struct UnpoolSrc {
+  uchar4 k;
+  float4 y;
+};
+__device__ __forceinline__ UnpoolSrc unpool_load4(const Tma2Params& p, int64_t pooled) {
+  UnpoolSrc u;
+  u.k = __ldg(reinterpret_cast<const uchar4*>(p.up_idx + pooled));
+  u.y = __ldg(reinterpret_cast<const float4*>(p.up_y + pooled));
+  return u;
+}
+__device__ __forceinline__ void unpool_store4(const Tma2Params& p, float4 val, const UnpoolSrc& u,
+                                              int64_t base, int flags) {
+  val.x *= u.y.x > 0.f ? 1.f : p.alpha;
+  val.y *= u.y.y > 0.f ? 1.f : p.alpha;
+  val.z *= u.y.z > 0.f ? 1.f : p.alpha;
+  val.w *= u.y.w > 0.f ? 1.f : p.alpha;
+  val = round_out4(val, p.round_out);
+  float* o = p.C + base;
+  const int64_t rs = (int64_t)p.up_W * p.ldc;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    if ((w & 1) && !(flags & 1)) continue;
+    if ((w & 2) && !(flags & 2)) continue;
+    *reinterpret_cast<float4*>(o + (w >> 1) * rs + (w & 1) * p.ldc) =
+        make_float4(u.k.x == w ? val.x : 0.f, u.k.y == w ? val.y : 0.f, u.k.z == w ? val.z : 0.f,
+                    u.k.w == w ? val.w : 0.f);
+  }
+}
+
+// the 32 x 32 block of store_block_rows, scattered (EPI == 2): lane (row group lane >> 3, chunk
+// lane & 7) handles rows (lane >> 3) + 4 r; ub / uf = unpool_row of those rows, src = their
+// prefetched argmax / pool output for this column block
+__device__ __forceinline__ void load_unpool_rows(UnpoolSrc (&src)[8], const Tma2Params& p,
+                                                 int m_base, uint32_t ok_mask, int col0, int lane) {
+  const int chunk = lane & 7;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = (lane >> 3) + 4 * r;
+    if ((ok_mask >> r) & 1u)
+      src[r] = unpool_load4(p, (int64_t)(m_base + row) * p.ldc + col0 + chunk * 4);
+  }
+}
+__device__ __forceinline__ void store_block_rows_unpool(uint8_t* tile, const uint32_t (&v)[32],
+                                                        int lane, const Tma2Params& p,
+                                                        const int64_t (&ub)[8], uint32_t uf,
+                                                        uint32_t ok_mask, int col0,
+                                                        const UnpoolSrc (&src)[8]) {
+  float4* t4 = reinterpret_cast<float4*>(tile);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    t4[lane * 8 + (j ^ (lane & 7))] =
+        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+  __syncwarp();
+  const int chunk = lane & 7;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = (lane >> 3) + 4 * r;
+    const float4 val = t4[row * 8 + (chunk ^ (row & 7))];
+    if ((ok_mask >> r) & 1u)
+      unpool_store4(p, val, src[r], ub[r] + col0 + chunk * 4, (int)((uf >> (2 * r)) & 3u));
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
@@ -443,11 +528,15 @@ struct ModeCfg {
 // ACT: the dgrad instantiation with the leaky_relu-backward epilogue (its prefetch registers
 // would otherwise cost the plain data gradient 2-3 %)
 // Launched with a runtime cluster dimension of 2 * p.ksplit CTAs (launch_conv_tma2).
-template <int MODE, bool ACT = false>
+// EPI (dgrad): 0 plain store, 1 = ACT, 2 = UNPOOL (scatter through a 2x2 max-pool's argmax, see
+// Tma2Params::up_idx)
+template <int MODE, int EPI = 0>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_tma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ Tma2Params p) {
   using Cfg = ModeCfg<MODE>;
+  constexpr bool ACT = EPI == 1;
+  constexpr bool UNPOOL = EPI == 2;
   constexpr bool A_MN = (MODE == kWgrad);
   constexpr bool B_MN = (MODE != kDgrad);
   const int kS = p.stages;
@@ -741,6 +830,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       const bool use_act = ACT && vec_store && act_delta != 0 && S == 1;
       float4 act_cur[8], act_next[8];
       if (use_act) load_act_rows(act_cur, rp, ok_mask, 0, lane, act_delta);
+      int64_t ub[8];
+      uint32_t uf = 0;
+      if (UNPOOL && S == 1) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          int fl = 0;
+          ub[r] = 0;
+          if ((ok_mask >> r) & 1u) unpool_row(p, m_base + (lane >> 3) + 4 * r, ub[r], fl);
+          uf |= (uint32_t)fl << (2 * r);
+        }
+      }
       mbar_wait(tmem_full_bar(acc), ((uint32_t)it >> 1) & 1u);
       trace_at(p, tr && warp == kWarpEpi0 && it < 4, 6 + it);
       tc_fence_after();
@@ -769,9 +869,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
         if (use_act && cb + 32 < tc.bn) load_act_rows(act_next, rp, ok_mask, cb + 32, lane, act_delta);
+        UnpoolSrc usrc[8];
+        if (UNPOOL) load_unpool_rows(usrc, p, m_base, ok_mask, tc.n0 + cb, lane);
         tmem_ld_wait();
         if (MODE == kFprop && p.leaky) leaky_block(v, p.alpha);
-        if (vec_store) {
+        if (UNPOOL) {
+          store_block_rows_unpool(epi_tile, v, lane, p, ub, uf, ok_mask, tc.n0 + cb, usrc);
+        } else if (vec_store) {
           store_block_rows(epi_tile, v, lane, rp, ok_mask, cb, use_act, act_cur, p.alpha,
                            p.round_out);
 #pragma unroll
@@ -810,6 +914,56 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int64_t act_delta =
         (ACT && p.act) ? reinterpret_cast<const char*>(p.act) - reinterpret_cast<const char*>(p.C) : 0;
     const int total = nblk * rows_per * 8;
+    if (UNPOOL) {
+      // three items per thread and pass: every global load (argmax, pool output) and every
+      // distributed-shared-memory read of a pass is in flight before the first store
+      constexpr int U = 3;
+      for (int idx0 = t; idx0 < total; idx0 += U * kThreads) {
+        UnpoolSrc src[U];
+        int64_t base[U];
+        int flags[U];
+        uint32_t off[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int idx = idx0 + u * kThreads;
+          const int chunk = idx & 7;
+          const int r = (idx >> 3) % rows_per;
+          const int cbk = (idx >> 3) / rows_per;
+          const int row = row0 + r;
+          const int m = m_half + row;
+          ok[u] = idx < total && m < p.M;
+          const int rl = row & 31;
+          off[u] = (uint32_t)((row >> 5) * nblk + cbk) * 4096u +
+                   (uint32_t)(rl * 8 + (chunk ^ (rl & 7))) * 16u;
+          base[u] = 0;
+          flags[u] = 0;
+          if (ok[u]) {
+            const int col = tc.n0 + cbk * 32 + chunk * 4;
+            unpool_row(p, m, base[u], flags[u]);
+            base[u] += col;
+            src[u] = unpool_load4(p, (int64_t)m * p.ldc + col);
+          }
+        }
+        float4 acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[u]) {
+            for (int q = 0; q < S; ++q) {
+              const float4 v = ld_dsmem_f4(mapa(tiles + off[u], (uint32_t)(2 * q) + rank));
+              acc[u].x += v.x;
+              acc[u].y += v.y;
+              acc[u].z += v.z;
+              acc[u].w += v.w;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (ok[u]) unpool_store4(p, acc[u], src[u], base[u], flags[u]);
+      }
+    } else
     for (int idx = t; idx < total; idx += kThreads) {
       const int chunk = idx & 7;
       const int r = (idx >> 3) % rows_per;
@@ -1550,6 +1704,12 @@ static int launch_conv_tma2_one(int mode, const IgemmParams& ip, cudaStream_t st
   p.leaky = (mode == kFprop) ? ip.leaky : 0;
   p.alpha = ip.leaky_alpha;
   p.act = (mode == kDgrad) ? ip.act : nullptr;
+  if (mode == kDgrad && ip.up_idx) {
+    p.up_idx = ip.up_idx;
+    p.up_y = ip.up_y;
+    p.up_H = ip.up_H;
+    p.up_W = ip.up_W;
+  }
   p.round_out = g_round_tf32_outputs;
   p.split3 = (mode == kFprop) ? ip.split3 : 0;
   const int up_h = (g.OH - 1) * g.sy + 1 - g.H - g.pad_t, up_w = (g.OW - 1) * g.sx + 1 - g.W - g.pad_l;
@@ -1683,13 +1843,15 @@ static int launch_conv_tma2_one(int mode, const IgemmParams& ip, cudaStream_t st
                        cudaGetErrorString(cudaGetLastError()));                                 \
   } while (0)
   if (mode == kFprop)
-    SP_TMA2_LAUNCH(kFprop, false);
+    SP_TMA2_LAUNCH(kFprop, 0);
+  else if (mode == kDgrad && p.up_idx)
+    SP_TMA2_LAUNCH(kDgrad, 2);
   else if (mode == kDgrad && p.act)
-    SP_TMA2_LAUNCH(kDgrad, true);
+    SP_TMA2_LAUNCH(kDgrad, 1);
   else if (mode == kDgrad)
-    SP_TMA2_LAUNCH(kDgrad, false);
+    SP_TMA2_LAUNCH(kDgrad, 0);
   else
-    SP_TMA2_LAUNCH(kWgrad, false);
+    SP_TMA2_LAUNCH(kWgrad, 0);
 #undef SP_TMA2_LAUNCH
   return 0;
 }

@@ -36,6 +36,12 @@ struct IgemmParams {
   // 1 : leaky_alpha) with `act` laid out like the output -- the gradient of leaky_relu applied
   // to the data gradient as it is stored
   const float* act;
+  // kDgrad on the 2-SM TMA kernel: scatter the data gradient through the argmax of the 2x2 /
+  // stride-2 max-pool that produced the conv's input, times leaky_relu's slope (sign of the pool
+  // output up_y): C is then the FULL-resolution gradient [N, up_H, up_W, ldc] (conv_tma2.cu)
+  const uint8_t* up_idx;
+  const float* up_y;
+  int up_H, up_W;
   // conv fprop with SP_PRECISION_TF32_SPLIT: operands are (r, l) TF32 split pairs interleaved
   // per 32 channels and g.C counts both parts (tf32.cu); only the 2-SM TMA kernel takes it
   int split3;

@@ -142,6 +142,18 @@ int sp_memcpy_d2h(void* host_dst, const void* src, size_t bytes, sp_stream_t str
   return 0;
 }
 
+// into PAGE-LOCKED host memory, without waiting: pair with sp_event_record / sp_event_synchronize
+int sp_memcpy_d2h_async(void* pinned_dst, const void* src, size_t bytes, sp_stream_t stream) {
+  if (bytes != 0)
+    SP_CHECK_CUDA(
+        cudaMemcpyAsync(pinned_dst, src, bytes, cudaMemcpyDeviceToHost, sp::as_stream(stream)));
+  return 0;
+}
+int sp_event_synchronize(void* event) {
+  SP_CHECK_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(event)));
+  return 0;
+}
+
 int sp_memcpy_d2d(void* dst, const void* src, size_t bytes, sp_stream_t stream) {
   if (bytes == 0) return 0;
   SP_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, sp::as_stream(stream)));

@@ -81,7 +81,7 @@ class _Record:
                  "param_arrays", "shadow_refs", "graph_f", "kernels_f", "root", "epoch",
                  "graph_b", "kernels_b", "grads", "b_epoch", "side", "graph_u", "kernels_u",
                  "u_vars", "u_opt", "u_hyper", "u_outs", "u_refreshed", "user_inputs", "keep",
-                 "exchange_bucket", "ready_event", "b_requested", "spec_streak", "pending_b")
+                 "exchange_bucket", "ready_event", "b_requested", "spec_streak", "pending_b", "mirror", "pending_f")
 
     def __init__(self):
         self.graph_b = self.graph_u = None
@@ -89,9 +89,11 @@ class _Record:
         self.b_epoch = -1
         self.keep = []
         self.ready_event = None
+        self.mirror = None
         self.b_requested = False
         self.spec_streak = 0
         self.pending_b = ()
+        self.pending_f = ()
 
 
 class _RootState:
@@ -228,6 +230,16 @@ class _Abort(Exception):
     pass
 
 
+_MIRROR_BYTES = 64
+_MIRROR_SLOTS = 16
+
+
+def _mirror_ring():
+    """(page-locked [slots, bytes] uint8 array, per-slot generation counters), or None."""
+    buf = A.pinned_empty((_MIRROR_SLOTS, _MIRROR_BYTES), np.uint8)
+    return None if buf is None else (buf, [0] * _MIRROR_SLOTS)
+
+
 def _shadows_intact(rec) -> bool:
     """The TF32 shadows (rounded / split copies) of the parameters that the recorded kernels
     read must still be the arrays' current shadows (U refreshes exactly those)."""
@@ -330,6 +342,19 @@ def _record_forward(root, state, key):
             ph.arguments = [uv]
     if not isinstance(rec.root, Variable) or rec.root._array._thunk is not None:
         raise _Abort("root value is not a launched Variable")
+    # Arrays of the recorded tape whose kernel was NOT launched (a consumer fused them away: the
+    # first conv's full-resolution output when conv + leaky_relu + pool ran as one kernel) are
+    # launched on demand by whoever reads them -- eagerly, after a replay (the deferred input
+    # gradient needs that tensor).  Re-armed at every replay: a buffer materialised for one
+    # step's inputs must not be mistaken for the next step's.
+    from . import core
+
+    pending = []
+    for node in core._tape_order(rec.root):
+        arr = node._array
+        if type(arr) is DeviceArray and arr._ptr is None and arr._thunk is not None:
+            pending.append((arr, arr._thunk, arr._tag))
+    rec.pending_f = pending
     rec.shadow_refs = _snapshot_shadows(rec.param_arrays)
     state.records[key] = rec
     state.n_records += 1
@@ -368,6 +393,11 @@ def _replay_forward(rec):
     user_values = [ph.arguments[0] for ph in rec.placeholders]
     for dst, v in zip(rec.static_inputs, user_values):
         _feed(dst, v)
+    for arr, thunk, tag_ in rec.pending_f:
+        if arr._thunk is None:  # materialised after an earlier replay: pending again
+            arr._buf = arr._ptr = None
+            arr._thunk, arr._tag = thunk, tag_
+            arr._tf32 = arr._shadow = None
     rec.graph_f.replay()
     _abi.counter.launches += rec.kernels_f
     stats["replays_f"] += 1
@@ -383,8 +413,22 @@ def _replay_forward(rec):
     # for this event on a copy stream, not for whatever is enqueued behind it
     if rec.ready_event is None:
         rec.ready_event = A.new_event()
+    mirror = None
+    if 0 < value.nbytes <= _MIRROR_BYTES:
+        # a small result (the loss): also mirrored into page-locked host memory, so that the
+        # read costs an event wait only.  A ring: results may be read a few steps later.
+        ring = rec.mirror
+        if ring is None:
+            ring = rec.mirror = _mirror_ring()
+        if ring is not None:
+            buf, gens = ring
+            slot = rec.epoch % _MIRROR_SLOTS
+            gens[slot] += 1
+            view = buf[slot]
+            F.sp_memcpy_d2h_async(view.ctypes.data, value._ptr, value.nbytes, A.stream())
+            mirror = (view, gens, slot, gens[slot])
     F.sp_event_record(rec.ready_event, A.stream())
-    out._ready = rec.ready_event
+    out._ready = rec.ready_event if mirror is None else (rec.ready_event,) + mirror
     if rec.graph_b is not None and speculate_backward:
         # The loop has asked for the gradients of every recent result of this recording: start
         # the backward pass now, behind the forward pass, instead of after the host has read

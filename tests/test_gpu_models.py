@@ -453,6 +453,65 @@ def test_leaf_gradient_read_after_the_update_sees_the_old_weights(optimiser):
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x1"])
+@pytest.mark.parametrize("batch,image,widths,pads", [
+    (32, 32, (32, 128, 128), ("SAME", "VALID", "VALID")),    # README CNN: split-K cluster epilogue
+    (140, 32, (32, 64, 32), ("SAME", "VALID", "VALID")),     # too few k stages to split: direct epilogue
+    (96, 30, (32, 64, 64), ("SAME", "VALID", "SAME")),       # 13x13 -> 7x7 pool: clipped windows
+])
+def test_conv_data_gradient_scattered_through_the_pool_is_bit_identical(batch, image, widths, pads,
+                                                                        precision):
+    """conv -> leaky_relu -> maxpool2d(2, 2, stride 2) -> conv: the second conv's data gradient
+    is scattered through the pool's argmax and multiplied by leaky_relu's slope in the epilogue
+    of the conv kernel (sp_conv2d_dgrad_unpool_leaky) -- no pooled gradient tensor, no pool
+    backward launch -- and every gradient equals the separate launches bit for bit."""
+    from smallpebble_b200 import _abi, core
+
+    rng = np.random.default_rng(batch + image)
+    x = rng.random((batch, image, image, 3)) - 0.5
+    ws, cin = [], 3
+    for wd in widths:
+        ws.append((rng.random((3, 3, cin, wd)) - 0.5) * 2.0 / np.sqrt(9 * cin))
+        cin = wd
+    sp.set_precision(precision)
+    calls = []
+    orig = _abi.f.sp_conv2d_dgrad_unpool_leaky
+
+    def spy(*args):
+        calls.append(1)
+        return orig(*args)
+
+    def run():
+        xv = sp.Variable(x)
+        wv = [sp.learnable(sp.Variable(w)) for w in ws]
+        h = xv
+        acts = []
+        for i, (w, pad) in enumerate(zip(wv, pads)):
+            h = sp.conv2d(h, w, pad)
+            acts.append(h)
+            if i < len(wv) - 1:
+                h = sp.maxpool2d(sp.leaky_relu(h, 0.1), 2, 2, strides=[2, 2])
+        gy = np.random.default_rng(5).random(h.shape) - 0.5
+        g = sp.get_gradients(sp.mul(h, sp.Variable(gy)))
+        return [np.asarray(g[w]) for w in wv] + [np.asarray(g[acts[1]]), np.asarray(g[xv])]
+
+    _abi.f.sp_conv2d_dgrad_unpool_leaky = spy
+    default = core._fuse_dgrad_unpool  # (off: measured slower inside the backward graph)
+    try:
+        core._fuse_dgrad_unpool = True
+        fused = run()
+        n_fused = len(calls)
+        core._fuse_dgrad_unpool = False
+        plain = run()
+    finally:
+        _abi.f.sp_conv2d_dgrad_unpool_leaky = orig
+        core._fuse_dgrad_unpool = default
+        sp.set_precision("tf32")
+    assert n_fused == 1 and len(calls) == 1  # the third conv's data gradient; never when off
+    for a, b in zip(fused, plain):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x1"])
 @pytest.mark.parametrize("shape,k,padding", [((16, 32, 32, 3), 32, "SAME"), ((5, 14, 18, 3), 16, "VALID"),
                                              ((3, 40, 36, 3), 32, "SAME"), ((2, 10, 10, 3), 64, "VALID")])
 def test_first_layer_conv_leaky_pool_in_one_kernel_is_bit_identical(shape, k, padding, precision):
