@@ -250,6 +250,14 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
 int sp_gemm_bias(int64_t M, int64_t N, int64_t K, const float* A, const float* B,
                  const float* bias, float* C, int precision, sp_stream_t stream);
 
+/* leaky_relu(A . B + bias, alpha): a hidden sp.linearlayer with its activation (sp.py:630-635,
+ * 231-236; README.md:126-131) -- one launch for small products (K split over a thread-block
+ * cluster on the CUDA cores, exact fp32), else sp_gemm_bias + the in-place activation; the same
+ * bits as the separate calls. */
+int sp_gemm_bias_leaky(int64_t M, int64_t N, int64_t K, const float* A, const float* B,
+                       const float* bias, float* C, int precision, float alpha,
+                       sp_stream_t stream);
+
 /* The classifier head of the README models in one call (README.md:132-137, 277-281;
  * sp.py:239-247, 100-108, 612-621): logits = A . B + bias, probs = softmax(logits), loss = summed
  * cross entropy against labels, dlogits = probs - onehot with its column sums (the gradients

@@ -83,6 +83,7 @@ SIGNATURES = {
     "sp_stream_wait_event": (C.c_int, [vp, vp]),
     "sp_softmax_xent_bwd_colsum": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp]),
     "sp_gemm_bias": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, C.c_int, vp]),
+    "sp_gemm_bias_leaky": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, C.c_int, f32, vp]),
     "sp_gemm_bias_softmax_xent": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
     "sp_maxpool2d_fwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [vp]),
     "sp_maxpool2d_bwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [vp]),

@@ -465,12 +465,13 @@ class DeviceArray:
         out = np.empty(self.shape, self.dtype)
         ready = self._ready
         if type(ready) is tuple:
-            # (event, host mirror, slot generations, slot, generation): the producer also copied
-            # the contents into page-locked host memory before the event -- one wait, no copy
-            # of our own -- unless the ring has come round to this slot since
-            ready, mirror, gens, slot, gen = ready
+            # (ready event, mirror event, host mirror, slot generations, slot, generation): the
+            # producer also copied the contents into page-locked host memory (done at the
+            # mirror event) -- one wait, no copy of our own -- unless the ring has come round
+            # to this slot since
+            ready, landed, mirror, gens, slot, gen = ready
             if gens[slot] == gen:
-                F.sp_event_synchronize(ready)
+                F.sp_event_synchronize(landed)
                 out.reshape(-1).view(np.uint8)[:] = mirror[:out.nbytes]
                 _counters["d2h_bytes"] += out.nbytes
                 return out

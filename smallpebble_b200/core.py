@@ -513,15 +513,17 @@ def add(a: Variable, b: Variable) -> Variable:
         # the left operand is a layer matmul that has not been launched and the right one a
         # row vector: matmul + bias in one call (sp.py:630-635); the matmul node's own value
         # stays deferred unless somebody reads it
-        _, av, bv, rows, n, k = tag
-        bias, fwd_prec = b.array, _fwd_native_precision()
+        av, bv, rows, n, k = tag[1:6]
+        bias = b.array
+        fwd_prec = tag[6] if len(tag) > 6 else _fwd_native_precision()
 
         def launch_gemm_bias(out):
             F.sp_gemm_bias(rows, n, k, av.ptr, bv.ptr, bias.ptr, out.ptr, fwd_prec, A.stream())
 
-        if _fuse_head and n <= 16 and rows * n:
-            # the 10-way classifier: still not launched -- softmax + cross_entropy may take the
-            # whole head into one kernel (core.cross_entropy); anything else launches it here
+        if (_fuse_head and n <= 16 and rows * n) or (_fuse_linear and n > 16 and rows * n):
+            # still not launched: softmax + cross_entropy may take the whole classifier head
+            # into one kernel (core.cross_entropy), a leaky_relu the hidden layer with its
+            # activation (core.leaky_relu); anything else launches it here
             value = DeviceArray.deferred(sa, launch_gemm_bias,
                                          ("gemm_bias", av, bv, bias, rows, n, k, fwd_prec), rows * n)
         else:
@@ -629,6 +631,11 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
             # the input is a conv2d that has not been launched: the activation is applied in
             # the conv kernel's epilogue and the pre-activation tensor is never written
             tag[1](out, alpha)
+        elif tag is not None and tag[0] == "gemm_bias" and alpha > 0:
+            # ... or a linear layer `matmul(x, w) + b` that has not been launched: one call
+            _, gav, gbv, gbias, m, n, k, gprec = tag
+            F.sp_gemm_bias_leaky(m, n, k, gav.ptr, gbv.ptr, gbias.ptr, out.ptr, gprec, alpha,
+                                 A.stream())
         else:
             F.sp_leaky_relu_fwd(x.ptr, out.ptr, x.size, alpha, A.stream())
 
@@ -954,10 +961,19 @@ def matmul(a: Variable, b: Variable) -> Variable:
                 ("matmul", av, bv, rows, N, K))
         elif _compensate and N > 16 and rows and K and 2.0 * rows * N * K < _X3_MIN_FLOP:
             # a small product (the README MLP's layers: 31 MFLOP): exact fp32 on CUDA cores,
-            # K split over the chip -- one launch pair instead of operand splits plus a
-            # tensor-core kernel that would run its 3K-long loop on two CTAs
-            value = _gemm(0, 0, rows, N, K, av, K, 0, bv, N, 0, 1, a_batch + (M, N),
-                          _abi.PRECISION_FP32)
+            # K split over the CTAs of a cluster -- one launch instead of operand splits plus a
+            # tensor-core kernel that would run its 3K-long loop on two CTAs.  Deferred like
+            # the classifier's: `+ bias` and a following leaky_relu join the same launch
+            # (core.add, core.leaky_relu: sp_gemm_bias_leaky)
+            if _fuse_linear and len(a_batch) == 0:
+                value = DeviceArray.deferred(
+                    (M, N),
+                    lambda out: F.sp_gemm(0, 0, rows, N, K, av.ptr, K, 0, bv.ptr, N, 0, out.ptr, N,
+                                          rows * N, 1, _abi.PRECISION_FP32, A.stream()),
+                    ("matmul", av, bv, rows, N, K, _abi.PRECISION_FP32))
+            else:
+                value = _gemm(0, 0, rows, N, K, av, K, 0, bv, N, 0, 1, a_batch + (M, N),
+                              _abi.PRECISION_FP32)
         elif _compensate and N > 16 and rows and K:
             # error-compensated forward product (3xTF32) as ONE tensor-core GEMM over a
             # contraction axis of 3K: [a_r | a_l | a_r] . [b_r ; b_r ; b_l]  (csrc/tf32.cu)
@@ -1183,6 +1199,7 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
 _pooled_wgrad = os.environ.get("SP_POOLED_WGRAD", "1") != "0"
 _fuse_conv_pool = os.environ.get("SP_FUSE_CONV_POOL", "1") != "0"  # conv + leaky + pool, one kernel
 _fuse_head = os.environ.get("SP_FUSE_HEAD", "1") != "0"  # matmul + bias + softmax + cross_entropy
+_fuse_linear = os.environ.get("SP_FUSE_LINEAR", "1") != "0"  # small matmul + bias + leaky_relu
 # conv data gradient scattered through the following pool / leaky_relu backward in the conv
 # kernel's epilogue (sp_conv2d_dgrad_unpool_leaky).  OFF by default: alone the fused kernel beats
 # the two launches (15.1 vs 18.2 us on the README CNN's conv3), but inside the backward graph the

@@ -31,7 +31,8 @@ float* scratch_for_current_device();
 // arrival counters of single-launch "last block finishes the job" kernels.
 //   [0, 24)  fused Adam: per-tensor arrivals          [32], [33] grid barrier (count, generation)
 //   [40]     classifier head: arrivals of the skinny GEMM's row blocks (gemm_skinny.cu)
-constexpr int kSyncWords = 64;
+//   [64, 192) fused split-K GEMM: arrivals per output tile (igemm_simt.cu)
+constexpr int kSyncWords = 256;
 unsigned int* sync_words_for_current_device();
 
 inline cudaStream_t as_stream(sp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -177,6 +177,40 @@ int sp_debug_tma2_trace(void* device_buffer) {
   return 0;
 }
 
+}  // extern "C"
+
+namespace {
+// Small dense products on the CUDA cores (exact fp32): a few 64 x 64 output tiles with a
+// contraction axis of up to 4096 run as ONE launch whose K axis is split over several CTAs per
+// tile (igemm_simt.cu: gemm_simt_splitk_fused_kernel; the CTA that arrives last adds the
+// partial tiles in slice order, then bias and leaky_relu) instead of a split-K pass plus a
+// reduction launch (plus bias and activation launches): the hidden layers of the README MLP
+// (200 x 784 x 100, README.md:122-137).  Fills in the split and its scratch.
+bool cluster_gemm_plan(sp::IgemmParams& p, int* S) {
+  if (p.batch > 1 || p.k_splits > 1 || p.ldc != p.N || sp::g_umma_policy == 1) return false;
+  const int sms = sp::device_info().sm_count > 0 ? sp::device_info().sm_count : 148;
+  const int64_t tiles = ((p.M + 63) / 64) * ((p.N + 63) / 64);
+  if (tiles * 2 > sms || tiles > 128 || p.K < 64 || p.K > 4096) return false;
+  // measured (scripts/linear_probe.py): every slice costs the last CTA ~0.5 us and the hand-over
+  // (fence, counter) ~2 us, a k-tile ~0.25 us: slices of >= 6 k-tiles, at most 8 of them
+  int64_t s = std::min<int64_t>(8, p.K / 96);
+  s = std::min<int64_t>(s, (2 * sms) / tiles);            // ~2 CTAs per SM at most
+  s = std::min<int64_t>(s, (int64_t)(sp::kScratchFloats / 2) / (p.M * p.N));
+  if (s < 1) s = 1;
+  *S = (int)s;
+  if (s > 1) {
+    float* scratch = sp::scratch_for_current_device();
+    unsigned int* words = sp::sync_words_for_current_device();
+    if (!scratch || !words) return false;
+    p.splitk_part = scratch + sp::kScratchFloats / 2;
+    p.tail_counter = words + 64;
+  }
+  return true;
+}
+}  // namespace
+
+extern "C" {
+
 // C[M, N] = A[M, K] . B[K, N] + bias[N] (row-major, dense): the linear layer of sp.py:630-635,
 // `add(matmul(x, w), b)`, in one call.  N <= 16 with a long K runs as ONE kernel (skinny rows
 // kernel, bias added after the complete sum: bit-identical to matmul followed by add);
@@ -207,10 +241,58 @@ int sp_gemm_bias(int64_t M, int64_t N, int64_t K, const float* A, const float* B
       SP_CHECK_LAUNCH("gemm_bias(skinny)");
       return 0;
     }
+    int S = 1;
+    if (!sp::use_umma(sp::kGemm, p, precision) && cluster_gemm_plan(p, &S)) {
+      p.cluster_k = S;  // bias added after the complete sum: the bits of a separate add
+      if (int rc = sp::launch_igemm_simt_cluster(p, sp::as_stream(stream))) return rc;
+      SP_CHECK_LAUNCH("gemm_bias(cluster)");
+      return 0;
+    }
   }
   if (int rc = sp_gemm(0, 0, M, N, K, A, K, 0, B, N, 0, C, N, M * N, 1, precision, stream)) return rc;
   const int64_t shape[2] = {M, N}, sc[2] = {N, 1}, sb[2] = {0, 1};
   return sp_ewise_binary(SP_BINARY_ADD, C, sc, bias, sb, C, 2, shape, stream);
+}
+
+// leaky_relu(A . B + bias, alpha): a hidden linear layer of the README MLP with its activation
+// (sp.py:630-635, 231-236) -- one launch when the cluster kernel above takes the product,
+// otherwise sp_gemm_bias followed by the in-place activation.  Bit-identical either way.
+int sp_gemm_bias_leaky(int64_t M, int64_t N, int64_t K, const float* A, const float* B,
+                       const float* bias, float* C, int precision, float alpha,
+                       sp_stream_t stream) {
+  SP_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative extent");
+  SP_REQUIRE(precision == SP_PRECISION_FP32 || precision == SP_PRECISION_TF32 ||
+                 precision == SP_PRECISION_TF32X3, "bad precision");
+  if (M == 0 || N == 0) return 0;
+  if (K > 0) {
+    sp::IgemmParams p = sp::base_params();
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.A = A;
+    p.B = B;
+    p.C = C;
+    p.ldc = N;
+    p.a_rs = K;
+    p.a_cs = 1;
+    p.b_rs = N;
+    p.b_cs = 1;
+    p.bias = bias;
+    p.leaky = 1;
+    p.leaky_alpha = alpha;
+    int S = 1;
+    if (!sp::use_umma(sp::kGemm, p, precision) &&
+        !(sp::g_umma_policy != 1 && sp::gemm_skinny_supported(p)) && cluster_gemm_plan(p, &S)) {
+      p.cluster_k = S;
+      if (int rc = sp::launch_igemm_simt_cluster(p, sp::as_stream(stream))) return rc;
+      SP_CHECK_LAUNCH("gemm_bias_leaky(cluster)");
+      return 0;
+    }
+  }
+  if (int rc = sp_gemm_bias(M, N, K, A, B, bias, C, precision, stream)) return rc;
+  if (int rc = sp::launch_leaky_fwd_inplace(C, M * N, alpha, sp::as_stream(stream))) return rc;
+  SP_CHECK_LAUNCH("gemm_bias_leaky(leaky)");
+  return 0;
 }
 
 // The classifier head in one call: logits = A . B + bias, probs = softmax(logits), loss = the
@@ -375,6 +457,15 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   // CUDA-core kernel.  A long inner dimension with only a few output tiles (the 10-way
   // classifier: 128 x 10 x 1152) would leave the chip idle: split K over CTAs into the
   // library scratch and sum the partial tiles in a fixed order.
+  {
+    int S = 1;
+    if (cluster_gemm_plan(p, &S) && S > 1) {  // one launch: K split over a cluster
+      p.cluster_k = S;
+      if (int rc = sp::launch_igemm_simt_cluster(p, st)) return rc;
+      SP_CHECK_LAUNCH("gemm(cluster split-K)");
+      return 0;
+    }
+  }
   const int sms = sp::device_info().sm_count > 0 ? sp::device_info().sm_count : 148;
   const int64_t tiles = ((M + 63) / 64) * ((N + 63) / 64);
   if (batch == 1 && ldc == N && tiles * 2 <= sms && K >= 256) {

@@ -54,10 +54,13 @@ struct IgemmParams {
   int k_splits;
   int64_t k_chunk;  // multiple of the kernel's K tile
   int64_t split_stride_c;
-  // CUDA-core GEMM only: K split over the CTAs of a thread-block cluster (1, 1, cluster_k <= 8),
-  // partial tiles added through distributed shared memory in rank order, then `bias` (if any)
-  // and the leaky epilogue: a small linear layer in ONE launch (launch_igemm_simt_cluster)
+  // CUDA-core GEMM only (launch_igemm_simt_cluster): K split over cluster_k CTAs per output tile
+  // in ONE launch -- partial tiles in splitk_part ([cluster_k][M][N] floats), the CTA that
+  // arrives last at the tile's word of tail_counter adds them in slice order, then `bias` (if
+  // any) and the leaky epilogue: a small linear layer without reduction / bias / activation
+  // launches
   int cluster_k;
+  float* splitk_part;
   // skinny rows kernel only (gemm_skinny.cu): C are the logits of a classifier whose
   // softmax + cross_entropy (sp.py:612-621) the LAST block to finish computes in the same
   // launch -- probabilities, the summed loss, p - onehot and its column sums, bit-identical to
@@ -73,7 +76,7 @@ struct IgemmParams {
 };
 
 int launch_igemm_simt(int mode, const IgemmParams& p, cudaStream_t stream);
-// kGemm with p.cluster_k > 1 (K split over a cluster, bias / leaky epilogue)
+// kGemm with K split over p.cluster_k CTAs per tile, last arrival reduces; bias / leaky epilogue
 int launch_igemm_simt_cluster(const IgemmParams& p, cudaStream_t stream);
 int launch_igemm_umma(int mode, const IgemmParams& p, cudaStream_t stream);
 // true when the tcgen05 kernel supports this problem (shape / alignment constraints)

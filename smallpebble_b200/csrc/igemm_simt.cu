@@ -165,36 +165,22 @@ __global__ void __launch_bounds__(kThreads) igemm_simt_kernel(const __grid_const
 
 // ---- small dense layers in one launch: y = [leaky](A . B [+ bias]) -------------------------
 // The README MLP's layers (200 x 784 x 100: 31 MFLOP) are far below anything a tile kernel with
-// a serial K loop can spread over the chip: 8 output tiles.  Here the K axis is split over the
-// CTAs of a cluster (1, 1, S <= 8): every CTA runs the loop above on its slice, parks its
-// 64 x 64 partial tile in shared memory, and after one cluster barrier adds the S partials of
-// its own 64 / S rows in RANK ORDER through distributed shared memory (fixed order: results do
-// not depend on timing), adds the bias, applies leaky_relu and stores -- no workspace, no
-// reduction launch, no separate bias / activation launches.
-__device__ __forceinline__ uint32_t cluster_rank_z() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ float ld_cluster_f32(const float* local, uint32_t rank) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(r) : "memory");
-  return v;
-}
-
+// a serial K loop can spread over the chip: 8 output tiles, and their run time is the number of
+// DEPENDENT global round trips.  Here the K axis is split over gridDim.z CTAs per tile (slices
+// of a few 16-deep k-tiles whose loads are all issued up front), every CTA parks its partial
+// tile in the library scratch, and the CTA that arrives LAST at the tile's counter adds the
+// partials in slice order (fixed order: the result does not depend on timing), adds the bias,
+// applies leaky_relu and stores -- no reduction launch, no bias / activation launches.
 template <bool A_KFAST, bool B_KFAST>
-__global__ void __launch_bounds__(kThreads) gemm_simt_cluster_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(kThreads) gemm_simt_splitk_fused_kernel(const __grid_constant__ IgemmParams p) {
   pdl_entry();
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
-  __shared__ __align__(16) float Ps[BM][BN + 1];  // this CTA's partial tile
+  __shared__ int is_last;
 
   const int tid = threadIdx.x;
-  const int S = p.cluster_k;
-  const int rank = (int)cluster_rank_z();
+  const int S = (int)gridDim.z;
+  const int rank = (int)blockIdx.z;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int64_t n0 = (int64_t)blockIdx.y * BN;
   const float* A = p.A;
@@ -211,97 +197,153 @@ __global__ void __launch_bounds__(kThreads) gemm_simt_cluster_kernel(const __gri
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const int ty = tid >> 4, tx = tid & 15;
 
-  for (int64_t kb = k_begin; kb < k_end; kb += BK) {
-    float ra[4], rb[4];
+  constexpr int kAhead = 4;
+  for (int64_t kc = k_begin; kc < k_end; kc += kAhead * BK) {
+    float ra[kAhead][4], rb[kAhead][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int am, ak, bk, bn;
-      if (A_KFAST) {
-        ak = tid & 15;
-        am = (tid >> 4) + 16 * i;
-      } else {
-        am = tid & 63;
-        ak = (tid >> 6) + 4 * i;
+    for (int u = 0; u < kAhead; ++u) {
+      const int64_t kb = kc + u * BK;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int am, ak, bk, bn;
+        if (A_KFAST) {
+          ak = tid & 15;
+          am = (tid >> 4) + 16 * i;
+        } else {
+          am = tid & 63;
+          ak = (tid >> 6) + 4 * i;
+        }
+        if (B_KFAST) {
+          bk = tid & 15;
+          bn = (tid >> 4) + 16 * i;
+        } else {
+          bn = tid & 63;
+          bk = (tid >> 6) + 4 * i;
+        }
+        const int64_t gk_a = kb + ak, gk_b = kb + bk;
+        ra[u][i] = (gk_a < k_end) ? load_a<kGemm>(p, m0 + am, gk_a, A) : 0.f;
+        rb[u][i] = (gk_b < k_end) ? load_b<kGemm>(p, gk_b, n0 + bn, B) : 0.f;
       }
-      if (B_KFAST) {
-        bk = tid & 15;
-        bn = (tid >> 4) + 16 * i;
-      } else {
-        bn = tid & 63;
-        bk = (tid >> 6) + 4 * i;
+    }
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      if (kc + u * BK >= k_end) break;  // uniform over the block
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (A_KFAST)
+          As[tid & 15][(tid >> 4) + 16 * i] = ra[u][i];
+        else
+          As[(tid >> 6) + 4 * i][tid & 63] = ra[u][i];
+        if (B_KFAST)
+          Bs[tid & 15][(tid >> 4) + 16 * i] = rb[u][i];
+        else
+          Bs[(tid >> 6) + 4 * i][tid & 63] = rb[u][i];
       }
-      const int64_t gk_a = kb + ak, gk_b = kb + bk;
-      ra[i] = (gk_a < k_end) ? load_a<kGemm>(p, m0 + am, gk_a, A) : 0.f;
-      rb[i] = (gk_b < k_end) ? load_b<kGemm>(p, gk_b, n0 + bn, B) : 0.f;
-    }
-    __syncthreads();
+      __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (A_KFAST)
-        As[tid & 15][(tid >> 4) + 16 * i] = ra[i];
-      else
-        As[(tid >> 6) + 4 * i][tid & 63] = ra[i];
-      if (B_KFAST)
-        Bs[tid & 15][(tid >> 4) + 16 * i] = rb[i];
-      else
-        Bs[(tid >> 6) + 4 * i][tid & 63] = rb[i];
-    }
-    __syncthreads();
+      for (int k = 0; k < BK; ++k) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
     }
   }
+
+  if (S > 1) {
+    // park the partial tile ([slice][M][N], like C), then see who is last at this tile
+    float* part = p.splitk_part + (int64_t)rank * p.M * p.N;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + ty * 4 + i;
+      if (m >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) Ps[ty * 4 + i][tx * 4 + j] = acc[i][j];
-  __syncthreads();
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  // rows [rank * 64 / S, (rank + 1) * 64 / S) of the tile are this CTA's to finish
-  const int r0 = BM * rank / S, r1 = BM * (rank + 1) / S;
-  for (int idx = tid; idx < (r1 - r0) * BN; idx += kThreads) {
-    const int r = r0 + idx / BN, c = idx % BN;
-    const int64_t m = m0 + r, n = n0 + c;
-    if (m >= p.M || n >= p.N) continue;
-    float v = 0.f;
-    for (int q = 0; q < S; ++q) v += ld_cluster_f32(&Ps[r][c], (uint32_t)q);
-    if (p.bias) v += p.bias[n];
-    if (p.leaky) v = v > 0.f ? v : p.leaky_alpha * v;
-    p.C[m * p.ldc + n] = v;
+      for (int j = 0; j < 4; ++j) {
+        const int64_t n = n0 + tx * 4 + j;
+        if (n < p.N) __stcg(part + m * p.N + n, acc[i][j]);
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    unsigned int* counter = p.tail_counter + blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) {
+      const unsigned int prev = atomicAdd(counter, 1u);
+      is_last = prev == (unsigned int)S - 1;
+      if (is_last) *counter = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float sum[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sum[i][j] = 0.f;
+    // slice order, whoever arrived last; the loads of four slices are in flight together (a
+    // loop that adds slice by slice pays one L2 round trip per slice)
+    const int64_t mn = p.M * p.N;
+    const bool vec = (p.N & 3) == 0 && n0 + tx * 4 + 3 < p.N;
+    for (int q0 = 0; q0 < S; q0 += 4) {
+      float v[4][4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* pq = p.splitk_part + (int64_t)(q0 + u) * mn;
+        const bool on = q0 + u < S;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t m = m0 + ty * 4 + i;
+          if (on && m < p.M && vec) {
+            const float4 t4 = __ldcg(reinterpret_cast<const float4*>(pq + m * p.N + n0 + tx * 4));
+            v[u][i][0] = t4.x, v[u][i][1] = t4.y, v[u][i][2] = t4.z, v[u][i][3] = t4.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int64_t n = n0 + tx * 4 + j;
+              v[u][i][j] = (on && m < p.M && n < p.N) ? __ldcg(pq + m * p.N + n) : 0.f;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (q0 + u < S) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sum[i][j] += v[u][i][j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = sum[i][j];
   }
-  // nobody leaves while a peer may still read this CTA's partial tile
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[n];  // after the complete sum: the bits of a separate add
+      if (p.leaky) v = v > 0.f ? v : p.leaky_alpha * v;
+      p.C[m * p.ldc + n] = v;
+    }
+  }
 }
 
 template <bool AK, bool BK_>
-int launch_cluster(const IgemmParams& p, cudaStream_t st) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN),
-                     (unsigned)p.cluster_k);
-  cfg.blockDim = dim3(kThreads);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = (unsigned)p.cluster_k;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 2;
-  if (cudaLaunchKernelEx(&cfg, gemm_simt_cluster_kernel<AK, BK_>, p) != cudaSuccess)
-    return set_error(SP_ERR_DRIVER, "gemm_simt_cluster: launch failed: %s",
-                     cudaGetErrorString(cudaGetLastError()));
+int launch_splitk_fused(const IgemmParams& p, cudaStream_t st) {
+  const dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN),
+                  (unsigned)p.cluster_k);
+  sp::launch_pdl(gemm_simt_splitk_fused_kernel<AK, BK_>, grid, dim3(kThreads), 0, st, p);
   return 0;
 }
 
@@ -320,14 +362,16 @@ int launch(const IgemmParams& p, cudaStream_t st) {
 
 int launch_igemm_simt_cluster(const IgemmParams& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0) return 0;
-  if (p.cluster_k < 1 || p.cluster_k > 8 || p.batch > 1 || p.k_splits > 1)
-    return set_error(SP_ERR_INVALID_ARGUMENT, "gemm_simt_cluster: bad split");
+  if (p.cluster_k < 1 || p.cluster_k > 64 || p.batch > 1 || p.k_splits > 1)
+    return set_error(SP_ERR_INVALID_ARGUMENT, "gemm_simt_splitk_fused: bad split");
+  if (p.cluster_k > 1 && !(p.splitk_part && p.tail_counter))
+    return set_error(SP_ERR_WORKSPACE, "gemm_simt_splitk_fused: no scratch");
   if ((p.N + BN - 1) / BN > 65535) return set_error(SP_ERR_UNSUPPORTED, "igemm: N too large");
   const bool ak = (p.a_cs == 1), bk = (p.b_rs == 1 && p.b_cs != 1);
-  if (ak && bk) return launch_cluster<true, true>(p, st);
-  if (ak && !bk) return launch_cluster<true, false>(p, st);
-  if (!ak && bk) return launch_cluster<false, true>(p, st);
-  return launch_cluster<false, false>(p, st);
+  if (ak && bk) return launch_splitk_fused<true, true>(p, st);
+  if (ak && !bk) return launch_splitk_fused<true, false>(p, st);
+  if (!ak && bk) return launch_splitk_fused<false, true>(p, st);
+  return launch_splitk_fused<false, false>(p, st);
 }
 
 int launch_igemm_simt(int mode, const IgemmParams& p, cudaStream_t st) {

@@ -235,9 +235,12 @@ _MIRROR_SLOTS = 16
 
 
 def _mirror_ring():
-    """(page-locked [slots, bytes] uint8 array, per-slot generation counters), or None."""
+    """(page-locked [slots, bytes] uint8 array, per-slot generation counters, per-slot events),
+    or None."""
     buf = A.pinned_empty((_MIRROR_SLOTS, _MIRROR_BYTES), np.uint8)
-    return None if buf is None else (buf, [0] * _MIRROR_SLOTS)
+    if buf is None:
+        return None
+    return buf, [0] * _MIRROR_SLOTS, [A.new_event() for _ in range(_MIRROR_SLOTS)]
 
 
 def _shadows_intact(rec) -> bool:
@@ -413,22 +416,26 @@ def _replay_forward(rec):
     # for this event on a copy stream, not for whatever is enqueued behind it
     if rec.ready_event is None:
         rec.ready_event = A.new_event()
-    mirror = None
+    F.sp_event_record(rec.ready_event, A.stream())
+    out._ready = rec.ready_event
     if 0 < value.nbytes <= _MIRROR_BYTES:
-        # a small result (the loss): also mirrored into page-locked host memory, so that the
-        # read costs an event wait only.  A ring: results may be read a few steps later.
+        # a small result (the loss): also mirrored into page-locked host memory -- on the read
+        # stream, behind the event, so that the compute stream goes straight on with the
+        # backward pass -- and a host read costs one event wait instead of a copy of its own.
+        # A ring of slots: results may be read a few steps later.
         ring = rec.mirror
         if ring is None:
             ring = rec.mirror = _mirror_ring()
         if ring is not None:
-            buf, gens = ring
+            buf, gens, landed = ring
             slot = rec.epoch % _MIRROR_SLOTS
             gens[slot] += 1
             view = buf[slot]
-            F.sp_memcpy_d2h_async(view.ctypes.data, value._ptr, value.nbytes, A.stream())
-            mirror = (view, gens, slot, gens[slot])
-    F.sp_event_record(rec.ready_event, A.stream())
-    out._ready = rec.ready_event if mirror is None else (rec.ready_event,) + mirror
+            side = A._read_stream()
+            F.sp_stream_wait_event(side, rec.ready_event)
+            F.sp_memcpy_d2h_async(view.ctypes.data, out._ptr, value.nbytes, side)  # (the private copy)
+            F.sp_event_record(landed[slot], side)
+            out._ready = (rec.ready_event, landed[slot], view, gens, slot, gens[slot])
     if rec.graph_b is not None and speculate_backward:
         # The loop has asked for the gradients of every recent result of this recording: start
         # the backward pass now, behind the forward pass, instead of after the host has read

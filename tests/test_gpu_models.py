@@ -349,6 +349,51 @@ def test_classifier_head_in_one_kernel_is_bit_identical(rows, k, n, precision):
     assert_close(fused[2], ref, 2e-5 if precision != "tf32x1" else 2e-3, "loss")
 
 
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+@pytest.mark.parametrize("rows,k,n", [(200, 784, 100), (200, 100, 100), (37, 300, 48), (128, 2048, 64),
+                                      (5, 64, 17), (64, 70, 130)])
+def test_hidden_linear_layer_in_one_kernel_is_bit_identical(rows, k, n, precision):
+    """leaky_relu(matmul(x, w) + b) of a small layer (the README MLP's hidden layers) is ONE
+    launch (sp_gemm_bias_leaky: K split over a thread-block cluster, partial tiles added through
+    distributed shared memory in rank order, bias and activation in the epilogue).  Values and
+    gradients equal the separate launches bit for bit, and the float64 product within fp32."""
+    from smallpebble_b200 import _abi, core
+
+    rng = np.random.default_rng(rows + k + n)
+    x = rng.random((rows, k)) - 0.5
+    w = (rng.random((k, n)) - 0.5) * 4 / np.sqrt(k)
+    b = rng.random((n,)) - 0.5
+    sp.set_precision(precision)
+
+    def run(fuse):
+        core._fuse_linear = fuse
+        try:
+            xv, wv, bv = sp.Variable(x), sp.Variable(w), sp.Variable(b)
+            before = _abi.counter.launches
+            z = sp.add(sp.matmul(xv, wv), bv)
+            h = sp.leaky_relu(z, 0.05)
+            launches = _abi.counter.launches - before
+            gy = np.random.default_rng(9).random(h.shape) - 0.5
+            g = sp.get_gradients(sp.mul(h, sp.Variable(gy)))
+            return [np.asarray(h.array), np.asarray(g[wv]), np.asarray(g[xv]), np.asarray(g[bv]),
+                    np.asarray(z.array)], launches
+        finally:
+            core._fuse_linear = True
+
+    try:
+        fused, n_fused = run(True)
+        plain, n_plain = run(False)
+    finally:
+        sp.set_precision("tf32")
+    if precision == "tf32":  # (compensated mode: small forward products run exactly on CUDA cores)
+        assert n_fused == 1 and n_plain >= 3
+    for a, c in zip(fused, plain):
+        assert np.array_equal(a, c)
+    z = x @ w + b
+    assert_close(fused[0], np.where(z > 0, z, 0.05 * z), 2e-5, "layer output")
+    assert_close(fused[4], z, 2e-5, "pre-activation, launched on demand")
+
+
 @pytest.mark.parametrize("policy", [0, 32 + 256, 32 + 128], ids=["policy", "tma2", "halo"])
 @pytest.mark.parametrize("alpha", [0.02, 0.0])
 def test_conv_leaky_epilogue_fusion_is_bit_identical(policy, alpha):
