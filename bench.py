@@ -244,6 +244,18 @@ def algorithmic_work(name, args):
             nbytes = 4.0 * (g.N * g.H * g.W * g.C + g.N * g.OH * g.OW * g.K + g.KH * g.KW * g.C * g.K)
             return "hbm", nbytes, desc + " (first layer)"
         return "tensor", flops, desc
+    if name == "sp_conv2d_leaky_pool2_fwd":
+        # conv2d + leaky_relu + 2x2 maxpool2d of the first layer in one kernel: reads x and w,
+        # writes the pooled tensor, its uint8 argmax and (when asked) the (r, l) split
+        g = args[5]
+        g = g.contents if hasattr(g, "contents") else g
+        pooled = g.N * (g.OH // 2) * (g.OW // 2) * g.K
+        nbytes = 4.0 * (g.N * g.H * g.W * g.C + g.KH * g.KW * g.C * g.K) + pooled * (5.0 + (8.0 if args[4] else 0.0))
+        return "hbm", nbytes, (f"conv2d+leaky_relu+maxpool2d N={g.N} HxW={g.H}x{g.W} C={g.C} K={g.K} "
+                               f"k={g.KH}x{g.KW} pool 2x2/2 (first layer, one kernel)")
+    if name in ("sp_gemm_bias_leaky", "sp_gemm_bias", "sp_gemm_bias_softmax_xent"):
+        m, n, k = args[0], args[1], args[2]
+        return "tensor", 2.0 * m * n * k, f"{name[3:]} M={m} N={n} K={k}"
     if name == "sp_gemm":
         m, n, k, batch = args[2], args[3], args[4], args[14]
         return "tensor", 2.0 * m * n * k * max(batch, 1), f"gemm M={m} N={n} K={k} batch={batch}"
@@ -417,13 +429,20 @@ def run_ours(args):
     # step: the loop is host-bound, and with an idle device every event pair would also contain
     # the host time between the first event and the launch.  Queued behind the memsets, the
     # kernels and their events run back to back and the pairs measure device time (cold L2).
-    for _ in range(8):
-        flush_l2()
-    _abi.prof.begin_step()
-    step_resident()
-    torch.cuda.synchronize()
+    # Five such steps, the MEDIAN per call: half a dozen calls of this step take 15-20 us each
+    # and a single pass picks a different "dominant" one from run to run.
+    passes = {}
+    for rep in range(5):
+        _abi.prof.records.clear()
+        for _ in range(8):
+            flush_l2()
+        _abi.prof.begin_step()
+        step_resident(rep)
+        torch.cuda.synchronize()
+        for name, seq, a, e0, e1 in _abi.prof.records:
+            passes.setdefault((name, seq), [[], a])[0].append(e0.elapsed_time(e1))
     _abi.prof.active = False
-    per_call = [(e0.elapsed_time(e1), name, seq, a) for name, seq, a, e0, e1 in _abi.prof.records]
+    per_call = [(statistics.median(ts), name, seq, a) for (name, seq), (ts, a) in passes.items()]
     per_call.sort(key=lambda r: -r[0])
     top = next((r for r in per_call if algorithmic_work(r[1], r[3]) is not None), None)
     calls_per_step = len(per_call)
