@@ -111,8 +111,23 @@ int sp_memcpy_d2h(void* host_dst, const void* src, size_t bytes, sp_stream_t str
  * np.isnan(loss_val.array) (README.md:319) costs one event wait, not a copy of its own */
 int sp_memcpy_d2h_async(void* pinned_dst, const void* src, size_t bytes, sp_stream_t stream);
 int sp_event_synchronize(void* event);
+/* ... or without any stream synchronisation: dst = src on the device and the same 4..64 bytes
+ * published to a 68-byte page-locked host slot (payload, then word 16 = seq behind a system
+ * fence); the host polls word 16 */
+int sp_copy_publish(const void* src, void* dst, size_t bytes, void* host_slot, unsigned int seq,
+                    sp_stream_t stream);
 int sp_memcpy_d2d(void* dst, const void* src, size_t bytes, sp_stream_t stream);
 int sp_fill_f32(float* dst, int64_t n, float value, sp_stream_t stream);
+/* ... or narrowed on HOST cores while the copy is in flight, so that half the bytes cross PCIe
+ * (csrc/host_pipe.cu: a small persistent worker pool converts 4096-element sub-chunks into the
+ * page-locked `stage` buffer, every completed 256 KB chunk goes on `stream` at once, `landed`
+ * -- an sp_event_create event -- is recorded behind the last one).  _begin returns immediately;
+ * call _finish before ordering a stream behind `landed`, before the next _begin and before
+ * touching src / stage again.  Same values as the device narrowing (round to nearest even). */
+int sp_host_pipe_threads(int* threads);
+int sp_h2d_f64_as_f32_begin(const double* src, float* stage, float* dev, int64_t n, void* landed,
+                            sp_stream_t stream);
+int sp_h2d_f64_as_f32_finish(void);
 /* float64 host data uploaded raw then narrowed on device (np.float64 -> device fp32) */
 int sp_cast_f64_f32(const double* src, float* dst, int64_t n, sp_stream_t stream);
 int sp_cast_i64_i32(const int64_t* src, int32_t* dst, int64_t n, sp_stream_t stream);

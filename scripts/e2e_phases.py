@@ -38,3 +38,19 @@ loop(60, False); torch.cuda.synchronize()
 t = time.perf_counter(); ph = loop(400, True); torch.cuda.synchronize(); tot = (time.perf_counter() - t) / 400 * 1e6
 print(f"{kind}: {tot:.1f} us/step wall; assign {ph[0]:.1f}  run {ph[1]:.1f}  isnan(loss) {ph[2]:.1f}  "
       f"get_gradients {ph[3]:.1f}  training_step {ph[4]:.1f}")
+
+# host time of the three graph launches and of the input feed, by call order within a step
+from smallpebble_b200 import steady as _st
+acc = {"replay": [0.0, 0.0, 0.0], "feed": 0.0, "n": 0}
+_orig_replay = torch.cuda.CUDAGraph.replay
+_k = [0]
+def _timed_replay(self):
+    t = time.perf_counter(); _orig_replay(self); acc["replay"][_k[0] % 3] += time.perf_counter() - t; _k[0] += 1
+torch.cuda.CUDAGraph.replay = _timed_replay
+_orig_feed = _st._feed
+def _timed_feed(dst, v):
+    t = time.perf_counter(); _orig_feed(dst, v); acc["feed"] += time.perf_counter() - t
+_st._feed = _timed_feed
+loop(20, False); _k[0] = 0; acc["replay"] = [0.0, 0.0, 0.0]; acc["feed"] = 0.0
+loop(300, False); torch.cuda.synchronize()
+print("graph launch host us (F, B, U):", [round(v / 300 * 1e6, 1) for v in acc["replay"]], " feed (x + labels):", round(acc["feed"] / 300 * 1e6, 1))

@@ -79,6 +79,10 @@ SIGNATURES = {
     "sp_event_create": (C.c_int, [vp]),
     "sp_event_record": (C.c_int, [vp, vp]),
     "sp_event_synchronize": (C.c_int, [vp]),
+    "sp_host_pipe_threads": (C.c_int, [C.POINTER(C.c_int)]),
+    "sp_h2d_f64_as_f32_begin": (C.c_int, [vp, vp, vp, i64, vp, vp]),
+    "sp_h2d_f64_as_f32_finish": (C.c_int, []),
+    "sp_copy_publish": (C.c_int, [vp, vp, sz, vp, C.c_uint, vp]),
     "sp_memcpy_d2h_async": (C.c_int, [vp, vp, sz, vp]),
     "sp_stream_wait_event": (C.c_int, [vp, vp]),
     "sp_softmax_xent_bwd_colsum": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp]),
@@ -148,7 +152,7 @@ _LAUNCHING = {
     n for n in SIGNATURES
     if n not in ("sp_abi_version", "sp_last_error", "sp_device_info", "sp_debug_set_umma_policy",
                  "sp_debug_tma2_trace", "sp_debug_peer_trace", "sp_host_is_pinned", "sp_stream_create", "sp_event_create",
-                 "sp_event_record", "sp_event_synchronize", "sp_memcpy_d2h_async", "sp_stream_wait_event", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
+                 "sp_event_record", "sp_event_synchronize", "sp_host_pipe_threads", "sp_h2d_f64_as_f32_begin", "sp_h2d_f64_as_f32_finish", "sp_memcpy_d2h_async", "sp_stream_wait_event", "sp_memcpy_h2d", "sp_memcpy_d2h", "sp_memcpy_d2d", "sp_l2_flush",
                  "sp_conv2d_wgrad_workspace", "sp_set_tf32_output_rounding", "sp_conv2d_x3_plan",
                  "sp_set_scratch_lane", "sp_conv2d_wgrad_pooled_supported", "sp_conv2d_leaky_pool2_supported", "sp_conv2d_dgrad_unpool_supported", "sp_nccl_load", "sp_nccl_unique_id", "sp_nccl_init",
                  "sp_allreduce_sum_f32", "sp_nccl_destroy", "sp_peer_alloc", "sp_peer_open",

@@ -465,16 +465,20 @@ class DeviceArray:
         out = np.empty(self.shape, self.dtype)
         ready = self._ready
         if type(ready) is tuple:
-            # (ready event, mirror event, host mirror, slot generations, slot, generation): the
-            # producer also copied the contents into page-locked host memory (done at the
-            # mirror event) -- one wait, no copy of our own -- unless the ring has come round
-            # to this slot since
-            ready, landed, mirror, gens, slot, gen = ready
+            # (ready event, host slot, slot generations, slot, generation): the producer also
+            # published the contents to a page-locked host slot -- payload words, then the
+            # generation in word 16 behind a system fence (sp_copy_publish).  Poll that word:
+            # no copy, no stream or event wait -- unless the ring has come round to this slot
+            # since, or the word does not show up (then the event path below)
+            ready, mirror, gens, slot, gen = ready
             if gens[slot] == gen:
-                F.sp_event_synchronize(landed)
-                out.reshape(-1).view(np.uint8)[:] = mirror[:out.nbytes]
-                _counters["d2h_bytes"] += out.nbytes
-                return out
+                spins = 0
+                while mirror[16] != gen and spins < 2000000:
+                    spins += 1
+                if mirror[16] == gen:
+                    out.reshape(-1).view(np.uint32)[:] = mirror[:out.nbytes // 4]
+                    _counters["d2h_bytes"] += out.nbytes
+                    return out
         if ready is not None:
             # the contents were final at this event (the result of a replayed forward pass):
             # read them on the copy stream as soon as it has fired, without waiting for work
@@ -708,7 +712,8 @@ class _UploadRing:
     def __init__(self):
         self.stream = None
         self.slots = [{"buf": None, "ptr": 0, "nbytes": 0, "landed": None, "free": None,
-                       "free_valid": False, "host": None, "gen": 0} for _ in range(self.SLOTS)]
+                       "free_valid": False, "host": None, "gen": 0, "stage": None, "f32": False}
+                      for _ in range(self.SLOTS)]
         self.next = 0
 
     def reset(self):
@@ -729,6 +734,8 @@ class _UploadRing:
         if slot["landed"] is None:
             slot["landed"], slot["free"] = new_event(), new_event()
         elif slot["host"] is not None:
+            if slot["f32"]:
+                F.sp_h2d_f64_as_f32_finish()        # (its copies are all enqueued)
             F.sp_event_synchronize(slot["landed"])  # three uploads ago: long complete
         if slot["nbytes"] < nbytes:
             torch = _lazy_torch()
@@ -743,12 +750,34 @@ class _UploadRing:
             F.sp_stream_wait_event(self.stream, slot["free"])
         if slot["free_valid"]:
             F.sp_stream_wait_event(self.stream, slot["free"])
+        if host_pipe and host.dtype == np.float64 and nbytes >= _HOST_PIPE_MIN:
+            # narrowed on host cores while the copy runs: half the bytes cross PCIe, the slot
+            # ends up holding fp32 (csrc/host_pipe.cu); returns at once
+            stage = slot["stage"]
+            if stage is None or stage.size < host.size:
+                stage = slot["stage"] = pinned_empty((host.size,), np.float32)
+            if stage is not None:
+                F.sp_h2d_f64_as_f32_begin(host.ctypes.data, stage.ctypes.data, slot["ptr"],
+                                          host.size, slot["landed"], self.stream)
+                slot["f32"] = True
+                slot["host"] = host
+                if wait:
+                    self.ready(slot)
+                return slot
         F.sp_memcpy_h2d(slot["ptr"], host.ctypes.data, nbytes, self.stream)
         F.sp_event_record(slot["landed"], self.stream)
+        slot["f32"] = False
         slot["host"] = host
         if wait:
             F.sp_stream_wait_event(stream(), slot["landed"])
         return slot
+
+    @staticmethod
+    def ready(slot):
+        """Order the compute stream behind the slot's copy."""
+        if slot["f32"]:
+            F.sp_h2d_f64_as_f32_finish()  # the pool has enqueued every chunk and the event
+        F.sp_stream_wait_event(stream(), slot["landed"])
 
     @staticmethod
     def consumed(slot):
@@ -765,6 +794,13 @@ _upload_ring = _UploadRing()
 # `run()` reaches the upload, and the host-to-device copy is on the loop's critical path.
 _prestaged = {}
 eager_staging = os.environ.get("SP_EAGER_UPLOAD", "1") != "0"
+# Optional: float64 batches of a megabyte or more narrowed to fp32 by a pool of host threads
+# while the copy is in flight (csrc/host_pipe.cu), which halves the bytes on the longest leg of
+# the README loop's critical path.  OFF by default: on this pool's hosts (16 virtual cores)
+# eight threads need ~100 us for the 3.1 MB batch -- the copy engine moves the float64 bytes in
+# 61 us -- so the loop got slower, not faster (scripts/e2e_phases.py).
+host_pipe = os.environ.get("SP_HOST_PIPE", "0") == "1"
+_HOST_PIPE_MIN = 1 << 20
 
 
 def _prestage(host: np.ndarray) -> None:
@@ -785,12 +821,16 @@ def upload_f64_narrowed(host: np.ndarray, dst_ptr: int) -> None:
     pre = _prestaged.pop(host.ctypes.data, None) if _prestaged else None
     if pre is not None and pre[0]["gen"] == pre[1] and pre[2] == host.nbytes:
         slot = pre[0]
-        F.sp_stream_wait_event(stream(), slot["landed"])
+        _UploadRing.ready(slot)
     else:
         slot = _upload_ring.upload(host)
-    F.sp_cast_f64_f32(slot["ptr"], dst_ptr, host.size, stream())
+    if slot["f32"]:  # narrowed on the way (host pipeline): fp32 arrived
+        F.sp_memcpy_d2d(dst_ptr, slot["ptr"], host.size * 4, stream())
+        _counters["h2d_bytes"] += host.size * 4
+    else:
+        F.sp_cast_f64_f32(slot["ptr"], dst_ptr, host.size, stream())
+        _counters["h2d_bytes"] += host.nbytes
     _UploadRing.consumed(slot)
-    _counters["h2d_bytes"] += host.nbytes
 
 
 def pinned_empty(shape, dtype):
@@ -817,10 +857,17 @@ def _is_pinned(a: np.ndarray) -> bool:
 
 
 def _keep_alive_until_copied(host: np.ndarray) -> None:
-    ev = _torch.cuda.Event()
-    ev.record()
-    if len(_in_flight_sources) >= 8:
-        _in_flight_sources[:] = [(e, h) for e, h in _in_flight_sources if not e.query()]
+    """Hold a reference to a PAGE-LOCKED source of an asynchronous host-to-device copy until the
+    copy has run: a ring of eight raw events, the oldest waited for (long complete) when it comes
+    round.  Pageable sources need none of this: cudaMemcpyAsync stages them before it returns."""
+    if host.nbytes < _PIN_THRESHOLD and host.ctypes.data not in _pinned.owned:
+        return  # from_host pins nothing below the threshold
+    if len(_in_flight_sources) < 8:
+        ev = new_event()
+    else:
+        ev, _ = _in_flight_sources.pop(0)
+        F.sp_event_synchronize(ev)
+    F.sp_event_record(ev, stream())
     _in_flight_sources.append((ev, host))
 
 _UFUNC_TO_OP = {np.add: "add", np.subtract: "sub", np.multiply: "mul", np.true_divide: "div"}

@@ -52,6 +52,23 @@ __global__ void fill_f32_kernel(float* __restrict__ dst, int64_t n, float v) {
     dst[i] = v;
 }
 
+// A small result (the loss, <= 16 words) copied to a private device buffer AND published to
+// page-locked host memory the device can address: payload first, then -- behind a system-scope
+// fence -- the sequence word the host is polling.  One warp.
+__global__ void copy_publish_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                    int words, volatile uint32_t* host_slot, uint32_t seq) {
+  pdl_entry();
+  const int i = threadIdx.x;
+  if (i < words) {
+    const uint32_t v = src[i];
+    dst[i] = v;
+    host_slot[i] = v;
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (i == 0) host_slot[16] = seq;
+}
+
 __global__ void cast_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst,
                                     int64_t n) {
   pdl_entry();
@@ -165,6 +182,22 @@ int sp_fill_f32(float* dst, int64_t n, float value, sp_stream_t stream) {
   SP_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "dst must be 16-byte aligned");
   sp::launch_pdl(fill_f32_kernel, dim3(sp::wave_grid(n, 256 * 4 * 4, 8)), dim3(256), 0, sp::as_stream(stream), dst, n, value);
   SP_CHECK_LAUNCH("fill_f32");
+  return 0;
+}
+
+// dst (device) = src (device), and the same `bytes` (a multiple of 4, at most 64) to the 68-byte
+// page-locked, device-addressable `host_slot`: [0, 64) payload, word 16 = seq, written LAST
+// behind a system fence -- the host polls that word instead of synchronising a stream.
+int sp_copy_publish(const void* src, void* dst, size_t bytes, void* host_slot, unsigned int seq,
+                    sp_stream_t stream) {
+  SP_REQUIRE(src && dst && host_slot, "null operand");
+  SP_REQUIRE(bytes > 0 && bytes <= 64 && bytes % 4 == 0, "sp_copy_publish: 4..64 bytes in words");
+  SP_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) |
+               reinterpret_cast<uintptr_t>(host_slot)) & 3) == 0, "unaligned operand");
+  sp::launch_pdl(copy_publish_kernel, dim3(1), dim3(32), 0, sp::as_stream(stream),
+                 static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst), (int)(bytes / 4),
+                 static_cast<volatile uint32_t*>(host_slot), (uint32_t)seq);
+  SP_CHECK_LAUNCH("copy_publish");
   return 0;
 }
 

@@ -235,12 +235,13 @@ _MIRROR_SLOTS = 16
 
 
 def _mirror_ring():
-    """(page-locked [slots, bytes] uint8 array, per-slot generation counters, per-slot events),
-    or None."""
-    buf = A.pinned_empty((_MIRROR_SLOTS, _MIRROR_BYTES), np.uint8)
+    """(page-locked [slots, 17] uint32 array: 16 payload words + the sequence word, per-slot
+    generation counters), or None."""
+    buf = A.pinned_empty((_MIRROR_SLOTS, 17), np.uint32)
     if buf is None:
         return None
-    return buf, [0] * _MIRROR_SLOTS, [A.new_event() for _ in range(_MIRROR_SLOTS)]
+    buf[...] = 0
+    return buf, [0] * _MIRROR_SLOTS
 
 
 def _shadows_intact(rec) -> bool:
@@ -409,33 +410,33 @@ def _replay_forward(rec):
     static_root = rec.root
     value = static_root._array
     out = DeviceArray.empty(value.shape, value.dtype, value.size)
-    if value.size:
-        F.sp_memcpy_d2d(out._ptr, value._ptr, value.nbytes, A.stream())
     out._tf32 = value._tf32
     # the root value is final here: a host read (`np.isnan(loss_val.array)`, README.md:319) waits
     # for this event on a copy stream, not for whatever is enqueued behind it
     if rec.ready_event is None:
         rec.ready_event = A.new_event()
-    F.sp_event_record(rec.ready_event, A.stream())
-    out._ready = rec.ready_event
-    if 0 < value.nbytes <= _MIRROR_BYTES:
-        # a small result (the loss): also mirrored into page-locked host memory -- on the read
-        # stream, behind the event, so that the compute stream goes straight on with the
-        # backward pass -- and a host read costs one event wait instead of a copy of its own.
-        # A ring of slots: results may be read a few steps later.
+    ring = None
+    if 0 < value.nbytes <= _MIRROR_BYTES and value.nbytes % 4 == 0:
         ring = rec.mirror
         if ring is None:
-            ring = rec.mirror = _mirror_ring()
-        if ring is not None:
-            buf, gens, landed = ring
-            slot = rec.epoch % _MIRROR_SLOTS
-            gens[slot] += 1
-            view = buf[slot]
-            side = A._read_stream()
-            F.sp_stream_wait_event(side, rec.ready_event)
-            F.sp_memcpy_d2h_async(view.ctypes.data, out._ptr, value.nbytes, side)  # (the private copy)
-            F.sp_event_record(landed[slot], side)
-            out._ready = (rec.ready_event, landed[slot], view, gens, slot, gens[slot])
+            ring = rec.mirror = _mirror_ring() or False
+    if ring:
+        # a small result (the loss): the kernel that makes the caller's private copy also
+        # publishes it to a page-locked host slot (payload, then a sequence word behind a system
+        # fence), so a host read polls one word instead of synchronising a stream -- no copy,
+        # no event wait, no wake-up.  A ring of slots: results may be read a few steps later.
+        buf, gens = ring
+        slot = rec.epoch % _MIRROR_SLOTS
+        gen = gens[slot] = (gens[slot] + 1) & 0x7fffffff or 1
+        view = buf[slot]
+        F.sp_copy_publish(value._ptr, out._ptr, value.nbytes, view.ctypes.data, gen, A.stream())
+        F.sp_event_record(rec.ready_event, A.stream())
+        out._ready = (rec.ready_event, view, gens, slot, gen)
+    else:
+        if value.size:
+            F.sp_memcpy_d2d(out._ptr, value._ptr, value.nbytes, A.stream())
+        F.sp_event_record(rec.ready_event, A.stream())
+        out._ready = rec.ready_event
     if rec.graph_b is not None and speculate_backward:
         # The loop has asked for the gradients of every recent result of this recording: start
         # the backward pass now, behind the forward pass, instead of after the host has read

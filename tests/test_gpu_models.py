@@ -140,6 +140,54 @@ def test_pinned_host_batches_upload_without_a_host_pass():
         assert np.array_equal(np.asarray(sp.Variable(pageable).array), pinned.astype(np.float32))
 
 
+def test_host_pipeline_narrows_float64_batches_exactly():
+    """Page-locked float64 batches of >= 1 MB are converted to fp32 by the host thread pool while
+    their copy is in flight (sp_h2d_f64_as_f32_begin / _finish): every value equals NumPy's
+    round-to-nearest narrowing -- denormals, huge and tiny magnitudes, odd sizes, batches wrapped
+    but never used (their staging slot is recycled), back-to-back uploads."""
+    import ctypes
+
+    import torch
+
+    from smallpebble_b200 import _abi
+    from smallpebble_b200 import array as A
+
+    threads = ctypes.c_int(0)
+    _abi.f.sp_host_pipe_threads(threads)
+    assert threads.value >= 1
+    rng = np.random.default_rng(8)
+    sizes = [131072, 131072 + 5, 393216, 1_000_003, 65536 * 3 + 4095]
+    batches = []
+    for n in sizes:
+        x = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+        x[...] = (rng.random(n) - 0.5) * 10.0 ** rng.integers(-44, 38, n)
+        x[:7] = [0.0, -0.0, 1e-45, -3e-39, 3.4028235e38, 1.0 + 2.0 ** -24, 1.0 + 2.0 ** -24 + 2.0 ** -40]
+        batches.append(x)
+    with np.errstate(over="ignore", under="ignore"):
+        want = [x.astype(np.float32) for x in batches]
+    default = A.host_pipe  # (off: measured slower than the plain float64 copy on this pool's hosts)
+    A.host_pipe = True
+    try:
+        before = A.transfer_counters()["h2d_bytes"]
+        for rep in range(6):
+            held = [sp.Variable(x) for x in batches]          # five uploads started, three slots
+            unused = [sp.Variable(x) for x in batches[:2]]    # wrapped, never read
+            for v, w in zip(held, want):
+                v.array.ptr                                    # on the device now
+                got = np.asarray(v.array)
+                assert np.array_equal(got.view(np.uint32), w.view(np.uint32))
+            del unused
+        moved = A.transfer_counters()["h2d_bytes"] - before
+        assert moved == 6 * sum(4 * n for n in sizes)          # fp32 on the wire, used arrays only
+        A.host_pipe = False
+        for x, w in zip(batches, want):                        # the device-narrowing path: same bits
+            v = sp.Variable(x)
+            v.array.ptr
+            assert np.array_equal(np.asarray(v.array).view(np.uint32), w.view(np.uint32))
+    finally:
+        A.host_pipe = default
+
+
 def test_device_array_free_list_never_aliases_live_buffers():
     """array.py recycles buffers by byte size; a buffer must not come back while a view or an
     in-place-rebound alias of it is alive, and it must come back once the last holder dies."""
