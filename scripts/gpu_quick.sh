@@ -1,13 +1,2 @@
 #!/bin/bash
-timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; python - <<'P'
-import json
-d=json.load(open('gpurun_out/bench.json'))
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches','host_issue_ms_per_step','abi_calls_per_step')}, 'e2e', d['e2e'], 'graph', d['cuda_graph'] and d['cuda_graph']['ms_per_step'])
-print(d['regions'])
-print(d['roofline']['kernel'], d['roofline']['frac'], d['roofline']['avg_launch_ms'], d['roofline']['traffic'])
-print(d['top_calls_one_step_ms'])
-print(json.dumps(d.get('other_configs'))[:700])
-P
-tail -3 gpurun_out/bench.err
+timeout 600 python -m pytest tests/test_gpu_steady.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -8

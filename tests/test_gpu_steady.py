@@ -67,6 +67,43 @@ def test_replayed_loop_is_bit_identical_to_eager(kind, batch, replay_on):
     assert got[4] == want[4] == [steps] * len(got[4])
 
 
+def test_replayed_loop_from_page_locked_batches_reads_every_loss_right(replay_on):
+    """The end-to-end README loop: float64 batches in page-locked memory (their DMA starts when
+    they are wrapped, array.py `_prestage`), the loss read every step (published to a polled
+    host slot by the replayed forward pass, steady.py) and AGAIN long after the slot ring has
+    come round -- every value equals the eager loop's, bit for bit."""
+    import torch
+
+    rng = np.random.default_rng(6)
+    batch, steps = 16, 40  # (the slot ring holds 16 results per recording)
+    pins = torch.empty((4, batch, 32, 32, 3), dtype=torch.float64).pin_memory().numpy()
+    pins[...] = rng.random(pins.shape)
+    ys = [rng.integers(0, 10, batch) for _ in range(4)]
+
+    def loop(enabled):
+        steady.set_enabled(enabled)
+        wl = workloads.cifar_cnn(seed=0)
+        adam = sp.Adam()
+        now, kept = [], []
+        for i in range(steps):
+            wl.x_in.assign_value(sp.Variable(pins[i % 4]))
+            wl.y_true.assign_value(ys[i % 4])
+            loss_val = wl.loss.run()
+            now.append(float(np.asarray(loss_val.array)))   # read at once (polls the host slot)
+            kept.append(loss_val.array)                       # ... and kept for later
+            adam.training_step(wl.learnables, sp.get_gradients(loss_val))
+        later = [float(np.asarray(a)) for a in kept]         # most slots have been reused by now
+        return now, later, [np.asarray(p.array) for p in wl.learnables]
+
+    before = dict(steady.stats)
+    got = loop(True)
+    assert steady.stats["replays_f"] - before["replays_f"] >= steps - 8
+    want = loop(False)
+    assert got[0] == want[0] and got[1] == want[1] and got[0] == got[1]
+    for a, b in zip(got[2], want[2]):
+        assert np.array_equal(a, b)
+
+
 def test_replay_falls_back_when_the_pattern_changes(replay_on):
     """New batch size, a rebound parameter, a second optimiser: each is served by the eager
     path (and re-recorded later); results equal the eager loop's."""
