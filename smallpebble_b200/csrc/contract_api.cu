@@ -186,7 +186,7 @@ namespace {
 // partial tiles in slice order, then bias and leaky_relu) instead of a split-K pass plus a
 // reduction launch (plus bias and activation launches): the hidden layers of the README MLP
 // (200 x 784 x 100, README.md:122-137).  Fills in the split and its scratch.
-bool cluster_gemm_plan(sp::IgemmParams& p, int* S) {
+bool small_gemm_plan(sp::IgemmParams& p, int* S) {
   if (p.batch > 1 || p.k_splits > 1 || p.ldc != p.N || sp::g_umma_policy == 1) return false;
   const int sms = sp::device_info().sm_count > 0 ? sp::device_info().sm_count : 148;
   const int64_t tiles = ((p.M + 63) / 64) * ((p.N + 63) / 64);
@@ -242,10 +242,10 @@ int sp_gemm_bias(int64_t M, int64_t N, int64_t K, const float* A, const float* B
       return 0;
     }
     int S = 1;
-    if (!sp::use_umma(sp::kGemm, p, precision) && cluster_gemm_plan(p, &S)) {
-      p.cluster_k = S;  // bias added after the complete sum: the bits of a separate add
-      if (int rc = sp::launch_igemm_simt_cluster(p, sp::as_stream(stream))) return rc;
-      SP_CHECK_LAUNCH("gemm_bias(cluster)");
+    if (!sp::use_umma(sp::kGemm, p, precision) && small_gemm_plan(p, &S)) {
+      p.splitk_fused = S;  // bias added after the complete sum: the bits of a separate add
+      if (int rc = sp::launch_gemm_simt_splitk_fused(p, sp::as_stream(stream))) return rc;
+      SP_CHECK_LAUNCH("gemm_bias(fused split-K)");
       return 0;
     }
   }
@@ -255,7 +255,7 @@ int sp_gemm_bias(int64_t M, int64_t N, int64_t K, const float* A, const float* B
 }
 
 // leaky_relu(A . B + bias, alpha): a hidden linear layer of the README MLP with its activation
-// (sp.py:630-635, 231-236) -- one launch when the cluster kernel above takes the product,
+// (sp.py:630-635, 231-236) -- one launch when the fused split-K kernel above takes the product,
 // otherwise sp_gemm_bias followed by the in-place activation.  Bit-identical either way.
 int sp_gemm_bias_leaky(int64_t M, int64_t N, int64_t K, const float* A, const float* B,
                        const float* bias, float* C, int precision, float alpha,
@@ -282,10 +282,10 @@ int sp_gemm_bias_leaky(int64_t M, int64_t N, int64_t K, const float* A, const fl
     p.leaky_alpha = alpha;
     int S = 1;
     if (!sp::use_umma(sp::kGemm, p, precision) &&
-        !(sp::g_umma_policy != 1 && sp::gemm_skinny_supported(p)) && cluster_gemm_plan(p, &S)) {
-      p.cluster_k = S;
-      if (int rc = sp::launch_igemm_simt_cluster(p, sp::as_stream(stream))) return rc;
-      SP_CHECK_LAUNCH("gemm_bias_leaky(cluster)");
+        !(sp::g_umma_policy != 1 && sp::gemm_skinny_supported(p)) && small_gemm_plan(p, &S)) {
+      p.splitk_fused = S;
+      if (int rc = sp::launch_gemm_simt_splitk_fused(p, sp::as_stream(stream))) return rc;
+      SP_CHECK_LAUNCH("gemm_bias_leaky(fused split-K)");
       return 0;
     }
   }
@@ -459,10 +459,10 @@ int sp_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   // library scratch and sum the partial tiles in a fixed order.
   {
     int S = 1;
-    if (cluster_gemm_plan(p, &S) && S > 1) {  // one launch: K split over a cluster
-      p.cluster_k = S;
-      if (int rc = sp::launch_igemm_simt_cluster(p, st)) return rc;
-      SP_CHECK_LAUNCH("gemm(cluster split-K)");
+    if (small_gemm_plan(p, &S) && S > 1) {  // one launch: K split over CTAs, last arrival reduces
+      p.splitk_fused = S;
+      if (int rc = sp::launch_gemm_simt_splitk_fused(p, st)) return rc;
+      SP_CHECK_LAUNCH("gemm(fused split-K)");
       return 0;
     }
   }

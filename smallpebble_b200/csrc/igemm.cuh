@@ -54,12 +54,12 @@ struct IgemmParams {
   int k_splits;
   int64_t k_chunk;  // multiple of the kernel's K tile
   int64_t split_stride_c;
-  // CUDA-core GEMM only (launch_igemm_simt_cluster): K split over cluster_k CTAs per output tile
-  // in ONE launch -- partial tiles in splitk_part ([cluster_k][M][N] floats), the CTA that
+  // CUDA-core GEMM only (launch_gemm_simt_splitk_fused): K split over splitk_fused CTAs per output tile
+  // in ONE launch -- partial tiles in splitk_part ([splitk_fused][M][N] floats), the CTA that
   // arrives last at the tile's word of tail_counter adds them in slice order, then `bias` (if
   // any) and the leaky epilogue: a small linear layer without reduction / bias / activation
   // launches
-  int cluster_k;
+  int splitk_fused;
   float* splitk_part;
   // skinny rows kernel only (gemm_skinny.cu): C are the logits of a classifier whose
   // softmax + cross_entropy (sp.py:612-621) the LAST block to finish computes in the same
@@ -76,8 +76,8 @@ struct IgemmParams {
 };
 
 int launch_igemm_simt(int mode, const IgemmParams& p, cudaStream_t stream);
-// kGemm with K split over p.cluster_k CTAs per tile, last arrival reduces; bias / leaky epilogue
-int launch_igemm_simt_cluster(const IgemmParams& p, cudaStream_t stream);
+// kGemm with K split over p.splitk_fused CTAs per tile, last arrival reduces; bias / leaky epilogue
+int launch_gemm_simt_splitk_fused(const IgemmParams& p, cudaStream_t stream);
 int launch_igemm_umma(int mode, const IgemmParams& p, cudaStream_t stream);
 // true when the tcgen05 kernel supports this problem (shape / alignment constraints)
 bool igemm_umma_supported(int mode, const IgemmParams& p);

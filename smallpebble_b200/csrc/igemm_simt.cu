@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) gemm_simt_splitk_fused_kernel(const 
 template <bool AK, bool BK_>
 int launch_splitk_fused(const IgemmParams& p, cudaStream_t st) {
   const dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN),
-                  (unsigned)p.cluster_k);
+                  (unsigned)p.splitk_fused);
   sp::launch_pdl(gemm_simt_splitk_fused_kernel<AK, BK_>, grid, dim3(kThreads), 0, st, p);
   return 0;
 }
@@ -360,11 +360,11 @@ int launch(const IgemmParams& p, cudaStream_t st) {
 
 }  // namespace
 
-int launch_igemm_simt_cluster(const IgemmParams& p, cudaStream_t st) {
+int launch_gemm_simt_splitk_fused(const IgemmParams& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0) return 0;
-  if (p.cluster_k < 1 || p.cluster_k > 64 || p.batch > 1 || p.k_splits > 1)
+  if (p.splitk_fused < 1 || p.splitk_fused > 64 || p.batch > 1 || p.k_splits > 1)
     return set_error(SP_ERR_INVALID_ARGUMENT, "gemm_simt_splitk_fused: bad split");
-  if (p.cluster_k > 1 && !(p.splitk_part && p.tail_counter))
+  if (p.splitk_fused > 1 && !(p.splitk_part && p.tail_counter))
     return set_error(SP_ERR_WORKSPACE, "gemm_simt_splitk_fused: no scratch");
   if ((p.N + BN - 1) / BN > 65535) return set_error(SP_ERR_UNSUPPORTED, "igemm: N too large");
   const bool ak = (p.a_cs == 1), bk = (p.b_rs == 1 && p.b_cs != 1);
