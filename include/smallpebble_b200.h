@@ -251,6 +251,11 @@ int sp_maxpool2d_leaky_fwd(const float* x, float* y, uint8_t* idx, int N, int H,
 int sp_maxpool2d_leaky_bwd(const float* gy, const uint8_t* idx, const float* x, float* dx, int N,
                            int H, int W, int C, int KH, int KW, int sy, int sx, int pad_t,
                            int pad_l, int OH, int OW, float alpha, sp_stream_t stream);
+/* the same for a 2x2 / stride-2 pool whose input was never stored (sp_conv2d_leaky_pool2_fwd):
+ * leaky_relu's slope comes from the pool's OUTPUT (same sign at the argmax for alpha > 0) */
+int sp_maxpool2d_leaky_bwd_y(const float* gy, const uint8_t* idx, const float* y_pooled, float* dx,
+                             int N, int H, int W, int C, int KH, int KW, int sy, int sx, int pad_t,
+                             int pad_l, int OH, int OW, float alpha, sp_stream_t stream);
 
 /* ---- matmul (sp.py:239-247): C[b] = op(A[b]) * op(B[b]), row-major, strided batch ---- */
 /* transX = 0: X stored [rows, cols] with leading dimension ldx; 1: stored transposed.

@@ -94,6 +94,7 @@ SIGNATURES = {
     "sp_maxpool2d_leaky_fwd": (C.c_int, [vp, vp, vp] + [C.c_int] * 12 + [f32, vp]),
     "sp_maxpool2d_fwd_split": (C.c_int, [vp, vp, vp, vp, i64, C.c_int] + [C.c_int] * 13 + [f32, vp]),
     "sp_maxpool2d_leaky_bwd": (C.c_int, [vp, vp, vp, vp] + [C.c_int] * 12 + [f32, vp]),
+    "sp_maxpool2d_leaky_bwd_y": (C.c_int, [vp, vp, vp, vp] + [C.c_int] * 12 + [f32, vp]),
     "sp_gemm": (C.c_int, [C.c_int, C.c_int, i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64,
                           i64, i64, C.c_int, vp]),
     "sp_conv2d_fprop": (C.c_int, [vp, vp, vp, C.POINTER(ConvGeom), C.c_int, vp]),

@@ -110,8 +110,19 @@ class CapturedStep:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         launches0 = _abi.counter.launches
-        with torch.cuda.graph(graph):
-            outputs = self.fn(*static)
+        # (no garbage collection inside the capture: destroying an older graph or stream that a
+        # collected cycle holds would invalidate it -- see steady._capture)
+        import gc
+
+        gc_was_on = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        try:
+            with torch.cuda.graph(graph):
+                outputs = self.fn(*static)
+        finally:
+            if gc_was_on:
+                gc.enable()
         kernels = _abi.counter.launches - launches0
         return graph, static, outputs, kernels
 

@@ -656,7 +656,15 @@ def leaky_relu(a: Variable, alpha: float = 0.02) -> Variable:
 
             def launch_pool_bwd(out):
                 r = _want_rounding(a)  # (the library-global switch may have moved since)
-                F.sp_maxpool2d_leaky_bwd(g0.ptr, idx.ptr, x.ptr, out.ptr, *geom, alpha, A.stream())
+                if (x.pending_tag is not None and alpha > 0 and geom[4:8] == (2, 2, 2, 2)
+                        and x.shape[3] % 4 == 0):
+                    # the pool's input was never stored (conv + leaky_relu + pool ran as one
+                    # kernel): the slope at the argmax is the slope at the pooled value
+                    F.sp_maxpool2d_leaky_bwd_y(g0.ptr, idx.ptr, ypool.ptr, out.ptr, *geom, alpha,
+                                               A.stream())
+                else:
+                    F.sp_maxpool2d_leaky_bwd(g0.ptr, idx.ptr, x.ptr, out.ptr, *geom, alpha,
+                                             A.stream())
                 out._tf32 = r  # rounded as stored: an operand of the conv gradients
 
             if alpha > 0 and getattr(a, "_pooled_wgrad", None) == geom:
@@ -1113,12 +1121,13 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
         """maxpool2d(leaky_relu(conv2d(x, w), alpha), 2, 2, strides [2, 2]) in ONE kernel
         (sp_conv2d_leaky_pool2_fwd: first-layer geometries) -- the full-resolution tensor stays
         unlaunched.  False: no such kernel for this conv, the caller pools the usual way."""
-        g, pr = geom, prec
+        xa, wa, g, pr = x, w, geom, prec
+        xsplit = wsplit = None
         if compensate:
-            code, g, pr, xsplit, _ = _conv_x3(plan)
-            if xsplit is not None:
-                return False
-        key = ("pool2", pr)
+            code, g, pr, xsplit, wsplit = _conv_x3(plan)
+            if xsplit is not None and code != _abi.X3_SPLIT2:
+                return False  # (K-concatenated operands: not a layout the pooled epilogue takes)
+        key = ("pool2", pr, _steady.config_epoch)
         ok = plan[4].get(key)
         if ok is None:
             flag = C.c_int(0)
@@ -1126,7 +1135,13 @@ def conv2d(images: Variable, kernels: Variable, padding: str = "SAME", strides=(
             ok = plan[4][key] = bool(flag.value)
         if not ok:
             return False
-        F.sp_conv2d_leaky_pool2_fwd(x.ptr, w.ptr, ypool.ptr, idx.ptr,
+        if xsplit is not None:
+            # error-compensated tcgen05 layer: pre-split (r, l) operands, as in launch()
+            if images.local_gradients and getattr(images, "_argmax", None) is not None:
+                _split_hints[x.shape] = xsplit
+            xa = A.tf32_split(x, *xsplit)
+            wa = A.tf32_split(w, *wsplit)
+        F.sp_conv2d_leaky_pool2_fwd(xa.ptr, wa.ptr, ypool.ptr, idx.ptr,
                                     split._ptr if split is not None else None, g, pr, alpha,
                                     A.stream())
         return True
@@ -1261,9 +1276,10 @@ def maxpool2d(images: Variable, kernheight: int, kernwidth: int, padding: str = 
         if ctag is not None and ctag[0] == "conv2d" and len(ctag) > 2:
             conv_pool = ctag[2]  # the conv that feeds the leaky_relu has not been launched
     done = False
-    if conv_pool is not None and (hint is None or hint == (_abi.SPLIT_RL, out_shape[3])):
-        # conv2d + leaky_relu + this pool as one kernel (first-layer convs); the (r, l) split
-        # comes out of the same kernel when its blocks are whole pixels
+    if conv_pool is not None and (hint is None or hint == (_abi.SPLIT_RL, min(out_shape[3], 32))):
+        # conv2d + leaky_relu + this pool as one kernel (first-layer convs, and the layers of
+        # the 2-SM tcgen05 kernel, which pools in its epilogue); the (r, l) split of the pooled
+        # tensor comes out of the same kernel (blocks of 32 channels, or whole pixels below that)
         split = DeviceArray.empty((out_size * 2,), A.FLOAT, out_size * 2) if hint is not None else None
         done = conv_pool(y, idx, split, tag[2])
         if done and split is not None:

@@ -807,14 +807,46 @@ int sp_conv2d_wgrad(const float* x, const float* gy, float* dw, const sp_conv_ge
   return 0;
 }
 
-// maxpool2d(leaky_relu(conv2d(x, w), alpha), 2, 2, strides 2) in ONE kernel for first-layer
+// maxpool2d(leaky_relu(conv2d(x, w), alpha), 2, 2, strides 2) in ONE kernel: first-layer
 // geometries (RGB, 3 x 3, stride 1, even output grid, 16 / 32 filters; SP_PRECISION_TF32 or
-// SP_PRECISION_TF32X3): the full-resolution activation tensor is never written.  Bit-identical
-// to sp_conv2d_fprop followed by sp_maxpool2d_leaky_fwd / sp_maxpool2d_fwd_split.
+// SP_PRECISION_TF32X3: conv_smallc.cu) and the layers the 2-SM TMA kernel takes (C, K in whole
+// 32 / 64-channel blocks, whole pooling windows inside a CTA's 128 rows; SP_PRECISION_TF32 or
+// SP_PRECISION_TF32_SPLIT with pre-split operands: the pool runs in the tcgen05 epilogue,
+// conv_tma2.cu).  The full-resolution activation tensor is never written; the split (if asked
+// for) is SP_SPLIT_RL in blocks of min(K, 32) channels.  Bit-identical to sp_conv2d_fprop
+// followed by sp_maxpool2d_leaky_fwd / sp_maxpool2d_fwd_split.
+// (for the tcgen05 layers: the problem as the 2-SM TMA kernel sees it, or false)
+static bool pool2_tma2_params(const sp_conv_geom* g, int precision, sp::IgemmParams* out) {
+  sp::IgemmParams p = sp::base_params();
+  p.g = *g;
+  p.M = (int64_t)g->N * g->OH * g->OW;
+  p.N = g->K;
+  p.K = (int64_t)g->KH * g->KW * g->C;
+  p.ldc = g->K;
+  *out = p;
+  if (precision == SP_PRECISION_TF32_SPLIT) {
+    if (g->C % 64 != 0) return false;
+    out->split3 = 1;
+  } else if (precision != SP_PRECISION_TF32) {
+    return false;
+  }
+  if (p.M == 0 || sp::g_umma_policy == 2 || sp::g_tma2_policy == 2) return false;
+  // single-pass mode: only where the policy picks this kernel anyway (not the halo variant)
+  if (precision == SP_PRECISION_TF32 &&
+      (sp::use_halo(sp::kFprop, p, precision) || !sp::use_tma2(sp::kFprop, p, precision)))
+    return false;
+  return sp::conv_tma2_pool_supported(*out);
+}
+
 int sp_conv2d_leaky_pool2_supported(const sp_conv_geom* g, int precision, int* supported) {
   if (int rc = sp::check_geom(g)) return rc;
   SP_REQUIRE(supported != nullptr, "null output");
-  *supported = (sp::g_umma_policy == 0 && sp::conv_leaky_pool2_supported(*g, precision)) ? 1 : 0;
+  sp::IgemmParams p;
+  *supported = 0;
+  if (sp::g_umma_policy == 0 && sp::conv_leaky_pool2_supported(*g, precision))
+    *supported = 1;
+  else if (!sp::small_c_supported(*g) && pool2_tma2_params(g, precision, &p))
+    *supported = 1;
   return 0;
 }
 
@@ -823,9 +855,27 @@ int sp_conv2d_leaky_pool2_fwd(const float* x, const float* w, float* y_pooled, u
                               sp_stream_t stream) {
   if (int rc = sp::check_geom(g)) return rc;
   SP_REQUIRE(x && w && y_pooled && argmax, "null operand");
+  if ((int64_t)g->N * g->OH * g->OW * g->K == 0) return 0;
+  sp::IgemmParams p;
+  if (!sp::small_c_supported(*g) && pool2_tma2_params(g, precision, &p)) {
+    // a tcgen05 layer: the pool runs in the epilogue of the 2-SM TMA kernel
+    if ((reinterpret_cast<uintptr_t>(y_pooled) | reinterpret_cast<uintptr_t>(split)) & 15 ||
+        reinterpret_cast<uintptr_t>(argmax) & 3)
+      return sp::set_error(SP_ERR_UNSUPPORTED, "conv2d_leaky_pool2: unaligned outputs");
+    p.A = x;
+    p.B = w;
+    p.C = nullptr;
+    p.leaky = 1;
+    p.leaky_alpha = alpha;
+    p.pool_y = y_pooled;
+    p.pool_idx = argmax;
+    p.pool_split = split;
+    if (int rc = sp::launch_conv_tma2(sp::kFprop, p, sp::as_stream(stream))) return rc;
+    SP_CHECK_LAUNCH("conv2d_leaky_pool2_fwd(2-SM TMA)");
+    return 0;
+  }
   if (sp::g_umma_policy != 0)
     return sp::set_error(SP_ERR_UNSUPPORTED, "conv2d_leaky_pool2: kernel policy pins another kernel");
-  if ((int64_t)g->N * g->OH * g->OW * g->K == 0) return 0;
   if (int rc = sp::launch_conv_leaky_pool2(x, w, y_pooled, argmax, split, *g, precision, alpha,
                                            sp::as_stream(stream)))
     return rc;

@@ -84,6 +84,19 @@ struct Tma2Params {
   int out_sy, out_sx;            // output pixel (u, v) of the phase = real pixel
   int out_oy, out_ox;            //   (out_oy + out_sy * u, out_ox + out_sx * v)
   int out_H, out_W;              // of an image of out_H x out_W pixels (out_sy == 0: dense rows)
+  // fprop, EPI == 3 (POOL): the conv's output goes through leaky_relu (p.leaky) and a 2 x 2 /
+  // stride-2 max-pool (sp.py:282-300; no padding on the top / left, zero padding competes at the
+  // bottom / right) INSIDE the epilogue: only the pooled tensor, its uint8 argmax and optionally
+  // the TF32 (r, l) split of the pooled tensor (32-channel blocks: what a compensated conv2d
+  // consumes) are written.  A CTA's 128 accumulator rows then cover whole pooling windows: either
+  // pool_ipc whole images (mode 1: OH*OW <= 128) or pool_R (even) output rows of ONE image
+  // (mode 2); CTA tile ct = m_pair * 2 + rank starts at pixel pool_tile(ct).m_start and its rows
+  // beyond .valid are loaded and multiplied but never used.
+  float* pool_y;
+  uint8_t* pool_idx;
+  float* pool_split;
+  int pool_mode, pool_ipc, pool_R, pool_tpi, pool_cta_tiles;
+  int POH, POW, n_img;
   // dgrad, EPI == 2: the data gradient is the gradient of a 2 x 2 / stride-2 max-pooled tensor
   // (sp.py:282-300) whose input went through leaky_relu: row m = pooled pixel (n, u, v) is
   // scattered to its window's argmax in the FULL-resolution gradient C [N, up_H, up_W, ldc],
@@ -491,6 +504,92 @@ __device__ __forceinline__ void store_block_rows_unpool(uint8_t* tile, const uin
   __syncwarp();
 }
 
+// ---- EPI == 3: max-pool inside the forward epilogue -----------------------------------------
+struct PoolTile {
+  int m_start;  // first output pixel (linear over N x OH x OW) of this CTA's 128 rows
+  int img0;     // first image
+  int imgs;     // images in the tile (mode 2: 1)
+  int oy0;      // first output row inside the image (mode 1: 0)
+  int rows;     // output rows per image in the tile
+};
+__device__ __forceinline__ PoolTile pool_tile(const Tma2Params& p, int ct) {
+  PoolTile t;
+  const int hw = p.D1 * p.D2;
+  if (ct >= p.pool_cta_tiles) {
+    t.m_start = t.img0 = t.imgs = t.oy0 = t.rows = 0;
+  } else if (p.pool_mode == 1) {
+    t.img0 = ct * p.pool_ipc;
+    t.imgs = min(p.pool_ipc, p.n_img - t.img0);
+    t.oy0 = 0;
+    t.rows = p.D1;
+    t.m_start = t.img0 * hw;
+  } else {
+    t.img0 = ct / p.pool_tpi;
+    t.imgs = 1;
+    t.oy0 = (ct - t.img0 * p.pool_tpi) * p.pool_R;
+    t.rows = min(p.pool_R, p.D1 - t.oy0);
+    t.m_start = t.img0 * hw + t.oy0 * p.D2;
+  }
+  return t;
+}
+__device__ __forceinline__ void pool_take(float v, int k, float& best, int& bi) {
+  if (v > best || (v != v && best == best)) {  // first maximum wins, NaN wins (pool.cu: take)
+    best = v;
+    bi = k;
+  }
+}
+// One 32-channel column block of a CTA tile sits in shared memory as four XOR-swizzled 32-row
+// tiles (row l: tile l / 32, 16-byte chunk c at ((l % 32) * 8 + (c ^ (l & 7)))), leaky_relu
+// already applied.  `nthreads` threads pool it: one (pooled pixel, chunk) item at a time -- the
+// four window values (zero where the window leaves the image: the padding competes), first
+// maximum in (dy, dx) order, then the stores sp_maxpool2d_fwd_split would make.
+__device__ __forceinline__ void pool_items(const Tma2Params& p, const PoolTile& pt,
+                                           const uint8_t* tile0, int col0, int tid, int nthreads) {
+  const int prows = (pt.rows + 1) >> 1;
+  const int items = pt.imgs * prows * p.POW * 8;
+  const int img_px = pt.rows * p.D2;
+  for (int it = tid; it < items; it += nthreads) {
+    const int chunk = it & 7;
+    int pp = it >> 3;
+    const int px = pp % p.POW;
+    pp /= p.POW;
+    const int pyl = pp % prows, il = pp / prows;
+    float4 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int oyl = 2 * pyl + (k >> 1), ox = 2 * px + (k & 1);
+      w[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (oyl < pt.rows && ox < p.D2) {
+        const int l = il * img_px + oyl * p.D2 + ox;
+        const int rl = l & 31;
+        w[k] = reinterpret_cast<const float4*>(tile0 + (l >> 5) * 4096)[rl * 8 + (chunk ^ (rl & 7))];
+      }
+    }
+    float4 best = w[0];
+    int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      pool_take(w[k].x, k, best.x, b0);
+      pool_take(w[k].y, k, best.y, b1);
+      pool_take(w[k].z, k, best.z, b2);
+      pool_take(w[k].w, k, best.w, b3);
+    }
+    const int64_t gp = ((int64_t)(pt.img0 + il) * p.POH + (pt.oy0 >> 1) + pyl) * p.POW + px;
+    const int col = col0 + chunk * 4;
+    const int64_t o = gp * p.N + col;
+    *reinterpret_cast<float4*>(p.pool_y + o) = best;
+    *reinterpret_cast<uchar4*>(p.pool_idx + o) =
+        make_uchar4((unsigned char)b0, (unsigned char)b1, (unsigned char)b2, (unsigned char)b3);
+    if (p.pool_split) {
+      const float4 r = make_float4(rna_tf32(best.x), rna_tf32(best.y), rna_tf32(best.z), rna_tf32(best.w));
+      // SP_SPLIT_RL in 32-channel blocks: [pixel][block][r (32) | l (32)]
+      float* d = p.pool_split + (gp * (p.N >> 5) + (col >> 5)) * 64 + (col & 31);
+      *reinterpret_cast<float4*>(d) = r;
+      *reinterpret_cast<float4*>(d + 32) = make_float4(best.x - r.x, best.y - r.y, best.z - r.z, best.w - r.w);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
@@ -528,8 +627,9 @@ struct ModeCfg {
 // ACT: the dgrad instantiation with the leaky_relu-backward epilogue (its prefetch registers
 // would otherwise cost the plain data gradient 2-3 %)
 // Launched with a runtime cluster dimension of 2 * p.ksplit CTAs (launch_conv_tma2).
-// EPI (dgrad): 0 plain store, 1 = ACT, 2 = UNPOOL (scatter through a 2x2 max-pool's argmax, see
-// Tma2Params::up_idx)
+// EPI: 0 plain store, 1 = ACT (dgrad), 2 = UNPOOL (dgrad: scatter through a 2x2 max-pool's
+// argmax, see Tma2Params::up_idx), 3 = POOL (fprop: leaky_relu + 2x2 max-pool in the epilogue,
+// see Tma2Params::pool_y)
 template <int MODE, int EPI = 0>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_tma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -537,6 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   using Cfg = ModeCfg<MODE>;
   constexpr bool ACT = EPI == 1;
   constexpr bool UNPOOL = EPI == 2;
+  constexpr bool POOL = EPI == 3;
   constexpr bool A_MN = (MODE == kWgrad);
   constexpr bool B_MN = (MODE != kDgrad);
   const int kS = p.stages;
@@ -621,6 +722,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           wdx = tp - wdy * p.KW;
         } else {
           int m = (tc.m_pair * 2 + (int)rank) * 128;
+          if (POOL) m = pool_tile(p, tc.m_pair * 2 + (int)rank).m_start;
           if (m >= p.M) m = 0;  // fully out-of-range half tile: load anything, never stored
           const int q = m / p.D2;
           cw = p.base_w + (m - q * p.D2) * p.sx;
@@ -865,6 +967,33 @@ __global__ void __launch_bounds__(kThreads, 1)
         trace_at(p, tr && warp == kWarpEpi0 && it < 4, 10 + it);
         continue;
       }
+      if (POOL) {
+        // leaky_relu + 2x2 max-pool of this CTA's rows, one 32-channel block at a time: the four
+        // epilogue warps park their 32 x 32 blocks side by side, meet at a named barrier, pool
+        const PoolTile pt = pool_tile(p, tc.m_pair * 2 + (int)rank);
+        const uint8_t* tile0 = smem_raw + (tiles - smem_u32(smem_raw)) + kRingBytes;
+        const int etid = (warp - kWarpEpi0) * 32 + lane;
+        for (int cb = 0; cb < tc.bn; cb += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
+          tmem_ld_wait();
+          if (p.leaky) leaky_block(v, p.alpha);
+          float4* t4 = reinterpret_cast<float4*>(epi_tile);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            t4[lane * 8 + (j ^ (lane & 7))] =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          pool_items(p, pt, tile0, tc.n0 + cb, etid, 128);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(empty_leader0 + 8u * acc);
+        trace_at(p, tr && warp == kWarpEpi0 && it < 4, 10 + it);
+        continue;
+      }
       for (int cb = 0; cb < tc.bn; cb += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
@@ -914,7 +1043,39 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int64_t act_delta =
         (ACT && p.act) ? reinterpret_cast<const char*>(p.act) - reinterpret_cast<const char*>(p.C) : 0;
     const int total = nblk * rows_per * 8;
-    if (UNPOOL) {
+    if (POOL) {
+      // column blocks instead of row slices: pair q of the cluster finishes blocks q, q + S, ...
+      // for ALL 128 rows of its half (the S partials added in pair order, as below), parks the
+      // block in the epilogue tiles and pools it
+      const PoolTile pt = pool_tile(p, tc.m_pair * 2 + (int)rank);
+      uint8_t* tile0 = smem_raw + (tiles - smem_u32(smem_raw)) + kRingBytes;
+      for (int cbk = pair; cbk < nblk; cbk += S) {
+        for (int idx = t; idx < 128 * 8; idx += kThreads) {
+          const int chunk = idx & 7, row = idx >> 3;
+          const int rl = row & 31;
+          const uint32_t inner = (uint32_t)(rl * 8 + (chunk ^ (rl & 7))) * 16u;
+          const uint32_t off = (uint32_t)((row >> 5) * nblk + cbk) * 4096u + inner;
+          float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < S; ++q) {
+            const float4 v = ld_dsmem_f4(mapa(tiles + off, (uint32_t)(2 * q) + rank));
+            acc4.x += v.x;
+            acc4.y += v.y;
+            acc4.z += v.z;
+            acc4.w += v.w;
+          }
+          if (p.leaky) {
+            acc4.x = acc4.x > 0.f ? acc4.x : p.alpha * acc4.x;
+            acc4.y = acc4.y > 0.f ? acc4.y : p.alpha * acc4.y;
+            acc4.z = acc4.z > 0.f ? acc4.z : p.alpha * acc4.z;
+            acc4.w = acc4.w > 0.f ? acc4.w : p.alpha * acc4.w;
+          }
+          *reinterpret_cast<float4*>(tile0 + (row >> 5) * 4096 + inner) = acc4;
+        }
+        __syncthreads();
+        pool_items(p, pt, tile0, tc.n0 + cbk * 32, t, kThreads);
+        __syncthreads();
+      }
+    } else if (UNPOOL) {
       // three items per thread and pass: every global load (argmax, pool output) and every
       // distributed-shared-memory read of a pass is in flight before the first store
       constexpr int U = 3;
@@ -1589,6 +1750,17 @@ bool conv_tma2_supported(int mode, const IgemmParams& p) {
   return false;
 }
 
+// leaky_relu + 2x2 / stride-2 max-pool in the forward epilogue (launch_conv_tma2 with
+// IgemmParams::pool_y): whole pooling windows must fit a CTA's 128 rows
+bool conv_tma2_pool_supported(const IgemmParams& p) {
+  const sp_conv_geom& g = p.g;
+  if (!conv_tma2_supported(kFprop, p)) return false;
+  if (g.K % 32 != 0 || p.k_splits > 1) return false;
+  if (g.OH < 1 || g.OW < 1) return false;
+  if (g.OH * g.OW > 128 && g.OW > 64) return false;  // (two output rows per CTA tile at least)
+  return (int64_t)g.N * ((g.OH + 1) / 2) * ((g.OW + 1) / 2) * g.K < 0x7fffffffLL;
+}
+
 // How many clusters of `size` CTAs of the 2-SM kernel can be resident at once (one CTA per SM:
 // the stage ring takes the whole shared memory).  Queried once per size.
 int conv_tma2_max_clusters(int size) {
@@ -1704,6 +1876,28 @@ static int launch_conv_tma2_one(int mode, const IgemmParams& ip, cudaStream_t st
   p.leaky = (mode == kFprop) ? ip.leaky : 0;
   p.alpha = ip.leaky_alpha;
   p.act = (mode == kDgrad) ? ip.act : nullptr;
+  if (mode == kFprop && ip.pool_y) {
+    // pooled epilogue: CTA tiles cover whole pooling windows (see Tma2Params::pool_y)
+    const int hw = g.OH * g.OW;
+    p.pool_y = ip.pool_y;
+    p.pool_idx = ip.pool_idx;
+    p.pool_split = ip.pool_split;
+    p.POH = (g.OH + 1) / 2;
+    p.POW = (g.OW + 1) / 2;
+    p.n_img = g.N;
+    if (hw <= 128) {
+      p.pool_mode = 1;
+      p.pool_ipc = 128 / hw;
+      p.pool_cta_tiles = (g.N + p.pool_ipc - 1) / p.pool_ipc;
+    } else {
+      p.pool_mode = 2;
+      p.pool_R = (128 / g.OW) & ~1;
+      p.pool_tpi = (g.OH + p.pool_R - 1) / p.pool_R;
+      p.pool_cta_tiles = g.N * p.pool_tpi;
+    }
+    p.m_pairs = (p.pool_cta_tiles + 1) / 2;
+    p.total_tiles = p.m_pairs * p.n_tiles * p.splits;
+  }
   if (mode == kDgrad && ip.up_idx) {
     p.up_idx = ip.up_idx;
     p.up_y = ip.up_y;
@@ -1842,7 +2036,9 @@ static int launch_conv_tma2_one(int mode, const IgemmParams& ip, cudaStream_t st
       return set_error(SP_ERR_DRIVER, "conv_tma2: launch failed: %s",                           \
                        cudaGetErrorString(cudaGetLastError()));                                 \
   } while (0)
-  if (mode == kFprop)
+  if (mode == kFprop && p.pool_y)
+    SP_TMA2_LAUNCH(kFprop, 3);
+  else if (mode == kFprop)
     SP_TMA2_LAUNCH(kFprop, 0);
   else if (mode == kDgrad && p.up_idx)
     SP_TMA2_LAUNCH(kDgrad, 2);

@@ -42,6 +42,12 @@ struct IgemmParams {
   const uint8_t* up_idx;
   const float* up_y;
   int up_H, up_W;
+  // kFprop on the 2-SM TMA kernel: leaky_relu (leaky / leaky_alpha) and a 2x2 / stride-2 max-pool
+  // in the epilogue -- pooled tensor [N, ceil(OH/2), ceil(OW/2), K], uint8 argmax, optional
+  // SP_SPLIT_RL split in 32-channel blocks; C is not written (conv_tma2.cu)
+  float* pool_y;
+  uint8_t* pool_idx;
+  float* pool_split;
   // conv fprop with SP_PRECISION_TF32_SPLIT: operands are (r, l) TF32 split pairs interleaved
   // per 32 channels and g.C counts both parts (tf32.cu); only the 2-SM TMA kernel takes it
   int split3;
@@ -87,6 +93,7 @@ void igemm_umma_set_sync_mode(int mode);
 
 // 2-SM (cta_group::2) TMA-fed tcgen05 conv kernels, conv_tma2.cu: channel counts % 32 == 0
 bool conv_tma2_supported(int mode, const IgemmParams& p);
+bool conv_tma2_pool_supported(const IgemmParams& p);  // pooled forward epilogue (pool_y)
 int launch_conv_tma2(int mode, const IgemmParams& p, cudaStream_t stream);
 // clusters of `size` (2, 4 or 8) CTAs of that kernel that fit on the device at once
 int conv_tma2_max_clusters(int size);

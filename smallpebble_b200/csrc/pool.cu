@@ -154,7 +154,10 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_vec4_fixed(const float* 
 // Non-overlapping windows tile the padded image, so every in-range input pixel is written by
 // exactly one thread (no atomics, deterministic); windows beyond OH/OW (rows/columns that no
 // pooling window covers, VALID padding) are visited too and write zeros.
-template <int KH, int KW>
+// YSLOPE: `xl` is the POOL's OUTPUT (laid out like gy), not the full-resolution input: leaky's
+// slope at a window's argmax is the slope at the pooled value (leaky_relu is monotonic, alpha >
+// 0) -- for pools whose input was never stored (conv + leaky + pool ran as one kernel).
+template <int KH, int KW, bool YSLOPE = false>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_tile_vec4(const float* __restrict__ gy,
                                                                   const uint8_t* __restrict__ idx,
                                                                   float* __restrict__ dx,
@@ -177,6 +180,13 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_tile_vec4(const float* _
         const int64_t o = (((int64_t)n * g.OH + oy) * g.OW + ox) * C4 + c4;
         k = __ldg(reinterpret_cast<const uchar4*>(idx) + o);
         gv = ld_stream_f4(gy + 4 * o);
+        if (YSLOPE) {
+          const float4 yv = ld_stream_f4(xl + 4 * o);
+          gv.x *= slope(yv.x, g.alpha);
+          gv.y *= slope(yv.y, g.alpha);
+          gv.z *= slope(yv.z, g.alpha);
+          gv.w *= slope(yv.w, g.alpha);
+        }
       }
 #pragma unroll
       for (int dy = 0; dy < KH; ++dy) {
@@ -188,7 +198,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_tile_vec4(const float* _
             float4 out = make_float4(k.x == want ? gv.x : 0.f, k.y == want ? gv.y : 0.f,
                                      k.z == want ? gv.z : 0.f, k.w == want ? gv.w : 0.f);
             const int64_t off = ((int64_t)iy * g.W + ix) * g.C + 4 * c4;
-            if (g.leaky) {
+            if (g.leaky && !YSLOPE) {
               const float4 xv = ld_stream_f4(xl + (int64_t)n * g.H * g.W * g.C + off);
               out.x *= slope(xv.x, g.alpha);
               out.y *= slope(xv.y, g.alpha);
@@ -471,6 +481,27 @@ int sp_maxpool2d_bwd(const float* gy, const uint8_t* idx, float* dx, int N, int 
                      sp_stream_t stream) {
   return maxpool2d_bwd_impl(gy, idx, dx, nullptr, N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW,
                             0, 0.f, stream);
+}
+
+// sp_maxpool2d_leaky_bwd for a 2x2 / stride-2 pool whose INPUT was never stored (conv2d +
+// leaky_relu + pool ran as one kernel): leaky's slope is taken from the pool's OUTPUT y_pooled
+// (same sign as the input at the argmax for alpha > 0).  Bit-identical to the form above.
+int sp_maxpool2d_leaky_bwd_y(const float* gy, const uint8_t* idx, const float* y_pooled, float* dx,
+                             int N, int H, int W, int C, int KH, int KW, int sy, int sx, int pad_t,
+                             int pad_l, int OH, int OW, float alpha, sp_stream_t stream) {
+  if (!y_pooled) return sp::set_error(SP_ERR_INVALID_ARGUMENT, "sp_maxpool2d_leaky_bwd_y: null y");
+  const PoolGeom g{N, H, W, C, KH, KW, sy, sx, pad_t, pad_l, OH, OW, 1, alpha,
+                   sp::g_round_tf32_outputs, nullptr, 1, 1, 0};
+  if (int rc = check(g)) return rc;
+  if (!(KH == 2 && KW == 2 && sy == 2 && sx == 2 && C % 4 == 0 && alpha > 0.f && aligned16(gy) &&
+        aligned16(dx) && aligned16(y_pooled) && (reinterpret_cast<uintptr_t>(idx) & 3) == 0))
+    return sp::set_error(SP_ERR_UNSUPPORTED, "sp_maxpool2d_leaky_bwd_y: 2x2 / stride-2 pools, C % 4 == 0, alpha > 0");
+  if ((int64_t)N * H * W * C == 0) return 0;
+  const int VOH = (H + pad_t + 1) / 2, VOW = (W + pad_l + 1) / 2;
+  sp::launch_pdl(maxpool_bwd_tile_vec4<2, 2, true>, dim3(row_grid(N * VOH, VOW * (C / 4))),
+                 dim3(kThreads), 0, sp::as_stream(stream), gy, idx, dx, y_pooled, g, VOH, VOW);
+  SP_CHECK_LAUNCH("maxpool2d_leaky_bwd_y");
+  return 0;
 }
 
 int sp_maxpool2d_leaky_bwd(const float* gy, const uint8_t* idx, const float* x, float* dx, int N,

@@ -36,6 +36,7 @@ eager path for that call and re-records when the steps have settled again.
 
 from __future__ import annotations
 
+import gc
 import os
 
 import numpy as np
@@ -290,11 +291,21 @@ def _capture(pool, fn):
     graph = torch.cuda.CUDAGraph()
     launches0 = _abi.counter.launches
     A.forbid_uploads = True
+    # No garbage collection while the stream is capturing: a cycle collected in the middle of a
+    # recording may hold CUDA graphs, streams or pinned buffers of an EARLIER model (a previous
+    # root's recordings), and destroying those calls into the driver -- which invalidates the
+    # capture in progress ("operation not permitted when stream is capturing").  torch no longer
+    # collects before a capture by default, so do it here, then hold the collector off.
+    gc_was_on = gc.isenabled()
+    gc.collect()
+    gc.disable()
     try:
         with A.pool_bypass():
             with torch.cuda.graph(graph, pool=pool):
                 result = fn()
     except Exception as exc:  # noqa: BLE001 - anything that cannot be captured: stay eager
+        if gc_was_on:
+            gc.enable()
         A.forbid_uploads = False
         try:
             torch.cuda.synchronize()
@@ -303,6 +314,8 @@ def _capture(pool, fn):
         if os.environ.get("SP_STEADY_DEBUG") == "1":
             raise
         raise _Abort(str(exc)) from exc
+    if gc_was_on:
+        gc.enable()
     A.forbid_uploads = False
     return graph, result, _abi.counter.launches - launches0
 

@@ -605,6 +605,73 @@ def test_conv_data_gradient_scattered_through_the_pool_is_bit_identical(batch, i
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x1"])
+@pytest.mark.parametrize("batch,image,widths,pads", [
+    (128, 32, (32, 128, 128), ("VALID", "VALID", "VALID")),  # the README CNN: 13x13 -> 7x7, 5x5 -> 3x3
+    (16, 32, (32, 128, 128), ("VALID", "VALID", "VALID")),   # few tiles: every layer on split-K clusters
+    (40, 32, (32, 64, 256), ("SAME", "SAME", "SAME")),        # 16x16 -> 8x8 (two rows per tile), 256 filters
+    (24, 48, (32, 64, 64), ("SAME", "VALID", "SAME")),        # 22x22 -> 11x11, 11x11 -> 6x6
+])
+def test_tcgen05_conv_leaky_pool_in_one_kernel_is_bit_identical(batch, image, widths, pads, precision):
+    """conv2d -> leaky_relu -> maxpool2d(2, 2, stride 2) of a tensor-core layer as ONE kernel: the
+    2-SM tcgen05 kernel's CTA tiles are laid over whole pooling windows and its epilogue pools
+    (sp_conv2d_leaky_pool2_fwd; conv_tma2.cu EPI = 3).  Pooled values, argmax bytes, the (r, l)
+    split the next compensated conv consumes, every gradient -- including the input gradient,
+    whose pool backward takes leaky's slope from the pooled output -- and the full-resolution
+    tensor launched on demand equal the separate launches bit for bit."""
+    from smallpebble_b200 import _abi, core
+
+    rng = np.random.default_rng(batch + image)
+    x = rng.random((batch, image, image, 3)) - 0.5
+    ws, cin = [], 3
+    for wd in widths:
+        ws.append((rng.random((3, 3, cin, wd)) - 0.5) * 2.0 / np.sqrt(9 * cin))
+        cin = wd
+    sp.set_precision(precision)
+    calls = []
+    orig = _abi.f.sp_conv2d_leaky_pool2_fwd
+
+    def spy(*args):
+        calls.append(args[5].C if hasattr(args[5], "C") else 0)
+        return orig(*args)
+
+    def run(read_full):
+        xv = sp.Variable(x)
+        wv = [sp.learnable(sp.Variable(w)) for w in ws]
+        h, convs, pools = xv, [], []
+        for w, pad in zip(wv, pads):
+            h = sp.conv2d(h, w, pad)
+            convs.append(h)
+            h = sp.maxpool2d(sp.leaky_relu(h, 0.1), 2, 2, strides=[2, 2])
+            pools.append(h)
+        gy = np.random.default_rng(5).random(h.shape) - 0.5
+        g = sp.get_gradients(sp.mul(h, sp.Variable(gy)))
+        res = [np.asarray(p.array) for p in pools] + [np.asarray(p._argmax) for p in pools]
+        res += [np.asarray(g[w]) for w in wv] + [np.asarray(g[xv])]
+        if read_full:
+            res += [np.asarray(c.array) for c in convs]  # launched on demand
+        return res
+
+    _abi.f.sp_conv2d_leaky_pool2_fwd = spy
+    try:
+        core._fuse_conv_pool = True
+        run(False)                       # (first pass: the consumers' split hints get known)
+        del calls[:]
+        fused = run(True)
+        n_fused = len(calls)
+        core._fuse_conv_pool = False
+        plain = run(True)
+    finally:
+        _abi.f.sp_conv2d_leaky_pool2_fwd = orig
+        core._fuse_conv_pool = True
+        sp.set_precision("tf32")
+    assert len(calls) == n_fused and n_fused >= 1, calls
+    if batch >= 24:  # (below that the layers are too small for the 2-SM kernel's policy)
+        assert n_fused >= 2 and any(c >= 32 for c in calls), calls  # tensor-core layers too
+    for i, (a, b) in enumerate(zip(fused, plain)):
+        assert np.array_equal(a, b), i
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x1"])
 @pytest.mark.parametrize("shape,k,padding", [((16, 32, 32, 3), 32, "SAME"), ((5, 14, 18, 3), 16, "VALID"),
                                              ((3, 40, 36, 3), 32, "SAME"), ((2, 10, 10, 3), 64, "VALID")])
 def test_first_layer_conv_leaky_pool_in_one_kernel_is_bit_identical(shape, k, padding, precision):
