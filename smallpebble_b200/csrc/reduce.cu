@@ -106,6 +106,53 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restric
   }
 }
 
+// A SMALL matrix (a hidden layer's [200, 100] gradient -> its bias gradient): with the block
+// shape below that is ONE block whose 8 row-lanes walk 25 rows each, six dependent round trips
+// (5.3 us in the README MLP's backward pass).  Here a block is 8 column-quads x 32 row-lanes:
+// four blocks, every thread's loads (<= 8 per pass) in flight together, then the 32 lanes of a
+// quad added in lane order through shared memory (fixed order: deterministic).
+__global__ void __launch_bounds__(kThreads) colsum_small_vec4_kernel(const float* __restrict__ x,
+                                                                     float* __restrict__ out,
+                                                                     int reduce, int inner) {
+  pdl_entry();
+  __shared__ float4 tile[32][9];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int inner4 = inner >> 2;
+  const int col4 = (int)blockIdx.x * 8 + tx;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col4 < inner4) {
+    const float* p = x + 4 * col4;
+    for (int r0 = ty; r0 < reduce; r0 += 256) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + 32 * u;
+        v[u] = r < reduce ? ld_stream_f4(p + (int64_t)r * inner) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc.x += v[u].x;
+        acc.y += v[u].y;
+        acc.z += v[u].z;
+        acc.w += v[u].w;
+      }
+    }
+  }
+  tile[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col4 < inner4) {
+    float4 s = tile[0][tx];
+#pragma unroll
+    for (int k = 1; k < 32; ++k) {
+      s.x += tile[k][tx].x;
+      s.y += tile[k][tx].y;
+      s.z += tile[k][tx].z;
+      s.w += tile[k][tx].w;
+    }
+    reinterpret_cast<float4*>(out)[col4] = s;
+  }
+}
+
 // inner % 4 == 0, 16-byte aligned: each thread sums 4 adjacent columns with 128-bit loads,
 // 4 independent row streams in flight.  Block = 32 column-quads x 8 row-lanes.
 __global__ void __launch_bounds__(kThreads) colsum_vec4_kernel(const float* __restrict__ x,
@@ -483,6 +530,12 @@ int reduce_sum_impl(const float* x, float* out, int64_t outer, int64_t reduce, i
   } else {
     const bool vec = (inner % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec && outer == 1 && inner <= 512 && reduce >= 64 && reduce <= 4096 &&
+        reduce * inner < (1 << 16)) {
+      sp::launch_pdl(colsum_small_vec4_kernel, dim3((unsigned)((inner / 4 + 7) / 8)), dim3(kThreads), 0,
+                     st, x, out, (int)reduce, (int)inner);
+      return 0;
+    }
     const int64_t col_blocks = vec ? (inner / 4 + 31) / 32 : (inner + 31) / 32;
     int splits = 1;
     // tiny inputs (a [128, 10] bias gradient) are one block's work: no second pass
