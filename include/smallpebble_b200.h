@@ -117,6 +117,10 @@ int sp_event_synchronize(void* event);
 int sp_copy_publish(const void* src, void* dst, size_t bytes, void* host_slot, unsigned int seq,
                     sp_stream_t stream);
 int sp_memcpy_d2d(void* dst, const void* src, size_t bytes, sp_stream_t stream);
+/* several device-to-device copies of 4-byte-word arrays in one kernel launch (the inputs of a
+ * replayed training step into its static buffers); n_tensors <= 24 */
+int sp_copy_multi(int n_tensors, const void* const* src, void* const* dst, const int64_t* words,
+                  sp_stream_t stream);
 int sp_fill_f32(float* dst, int64_t n, float value, sp_stream_t stream);
 /* ... or narrowed on HOST cores while the copy is in flight, so that half the bytes cross PCIe
  * (csrc/host_pipe.cu: a small persistent worker pool converts 4096-element sub-chunks into the

@@ -143,6 +143,7 @@ SIGNATURES = {
     "sp_nccl_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "sp_allreduce_sum_f32": (C.c_int, [vp, vp, i64, vp]),
     "sp_nccl_destroy": (C.c_int, [vp]),
+    "sp_copy_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), p_i64, vp]),
     "sp_pack_multi": (C.c_int, [C.c_int, C.POINTER(vp), p_i64, p_i64, vp, vp]),
 }
 

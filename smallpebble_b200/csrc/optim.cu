@@ -369,6 +369,25 @@ __global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_const
   for (int64_t i = base + threadIdx.x; i < end; i += kThreads) dst[i] = src[i];
 }
 
+// dst[t][i] = src[t][i] for several arrays of 4-byte words in one launch (launch_pdl: the copy's
+// launch overlaps the tail of whatever runs before it)
+__global__ void __launch_bounds__(kThreads) copy_multi_kernel(const __grid_constant__ AxpyArgs a) {
+  pdl_entry();
+  const int t = find_tensor(a, blockIdx.x);
+  const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * kChunk;
+  const int64_t end = min(a.n[t], base + kChunk);
+  float* __restrict__ dst = a.p[t];
+  const float* __restrict__ src = a.g[t];
+  if (a.dst_offset[t]) {  // both 16-byte aligned: 128-bit copies
+    const int64_t b4 = base >> 2, e4 = end >> 2;
+    for (int64_t i = b4 + threadIdx.x; i < e4; i += kThreads)
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    for (int64_t i = (e4 << 2) + threadIdx.x; i < end; i += kThreads) dst[i] = src[i];
+  } else {
+    for (int64_t i = base + threadIdx.x; i < end; i += kThreads) dst[i] = src[i];
+  }
+}
+
 inline int blocks_for(int64_t n) { return (int)((n + kChunk - 1) / kChunk); }
 
 // arrival counters: words [0, kMaxTensors) of the library's zero-initialised sync words
@@ -653,6 +672,34 @@ int sp_sgd_multi(int n_tensors, float* const* host_p, const float* const* host_g
     sp::launch_pdl(sgd_multi_kernel, dim3(blocks), dim3(kThreads), 0, st, a, lr);
     SP_CHECK_LAUNCH("sgd_multi");
   }
+  return 0;
+}
+
+// Several device-to-device copies of 4-byte-word arrays (fp32 / int32) in ONE kernel launch:
+// the inputs of a replayed step go into its static buffers this way (two cudaMemcpyAsync nodes
+// cost ~3 us of copy-engine latency each on a 150 us step).  n_tensors <= 24.
+int sp_copy_multi(int n_tensors, const void* const* host_src, void* const* host_dst,
+                  const int64_t* host_words, sp_stream_t stream) {
+  SP_REQUIRE(n_tensors >= 0 && n_tensors <= kMaxTensors, "sp_copy_multi: at most 24 arrays");
+  AxpyArgs a;
+  a.count = 0;
+  int blocks = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    const int64_t n = host_words[i];
+    if (n <= 0) continue;
+    SP_REQUIRE(host_src[i] && host_dst[i], "sp_copy_multi: null pointer");
+    const int k = a.count++;
+    a.p[k] = static_cast<float*>(host_dst[i]);
+    a.g[k] = static_cast<const float*>(host_src[i]);
+    a.n[k] = n;
+    a.dst_offset[k] = ((reinterpret_cast<uintptr_t>(host_dst[i]) | reinterpret_cast<uintptr_t>(host_src[i])) & 15) == 0;
+    a.block_start[k] = blocks;
+    blocks += blocks_for(n);
+  }
+  if (a.count == 0) return 0;
+  a.block_start[a.count] = blocks;
+  sp::launch_pdl(copy_multi_kernel, dim3(blocks), dim3(kThreads), 0, sp::as_stream(stream), a);
+  SP_CHECK_LAUNCH("copy_multi");
   return 0;
 }
 

@@ -36,6 +36,7 @@ eager path for that call and re-records when the steps have settled again.
 
 from __future__ import annotations
 
+import ctypes as C
 import gc
 import os
 
@@ -408,8 +409,19 @@ def _replay_forward(rec):
     from .core import Variable
 
     user_values = [ph.arguments[0] for ph in rec.placeholders]
+    resident = []
     for dst, v in zip(rec.static_inputs, user_values):
-        _feed(dst, v)
+        src = v._array if isinstance(v, Variable) else v
+        if (type(src) is DeviceArray and src._ptr is not None and src.dtype.itemsize == 4
+                and src.dtype == dst.dtype and src.shape == dst.shape):
+            resident.append((dst, src))  # already on the device: copied below, all in one launch
+        else:
+            _feed(dst, v)
+    if resident:
+        n = len(resident)
+        F.sp_copy_multi(n, (C.c_void_p * n)(*[s_._ptr for _, s_ in resident]),
+                        (C.c_void_p * n)(*[d._ptr for d, _ in resident]),
+                        _abi.dims([d.size for d, _ in resident]), A.stream())
     for arr, thunk, tag_ in rec.pending_f:
         if arr._thunk is None:  # materialised after an earlier replay: pending again
             arr._buf = arr._ptr = None
