@@ -249,7 +249,16 @@ def algorithmic_work(name, args):
         # writes the pooled tensor, its uint8 argmax and (when asked) the (r, l) split
         g = args[5]
         g = g.contents if hasattr(g, "contents") else g
-        pooled = g.N * (g.OH // 2) * (g.OW // 2) * g.K
+        if g.C > 4:
+            # a tensor-core layer: the pool runs in the tcgen05 epilogue; ALGORITHMIC flops of
+            # one product over the real channels (split operands carry 2C and three passes)
+            channels, extra = g.C, ""
+            if args[6] == _abi.PRECISION_TF32_SPLIT:
+                channels, extra = g.C // 2, " (3xTF32: three tensor passes issued)"
+            flops = 2.0 * g.N * g.OH * g.OW * g.K * g.KH * g.KW * channels
+            return "tensor", flops, (f"conv2d+leaky_relu+maxpool2d N={g.N} HxW={g.H}x{g.W} C={g.C} "
+                                     f"K={g.K} k={g.KH}x{g.KW} pool 2x2/2 in the epilogue{extra}")
+        pooled = g.N * ((g.OH + 1) // 2) * ((g.OW + 1) // 2) * g.K
         nbytes = 4.0 * (g.N * g.H * g.W * g.C + g.KH * g.KW * g.C * g.K) + pooled * (5.0 + (8.0 if args[4] else 0.0))
         return "hbm", nbytes, (f"conv2d+leaky_relu+maxpool2d N={g.N} HxW={g.H}x{g.W} C={g.C} K={g.K} "
                                f"k={g.KH}x{g.KW} pool 2x2/2 (first layer, one kernel)")
