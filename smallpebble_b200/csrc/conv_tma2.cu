@@ -533,10 +533,11 @@ __device__ __forceinline__ PoolTile pool_tile(const Tma2Params& p, int ct) {
   return t;
 }
 __device__ __forceinline__ void pool_take(float v, int k, float& best, int& bi) {
-  if (v > best || (v != v && best == best)) {  // first maximum wins, NaN wins (pool.cu: take)
-    best = v;
-    bi = k;
-  }
+  // first maximum wins, NaN wins (pool.cu: take): v > best, or v is NaN and best is not --
+  // i.e. NOT (v <= best) while best is a number; as selects, not branches
+  const bool t = !(v <= best) && best == best;
+  best = t ? v : best;
+  bi = t ? k : bi;
 }
 // One 32-channel column block of a CTA tile sits in shared memory as four XOR-swizzled 32-row
 // tiles (row l: tile l / 32, 16-byte chunk c at ((l % 32) * 8 + (c ^ (l & 7)))), leaky_relu
@@ -584,6 +585,96 @@ __device__ __forceinline__ void pool_items(const Tma2Params& p, const PoolTile& 
       const float4 r = make_float4(rna_tf32(best.x), rna_tf32(best.y), rna_tf32(best.z), rna_tf32(best.w));
       // SP_SPLIT_RL in 32-channel blocks: [pixel][block][r (32) | l (32)]
       float* d = p.pool_split + (gp * (p.N >> 5) + (col >> 5)) * 64 + (col & 31);
+      *reinterpret_cast<float4*>(d) = r;
+      *reinterpret_cast<float4*>(d + 32) = make_float4(best.x - r.x, best.y - r.y, best.z - r.z, best.w - r.w);
+    }
+  }
+}
+
+// The same work with everything that does not depend on the column block computed ONCE per
+// tile: which (pooled pixel, chunk) items a thread owns, where their four window values sit in
+// the parked block (16-byte slot index; 0xffff = outside the image: a zero competes) and where
+// the results go.  In-kernel stamps (scripts/pool_trace.py) put pool_items() at ~2300 cycles per
+// column block on the README CNN's second layer -- ~320 instructions per item issued by ONE
+// warp per scheduler -- against ~950 for the whole plain epilogue of a block.
+constexpr int kPoolPlan = 4;  // items per thread the plan holds; larger tiles take pool_items()
+struct PoolPlan {
+  uint32_t w01[kPoolPlan], w23[kPoolPlan];  // slot indices of window values 0|1 and 2|3
+  int o[kPoolPlan];                         // pooled element offset of the item at column 0
+  int count;
+};
+__device__ __forceinline__ bool pool_plan(const Tma2Params& p, const PoolTile& pt, int tid,
+                                          int nthreads, PoolPlan& pl) {
+  const int prows = (pt.rows + 1) >> 1;
+  const int items = pt.imgs * prows * p.POW * 8;
+  const int img_px = pt.rows * p.D2;
+  pl.count = 0;
+  if (items > kPoolPlan * nthreads) return false;
+#pragma unroll
+  for (int q = 0; q < kPoolPlan; ++q) {
+    const int it = tid + q * nthreads;
+    pl.w01[q] = pl.w23[q] = 0xffffffffu;
+    pl.o[q] = 0;
+    if (it < items) {
+      pl.count = q + 1;
+      const int chunk = it & 7;
+      int pp = it >> 3;
+      const int px = pp % p.POW;
+      pp /= p.POW;
+      const int pyl = pp % prows, il = pp / prows;
+      uint32_t slot[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int oyl = 2 * pyl + (k >> 1), ox = 2 * px + (k & 1);
+        const int l = il * img_px + oyl * p.D2 + ox;
+        const int rl = l & 31;
+        const bool in = oyl < pt.rows && ox < p.D2;
+        slot[k] = in ? (uint32_t)((l >> 5) * 256 + rl * 8 + (chunk ^ (rl & 7))) : 0xffffu;
+      }
+      pl.w01[q] = slot[0] | (slot[1] << 16);
+      pl.w23[q] = slot[2] | (slot[3] << 16);
+      const int gp = ((pt.img0 + il) * p.POH + (pt.oy0 >> 1) + pyl) * p.POW + px;
+      pl.o[q] = gp * p.N + chunk * 4;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ float4 pool_slot(const float4* t4, uint32_t slot) {
+  const float4 v = t4[slot & 1023u];  // (always a legal address; discarded when out of the image)
+  const bool in = slot != 0xffffu;
+  return make_float4(in ? v.x : 0.f, in ? v.y : 0.f, in ? v.z : 0.f, in ? v.w : 0.f);
+}
+__device__ __forceinline__ void pool_apply(const Tma2Params& p, const PoolPlan& pl,
+                                           const uint8_t* tile0, int col0) {
+  const float4* t4 = reinterpret_cast<const float4*>(tile0);
+#pragma unroll
+  for (int q = 0; q < kPoolPlan; ++q) {
+    if (q >= pl.count) break;
+    const float4 w0 = pool_slot(t4, pl.w01[q] & 0xffffu), w1 = pool_slot(t4, pl.w01[q] >> 16);
+    const float4 w2 = pool_slot(t4, pl.w23[q] & 0xffffu), w3 = pool_slot(t4, pl.w23[q] >> 16);
+    float4 best = w0;
+    int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    pool_take(w1.x, 1, best.x, b0);
+    pool_take(w1.y, 1, best.y, b1);
+    pool_take(w1.z, 1, best.z, b2);
+    pool_take(w1.w, 1, best.w, b3);
+    pool_take(w2.x, 2, best.x, b0);
+    pool_take(w2.y, 2, best.y, b1);
+    pool_take(w2.z, 2, best.z, b2);
+    pool_take(w2.w, 2, best.w, b3);
+    pool_take(w3.x, 3, best.x, b0);
+    pool_take(w3.y, 3, best.y, b1);
+    pool_take(w3.z, 3, best.z, b2);
+    pool_take(w3.w, 3, best.w, b3);
+    const int64_t o = (int64_t)pl.o[q] + col0;
+    *reinterpret_cast<float4*>(p.pool_y + o) = best;
+    *reinterpret_cast<uint32_t*>(p.pool_idx + o) =
+        (uint32_t)b0 | ((uint32_t)b1 << 8) | ((uint32_t)b2 << 16) | ((uint32_t)b3 << 24);
+    if (p.pool_split) {
+      const float4 r = make_float4(rna_tf32(best.x), rna_tf32(best.y), rna_tf32(best.z), rna_tf32(best.w));
+      // [pixel][32-channel block][r (32) | l (32)]: element e of the pooled tensor sits at
+      // 2 * (e - e % 32) + e % 32, col0 is a multiple of 32
+      float* d = p.pool_split + 2 * (o - (pl.o[q] & 31)) + (pl.o[q] & 31);
       *reinterpret_cast<float4*>(d) = r;
       *reinterpret_cast<float4*>(d + 32) = make_float4(best.x - r.x, best.y - r.y, best.z - r.z, best.w - r.w);
     }
@@ -973,10 +1064,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         const PoolTile pt = pool_tile(p, tc.m_pair * 2 + (int)rank);
         const uint8_t* tile0 = smem_raw + (tiles - smem_u32(smem_raw)) + kRingBytes;
         const int etid = (warp - kWarpEpi0) * 32 + lane;
+        PoolPlan plan;
+        const bool planned = pool_plan(p, pt, etid, 128, plan);
         for (int cb = 0; cb < tc.bn; cb += 32) {
           uint32_t v[32];
+          const bool trf = tr && warp == kWarpEpi0 && it == 0 && cb < 64;
+          const int tb = 450 + (cb >> 5) * 6;
+          trace_at(p, trf, tb);
           tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
           tmem_ld_wait();
+          trace_at(p, trf, tb + 1);
           if (p.leaky) leaky_block(v, p.alpha);
           float4* t4 = reinterpret_cast<float4*>(epi_tile);
 #pragma unroll
@@ -984,9 +1081,16 @@ __global__ void __launch_bounds__(kThreads, 1)
             t4[lane * 8 + (j ^ (lane & 7))] =
                 make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          trace_at(p, trf, tb + 2);
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          pool_items(p, pt, tile0, tc.n0 + cb, etid, 128);
+          trace_at(p, trf, tb + 3);
+          if (planned)
+            pool_apply(p, plan, tile0, tc.n0 + cb);
+          else
+            pool_items(p, pt, tile0, tc.n0 + cb, etid, 128);
+          trace_at(p, trf, tb + 4);
           asm volatile("bar.sync 1, 128;" ::: "memory");
+          trace_at(p, trf, tb + 5);
         }
         tc_fence_before();
         __syncwarp();
@@ -1049,6 +1153,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       // block in the epilogue tiles and pools it
       const PoolTile pt = pool_tile(p, tc.m_pair * 2 + (int)rank);
       uint8_t* tile0 = smem_raw + (tiles - smem_u32(smem_raw)) + kRingBytes;
+      PoolPlan plan;
+      const bool planned = pool_plan(p, pt, t, kThreads, plan);
       for (int cbk = pair; cbk < nblk; cbk += S) {
         for (int idx = t; idx < 128 * 8; idx += kThreads) {
           const int chunk = idx & 7, row = idx >> 3;
@@ -1072,7 +1178,10 @@ __global__ void __launch_bounds__(kThreads, 1)
           *reinterpret_cast<float4*>(tile0 + (row >> 5) * 4096 + inner) = acc4;
         }
         __syncthreads();
-        pool_items(p, pt, tile0, tc.n0 + cbk * 32, t, kThreads);
+        if (planned)
+          pool_apply(p, plan, tile0, tc.n0 + cbk * 32);
+        else
+          pool_items(p, pt, tile0, tc.n0 + cbk * 32, t, kThreads);
         __syncthreads();
       }
     } else if (UNPOOL) {
