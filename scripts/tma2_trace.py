@@ -3,7 +3,9 @@ stamps written through sp_debug_tma2_trace.  Slots (int64):
   0 kernel entry | 1 setup done (barriers, TMEM, cluster sync) | 2..5 MMA issuer: all MMAs of
   tile i issued | 6..9 epilogue: accumulator i ready | 10..13 epilogue: tile i stored |
   14 teardown done | 16+k A producer issues k-block k | 16+96+k B producer | 16+192+k MMA
-  issuer sees k-block k landed.
+  issuer sees k-block k landed | 450+6b .. 455+6b (b = 0, 1): pooled epilogue (EPI = 3) of the
+  first tile, column block b: start, TMEM loaded, parked, barrier 1, pooled, barrier 2
+  (scripts/pool_trace.py).
 
     python scripts/tma2_trace.py [case ...]
 """
